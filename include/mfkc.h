@@ -1,0 +1,223 @@
+/*
+ * mfkc.h -- C ABI of libmfkc: the B200-native (sm_100a) k-mer counting hot path
+ * of MetaFast (kmer-counter-many -> .kmers.bin / .stat.txt -> features-calculator).
+ *
+ * Plain C: opaque handles, pointers and sizes only; no callbacks, no structs by
+ * value, no C++ exceptions across the boundary.  Callable from Panama FFM
+ * (Linker.downcallHandle), JNI, ctypes or C++ alike (INTEGRATION.md shows the
+ * Java binding a MetaFast maintainer would add).
+ *
+ * Every entry point names the reference interface it replaces.  Prefixes:
+ *   src/    = ctlab/metafast  src/
+ *   [itmo]/ = lib/itmo-assembler-src.jar!/ru/ifmo/genetics/
+ *
+ * Conventions
+ *   - return 0 (MFKC_OK) or a negative MFKC_E_* code; text via mfkc_last_error().
+ *   - the caller owns every buffer it passes; the library owns device memory
+ *     and the pinned buffers it handed out.
+ *   - a context is driven by one host thread at a time; several contexts may
+ *     coexist (one per GPU / per sample stream).
+ *   - there is NO CPU fallback: without a CUDA device mfkc_create fails with
+ *     MFKC_E_CUDA.
+ */
+#ifndef MFKC_H
+#define MFKC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFKC_ABI_VERSION 1
+
+enum {
+    MFKC_OK = 0,
+    MFKC_E_BADARG = -1,     /* IllegalArgumentException / System.exit(1) paths of the tools */
+    MFKC_E_CUDA = -2,
+    MFKC_E_NCCL = -3,
+    MFKC_E_TABLE_FULL = -4, /* table cannot grow any further (device memory exhausted) */
+    MFKC_E_OOM = -5,
+    MFKC_E_STATE = -6,      /* call sequence violated (e.g. emit_next before emit_begin) */
+    MFKC_E_IO = -7,         /* file cannot be opened / read / written */
+    MFKC_E_FORMAT = -8      /* malformed FASTA/FASTQ/.kmers.bin/components.bin, bad nucleotide */
+};
+
+enum { MFKC_VARIANT_HASH = 0, MFKC_VARIANT_SORT = 1 };
+
+#define MFKC_MAX_COUNT 32767        /* Short.MAX_VALUE: [itmo]/utils/NumUtils.java:21-26 */
+#define MFKC_HIST_BINS 32768        /* histogram index = count, 1..32767 */
+
+typedef struct mfkc_ctx mfkc_ctx;
+
+/* Configuration; zero-initialise, set struct_size = sizeof(mfkc_cfg). */
+typedef struct mfkc_cfg {
+    uint32_t struct_size;
+    int32_t  k;                 /* 1..31: 64-bit keys (reference range, src/tools/KmersCounterMain.java:66-73);
+                                   32..63: 128-bit keys (extension, no reference behaviour) */
+    int32_t  min_seq_len;       /* minSeqLen of IOUtils.loadReads (src/io/IOUtils.java:761); 0 for the counter */
+    int32_t  device;            /* CUDA device ordinal */
+    int32_t  variant;           /* MFKC_VARIANT_HASH | MFKC_VARIANT_SORT */
+    int32_t  n_shards;          /* hash-range sharding: number of key-space shards (GPUs); 0/1 = unsharded */
+    int32_t  shard_id;          /* the shard this context owns */
+    int32_t  reserved0;
+    uint64_t table_slots;       /* initial table capacity in slots; 0 = derive from expected_distinct / default */
+    uint64_t expected_distinct; /* sizing hint (distinct k-mers); 0 = unknown, table grows x2 on demand */
+    uint64_t max_table_bytes;   /* growth limit; 0 = 80 % of free device memory */
+    uint64_t reserved1[4];
+} mfkc_cfg;
+
+/* ---- lifecycle ------------------------------------------------------------------------
+ * Replaces `new BigLong2ShortHashMap(..)` + the ReadsLoadWorker pool set-up in
+ * IOUtils.loadReads (src/io/IOUtils.java:772-781). */
+int  mfkc_abi_version(void);
+int  mfkc_device_count(void);                      /* 0 when no CUDA device / driver */
+int  mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out);
+void mfkc_destroy(mfkc_ctx *ctx);
+const char *mfkc_last_error(const mfkc_ctx *ctx);  /* ctx may be NULL: last create() failure */
+int  mfkc_reset(mfkc_ctx *ctx);                    /* next sample: empty table, keep allocations */
+
+/* Pinned host buffers for the Java side to wrap as direct ByteBuffer / MemorySegment. */
+int  mfkc_pinned_alloc(mfkc_ctx *ctx, size_t bytes, void **host_ptr);
+int  mfkc_pinned_free(mfkc_ctx *ctx, void *host_ptr);
+
+/* ---- ingest: replaces ReadsWorker.process(List<Dna>) (src/io/ReadsWorker.java:25,
+ * src/io/IOUtils.java:756-769) fed by ReadsDispatcher.getWorkRange
+ * (src/io/ReadsDispatcher.java:34-53) --------------------------------------------------
+ * bases   = ASCII nucleotides (AaCcGgTt only) of reads that already passed the parser
+ *           rules (N-drop, phred-0 drop: mfkc_reader_* below does that);
+ * offsets = n_reads+1 byte offsets into `bases` (read i = bases[offsets[i]..offsets[i+1])).
+ * Host-buffer version: copies asynchronously, returns once `bases`/`offsets` may be
+ * refilled; counting continues in the background (double-buffered).
+ * Any batch size is accepted (the reference uses 32768 reads, src/io/IOUtils.java:29). */
+int  mfkc_submit_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads);
+/* Same, for inputs already resident in device memory (no copy; used for kernel-only timing). */
+int  mfkc_submit_reads_device(mfkc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets,
+                              uint32_t n_reads, uint64_t n_bases);
+/* All submitted work is counted when this returns (latch.await(), src/io/IOUtils.java:853). */
+int  mfkc_flush(mfkc_ctx *ctx);
+
+/* ---- results: replaces IOUtils.printKmers (src/io/IOUtils.java:45-71) and the statistics
+ * of loadReads (src/io/IOUtils.java:783-800) --------------------------------------------
+ * stats[0] = distinct k-mers (hm.size()), [1] = k-mer instances counted,
+ * [2] = totalSeq, [3] = goodSeq, [4] = totalLen, [5] = goodLen. */
+int  mfkc_stats(mfkc_ctx *ctx, uint64_t stats[6]);
+/* hist[c] = number of distinct k-mers with (saturated) count c, ALL entries
+ * (QuickQuantitativeStatistics, src/io/IOUtils.java:59). */
+int  mfkc_histogram(mfkc_ctx *ctx, uint64_t hist[MFKC_HIST_BINS]);
+/* Select entries with count > threshold (src/io/IOUtils.java:61), order them by ascending key;
+ * *n_good = how many.  Also (re)computes the histogram. */
+int  mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_good);
+/* Next chunk of big-endian records (int64 key + int16 count = 10 bytes for k<=31; 16+2 bytes
+ * for k>=32), a whole number of records; *written = 0 at the end. */
+int  mfkc_emit_next(mfkc_ctx *ctx, uint8_t *out, size_t cap, size_t *written);
+/* Device-resident result (for on-device consumers / kernel-only timing): pointers stay valid
+ * until the next submit/reset/emit_begin.  keys ascending; counts saturated. */
+int  mfkc_emit_device(mfkc_ctx *ctx, const uint64_t **d_keys, const uint16_t **d_counts, uint64_t *n);
+
+/* ---- hash-range sharding across GPUs (one context per GPU; exchange by the caller with
+ * NCCL all-to-all, see metafast_b200/sharded.py) -- no reference analogue --
+ * Extract canonical k-mers of a batch and bucket them by owner shard
+ * owner(key) = mix(key) mod n_shards.  d_keys_out (device, capacity cap_keys) receives the
+ * keys grouped by shard; bucket_counts[n_shards] (host) the size of each group.  */
+int  mfkc_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets,
+                           uint32_t n_reads, uint64_t n_bases,
+                           uint64_t *d_keys_out, uint64_t cap_keys, uint64_t *bucket_counts);
+/* Count n keys (device pointer) into this context's table -- the receive side of the exchange. */
+int  mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uint64_t n);
+/* owner shard of a key (host helper, identical to the device function). */
+uint32_t mfkc_owner_shard(uint64_t key, uint32_t n_shards);
+
+/* ---- features-calculator: replaces the BigLong2LongHashMap set-up
+ * (src/tools/FeaturesCalculatorMain.java:97-103), IOUtils.calculatePresenceForKmers /
+ * ...ForReads (src/io/IOUtils.java:577-597, 806-834) and buildAndPrintVector
+ * (src/tools/FeaturesCalculatorMain.java:169-236) -------------------------------------- */
+/* keys = all component k-mers, component c = keys[comp_offsets[c]..comp_offsets[c+1]). */
+int  mfkc_fc_load_components(mfkc_ctx *ctx, const int64_t *keys, const uint64_t *comp_offsets, uint32_t n_comp);
+/* --selected: records of the selected .kmers.bin files (loadKmers with threshold 0,
+ * src/io/IOUtils.java:237-258,369-401).  records = NULL switches the filter off; a non-NULL
+ * pointer with n_records = 0 is an (empty) active filter, as an empty --selected file is in the
+ * reference.  May be called repeatedly to append. */
+int  mfkc_fc_set_selected(mfkc_ctx *ctx, const uint8_t *be_records, uint64_t n_records);
+int  mfkc_fc_reset_values(mfkc_ctx *ctx);          /* hm.resetValues(), FeaturesCalculatorMain.java:122,151 */
+/* 10-byte BE records in any chunking (the reference reads 16 777 200-byte chunks, IOUtils.java:30). */
+int  mfkc_fc_add_records(mfkc_ctx *ctx, const uint8_t *be_records, uint64_t n_records);
+/* reads mode (-i): same arguments as mfkc_submit_reads; no minSeqLen on this path. */
+int  mfkc_fc_add_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads);
+/* per component: vec = sum of values > threshold, found = how many such, cnt = keys considered.
+ * breadth = (double)found / cnt is left to the host (Java formatting). */
+int  mfkc_fc_features(mfkc_ctx *ctx, int64_t threshold, int64_t *vec, uint64_t *found, uint64_t *cnt);
+
+/* ---- host side of the path (CPU; no GPU needed): the parser rules of
+ * [itmo]/io/ReadersUtils.java:27-102, readers/FastaReader.java:54-108,
+ * readers/FastqReader.java:53-114, readers/FastaReaderFromXQSource.java:62-85 and the
+ * naming rules of src/tools/KmersCounterForManyFilesMain.java:73-108,
+ * src/tools/KmersCounterMain.java:122-137 ---------------------------------------------- */
+typedef struct mfkc_reader mfkc_reader;
+int  mfkc_reader_open(const char *path, mfkc_reader **out, char *err, size_t err_cap);
+/* Fill `bases` (cap_bases bytes) and `offsets` (cap_reads+1 entries) with the next kept reads;
+ * *n_reads = 0 at end of file.  A read longer than cap_bases is an MFKC_E_BADARG. */
+int  mfkc_reader_next(mfkc_reader *r, uint8_t *bases, size_t cap_bases, uint64_t *offsets,
+                      uint32_t cap_reads, uint32_t *n_reads);
+/* counters: [0] = records seen, [1] = records dropped (N / phred 0) */
+int  mfkc_reader_counters(const mfkc_reader *r, uint64_t counters[2]);
+const char *mfkc_reader_error(const mfkc_reader *r);
+const char *mfkc_reader_name(const mfkc_reader *r);   /* NamedSource.name() */
+void mfkc_reader_close(mfkc_reader *r);
+
+/* .stat.txt text of QuickQuantitativeStatistics.printToFile (header of IOUtils.java:69). */
+int  mfkc_write_stat_file(const char *path, const uint64_t hist[MFKC_HIST_BINS]);
+
+/* ---- synthetic Illumina-like reads (bench / tests).  Deterministic
+ * in (seed, sample, read index): host and device generators agree byte for byte. ---------- */
+typedef struct mfkc_synth_cfg {
+    uint32_t struct_size;
+    uint32_t n_genomes;        /* default 64 */
+    uint64_t seed;             /* default 0x4D464B43 */
+    uint64_t total_genome_bp;  /* default 150 000 000 */
+    uint32_t read_len;         /* default 150 */
+    uint32_t sample;           /* abundance vector id */
+    uint32_t err_ppm_first;    /* substitution rate at read start, ppm (default 1000)  */
+    uint32_t err_ppm_last;     /* substitution rate at read end, ppm (default 10000)   */
+    uint32_t n_read_ppm;       /* reads that get one 'N' (default 1000)                */
+    uint32_t poly_tail_ppm;    /* reads with a poly-A / poly-G tail (default 100)      */
+    uint64_t reserved[4];
+} mfkc_synth_cfg;
+void mfkc_synth_defaults(mfkc_synth_cfg *cfg);
+/* Host generator: reads [first_read, first_read+n_reads) as fixed-stride ASCII (read_len bytes
+ * each, may contain 'N'). */
+int  mfkc_synth_reads_host(const mfkc_synth_cfg *cfg, uint64_t first_read, uint64_t n_reads, uint8_t *out);
+/* Device generator: only the reads WITHOUT 'N' (what the parser would keep), densely packed
+ * into d_bases (capacity n_reads*read_len); *n_kept reads written.  d_offsets (n_reads+1) gets
+ * the offsets.  Uses the context's device and stream. */
+int  mfkc_synth_reads_device(mfkc_ctx *ctx, const mfkc_synth_cfg *cfg, uint64_t first_read, uint64_t n_reads,
+                             uint8_t *d_bases, uint64_t *d_offsets, uint64_t *n_kept);
+
+/* ---- raw device memory helpers so that a non-CUDA host (Java, ctypes) can stage
+ * device-resident inputs; thin wrappers over cudaMalloc/cudaFree/cudaMemcpy. ------------- */
+int  mfkc_device_alloc(mfkc_ctx *ctx, size_t bytes, void **d_ptr);
+int  mfkc_device_free(mfkc_ctx *ctx, void *d_ptr);
+int  mfkc_memcpy_h2d(mfkc_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int  mfkc_memcpy_d2h(mfkc_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int  mfkc_device_sync(mfkc_ctx *ctx);
+/* CUDA-event timing on the context's streams: marks bracket work submitted in between. */
+int  mfkc_timer_start(mfkc_ctx *ctx);
+int  mfkc_timer_stop_ms(mfkc_ctx *ctx, float *ms);           /* synchronises */
+/* Kernel time/launch accounting since the last reset_profile: name-indexed (see
+ * mfkc_profile_name).  Each slot holds accumulated CUDA-event milliseconds (only when
+ * profiling is enabled -- it serialises the pipeline) and launch counts (always). */
+int  mfkc_profile_enable(mfkc_ctx *ctx, int on);
+int  mfkc_profile_reset(mfkc_ctx *ctx);
+int  mfkc_profile_get(mfkc_ctx *ctx, int slot, double *ms, uint64_t *launches);
+const char *mfkc_profile_name(int slot);                      /* NULL past the last slot */
+
+/* Random-sector read-modify-write microbenchmark (GUPS-style) on a table of `bytes` bytes:
+ * n_updates atomic adds to uniformly random 32-byte sectors; returns device milliseconds.
+ * This measures the random-access HBM roofline the hash variant is compared against. */
+int  mfkc_gups(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFKC_H */

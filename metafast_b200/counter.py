@@ -1,0 +1,329 @@
+"""Thin Python host layer over the C ABI (used by tests, bench.py and the smoke check).
+
+The classes mirror the seams of the reference that libmfkc replaces:
+
+* ``KmerCounter.submit / flush / emit``  <->  IOUtils.loadReads + IOUtils.printKmers
+  (src/io/IOUtils.java:772-803, 45-71)
+* ``FeaturesCalculator``                <->  FeaturesCalculatorMain's map set-up,
+  IOUtils.calculatePresenceForKmers/Reads and buildAndPrintVector
+  (src/tools/FeaturesCalculatorMain.java:97-103,169-236; src/io/IOUtils.java:577-597,806-834)
+* ``read_file``                         <->  ReadersUtils.readDnaLazy ([itmo]/io/ReadersUtils.java:85-102)
+
+Everything is executed by libmfkc (CUDA kernels for the device work, C++ for the parsers).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def pack_reads(reads: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+    """List of read strings -> (ASCII bases uint8[], offsets uint64[n+1])."""
+    offsets = np.zeros(len(reads) + 1, dtype=np.uint64)
+    if reads:
+        offsets[1:] = np.cumsum([len(r) for r in reads], dtype=np.uint64)
+    bases = np.frombuffer("".join(reads).encode("latin-1"), dtype=np.uint8).copy()
+    if bases.size == 0:
+        bases = np.zeros(1, dtype=np.uint8)
+    return bases, offsets
+
+
+class _Ctx:
+    def __init__(self, k: int, min_seq_len: int = 0, device: int = 0, variant: int = _abi.VARIANT_HASH,
+                 table_slots: int = 0, expected_distinct: int = 0, n_shards: int = 0, shard_id: int = 0,
+                 max_table_bytes: int = 0):
+        self.lib = _abi.load()
+        cfg = _abi.MfkcCfg()
+        cfg.struct_size = C.sizeof(_abi.MfkcCfg)
+        cfg.k, cfg.min_seq_len, cfg.device, cfg.variant = k, min_seq_len, device, variant
+        cfg.n_shards, cfg.shard_id = n_shards, shard_id
+        cfg.table_slots, cfg.expected_distinct, cfg.max_table_bytes = table_slots, expected_distinct, max_table_bytes
+        h = C.c_void_p()
+        rc = self.lib.mfkc_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise _abi.MfkcError(rc, self.lib.mfkc_last_error(None).decode())
+        self.h = h
+        self.k = k
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise _abi.MfkcError(rc, self.lib.mfkc_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mfkc_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- raw device helpers
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._ck(self.lib.mfkc_device_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr: int):
+        self._ck(self.lib.mfkc_device_free(self.h, C.c_void_p(ptr)))
+
+    def h2d(self, dptr: int, arr: np.ndarray):
+        self._ck(self.lib.mfkc_memcpy_h2d(self.h, C.c_void_p(dptr), _ptr(arr), arr.nbytes))
+
+    def d2h(self, arr: np.ndarray, dptr: int):
+        self._ck(self.lib.mfkc_memcpy_d2h(self.h, _ptr(arr), C.c_void_p(dptr), arr.nbytes))
+
+    def sync(self):
+        self._ck(self.lib.mfkc_device_sync(self.h))
+
+    def pinned(self, nbytes: int, dtype=np.uint8) -> np.ndarray:
+        p = C.c_void_p()
+        self._ck(self.lib.mfkc_pinned_alloc(self.h, nbytes, C.byref(p)))
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        a = np.frombuffer(buf, dtype=np.uint8).view(dtype)
+        a.flags.writeable = True
+        return a
+
+    def timer_start(self):
+        self._ck(self.lib.mfkc_timer_start(self.h))
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.mfkc_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile(self, enable: Optional[bool] = None, reset: bool = False) -> dict:
+        if enable is not None:
+            self._ck(self.lib.mfkc_profile_enable(self.h, 1 if enable else 0))
+        if reset:
+            self._ck(self.lib.mfkc_profile_reset(self.h))
+        out = {}
+        i = 0
+        while True:
+            name = self.lib.mfkc_profile_name(i)
+            if name is None:
+                break
+            ms, n = C.c_double(), C.c_uint64()
+            self._ck(self.lib.mfkc_profile_get(self.h, i, C.byref(ms), C.byref(n)))
+            out[name.decode()] = (ms.value, n.value)
+            i += 1
+        return out
+
+    def gups(self, nbytes: int, n_updates: int, dependent: bool = False) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.mfkc_gups(self.h, nbytes, n_updates | ((1 << 63) if dependent else 0), C.byref(ms)))
+        return ms.value
+
+
+class KmerCounter(_Ctx):
+    """One sample's k-mer counter (BigLong2ShortHashMap + ReadsLoadWorker pool analogue)."""
+
+    def submit(self, bases: np.ndarray, offsets: np.ndarray):
+        assert bases.dtype == np.uint8 and offsets.dtype == np.uint64
+        self._ck(self.lib.mfkc_submit_reads(self.h, _ptr(bases), _ptr(offsets), len(offsets) - 1))
+
+    def submit_reads(self, reads: Sequence[str]):
+        b, o = pack_reads(reads)
+        self.submit(b, o)
+
+    def submit_device(self, d_bases: int, d_offsets: int, n_reads: int, n_bases: int):
+        self._ck(self.lib.mfkc_submit_reads_device(self.h, C.c_void_p(d_bases), C.c_void_p(d_offsets), n_reads, n_bases))
+
+    def flush(self):
+        self._ck(self.lib.mfkc_flush(self.h))
+
+    def reset(self):
+        self._ck(self.lib.mfkc_reset(self.h))
+
+    def stats(self) -> dict:
+        s = (C.c_uint64 * 6)()
+        self._ck(self.lib.mfkc_stats(self.h, s))
+        return dict(zip(("distinct", "kmers", "total_seq", "good_seq", "total_len", "good_len"), list(s)))
+
+    def histogram(self) -> np.ndarray:
+        h = np.zeros(_abi.HIST_BINS, dtype=np.uint64)
+        self._ck(self.lib.mfkc_histogram(self.h, h.ctypes.data_as(_abi.u64p)))
+        return h
+
+    def emit_begin(self, threshold: int) -> int:
+        n = C.c_uint64()
+        self._ck(self.lib.mfkc_emit_begin(self.h, threshold, C.byref(n)))
+        return n.value
+
+    def emit(self, threshold: int, chunk_bytes: int = 16777200) -> bytes:
+        """All records (big-endian, ascending key) as one bytes object."""
+        n = self.emit_begin(threshold)
+        out = np.empty(n * 10, dtype=np.uint8) if n else np.empty(0, dtype=np.uint8)
+        pos = 0
+        w = C.c_size_t()
+        while True:
+            cap = min(chunk_bytes, out.nbytes - pos)
+            self._ck(self.lib.mfkc_emit_next(self.h, C.c_void_p(out.ctypes.data + pos) if cap else None, cap, C.byref(w)))
+            if w.value == 0:
+                break
+            pos += w.value
+        assert pos == n * 10
+        return out.tobytes()
+
+    def emit_into(self, threshold: int, out: np.ndarray) -> int:
+        """Records into a caller-provided (ideally pinned) uint8 buffer; returns bytes written."""
+        n = self.emit_begin(threshold)
+        if n * 10 > out.nbytes:
+            raise ValueError("output buffer too small: need %d bytes" % (n * 10))
+        pos = 0
+        w = C.c_size_t()
+        while pos < n * 10:
+            self._ck(self.lib.mfkc_emit_next(self.h, C.c_void_p(out.ctypes.data + pos), out.nbytes - pos, C.byref(w)))
+            if w.value == 0:
+                break
+            pos += w.value
+        return pos
+
+    def emit_device(self) -> Tuple[int, int, int]:
+        k, c, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.mfkc_emit_device(self.h, C.byref(k), C.byref(c), C.byref(n)))
+        return k.value, c.value, n.value
+
+    # ---- sharding
+    def extract_bucketed(self, d_bases: int, d_offsets: int, n_reads: int, n_bases: int, d_keys_out: int,
+                         cap_keys: int, n_shards: int) -> List[int]:
+        cnt = (C.c_uint64 * max(n_shards, 1))()
+        self._ck(self.lib.mfkc_extract_bucketed(self.h, C.c_void_p(d_bases), C.c_void_p(d_offsets), n_reads, n_bases,
+                                                C.c_void_p(d_keys_out), cap_keys, cnt))
+        return list(cnt)
+
+    def count_keys_device(self, d_keys: int, n: int):
+        self._ck(self.lib.mfkc_count_keys_device(self.h, C.c_void_p(d_keys), n))
+
+
+class FeaturesCalculator(_Ctx):
+    """features-calculator on the device (K6/K7/K8)."""
+
+    def load_components(self, comps: Sequence[Sequence[int]]):
+        off = np.zeros(len(comps) + 1, dtype=np.uint64)
+        if comps:
+            off[1:] = np.cumsum([len(c) for c in comps], dtype=np.uint64)
+        flat = np.array([k for c in comps for k in c], dtype=np.uint64).view(np.int64)
+        if flat.size == 0:
+            flat = np.zeros(1, dtype=np.int64)
+        self.n_comp = len(comps)
+        self._ck(self.lib.mfkc_fc_load_components(self.h, _ptr(flat), _ptr(off), len(comps)))
+
+    def set_selected(self, records: Optional[bytes]):
+        if records is None:
+            self._ck(self.lib.mfkc_fc_set_selected(self.h, None, 0))
+            return
+        a = np.frombuffer(records, dtype=np.uint8) if records else np.zeros(1, dtype=np.uint8)
+        self._ck(self.lib.mfkc_fc_set_selected(self.h, _ptr(a), len(records) // 10))
+
+    def reset_values(self):
+        self._ck(self.lib.mfkc_fc_reset_values(self.h))
+
+    def add_records(self, records: bytes, chunk: int = 16777200):
+        a = np.frombuffer(records, dtype=np.uint8)
+        for s in range(0, len(records), chunk):
+            part = a[s:s + chunk]
+            self._ck(self.lib.mfkc_fc_add_records(self.h, _ptr(part), part.nbytes // 10))
+
+    def add_reads(self, reads: Sequence[str]):
+        b, o = pack_reads(reads)
+        self._ck(self.lib.mfkc_fc_add_reads(self.h, _ptr(b), _ptr(o), len(reads)))
+
+    def features(self, threshold: int = 0):
+        n = self.n_comp
+        vec = np.zeros(max(n, 1), dtype=np.int64)
+        found = np.zeros(max(n, 1), dtype=np.uint64)
+        cnt = np.zeros(max(n, 1), dtype=np.uint64)
+        self._ck(self.lib.mfkc_fc_features(self.h, threshold, _ptr(vec), _ptr(found), _ptr(cnt)))
+        return vec[:n], found[:n], cnt[:n]
+
+
+# ---- host-side pieces (CPU, no GPU needed) ------------------------------------------------
+class ReaderError(_abi.MfkcError):
+    pass
+
+
+def read_file(path: str, batch_reads: int = 1 << 15, batch_bases: int = 1 << 24) -> Iterator[Tuple[np.ndarray, np.ndarray]]:
+    """Yield (bases, offsets) batches of the reads the reference's parser would keep."""
+    lib = _abi.load()
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib.mfkc_reader_open(path.encode(), C.byref(h), err, 512)
+    if rc != 0:
+        raise ReaderError(rc, err.value.decode())
+    try:
+        bases = np.empty(batch_bases, dtype=np.uint8)
+        offsets = np.empty(batch_reads + 1, dtype=np.uint64)
+        n = C.c_uint32()
+        while True:
+            rc = lib.mfkc_reader_next(h, _ptr(bases), bases.nbytes, _ptr(offsets), batch_reads, C.byref(n))
+            if rc != 0:
+                raise ReaderError(rc, lib.mfkc_reader_error(h).decode())
+            if n.value == 0:
+                break
+            nb = int(offsets[n.value])
+            yield bases[:max(nb, 1)].copy(), offsets[: n.value + 1].copy()
+    finally:
+        lib.mfkc_reader_close(h)
+
+
+def read_file_reads(path: str) -> List[str]:
+    out: List[str] = []
+    for b, o in read_file(path):
+        s = b.tobytes().decode("latin-1")
+        out += [s[int(o[i]):int(o[i + 1])] for i in range(len(o) - 1)]
+    return out
+
+
+def reader_name(path: str) -> str:
+    lib = _abi.load()
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib.mfkc_reader_open(path.encode(), C.byref(h), err, 512)
+    if rc != 0:
+        raise ReaderError(rc, err.value.decode())
+    try:
+        return lib.mfkc_reader_name(h).decode()
+    finally:
+        lib.mfkc_reader_close(h)
+
+
+def synth_cfg(**kw) -> _abi.SynthCfg:
+    lib = _abi.load()
+    c = _abi.SynthCfg()
+    lib.mfkc_synth_defaults(C.byref(c))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def synth_reads_host(cfg: _abi.SynthCfg, first: int, n: int) -> np.ndarray:
+    lib = _abi.load()
+    out = np.empty((n, cfg.read_len), dtype=np.uint8)
+    rc = lib.mfkc_synth_reads_host(C.byref(cfg), first, n, _ptr(out))
+    if rc != 0:
+        raise _abi.MfkcError(rc, "mfkc_synth_reads_host")
+    return out
+
+
+def write_stat_file(path: str, hist: np.ndarray):
+    lib = _abi.load()
+    rc = lib.mfkc_write_stat_file(path.encode(), hist.ctypes.data_as(_abi.u64p))
+    if rc != 0:
+        raise _abi.MfkcError(rc, "cannot write " + path)

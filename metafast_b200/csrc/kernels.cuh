@@ -1,0 +1,701 @@
+// kernels.cuh -- hand-written sm_100a kernels of the k-mer counting path (64-bit keys, k <= 31).
+//
+//   K0 mark_read_ends_kernel   read boundaries -> 1 bit per base, read/length statistics
+//   K1+K2+K3 extract_kernel<Sink>  ASCII -> 2-bit pack (smem) -> canonical k-mers -> sink
+//        sinks: table upsert (hash variant), append (sort variant), shard bucketing,
+//               features-calculator presence accumulate
+//   K3  rehash_kernel          table growth
+//   K4  table_hist_kernel / table_compact_kernel / records_kernel   histogram, filter, BE records
+//   K6  fc_* kernels           membership + accumulate, per-component reduce
+//
+// Reference semantics restated here:
+//   [itmo]/dna/kmers/ShortKmer.java:54-56,68-71,122-149  (canonical rolling k-mers)
+//   [itmo]/utils/KmerUtils.java:12-22                    (reverse complement)
+//   [itmo]/structures/map/Long2ShortHashMap.java:119-157 (addAndBound = saturating count)
+//   src/io/IOUtils.java:45-71, 577-588, 756-769, 806-825
+#pragma once
+#include "device_common.cuh"
+
+namespace mfkc {
+
+// ------------------------------------------------------------------------------------------
+// device-side counters (one struct per context, lives in device memory)
+// ------------------------------------------------------------------------------------------
+struct Counters {
+    unsigned long long distinct;      // successful slot claims (hm.size())
+    unsigned long long kmers;         // k-mer instances extracted
+    unsigned long long total_seq, good_seq, total_len, good_len;   // IOUtils.java:752-769
+    unsigned long long bad_chars;     // bytes outside AaCcGgTt seen by the packer
+    unsigned long long appended;      // sort variant / bucketing: keys written
+    unsigned long long overflow;      // appended past capacity (keys dropped -> error)
+    unsigned long long n_good;        // compaction cursor
+    unsigned long long pad[6];
+};
+
+// ------------------------------------------------------------------------------------------
+// K0: read boundaries.  flags: 1 bit per base position (bit p&31 of word p>>5), set at the LAST
+// base of every read, and at every base of reads that must yield nothing although they are
+// >= k long (len < min_seq_len, IOUtils.java:761).  A k-mer starting at p is valid iff no flag
+// is set in [p, p+k-2] and p+k <= n_bases; reads shorter than k are thereby skipped for free
+// (ShortKmer.java:123,127).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mark_read_ends_kernel(const uint64_t *__restrict__ offsets, uint32_t n_reads, uint64_t n_bases,
+                      int k, int min_len, int count_stats, uint32_t *__restrict__ flags,
+                      Counters *__restrict__ ctr) {
+    unsigned long long t_seq = 0, g_seq = 0, t_len = 0, g_len = 0, kmers = 0;
+    const uint64_t base0 = offsets[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_reads; i += gridDim.x * blockDim.x) {
+        uint64_t s = offsets[i] - base0, e = offsets[i + 1] - base0;
+        if (e > n_bases) e = n_bases;
+        if (s > e) s = e;
+        const uint64_t len = e - s;
+        t_seq++; t_len += len;
+        const bool good = (long long)len >= (long long)min_len;
+        if (good) { g_seq++; g_len += len; if (len >= (uint64_t)k) kmers += len - k + 1; }
+        if (len == 0) continue;
+        if (good || len < (uint64_t)k) {
+            atomicOr(&flags[(e - 1) >> 5], 1u << ((e - 1) & 31));
+        } else {
+            for (uint64_t p = s; p < e; p++) atomicOr(&flags[p >> 5], 1u << (p & 31));
+        }
+    }
+    if (!count_stats) return;
+    // warp-reduce, one atomic per warp
+    for (int o = 16; o; o >>= 1) {
+        t_seq += __shfl_xor_sync(0xffffffffu, t_seq, o); g_seq += __shfl_xor_sync(0xffffffffu, g_seq, o);
+        t_len += __shfl_xor_sync(0xffffffffu, t_len, o); g_len += __shfl_xor_sync(0xffffffffu, g_len, o);
+        kmers += __shfl_xor_sync(0xffffffffu, kmers, o);
+    }
+    if (lane_id() == 0 && t_seq) {
+        atomicAdd(&ctr->total_seq, t_seq); atomicAdd(&ctr->good_seq, g_seq);
+        atomicAdd(&ctr->total_len, t_len); atomicAdd(&ctr->good_len, g_len);
+        atomicAdd(&ctr->kmers, kmers);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// table operations
+// ------------------------------------------------------------------------------------------
+// count += 1 for `key` (Long2ShortHashMap.addAndBound with inc = 1).  Thread-per-key linear
+// probing; one 128-bit load brings key and count of a slot (same sector).  Returns true when
+// this call claimed a new slot.
+__device__ __forceinline__ bool table_upsert1(Slot *__restrict__ tab, uint64_t cap, uint64_t key) {
+    uint64_t i = home_slot(key, cap);
+    for (;;) {
+        const ulonglong2 s = ld_cg_u64x2(&tab[i]);
+        if (s.x == key) {
+            // saturation: once the stored count reached 32767 further increments are no-ops
+            if ((uint32_t)s.y < MAX_COUNT) atomicAdd(&tab[i].count, 1u);
+            return false;
+        }
+        if (s.x == EMPTY_KEY) {
+            const unsigned long long prev = atomicCAS(&tab[i].key, EMPTY_KEY, (unsigned long long)key);
+            if (prev == EMPTY_KEY) { atomicAdd(&tab[i].count, 1u); return true; }
+            if (prev == key) { atomicAdd(&tab[i].count, 1u); return false; }
+        }
+        if (++i == cap) i = 0;
+    }
+}
+
+// count = sat_add(count, inc) for arbitrary inc (rehash, pre-aggregated (key,count) pairs).
+__device__ __forceinline__ bool table_upsert_n(Slot *__restrict__ tab, uint64_t cap, uint64_t key, uint32_t inc) {
+    uint64_t i = home_slot(key, cap);
+    bool claimed = false;
+    for (;;) {
+        unsigned long long cur = ld_cg_u64x2(&tab[i]).x;
+        if (cur == EMPTY_KEY) {
+            cur = atomicCAS(&tab[i].key, EMPTY_KEY, (unsigned long long)key);
+            if (cur == EMPTY_KEY) { claimed = true; cur = key; }
+        }
+        if (cur == key) {
+            uint32_t old = *(volatile uint32_t *)&tab[i].count;
+            for (;;) {
+                if (old >= MAX_COUNT) break;
+                uint32_t nv = old + inc; if (nv > MAX_COUNT || nv < old) nv = MAX_COUNT;
+                const uint32_t seen = atomicCAS(&tab[i].count, old, nv);
+                if (seen == old) break;
+                old = seen;
+            }
+            return claimed;
+        }
+        if (++i == cap) i = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+table_clear_kernel(Slot *__restrict__ tab, uint64_t cap) {
+    // 16-byte stores, fully coalesced
+    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
+        reinterpret_cast<uint4 *>(tab)[i] = e;
+}
+
+__global__ void __launch_bounds__(256)
+rehash_kernel(const Slot *__restrict__ old_tab, uint64_t old_cap, Slot *__restrict__ new_tab, uint64_t new_cap) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 s = ld_nc_u128(&old_tab[i]);
+        const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
+        if (key != EMPTY_KEY) table_upsert_n(new_tab, new_cap, key, s.z < MAX_COUNT ? s.z : MAX_COUNT);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// sinks of the extraction kernel
+// ------------------------------------------------------------------------------------------
+struct SinkTable {              // hash variant: upsert into the HBM-resident table
+    Slot *tab; uint64_t cap; Counters *ctr;
+    static constexpr bool kPrefetch = true;
+    __device__ __forceinline__ void prefetch(uint64_t key) const { prefetch_l2(&tab[home_slot(key, cap)]); }
+    __device__ __forceinline__ uint32_t put(uint64_t key) const { return table_upsert1(tab, cap, key) ? 1u : 0u; }
+    __device__ __forceinline__ void finish(uint32_t local) const {
+        // local = number of new slots claimed by this thread: warp-reduce -> one atomic per warp
+        for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if (lane_id() == 0 && local) atomicAdd(&ctr->distinct, (unsigned long long)local);
+    }
+};
+
+struct SinkAppend {             // sort variant: append every key to a flat device array
+    unsigned long long *out; uint64_t cap; Counters *ctr;
+    static constexpr bool kPrefetch = false;
+    __device__ __forceinline__ void prefetch(uint64_t) const {}
+    __device__ __forceinline__ uint32_t put(uint64_t) const { return 0; }   // unused (bulk path)
+    __device__ __forceinline__ void finish(uint32_t) const {}
+};
+
+struct SinkPresence {           // features-calculator reads mode: if (contains(key)) acc += 1
+    FcSlot *tab; uint64_t cap;
+    static constexpr bool kPrefetch = true;
+    __device__ __forceinline__ void prefetch(uint64_t key) const { prefetch_l2(&tab[home_slot(key, cap)]); }
+    __device__ __forceinline__ uint32_t put(uint64_t key) const;
+    __device__ __forceinline__ void finish(uint32_t) const {}
+};
+
+// NumUtils.addAndBound(long,long) ([itmo]/utils/NumUtils.java:27-32) with Java's wrapping arithmetic.
+__device__ __forceinline__ long long add_and_bound64(long long v, long long inc) {
+    const long long lim = (long long)(0x7fffffffffffffffULL - (unsigned long long)inc);
+    if (v > lim) return 0x7fffffffffffffffLL;
+    return (long long)((unsigned long long)v + (unsigned long long)inc);
+}
+
+// if (hm.contains(key)) hm.addAndBound(key, inc)   (src/io/IOUtils.java:583-587, 817-821)
+__device__ __forceinline__ void fc_accumulate(FcSlot *__restrict__ tab, uint64_t cap, uint64_t key, long long inc) {
+    uint64_t i = home_slot(key, cap);
+    for (;;) {
+        const unsigned long long cur = ld_cg_u64x2(&tab[i]).x;
+        if (cur == EMPTY_KEY) return;                 // not a component k-mer
+        if (cur == key) {
+            unsigned long long old = *(volatile unsigned long long *)&tab[i].acc;
+            for (;;) {
+                const unsigned long long nv = (unsigned long long)add_and_bound64((long long)old, inc);
+                const unsigned long long seen = atomicCAS((unsigned long long *)&tab[i].acc, old, nv);
+                if (seen == old) return;
+                old = seen;
+            }
+        }
+        if (++i == cap) i = 0;
+    }
+}
+__device__ __forceinline__ uint32_t SinkPresence::put(uint64_t key) const { fc_accumulate(tab, cap, key, 1); return 0; }
+
+// ------------------------------------------------------------------------------------------
+// K1+K2(+K3): flat extraction.  The batch is one concatenated ASCII stream; thread t of a tile
+// owns the 16 bases [16w, 16w+16) (one aligned 128-bit load), packs them to one 32-bit word in
+// shared memory (base 0 in the top bit pair), and produces the (up to) 16 k-mers that START in
+// its word from the 96-bit window (own word + two successors; 2 halo words per tile).  The
+// forward k-mer is a funnel shift of the window, the reverse complement is rolled
+// (ShortKmer.shiftRight, ShortKmer.java:68-71) from a bit-reversal seed (KmerUtils.java:12-22).
+// ------------------------------------------------------------------------------------------
+constexpr int EX_THREADS = 256;
+
+__device__ __forceinline__ uint64_t revcomp64(uint64_t fw, int k) {
+    // reverse the 2-bit groups of fw, complement, right-align (KmerUtils.reverseComplement)
+    uint64_t x = __brevll(fw);                                         // reverses single bits
+    x = ((x & 0x5555555555555555ULL) << 1) | ((x >> 1) & 0x5555555555555555ULL);   // restore pair order
+    return (~x) >> (64 - 2 * k);
+}
+
+// Computes the canonical keys starting in this thread's word.  keys[j] valid iff bit j of the
+// returned mask is set.
+__device__ __forceinline__ uint32_t kmers_of_word(uint32_t w0, uint32_t w1, uint32_t w2, uint64_t flag_bits,
+                                                  long long limit /* n_bases - k - 16*w */, int k,
+                                                  uint64_t (&keys)[16]) {
+    const uint64_t span = (k > 1) ? ((1ULL << (k - 1)) - 1ULL) : 0ULL;  // flags over [p, p+k-2]
+    const int rs = 64 - 2 * k;
+    const int top = 2 * k - 2;
+    uint32_t valid = 0;
+    uint64_t rc = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t hi = j ? __funnelshift_l(w1, w0, 2 * j) : w0;
+        const uint32_t lo = j ? __funnelshift_l(w2, w1, 2 * j) : w1;
+        const uint64_t fw = (((uint64_t)hi << 32) | lo) >> rs;
+        if (j == 0) rc = revcomp64(fw, k);
+        else rc = (rc >> 2) | ((uint64_t)((~(uint32_t)fw) & 3u) << top);
+        keys[j] = fw < rc ? fw : rc;                                     // ShortKmer.toLong
+        const bool ok = ((flag_bits >> j) & span) == 0 && (long long)j <= limit;
+        valid |= (ok ? 1u : 0u) << j;
+    }
+    return valid;
+}
+
+template <class Sink>
+__global__ void __launch_bounds__(EX_THREADS)
+extract_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
+               int k, Sink sink, Counters *__restrict__ ctr) {
+    __shared__ uint32_t s_words[EX_THREADS + 2];
+    __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t n_words = (n_bases + 15) >> 4;
+    const uint64_t n_tiles = (n_words + EX_THREADS - 1) / EX_THREADS;
+    const uint64_t n_flag_words = (n_bases + 31) >> 5;
+    uint32_t claimed = 0;
+    uint32_t bad = 0;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t w_base = tile * EX_THREADS;
+        // ---- K1: pack own word (+ 2 halo words by threads 0,1)
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            if (rep == 1 && tid >= 2) break;
+            const uint32_t slot = rep ? EX_THREADS + tid : tid;
+            const uint64_t w = w_base + slot;
+            uint32_t word = 0;
+            const uint64_t b0 = w << 4;
+            if (b0 + 16 <= n_bases) {
+                const uint4 v = ld_nc_u128(bases + b0);
+                word = pack16(v);
+                bad |= bad4(v.x) | bad4(v.y) | bad4(v.z) | bad4(v.w);
+            } else if (b0 < n_bases) {                      // ragged tail of the batch
+                for (uint32_t j = 0; j < 16 && b0 + j < n_bases; j++) {
+                    const uint32_t c = bases[b0 + j];
+                    bad |= bad4(c | 0x41414100u);
+                    word |= pack4(c) >> 6 << (30 - 2 * j);
+                }
+            }
+            s_words[slot] = word;
+        }
+        // boundary flags for positions [16*w_base, 16*w_base + 16*EX_THREADS + 64)
+        if (tid < EX_THREADS / 2 + 2) {
+            const uint64_t fw = (w_base >> 1) + tid;
+            s_flags[tid] = fw < n_flag_words ? flags[fw] : 0u;
+        }
+        __syncthreads();
+
+        // ---- K2: canonical k-mers starting in my word
+        const uint64_t w = w_base + tid;
+        if ((w << 4) < n_bases) {
+            const uint32_t w0 = s_words[tid], w1 = s_words[tid + 1], w2 = s_words[tid + 2];
+            const uint32_t f0 = s_flags[tid >> 1], f1 = s_flags[(tid >> 1) + 1], f2 = s_flags[(tid >> 1) + 2];
+            // 64 flag bits starting at position 16*w
+            const uint64_t fbits = (tid & 1) ? (((uint64_t)f0 >> 16) | ((uint64_t)f1 << 16) | ((uint64_t)f2 << 48))
+                                             : ((uint64_t)f0 | ((uint64_t)f1 << 32));
+            uint64_t keys[16];
+            const long long limit = (long long)n_bases - k - (long long)(w << 4);
+            const uint32_t valid = kmers_of_word(w0, w1, w2, fbits, limit, k, keys);
+            // ---- K3: sink
+            if (Sink::kPrefetch) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) if (valid >> j & 1) sink.prefetch(keys[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) if (valid >> j & 1) claimed += sink.put(keys[j]);
+        }
+        __syncthreads();
+    }
+    sink.finish(claimed);
+    if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
+}
+
+// Bulk-append flavour (sort variant and shard bucketing): the keys of a tile are written to
+// `out` grouped by bucket (n_buckets = 1 for the sort variant).  Positions are claimed with one
+// atomic per (warp, bucket): lanes agree on their bucket via match.any.
+struct BucketSink {
+    unsigned long long *out;            // bucket b occupies out[bucket_base[b] .. )
+    const uint64_t *bucket_base;        // device, n_buckets entries (unused when count_only)
+    unsigned long long *bucket_cursor;  // device, n_buckets entries (zeroed before launch)
+    uint64_t out_cap;
+    uint32_t n_buckets;
+    int count_only;                     // pass 1: only bucket_cursor[b] += 1
+};
+
+template <int dummy = 0>
+__global__ void __launch_bounds__(EX_THREADS)
+extract_bucket_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
+                      int k, BucketSink sink, Counters *__restrict__ ctr) {
+    __shared__ uint32_t s_words[EX_THREADS + 2];
+    __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t n_words = (n_bases + 15) >> 4;
+    const uint64_t n_tiles = (n_words + EX_THREADS - 1) / EX_THREADS;
+    const uint64_t n_flag_words = (n_bases + 31) >> 5;
+    uint32_t bad = 0;
+    unsigned long long overflow = 0;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t w_base = tile * EX_THREADS;
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            if (rep == 1 && tid >= 2) break;
+            const uint32_t slot = rep ? EX_THREADS + tid : tid;
+            const uint64_t w = w_base + slot;
+            uint32_t word = 0;
+            const uint64_t b0 = w << 4;
+            if (b0 + 16 <= n_bases) {
+                const uint4 v = ld_nc_u128(bases + b0);
+                word = pack16(v);
+                bad |= bad4(v.x) | bad4(v.y) | bad4(v.z) | bad4(v.w);
+            } else if (b0 < n_bases) {
+                for (uint32_t j = 0; j < 16 && b0 + j < n_bases; j++) {
+                    const uint32_t c = bases[b0 + j];
+                    bad |= bad4(c | 0x41414100u);
+                    word |= pack4(c) >> 6 << (30 - 2 * j);
+                }
+            }
+            s_words[slot] = word;
+        }
+        if (tid < EX_THREADS / 2 + 2) {
+            const uint64_t fw = (w_base >> 1) + tid;
+            s_flags[tid] = fw < n_flag_words ? flags[fw] : 0u;
+        }
+        __syncthreads();
+
+        const uint64_t w = w_base + tid;
+        uint64_t keys[16];
+        uint32_t valid = 0;
+        if ((w << 4) < n_bases) {
+            const uint32_t w0 = s_words[tid], w1 = s_words[tid + 1], w2 = s_words[tid + 2];
+            const uint32_t f0 = s_flags[tid >> 1], f1 = s_flags[(tid >> 1) + 1], f2 = s_flags[(tid >> 1) + 2];
+            const uint64_t fbits = (tid & 1) ? (((uint64_t)f0 >> 16) | ((uint64_t)f1 << 16) | ((uint64_t)f2 << 48))
+                                             : ((uint64_t)f0 | ((uint64_t)f1 << 32));
+            const long long limit = (long long)n_bases - k - (long long)(w << 4);
+            valid = kmers_of_word(w0, w1, w2, fbits, limit, k, keys);
+        }
+        // all 32 lanes take part in the warp-level position claims
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const bool ok = (valid >> j) & 1;
+            const uint32_t b = (ok && sink.n_buckets > 1) ? owner_shard(keys[j], sink.n_buckets) : 0u;
+            const uint32_t active = __ballot_sync(0xffffffffu, ok);
+            if (!active) continue;
+            uint32_t peers;
+            if (sink.n_buckets > 1) peers = __match_any_sync(0xffffffffu, ok ? b : 0xFFFFFFFFu);
+            else peers = active;
+            if (ok) {
+                const uint32_t rank = __popc(peers & lanemask_lt());
+                const int leader = __ffs(peers) - 1;
+                unsigned long long pos = 0;
+                if ((int)lane_id() == leader) pos = atomicAdd(&sink.bucket_cursor[b], (unsigned long long)__popc(peers));
+                pos = __shfl_sync(peers, pos, leader);
+                if (!sink.count_only) {
+                    const uint64_t at = sink.bucket_base[b] + pos + rank;
+                    if (at < sink.out_cap) sink.out[at] = keys[j]; else overflow++;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (overflow) atomicAdd(&ctr->overflow, overflow);
+    if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
+}
+
+// receive side of the shard exchange / generic "count these keys"
+__global__ void __launch_bounds__(256)
+count_keys_kernel(const unsigned long long *__restrict__ keys, uint64_t n, Slot *__restrict__ tab, uint64_t cap,
+                  Counters *__restrict__ ctr) {
+    uint32_t claimed = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        claimed += table_upsert1(tab, cap, keys[i]) ? 1u : 0u;
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+}
+
+// (key,count) pairs -> table (used by tests of table_upsert_n and by pre-aggregated inputs)
+__global__ void __launch_bounds__(256)
+count_pairs_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ counts, uint64_t n,
+                   Slot *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr) {
+    uint32_t claimed = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        claimed += table_upsert_n(tab, cap, keys[i], counts[i]) ? 1u : 0u;
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: histogram over ALL entries (src/io/IOUtils.java:59), filter count > b, compaction
+// ------------------------------------------------------------------------------------------
+constexpr int HIST_SMEM_BINS = 2048;
+
+__global__ void __launch_bounds__(256)
+table_hist_kernel(const Slot *__restrict__ tab, uint64_t cap, unsigned long long *__restrict__ hist) {
+    __shared__ uint32_t s_hist[HIST_SMEM_BINS];
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 s = ld_nc_u128(&tab[i]);
+        if ((s.x & s.y) != 0xFFFFFFFFu) {
+            const uint32_t c = s.z < MAX_COUNT ? s.z : MAX_COUNT;
+            if (c < HIST_SMEM_BINS) atomicAdd(&s_hist[c], 1u);
+            else atomicAdd(&hist[c], 1ULL);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+
+__global__ void __launch_bounds__(256)
+table_compact_kernel(const Slot *__restrict__ tab, uint64_t cap, uint32_t threshold,
+                     unsigned long long *__restrict__ out_keys, uint16_t *__restrict__ out_counts,
+                     uint64_t out_cap, Counters *__restrict__ ctr) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_iter = (cap + stride - 1) / stride;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint64_t it = 0; it < n_iter; it++, i += stride) {
+        bool good = false;
+        unsigned long long key = 0; uint32_t c = 0;
+        if (i < cap) {
+            const uint4 s = ld_nc_u128(&tab[i]);
+            key = ((unsigned long long)s.y << 32) | s.x;
+            c = s.z < MAX_COUNT ? s.z : MAX_COUNT;
+            good = key != EMPTY_KEY && c > threshold;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, good);
+        if (!m) continue;
+        unsigned long long base = 0;
+        if (lane_id() == 0) base = atomicAdd(&ctr->n_good, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (good) {
+            const uint64_t at = base + __popc(m & lanemask_lt());
+            if (at < out_cap) { out_keys[at] = key; out_counts[at] = (uint16_t)c; }
+        }
+    }
+}
+
+// sorted (key,count) -> big-endian 10-byte records (src/io/IOUtils.java:61-65: writeLong, writeShort)
+__global__ void __launch_bounds__(256)
+records_kernel(const unsigned long long *__restrict__ keys, const uint16_t *__restrict__ counts, uint64_t n,
+               uint16_t *__restrict__ out /* 5 x u16 per record */) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[i];
+        const uint32_t c = counts[i];
+        uint16_t *o = out + 5 * i;
+        // big-endian bytes, emitted as little-endian u16 stores of byte-swapped halves
+        const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+        o[0] = (uint16_t)__byte_perm(hi, 0, 0x0023);   // bytes 3,2 of hi -> [b3][b2] in memory order
+        o[1] = (uint16_t)__byte_perm(hi, 0, 0x0001);
+        o[2] = (uint16_t)__byte_perm(lo, 0, 0x0023);
+        o[3] = (uint16_t)__byte_perm(lo, 0, 0x0001);
+        o[4] = (uint16_t)__byte_perm(c, 0, 0x0001);
+    }
+}
+
+// sort variant: run-length encode a sorted key array.  heads[i] = 1 iff keys[i] starts a run.
+__global__ void __launch_bounds__(256)
+rle_mark_kernel(const unsigned long long *__restrict__ keys, uint64_t n, unsigned long long *__restrict__ n_runs_block) {
+    // counts run heads per block (block b covers a contiguous slice) for the exclusive scan
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = per_block * blockIdx.x;
+    const uint64_t hi = lo + per_block < n ? lo + per_block : n;
+    uint32_t local = 0;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+        local += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane_id() == 0 && local) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) n_runs_block[blockIdx.x] = s_cnt;
+}
+
+// After an exclusive scan of n_runs_block (-> run_base[b]): each block walks its slice in order and
+// writes (key, run length) for every run head; run length = distance to the next head, found by
+// scanning forward (runs are short on average; heavy runs are walked by one thread but only once).
+__global__ void __launch_bounds__(256)
+rle_write_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ weights /* may be NULL */,
+                 uint64_t n, const unsigned long long *__restrict__ run_base,
+                 unsigned long long *__restrict__ out_keys, uint32_t *__restrict__ out_counts) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base;
+    const uint64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = per_block * blockIdx.x;
+    const uint64_t hi = lo + per_block < n ? lo + per_block : n;
+    if (threadIdx.x == 0) s_base = run_base[blockIdx.x];
+    __syncthreads();
+    for (uint64_t start = lo; start < hi; start += blockDim.x) {
+        const uint64_t i = start + threadIdx.x;
+        const bool head = i < hi && (i == 0 || keys[i] != keys[i - 1]);
+        const uint32_t m = __ballot_sync(0xffffffffu, head);
+        if (lane_id() == 0) s_warp[threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int wv = 0; wv < 8; wv++) { const uint32_t c = s_warp[wv]; if (wv < (int)(threadIdx.x >> 5)) before += c; total += c; }
+        if (head) {
+            const uint64_t at = s_base + before + __popc(m & lanemask_lt());
+            const unsigned long long key = keys[i];
+            unsigned long long len = 0;
+            for (uint64_t j = i; j < n && keys[j] == key; j++) {
+                len += weights ? weights[j] : 1u;
+                if (len >= MAX_COUNT && !weights) { /* saturated: skip ahead cheaply */ }
+            }
+            out_keys[at] = key;
+            out_counts[at] = len > MAX_COUNT ? MAX_COUNT : (uint32_t)len;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+}
+
+// histogram + filter over an already RLE'd sorted (key,count) array (sort variant emit)
+__global__ void __launch_bounds__(256)
+pairs_hist_kernel(const uint32_t *__restrict__ counts, uint64_t n, unsigned long long *__restrict__ hist) {
+    __shared__ uint32_t s_hist[HIST_SMEM_BINS];
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = counts[i] < MAX_COUNT ? counts[i] : MAX_COUNT;
+        if (c < HIST_SMEM_BINS) atomicAdd(&s_hist[c], 1u); else atomicAdd(&hist[c], 1ULL);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// K6/K7: features-calculator
+// ------------------------------------------------------------------------------------------
+// hm.put(kmer, 0) for every component k-mer (FeaturesCalculatorMain.java:97-103)
+__global__ void __launch_bounds__(256)
+fc_build_kernel(const unsigned long long *__restrict__ keys, uint64_t n, FcSlot *__restrict__ tab, uint64_t cap,
+                Counters *__restrict__ ctr) {
+    uint32_t claimed = 0;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[t];
+        uint64_t i = home_slot(key, cap);
+        for (;;) {
+            unsigned long long cur = ld_cg_u64x2(&tab[i]).x;
+            if (cur == EMPTY_KEY) {
+                cur = atomicCAS(&tab[i].key, EMPTY_KEY, key);
+                if (cur == EMPTY_KEY) { claimed++; break; }
+            }
+            if (cur == key) break;
+            if (++i == cap) i = 0;
+        }
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+}
+
+__global__ void __launch_bounds__(256)
+fc_clear_kernel(FcSlot *__restrict__ tab, uint64_t cap, int keys_too) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (keys_too) tab[i].key = EMPTY_KEY;
+        tab[i].acc = 0;
+    }
+}
+
+__device__ __forceinline__ void load_record(const uint8_t *__restrict__ rec, unsigned long long &key, int &freq) {
+    // 10-byte big-endian record at a 2-byte aligned address (KmersLoadWorker.java:24-27)
+    const uint16_t *p = reinterpret_cast<const uint16_t *>(rec);
+    unsigned long long kk = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const uint32_t h = p[j]; kk = (kk << 16) | (uint32_t)__byte_perm(h, 0, 0x4401); }
+    key = kk;
+    const uint32_t h = p[4];
+    freq = (int)(short)__byte_perm(h, 0, 0x4401);
+}
+
+// KmersPresenceWorker.processKmer (src/io/IOUtils.java:583-587)
+__global__ void __launch_bounds__(256)
+fc_records_kernel(const uint8_t *__restrict__ recs, uint64_t n, FcSlot *__restrict__ tab, uint64_t cap) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long key; int freq;
+        load_record(recs + 10 * t, key, freq);
+        fc_accumulate(tab, cap, key, (long long)freq);
+    }
+}
+
+// Kmers2HMWorker.processKmer with threshold 0 (src/io/IOUtils.java:249-257): selected[key] =
+// sat_add16(selected[key], freq) for freq > 0.  The selected set reuses Slot.
+__global__ void __launch_bounds__(256)
+fc_selected_kernel(const uint8_t *__restrict__ recs, uint64_t n, Slot *__restrict__ tab, uint64_t cap,
+                   Counters *__restrict__ ctr) {
+    uint32_t claimed = 0;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long key; int freq;
+        load_record(recs + 10 * t, key, freq);
+        if (freq > 0) claimed += table_upsert_n(tab, cap, key, (uint32_t)freq) ? 1u : 0u;
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+}
+
+__device__ __forceinline__ long long fc_lookup(const FcSlot *__restrict__ tab, uint64_t cap, unsigned long long key) {
+    uint64_t i = home_slot(key, cap);
+    for (;;) {
+        const ulonglong2 s = ld_cg_u64x2(&tab[i]);
+        if (s.x == key) return (long long)s.y;
+        if (s.x == EMPTY_KEY) return 0;                     // getWithZero
+        if (++i == cap) i = 0;
+    }
+}
+__device__ __forceinline__ uint32_t sel_lookup(const Slot *__restrict__ tab, uint64_t cap, unsigned long long key) {
+    uint64_t i = home_slot(key, cap);
+    for (;;) {
+        const ulonglong2 s = ld_cg_u64x2(&tab[i]);
+        if (s.x == key) return (uint32_t)s.y;
+        if (s.x == EMPTY_KEY) return 0;
+        if (++i == cap) i = 0;
+    }
+}
+
+// buildAndPrintVector inner loop (src/tools/FeaturesCalculatorMain.java:186-204): one warp per
+// component, lanes stride over its keys, int64 sums (wrapping like Java long).
+__global__ void __launch_bounds__(256)
+fc_features_kernel(const unsigned long long *__restrict__ comp_keys, const uint64_t *__restrict__ comp_off,
+                   uint32_t n_comp, const FcSlot *__restrict__ tab, uint64_t cap,
+                   const Slot *__restrict__ sel, uint64_t sel_cap, long long threshold,
+                   long long *__restrict__ vec, unsigned long long *__restrict__ found, unsigned long long *__restrict__ cnt) {
+    const uint32_t warps_per_block = blockDim.x >> 5;
+    for (uint32_t c = blockIdx.x * warps_per_block + (threadIdx.x >> 5); c < n_comp; c += gridDim.x * warps_per_block) {
+        unsigned long long sum = 0, f = 0, n = 0;
+        for (uint64_t i = comp_off[c] + lane_id(); i < comp_off[c + 1]; i += 32) {
+            const unsigned long long key = comp_keys[i];
+            if (sel == nullptr || sel_lookup(sel, sel_cap, key) > 0) {
+                const long long v = fc_lookup(tab, cap, key);
+                if (v > threshold) { sum += (unsigned long long)v; f++; }
+                n++;
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            f += __shfl_xor_sync(0xffffffffu, f, o);
+            n += __shfl_xor_sync(0xffffffffu, n, o);
+        }
+        if (lane_id() == 0) { vec[c] = (long long)sum; found[c] = f; cnt[c] = n; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// GUPS-style microbenchmark: random 32-byte-sector read-modify-write over a big table.
+// mode 0: one red.add per update; mode 1: dependent load + red.add (the shape of an upsert).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gups_kernel(unsigned long long *__restrict__ tab, uint64_t n_sectors, uint64_t n_updates, uint64_t seed, int mode) {
+    unsigned long long sink = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_updates; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = mulhi64(mix64(i + seed), n_sectors);
+        unsigned long long *p = tab + 4 * s;
+        if (mode == 1) {
+            const ulonglong2 v = ld_cg_u64x2(p);
+            if (v.x != 0x123456789ULL) atomicAdd((unsigned int *)(p + 1), 1u); else sink += v.y;
+        } else {
+            atomicAdd((unsigned int *)(p + 1), 1u);
+        }
+    }
+    if (sink == 0xdeadbeefULL) tab[0] = sink;
+}
+
+}  // namespace mfkc

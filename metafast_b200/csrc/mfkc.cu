@@ -1,0 +1,1184 @@
+// mfkc.cu -- context management and the C ABI (include/mfkc.h) over the sm_100a kernels.
+// Device work only; the host-side parser / writers live in host_io.cpp.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mfkc.h"
+#include "kernels.cuh"
+#include "radix_sort.cuh"
+#include "synth.h"
+
+using namespace mfkc;
+
+// ------------------------------------------------------------------------------------------
+// profiling slots
+// ------------------------------------------------------------------------------------------
+enum ProfSlot {
+    P_MARK = 0, P_EXTRACT_COUNT, P_EXTRACT_BUCKET, P_COUNT_KEYS, P_REHASH, P_CLEAR, P_HIST, P_COMPACT,
+    P_SORT, P_RECORDS, P_RLE, P_FC_BUILD, P_FC_RECORDS, P_FC_READS, P_FC_FEATURES, P_GUPS, P_SYNTH, P_NSLOTS
+};
+static const char *kProfNames[P_NSLOTS] = {
+    "mark_read_ends", "extract_count", "extract_bucket", "count_keys", "rehash", "table_clear", "table_hist",
+    "table_compact", "radix_sort", "records", "rle", "fc_build", "fc_records", "fc_reads", "fc_features",
+    "gups", "synth"};
+
+struct PendingTiming { int slot; cudaEvent_t a, b; };
+
+struct Staging {
+    uint8_t *d_bases = nullptr; size_t cap_bases = 0;
+    uint64_t *d_offsets = nullptr; size_t cap_offsets = 0;
+    uint32_t *d_flags = nullptr; size_t cap_flags = 0;      // in u32 words
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_done = nullptr;
+    unsigned long long *h_snap = nullptr;                    // pinned snapshot of Counters::distinct
+    bool pending = false;
+    uint64_t kmers_submitted_at_end = 0;                     // cumulative upper bound when this batch was queued
+};
+
+struct mfkc_ctx {
+    mfkc_cfg cfg{};
+    int device = 0, sm_count = 148;
+    std::string err;
+    Staging st[2];                     // copy streams + staging buffers (double-buffered H2D)
+    cudaStream_t compute = nullptr;    // every kernel runs here, in submission order
+    int next_buf = 0;
+
+    // hash variant
+    Slot *tab = nullptr; uint64_t cap = 0;
+    uint64_t distinct_ub = 0;          // host-side upper bound of occupied slots
+    uint64_t kmers_ub_total = 0;       // cumulative upper bound of submitted k-mer instances
+    uint64_t max_table_bytes = 0;
+
+    // sort variant
+    unsigned long long *sv_keys = nullptr; uint64_t sv_cap = 0, sv_ub = 0;
+    unsigned long long *svs_keys = nullptr; uint32_t *svs_counts = nullptr; uint64_t svs_n = 0;   // compacted state
+    unsigned long long *d_bucket_cursor = nullptr; uint64_t *d_bucket_base = nullptr;             // <= 64 shards
+    uint64_t *h_bucket = nullptr;                                                                  // pinned
+
+    Counters *d_ctr = nullptr; Counters *h_ctr = nullptr;
+    unsigned long long *d_hist = nullptr; uint64_t *h_hist = nullptr; bool hist_valid = false;
+    bool dirty = false;                // work submitted since the last flush
+
+    // emit
+    unsigned long long *em_keys = nullptr; uint16_t *em_counts = nullptr; uint64_t em_n = 0;
+    uint8_t *em_records = nullptr; uint64_t em_cursor = 0; bool em_valid = false;
+
+    // features-calculator
+    FcSlot *fc_tab = nullptr; uint64_t fc_cap = 0;
+    unsigned long long *fc_keys = nullptr; uint64_t *fc_off = nullptr; uint32_t fc_ncomp = 0; uint64_t fc_nkeys = 0;
+    Slot *fc_sel = nullptr; uint64_t fc_sel_cap = 0; uint64_t fc_sel_n = 0;
+    Counters *d_fc_ctr = nullptr;
+
+    // synth
+    mfkc_synth_tables *d_synth = nullptr;
+
+    // timing / profile
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool profiling = false;
+    double prof_ms[P_NSLOTS] = {0};
+    uint64_t prof_launches[P_NSLOTS] = {0};
+    std::vector<PendingTiming> pending;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<void *> pinned;
+};
+
+static thread_local std::string g_create_err;
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            char b__[512];                                                                        \
+            snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            ctx->err = b__;                                                                       \
+            return e__ == cudaErrorMemoryAllocation ? MFKC_E_OOM : MFKC_E_CUDA;                   \
+        }                                                                                         \
+    } while (0)
+
+#define TRY(expr) do { int r__ = (expr); if (r__ != MFKC_OK) return r__; } while (0)
+
+static int fail(mfkc_ctx *ctx, int code, const char *msg) { if (ctx) ctx->err = msg; return code; }
+
+static cudaEvent_t get_event(mfkc_ctx *ctx) {
+    if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {           // counts the launch; brackets it with events when profiling is on
+    mfkc_ctx *ctx; int slot; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(mfkc_ctx *c, int sl, cudaStream_t st) : ctx(c), slot(sl), s(st) {
+        ctx->prof_launches[slot]++;
+        if (ctx->profiling) { a = get_event(ctx); b = get_event(ctx); cudaEventRecord(a, s); }
+    }
+    ~ProfScope() { if (a) { cudaEventRecord(b, s); ctx->pending.push_back({slot, a, b}); } }
+};
+static void drain_timings(mfkc_ctx *ctx) {
+    for (auto &p : ctx->pending) {
+        float ms = 0; cudaEventSynchronize(p.b);
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) ctx->prof_ms[p.slot] += ms;
+        ctx->ev_pool.push_back(p.a); ctx->ev_pool.push_back(p.b);
+    }
+    ctx->pending.clear();
+}
+
+static int grid_for(const mfkc_ctx *ctx, uint64_t work_items, int threads, int blocks_per_sm = 8) {
+    uint64_t blocks = (work_items + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)ctx->sm_count * blocks_per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+static int sync_all(mfkc_ctx *ctx) {
+    CU_TRY(cudaStreamSynchronize(ctx->st[0].stream));
+    CU_TRY(cudaStreamSynchronize(ctx->st[1].stream));
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
+    ctx->st[0].pending = ctx->st[1].pending = false;
+    return MFKC_OK;
+}
+
+static int read_counters(mfkc_ctx *ctx) {      // requires streams idle
+    CU_TRY(cudaMemcpy(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost));
+    return MFKC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------
+extern "C" int mfkc_abi_version(void) { return MFKC_ABI_VERSION; }
+
+extern "C" int mfkc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char *mfkc_last_error(const mfkc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+static int table_alloc(mfkc_ctx *ctx, uint64_t slots, Slot **out) {
+    Slot *t = nullptr;
+    cudaError_t e = cudaMalloc(&t, slots * sizeof(Slot));
+    if (e != cudaSuccess) { cudaGetLastError(); ctx->err = "cannot allocate k-mer table"; return MFKC_E_OOM; }
+    {
+        ProfScope ps(ctx, P_CLEAR, ctx->compute);
+        table_clear_kernel<<<grid_for(ctx, slots, 256, 16), 256, 0, ctx->compute>>>(t, slots);
+    }
+    CU_TRY(cudaGetLastError());
+    *out = t;
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
+    if (!cfg || !out) { g_create_err = "null argument"; return MFKC_E_BADARG; }
+    if (cfg->struct_size != sizeof(mfkc_cfg)) { g_create_err = "mfkc_cfg.struct_size mismatch"; return MFKC_E_BADARG; }
+    if (cfg->k <= 0) { g_create_err = "The size of k-mer must be at least 1."; return MFKC_E_BADARG; }        // KmersCounterMain.java:66-69
+    if (cfg->k > 31) { g_create_err = "The size of k-mer must be no more than 31."; return MFKC_E_BADARG; }   // KmersCounterMain.java:70-73
+    if (cfg->variant != MFKC_VARIANT_HASH && cfg->variant != MFKC_VARIANT_SORT) { g_create_err = "unknown variant"; return MFKC_E_BADARG; }
+    if (cfg->n_shards > 64 || (cfg->n_shards > 1 && (cfg->shard_id < 0 || cfg->shard_id >= cfg->n_shards))) {
+        g_create_err = "bad shard configuration"; return MFKC_E_BADARG;
+    }
+    int n_dev = mfkc_device_count();
+    if (n_dev <= 0) { g_create_err = "no CUDA device available (libmfkc has no CPU fallback)"; return MFKC_E_CUDA; }
+    if (cfg->device < 0 || cfg->device >= n_dev) { g_create_err = "bad device ordinal"; return MFKC_E_BADARG; }
+
+    mfkc_ctx *ctx = new mfkc_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    auto bail = [&](int code) { g_create_err = ctx->err; mfkc_destroy(ctx); return code; };
+#define CR_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return bail(MFKC_E_CUDA); } } while (0)
+    CR_TRY(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CR_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < 2; i++) {
+        CR_TRY(cudaStreamCreateWithFlags(&ctx->st[i].stream, cudaStreamNonBlocking));
+        CR_TRY(cudaEventCreateWithFlags(&ctx->st[i].ev_copy, cudaEventDisableTiming));
+        CR_TRY(cudaEventCreateWithFlags(&ctx->st[i].ev_done, cudaEventDisableTiming));
+        CR_TRY(cudaMallocHost(&ctx->st[i].h_snap, sizeof(unsigned long long)));
+    }
+    CR_TRY(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    CR_TRY(cudaEventCreate(&ctx->t0));
+    CR_TRY(cudaEventCreate(&ctx->t1));
+    CR_TRY(cudaMalloc(&ctx->d_ctr, sizeof(Counters)));
+    CR_TRY(cudaMemset(ctx->d_ctr, 0, sizeof(Counters)));
+    CR_TRY(cudaMalloc(&ctx->d_fc_ctr, sizeof(Counters)));
+    CR_TRY(cudaMemset(ctx->d_fc_ctr, 0, sizeof(Counters)));
+    CR_TRY(cudaMallocHost(&ctx->h_ctr, sizeof(Counters)));
+    CR_TRY(cudaMalloc(&ctx->d_hist, MFKC_HIST_BINS * sizeof(unsigned long long)));
+    CR_TRY(cudaMallocHost(&ctx->h_hist, MFKC_HIST_BINS * sizeof(uint64_t)));
+    CR_TRY(cudaMalloc(&ctx->d_bucket_cursor, 64 * sizeof(unsigned long long)));
+    CR_TRY(cudaMalloc(&ctx->d_bucket_base, 64 * sizeof(uint64_t)));
+    CR_TRY(cudaMallocHost(&ctx->h_bucket, 64 * sizeof(uint64_t)));
+    CR_TRY(cudaMemset(ctx->d_bucket_cursor, 0, 64 * sizeof(unsigned long long)));
+    CR_TRY(cudaMemset(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t)));
+
+    size_t free_b = 0, total_b = 0;
+    CR_TRY(cudaMemGetInfo(&free_b, &total_b));
+    ctx->max_table_bytes = cfg->max_table_bytes ? cfg->max_table_bytes : (uint64_t)(free_b * 0.8);
+
+    if (cfg->variant == MFKC_VARIANT_HASH) {
+        uint64_t slots = cfg->table_slots;
+        if (!slots && cfg->expected_distinct) slots = cfg->expected_distinct * 2;      // load 0.5
+        if (!slots) slots = 1ull << 22;                                                // 64 MiB, grows on demand
+        if (slots < 1024) slots = 1024;
+        if (slots * sizeof(Slot) > ctx->max_table_bytes) slots = ctx->max_table_bytes / sizeof(Slot);
+        int r = table_alloc(ctx, slots, &ctx->tab);
+        if (r != MFKC_OK) return bail(r);
+        ctx->cap = slots;
+    }
+    CR_TRY(cudaDeviceSynchronize());
+#undef CR_TRY
+    *out = ctx;
+    return MFKC_OK;
+}
+
+static void free_emit(mfkc_ctx *ctx) {
+    cudaFree(ctx->em_keys); cudaFree(ctx->em_counts); cudaFree(ctx->em_records);
+    ctx->em_keys = nullptr; ctx->em_counts = nullptr; ctx->em_records = nullptr;
+    ctx->em_n = 0; ctx->em_cursor = 0; ctx->em_valid = false;
+}
+
+extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+        Staging &s = ctx->st[i];
+        cudaFree(s.d_bases); cudaFree(s.d_offsets); cudaFree(s.d_flags);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.ev_copy) cudaEventDestroy(s.ev_copy);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+        if (s.h_snap) cudaFreeHost(s.h_snap);
+    }
+    if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    free_emit(ctx);
+    cudaFree(ctx->tab); cudaFree(ctx->sv_keys); cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts);
+    cudaFree(ctx->d_bucket_cursor); cudaFree(ctx->d_bucket_base);
+    if (ctx->h_bucket) cudaFreeHost(ctx->h_bucket);
+    cudaFree(ctx->d_ctr); cudaFree(ctx->d_fc_ctr); cudaFree(ctx->d_hist);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
+    cudaFree(ctx->fc_tab); cudaFree(ctx->fc_keys); cudaFree(ctx->fc_off); cudaFree(ctx->fc_sel);
+    cudaFree(ctx->d_synth);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    for (void *p : ctx->pinned) cudaFreeHost(p);
+    delete ctx;
+}
+
+extern "C" int mfkc_reset(mfkc_ctx *ctx) {
+    if (!ctx) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(sync_all(ctx));
+    if (ctx->tab) {
+        ProfScope ps(ctx, P_CLEAR, ctx->compute);
+        table_clear_kernel<<<grid_for(ctx, ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap);
+    }
+    CU_TRY(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->compute));
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
+    ctx->distinct_ub = 0; ctx->kmers_ub_total = 0; ctx->sv_ub = 0; ctx->svs_n = 0;
+    cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts); ctx->svs_keys = nullptr; ctx->svs_counts = nullptr;
+    ctx->hist_valid = false; ctx->dirty = false;
+    free_emit(ctx);
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_pinned_alloc(mfkc_ctx *ctx, size_t bytes, void **host_ptr) {
+    if (!ctx || !host_ptr) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    CU_TRY(cudaMallocHost(&p, bytes ? bytes : 1));
+    ctx->pinned.push_back(p);
+    *host_ptr = p;
+    return MFKC_OK;
+}
+extern "C" int mfkc_pinned_free(mfkc_ctx *ctx, void *host_ptr) {
+    if (!ctx) return MFKC_E_BADARG;
+    auto it = std::find(ctx->pinned.begin(), ctx->pinned.end(), host_ptr);
+    if (it == ctx->pinned.end()) return fail(ctx, MFKC_E_BADARG, "pointer was not allocated by mfkc_pinned_alloc");
+    ctx->pinned.erase(it);
+    CU_TRY(cudaFreeHost(host_ptr));
+    return MFKC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// table growth
+// ------------------------------------------------------------------------------------------
+static constexpr double kMaxLoad = 0.60;     // never exceeded: checked against an upper bound before each batch
+static constexpr double kGrowLoad = 0.30;    // load right after growing
+
+static void poll_snapshots(mfkc_ctx *ctx) {
+    for (int i = 0; i < 2; i++) {
+        Staging &s = ctx->st[i];
+        if (s.pending && cudaEventQuery(s.ev_done) == cudaSuccess) {
+            s.pending = false;
+            const uint64_t cand = *s.h_snap + (ctx->kmers_ub_total - s.kmers_submitted_at_end);
+            if (cand < ctx->distinct_ub) ctx->distinct_ub = cand;
+        }
+    }
+}
+
+static int grow_table(mfkc_ctx *ctx, uint64_t need_slots) {
+    uint64_t new_cap = std::max<uint64_t>(ctx->cap * 2, need_slots);
+    const uint64_t limit = ctx->max_table_bytes / sizeof(Slot);
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t fit = (uint64_t)(free_b * 0.95) / sizeof(Slot);          // old table stays alive during the rehash
+    if (new_cap > limit) new_cap = limit;
+    if (new_cap > fit) new_cap = fit;
+    if (new_cap <= ctx->cap) return fail(ctx, MFKC_E_TABLE_FULL, "k-mer table cannot grow: device memory exhausted");
+    Slot *nt = nullptr;
+    TRY(table_alloc(ctx, new_cap, &nt));
+    {
+        ProfScope ps(ctx, P_REHASH, ctx->compute);
+        rehash_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap, nt, new_cap);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
+    CU_TRY(cudaFree(ctx->tab));
+    ctx->tab = nt; ctx->cap = new_cap;
+    return MFKC_OK;
+}
+
+// Guarantee that `add` more upserts cannot push the load above kMaxLoad.
+static int reserve_slots(mfkc_ctx *ctx, uint64_t add) {
+    poll_snapshots(ctx);
+    if ((double)(ctx->distinct_ub + add) <= kMaxLoad * (double)ctx->cap) { ctx->distinct_ub += add; return MFKC_OK; }
+    TRY(sync_all(ctx));
+    TRY(read_counters(ctx));
+    ctx->distinct_ub = ctx->h_ctr->distinct;
+    if ((double)(ctx->distinct_ub + add) > kMaxLoad * (double)ctx->cap) {
+        const uint64_t need = (uint64_t)((double)(ctx->distinct_ub + add) / kGrowLoad) + 1024;
+        int r = grow_table(ctx, need);
+        if (r != MFKC_OK) {
+            // a smaller step may still fit
+            if ((double)(ctx->distinct_ub + add) <= 0.9 * (double)ctx->cap) { /* tolerate a higher load */ }
+            else return r;
+        } else if ((double)(ctx->distinct_ub + add) > 0.9 * (double)ctx->cap) {
+            return fail(ctx, MFKC_E_TABLE_FULL, "k-mer table cannot grow enough for this batch");
+        }
+    }
+    ctx->distinct_ub += add;
+    return MFKC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// ingest
+// ------------------------------------------------------------------------------------------
+static int ensure_staging(mfkc_ctx *ctx, Staging &s, uint64_t n_bases, uint64_t n_offsets, bool need_bases) {
+    if (need_bases && n_bases + 64 > s.cap_bases) {
+        CU_TRY(cudaStreamSynchronize(s.stream)); CU_TRY(cudaStreamSynchronize(ctx->compute));
+        cudaFree(s.d_bases); s.d_bases = nullptr;
+        s.cap_bases = (size_t)((n_bases + 64) * 1.25) + 4096;
+        CU_TRY(cudaMalloc(&s.d_bases, s.cap_bases));
+    }
+    if (need_bases && n_offsets > s.cap_offsets) {
+        CU_TRY(cudaStreamSynchronize(s.stream)); CU_TRY(cudaStreamSynchronize(ctx->compute));
+        cudaFree(s.d_offsets); s.d_offsets = nullptr;
+        s.cap_offsets = (size_t)(n_offsets * 1.25) + 1024;
+        CU_TRY(cudaMalloc(&s.d_offsets, s.cap_offsets * sizeof(uint64_t)));
+    }
+    const size_t flag_words = (size_t)((n_bases + 31) / 32) + 4;
+    if (flag_words > s.cap_flags) {
+        CU_TRY(cudaStreamSynchronize(s.stream)); CU_TRY(cudaStreamSynchronize(ctx->compute));
+        cudaFree(s.d_flags); s.d_flags = nullptr;
+        s.cap_flags = (size_t)(flag_words * 1.25) + 1024;
+        CU_TRY(cudaMalloc(&s.d_flags, s.cap_flags * sizeof(uint32_t)));
+    }
+    return MFKC_OK;
+}
+
+// queue K0 (+ memset) for a device-resident batch on the compute stream
+static int launch_mark(mfkc_ctx *ctx, Staging &s, const uint64_t *d_offsets, uint32_t n_reads, uint64_t n_bases,
+                       int min_len, int count_stats, Counters *ctr) {
+    const size_t flag_words = (size_t)((n_bases + 31) / 32) + 4;
+    CU_TRY(cudaMemsetAsync(s.d_flags, 0, flag_words * sizeof(uint32_t), ctx->compute));
+    {
+        ProfScope ps(ctx, P_MARK, ctx->compute);
+        mark_read_ends_kernel<<<grid_for(ctx, n_reads, 256, 8), 256, 0, ctx->compute>>>(
+            d_offsets, n_reads, n_bases, ctx->cfg.k, min_len, count_stats, s.d_flags, ctr);
+    }
+    CU_TRY(cudaGetLastError());
+    return MFKC_OK;
+}
+
+static int extract_grid(const mfkc_ctx *ctx, uint64_t n_bases) {
+    const uint64_t tiles = ((n_bases + 15) / 16 + EX_THREADS - 1) / EX_THREADS;
+    return grid_for(ctx, tiles * EX_THREADS, EX_THREADS, 8);
+}
+
+static int sort_variant_reserve(mfkc_ctx *ctx, uint64_t add);
+
+// count a device-resident batch (bases/offsets already on the device, visible to the compute stream)
+static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases, const uint64_t *d_offsets,
+                              uint32_t n_reads, uint64_t n_bases) {
+    const int k = ctx->cfg.k;
+    const uint64_t kmers_ub = n_bases >= (uint64_t)k ? n_bases - k + 1 : 0;
+    if (ctx->cfg.variant == MFKC_VARIANT_HASH) TRY(reserve_slots(ctx, kmers_ub));
+    else TRY(sort_variant_reserve(ctx, kmers_ub));
+    ctx->kmers_ub_total += kmers_ub;
+    TRY(launch_mark(ctx, s, d_offsets, n_reads, n_bases, ctx->cfg.min_seq_len, 1, ctx->d_ctr));
+    if (n_bases >= (uint64_t)k) {
+        if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
+            ProfScope ps(ctx, P_EXTRACT_COUNT, ctx->compute);
+            SinkTable sink{ctx->tab, ctx->cap, ctx->d_ctr};
+            extract_kernel<SinkTable><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                d_bases, n_bases, s.d_flags, k, sink, ctx->d_ctr);
+        } else {
+            ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
+            BucketSink sink{ctx->sv_keys, ctx->d_bucket_base, &ctx->d_ctr->appended, ctx->sv_cap, 1, 0};
+            extract_bucket_kernel<0><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                d_bases, n_bases, s.d_flags, k, sink, ctx->d_ctr);
+        }
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaMemcpyAsync(s.h_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaEventRecord(s.ev_done, ctx->compute));
+    s.pending = true;
+    s.kmers_submitted_at_end = ctx->kmers_ub_total;
+    ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_submit_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads) {
+    if (!ctx || (!bases && n_reads) || !offsets) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (n_reads == 0) return MFKC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const uint64_t base0 = offsets[0];
+    if (offsets[n_reads] < base0) return fail(ctx, MFKC_E_BADARG, "offsets must be non-decreasing");
+    const uint64_t n_bases = offsets[n_reads] - base0;
+    Staging &s = ctx->st[ctx->next_buf];
+    ctx->next_buf ^= 1;
+    TRY(ensure_staging(ctx, s, n_bases, (uint64_t)n_reads + 1, true));
+    // the staging buffer is free once the kernels of the batch that used it last are done
+    CU_TRY(cudaStreamWaitEvent(s.stream, s.ev_done, 0));
+    CU_TRY(cudaMemcpyAsync(s.d_bases, bases + base0, n_bases, cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(cudaMemcpyAsync(s.d_offsets, offsets, ((size_t)n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(cudaEventRecord(s.ev_copy, s.stream));
+    CU_TRY(cudaStreamWaitEvent(ctx->compute, s.ev_copy, 0));
+    int r = count_batch_device(ctx, s, s.d_bases, s.d_offsets, n_reads, n_bases);
+    // the caller may refill its buffers once the copies are done
+    CU_TRY(cudaEventSynchronize(s.ev_copy));
+    return r;
+}
+
+extern "C" int mfkc_submit_reads_device(mfkc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets,
+                                        uint32_t n_reads, uint64_t n_bases) {
+    if (!ctx || !d_bases || !d_offsets) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (n_reads == 0) return MFKC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    Staging &s = ctx->st[ctx->next_buf];
+    ctx->next_buf ^= 1;
+    TRY(ensure_staging(ctx, s, n_bases, 0, false));
+    return count_batch_device(ctx, s, d_bases, d_offsets, n_reads, n_bases);
+}
+
+extern "C" int mfkc_flush(mfkc_ctx *ctx) {
+    if (!ctx) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(sync_all(ctx));
+    TRY(read_counters(ctx));
+    if (ctx->cfg.variant == MFKC_VARIANT_HASH) ctx->distinct_ub = ctx->h_ctr->distinct;
+    ctx->dirty = false;
+    if (ctx->h_ctr->bad_chars) return fail(ctx, MFKC_E_FORMAT, "Incorrect nucleotide char in submitted reads (only AaCcGgTt are accepted)");
+    if (ctx->h_ctr->overflow) return fail(ctx, MFKC_E_STATE, "internal key buffer overflow");
+    return MFKC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// radix sort driver (keys with optional payload), ping-pong between (a) and (b); result in *a
+// ------------------------------------------------------------------------------------------
+template <typename V, bool HAS_V>
+static int radix_sort(mfkc_ctx *ctx, cudaStream_t st, unsigned long long *&a, unsigned long long *&b, V *&va, V *&vb,
+                      uint64_t n, int key_bits) {
+    if (n < 2) return MFKC_OK;
+    const RadixPlan plan = radix_plan(n);
+    uint32_t *hist = nullptr; unsigned long long *offs = nullptr, *chunk = nullptr; uint32_t *d_triv = nullptr;
+    CU_TRY(cudaMalloc(&hist, plan.hist_bytes));
+    CU_TRY(cudaMalloc(&offs, plan.offs_bytes));
+    CU_TRY(cudaMalloc(&chunk, plan.chunk_bytes));
+    CU_TRY(cudaMalloc(&d_triv, sizeof(uint32_t)));
+    const int grid = (int)std::min<uint64_t>((plan.n_parts + RS_WARPS - 1) / RS_WARPS, (uint64_t)ctx->sm_count * 8);
+    int rc = MFKC_OK;
+    ProfScope ps(ctx, P_SORT, st);
+    ctx->prof_launches[P_SORT]--;            // counted per kernel below
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        rs_hist_kernel<<<grid, RS_WARPS * 32, 0, st>>>(a, n, shift, plan.n_parts, hist);
+        rs_chunk_kernel<<<plan.n_chunks, RS_RADIX, 0, st>>>(hist, plan.n_parts, chunk);
+        rs_base_kernel<<<1, RS_RADIX, 0, st>>>(chunk, plan.n_chunks, n, d_triv);
+        uint32_t triv = 0;
+        if (cudaMemcpyAsync(&triv, d_triv, sizeof triv, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { rc = MFKC_E_CUDA; break; }
+        ctx->prof_launches[P_SORT] += triv ? 3 : 5;
+        if (triv) continue;                                   // every key has the same digit: order unchanged
+        rs_offsets_kernel<<<plan.n_chunks, RS_RADIX, 0, st>>>(hist, plan.n_parts, chunk, offs);
+        rs_scatter_kernel<V, HAS_V><<<grid, RS_WARPS * 32, 0, st>>>(a, va, n, shift, plan.n_parts, offs, b, vb);
+        std::swap(a, b);
+        std::swap(va, vb);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(hist); cudaFree(offs); cudaFree(chunk); cudaFree(d_triv);
+    if (e != cudaSuccess) { ctx->err = std::string("radix sort: ") + cudaGetErrorString(e); return MFKC_E_CUDA; }
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// sort variant: keys -> sorted run-length (key,count) state
+// ------------------------------------------------------------------------------------------
+// RLE of a sorted key array (optionally weighted): returns new arrays
+static int rle_sorted(mfkc_ctx *ctx, cudaStream_t st, const unsigned long long *keys, const uint32_t *weights, uint64_t n,
+                      unsigned long long **out_keys, uint32_t **out_counts, uint64_t *out_n) {
+    *out_keys = nullptr; *out_counts = nullptr; *out_n = 0;
+    if (n == 0) return MFKC_OK;
+    const int grid = grid_for(ctx, n, 256, 8);
+    unsigned long long *d_blk = nullptr;
+    CU_TRY(cudaMalloc(&d_blk, (size_t)grid * sizeof(unsigned long long)));
+    ProfScope ps(ctx, P_RLE, st);
+    rle_mark_kernel<<<grid, 256, 0, st>>>(keys, n, d_blk);
+    std::vector<unsigned long long> h(grid);
+    CU_TRY(cudaMemcpyAsync(h.data(), d_blk, (size_t)grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    unsigned long long run = 0;
+    for (int i = 0; i < grid; i++) { const unsigned long long c = h[i]; h[i] = run; run += c; }
+    CU_TRY(cudaMemcpyAsync(d_blk, h.data(), (size_t)grid * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    unsigned long long *ok = nullptr; uint32_t *oc = nullptr;
+    CU_TRY(cudaMalloc(&ok, (size_t)run * sizeof(unsigned long long)));
+    CU_TRY(cudaMalloc(&oc, (size_t)run * sizeof(uint32_t)));
+    rle_write_kernel<<<grid, 256, 0, st>>>(keys, weights, n, d_blk, ok, oc);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_blk);
+    *out_keys = ok; *out_counts = oc; *out_n = run;
+    return MFKC_OK;
+}
+
+// fold the raw key buffer into the sorted (key,count) state
+static int sort_variant_compact(mfkc_ctx *ctx) {
+    TRY(sync_all(ctx));
+    TRY(read_counters(ctx));
+    uint64_t n = ctx->h_ctr->appended;
+    if (n > ctx->sv_cap) n = ctx->sv_cap;
+    cudaStream_t st = ctx->compute;
+    const int key_bits = 2 * ctx->cfg.k;
+    if (n) {
+        unsigned long long *alt = nullptr; uint32_t *dummy_a = nullptr, *dummy_b = nullptr;
+        CU_TRY(cudaMalloc(&alt, (size_t)n * sizeof(unsigned long long)));
+        unsigned long long *a = ctx->sv_keys, *b = alt;
+        int r = radix_sort<uint32_t, false>(ctx, st, a, b, dummy_a, dummy_b, n, key_bits);
+        unsigned long long *rk = nullptr; uint32_t *rc = nullptr; uint64_t rn = 0;
+        if (r == MFKC_OK) r = rle_sorted(ctx, st, a, nullptr, n, &rk, &rc, &rn);
+        cudaFree(alt);      // ctx->sv_keys itself (the larger allocation) is kept for the next round
+        if (r != MFKC_OK) return r;
+        if (ctx->svs_n == 0) {
+            cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts);
+            ctx->svs_keys = rk; ctx->svs_counts = rc; ctx->svs_n = rn;
+        } else {
+            // merge: concatenate, sort pairs by key, weighted RLE
+            const uint64_t m = ctx->svs_n + rn;
+            unsigned long long *ck = nullptr, *ck2 = nullptr; uint32_t *cc = nullptr, *cc2 = nullptr;
+            CU_TRY(cudaMalloc(&ck, (size_t)m * 8)); CU_TRY(cudaMalloc(&ck2, (size_t)m * 8));
+            CU_TRY(cudaMalloc(&cc, (size_t)m * 4)); CU_TRY(cudaMalloc(&cc2, (size_t)m * 4));
+            CU_TRY(cudaMemcpyAsync(ck, ctx->svs_keys, ctx->svs_n * 8, cudaMemcpyDeviceToDevice, st));
+            CU_TRY(cudaMemcpyAsync(ck + ctx->svs_n, rk, rn * 8, cudaMemcpyDeviceToDevice, st));
+            CU_TRY(cudaMemcpyAsync(cc, ctx->svs_counts, ctx->svs_n * 4, cudaMemcpyDeviceToDevice, st));
+            CU_TRY(cudaMemcpyAsync(cc + ctx->svs_n, rc, rn * 4, cudaMemcpyDeviceToDevice, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            cudaFree(rk); cudaFree(rc); cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts);
+            ctx->svs_keys = nullptr; ctx->svs_counts = nullptr; ctx->svs_n = 0;
+            r = radix_sort<uint32_t, true>(ctx, st, ck, ck2, cc, cc2, m, key_bits);
+            if (r == MFKC_OK) r = rle_sorted(ctx, st, ck, cc, m, &ctx->svs_keys, &ctx->svs_counts, &ctx->svs_n);
+            cudaFree(ck); cudaFree(ck2); cudaFree(cc); cudaFree(cc2);
+            if (r != MFKC_OK) return r;
+        }
+    }
+    CU_TRY(cudaMemsetAsync(&ctx->d_ctr->appended, 0, sizeof(unsigned long long), st));
+    CU_TRY(cudaStreamSynchronize(st));
+    ctx->sv_ub = 0;
+    return MFKC_OK;
+}
+
+static int sort_variant_reserve(mfkc_ctx *ctx, uint64_t add) {
+    if (ctx->sv_ub + add <= ctx->sv_cap) { ctx->sv_ub += add; return MFKC_OK; }
+    // tighten the bound with the real cursor, then grow or fold
+    TRY(sync_all(ctx));
+    TRY(read_counters(ctx));
+    ctx->sv_ub = ctx->h_ctr->appended;
+    if (ctx->sv_ub + add > ctx->sv_cap) {
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t want = std::max<uint64_t>((ctx->sv_ub + add) * 2, 1ull << 20);
+        // sorting needs a second buffer of the same size plus ~10 % workspace
+        const bool can_grow = (double)want * 8.0 * 2.3 + (double)ctx->sv_cap * 8.0 < (double)free_b + (double)ctx->sv_cap * 8.0 &&
+                              (double)want * 8.0 * 2.3 < (double)total_b * 0.8;
+        if (can_grow) {
+            unsigned long long *nk = nullptr;
+            CU_TRY(cudaMalloc(&nk, (size_t)want * 8));
+            if (ctx->sv_ub) CU_TRY(cudaMemcpy(nk, ctx->sv_keys, (size_t)ctx->sv_ub * 8, cudaMemcpyDeviceToDevice));
+            cudaFree(ctx->sv_keys);
+            ctx->sv_keys = nk; ctx->sv_cap = want;
+        } else {
+            TRY(sort_variant_compact(ctx));
+            if (add > ctx->sv_cap) return fail(ctx, MFKC_E_OOM, "batch larger than the sort variant's key buffer");
+        }
+    }
+    ctx->sv_ub += add;
+    return MFKC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------
+static int finalize_counts(mfkc_ctx *ctx) {       // everything submitted is reflected in table / sorted state
+    if (ctx->dirty) TRY(mfkc_flush(ctx));
+    if (ctx->cfg.variant == MFKC_VARIANT_SORT) {
+        TRY(read_counters(ctx));
+        if (ctx->h_ctr->appended) TRY(sort_variant_compact(ctx));
+    }
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_stats(mfkc_ctx *ctx, uint64_t stats[6]) {
+    if (!ctx || !stats) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(finalize_counts(ctx));
+    TRY(sync_all(ctx));
+    TRY(read_counters(ctx));
+    stats[0] = ctx->cfg.variant == MFKC_VARIANT_HASH ? ctx->h_ctr->distinct : ctx->svs_n;
+    stats[1] = ctx->h_ctr->kmers;
+    stats[2] = ctx->h_ctr->total_seq; stats[3] = ctx->h_ctr->good_seq;
+    stats[4] = ctx->h_ctr->total_len; stats[5] = ctx->h_ctr->good_len;
+    return MFKC_OK;
+}
+
+static int compute_hist(mfkc_ctx *ctx) {
+    if (ctx->hist_valid) return MFKC_OK;
+    TRY(finalize_counts(ctx));
+    cudaStream_t st = ctx->compute;
+    CU_TRY(cudaMemsetAsync(ctx->d_hist, 0, MFKC_HIST_BINS * sizeof(unsigned long long), st));
+    {
+        ProfScope ps(ctx, P_HIST, st);
+        if (ctx->cfg.variant == MFKC_VARIANT_HASH)
+            table_hist_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, st>>>(ctx->tab, ctx->cap, ctx->d_hist);
+        else if (ctx->svs_n)
+            pairs_hist_kernel<<<grid_for(ctx, ctx->svs_n, 256, 8), 256, 0, st>>>(ctx->svs_counts, ctx->svs_n, ctx->d_hist);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, MFKC_HIST_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    ctx->hist_valid = true;
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_histogram(mfkc_ctx *ctx, uint64_t hist[MFKC_HIST_BINS]) {
+    if (!ctx || !hist) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(compute_hist(ctx));
+    memcpy(hist, ctx->h_hist, MFKC_HIST_BINS * sizeof(uint64_t));
+    return MFKC_OK;
+}
+
+// order-preserving filter of the sorted state (sort variant): counts > threshold
+__global__ void __launch_bounds__(256)
+select_mark_kernel(const uint32_t *__restrict__ counts, uint64_t n, uint32_t threshold, unsigned long long *__restrict__ blk) {
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = per_block * blockIdx.x;
+    const uint64_t hi = lo + per_block < n ? lo + per_block : n;
+    uint32_t local = 0;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) local += counts[i] > threshold ? 1u : 0u;
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) blk[blockIdx.x] = s_cnt;
+}
+__global__ void __launch_bounds__(256)
+select_write_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ counts, uint64_t n,
+                    uint32_t threshold, const unsigned long long *__restrict__ blk_base,
+                    unsigned long long *__restrict__ out_keys, uint16_t *__restrict__ out_counts) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base;
+    const uint64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = per_block * blockIdx.x;
+    const uint64_t hi = lo + per_block < n ? lo + per_block : n;
+    if (threadIdx.x == 0) s_base = blk_base[blockIdx.x];
+    __syncthreads();
+    for (uint64_t start = lo; start < hi; start += blockDim.x) {
+        const uint64_t i = start + threadIdx.x;
+        const uint32_t c = i < hi ? counts[i] : 0u;
+        const bool good = i < hi && c > threshold;
+        const uint32_t m = __ballot_sync(0xffffffffu, good);
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = __popc(m);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int wv = 0; wv < 8; wv++) { const uint32_t cc = s_warp[wv]; if (wv < (int)(threadIdx.x >> 5)) before += cc; total += cc; }
+        if (good) {
+            const uint64_t at = s_base + before + __popc(m & mfkc::lanemask_lt());
+            out_keys[at] = keys[i];
+            out_counts[at] = (uint16_t)(c < MAX_COUNT ? c : MAX_COUNT);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+}
+
+extern "C" int mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_good) {
+    if (!ctx) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(compute_hist(ctx));
+    free_emit(ctx);
+    // entries with value > threshold (src/io/IOUtils.java:61); counts are 1..32767
+    uint64_t good = 0;
+    const int64_t thr = threshold;
+    for (int c = 1; c < MFKC_HIST_BINS; c++) if ((int64_t)c > thr) good += ctx->h_hist[c];
+    const uint32_t thr_u = thr < 0 ? 0u : (uint32_t)std::min<int64_t>(thr, 0x7fffffff);
+    cudaStream_t st = ctx->compute;
+    ctx->em_n = good;
+    if (good) {
+        CU_TRY(cudaMalloc(&ctx->em_keys, (size_t)good * 8));
+        CU_TRY(cudaMalloc(&ctx->em_counts, (size_t)good * 2));
+        if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
+            unsigned long long *k2 = nullptr; uint16_t *c2 = nullptr;
+            CU_TRY(cudaMalloc(&k2, (size_t)good * 8));
+            CU_TRY(cudaMalloc(&c2, (size_t)good * 2));
+            CU_TRY(cudaMemsetAsync(&ctx->d_ctr->n_good, 0, sizeof(unsigned long long), st));
+            {
+                ProfScope ps(ctx, P_COMPACT, st);
+                table_compact_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, st>>>(
+                    ctx->tab, ctx->cap, thr < 0 ? 0u : thr_u, ctx->em_keys, ctx->em_counts, good, ctx->d_ctr);
+            }
+            CU_TRY(cudaGetLastError());
+            int r = radix_sort<uint16_t, true>(ctx, st, ctx->em_keys, k2, ctx->em_counts, c2, good, 2 * ctx->cfg.k);
+            cudaFree(k2); cudaFree(c2);
+            TRY(r);
+        } else {
+            const int grid = grid_for(ctx, ctx->svs_n, 256, 8);
+            unsigned long long *d_blk = nullptr;
+            CU_TRY(cudaMalloc(&d_blk, (size_t)grid * 8));
+            ProfScope ps(ctx, P_COMPACT, st);
+            select_mark_kernel<<<grid, 256, 0, st>>>(ctx->svs_counts, ctx->svs_n, thr_u, d_blk);
+            std::vector<unsigned long long> h(grid);
+            CU_TRY(cudaMemcpyAsync(h.data(), d_blk, (size_t)grid * 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            unsigned long long run = 0;
+            for (int i = 0; i < grid; i++) { const unsigned long long c = h[i]; h[i] = run; run += c; }
+            CU_TRY(cudaMemcpyAsync(d_blk, h.data(), (size_t)grid * 8, cudaMemcpyHostToDevice, st));
+            select_write_kernel<<<grid, 256, 0, st>>>(ctx->svs_keys, ctx->svs_counts, ctx->svs_n, thr_u, d_blk,
+                                                     ctx->em_keys, ctx->em_counts);
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaStreamSynchronize(st));
+            cudaFree(d_blk);
+            if (run != good) return fail(ctx, MFKC_E_STATE, "internal: selection count mismatch");
+        }
+        CU_TRY(cudaMalloc(&ctx->em_records, (size_t)good * 10));
+        {
+            ProfScope ps(ctx, P_RECORDS, st);
+            records_kernel<<<grid_for(ctx, good, 256, 8), 256, 0, st>>>(ctx->em_keys, ctx->em_counts, good,
+                                                                      reinterpret_cast<uint16_t *>(ctx->em_records));
+        }
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    // a negative threshold would also pass count-0 entries; the table never holds any
+    ctx->em_cursor = 0; ctx->em_valid = true;
+    if (n_good) *n_good = good;
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_emit_next(mfkc_ctx *ctx, uint8_t *out, size_t cap, size_t *written) {
+    if (!ctx || !written) return MFKC_E_BADARG;
+    if (!ctx->em_valid) return fail(ctx, MFKC_E_STATE, "mfkc_emit_next without mfkc_emit_begin");
+    CU_TRY(cudaSetDevice(ctx->device));
+    const uint64_t left = ctx->em_n - ctx->em_cursor;
+    uint64_t take = std::min<uint64_t>(left, cap / 10);
+    if (take && !out) return MFKC_E_BADARG;
+    if (take) CU_TRY(cudaMemcpy(out, ctx->em_records + ctx->em_cursor * 10, (size_t)take * 10, cudaMemcpyDeviceToHost));
+    ctx->em_cursor += take;
+    *written = (size_t)take * 10;
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_emit_device(mfkc_ctx *ctx, const uint64_t **d_keys, const uint16_t **d_counts, uint64_t *n) {
+    if (!ctx) return MFKC_E_BADARG;
+    if (!ctx->em_valid) return fail(ctx, MFKC_E_STATE, "mfkc_emit_device without mfkc_emit_begin");
+    if (d_keys) *d_keys = reinterpret_cast<const uint64_t *>(ctx->em_keys);
+    if (d_counts) *d_counts = ctx->em_counts;
+    if (n) *n = ctx->em_n;
+    return MFKC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// hash-range sharding helpers
+// ------------------------------------------------------------------------------------------
+extern "C" uint32_t mfkc_owner_shard(uint64_t key, uint32_t n_shards) { return n_shards > 1 ? owner_shard(key, n_shards) : 0u; }
+
+extern "C" int mfkc_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t n_reads,
+                                     uint64_t n_bases, uint64_t *d_keys_out, uint64_t cap_keys, uint64_t *bucket_counts) {
+    if (!ctx || !d_bases || !d_offsets || !d_keys_out || !bucket_counts) return fail(ctx, MFKC_E_BADARG, "null argument");
+    const uint32_t ns = ctx->cfg.n_shards > 1 ? (uint32_t)ctx->cfg.n_shards : 1u;
+    CU_TRY(cudaSetDevice(ctx->device));
+    Staging &s = ctx->st[0];
+    TRY(ensure_staging(ctx, s, n_bases, 0, false));
+    for (uint32_t i = 0; i < ns; i++) bucket_counts[i] = 0;
+    if (n_reads == 0) return MFKC_OK;
+    const int k = ctx->cfg.k;
+    TRY(launch_mark(ctx, s, d_offsets, n_reads, n_bases, ctx->cfg.min_seq_len, 1, ctx->d_ctr));
+    if (n_bases < (uint64_t)k) { CU_TRY(cudaStreamSynchronize(ctx->compute)); return MFKC_OK; }
+    const int grid = extract_grid(ctx, n_bases);
+    // pass 1: bucket sizes
+    CU_TRY(cudaMemsetAsync(ctx->d_bucket_cursor, 0, 64 * sizeof(unsigned long long), ctx->compute));
+    {
+        ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
+        BucketSink sink{reinterpret_cast<unsigned long long *>(d_keys_out), ctx->d_bucket_base, ctx->d_bucket_cursor, cap_keys, ns, 1};
+        extract_bucket_kernel<0><<<grid, EX_THREADS, 0, ctx->compute>>>(d_bases, n_bases, s.d_flags, k, sink, ctx->d_ctr);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(ctx->h_bucket, ctx->d_bucket_cursor, ns * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
+    uint64_t base[64], run = 0;
+    for (uint32_t i = 0; i < ns; i++) { bucket_counts[i] = ctx->h_bucket[i]; base[i] = run; run += ctx->h_bucket[i]; }
+    if (run > cap_keys) return fail(ctx, MFKC_E_BADARG, "d_keys_out too small for this batch");
+    CU_TRY(cudaMemcpyAsync(ctx->d_bucket_base, base, ns * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->compute));
+    CU_TRY(cudaMemsetAsync(ctx->d_bucket_cursor, 0, 64 * sizeof(unsigned long long), ctx->compute));
+    // pass 2: write grouped keys
+    {
+        ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
+        BucketSink sink{reinterpret_cast<unsigned long long *>(d_keys_out), ctx->d_bucket_base, ctx->d_bucket_cursor, cap_keys, ns, 0};
+        extract_bucket_kernel<0><<<grid, EX_THREADS, 0, ctx->compute>>>(d_bases, n_bases, s.d_flags, k, sink, ctx->d_ctr);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
+    // restore the sort-variant base (bucket 0 starts at 0)
+    CU_TRY(cudaMemset(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t)));
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uint64_t n) {
+    if (!ctx || (!d_keys && n)) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (ctx->cfg.variant != MFKC_VARIANT_HASH) return fail(ctx, MFKC_E_STATE, "mfkc_count_keys_device needs the hash variant");
+    if (n == 0) return MFKC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(reserve_slots(ctx, n));
+    ctx->kmers_ub_total += n;
+    Staging &s = ctx->st[ctx->next_buf];
+    ctx->next_buf ^= 1;
+    {
+        ProfScope ps(ctx, P_COUNT_KEYS, ctx->compute);
+        count_keys_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->compute>>>(
+            reinterpret_cast<const unsigned long long *>(d_keys), n, ctx->tab, ctx->cap, ctx->d_ctr);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(s.h_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaEventRecord(s.ev_done, ctx->compute));
+    s.pending = true; s.kmers_submitted_at_end = ctx->kmers_ub_total;
+    ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
+    return MFKC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// features-calculator
+// ------------------------------------------------------------------------------------------
+extern "C" int mfkc_fc_load_components(mfkc_ctx *ctx, const int64_t *keys, const uint64_t *comp_offsets, uint32_t n_comp) {
+    if (!ctx || !comp_offsets || (n_comp && comp_offsets[n_comp] && !keys)) return fail(ctx, MFKC_E_BADARG, "null argument");
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->compute;
+    cudaFree(ctx->fc_tab); cudaFree(ctx->fc_keys); cudaFree(ctx->fc_off);
+    ctx->fc_tab = nullptr; ctx->fc_keys = nullptr; ctx->fc_off = nullptr;
+    const uint64_t nk = comp_offsets[n_comp] - comp_offsets[0];
+    ctx->fc_nkeys = nk; ctx->fc_ncomp = n_comp;
+    ctx->fc_cap = std::max<uint64_t>(nk * 2 + 64, 1024);
+    CU_TRY(cudaMalloc(&ctx->fc_tab, ctx->fc_cap * sizeof(FcSlot)));
+    CU_TRY(cudaMalloc(&ctx->fc_keys, std::max<uint64_t>(nk, 1) * 8));
+    CU_TRY(cudaMalloc(&ctx->fc_off, ((size_t)n_comp + 1) * 8));
+    std::vector<uint64_t> off(n_comp + 1);
+    for (uint32_t i = 0; i <= n_comp; i++) off[i] = comp_offsets[i] - comp_offsets[0];
+    CU_TRY(cudaMemcpyAsync(ctx->fc_off, off.data(), ((size_t)n_comp + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nk) CU_TRY(cudaMemcpyAsync(ctx->fc_keys, keys + comp_offsets[0], nk * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(ctx->d_fc_ctr, 0, sizeof(Counters), st));
+    fc_clear_kernel<<<grid_for(ctx, ctx->fc_cap, 256, 8), 256, 0, st>>>(ctx->fc_tab, ctx->fc_cap, 1);
+    if (nk) {
+        ProfScope ps(ctx, P_FC_BUILD, st);
+        fc_build_kernel<<<grid_for(ctx, nk, 256, 8), 256, 0, st>>>(ctx->fc_keys, nk, ctx->fc_tab, ctx->fc_cap, ctx->d_fc_ctr);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_fc_reset_values(mfkc_ctx *ctx) {
+    if (!ctx) return MFKC_E_BADARG;
+    if (!ctx->fc_tab) return fail(ctx, MFKC_E_STATE, "no components loaded");
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(sync_all(ctx));
+    fc_clear_kernel<<<grid_for(ctx, ctx->fc_cap, 256, 8), 256, 0, ctx->compute>>>(ctx->fc_tab, ctx->fc_cap, 0);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
+    return MFKC_OK;
+}
+
+// stage host records on the device (through the bases staging buffer of slot 0)
+static int stage_records(mfkc_ctx *ctx, Staging &s, const uint8_t *recs, uint64_t n) {
+    TRY(ensure_staging(ctx, s, n * 10, 1, true));
+    CU_TRY(cudaMemcpyAsync(s.d_bases, recs, (size_t)n * 10, cudaMemcpyHostToDevice, s.stream));
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_fc_set_selected(mfkc_ctx *ctx, const uint8_t *be_records, uint64_t n_records) {
+    if (!ctx) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(sync_all(ctx));
+    cudaStream_t st = ctx->compute;
+    if (!be_records) {                       // no --selected: every component k-mer is considered
+        cudaFree(ctx->fc_sel); ctx->fc_sel = nullptr; ctx->fc_sel_cap = 0; ctx->fc_sel_n = 0;
+        return MFKC_OK;
+    }
+    // (re)size the selected set for the cumulative number of records
+    const uint64_t need = (ctx->fc_sel_n + n_records) * 2 + 1024;
+    if (need > ctx->fc_sel_cap) {
+        Slot *nt = nullptr;
+        TRY(table_alloc(ctx, need, &nt));
+        if (ctx->fc_sel) {
+            rehash_kernel<<<grid_for(ctx, ctx->fc_sel_cap, 256, 8), 256, 0, st>>>(ctx->fc_sel, ctx->fc_sel_cap, nt, need);
+            CU_TRY(cudaStreamSynchronize(st));
+            cudaFree(ctx->fc_sel);
+        }
+        ctx->fc_sel = nt; ctx->fc_sel_cap = need;
+    }
+    if (n_records) {
+        TRY(stage_records(ctx, ctx->st[0], be_records, n_records));
+        CU_TRY(cudaStreamSynchronize(ctx->st[0].stream));
+        fc_selected_kernel<<<grid_for(ctx, n_records, 256, 8), 256, 0, st>>>(ctx->st[0].d_bases, n_records, ctx->fc_sel,
+                                                                            ctx->fc_sel_cap, ctx->d_fc_ctr);
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+    ctx->fc_sel_n += n_records;
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_fc_add_records(mfkc_ctx *ctx, const uint8_t *be_records, uint64_t n_records) {
+    if (!ctx || (!be_records && n_records)) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (!ctx->fc_tab) return fail(ctx, MFKC_E_STATE, "no components loaded");
+    if (n_records == 0) return MFKC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    Staging &s = ctx->st[ctx->next_buf];
+    ctx->next_buf ^= 1;
+    CU_TRY(cudaStreamWaitEvent(s.stream, s.ev_done, 0));
+    TRY(stage_records(ctx, s, be_records, n_records));
+    CU_TRY(cudaEventRecord(s.ev_copy, s.stream));
+    CU_TRY(cudaStreamWaitEvent(ctx->compute, s.ev_copy, 0));
+    {
+        ProfScope ps(ctx, P_FC_RECORDS, ctx->compute);
+        fc_records_kernel<<<grid_for(ctx, n_records, 256, 8), 256, 0, ctx->compute>>>(s.d_bases, n_records, ctx->fc_tab, ctx->fc_cap);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(s.ev_done, ctx->compute));
+    CU_TRY(cudaEventSynchronize(s.ev_copy));
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_fc_add_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads) {
+    if (!ctx || (!bases && n_reads) || !offsets) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (!ctx->fc_tab) return fail(ctx, MFKC_E_STATE, "no components loaded");
+    if (n_reads == 0) return MFKC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const uint64_t base0 = offsets[0];
+    const uint64_t n_bases = offsets[n_reads] - base0;
+    Staging &s = ctx->st[ctx->next_buf];
+    ctx->next_buf ^= 1;
+    TRY(ensure_staging(ctx, s, n_bases, (uint64_t)n_reads + 1, true));
+    CU_TRY(cudaStreamWaitEvent(s.stream, s.ev_done, 0));
+    CU_TRY(cudaMemcpyAsync(s.d_bases, bases + base0, n_bases, cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(cudaMemcpyAsync(s.d_offsets, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(cudaEventRecord(s.ev_copy, s.stream));
+    CU_TRY(cudaStreamWaitEvent(ctx->compute, s.ev_copy, 0));
+    // ReadsPresenceWorker has no minSeqLen (src/io/IOUtils.java:806-825)
+    TRY(launch_mark(ctx, s, s.d_offsets, n_reads, n_bases, 0, 0, ctx->d_fc_ctr));
+    if (n_bases >= (uint64_t)ctx->cfg.k) {
+        ProfScope ps(ctx, P_FC_READS, ctx->compute);
+        SinkPresence sink{ctx->fc_tab, ctx->fc_cap};
+        extract_kernel<SinkPresence><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+            s.d_bases, n_bases, s.d_flags, ctx->cfg.k, sink, ctx->d_fc_ctr);
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaEventRecord(s.ev_done, ctx->compute));
+    CU_TRY(cudaEventSynchronize(s.ev_copy));
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_fc_features(mfkc_ctx *ctx, int64_t threshold, int64_t *vec, uint64_t *found, uint64_t *cnt) {
+    if (!ctx || !vec || !found || !cnt) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (!ctx->fc_tab) return fail(ctx, MFKC_E_STATE, "no components loaded");
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(sync_all(ctx));
+    CU_TRY(cudaMemcpy(ctx->h_ctr, ctx->d_fc_ctr, sizeof(Counters), cudaMemcpyDeviceToHost));
+    if (ctx->h_ctr->bad_chars) return fail(ctx, MFKC_E_FORMAT, "Incorrect nucleotide char in submitted reads (only AaCcGgTt are accepted)");
+    const uint32_t nc = ctx->fc_ncomp;
+    if (nc == 0) return MFKC_OK;
+    cudaStream_t st = ctx->compute;
+    long long *d_vec = nullptr; unsigned long long *d_found = nullptr, *d_cnt = nullptr;
+    CU_TRY(cudaMalloc(&d_vec, (size_t)nc * 8)); CU_TRY(cudaMalloc(&d_found, (size_t)nc * 8)); CU_TRY(cudaMalloc(&d_cnt, (size_t)nc * 8));
+    {
+        ProfScope ps(ctx, P_FC_FEATURES, st);
+        const int grid = grid_for(ctx, (uint64_t)nc * 32, 256, 8);
+        fc_features_kernel<<<grid, 256, 0, st>>>(ctx->fc_keys, ctx->fc_off, nc, ctx->fc_tab, ctx->fc_cap, ctx->fc_sel,
+                                                ctx->fc_sel_cap, (long long)threshold, d_vec, d_found, d_cnt);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(vec, d_vec, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(found, d_found, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(cnt, d_cnt, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_vec); cudaFree(d_found); cudaFree(d_cnt);
+    return MFKC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic reads on the device
+// ------------------------------------------------------------------------------------------
+extern "C" int mfkc_synth_tables_build(const mfkc_synth_cfg *cfg, mfkc_synth_tables *t);   // host_io.cpp
+
+__global__ void __launch_bounds__(256)
+synth_kernel(const mfkc_synth_tables *__restrict__ t, const uint64_t *__restrict__ kept_index, uint64_t n_kept,
+             uint8_t *__restrict__ out, uint64_t *__restrict__ offsets) {
+    const uint32_t L = t->read_len;
+    const uint64_t total = n_kept * L;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t j = i / L;
+        const uint32_t b = (uint32_t)(i - j * L);
+        mfkc_synth_read r;
+        mfkc_synth_read_header(*t, kept_index[j], r);
+        out[i] = mfkc_synth_read_base(*t, r, b);
+        if (b == 0) offsets[j] = i;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n_kept] = total;
+}
+
+extern "C" int mfkc_synth_reads_device(mfkc_ctx *ctx, const mfkc_synth_cfg *cfg, uint64_t first_read, uint64_t n_reads,
+                                       uint8_t *d_bases, uint64_t *d_offsets, uint64_t *n_kept) {
+    if (!ctx || !cfg || !d_bases || !d_offsets || !n_kept) return fail(ctx, MFKC_E_BADARG, "null argument");
+    CU_TRY(cudaSetDevice(ctx->device));
+    mfkc_synth_tables *t = new mfkc_synth_tables();
+    int r = mfkc_synth_tables_build(cfg, t);
+    if (r != MFKC_OK) { delete t; return fail(ctx, r, "bad synthetic-read configuration"); }
+    std::vector<uint64_t> kept; kept.reserve(n_reads);
+    for (uint64_t i = 0; i < n_reads; i++) if (!mfkc_synth_read_has_n(*t, first_read + i)) kept.push_back(first_read + i);
+    cudaStream_t st = ctx->compute;
+    if (!ctx->d_synth) CU_TRY(cudaMalloc(&ctx->d_synth, sizeof(mfkc_synth_tables)));
+    uint64_t *d_idx = nullptr;
+    CU_TRY(cudaMalloc(&d_idx, std::max<size_t>(kept.size(), 1) * 8));
+    CU_TRY(cudaMemcpyAsync(ctx->d_synth, t, sizeof(mfkc_synth_tables), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_idx, kept.data(), kept.size() * 8, cudaMemcpyHostToDevice, st));
+    {
+        ProfScope ps(ctx, P_SYNTH, st);
+        synth_kernel<<<grid_for(ctx, kept.size() * (uint64_t)t->read_len + 1, 256, 8), 256, 0, st>>>(
+            ctx->d_synth, d_idx, kept.size(), d_bases, d_offsets);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_idx);
+    *n_kept = kept.size();
+    delete t;
+    return MFKC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// raw device helpers, timing, profile, GUPS
+// ------------------------------------------------------------------------------------------
+extern "C" int mfkc_device_alloc(mfkc_ctx *ctx, size_t bytes, void **d_ptr) {
+    if (!ctx || !d_ptr) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaMalloc(d_ptr, bytes ? bytes : 1));
+    return MFKC_OK;
+}
+extern "C" int mfkc_device_free(mfkc_ctx *ctx, void *d_ptr) {
+    if (!ctx) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaFree(d_ptr));
+    return MFKC_OK;
+}
+extern "C" int mfkc_memcpy_h2d(mfkc_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    if (!ctx) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+    return MFKC_OK;
+}
+extern "C" int mfkc_memcpy_d2h(mfkc_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+    if (!ctx) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return MFKC_OK;
+}
+extern "C" int mfkc_device_sync(mfkc_ctx *ctx) {
+    if (!ctx) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaDeviceSynchronize());
+    return MFKC_OK;
+}
+
+// Every kernel runs on the compute stream and every H2D copy is awaited by it, so two events
+// on the compute stream bracket all device work submitted in between.
+extern "C" int mfkc_timer_start(mfkc_ctx *ctx) {
+    if (!ctx) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(sync_all(ctx));
+    CU_TRY(cudaEventRecord(ctx->t0, ctx->compute));
+    return MFKC_OK;
+}
+extern "C" int mfkc_timer_stop_ms(mfkc_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaEventRecord(ctx->t1, ctx->compute));
+    CU_TRY(cudaEventSynchronize(ctx->t1));
+    CU_TRY(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_profile_enable(mfkc_ctx *ctx, int on) { if (!ctx) return MFKC_E_BADARG; ctx->profiling = on != 0; return MFKC_OK; }
+extern "C" int mfkc_profile_reset(mfkc_ctx *ctx) {
+    if (!ctx) return MFKC_E_BADARG;
+    drain_timings(ctx);
+    for (int i = 0; i < P_NSLOTS; i++) { ctx->prof_ms[i] = 0; ctx->prof_launches[i] = 0; }
+    return MFKC_OK;
+}
+extern "C" int mfkc_profile_get(mfkc_ctx *ctx, int slot, double *ms, uint64_t *launches) {
+    if (!ctx || slot < 0 || slot >= P_NSLOTS) return MFKC_E_BADARG;
+    drain_timings(ctx);
+    if (ms) *ms = ctx->prof_ms[slot];
+    if (launches) *launches = ctx->prof_launches[slot];
+    return MFKC_OK;
+}
+extern "C" const char *mfkc_profile_name(int slot) { return slot >= 0 && slot < P_NSLOTS ? kProfNames[slot] : nullptr; }
+
+extern "C" int mfkc_gups(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, float *ms) {
+    if (!ctx || !ms || bytes < 32) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int mode = (int)(n_updates >> 63);            // top bit selects the dependent-load flavour
+    n_updates &= ~(1ull << 63);
+    unsigned long long *tab = nullptr;
+    CU_TRY(cudaMalloc(&tab, bytes));
+    CU_TRY(cudaMemset(tab, 0, bytes));
+    cudaStream_t st = ctx->compute;
+    const uint64_t n_sectors = bytes / 32;
+    cudaEvent_t a = get_event(ctx), b = get_event(ctx);
+    gups_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(tab, n_sectors, n_updates / 8 + 1, 1, mode);   // warm-up
+    CU_TRY(cudaEventRecord(a, st));
+    {
+        ProfScope ps(ctx, P_GUPS, st);
+        gups_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(tab, n_sectors, n_updates, 0x9e3779b9ULL, mode);
+    }
+    CU_TRY(cudaEventRecord(b, st));
+    CU_TRY(cudaEventSynchronize(b));
+    CU_TRY(cudaEventElapsedTime(ms, a, b));
+    ctx->ev_pool.push_back(a); ctx->ev_pool.push_back(b);
+    CU_TRY(cudaFree(tab));
+    return MFKC_OK;
+}

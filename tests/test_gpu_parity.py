@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle, bit-exact.
+
+Oracles: oracle/oracle.py (numpy restatement) and oracle/ref_cpu.c (C restatement with the
+reference's threading + striped hash maps).  Golden numbers: tests/golden/config1.json.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import metafast_b200 as m
+from oracle import oracle as orc
+from tests import _oracle_c
+from tests.conftest import GOLDEN, INPUTS
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [m.VARIANT_HASH, m.VARIANT_SORT]
+
+
+def run_counter(reads_batches, k, b, variant, min_len=0, **kw):
+    with m.KmerCounter(k, min_seq_len=min_len, variant=variant, **kw) as kc:
+        for batch in reads_batches:
+            kc.submit_reads(batch)
+        kc.flush()
+        rec = kc.emit(b)
+        hist = kc.histogram()
+        st = kc.stats()
+    return rec, hist, st
+
+
+def check_against_oracle(reads, k, b, variant, min_len=0, batches=1, **kw):
+    reads = list(reads)
+    step = max(1, (len(reads) + batches - 1) // batches)
+    parts = [reads[i:i + step] for i in range(0, len(reads), step)] or [[]]
+    rec, hist, st = run_counter(parts, k, b, variant, min_len, **kw)
+    counts = orc.count_reads(reads, k, min_len)
+    assert rec == orc.kmers_bin(counts, b, k)
+    assert {int(c): int(hist[c]) for c in np.nonzero(hist)[0]} == orc.histogram(counts)
+    assert st["distinct"] == len(counts)
+    tot, good, tot_len, good_len = orc.read_stats(reads, min_len)
+    assert (st["total_seq"], st["good_seq"], st["total_len"], st["good_len"]) == (tot, good, tot_len, good_len)
+    assert st["kmers"] == sum(max(0, len(r) - k + 1) for r in reads if len(r) >= min_len)
+    return rec
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_config1_golden(built, variant, n):
+    """BASELINE config 1: meta_test_{1,2,3}.fa, k=31, default -b 1."""
+    gold = json.load(open(os.path.join(GOLDEN, "config1.json")))["meta_test_%d" % n]
+    path = os.path.join(INPUTS, "meta_test_%d.fa" % n)
+    reads = m.read_file_reads(path)
+    assert len(reads) == gold["reads"]
+    rec, hist, st = run_counter([reads], 31, 1, variant)
+    assert len(rec) == gold["kmers_bin_bytes"]
+    assert orc.sha256_hex(rec) == gold["sha256_sorted_records"]
+    assert st["distinct"] == gold["distinct"] and st["kmers"] == gold["kmer_instances"]
+    assert {str(int(c)): int(hist[c]) for c in np.nonzero(hist)[0]} == gold["hist"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_tinytest_fastq(built, variant):
+    reads = m.read_file_reads(os.path.join(INPUTS, "tinytest_A.fastq"))
+    rec, hist, st = run_counter([reads], 5, 0, variant)
+    keys = [k for k, c in orc.load_kmers_bin(rec)]
+    assert keys == [26, 35, 104, 140, 193, 262, 416, 444, 501, 560]
+    assert all(c == 1 for k, c in orc.load_kmers_bin(rec))
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("k", [1, 2, 5, 15, 16, 17, 21, 30, 31])
+def test_edge_cases(built, variant, k):
+    rng = np.random.default_rng(1234 + k)
+    reads = []
+    for L in list(range(0, 70)) + [150, 151, 255, 256, 257, 1000]:
+        reads.append("".join(rng.choice(list("ACGT"), L)))
+    reads += ["A" * 64, "T" * 64, "a" * 40, "G" * 33, "C" * 33]          # poly-A/T = key 0, lower case
+    reads += ["ACGT" * 20, "AATT" * 12, "GC" * 31, "acgtACGT" * 9]         # palindromic k-mers (fw == rc)
+    reads += ["", "A", "AC"]
+    check_against_oracle(reads, k, 0, variant)
+    check_against_oracle(reads, k, 1, variant, batches=7)
+    check_against_oracle(reads, k, 2, variant, min_len=40, batches=3)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_saturation(built, variant):
+    """counts saturate at 32767 ([itmo]/utils/NumUtils.java:21-26)."""
+    k = 9
+    read = "ACGTTGCAAGGCTTAACG"
+    reads = [read] * 40000 + ["A" * 30] * 2000 + ["ACGTTGCAAGG"] * 10
+    rec = check_against_oracle(reads, k, 1, variant, batches=5)
+    cs = [c for _, c in orc.load_kmers_bin(rec)]
+    assert max(cs) == 32767 and cs.count(32767) >= 10
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_empty_inputs(built, variant):
+    rec, hist, st = run_counter([[]], 31, 1, variant)
+    assert rec == b"" and hist.sum() == 0 and st["distinct"] == 0
+    rec, hist, st = run_counter([["ACGT"], ["", ""]], 31, 0, variant)      # all reads shorter than k
+    assert rec == b"" and st["total_seq"] == 3 and st["kmers"] == 0
+
+
+def test_table_growth(built):
+    """the table starts tiny and must grow (Long2ShortHashMap.enlargeAndRehash analogue)."""
+    rng = np.random.default_rng(7)
+    reads = ["".join(rng.choice(list("ACGT"), 150)) for _ in range(4000)]
+    check_against_oracle(reads, 31, 0, m.VARIANT_HASH, batches=16, table_slots=1024)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_random_vs_c_oracle(built, variant):
+    """~1.2 M k-mer instances with repeats, checked against the threaded C restatement."""
+    cfg = m.synth_cfg(total_genome_bp=200000, n_genomes=8)
+    raw = m.synth_reads_host(cfg, 0, 10000)
+    keep = ~(raw == ord("N")).any(axis=1)
+    bases = np.ascontiguousarray(raw[keep]).reshape(-1)
+    n = int(keep.sum())
+    offsets = (np.arange(n + 1, dtype=np.uint64) * np.uint64(cfg.read_len))
+    want_rec, want_hist, want_distinct, want_stats = _oracle_c.count(bases, offsets, 31, 2, P=4)
+    with m.KmerCounter(31, variant=variant) as kc:
+        step = 1500
+        for s in range(0, n, step):
+            e = min(n, s + step)
+            kc.submit(bases, offsets[s:e + 1])          # sub-range of one big buffer (offsets[0] != 0)
+        kc.flush()
+        rec = kc.emit(2)
+        hist = kc.histogram()
+        st = kc.stats()
+    assert rec == want_rec
+    assert (hist == want_hist).all()
+    assert st["distinct"] == want_distinct
+    assert [st["total_seq"], st["good_seq"], st["total_len"], st["good_len"]] == want_stats
+
+
+def test_bad_nucleotide_is_an_error(built):
+    with m.KmerCounter(5) as kc:
+        kc.submit_reads(["ACGTACGTNACGT"])
+        with pytest.raises(m.MfkcError) as e:
+            kc.flush()
+        assert e.value.code == -8
+
+
+def test_bad_arguments(built):
+    for k in (0, -3, 32, 64):
+        with pytest.raises(m.MfkcError) as e:
+            m.KmerCounter(k)
+        assert e.value.code == -1
+
+
+def test_reset_between_samples(built):
+    a = ["ACGTACGTACGTAAACCCGGGTTT" * 3]
+    b = ["TTTTGGGGCCCCAAAATTGGCCAA" * 3]
+    with m.KmerCounter(11) as kc:
+        kc.submit_reads(a); kc.flush(); ra = kc.emit(0)
+        kc.reset()
+        kc.submit_reads(b); kc.flush(); rb = kc.emit(0)
+    assert ra == orc.kmers_bin(orc.count_reads(a, 11), 0, 11)
+    assert rb == orc.kmers_bin(orc.count_reads(b, 11), 0, 11)
+
+
+def test_synth_device_matches_host(built):
+    cfg = m.synth_cfg(total_genome_bp=300000, n_genomes=5, n_read_ppm=20000, poly_tail_ppm=5000)
+    n = 3000
+    raw = m.synth_reads_host(cfg, 100, n)
+    keep = ~(raw == ord("N")).any(axis=1)
+    want = np.ascontiguousarray(raw[keep]).reshape(-1)
+    import ctypes as C
+    with m.KmerCounter(31) as kc:
+        d_b = kc.device_alloc(n * cfg.read_len)
+        d_o = kc.device_alloc((n + 1) * 8)
+        kept = C.c_uint64()
+        kc._ck(kc.lib.mfkc_synth_reads_device(kc.h, C.byref(cfg), 100, n, C.c_void_p(d_b), C.c_void_p(d_o), C.byref(kept)))
+        assert kept.value == int(keep.sum()) and 0 < kept.value < n
+        got = np.empty(kept.value * cfg.read_len, dtype=np.uint8)
+        off = np.empty(kept.value + 1, dtype=np.uint64)
+        kc.d2h(got, d_b); kc.d2h(off, d_o)
+        assert (got == want).all()
+        assert (off == np.arange(kept.value + 1, dtype=np.uint64) * np.uint64(cfg.read_len)).all()
+        # and count straight from the device-resident batch
+        kc.submit_device(d_b, d_o, kept.value, kept.value * cfg.read_len)
+        kc.flush()
+        rec = kc.emit(1)
+        kc.device_free(d_b); kc.device_free(d_o)
+    offsets = np.arange(kept.value + 1, dtype=np.uint64) * np.uint64(cfg.read_len)
+    want_rec, _, _, _ = _oracle_c.count(want, offsets, 31, 1, P=2)
+    assert rec == want_rec
+
+
+@pytest.mark.parametrize("n_shards", [2, 3, 8])
+def test_logical_shards_equal_unsharded(built, n_shards):
+    """Hash-range sharding with G logical shards on one GPU: bucket -> 'exchange' -> per-shard
+    count -> key-ordered merge must equal the unsharded result."""
+    cfg = m.synth_cfg(total_genome_bp=100000, n_genomes=4, n_read_ppm=0)
+    n = 4000
+    raw = m.synth_reads_host(cfg, 0, n)
+    bases = np.ascontiguousarray(raw).reshape(-1)
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(cfg.read_len)
+    want_rec, want_hist, _, _ = _oracle_c.count(bases, offsets, 31, 1, P=2)
+    lib = m.load()
+    shards = [m.KmerCounter(31, n_shards=n_shards, shard_id=s) for s in range(n_shards)]
+    try:
+        src = shards[0]
+        d_b = src.device_alloc(bases.nbytes); d_o = src.device_alloc(offsets.nbytes)
+        src.h2d(d_b, bases); src.h2d(d_o, offsets)
+        cap = bases.size
+        d_keys = src.device_alloc(cap * 8)
+        counts = src.extract_bucketed(d_b, d_o, n, bases.size, d_keys, cap, n_shards)
+        assert sum(counts) == n * (cfg.read_len - 30)
+        keys = np.empty(sum(counts), dtype=np.uint64)
+        src.d2h(keys, d_keys)
+        pos = 0
+        merged = []
+        hist = np.zeros(m.HIST_BINS, dtype=np.uint64)
+        for s in range(n_shards):
+            part = keys[pos:pos + counts[s]]; pos += counts[s]
+            assert all(lib.mfkc_owner_shard(int(x), n_shards) == s for x in part[:200])
+            d_part = shards[s].device_alloc(max(part.nbytes, 8))
+            if part.size:
+                shards[s].h2d(d_part, part)
+                shards[s].count_keys_device(d_part, part.size)
+            shards[s].flush()
+            merged.append(shards[s].emit(1))
+            hist += shards[s].histogram()
+            shards[s].device_free(d_part)
+        # shards hold disjoint key sets: the deterministic merge is a k-way merge by key
+        recs = sorted(r for part in merged for r in (part[i:i + 10] for i in range(0, len(part), 10)))
+        assert b"".join(recs) == want_rec
+        assert (hist == want_hist).all()
+        src.device_free(d_b); src.device_free(d_o); src.device_free(d_keys)
+    finally:
+        for s in shards:
+            s.close()
+
+
+# ---------------------------------------------------------------- features-calculator
+def _components_from(counts, rng, n_comp=40):
+    keys = sorted(counts)
+    comps = []
+    for _ in range(n_comp):
+        size = int(rng.integers(0, 60))
+        comp = [keys[int(i)] for i in rng.integers(0, len(keys), size)]
+        comp += [int(x) for x in rng.integers(0, 1 << 62, int(rng.integers(0, 5)))]   # keys absent from the sample
+        comps.append(comp)
+    comps.append([])                        # empty component: breadth NaN
+    comps.append([keys[0]] * 5)             # duplicated key
+    return comps
+
+
+def test_features_from_kmers_files(built):
+    rng = np.random.default_rng(99)
+    path = os.path.join(INPUTS, "meta_test_3.fa")
+    reads = orc.parse_reads(path)
+    counts = orc.count_reads(reads, 31)
+    records = orc.kmers_bin(counts, 1, 31)
+    comps = _components_from(counts, rng)
+    sel_counts = {k: c for k, c in counts.items() if k % 3 == 0}
+    selected = orc.kmers_bin(sel_counts, 0, 31)
+    with m.FeaturesCalculator(31) as fc:
+        fc.load_components(comps)
+        for thr, sel in ((0, None), (3, None), (0, selected), (2, selected), (0, b"")):
+            fc.set_selected(sel)
+            fc.reset_values()
+            fc.add_records(records, chunk=10 * 1000)
+            vec, found, cnt = fc.features(thr)
+            acc = orc.presence_for_kmers([k for c in comps for k in c], orc.load_kmers_bin(records))
+            seld = None if sel is None else orc.load_kmers([sel], 0)
+            wv, wb, wf, wc = orc.features([(0, c) for c in comps], acc, thr, seld)
+            assert list(vec) == wv and list(found) == wf and list(cnt) == wc
+            cv, cf, cc = _oracle_c.features_kmers(comps, records, sel, thr)
+            assert list(cv) == wv and list(cf) == wf and list(cc) == wc
+            fc.set_selected(None)
+        # a file loaded twice adds up (no reset in between); negative 'freq' follows Java's addAndBound
+        fc.reset_values()
+        fc.add_records(records); fc.add_records(records)
+        vec2, _, _ = fc.features(0)
+        acc = orc.presence_for_kmers([k for c in comps for k in c], orc.load_kmers_bin(records) * 2)
+        assert list(vec2) == orc.features([(0, c) for c in comps], acc, 0)[0]
+
+
+def test_features_from_reads(built):
+    rng = np.random.default_rng(5)
+    reads = orc.parse_reads(os.path.join(INPUTS, "meta_test_2.fa"))
+    counts = orc.count_reads(reads, 21)
+    comps = _components_from(counts, rng, 25)
+    with m.FeaturesCalculator(21) as fc:
+        fc.load_components(comps)
+        fc.reset_values()
+        fc.add_reads(reads[:300]); fc.add_reads(reads[300:])
+        vec, found, cnt = fc.features(0)
+    acc = orc.presence_for_reads([k for c in comps for k in c], reads, 21)
+    wv, wb, wf, wc = orc.features([(0, c) for c in comps], acc, 0)
+    assert list(vec) == wv and list(found) == wf and list(cnt) == wc
