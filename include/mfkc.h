@@ -212,10 +212,16 @@ int  mfkc_profile_reset(mfkc_ctx *ctx);
 int  mfkc_profile_get(mfkc_ctx *ctx, int slot, double *ms, uint64_t *launches);
 const char *mfkc_profile_name(int slot);                      /* NULL past the last slot */
 
-/* Random-sector read-modify-write microbenchmark (GUPS-style) on a table of `bytes` bytes:
- * n_updates atomic adds to uniformly random 32-byte sectors; returns device milliseconds.
- * This measures the random-access HBM roofline the hash variant is compared against. */
+/* Random-sector microbenchmark (GUPS-style) on a table of `bytes` bytes: n_updates accesses to
+ * uniformly random 32-byte sectors; returns device milliseconds.  It measures the random-access
+ * HBM roofline the hash variant is compared against.
+ *   mode 0: red.add only          mode 1: dependent 128-bit load + red.add (= one table upsert)
+ *   mode 2: 128-bit load only     mode 3: mode 1 swept window by window (window_bytes, with
+ *                                         blocks_per_window CTAs each): the region-blocked pattern
+ * mfkc_gups() is mode 1 over the whole table. */
 int  mfkc_gups(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, float *ms);
+int  mfkc_gups_ex(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, int mode, uint64_t window_bytes,
+                  uint32_t blocks_per_window, float *ms);
 
 #ifdef __cplusplus
 }

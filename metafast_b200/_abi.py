@@ -109,6 +109,8 @@ SIGNATURES = {
     "mfkc_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), u64p]),
     "mfkc_profile_name": (C.c_char_p, [C.c_int]),
     "mfkc_gups": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_float)]),
+    "mfkc_gups_ex": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.c_uint32,
+                               C.POINTER(C.c_float)]),
 }
 
 _lib = None

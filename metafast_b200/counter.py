@@ -125,9 +125,10 @@ class _Ctx:
             i += 1
         return out
 
-    def gups(self, nbytes: int, n_updates: int, dependent: bool = False) -> float:
+    def gups(self, nbytes: int, n_updates: int, mode: int = 1, window_bytes: int = 0, blocks_per_window: int = 0) -> float:
+        """Random-sector microbenchmark (see mfkc_gups_ex); returns milliseconds."""
         ms = C.c_float()
-        self._ck(self.lib.mfkc_gups(self.h, nbytes, n_updates | ((1 << 63) if dependent else 0), C.byref(ms)))
+        self._ck(self.lib.mfkc_gups_ex(self.h, nbytes, n_updates, mode, window_bytes, blocks_per_window, C.byref(ms)))
         return ms.value
 
 

@@ -55,7 +55,9 @@ mark_read_ends_kernel(const uint64_t *__restrict__ offsets, uint32_t n_reads, ui
         if (good) { g_seq++; g_len += len; if (len >= (uint64_t)k) kmers += len - k + 1; }
         if (len == 0) continue;
         if (good || len < (uint64_t)k) {
-            atomicOr(&flags[(e - 1) >> 5], 1u << ((e - 1) & 31));
+            // k == 1: 1-mers never cross a boundary, and the flag window degenerates to the start
+            // position itself (see kmers_of_word), so ordinary reads must stay unflagged
+            if (k > 1) atomicOr(&flags[(e - 1) >> 5], 1u << ((e - 1) & 31));
         } else {
             for (uint64_t p = s; p < e; p++) atomicOr(&flags[p >> 5], 1u << (p & 31));
         }
@@ -220,7 +222,8 @@ __device__ __forceinline__ uint64_t revcomp64(uint64_t fw, int k) {
 __device__ __forceinline__ uint32_t kmers_of_word(uint32_t w0, uint32_t w1, uint32_t w2, uint64_t flag_bits,
                                                   long long limit /* n_bases - k - 16*w */, int k,
                                                   uint64_t (&keys)[16]) {
-    const uint64_t span = (k > 1) ? ((1ULL << (k - 1)) - 1ULL) : 0ULL;  // flags over [p, p+k-2]
+    // flags over [p, p+k-2]; for k == 1 only "dead read" flags exist and the window is [p, p]
+    const uint64_t span = (k > 1) ? ((1ULL << (k - 1)) - 1ULL) : 1ULL;
     const int rs = 64 - 2 * k;
     const int top = 2 * k - 2;
     uint32_t valid = 0;
@@ -679,20 +682,45 @@ fc_features_kernel(const unsigned long long *__restrict__ comp_keys, const uint6
 }
 
 // ------------------------------------------------------------------------------------------
-// GUPS-style microbenchmark: random 32-byte-sector read-modify-write over a big table.
-// mode 0: one red.add per update; mode 1: dependent load + red.add (the shape of an upsert).
+// GUPS-style microbenchmark: random 32-byte-sector accesses over a big table.
+//   mode 0: one red.add per update (fire and forget)
+//   mode 1: dependent 128-bit load + red.add -- the shape of a table upsert
+//   mode 2: 128-bit load only (random sector reads)
+//   mode 3: like mode 1, but the table is swept window by window (window_sectors each): block b
+//           only touches window b / blocks_per_window, so the live working set is a few windows
+//           and stays L2-resident -- the access pattern of the region-blocked upsert.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gups_kernel(unsigned long long *__restrict__ tab, uint64_t n_sectors, uint64_t n_updates, uint64_t seed, int mode) {
+gups_kernel(unsigned long long *__restrict__ tab, uint64_t n_sectors, uint64_t n_updates, uint64_t seed, int mode,
+            uint64_t window_sectors, uint32_t blocks_per_window) {
     unsigned long long sink = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_updates; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t s = mulhi64(mix64(i + seed), n_sectors);
-        unsigned long long *p = tab + 4 * s;
-        if (mode == 1) {
-            const ulonglong2 v = ld_cg_u64x2(p);
-            if (v.x != 0x123456789ULL) atomicAdd((unsigned int *)(p + 1), 1u); else sink += v.y;
-        } else {
-            atomicAdd((unsigned int *)(p + 1), 1u);
+    if (mode == 3) {
+        const uint64_t n_windows = (n_sectors + window_sectors - 1) / window_sectors;
+        const uint64_t per_block = n_updates / ((uint64_t)n_windows * blocks_per_window) + 1;
+        for (uint64_t win = blockIdx.x / blocks_per_window; win < n_windows; win += gridDim.x / blocks_per_window) {
+            const uint64_t w0 = win * window_sectors;
+            const uint64_t wn = w0 + window_sectors <= n_sectors ? window_sectors : n_sectors - w0;
+            const uint64_t salt = (win * blocks_per_window + blockIdx.x % blocks_per_window) * per_block;
+            for (uint64_t i = threadIdx.x; i < per_block; i += blockDim.x) {
+                const uint64_t sct = w0 + mulhi64(mix64(salt + i + seed), wn);
+                unsigned long long *p = tab + 4 * sct;
+                const ulonglong2 v = ld_cg_u64x2(p);
+                if (v.x != 0x123456789ULL) atomicAdd((unsigned int *)(p + 1), 1u); else sink += v.y;
+            }
+        }
+    } else {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_updates; i += (uint64_t)gridDim.x * blockDim.x) {
+            const uint64_t sct = mulhi64(mix64(i + seed), n_sectors);
+            unsigned long long *p = tab + 4 * sct;
+            if (mode == 1) {
+                const ulonglong2 v = ld_cg_u64x2(p);
+                if (v.x != 0x123456789ULL) atomicAdd((unsigned int *)(p + 1), 1u); else sink += v.y;
+            } else if (mode == 2) {
+                const ulonglong2 v = ld_cg_u64x2(p);
+                sink += v.x ^ v.y;
+            } else {
+                atomicAdd((unsigned int *)(p + 1), 1u);
+            }
         }
     }
     if (sink == 0xdeadbeefULL) tab[0] = sink;

@@ -1158,27 +1158,40 @@ extern "C" int mfkc_profile_get(mfkc_ctx *ctx, int slot, double *ms, uint64_t *l
 }
 extern "C" const char *mfkc_profile_name(int slot) { return slot >= 0 && slot < P_NSLOTS ? kProfNames[slot] : nullptr; }
 
-extern "C" int mfkc_gups(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, float *ms) {
-    if (!ctx || !ms || bytes < 32) return MFKC_E_BADARG;
+extern "C" int mfkc_gups_ex(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, int mode, uint64_t window_bytes,
+                            uint32_t blocks_per_window, float *ms) {
+    if (!ctx || !ms || bytes < 32 || mode < 0 || mode > 3) return MFKC_E_BADARG;
     CU_TRY(cudaSetDevice(ctx->device));
-    const int mode = (int)(n_updates >> 63);            // top bit selects the dependent-load flavour
-    n_updates &= ~(1ull << 63);
     unsigned long long *tab = nullptr;
     CU_TRY(cudaMalloc(&tab, bytes));
     CU_TRY(cudaMemset(tab, 0, bytes));
     cudaStream_t st = ctx->compute;
     const uint64_t n_sectors = bytes / 32;
+    uint64_t win = window_bytes / 32;
+    if (win == 0 || win > n_sectors) win = n_sectors;
+    if (blocks_per_window == 0) blocks_per_window = 1;
+    int grid = ctx->sm_count * 8;
+    if (mode == 3) {
+        grid = (int)std::min<uint64_t>((n_sectors + win - 1) / win * blocks_per_window, 1u << 30);
+        if (grid < (int)blocks_per_window) grid = blocks_per_window;
+        grid -= grid % blocks_per_window;
+    }
     cudaEvent_t a = get_event(ctx), b = get_event(ctx);
-    gups_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(tab, n_sectors, n_updates / 8 + 1, 1, mode);   // warm-up
+    gups_kernel<<<grid, 256, 0, st>>>(tab, n_sectors, n_updates / 8 + 1, 1, mode, win, blocks_per_window);   // warm-up
     CU_TRY(cudaEventRecord(a, st));
     {
         ProfScope ps(ctx, P_GUPS, st);
-        gups_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(tab, n_sectors, n_updates, 0x9e3779b9ULL, mode);
+        gups_kernel<<<grid, 256, 0, st>>>(tab, n_sectors, n_updates, 0x9e3779b9ULL, mode, win, blocks_per_window);
     }
     CU_TRY(cudaEventRecord(b, st));
     CU_TRY(cudaEventSynchronize(b));
+    CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventElapsedTime(ms, a, b));
     ctx->ev_pool.push_back(a); ctx->ev_pool.push_back(b);
     CU_TRY(cudaFree(tab));
     return MFKC_OK;
+}
+
+extern "C" int mfkc_gups(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, float *ms) {
+    return mfkc_gups_ex(ctx, bytes, n_updates, 1, 0, 0, ms);
 }

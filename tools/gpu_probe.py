@@ -13,7 +13,7 @@ with m.KmerCounter(31, variant=variant, expected_distinct=hint) as kc:
     for gb in (1, 8, 32):
         for dep in (False, True):
             nupd = 1 << 29
-            ms = kc.gups(gb << 30, nupd, dep)
+            ms = kc.gups(gb << 30, nupd, 1 if dep else 0)
             print("gups table=%dGiB dependent=%d: %.2f ms  %.2f Gupd/s  %.1f GB/s (64B/upd)" % (gb, dep, ms, nupd / ms / 1e6, nupd * 64 / ms / 1e6), flush=True)
     # device-resident synthetic reads
     L = cfg.read_len
