@@ -44,7 +44,12 @@ enum {
     MFKC_E_FORMAT = -8      /* malformed FASTA/FASTQ/.kmers.bin/components.bin, bad nucleotide */
 };
 
-enum { MFKC_VARIANT_HASH = 0, MFKC_VARIANT_SORT = 1 };
+/* HASH        = HBM-resident open-addressing table, region-blocked: keys are partitioned by table
+ *               region and drained region by region so that every upsert hits L2 (default);
+ * SORT        = accumulate keys, radix sort, run-length encode;
+ * HASH_DIRECT = the same table updated straight from the extraction kernel (one random DRAM
+ *               sector per k-mer) -- kept as the measured baseline of the blocked design. */
+enum { MFKC_VARIANT_HASH = 0, MFKC_VARIANT_SORT = 1, MFKC_VARIANT_HASH_DIRECT = 2 };
 
 #define MFKC_MAX_COUNT 32767        /* Short.MAX_VALUE: [itmo]/utils/NumUtils.java:21-26 */
 #define MFKC_HIST_BINS 32768        /* histogram index = count, 1..32767 */
@@ -58,14 +63,17 @@ typedef struct mfkc_cfg {
                                    32..63: 128-bit keys (extension, no reference behaviour) */
     int32_t  min_seq_len;       /* minSeqLen of IOUtils.loadReads (src/io/IOUtils.java:761); 0 for the counter */
     int32_t  device;            /* CUDA device ordinal */
-    int32_t  variant;           /* MFKC_VARIANT_HASH | MFKC_VARIANT_SORT */
+    int32_t  variant;           /* MFKC_VARIANT_HASH | MFKC_VARIANT_SORT | MFKC_VARIANT_HASH_DIRECT */
     int32_t  n_shards;          /* hash-range sharding: number of key-space shards (GPUs); 0/1 = unsharded */
     int32_t  shard_id;          /* the shard this context owns */
     int32_t  reserved0;
     uint64_t table_slots;       /* initial table capacity in slots; 0 = derive from expected_distinct / default */
     uint64_t expected_distinct; /* sizing hint (distinct k-mers); 0 = unknown, table grows x2 on demand */
     uint64_t max_table_bytes;   /* growth limit; 0 = 80 % of free device memory */
-    uint64_t reserved1[4];
+    uint64_t staging_bytes;     /* HASH: key staging buffer; 0 = adaptive (starts at 4 batches, doubles when full) */
+    uint32_t region_shift;      /* HASH: log2(table slots per region); 0 = 19 (8 MiB regions) */
+    uint32_t reserved2;
+    uint64_t reserved1[2];
 } mfkc_cfg;
 
 /* ---- lifecycle ------------------------------------------------------------------------

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmfkc.so")
 
 MFKC_OK = 0
 E_BADARG, E_CUDA, E_NCCL, E_TABLE_FULL, E_OOM, E_STATE, E_IO, E_FORMAT = -1, -2, -3, -4, -5, -6, -7, -8
-VARIANT_HASH, VARIANT_SORT = 0, 1
+VARIANT_HASH, VARIANT_SORT, VARIANT_HASH_DIRECT = 0, 1, 2
 MAX_COUNT = 32767
 HIST_BINS = 32768
 
@@ -38,7 +38,10 @@ class MfkcCfg(C.Structure):
         ("table_slots", C.c_uint64),
         ("expected_distinct", C.c_uint64),
         ("max_table_bytes", C.c_uint64),
-        ("reserved1", C.c_uint64 * 4),
+        ("staging_bytes", C.c_uint64),
+        ("region_shift", C.c_uint32),
+        ("reserved2", C.c_uint32),
+        ("reserved1", C.c_uint64 * 2),
     ]
 
 

@@ -157,14 +157,6 @@ struct SinkTable {              // hash variant: upsert into the HBM-resident ta
     }
 };
 
-struct SinkAppend {             // sort variant: append every key to a flat device array
-    unsigned long long *out; uint64_t cap; Counters *ctr;
-    static constexpr bool kPrefetch = false;
-    __device__ __forceinline__ void prefetch(uint64_t) const {}
-    __device__ __forceinline__ uint32_t put(uint64_t) const { return 0; }   // unused (bulk path)
-    __device__ __forceinline__ void finish(uint32_t) const {}
-};
-
 struct SinkPresence {           // features-calculator reads mode: if (contains(key)) acc += 1
     FcSlot *tab; uint64_t cap;
     static constexpr bool kPrefetch = true;
@@ -400,6 +392,170 @@ extract_bucket_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const
     }
     if (overflow) atomicAdd(&ctr->overflow, overflow);
     if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
+}
+
+// ------------------------------------------------------------------------------------------
+// Region-blocked counting (the default hash variant).
+//
+// A table upsert that misses L2 costs a random 32-byte DRAM sector read plus its write-back;
+// measured on B200 that path saturates at ~15 G upserts/s, while the same upsert on an
+// L2-resident window runs at 65-79 G/s (profiles/, mfkc_gups_ex modes 1 and 3).  So keys are
+// first PARTITIONED by the table region their home slot falls in (region = 2^region_shift slots,
+// 8 MiB by default) into a staging buffer -- streaming writes -- and later DRAINED region by
+// region, so that all upserts of a region hit L2 and the region's sectors cross the HBM bus
+// once in and once out, whatever the number of k-mer instances.
+//   phase A  extract_partition_kernel / partition_keys_kernel   (per submitted batch)
+//   phase B  drain_regions_kernel                               (when staging is full / at flush)
+// A region segment that is full sends its keys straight to the table (slow but exact), so the
+// staging buffer never needs exact sizing.
+// ------------------------------------------------------------------------------------------
+constexpr int MAX_REGIONS = 2048;
+constexpr int PT_THREADS = 512;
+
+struct RegionStage {
+    unsigned long long *keys;     // region r owns keys[r*seg_cap, (r+1)*seg_cap)
+    unsigned int *cursor;         // per-region fill; values above seg_cap mean "the rest went direct"
+    uint64_t seg_cap;             // < 2^31
+    uint32_t n_regions;
+    int region_shift;             // log2(slots per region); table capacity = n_regions << region_shift
+};
+
+// Stage the (up to 16) keys of one thread.  s_hist must be zeroed and the block synchronised
+// before the call; contains two block-wide barriers.
+template <int NT>
+__device__ __forceinline__ uint32_t stage_keys_block(const uint64_t (&keys)[16], uint32_t valid, const RegionStage &rs,
+                                                     Slot *__restrict__ tab, uint64_t cap, uint32_t *s_hist) {
+    uint32_t tag[16];                                   // (region << 16) | rank-in-tile
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        tag[j] = 0;
+        if ((valid >> j) & 1) {
+            const uint32_t region = (uint32_t)(home_slot(keys[j], cap) >> rs.region_shift);
+            const uint32_t rank = atomicAdd(&s_hist[region], 1u);
+            tag[j] = (region << 16) | rank;             // a tile holds <= NT*16 = 8192 keys: rank < 2^16
+        }
+    }
+    __syncthreads();
+    // one global reservation per (tile, non-empty region)
+    for (uint32_t r = threadIdx.x; r < rs.n_regions; r += NT) {
+        const uint32_t c = s_hist[r];
+        if (c) s_hist[r] = atomicAdd(&rs.cursor[r], c);
+    }
+    __syncthreads();
+    uint32_t claimed = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if ((valid >> j) & 1) {
+            const uint32_t region = tag[j] >> 16;
+            const uint64_t pos = (uint64_t)s_hist[region] + (tag[j] & 0xFFFFu);
+            if (pos < rs.seg_cap) rs.keys[(uint64_t)region * rs.seg_cap + pos] = keys[j];
+            else claimed += table_upsert1(tab, cap, keys[j]) ? 1u : 0u;     // segment full: count directly
+        }
+    }
+    return claimed;
+}
+
+__global__ void __launch_bounds__(PT_THREADS)
+extract_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
+                         int k, RegionStage rs, Slot *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr) {
+    __shared__ uint32_t s_words[PT_THREADS + 2];
+    __shared__ uint32_t s_flags[PT_THREADS / 2 + 2];
+    __shared__ uint32_t s_hist[MAX_REGIONS];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t n_words = (n_bases + 15) >> 4;
+    const uint64_t n_tiles = (n_words + PT_THREADS - 1) / PT_THREADS;
+    const uint64_t n_flag_words = (n_bases + 31) >> 5;
+    uint32_t claimed = 0, bad = 0;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t w_base = tile * PT_THREADS;
+        for (uint32_t r = tid; r < rs.n_regions; r += PT_THREADS) s_hist[r] = 0;
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            if (rep == 1 && tid >= 2) break;
+            const uint32_t slot = rep ? PT_THREADS + tid : tid;
+            const uint64_t w = w_base + slot;
+            uint32_t word = 0;
+            const uint64_t b0 = w << 4;
+            if (b0 + 16 <= n_bases) {
+                const uint4 v = ld_nc_u128(bases + b0);
+                word = pack16(v);
+                bad |= bad4(v.x) | bad4(v.y) | bad4(v.z) | bad4(v.w);
+            } else if (b0 < n_bases) {
+                for (uint32_t j = 0; j < 16 && b0 + j < n_bases; j++) {
+                    const uint32_t c = bases[b0 + j];
+                    bad |= bad4(c | 0x41414100u);
+                    word |= pack4(c) >> 6 << (30 - 2 * j);
+                }
+            }
+            s_words[slot] = word;
+        }
+        if (tid < PT_THREADS / 2 + 2) {
+            const uint64_t fw = (w_base >> 1) + tid;
+            s_flags[tid] = fw < n_flag_words ? flags[fw] : 0u;
+        }
+        __syncthreads();
+        const uint64_t w = w_base + tid;
+        uint64_t keys[16];
+        uint32_t valid = 0;
+        if ((w << 4) < n_bases) {
+            const uint32_t w0 = s_words[tid], w1 = s_words[tid + 1], w2 = s_words[tid + 2];
+            const uint32_t f0 = s_flags[tid >> 1], f1 = s_flags[(tid >> 1) + 1], f2 = s_flags[(tid >> 1) + 2];
+            const uint64_t fbits = (tid & 1) ? (((uint64_t)f0 >> 16) | ((uint64_t)f1 << 16) | ((uint64_t)f2 << 48))
+                                             : ((uint64_t)f0 | ((uint64_t)f1 << 32));
+            const long long limit = (long long)n_bases - k - (long long)(w << 4);
+            valid = kmers_of_word(w0, w1, w2, fbits, limit, k, keys);
+        }
+        claimed += stage_keys_block<PT_THREADS>(keys, valid, rs, tab, cap, s_hist);
+        __syncthreads();
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+    if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
+}
+
+// phase A for keys that already exist as an array (receive side of the shard exchange)
+__global__ void __launch_bounds__(PT_THREADS)
+partition_keys_kernel(const unsigned long long *__restrict__ in, uint64_t n, RegionStage rs,
+                      Slot *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr) {
+    __shared__ uint32_t s_hist[MAX_REGIONS];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t tile_keys = (uint64_t)PT_THREADS * 16;
+    const uint64_t n_tiles = (n + tile_keys - 1) / tile_keys;
+    uint32_t claimed = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (uint32_t r = tid; r < rs.n_regions; r += PT_THREADS) s_hist[r] = 0;
+        __syncthreads();
+        uint64_t keys[16];
+        uint32_t valid = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {                   // coalesced: consecutive threads, consecutive keys
+            const uint64_t i = tile * tile_keys + (uint64_t)j * PT_THREADS + tid;
+            keys[j] = 0;
+            if (i < n) { keys[j] = in[i]; valid |= 1u << j; }
+        }
+        claimed += stage_keys_block<PT_THREADS>(keys, valid, rs, tab, cap, s_hist);
+        __syncthreads();
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+}
+
+// phase B: blocks_per_region consecutive CTAs own one region; the hardware launches CTAs in
+// index order, so only (resident CTAs / blocks_per_region) regions are live at any time.
+__global__ void __launch_bounds__(256)
+drain_regions_kernel(RegionStage rs, uint32_t blocks_per_region, Slot *__restrict__ tab, uint64_t cap,
+                     Counters *__restrict__ ctr) {
+    const uint32_t region = blockIdx.x / blocks_per_region;
+    const uint32_t sub = blockIdx.x % blocks_per_region;
+    uint64_t n = rs.cursor[region];
+    if (n > rs.seg_cap) n = rs.seg_cap;
+    const unsigned long long *__restrict__ keys = rs.keys + (uint64_t)region * rs.seg_cap;
+    uint32_t claimed = 0;
+    for (uint64_t i = (uint64_t)sub * 256 + threadIdx.x; i < n; i += (uint64_t)blocks_per_region * 256)
+        claimed += table_upsert1(tab, cap, keys[i]) ? 1u : 0u;
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
 
 // receive side of the shard exchange / generic "count these keys"

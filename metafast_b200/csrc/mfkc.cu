@@ -18,11 +18,11 @@ using namespace mfkc;
 // profiling slots
 // ------------------------------------------------------------------------------------------
 enum ProfSlot {
-    P_MARK = 0, P_EXTRACT_COUNT, P_EXTRACT_BUCKET, P_COUNT_KEYS, P_REHASH, P_CLEAR, P_HIST, P_COMPACT,
+    P_MARK = 0, P_EXTRACT_COUNT, P_EXTRACT_PARTITION, P_DRAIN, P_EXTRACT_BUCKET, P_COUNT_KEYS, P_REHASH, P_CLEAR, P_HIST, P_COMPACT,
     P_SORT, P_RECORDS, P_RLE, P_FC_BUILD, P_FC_RECORDS, P_FC_READS, P_FC_FEATURES, P_GUPS, P_SYNTH, P_NSLOTS
 };
 static const char *kProfNames[P_NSLOTS] = {
-    "mark_read_ends", "extract_count", "extract_bucket", "count_keys", "rehash", "table_clear", "table_hist",
+    "mark_read_ends", "extract_count", "extract_partition", "drain_regions", "extract_bucket", "count_keys", "rehash", "table_clear", "table_hist",
     "table_compact", "radix_sort", "records", "rle", "fc_build", "fc_records", "fc_reads", "fc_features",
     "gups", "synth"};
 
@@ -52,6 +52,13 @@ struct mfkc_ctx {
     uint64_t distinct_ub = 0;          // host-side upper bound of occupied slots
     uint64_t kmers_ub_total = 0;       // cumulative upper bound of submitted k-mer instances
     uint64_t max_table_bytes = 0;
+    // region-blocked staging (MFKC_VARIANT_HASH)
+    unsigned long long *rb_keys = nullptr; unsigned int *rb_cursor = nullptr;
+    uint64_t rb_cap = 0;               // staging capacity in keys
+    uint64_t rb_cap_max = 0;           // adaptive growth limit
+    uint64_t staged_ub = 0;            // upper bound of keys staged since the last drain
+    uint32_t n_regions = 1; int region_shift = 19;
+    cudaEvent_t ev_drain = nullptr; bool drain_pending = false; uint64_t kmers_at_drain = 0;
 
     // sort variant
     unsigned long long *sv_keys = nullptr; uint64_t sv_cap = 0, sv_ub = 0;
@@ -136,7 +143,7 @@ static int sync_all(mfkc_ctx *ctx) {
     CU_TRY(cudaStreamSynchronize(ctx->st[0].stream));
     CU_TRY(cudaStreamSynchronize(ctx->st[1].stream));
     CU_TRY(cudaStreamSynchronize(ctx->compute));
-    ctx->st[0].pending = ctx->st[1].pending = false;
+    ctx->st[0].pending = ctx->st[1].pending = false; ctx->drain_pending = false;
     return MFKC_OK;
 }
 
@@ -158,6 +165,16 @@ extern "C" int mfkc_device_count(void) {
 
 extern "C" const char *mfkc_last_error(const mfkc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
+// Round a requested capacity to whole regions: cap = n_regions << shift, n_regions <= MAX_REGIONS.
+static void plan_regions(const mfkc_ctx *ctx, uint64_t slots, uint64_t *cap, uint32_t *n_regions, int *shift) {
+    int sh = ctx->cfg.region_shift ? (int)ctx->cfg.region_shift : 19;
+    if (slots < (1ull << sh) && !ctx->cfg.region_shift) { sh = 10; while ((1ull << sh) < slots) sh++; }
+    uint64_t n = (slots + (1ull << sh) - 1) >> sh;
+    while (n > (uint64_t)MAX_REGIONS) { sh++; n = (slots + (1ull << sh) - 1) >> sh; }
+    if (n < 1) n = 1;
+    *cap = n << sh; *n_regions = (uint32_t)n; *shift = sh;
+}
+
 static int table_alloc(mfkc_ctx *ctx, uint64_t slots, Slot **out) {
     Slot *t = nullptr;
     cudaError_t e = cudaMalloc(&t, slots * sizeof(Slot));
@@ -176,7 +193,10 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     if (cfg->struct_size != sizeof(mfkc_cfg)) { g_create_err = "mfkc_cfg.struct_size mismatch"; return MFKC_E_BADARG; }
     if (cfg->k <= 0) { g_create_err = "The size of k-mer must be at least 1."; return MFKC_E_BADARG; }        // KmersCounterMain.java:66-69
     if (cfg->k > 31) { g_create_err = "The size of k-mer must be no more than 31."; return MFKC_E_BADARG; }   // KmersCounterMain.java:70-73
-    if (cfg->variant != MFKC_VARIANT_HASH && cfg->variant != MFKC_VARIANT_SORT) { g_create_err = "unknown variant"; return MFKC_E_BADARG; }
+    if (cfg->variant != MFKC_VARIANT_HASH && cfg->variant != MFKC_VARIANT_SORT && cfg->variant != MFKC_VARIANT_HASH_DIRECT) {
+        g_create_err = "unknown variant"; return MFKC_E_BADARG;
+    }
+    if (cfg->region_shift && (cfg->region_shift < 4 || cfg->region_shift > 30)) { g_create_err = "bad region_shift"; return MFKC_E_BADARG; }
     if (cfg->n_shards > 64 || (cfg->n_shards > 1 && (cfg->shard_id < 0 || cfg->shard_id >= cfg->n_shards))) {
         g_create_err = "bad shard configuration"; return MFKC_E_BADARG;
     }
@@ -200,6 +220,7 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
         CR_TRY(cudaMallocHost(&ctx->st[i].h_snap, sizeof(unsigned long long)));
     }
     CR_TRY(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    CR_TRY(cudaEventCreateWithFlags(&ctx->ev_drain, cudaEventDisableTiming));
     CR_TRY(cudaEventCreate(&ctx->t0));
     CR_TRY(cudaEventCreate(&ctx->t1));
     CR_TRY(cudaMalloc(&ctx->d_ctr, sizeof(Counters)));
@@ -219,15 +240,19 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     CR_TRY(cudaMemGetInfo(&free_b, &total_b));
     ctx->max_table_bytes = cfg->max_table_bytes ? cfg->max_table_bytes : (uint64_t)(free_b * 0.8);
 
-    if (cfg->variant == MFKC_VARIANT_HASH) {
+    if (cfg->variant != MFKC_VARIANT_SORT) {
         uint64_t slots = cfg->table_slots;
         if (!slots && cfg->expected_distinct) slots = cfg->expected_distinct * 2;      // load 0.5
         if (!slots) slots = 1ull << 22;                                                // 64 MiB, grows on demand
         if (slots < 1024) slots = 1024;
         if (slots * sizeof(Slot) > ctx->max_table_bytes) slots = ctx->max_table_bytes / sizeof(Slot);
+        plan_regions(ctx, slots, &slots, &ctx->n_regions, &ctx->region_shift);
         int r = table_alloc(ctx, slots, &ctx->tab);
         if (r != MFKC_OK) return bail(r);
         ctx->cap = slots;
+        CR_TRY(cudaMalloc(&ctx->rb_cursor, MAX_REGIONS * sizeof(unsigned int)));
+        CR_TRY(cudaMemset(ctx->rb_cursor, 0, MAX_REGIONS * sizeof(unsigned int)));
+        ctx->rb_cap_max = (uint64_t)(total_b * 0.25) / 8;
     }
     CR_TRY(cudaDeviceSynchronize());
 #undef CR_TRY
@@ -257,6 +282,7 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     }
     if (ctx->compute) cudaStreamDestroy(ctx->compute);
     free_emit(ctx);
+    cudaFree(ctx->rb_keys); cudaFree(ctx->rb_cursor);
     cudaFree(ctx->tab); cudaFree(ctx->sv_keys); cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts);
     cudaFree(ctx->d_bucket_cursor); cudaFree(ctx->d_bucket_base);
     if (ctx->h_bucket) cudaFreeHost(ctx->h_bucket);
@@ -265,6 +291,7 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
     cudaFree(ctx->fc_tab); cudaFree(ctx->fc_keys); cudaFree(ctx->fc_off); cudaFree(ctx->fc_sel);
     cudaFree(ctx->d_synth);
+    if (ctx->ev_drain) cudaEventDestroy(ctx->ev_drain);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     for (void *p : ctx->pinned) cudaFreeHost(p);
@@ -280,7 +307,9 @@ extern "C" int mfkc_reset(mfkc_ctx *ctx) {
         table_clear_kernel<<<grid_for(ctx, ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap);
     }
     CU_TRY(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->compute));
+    if (ctx->rb_cursor) CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS * sizeof(unsigned int), ctx->compute));
     CU_TRY(cudaStreamSynchronize(ctx->compute));
+    ctx->staged_ub = 0;
     ctx->distinct_ub = 0; ctx->kmers_ub_total = 0; ctx->sv_ub = 0; ctx->svs_n = 0;
     cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts); ctx->svs_keys = nullptr; ctx->svs_counts = nullptr;
     ctx->hist_valid = false; ctx->dirty = false;
@@ -313,6 +342,12 @@ static constexpr double kMaxLoad = 0.60;     // never exceeded: checked against 
 static constexpr double kGrowLoad = 0.30;    // load right after growing
 
 static void poll_snapshots(mfkc_ctx *ctx) {
+    if (ctx->drain_pending && cudaEventQuery(ctx->ev_drain) == cudaSuccess) {
+        ctx->drain_pending = false;
+        const uint64_t cand = *ctx->st[0].h_snap + (ctx->kmers_ub_total - ctx->kmers_at_drain);
+        if (cand < ctx->distinct_ub) ctx->distinct_ub = cand;
+    }
+    if (ctx->cfg.variant != MFKC_VARIANT_HASH_DIRECT) return;
     for (int i = 0; i < 2; i++) {
         Staging &s = ctx->st[i];
         if (s.pending && cudaEventQuery(s.ev_done) == cudaSuccess) {
@@ -331,6 +366,9 @@ static int grow_table(mfkc_ctx *ctx, uint64_t need_slots) {
     const uint64_t fit = (uint64_t)(free_b * 0.95) / sizeof(Slot);          // old table stays alive during the rehash
     if (new_cap > limit) new_cap = limit;
     if (new_cap > fit) new_cap = fit;
+    uint32_t nr = 1; int sh = 19;
+    plan_regions(ctx, new_cap, &new_cap, &nr, &sh);
+    while (new_cap > std::min(limit, fit) && new_cap > (1ull << sh)) new_cap -= 1ull << sh, nr--;
     if (new_cap <= ctx->cap) return fail(ctx, MFKC_E_TABLE_FULL, "k-mer table cannot grow: device memory exhausted");
     Slot *nt = nullptr;
     TRY(table_alloc(ctx, new_cap, &nt));
@@ -342,13 +380,17 @@ static int grow_table(mfkc_ctx *ctx, uint64_t need_slots) {
     CU_TRY(cudaStreamSynchronize(ctx->compute));
     CU_TRY(cudaFree(ctx->tab));
     ctx->tab = nt; ctx->cap = new_cap;
+    ctx->n_regions = nr; ctx->region_shift = sh;
     return MFKC_OK;
 }
 
 // Guarantee that `add` more upserts cannot push the load above kMaxLoad.
+static int drain_regions(mfkc_ctx *ctx);
+
 static int reserve_slots(mfkc_ctx *ctx, uint64_t add) {
     poll_snapshots(ctx);
     if ((double)(ctx->distinct_ub + add) <= kMaxLoad * (double)ctx->cap) { ctx->distinct_ub += add; return MFKC_OK; }
+    TRY(drain_regions(ctx));              // staged keys must be in the table before it is measured / rehashed
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
     ctx->distinct_ub = ctx->h_ctr->distinct;
@@ -370,6 +412,67 @@ static int reserve_slots(mfkc_ctx *ctx, uint64_t add) {
 // ------------------------------------------------------------------------------------------
 // ingest
 // ------------------------------------------------------------------------------------------
+static RegionStage region_stage(const mfkc_ctx *ctx) {
+    RegionStage rs;
+    rs.keys = ctx->rb_keys; rs.cursor = ctx->rb_cursor;
+    rs.n_regions = ctx->n_regions; rs.region_shift = ctx->region_shift;
+    uint64_t seg = ctx->rb_cap / ctx->n_regions;
+    if (seg > 0x7fffffffull) seg = 0x7fffffffull;
+    rs.seg_cap = seg;
+    return rs;
+}
+
+// phase B: upsert every staged key, region by region (asynchronous on the compute stream)
+static int drain_regions(mfkc_ctx *ctx) {
+    if (ctx->cfg.variant != MFKC_VARIANT_HASH || ctx->staged_ub == 0 || !ctx->rb_keys) return MFKC_OK;
+    const RegionStage rs = region_stage(ctx);
+    const uint64_t per_region = ctx->staged_ub / ctx->n_regions + 1;
+    uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 2048));
+    {
+        ProfScope ps(ctx, P_DRAIN, ctx->compute);
+        drain_regions_kernel<<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(rs, bpr, ctx->tab, ctx->cap, ctx->d_ctr);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS * sizeof(unsigned int), ctx->compute));
+    // distinct is exact for everything submitted so far once this point of the stream is reached
+    Staging &s0 = ctx->st[0];
+    CU_TRY(cudaMemcpyAsync(s0.h_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaEventRecord(ctx->ev_drain, ctx->compute));
+    ctx->drain_pending = true;
+    ctx->kmers_at_drain = ctx->kmers_ub_total;
+    ctx->staged_ub = 0;
+    return MFKC_OK;
+}
+
+// make room for `add` more staged keys (drains, and grows the adaptive staging buffer)
+static int reserve_staging(mfkc_ctx *ctx, uint64_t add) {
+    const uint64_t hard = 4000000000ull;          // cursors are 32-bit
+    if (!ctx->rb_keys) {
+        uint64_t want = ctx->cfg.staging_bytes ? ctx->cfg.staging_bytes / 8 : std::max<uint64_t>(4 * add, 1ull << 22);
+        if (!ctx->cfg.staging_bytes && want > ctx->rb_cap_max) want = std::max<uint64_t>(ctx->rb_cap_max, add);
+        if (want < add) want = add;
+        cudaError_t e = cudaMalloc(&ctx->rb_keys, want * 8);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, MFKC_E_OOM, "cannot allocate the key staging buffer"); }
+        ctx->rb_cap = want;
+    }
+    if (ctx->staged_ub + add <= std::min(ctx->rb_cap, hard)) return MFKC_OK;
+    TRY(drain_regions(ctx));
+    const bool adaptive = !ctx->cfg.staging_bytes;
+    if (add > ctx->rb_cap || (adaptive && ctx->rb_cap < ctx->rb_cap_max)) {
+        // the buffer filled up: double it (bounded), so later drains sweep the table less often
+        uint64_t want = std::max<uint64_t>(ctx->rb_cap * 2, add);
+        if (adaptive && want > ctx->rb_cap_max) want = std::max<uint64_t>(ctx->rb_cap_max, add);
+        if (want > ctx->rb_cap) {
+            TRY(sync_all(ctx));
+            cudaFree(ctx->rb_keys); ctx->rb_keys = nullptr; ctx->rb_cap = 0;
+            cudaError_t e = cudaMalloc(&ctx->rb_keys, want * 8);
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, MFKC_E_OOM, "cannot grow the key staging buffer"); }
+            ctx->rb_cap = want;
+        }
+    }
+    return MFKC_OK;
+}
+
 static int ensure_staging(mfkc_ctx *ctx, Staging &s, uint64_t n_bases, uint64_t n_offsets, bool need_bases) {
     if (need_bases && n_bases + 64 > s.cap_bases) {
         CU_TRY(cudaStreamSynchronize(s.stream)); CU_TRY(cudaStreamSynchronize(ctx->compute));
@@ -419,12 +522,19 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
                               uint32_t n_reads, uint64_t n_bases) {
     const int k = ctx->cfg.k;
     const uint64_t kmers_ub = n_bases >= (uint64_t)k ? n_bases - k + 1 : 0;
-    if (ctx->cfg.variant == MFKC_VARIANT_HASH) TRY(reserve_slots(ctx, kmers_ub));
-    else TRY(sort_variant_reserve(ctx, kmers_ub));
+    if (ctx->cfg.variant == MFKC_VARIANT_SORT) TRY(sort_variant_reserve(ctx, kmers_ub));
+    else TRY(reserve_slots(ctx, kmers_ub));
+    if (ctx->cfg.variant == MFKC_VARIANT_HASH) { TRY(reserve_staging(ctx, kmers_ub)); ctx->staged_ub += kmers_ub; }
     ctx->kmers_ub_total += kmers_ub;
     TRY(launch_mark(ctx, s, d_offsets, n_reads, n_bases, ctx->cfg.min_seq_len, 1, ctx->d_ctr));
     if (n_bases >= (uint64_t)k) {
         if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
+            ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
+            const uint64_t tiles = ((n_bases + 15) / 16 + PT_THREADS - 1) / PT_THREADS;
+            const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 2);
+            extract_partition_kernel<<<grid, PT_THREADS, 0, ctx->compute>>>(
+                d_bases, n_bases, s.d_flags, k, region_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr);
+        } else if (ctx->cfg.variant == MFKC_VARIANT_HASH_DIRECT) {
             ProfScope ps(ctx, P_EXTRACT_COUNT, ctx->compute);
             SinkTable sink{ctx->tab, ctx->cap, ctx->d_ctr};
             extract_kernel<SinkTable><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
@@ -437,9 +547,10 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
         }
         CU_TRY(cudaGetLastError());
     }
-    CU_TRY(cudaMemcpyAsync(s.h_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
+    if (ctx->cfg.variant == MFKC_VARIANT_HASH_DIRECT)
+        CU_TRY(cudaMemcpyAsync(s.h_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
     CU_TRY(cudaEventRecord(s.ev_done, ctx->compute));
-    s.pending = true;
+    s.pending = ctx->cfg.variant == MFKC_VARIANT_HASH_DIRECT;
     s.kmers_submitted_at_end = ctx->kmers_ub_total;
     ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
     return MFKC_OK;
@@ -481,9 +592,10 @@ extern "C" int mfkc_submit_reads_device(mfkc_ctx *ctx, const uint8_t *d_bases, c
 extern "C" int mfkc_flush(mfkc_ctx *ctx) {
     if (!ctx) return MFKC_E_BADARG;
     CU_TRY(cudaSetDevice(ctx->device));
+    TRY(drain_regions(ctx));
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
-    if (ctx->cfg.variant == MFKC_VARIANT_HASH) ctx->distinct_ub = ctx->h_ctr->distinct;
+    if (ctx->cfg.variant != MFKC_VARIANT_SORT) ctx->distinct_ub = ctx->h_ctr->distinct;
     ctx->dirty = false;
     if (ctx->h_ctr->bad_chars) return fail(ctx, MFKC_E_FORMAT, "Incorrect nucleotide char in submitted reads (only AaCcGgTt are accepted)");
     if (ctx->h_ctr->overflow) return fail(ctx, MFKC_E_STATE, "internal key buffer overflow");
@@ -649,7 +761,7 @@ extern "C" int mfkc_stats(mfkc_ctx *ctx, uint64_t stats[6]) {
     TRY(finalize_counts(ctx));
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
-    stats[0] = ctx->cfg.variant == MFKC_VARIANT_HASH ? ctx->h_ctr->distinct : ctx->svs_n;
+    stats[0] = ctx->cfg.variant != MFKC_VARIANT_SORT ? ctx->h_ctr->distinct : ctx->svs_n;
     stats[1] = ctx->h_ctr->kmers;
     stats[2] = ctx->h_ctr->total_seq; stats[3] = ctx->h_ctr->good_seq;
     stats[4] = ctx->h_ctr->total_len; stats[5] = ctx->h_ctr->good_len;
@@ -663,7 +775,7 @@ static int compute_hist(mfkc_ctx *ctx) {
     CU_TRY(cudaMemsetAsync(ctx->d_hist, 0, MFKC_HIST_BINS * sizeof(unsigned long long), st));
     {
         ProfScope ps(ctx, P_HIST, st);
-        if (ctx->cfg.variant == MFKC_VARIANT_HASH)
+        if (ctx->cfg.variant != MFKC_VARIANT_SORT)
             table_hist_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, st>>>(ctx->tab, ctx->cap, ctx->d_hist);
         else if (ctx->svs_n)
             pairs_hist_kernel<<<grid_for(ctx, ctx->svs_n, 256, 8), 256, 0, st>>>(ctx->svs_counts, ctx->svs_n, ctx->d_hist);
@@ -745,7 +857,7 @@ extern "C" int mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_goo
     if (good) {
         CU_TRY(cudaMalloc(&ctx->em_keys, (size_t)good * 8));
         CU_TRY(cudaMalloc(&ctx->em_counts, (size_t)good * 2));
-        if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
+        if (ctx->cfg.variant != MFKC_VARIANT_SORT) {
             unsigned long long *k2 = nullptr; uint16_t *c2 = nullptr;
             CU_TRY(cudaMalloc(&k2, (size_t)good * 8));
             CU_TRY(cudaMalloc(&c2, (size_t)good * 2));
@@ -863,22 +975,30 @@ extern "C" int mfkc_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, cons
 
 extern "C" int mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uint64_t n) {
     if (!ctx || (!d_keys && n)) return fail(ctx, MFKC_E_BADARG, "null argument");
-    if (ctx->cfg.variant != MFKC_VARIANT_HASH) return fail(ctx, MFKC_E_STATE, "mfkc_count_keys_device needs the hash variant");
+    if (ctx->cfg.variant == MFKC_VARIANT_SORT) return fail(ctx, MFKC_E_STATE, "mfkc_count_keys_device needs a hash variant");
     if (n == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(reserve_slots(ctx, n));
+    if (ctx->cfg.variant == MFKC_VARIANT_HASH) { TRY(reserve_staging(ctx, n)); ctx->staged_ub += n; }
     ctx->kmers_ub_total += n;
     Staging &s = ctx->st[ctx->next_buf];
     ctx->next_buf ^= 1;
-    {
+    if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
+        ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
+        const uint64_t tiles = (n + PT_THREADS * 16 - 1) / (PT_THREADS * 16);
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 2);
+        partition_keys_kernel<<<grid, PT_THREADS, 0, ctx->compute>>>(
+            reinterpret_cast<const unsigned long long *>(d_keys), n, region_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr);
+    } else {
         ProfScope ps(ctx, P_COUNT_KEYS, ctx->compute);
         count_keys_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->compute>>>(
             reinterpret_cast<const unsigned long long *>(d_keys), n, ctx->tab, ctx->cap, ctx->d_ctr);
     }
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(s.h_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
+    if (ctx->cfg.variant == MFKC_VARIANT_HASH_DIRECT)
+        CU_TRY(cudaMemcpyAsync(s.h_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
     CU_TRY(cudaEventRecord(s.ev_done, ctx->compute));
-    s.pending = true; s.kmers_submitted_at_end = ctx->kmers_ub_total;
+    s.pending = ctx->cfg.variant == MFKC_VARIANT_HASH_DIRECT; s.kmers_submitted_at_end = ctx->kmers_ub_total;
     ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
     return MFKC_OK;
 }

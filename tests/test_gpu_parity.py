@@ -16,7 +16,7 @@ from tests.conftest import GOLDEN, INPUTS
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [m.VARIANT_HASH, m.VARIANT_SORT]
+VARIANTS = [m.VARIANT_HASH, m.VARIANT_SORT, m.VARIANT_HASH_DIRECT]
 
 
 def run_counter(reads_batches, k, b, variant, min_len=0, **kw):
@@ -103,11 +103,24 @@ def test_empty_inputs(built, variant):
     assert rec == b"" and st["total_seq"] == 3 and st["kmers"] == 0
 
 
-def test_table_growth(built):
+@pytest.mark.parametrize("variant", [m.VARIANT_HASH, m.VARIANT_HASH_DIRECT])
+def test_table_growth(built, variant):
     """the table starts tiny and must grow (Long2ShortHashMap.enlargeAndRehash analogue)."""
     rng = np.random.default_rng(7)
     reads = ["".join(rng.choice(list("ACGT"), 150)) for _ in range(4000)]
-    check_against_oracle(reads, 31, 0, m.VARIANT_HASH, batches=16, table_slots=1024)
+    check_against_oracle(reads, 31, 0, variant, batches=16, table_slots=1024)
+
+
+@pytest.mark.parametrize("region_shift,staging_bytes", [(4, 0), (6, 8 * 5000), (8, 8 * 200000), (10, 8 * 100)])
+def test_region_blocking_geometry(built, region_shift, staging_bytes):
+    """Region-blocked hash variant with many tiny regions, staging buffers that overflow (keys then
+    go straight to the table), repeated drains and table growth in between."""
+    rng = np.random.default_rng(11)
+    genome = "".join(rng.choice(list("ACGT"), 20000))
+    reads = [genome[int(i):int(i) + 120] for i in rng.integers(0, len(genome) - 120, 6000)]
+    reads += ["A" * 100] * 300                       # one very hot key: a single region takes the surplus
+    check_against_oracle(reads, 25, 1, m.VARIANT_HASH, batches=12, table_slots=4096,
+                         region_shift=region_shift, staging_bytes=staging_bytes)
 
 
 @pytest.mark.parametrize("variant", VARIANTS)

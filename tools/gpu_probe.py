@@ -5,12 +5,13 @@ import numpy as np
 import metafast_b200 as m
 
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
-variant = m.VARIANT_SORT if len(sys.argv) > 2 and sys.argv[2] == "sort" else m.VARIANT_HASH
+variant = {"sort": m.VARIANT_SORT, "direct": m.VARIANT_HASH_DIRECT}.get(sys.argv[2] if len(sys.argv) > 2 else "", m.VARIANT_HASH)
 batch = int(sys.argv[3]) if len(sys.argv) > 3 else 1_000_000
 hint = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 cfg = m.synth_cfg()
-with m.KmerCounter(31, variant=variant, expected_distinct=hint) as kc:
-    for gb in (1, 8, 32):
+stg = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+with m.KmerCounter(31, variant=variant, expected_distinct=hint, staging_bytes=stg) as kc:
+    for gb in ():
         for dep in (False, True):
             nupd = 1 << 29
             ms = kc.gups(gb << 30, nupd, 1 if dep else 0)
