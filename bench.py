@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- canonical 31-mers counted per second (BASELINE.json metric) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
+
+Workload (BASELINE.json configs[1]): synthetic Illumina-like 150 bp reads, 20 M reads of one
+sample (community of 64 random genomes, 150 Mbp, log-normal abundances, 0.1 -> 1 % substitution
+ramp, 0.1 % N-reads dropped by the parser rule), k = 31, -b 2.  One STEP = one whole pass of the
+hot path over that sample: 2-bit pack + canonical k-mer extraction + counting + histogram +
+threshold filter + key-sorted big-endian records.
+
+  value  k-mers/s with the parsed reads already resident in HBM (device time, CUDA events).
+  e2e    the same step through the C ABI with HOST (pinned) buffers: every step copies the reads
+         host->device and the records + histogram device->host inside the timed region.
+  N > 1  one process per GPU (torchrun): every rank extracts the k-mers of ITS OWN 20 M reads
+         (weak scaling), buckets them by owner shard, exchanges them with an NCCL all-to-all and
+         counts only its own hash range (BASELINE.json configs[3] layout).
+
+The JSON line also carries `roofline` (counting kernels vs the measured HBM peak, plus the
+random-sector GUPS peak measured in the same run) and `cpu_baseline` (the C restatement of the
+reference's CPU algorithm -- oracle/ref_cpu.c -- on a bounded sample, rank 0, N = 1 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 31
+B_THRESHOLD = 2
+READ_LEN = 150
+N_READS = int(os.environ.get("MFKC_BENCH_READS", 20_000_000))          # per GPU
+BATCH_READS = int(os.environ.get("MFKC_BENCH_BATCH", 1_000_000))
+CPU_SAMPLE_READS = int(os.environ.get("MFKC_BENCH_CPU_READS", 1_000_000))
+ALGO_BYTES_PER_KMER = 64.0 + 0.25 * READ_LEN / (READ_LEN - K + 1)       # 64.3125
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ clocks under load
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _run(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 7:
+                self.samples.append(f)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for f in self.samples:
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference arm (CPU)
+def cpu_reference_run(n_reads, threads, seed_first=0):
+    """Time the C restatement of the reference's CPU algorithm (oracle/ref_cpu.c: P worker threads,
+    synchronized 32768-read dispatcher with the 2-bit pack inside, striped linear-probing maps,
+    iteration-order emit + histogram) on `n_reads` reads of the workload.  Returns (kmers, secs)."""
+    import numpy as np
+    import metafast_b200 as m
+    from tests import _oracle_c
+    lib = _oracle_c.load()
+    cfg = m.synth_cfg()
+    raw = m.synth_reads_host(cfg, seed_first, n_reads)
+    keep = ~(raw == ord("N")).any(axis=1)                       # the parser drops reads with N
+    bases = np.ascontiguousarray(raw[keep]).reshape(-1)
+    nk = int(keep.sum())
+    offsets = np.arange(nk + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+    t0 = time.perf_counter()
+    hm = lib.orc_map_new(threads)
+    rc = lib.orc_count_reads(hm, bases.ctypes.data, offsets.ctypes.data, nk, K, 0, threads)
+    assert rc == 0
+    hist = np.zeros(32768, dtype=np.uint64)
+    good = lib.orc_emit(hm, B_THRESHOLD, None, 0, hist.ctypes.data, 0)      # count pass (sizes the buffer)
+    out = np.empty(max(good, 1) * 10, dtype=np.uint8)
+    hist[:] = 0
+    lib.orc_emit(hm, B_THRESHOLD, out.ctypes.data, good, hist.ctypes.data, 0)
+    dt = time.perf_counter() - t0
+    lib.orc_map_free(hm)
+    return nk * (READ_LEN - K + 1), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+    g.build()
+    threads = os.cpu_count() or 1
+    sample = CPU_SAMPLE_READS
+    for _ in range(args.warmup and 1):
+        cpu_reference_run(min(sample, 100_000), threads)
+    kmers_tot, t_tot = 0, 0.0
+    for s in range(args.steps):
+        kmers, dt = cpu_reference_run(sample, threads, seed_first=0)
+        kmers_tot += kmers; t_tot += dt
+    value = kmers_tot / t_tot
+    line = {
+        "impl": "reference", "metric": "canonical 31-mers counted/s", "value": value, "unit": "kmers/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "kmers/s", "cores": threads, "kind": "port",
+                         "sample": "%d of the %d reads of the workload per step (oracle/ref_cpu.c: C restatement of the "
+                                   "reference's threaded algorithm; no JVM in the image)" % (sample, N_READS)},
+        "e2e": {"value": value, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: synthetic Illumina 150bp reads, %d reads per GPU (single sample), k=31, -b 2" % N_READS,
+            "k": K, "b": B_THRESHOLD, "read_len": READ_LEN, "reads_per_gpu": N_READS, "batch_reads": BATCH_READS,
+            "variant": os.environ.get("MFKC_BENCH_VARIANT", "hash (region-blocked)"),
+            "parallelism": "1 GPU" if n_gpus == 1 else "hash-range sharded over %d GPUs, NCCL all-to-all" % n_gpus,
+            "l2": "inputs (3 GB reads, multi-GB table) are far larger than the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------ this repository's arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mfkc", choices=["mfkc", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import metafast_b200 as m
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if m.load().mfkc_device_count() <= 0:
+        raise SystemExit("bench.py needs a CUDA device (libmfkc has no CPU fallback)")
+
+    variant = {"sort": m.VARIANT_SORT, "direct": m.VARIANT_HASH_DIRECT}.get(os.environ.get("MFKC_BENCH_VARIANT", ""), m.VARIANT_HASH)
+    kmers_ub = N_READS * (READ_LEN - K + 1)
+    kc = m.KmerCounter(K, device=local_rank, variant=variant, expected_kmers=kmers_ub,
+                       n_shards=world if world > 1 else 0, shard_id=rank if world > 1 else 0)
+    cfg = m.synth_cfg(sample=rank)                                   # every rank: its own reads of the community
+    # ---- synthetic parsed reads, device-resident
+    d_bases = kc.device_alloc(N_READS * READ_LEN)
+    d_offs = kc.device_alloc((N_READS + 1) * 8)
+    kept = C.c_uint64()
+    kc._ck(kc.lib.mfkc_synth_reads_device(kc.h, C.byref(cfg), rank * N_READS, N_READS, C.c_void_p(d_bases),
+                                          C.c_void_p(d_offs), C.byref(kept)))
+    n_reads = kept.value
+    n_bases = n_reads * READ_LEN
+    kmers_per_step = n_reads * (READ_LEN - K + 1)
+
+    if world > 1:
+        from metafast_b200.sharded import ShardedStep
+        sharded = ShardedStep(kc, dist, world, rank, BATCH_READS, READ_LEN, K)
+
+    def step_device():
+        """one whole pass, inputs resident in HBM"""
+        kc.reset()
+        if world > 1:
+            sharded.run_device(d_bases, d_offs, n_reads)
+        else:
+            for s in range(0, n_reads, BATCH_READS):
+                e = min(n_reads, s + BATCH_READS)
+                kc.submit_device(d_bases + s * READ_LEN, d_offs + s * 8, e - s, (e - s) * READ_LEN)
+        kc.flush()
+        return kc.emit_begin(B_THRESHOLD)
+
+    def barrier():
+        kc.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        n_good = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    kc.profile(enable=True, reset=True)
+    kc.timer_start()
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        n_good = step_device()
+    ms_total = kc.timer_stop_ms()
+    barrier()
+    wall = time.perf_counter() - t_wall
+    prof = kc.profile(enable=False)
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(ms_total)
+    st = kc.stats()
+    value = kmers_per_step * world * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the C ABI with host buffers (reads H2D, records + histogram D2H every step)
+    h_bases = kc.pinned(n_bases)
+    h_offs = kc.pinned((n_reads + 1) * 8, np.uint64)
+    kc.d2h(h_bases, d_bases)
+    kc.d2h(h_offs, d_offs)
+    h_out = kc.pinned(max(int(n_good * 1.05) + 1024, 1024) * 10)
+
+    def step_e2e():
+        kc.reset()
+        if world > 1:
+            sharded.run_host(h_bases, h_offs, n_reads)
+        else:
+            for s in range(0, n_reads, BATCH_READS):
+                e = min(n_reads, s + BATCH_READS)
+                kc.submit(h_bases, h_offs[s:e + 1])
+        kc.flush()
+        nbytes = kc.emit_into(B_THRESHOLD, h_out)
+        kc.histogram()
+        return nbytes
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_bytes = step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = kmers_per_step * world * args.steps / e2e_s
+
+    if rank != 0:
+        kc.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the counting kernels (CUDA-event durations recorded around every launch)
+    peak, peak_src = load_peaks()
+    count_kernels = {"hash (region-blocked)": ["extract_partition", "drain_regions"], "direct": ["extract_count"],
+                     "sort": ["extract_bucket", "radix_sort", "rle"]}[workload_config(1)["variant"]]
+    if world > 1:
+        count_kernels = ["extract_bucket", "extract_partition", "drain_regions"]
+    t_count_ms = sum(prof[k][0] for k in count_kernels if k in prof) / args.steps
+    launches = sum(v[1] for v in prof.values())
+    achieved = ALGO_BYTES_PER_KMER * kmers_per_step / (t_count_ms / 1e3) / 1e9 if t_count_ms else None
+    gups_ms = kc.gups(8 << 30, 1 << 28, 1)
+    gups_rate = (1 << 28) / (gups_ms / 1e3)
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+        "traffic": None, "peak_source": peak_src,
+        "kernel": "+".join(count_kernels), "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER,
+        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
+        "gups_random_sector_upserts_per_s": gups_rate,
+        "gups_algorithmic_gbs": gups_rate * 64 / 1e9,
+        "frac_of_gups": (kmers_per_step / (t_count_ms / 1e3)) / gups_rate if t_count_ms else None,
+        "note": "achieved = 64.3125 B per k-mer instance (SURVEY 8d) / summed CUDA-event time of the counting kernels; "
+                "gups_* = dependent 16 B load + red.add on random 32 B sectors of an 8 GiB table, measured in this run",
+    }
+    cpu = None
+    if world == 1 and not os.environ.get("MFKC_BENCH_NO_CPU"):
+        try:
+            import __graft_entry__ as g
+            threads = os.cpu_count() or 1
+            kmers, dt = cpu_reference_run(CPU_SAMPLE_READS, threads)
+            cpu = {"value": kmers / dt, "unit": "kmers/s", "cores": threads, "kind": "port",
+                   "sample": "first %d of the %d reads (oracle/ref_cpu.c, C restatement of the reference's threaded "
+                             "algorithm; the reference JVM cannot run here)" % (CPU_SAMPLE_READS, N_READS)}
+        except Exception as ex:                                   # the checker is optional for the measurement itself
+            cpu = {"value": None, "unit": "kmers/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    line = {
+        "metric": "canonical 31-mers counted/s", "value": value, "unit": "kmers/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": workload_config(world),
+        "e2e": {"value": e2e_value, "unit": "kmers/s", "h2d_bytes_per_step": int(n_bases + (n_reads + 1) * 8),
+                "d2h_bytes_per_step": int(out_bytes + 32768 * 8), "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "result": {"kmers_per_step_per_gpu": kmers_per_step, "distinct": st["distinct"], "records_gt_b": int(n_good),
+                   "host_wall_ms_per_step": 1e3 * wall / args.steps},
+    }
+    print(json.dumps(line))
+    kc.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,7 +73,10 @@ typedef struct mfkc_cfg {
     uint64_t staging_bytes;     /* HASH: key staging buffer; 0 = adaptive (starts at 4 batches, doubles when full) */
     uint32_t region_shift;      /* HASH: log2(table slots per region); 0 = 19 (8 MiB regions) */
     uint32_t reserved2;
-    uint64_t reserved1[2];
+    uint64_t expected_kmers;    /* sizing hint: k-mer INSTANCES of the sample (<= bases in the input files).  HASH: staging
+                                   holds them all (one drain) and, without expected_distinct, the table is sized for the
+                                   all-distinct worst case at load 0.85, memory permitting */
+    uint64_t reserved1[1];
 } mfkc_cfg;
 
 /* ---- lifecycle ------------------------------------------------------------------------

@@ -41,7 +41,8 @@ class MfkcCfg(C.Structure):
         ("staging_bytes", C.c_uint64),
         ("region_shift", C.c_uint32),
         ("reserved2", C.c_uint32),
-        ("reserved1", C.c_uint64 * 2),
+        ("expected_kmers", C.c_uint64),
+        ("reserved1", C.c_uint64 * 1),
     ]
 
 

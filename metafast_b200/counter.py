@@ -39,14 +39,14 @@ def pack_reads(reads: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
 class _Ctx:
     def __init__(self, k: int, min_seq_len: int = 0, device: int = 0, variant: int = _abi.VARIANT_HASH,
                  table_slots: int = 0, expected_distinct: int = 0, n_shards: int = 0, shard_id: int = 0,
-                 max_table_bytes: int = 0, staging_bytes: int = 0, region_shift: int = 0):
+                 max_table_bytes: int = 0, staging_bytes: int = 0, region_shift: int = 0, expected_kmers: int = 0):
         self.lib = _abi.load()
         cfg = _abi.MfkcCfg()
         cfg.struct_size = C.sizeof(_abi.MfkcCfg)
         cfg.k, cfg.min_seq_len, cfg.device, cfg.variant = k, min_seq_len, device, variant
         cfg.n_shards, cfg.shard_id = n_shards, shard_id
         cfg.table_slots, cfg.expected_distinct, cfg.max_table_bytes = table_slots, expected_distinct, max_table_bytes
-        cfg.staging_bytes, cfg.region_shift = staging_bytes, region_shift
+        cfg.staging_bytes, cfg.region_shift, cfg.expected_kmers = staging_bytes, region_shift, expected_kmers
         h = C.c_void_p()
         rc = self.lib.mfkc_create(C.byref(cfg), C.byref(h))
         if rc != 0:

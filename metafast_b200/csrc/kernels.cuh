@@ -425,15 +425,15 @@ struct RegionStage {
 template <int NT>
 __device__ __forceinline__ uint32_t stage_keys_block(const uint64_t (&keys)[16], uint32_t valid, const RegionStage &rs,
                                                      Slot *__restrict__ tab, uint64_t cap, uint32_t *s_hist) {
-    uint32_t tag[16];                                   // (region << 16) | rank-in-tile
+    uint32_t rk[8];                                     // rank-in-tile of key j: 16 bits each (tile <= 8192 keys)
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-        tag[j] = 0;
+        uint32_t rank = 0;
         if ((valid >> j) & 1) {
             const uint32_t region = (uint32_t)(home_slot(keys[j], cap) >> rs.region_shift);
-            const uint32_t rank = atomicAdd(&s_hist[region], 1u);
-            tag[j] = (region << 16) | rank;             // a tile holds <= NT*16 = 8192 keys: rank < 2^16
+            rank = atomicAdd(&s_hist[region], 1u);
         }
+        if (j & 1) rk[j >> 1] |= rank << 16; else rk[j >> 1] = rank;
     }
     __syncthreads();
     // one global reservation per (tile, non-empty region)
@@ -446,8 +446,9 @@ __device__ __forceinline__ uint32_t stage_keys_block(const uint64_t (&keys)[16],
 #pragma unroll
     for (int j = 0; j < 16; j++) {
         if ((valid >> j) & 1) {
-            const uint32_t region = tag[j] >> 16;
-            const uint64_t pos = (uint64_t)s_hist[region] + (tag[j] & 0xFFFFu);
+            const uint32_t region = (uint32_t)(home_slot(keys[j], cap) >> rs.region_shift);   // cheaper than 16 live registers
+            const uint32_t rank = (j & 1) ? (rk[j >> 1] >> 16) : (rk[j >> 1] & 0xFFFFu);
+            const uint64_t pos = (uint64_t)s_hist[region] + rank;
             if (pos < rs.seg_cap) rs.keys[(uint64_t)region * rs.seg_cap + pos] = keys[j];
             else claimed += table_upsert1(tab, cap, keys[j]) ? 1u : 0u;     // segment full: count directly
         }
@@ -455,7 +456,7 @@ __device__ __forceinline__ uint32_t stage_keys_block(const uint64_t (&keys)[16],
     return claimed;
 }
 
-__global__ void __launch_bounds__(PT_THREADS)
+__global__ void __launch_bounds__(PT_THREADS, 2)
 extract_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
                          int k, RegionStage rs, Slot *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr) {
     __shared__ uint32_t s_words[PT_THREADS + 2];
@@ -514,8 +515,85 @@ extract_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, co
     if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
 }
 
+// Phase A, second flavour: every key reserves its staging position with one returning atomic on
+// the region cursor in L2 (no shared-memory histogram, no block barriers).  The 16 atomics of a
+// thread are issued back to back, the dependent stores follow, so ~16 requests per thread are in
+// flight.  Region cursors are few (<= 2048) but live in L2, whose atomic units sustain ~190 G
+// atomics/s on resident lines (mfkc_gups_ex mode 0).
+__global__ void __launch_bounds__(EX_THREADS)
+extract_stage_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
+                     int k, RegionStage rs, Slot *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr) {
+    __shared__ uint32_t s_words[EX_THREADS + 2];
+    __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t n_words = (n_bases + 15) >> 4;
+    const uint64_t n_tiles = (n_words + EX_THREADS - 1) / EX_THREADS;
+    const uint64_t n_flag_words = (n_bases + 31) >> 5;
+    uint32_t claimed = 0, bad = 0;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t w_base = tile * EX_THREADS;
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            if (rep == 1 && tid >= 2) break;
+            const uint32_t slot = rep ? EX_THREADS + tid : tid;
+            const uint64_t w = w_base + slot;
+            uint32_t word = 0;
+            const uint64_t b0 = w << 4;
+            if (b0 + 16 <= n_bases) {
+                const uint4 v = ld_nc_u128(bases + b0);
+                word = pack16(v);
+                bad |= bad4(v.x) | bad4(v.y) | bad4(v.z) | bad4(v.w);
+            } else if (b0 < n_bases) {
+                for (uint32_t j = 0; j < 16 && b0 + j < n_bases; j++) {
+                    const uint32_t c = bases[b0 + j];
+                    bad |= bad4(c | 0x41414100u);
+                    word |= pack4(c) >> 6 << (30 - 2 * j);
+                }
+            }
+            s_words[slot] = word;
+        }
+        if (tid < EX_THREADS / 2 + 2) {
+            const uint64_t fw = (w_base >> 1) + tid;
+            s_flags[tid] = fw < n_flag_words ? flags[fw] : 0u;
+        }
+        __syncthreads();
+        const uint64_t w = w_base + tid;
+        if ((w << 4) < n_bases) {
+            const uint32_t w0 = s_words[tid], w1 = s_words[tid + 1], w2 = s_words[tid + 2];
+            const uint32_t f0 = s_flags[tid >> 1], f1 = s_flags[(tid >> 1) + 1], f2 = s_flags[(tid >> 1) + 2];
+            const uint64_t fbits = (tid & 1) ? (((uint64_t)f0 >> 16) | ((uint64_t)f1 << 16) | ((uint64_t)f2 << 48))
+                                             : ((uint64_t)f0 | ((uint64_t)f1 << 32));
+            uint64_t keys[16];
+            const long long limit = (long long)n_bases - k - (long long)(w << 4);
+            const uint32_t valid = kmers_of_word(w0, w1, w2, fbits, limit, k, keys);
+            uint32_t pos[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                pos[j] = 0;
+                if ((valid >> j) & 1) {
+                    const uint32_t region = (uint32_t)(home_slot(keys[j], cap) >> rs.region_shift);
+                    pos[j] = atomicAdd(&rs.cursor[region], 1u);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if ((valid >> j) & 1) {
+                    const uint32_t region = (uint32_t)(home_slot(keys[j], cap) >> rs.region_shift);
+                    if (pos[j] < rs.seg_cap) rs.keys[(uint64_t)region * rs.seg_cap + pos[j]] = keys[j];
+                    else claimed += table_upsert1(tab, cap, keys[j]) ? 1u : 0u;   // segment full: count directly
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+    if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
+}
+
 // phase A for keys that already exist as an array (receive side of the shard exchange)
-__global__ void __launch_bounds__(PT_THREADS)
+__global__ void __launch_bounds__(PT_THREADS, 2)
 partition_keys_kernel(const unsigned long long *__restrict__ in, uint64_t n, RegionStage rs,
                       Slot *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr) {
     __shared__ uint32_t s_hist[MAX_REGIONS];
@@ -552,8 +630,35 @@ drain_regions_kernel(RegionStage rs, uint32_t blocks_per_region, Slot *__restric
     if (n > rs.seg_cap) n = rs.seg_cap;
     const unsigned long long *__restrict__ keys = rs.keys + (uint64_t)region * rs.seg_cap;
     uint32_t claimed = 0;
-    for (uint64_t i = (uint64_t)sub * 256 + threadIdx.x; i < n; i += (uint64_t)blocks_per_region * 256)
-        claimed += table_upsert1(tab, cap, keys[i]) ? 1u : 0u;
+    constexpr int U = 4;                                  // independent upserts in flight per thread
+    const uint64_t stride = (uint64_t)blocks_per_region * 256;
+    for (uint64_t i0 = (uint64_t)sub * 256 + threadIdx.x; i0 < n; i0 += stride * U) {
+        unsigned long long key[U]; uint64_t slot[U]; ulonglong2 s[U]; bool live[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t i = i0 + (uint64_t)u * stride;
+            live[u] = i < n;
+            key[u] = live[u] ? keys[i] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) { slot[u] = home_slot(key[u], cap); if (live[u]) s[u] = ld_cg_u64x2(&tab[slot[u]]); }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!live[u]) continue;
+            uint64_t i = slot[u];
+            ulonglong2 v = s[u];
+            for (;;) {                                    // same protocol as table_upsert1, first probe preloaded
+                if (v.x == key[u]) { if ((uint32_t)v.y < MAX_COUNT) atomicAdd(&tab[i].count, 1u); break; }
+                if (v.x == EMPTY_KEY) {
+                    const unsigned long long prev = atomicCAS(&tab[i].key, EMPTY_KEY, key[u]);
+                    if (prev == EMPTY_KEY) { atomicAdd(&tab[i].count, 1u); claimed++; break; }
+                    if (prev == key[u]) { atomicAdd(&tab[i].count, 1u); break; }
+                }
+                if (++i == cap) i = 0;
+                v = ld_cg_u64x2(&tab[i]);
+            }
+        }
+    }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
@@ -629,6 +734,68 @@ table_compact_kernel(const Slot *__restrict__ tab, uint64_t cap, uint32_t thresh
             if (at < out_cap) { out_keys[at] = key; out_counts[at] = (uint16_t)c; }
         }
     }
+}
+
+// One pass over the table: histogram of ALL entries + compaction of the entries with
+// count > threshold.  Output positions are reserved with ONE global atomic per block iteration
+// (warp ballots -> shared prefix), so the cursor is not a serialisation point.
+__global__ void __launch_bounds__(256)
+table_scan_kernel(const Slot *__restrict__ tab, uint64_t cap, uint32_t threshold, unsigned long long *__restrict__ hist,
+                  unsigned long long *__restrict__ out_keys, uint16_t *__restrict__ out_counts, uint64_t out_cap,
+                  Counters *__restrict__ ctr) {
+    constexpr int U = 8;                                   // slots per thread per round: 8 x 16 B in flight
+    __shared__ uint32_t s_hist[HIST_SMEM_BINS];
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base;
+    for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t round_slots = (uint64_t)256 * U;
+    for (uint64_t base = (uint64_t)blockIdx.x * round_slots; base < cap; base += (uint64_t)gridDim.x * round_slots) {
+        uint4 s[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t i = base + (uint64_t)u * 256 + threadIdx.x;
+            s[u] = i < cap ? ld_nc_u128(&tab[i]) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+        }
+        uint32_t good_mask = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if ((s[u].x & s[u].y) != 0xFFFFFFFFu) {
+                const uint32_t c = s[u].z < MAX_COUNT ? s[u].z : MAX_COUNT;
+                s[u].z = c;
+                if (c < HIST_SMEM_BINS) atomicAdd(&s_hist[c], 1u); else atomicAdd(&hist[c], 1ULL);
+                if (c > threshold) good_mask |= 1u << u;
+            }
+        }
+        const uint32_t mine = __popc(good_mask);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int wv = 0; wv < 8; wv++) { const uint32_t cc = s_warp[wv]; if (wv < (int)warp) before += cc; total += cc; }
+        if (threadIdx.x == 0 && total) s_base = atomicAdd(&ctr->n_good, (unsigned long long)total);
+        __syncthreads();
+        if (mine) {
+            uint64_t at = s_base + before + incl - mine;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if ((good_mask >> u) & 1) {
+                    if (at < out_cap) {
+                        out_keys[at] = ((unsigned long long)s[u].y << 32) | s[u].x;
+                        out_counts[at] = (uint16_t)s[u].z;
+                    }
+                    at++;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i2 = threadIdx.x; i2 < HIST_SMEM_BINS; i2 += blockDim.x)
+        if (s_hist[i2]) atomicAdd(&hist[i2], (unsigned long long)s_hist[i2]);
 }
 
 // sorted (key,count) -> big-endian 10-byte records (src/io/IOUtils.java:61-65: writeLong, writeShort)

@@ -108,6 +108,11 @@ static thread_local std::string g_create_err;
 
 #define TRY(expr) do { int r__ = (expr); if (r__ != MFKC_OK) return r__; } while (0)
 
+// Temporaries (sort workspace, emit buffers, RLE outputs) come from the stream-ordered pool of the
+// device: cudaMalloc/cudaFree of multi-GB blocks cost 10-1000 ms each and serialise the device.
+#define TMP_ALLOC(ptr, bytes) CU_TRY(cudaMallocAsync((void **)&(ptr), (size_t)(bytes) ? (size_t)(bytes) : 1, ctx->compute))
+#define TMP_FREE(ptr) do { if (ptr) cudaFreeAsync((void *)(ptr), ctx->compute); } while (0)
+
 static int fail(mfkc_ctx *ctx, int code, const char *msg) { if (ctx) ctx->err = msg; return code; }
 
 static cudaEvent_t get_event(mfkc_ctx *ctx) {
@@ -165,6 +170,19 @@ extern "C" int mfkc_device_count(void) {
 
 extern "C" const char *mfkc_last_error(const mfkc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
+// cudaMalloc for the long-lived big blocks; if it fails, give the pool's cached memory back first
+static cudaError_t big_alloc(mfkc_ctx *ctx, void **p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) return e;
+    cudaGetLastError();
+    cudaDeviceSynchronize();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) cudaGetLastError();
+    return e;
+}
+
 // Round a requested capacity to whole regions: cap = n_regions << shift, n_regions <= MAX_REGIONS.
 static void plan_regions(const mfkc_ctx *ctx, uint64_t slots, uint64_t *cap, uint32_t *n_regions, int *shift) {
     int sh = ctx->cfg.region_shift ? (int)ctx->cfg.region_shift : 19;
@@ -177,8 +195,8 @@ static void plan_regions(const mfkc_ctx *ctx, uint64_t slots, uint64_t *cap, uin
 
 static int table_alloc(mfkc_ctx *ctx, uint64_t slots, Slot **out) {
     Slot *t = nullptr;
-    cudaError_t e = cudaMalloc(&t, slots * sizeof(Slot));
-    if (e != cudaSuccess) { cudaGetLastError(); ctx->err = "cannot allocate k-mer table"; return MFKC_E_OOM; }
+    cudaError_t e = big_alloc(ctx, (void **)&t, slots * sizeof(Slot));
+    if (e != cudaSuccess) { ctx->err = "cannot allocate k-mer table"; return MFKC_E_OOM; }
     {
         ProfScope ps(ctx, P_CLEAR, ctx->compute);
         table_clear_kernel<<<grid_for(ctx, slots, 256, 16), 256, 0, ctx->compute>>>(t, slots);
@@ -236,6 +254,20 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     CR_TRY(cudaMemset(ctx->d_bucket_cursor, 0, 64 * sizeof(unsigned long long)));
     CR_TRY(cudaMemset(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t)));
 
+    {   // random 16-byte slot probes: do not let L2 promote a missing sector to a 64/128-byte DRAM fetch
+        const char *g = getenv("MFKC_L2_FETCH");
+        const size_t gran = g ? (size_t)atoi(g) : 32;
+        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
+    {   // keep freed temporaries cached in the pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    }
     size_t free_b = 0, total_b = 0;
     CR_TRY(cudaMemGetInfo(&free_b, &total_b));
     ctx->max_table_bytes = cfg->max_table_bytes ? cfg->max_table_bytes : (uint64_t)(free_b * 0.8);
@@ -243,6 +275,8 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     if (cfg->variant != MFKC_VARIANT_SORT) {
         uint64_t slots = cfg->table_slots;
         if (!slots && cfg->expected_distinct) slots = cfg->expected_distinct * 2;      // load 0.5
+        if (!slots && cfg->expected_kmers && cfg->variant == MFKC_VARIANT_HASH)
+            slots = std::min<uint64_t>((uint64_t)(cfg->expected_kmers / 0.85) + 1024, (uint64_t)(total_b * 0.35) / sizeof(Slot));
         if (!slots) slots = 1ull << 22;                                                // 64 MiB, grows on demand
         if (slots < 1024) slots = 1024;
         if (slots * sizeof(Slot) > ctx->max_table_bytes) slots = ctx->max_table_bytes / sizeof(Slot);
@@ -261,7 +295,7 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
 }
 
 static void free_emit(mfkc_ctx *ctx) {
-    cudaFree(ctx->em_keys); cudaFree(ctx->em_counts); cudaFree(ctx->em_records);
+    TMP_FREE(ctx->em_keys); TMP_FREE(ctx->em_counts); TMP_FREE(ctx->em_records);
     ctx->em_keys = nullptr; ctx->em_counts = nullptr; ctx->em_records = nullptr;
     ctx->em_n = 0; ctx->em_cursor = 0; ctx->em_valid = false;
 }
@@ -280,8 +314,8 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
         if (s.ev_done) cudaEventDestroy(s.ev_done);
         if (s.h_snap) cudaFreeHost(s.h_snap);
     }
-    if (ctx->compute) cudaStreamDestroy(ctx->compute);
     free_emit(ctx);
+    if (ctx->compute) { cudaStreamSynchronize(ctx->compute); cudaStreamDestroy(ctx->compute); ctx->compute = nullptr; }
     cudaFree(ctx->rb_keys); cudaFree(ctx->rb_cursor);
     cudaFree(ctx->tab); cudaFree(ctx->sv_keys); cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts);
     cudaFree(ctx->d_bucket_cursor); cudaFree(ctx->d_bucket_base);
@@ -311,7 +345,7 @@ extern "C" int mfkc_reset(mfkc_ctx *ctx) {
     CU_TRY(cudaStreamSynchronize(ctx->compute));
     ctx->staged_ub = 0;
     ctx->distinct_ub = 0; ctx->kmers_ub_total = 0; ctx->sv_ub = 0; ctx->svs_n = 0;
-    cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts); ctx->svs_keys = nullptr; ctx->svs_counts = nullptr;
+    TMP_FREE(ctx->svs_keys); TMP_FREE(ctx->svs_counts); ctx->svs_keys = nullptr; ctx->svs_counts = nullptr;
     ctx->hist_valid = false; ctx->dirty = false;
     free_emit(ctx);
     return MFKC_OK;
@@ -339,7 +373,8 @@ extern "C" int mfkc_pinned_free(mfkc_ctx *ctx, void *host_ptr) {
 // table growth
 // ------------------------------------------------------------------------------------------
 static constexpr double kMaxLoad = 0.60;     // never exceeded: checked against an upper bound before each batch
-static constexpr double kGrowLoad = 0.30;    // load right after growing
+static constexpr double kGrowLoad = 0.30;    // load right after growing (direct variant)
+static constexpr double kHardLoad = 0.92;    // region-blocked variant: distinct + staged may reach this fraction of the table
 
 static void poll_snapshots(mfkc_ctx *ctx) {
     if (ctx->drain_pending && cudaEventQuery(ctx->ev_drain) == cudaSuccess) {
@@ -388,22 +423,27 @@ static int grow_table(mfkc_ctx *ctx, uint64_t need_slots) {
 static int drain_regions(mfkc_ctx *ctx);
 
 static int reserve_slots(mfkc_ctx *ctx, uint64_t add) {
+    // Direct variant: every submitted k-mer may claim a slot at once -> stay below kMaxLoad.
+    // Region-blocked variant: staged keys reach the table only at a drain, and the table stays
+    // correct (if slower) up to a load close to 1, so drains are forced only by kHardLoad.
+    const bool blocked = ctx->cfg.variant == MFKC_VARIANT_HASH;
+    const double limit = blocked ? kHardLoad : kMaxLoad;
     poll_snapshots(ctx);
-    if ((double)(ctx->distinct_ub + add) <= kMaxLoad * (double)ctx->cap) { ctx->distinct_ub += add; return MFKC_OK; }
+    if ((double)(ctx->distinct_ub + add) <= limit * (double)ctx->cap) { ctx->distinct_ub += add; return MFKC_OK; }
     TRY(drain_regions(ctx));              // staged keys must be in the table before it is measured / rehashed
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
     ctx->distinct_ub = ctx->h_ctr->distinct;
-    if ((double)(ctx->distinct_ub + add) > kMaxLoad * (double)ctx->cap) {
-        const uint64_t need = (uint64_t)((double)(ctx->distinct_ub + add) / kGrowLoad) + 1024;
-        int r = grow_table(ctx, need);
-        if (r != MFKC_OK) {
-            // a smaller step may still fit
-            if ((double)(ctx->distinct_ub + add) <= 0.9 * (double)ctx->cap) { /* tolerate a higher load */ }
-            else return r;
-        } else if ((double)(ctx->distinct_ub + add) > 0.9 * (double)ctx->cap) {
+    // after a forced drain leave room for a whole staging buffer so that the next one is far away
+    const uint64_t room = blocked ? std::max<uint64_t>(add, ctx->rb_cap) : add;
+    if ((double)(ctx->distinct_ub + room) > kMaxLoad * (double)ctx->cap) {
+        const uint64_t need = (uint64_t)((double)(ctx->distinct_ub + room) / (blocked ? kMaxLoad : kGrowLoad)) + 1024;
+        const int r = grow_table(ctx, need);
+        if ((double)(ctx->distinct_ub + add) > kHardLoad * (double)ctx->cap) {
+            if (r != MFKC_OK) return r;
             return fail(ctx, MFKC_E_TABLE_FULL, "k-mer table cannot grow enough for this batch");
         }
+        if (r != MFKC_OK) ctx->err.clear();       // could not grow as far as wished, but the batch fits
     }
     ctx->distinct_ub += add;
     return MFKC_OK;
@@ -449,10 +489,12 @@ static int reserve_staging(mfkc_ctx *ctx, uint64_t add) {
     const uint64_t hard = 4000000000ull;          // cursors are 32-bit
     if (!ctx->rb_keys) {
         uint64_t want = ctx->cfg.staging_bytes ? ctx->cfg.staging_bytes / 8 : std::max<uint64_t>(4 * add, 1ull << 22);
+        if (!ctx->cfg.staging_bytes && ctx->cfg.expected_kmers)
+            want = std::max<uint64_t>(want, ctx->cfg.expected_kmers + ctx->cfg.expected_kmers / 50 + (uint64_t)MAX_REGIONS * 64);
         if (!ctx->cfg.staging_bytes && want > ctx->rb_cap_max) want = std::max<uint64_t>(ctx->rb_cap_max, add);
         if (want < add) want = add;
-        cudaError_t e = cudaMalloc(&ctx->rb_keys, want * 8);
-        if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, MFKC_E_OOM, "cannot allocate the key staging buffer"); }
+        cudaError_t e = big_alloc(ctx, (void **)&ctx->rb_keys, want * 8);
+        if (e != cudaSuccess) return fail(ctx, MFKC_E_OOM, "cannot allocate the key staging buffer");
         ctx->rb_cap = want;
     }
     if (ctx->staged_ub + add <= std::min(ctx->rb_cap, hard)) return MFKC_OK;
@@ -465,8 +507,8 @@ static int reserve_staging(mfkc_ctx *ctx, uint64_t add) {
         if (want > ctx->rb_cap) {
             TRY(sync_all(ctx));
             cudaFree(ctx->rb_keys); ctx->rb_keys = nullptr; ctx->rb_cap = 0;
-            cudaError_t e = cudaMalloc(&ctx->rb_keys, want * 8);
-            if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, MFKC_E_OOM, "cannot grow the key staging buffer"); }
+            cudaError_t e = big_alloc(ctx, (void **)&ctx->rb_keys, want * 8);
+            if (e != cudaSuccess) return fail(ctx, MFKC_E_OOM, "cannot grow the key staging buffer");
             ctx->rb_cap = want;
         }
     }
@@ -530,10 +572,16 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
     if (n_bases >= (uint64_t)k) {
         if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
             ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
-            const uint64_t tiles = ((n_bases + 15) / 16 + PT_THREADS - 1) / PT_THREADS;
-            const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 2);
-            extract_partition_kernel<<<grid, PT_THREADS, 0, ctx->compute>>>(
-                d_bases, n_bases, s.d_flags, k, region_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr);
+            static const int stage_mode = getenv("MFKC_STAGE") ? atoi(getenv("MFKC_STAGE")) : 0;
+            if (stage_mode == 0) {            // shared-memory histogram flavour
+                const uint64_t tiles = ((n_bases + 15) / 16 + PT_THREADS - 1) / PT_THREADS;
+                const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 2);
+                extract_partition_kernel<<<grid, PT_THREADS, 0, ctx->compute>>>(
+                    d_bases, n_bases, s.d_flags, k, region_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr);
+            } else {                          // per-key cursor atomics in L2
+                extract_stage_kernel<<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                    d_bases, n_bases, s.d_flags, k, region_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr);
+            }
         } else if (ctx->cfg.variant == MFKC_VARIANT_HASH_DIRECT) {
             ProfScope ps(ctx, P_EXTRACT_COUNT, ctx->compute);
             SinkTable sink{ctx->tab, ctx->cap, ctx->d_ctr};
@@ -611,16 +659,18 @@ static int radix_sort(mfkc_ctx *ctx, cudaStream_t st, unsigned long long *&a, un
     if (n < 2) return MFKC_OK;
     const RadixPlan plan = radix_plan(n);
     uint32_t *hist = nullptr; unsigned long long *offs = nullptr, *chunk = nullptr; uint32_t *d_triv = nullptr;
-    CU_TRY(cudaMalloc(&hist, plan.hist_bytes));
-    CU_TRY(cudaMalloc(&offs, plan.offs_bytes));
-    CU_TRY(cudaMalloc(&chunk, plan.chunk_bytes));
-    CU_TRY(cudaMalloc(&d_triv, sizeof(uint32_t)));
-    const int grid = (int)std::min<uint64_t>((plan.n_parts + RS_WARPS - 1) / RS_WARPS, (uint64_t)ctx->sm_count * 8);
+    TMP_ALLOC(hist, plan.hist_bytes);
+    TMP_ALLOC(offs, plan.offs_bytes);
+    TMP_ALLOC(chunk, plan.chunk_bytes);
+    TMP_ALLOC(d_triv, sizeof(uint32_t));
+    const size_t smem = rs_scatter_smem_bytes<V, HAS_V>();
+    CU_TRY(cudaFuncSetAttribute(rs_scatter_kernel<V, HAS_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<uint64_t>(plan.n_parts, (uint64_t)ctx->sm_count * 8);
     int rc = MFKC_OK;
     ProfScope ps(ctx, P_SORT, st);
     ctx->prof_launches[P_SORT]--;            // counted per kernel below
     for (int shift = 0; shift < key_bits; shift += 8) {
-        rs_hist_kernel<<<grid, RS_WARPS * 32, 0, st>>>(a, n, shift, plan.n_parts, hist);
+        rs_hist_kernel<<<grid, RS_THREADS, 0, st>>>(a, n, shift, plan.n_parts, hist);
         rs_chunk_kernel<<<plan.n_chunks, RS_RADIX, 0, st>>>(hist, plan.n_parts, chunk);
         rs_base_kernel<<<1, RS_RADIX, 0, st>>>(chunk, plan.n_chunks, n, d_triv);
         uint32_t triv = 0;
@@ -629,13 +679,13 @@ static int radix_sort(mfkc_ctx *ctx, cudaStream_t st, unsigned long long *&a, un
         ctx->prof_launches[P_SORT] += triv ? 3 : 5;
         if (triv) continue;                                   // every key has the same digit: order unchanged
         rs_offsets_kernel<<<plan.n_chunks, RS_RADIX, 0, st>>>(hist, plan.n_parts, chunk, offs);
-        rs_scatter_kernel<V, HAS_V><<<grid, RS_WARPS * 32, 0, st>>>(a, va, n, shift, plan.n_parts, offs, b, vb);
+        rs_scatter_kernel<V, HAS_V><<<grid, RS_THREADS, smem, st>>>(a, va, n, shift, plan.n_parts, offs, b, vb);
         std::swap(a, b);
         std::swap(va, vb);
     }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(hist); cudaFree(offs); cudaFree(chunk); cudaFree(d_triv);
+    TMP_FREE(hist); TMP_FREE(offs); TMP_FREE(chunk); TMP_FREE(d_triv);
     if (e != cudaSuccess) { ctx->err = std::string("radix sort: ") + cudaGetErrorString(e); return MFKC_E_CUDA; }
     return rc;
 }
@@ -650,7 +700,7 @@ static int rle_sorted(mfkc_ctx *ctx, cudaStream_t st, const unsigned long long *
     if (n == 0) return MFKC_OK;
     const int grid = grid_for(ctx, n, 256, 8);
     unsigned long long *d_blk = nullptr;
-    CU_TRY(cudaMalloc(&d_blk, (size_t)grid * sizeof(unsigned long long)));
+    TMP_ALLOC(d_blk, (size_t)grid * sizeof(unsigned long long));
     ProfScope ps(ctx, P_RLE, st);
     rle_mark_kernel<<<grid, 256, 0, st>>>(keys, n, d_blk);
     std::vector<unsigned long long> h(grid);
@@ -660,12 +710,12 @@ static int rle_sorted(mfkc_ctx *ctx, cudaStream_t st, const unsigned long long *
     for (int i = 0; i < grid; i++) { const unsigned long long c = h[i]; h[i] = run; run += c; }
     CU_TRY(cudaMemcpyAsync(d_blk, h.data(), (size_t)grid * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
     unsigned long long *ok = nullptr; uint32_t *oc = nullptr;
-    CU_TRY(cudaMalloc(&ok, (size_t)run * sizeof(unsigned long long)));
-    CU_TRY(cudaMalloc(&oc, (size_t)run * sizeof(uint32_t)));
+    TMP_ALLOC(ok, (size_t)run * sizeof(unsigned long long));
+    TMP_ALLOC(oc, (size_t)run * sizeof(uint32_t));
     rle_write_kernel<<<grid, 256, 0, st>>>(keys, weights, n, d_blk, ok, oc);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(st));
-    cudaFree(d_blk);
+    TMP_FREE(d_blk);
     *out_keys = ok; *out_counts = oc; *out_n = run;
     return MFKC_OK;
 }
@@ -680,32 +730,32 @@ static int sort_variant_compact(mfkc_ctx *ctx) {
     const int key_bits = 2 * ctx->cfg.k;
     if (n) {
         unsigned long long *alt = nullptr; uint32_t *dummy_a = nullptr, *dummy_b = nullptr;
-        CU_TRY(cudaMalloc(&alt, (size_t)n * sizeof(unsigned long long)));
+        TMP_ALLOC(alt, (size_t)n * sizeof(unsigned long long));
         unsigned long long *a = ctx->sv_keys, *b = alt;
         int r = radix_sort<uint32_t, false>(ctx, st, a, b, dummy_a, dummy_b, n, key_bits);
         unsigned long long *rk = nullptr; uint32_t *rc = nullptr; uint64_t rn = 0;
         if (r == MFKC_OK) r = rle_sorted(ctx, st, a, nullptr, n, &rk, &rc, &rn);
-        cudaFree(alt);      // ctx->sv_keys itself (the larger allocation) is kept for the next round
+        TMP_FREE(alt);      // ctx->sv_keys itself (the larger allocation) is kept for the next round
         if (r != MFKC_OK) return r;
         if (ctx->svs_n == 0) {
-            cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts);
+            TMP_FREE(ctx->svs_keys); TMP_FREE(ctx->svs_counts);
             ctx->svs_keys = rk; ctx->svs_counts = rc; ctx->svs_n = rn;
         } else {
             // merge: concatenate, sort pairs by key, weighted RLE
             const uint64_t m = ctx->svs_n + rn;
             unsigned long long *ck = nullptr, *ck2 = nullptr; uint32_t *cc = nullptr, *cc2 = nullptr;
-            CU_TRY(cudaMalloc(&ck, (size_t)m * 8)); CU_TRY(cudaMalloc(&ck2, (size_t)m * 8));
-            CU_TRY(cudaMalloc(&cc, (size_t)m * 4)); CU_TRY(cudaMalloc(&cc2, (size_t)m * 4));
+            TMP_ALLOC(ck, (size_t)m * 8); TMP_ALLOC(ck2, (size_t)m * 8);
+            TMP_ALLOC(cc, (size_t)m * 4); TMP_ALLOC(cc2, (size_t)m * 4);
             CU_TRY(cudaMemcpyAsync(ck, ctx->svs_keys, ctx->svs_n * 8, cudaMemcpyDeviceToDevice, st));
             CU_TRY(cudaMemcpyAsync(ck + ctx->svs_n, rk, rn * 8, cudaMemcpyDeviceToDevice, st));
             CU_TRY(cudaMemcpyAsync(cc, ctx->svs_counts, ctx->svs_n * 4, cudaMemcpyDeviceToDevice, st));
             CU_TRY(cudaMemcpyAsync(cc + ctx->svs_n, rc, rn * 4, cudaMemcpyDeviceToDevice, st));
             CU_TRY(cudaStreamSynchronize(st));
-            cudaFree(rk); cudaFree(rc); cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts);
+            TMP_FREE(rk); TMP_FREE(rc); TMP_FREE(ctx->svs_keys); TMP_FREE(ctx->svs_counts);
             ctx->svs_keys = nullptr; ctx->svs_counts = nullptr; ctx->svs_n = 0;
             r = radix_sort<uint32_t, true>(ctx, st, ck, ck2, cc, cc2, m, key_bits);
             if (r == MFKC_OK) r = rle_sorted(ctx, st, ck, cc, m, &ctx->svs_keys, &ctx->svs_counts, &ctx->svs_n);
-            cudaFree(ck); cudaFree(ck2); cudaFree(cc); cudaFree(cc2);
+            TMP_FREE(ck); TMP_FREE(ck2); TMP_FREE(cc); TMP_FREE(cc2);
             if (r != MFKC_OK) return r;
         }
     }
@@ -845,36 +895,56 @@ select_write_kernel(const unsigned long long *__restrict__ keys, const uint32_t 
 extern "C" int mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_good) {
     if (!ctx) return MFKC_E_BADARG;
     CU_TRY(cudaSetDevice(ctx->device));
-    TRY(compute_hist(ctx));
+    TRY(finalize_counts(ctx));
     free_emit(ctx);
-    // entries with value > threshold (src/io/IOUtils.java:61); counts are 1..32767
-    uint64_t good = 0;
-    const int64_t thr = threshold;
-    for (int c = 1; c < MFKC_HIST_BINS; c++) if ((int64_t)c > thr) good += ctx->h_hist[c];
-    const uint32_t thr_u = thr < 0 ? 0u : (uint32_t)std::min<int64_t>(thr, 0x7fffffff);
+    // entries with value > threshold (src/io/IOUtils.java:61); stored counts are 1..32767, so every
+    // negative threshold behaves like 0
+    const uint32_t thr_u = threshold < 0 ? 0u : (uint32_t)threshold;
     cudaStream_t st = ctx->compute;
-    ctx->em_n = good;
-    if (good) {
-        CU_TRY(cudaMalloc(&ctx->em_keys, (size_t)good * 8));
-        CU_TRY(cudaMalloc(&ctx->em_counts, (size_t)good * 2));
-        if (ctx->cfg.variant != MFKC_VARIANT_SORT) {
-            unsigned long long *k2 = nullptr; uint16_t *c2 = nullptr;
-            CU_TRY(cudaMalloc(&k2, (size_t)good * 8));
-            CU_TRY(cudaMalloc(&c2, (size_t)good * 2));
+    uint64_t good = 0;
+    if (ctx->cfg.variant != MFKC_VARIANT_SORT) {
+        // one pass over the table: histogram + compaction (buffers sized by the exact distinct count)
+        TRY(read_counters(ctx));
+        const uint64_t distinct = ctx->h_ctr->distinct;
+        if (distinct) {
+            unsigned long long *k1 = nullptr, *k2 = nullptr; uint16_t *c1 = nullptr, *c2 = nullptr;
+            TMP_ALLOC(k1, (size_t)distinct * 8);
+            TMP_ALLOC(c1, (size_t)distinct * 2);
+            CU_TRY(cudaMemsetAsync(ctx->d_hist, 0, MFKC_HIST_BINS * sizeof(unsigned long long), st));
             CU_TRY(cudaMemsetAsync(&ctx->d_ctr->n_good, 0, sizeof(unsigned long long), st));
             {
                 ProfScope ps(ctx, P_COMPACT, st);
-                table_compact_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, st>>>(
-                    ctx->tab, ctx->cap, thr < 0 ? 0u : thr_u, ctx->em_keys, ctx->em_counts, good, ctx->d_ctr);
+                table_scan_kernel<<<grid_for(ctx, (ctx->cap + 7) / 8, 256, 8), 256, 0, st>>>(
+                    ctx->tab, ctx->cap, thr_u, ctx->d_hist, k1, c1, distinct, ctx->d_ctr);
             }
             CU_TRY(cudaGetLastError());
-            int r = radix_sort<uint16_t, true>(ctx, st, ctx->em_keys, k2, ctx->em_counts, c2, good, 2 * ctx->cfg.k);
-            cudaFree(k2); cudaFree(c2);
-            TRY(r);
+            CU_TRY(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, MFKC_HIST_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(&ctx->h_ctr->n_good, &ctx->d_ctr->n_good, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            ctx->hist_valid = true;
+            good = ctx->h_ctr->n_good;
+            if (good) {
+                TMP_ALLOC(k2, (size_t)good * 8);
+                TMP_ALLOC(c2, (size_t)good * 2);
+                int r = radix_sort<uint16_t, true>(ctx, st, k1, k2, c1, c2, good, 2 * ctx->cfg.k);
+                if (r != MFKC_OK) { TMP_FREE(k1); TMP_FREE(k2); TMP_FREE(c1); TMP_FREE(c2); return r; }
+                ctx->em_keys = k1; ctx->em_counts = c1;       // radix_sort leaves the result in (k1, c1)
+                TMP_FREE(k2); TMP_FREE(c2);
+            } else {
+                TMP_FREE(k1); TMP_FREE(c1);
+            }
         } else {
+            TRY(compute_hist(ctx));
+        }
+    } else {
+        TRY(compute_hist(ctx));
+        for (int c = 1; c < MFKC_HIST_BINS; c++) if ((uint32_t)c > thr_u) good += ctx->h_hist[c];
+        if (good) {
+            TMP_ALLOC(ctx->em_keys, (size_t)good * 8);
+            TMP_ALLOC(ctx->em_counts, (size_t)good * 2);
             const int grid = grid_for(ctx, ctx->svs_n, 256, 8);
             unsigned long long *d_blk = nullptr;
-            CU_TRY(cudaMalloc(&d_blk, (size_t)grid * 8));
+            TMP_ALLOC(d_blk, (size_t)grid * 8);
             ProfScope ps(ctx, P_COMPACT, st);
             select_mark_kernel<<<grid, 256, 0, st>>>(ctx->svs_counts, ctx->svs_n, thr_u, d_blk);
             std::vector<unsigned long long> h(grid);
@@ -887,10 +957,13 @@ extern "C" int mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_goo
                                                      ctx->em_keys, ctx->em_counts);
             CU_TRY(cudaGetLastError());
             CU_TRY(cudaStreamSynchronize(st));
-            cudaFree(d_blk);
+            TMP_FREE(d_blk);
             if (run != good) return fail(ctx, MFKC_E_STATE, "internal: selection count mismatch");
         }
-        CU_TRY(cudaMalloc(&ctx->em_records, (size_t)good * 10));
+    }
+    ctx->em_n = good;
+    if (good) {
+        TMP_ALLOC(ctx->em_records, (size_t)good * 10);
         {
             ProfScope ps(ctx, P_RECORDS, st);
             records_kernel<<<grid_for(ctx, good, 256, 8), 256, 0, st>>>(ctx->em_keys, ctx->em_counts, good,
@@ -899,7 +972,6 @@ extern "C" int mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_goo
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaStreamSynchronize(st));
     }
-    // a negative threshold would also pass count-0 entries; the table never holds any
     ctx->em_cursor = 0; ctx->em_valid = true;
     if (n_good) *n_good = good;
     return MFKC_OK;
@@ -1145,7 +1217,7 @@ extern "C" int mfkc_fc_features(mfkc_ctx *ctx, int64_t threshold, int64_t *vec, 
     if (nc == 0) return MFKC_OK;
     cudaStream_t st = ctx->compute;
     long long *d_vec = nullptr; unsigned long long *d_found = nullptr, *d_cnt = nullptr;
-    CU_TRY(cudaMalloc(&d_vec, (size_t)nc * 8)); CU_TRY(cudaMalloc(&d_found, (size_t)nc * 8)); CU_TRY(cudaMalloc(&d_cnt, (size_t)nc * 8));
+    TMP_ALLOC(d_vec, (size_t)nc * 8); TMP_ALLOC(d_found, (size_t)nc * 8); TMP_ALLOC(d_cnt, (size_t)nc * 8);
     {
         ProfScope ps(ctx, P_FC_FEATURES, st);
         const int grid = grid_for(ctx, (uint64_t)nc * 32, 256, 8);
@@ -1157,7 +1229,7 @@ extern "C" int mfkc_fc_features(mfkc_ctx *ctx, int64_t threshold, int64_t *vec, 
     CU_TRY(cudaMemcpyAsync(found, d_found, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(cnt, d_cnt, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
-    cudaFree(d_vec); cudaFree(d_found); cudaFree(d_cnt);
+    TMP_FREE(d_vec); TMP_FREE(d_found); TMP_FREE(d_cnt);
     return MFKC_OK;
 }
 
