@@ -1,1 +1,428 @@
-int main(){return 0;}
+// cli.cpp -- mfkc_cli: the host side of the path as a native tool with MetaFast's own command
+// lines, for boxes without a JVM (tests, benchmarks) and as the executable specification of what
+// the Java Tool subclasses do on top of the C ABI (java/ holds those classes).
+//
+//   mfkc_cli -t kmer-counter-many  -k K [-b B] -i reads... [-w workDir] [--output-dir D] [--stats-dir D]
+//   mfkc_cli -t kmer-counter       -k K [-b B] -i reads...            (one sample: all files into one table)
+//   mfkc_cli -t features-calculator -k K -cm components.bin [-ka kmers.bin...] [-i reads...]
+//                                   [--selected kmers.bin...] [--threshold T] [-w workDir]
+//   extras (optional, old command lines keep working): --gpu N, --gpu-variant hash|sort|direct
+//
+// Mirrors src/tools/KmersCounterForManyFilesMain.java:26-120, src/tools/KmersCounterMain.java:28-137,
+// src/tools/FeaturesCalculatorMain.java:30-236 and src/structures/ConnectedComponent.java:95-122:
+// same option names, defaults, output locations, log lines and exit codes.
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mfkc.h"
+
+namespace {
+
+[[noreturn]] void die(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    fputs("ERROR: ", stderr); vfprintf(stderr, fmt, ap); fputc('\n', stderr);
+    va_end(ap);
+    exit(1);                                              // Tool.java:450-462: logged, System.exit(1)
+}
+void info(const char *fmt, ...) { va_list ap; va_start(ap, fmt); fputs("INFO: ", stderr); vfprintf(stderr, fmt, ap); fputc('\n', stderr); va_end(ap); }
+void warn(const char *fmt, ...) { va_list ap; va_start(ap, fmt); fputs("WARN: ", stderr); vfprintf(stderr, fmt, ap); fputc('\n', stderr); va_end(ap); }
+
+// NumUtils.groupDigits ([itmo]/utils/NumUtils.java:163-174): 1'234'567
+std::string group_digits(unsigned long long v) {
+    std::string vs = std::to_string(v), ans;
+    while (vs.size() > 3) { ans = "'" + vs.substr(vs.size() - 3) + ans; vs.resize(vs.size() - 3); }
+    return vs + ans;
+}
+
+void mkdirs(const std::string &p) {
+    std::string cur;
+    for (size_t i = 0; i <= p.size(); i++) {
+        if (i == p.size() || p[i] == '/') { if (!cur.empty()) mkdir(cur.c_str(), 0777); }
+        if (i < p.size()) cur += p[i];
+    }
+}
+std::string base_name(const std::string &p) { const size_t i = p.find_last_of('/'); return i == std::string::npos ? p : p.substr(i + 1); }
+bool ends_with(const std::string &s, const std::string &suf) { return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0; }
+bool ends_with_ci(const std::string &s, const std::string &suf) {
+    return s.size() >= suf.size() && strcasecmp(s.c_str() + s.size() - suf.size(), suf.c_str()) == 0;
+}
+long long file_size(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0 ? (long long)st.st_size : 0; }
+
+// java.lang.Double.toString (JDK >= 19: shortest digits that round-trip)
+std::string java_double(double d) {
+    if (std::isnan(d)) return "NaN";
+    if (std::isinf(d)) return d > 0 ? "Infinity" : "-Infinity";
+    if (d == 0) return std::signbit(d) ? "-0.0" : "0.0";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, std::fabs(d), std::chars_format::scientific);   // d.ddddde[+-]xx, shortest
+    std::string s(buf, r.ptr);
+    const size_t e = s.find('e');
+    std::string digits = s.substr(0, e);
+    const int exp10 = atoi(s.c_str() + e + 1);
+    digits.erase(std::remove(digits.begin(), digits.end(), '.'), digits.end());
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    const std::string sign = d < 0 ? "-" : "";
+    const double a = std::fabs(d);
+    if (a >= 1e-3 && a < 1e7) {
+        const int point = exp10 + 1;                     // digits before the decimal point
+        std::string out;
+        if (point <= 0) out = "0." + std::string(-point, '0') + digits;
+        else if ((size_t)point >= digits.size()) out = digits + std::string(point - digits.size(), '0') + ".0";
+        else out = digits.substr(0, point) + "." + digits.substr(point);
+        return sign + out;
+    }
+    std::string frac = digits.size() > 1 ? digits.substr(1) : "0";
+    return sign + digits.substr(0, 1) + "." + frac + "E" + std::to_string(exp10);
+}
+
+struct Args {
+    std::string tool;
+    std::map<std::string, std::vector<std::string>> opt;    // canonical long name -> values
+    bool has(const std::string &k) const { return opt.count(k) != 0; }
+    std::string one(const std::string &k, const std::string &def = "") const {
+        auto it = opt.find(k);
+        return it == opt.end() || it->second.empty() ? def : it->second[0];
+    }
+    std::vector<std::string> many(const std::string &k) const { auto it = opt.find(k); return it == opt.end() ? std::vector<std::string>() : it->second; }
+};
+
+// commons-cli PosixParser behaviour that matters here: a multi-valued option takes every following
+// token up to the next option ([itmo]/utils/tool/parameters/MultiValuedParameter.java:13-18).
+Args parse_args(int argc, char **argv) {
+    static const std::map<std::string, std::string> alias = {
+        {"-t", "tool"}, {"--tool", "tool"}, {"-k", "k"}, {"--k", "k"}, {"-i", "reads"}, {"--reads", "reads"},
+        {"-b", "maximal-bad-frequence"}, {"--maximal-bad-frequence", "maximal-bad-frequence"},
+        {"--output-dir", "output-dir"}, {"--stats-dir", "stats-dir"}, {"-w", "work-dir"}, {"--work-dir", "work-dir"},
+        {"-cm", "components-file"}, {"--components-file", "components-file"}, {"-ka", "kmers"}, {"--kmers", "kmers"},
+        {"--selected", "selected"}, {"--threshold", "threshold"}, {"-p", "available-processors"},
+        {"--available-processors", "available-processors"}, {"--gpu", "gpu"}, {"--gpu-variant", "gpu-variant"},
+        {"--force", "force"}, {"-v", "verbose"}, {"--verbose", "verbose"}};
+    Args a;
+    std::string cur;
+    for (int i = 1; i < argc; i++) {
+        const std::string t = argv[i];
+        const bool is_opt = t.size() > 1 && t[0] == '-' && !(t[1] >= '0' && t[1] <= '9');
+        if (is_opt) {
+            auto it = alias.find(t);
+            if (it == alias.end()) die("Unrecognized option: %s", t.c_str());
+            cur = it->second;
+            a.opt[cur];
+        } else {
+            if (cur.empty()) die("Unexpected argument: %s", t.c_str());
+            a.opt[cur].push_back(t);
+        }
+    }
+    a.tool = a.one("tool", "matrix-builder");
+    return a;
+}
+
+int parse_int(const Args &a, const std::string &key, bool mandatory, int def) {
+    if (!a.has(key) || a.many(key).empty()) {
+        if (mandatory) die("Missing mandatory parameter --%s", key.c_str());
+        return def;
+    }
+    char *end = nullptr;
+    const std::string v = a.one(key);
+    const long x = strtol(v.c_str(), &end, 10);
+    if (*end) die("Can't parse '%s' as integer for --%s", v.c_str(), key.c_str());
+    return (int)x;
+}
+
+struct Gpu {
+    int device = 0;
+    int variant = MFKC_VARIANT_HASH;
+};
+Gpu gpu_opts(const Args &a) {
+    Gpu g;
+    g.device = parse_int(a, "gpu", false, 0);
+    const std::string v = a.one("gpu-variant", "hash");
+    if (v == "hash") g.variant = MFKC_VARIANT_HASH;
+    else if (v == "sort") g.variant = MFKC_VARIANT_SORT;
+    else if (v == "direct") g.variant = MFKC_VARIANT_HASH_DIRECT;
+    else die("--gpu-variant must be hash, sort or direct");
+    return g;
+}
+
+std::string reader_name(const std::string &path) {
+    mfkc_reader *r = nullptr; char err[512] = "";
+    if (mfkc_reader_open(path.c_str(), &r, err, sizeof err) != MFKC_OK) die("%s", err);
+    std::string n = mfkc_reader_name(r);
+    mfkc_reader_close(r);
+    return n;
+}
+
+#define CK(ctx, call) do { int rc__ = (call); if (rc__ != MFKC_OK) die("%s (libmfkc %d)", mfkc_last_error(ctx), rc__); } while (0)
+
+// ---- IOUtils.loadReads for one file: stream batches of kept reads into `submit`
+template <class F>
+void for_each_batch(mfkc_ctx *ctx, const std::string &file, F submit) {
+    info("Loading file %s...", base_name(file).c_str());
+    mfkc_reader *r = nullptr; char err[512] = "";
+    if (mfkc_reader_open(file.c_str(), &r, err, sizeof err) != MFKC_OK) die("%s", err);
+    const size_t cap_bases = 256u << 20; const uint32_t cap_reads = 1u << 21;
+    static void *h_bases = nullptr, *h_offs = nullptr;
+    if (!h_bases) { CK(ctx, mfkc_pinned_alloc(ctx, cap_bases, &h_bases)); CK(ctx, mfkc_pinned_alloc(ctx, ((size_t)cap_reads + 1) * 8, &h_offs)); }
+    unsigned long long reads = 0;
+    for (;;) {
+        uint32_t n = 0;
+        const int rc = mfkc_reader_next(r, (uint8_t *)h_bases, cap_bases, (uint64_t *)h_offs, cap_reads, &n);
+        if (rc != MFKC_OK) die("%s: %s", file.c_str(), mfkc_reader_error(r));
+        if (!n) break;
+        submit((const uint8_t *)h_bases, (const uint64_t *)h_offs, n);
+        reads += n;
+    }
+    uint64_t c[2]; mfkc_reader_counters(r, c);
+    if (c[1]) info("Skipped %s (%.1f%%) out of %s reads (because of N nucleotide), file %s", group_digits(c[1]).c_str(),
+                   c[1] * 100.0 / c[0], group_digits(c[0]).c_str(), base_name(file).c_str());
+    info("%s reads added", group_digits(reads).c_str());               // src/io/IOUtils.java:863
+    mfkc_reader_close(r);
+}
+
+// ---- KmersCounterMain.runImpl (src/tools/KmersCounterMain.java:65-120) for one sample
+std::string count_sample(mfkc_ctx *ctx, int k, int b, const std::vector<std::string> &files, const std::string &name,
+                         const std::string &out_dir, const std::string &st_dir) {
+    CK(ctx, mfkc_reset(ctx));
+    for (const auto &f : files)
+        for_each_batch(ctx, f, [&](const uint8_t *bases, const uint64_t *offs, uint32_t n) { CK(ctx, mfkc_submit_reads(ctx, bases, offs, n)); });
+    CK(ctx, mfkc_flush(ctx));
+    mkdirs(out_dir); mkdirs(st_dir);
+    const std::string out_file = out_dir + "/" + name + ".kmers.bin", st_file = st_dir + "/" + name + ".stat.txt";
+    uint64_t good = 0;
+    CK(ctx, mfkc_emit_begin(ctx, b, &good));
+    FILE *f = fopen(out_file.c_str(), "wb");
+    if (!f) die("Can't write %s", out_file.c_str());
+    static void *h_out = nullptr; const size_t chunk = 16777200;       // KMERS_WORK_RANGE_SIZE, src/io/IOUtils.java:30
+    if (!h_out) CK(ctx, mfkc_pinned_alloc(ctx, chunk, &h_out));
+    for (;;) {
+        size_t w = 0;
+        CK(ctx, mfkc_emit_next(ctx, (uint8_t *)h_out, chunk, &w));
+        if (!w) break;
+        if (fwrite(h_out, 1, w, f) != w) die("Can't write %s", out_file.c_str());
+    }
+    fclose(f);
+    static uint64_t hist[MFKC_HIST_BINS];
+    CK(ctx, mfkc_histogram(ctx, hist));
+    if (mfkc_write_stat_file(st_file.c_str(), hist) != MFKC_OK) die("Can't write %s", st_file.c_str());
+    uint64_t st[6]; CK(ctx, mfkc_stats(ctx, st));
+    const uint64_t size = st[0];
+    // src/tools/KmersCounterMain.java:103-116
+    info("%s k-mers found, %s (%.1f%%) of them is good (not erroneous)", group_digits(size).c_str(), group_digits(good).c_str(),
+         good * 100.0 / size);
+    if (size == 0) warn("No k-mers found in reads! Perhaps you reads file is empty or k-mer size is too big");
+    else if (good == 0 || good < (uint64_t)(size * 0.03))
+        warn("Too few good k-mers were found! Perhaps you should decrease k-mer size or --maximal-bad-frequency value");
+    const uint64_t all = (1ull << (2 * k)) / 2;
+    if (size == all) warn("All possible k-mers were found in reads! Perhaps you should increase k-mer size");
+    else if (size >= (uint64_t)(all * 0.99)) warn("Almost all possible k-mers were found in reads! Perhaps you should increase k-mer size");
+    info("Good k-mers printed to %s", out_file.c_str());
+    return out_file;
+}
+
+mfkc_ctx *make_ctx(int k, const Gpu &g, uint64_t expected_kmers) {
+    if (k <= 0) die("The size of k-mer must be at least 1.");               // KmersCounterMain.java:66-69
+    if (k > 31) die("The size of k-mer must be no more than 31.");          // KmersCounterMain.java:70-73
+    mfkc_cfg cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof cfg; cfg.k = k; cfg.device = g.device; cfg.variant = g.variant;
+    cfg.expected_kmers = expected_kmers;
+    mfkc_ctx *ctx = nullptr;
+    const int rc = mfkc_create(&cfg, &ctx);
+    if (rc != MFKC_OK) die("%s (libmfkc %d)", mfkc_last_error(nullptr), rc);
+    return ctx;
+}
+
+uint64_t estimate_bases(const std::vector<std::string> &files) {
+    // plain FASTQ: about half of the bytes are bases; gzip: ~4x compression.  Only a sizing hint.
+    double b = 0;
+    for (const auto &f : files) {
+        const double sz = (double)file_size(f);
+        const bool gz = ends_with_ci(f, ".gz");
+        const bool fq = ends_with_ci(f, ".fastq") || ends_with_ci(f, ".fq") || ends_with_ci(f, ".fastq.gz") || ends_with_ci(f, ".fq.gz");
+        b += sz * (gz ? 4.0 : 1.0) * (fq ? 0.5 : 1.0);
+    }
+    return (uint64_t)b;
+}
+
+// ---- kmer-counter-many (src/tools/KmersCounterForManyFilesMain.java:69-120)
+int tool_counter(const Args &a, bool many) {
+    const int k = parse_int(a, "k", true, 0);
+    const int b = parse_int(a, "maximal-bad-frequence", false, 1);
+    std::vector<std::string> files = a.many("reads");
+    if (files.empty()) die("Missing mandatory parameter --reads");
+    const std::string work = a.one("work-dir", "workDir");
+    const std::string out_dir = a.one("output-dir", work + "/kmers"), st_dir = a.one("stats-dir", work + "/stats");
+    const Gpu g = gpu_opts(a);
+    std::vector<std::pair<std::string, std::vector<std::string>>> samples;
+    if (many) {
+        std::sort(files.begin(), files.end());                             // Arrays.sort(files): path order
+        std::vector<std::string> names;
+        for (const auto &f : files) names.push_back(reader_name(f));
+        for (size_t i = 0; i < files.size();) {
+            const bool pair = i + 1 < files.size() &&
+                              ((ends_with(names[i], "_r1") && ends_with(names[i + 1], "_r2")) ||
+                               (ends_with(names[i], "_R1") && ends_with(names[i + 1], "_R2")));
+            if (pair) { samples.push_back({names[i].substr(0, names[i].size() - 3), {files[i], files[i + 1]}}); i += 2; }
+            else { samples.push_back({names[i], {files[i]}}); i += 1; }
+        }
+    } else {
+        // KmersCounterMain.getName :122-137
+        std::string name;
+        const std::string n1 = reader_name(files[0]);
+        if (files.size() == 2) {
+            const std::string n2 = reader_name(files[1]);
+            const bool pair = (ends_with(n1, "_r1") && ends_with(n2, "_r2")) || (ends_with(n1, "_R1") && ends_with(n2, "_R2"));
+            name = pair ? n1.substr(0, n1.size() - 3) : n1 + "+";
+        } else name = n1 + (files.size() > 1 ? "+" : "");
+        samples.push_back({name, files});
+    }
+    uint64_t biggest = 0;
+    for (const auto &s : samples) biggest = std::max(biggest, estimate_bases(s.second));
+    mfkc_ctx *ctx = make_ctx(k, g, biggest);
+    std::vector<std::string> outs;
+    for (const auto &s : samples) outs.push_back(count_sample(ctx, k, b, s.second, s.first, out_dir, st_dir));
+    mfkc_destroy(ctx);
+    for (const auto &o : outs) printf("%s\n", o.c_str());                 // "resulting-kmers-files"
+    return 0;
+}
+
+// ---- ConnectedComponent.loadComponents (src/structures/ConnectedComponent.java:95-122)
+void load_components(const std::string &path, std::vector<int64_t> &keys, std::vector<uint64_t> &off) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) die("Can't load components: file not found");
+    std::vector<uint8_t> buf((size_t)file_size(path));
+    if (fread(buf.data(), 1, buf.size(), f) != buf.size()) die("Can't load components: unknown IOException");
+    fclose(f);
+    size_t p = 0;
+    auto need = [&](size_t n) { if (p + n > buf.size()) die("Can't load components: file corrupted or format mismatch! Do you set a wrong file?"); };
+    auto be32 = [&]() { need(4); uint32_t v = 0; for (int i = 0; i < 4; i++) v = (v << 8) | buf[p++]; return (int32_t)v; };
+    auto be64 = [&]() { need(8); uint64_t v = 0; for (int i = 0; i < 8; i++) v = (v << 8) | buf[p++]; return (int64_t)v; };
+    const int32_t cnt = be32();
+    off.assign(1, 0);
+    for (int32_t i = 0; i < cnt; i++) {
+        const int32_t size = be32();
+        (void)be64();                                                       // weight
+        for (int32_t j = 0; j < size; j++) keys.push_back(be64());
+        off.push_back(keys.size());
+    }
+}
+
+std::vector<uint8_t> slurp(const std::string &path) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) die("Can't load k-mers file %s", path.c_str());
+    std::vector<uint8_t> buf((size_t)file_size(path));
+    if (fread(buf.data(), 1, buf.size(), f) != buf.size()) die("Can't load k-mers file %s", path.c_str());
+    fclose(f);
+    if (buf.size() % 10) die("BAD division by work range");                 // src/io/KmersLoadWorker.java:17-19
+    return buf;
+}
+
+// ---- features-calculator (src/tools/FeaturesCalculatorMain.java:77-236)
+int tool_features(const Args &a) {
+    const int k = parse_int(a, "k", true, 0);
+    if (!a.has("components-file")) die("Missing mandatory parameter --components-file");
+    const std::string cm = a.one("components-file");
+    const int threshold = parse_int(a, "threshold", false, 0);
+    const std::string work = a.one("work-dir", "workDir");
+    const Gpu g = gpu_opts(a);
+    std::vector<int64_t> keys; std::vector<uint64_t> off;
+    load_components(cm, keys, off);
+    const uint32_t n_comp = (uint32_t)off.size() - 1;
+    info("%s components loaded from %s", group_digits(n_comp).c_str(), cm.c_str());
+    if (n_comp == 0) die("No components were found in input files! Can't continue the calculations.");
+    const std::string out_dir = work + "/vectors";
+    mkdirs(out_dir);
+    mfkc_ctx *ctx = make_ctx(k, g, 0);
+    if (keys.empty()) keys.push_back(0);
+    CK(ctx, mfkc_fc_load_components(ctx, keys.data(), off.data(), n_comp));
+    const auto sel_files = a.many("selected");
+    if (!sel_files.empty()) {
+        static const uint8_t none = 0;
+        CK(ctx, mfkc_fc_set_selected(ctx, &none, 0));                       // an (initially empty) active filter
+        for (const auto &sf : sel_files) { info("Loading file %s...", base_name(sf).c_str()); auto b = slurp(sf); if (!b.empty()) CK(ctx, mfkc_fc_set_selected(ctx, b.data(), b.size() / 10)); }
+    }
+    std::vector<int64_t> vec(n_comp); std::vector<uint64_t> found(n_comp), cnt(n_comp);
+    auto print_vectors = [&](const std::string &stem, const std::string &shown) {
+        CK(ctx, mfkc_fc_features(ctx, threshold, vec.data(), found.data(), cnt.data()));
+        const std::string vf = out_dir + "/" + stem + ".vec", bf = out_dir + "/" + stem + ".breadth";
+        FILE *f = fopen(vf.c_str(), "w"); if (!f) die("Can't write vector to file %s", vf.c_str());
+        for (uint32_t i = 0; i < n_comp; i++) fprintf(f, "%lld\n", (long long)vec[i]);
+        fclose(f);
+        f = fopen(bf.c_str(), "w"); if (!f) die("Can't write vector to file %s", bf.c_str());
+        for (uint32_t i = 0; i < n_comp; i++) fprintf(f, "%s\n", java_double((double)found[i] / (double)cnt[i]).c_str());   // 0/0 -> NaN
+        fclose(f);
+        info("Features for file %s printed to %s", shown.c_str(), vf.c_str());
+        info("Components breadth coverage for file %s printed to %s", shown.c_str(), bf.c_str());
+        printf("%s\n", vf.c_str());                                        // "features-files"
+    };
+    for (const auto &rf : a.many("reads")) {                               // :120-134
+        CK(ctx, mfkc_fc_reset_values(ctx));
+        for_each_batch(ctx, rf, [&](const uint8_t *bases, const uint64_t *offs, uint32_t n) { CK(ctx, mfkc_fc_add_reads(ctx, bases, offs, n)); });
+        print_vectors(reader_name(rf), base_name(rf));
+    }
+    for (const auto &kf : a.many("kmers")) {                               // :136-163
+        CK(ctx, mfkc_fc_reset_values(ctx));
+        info("Loading file %s...", base_name(kf).c_str());
+        const auto recs = slurp(kf);
+        const size_t chunk = 16777200;                                      // src/io/IOUtils.java:30
+        for (size_t p = 0; p < recs.size(); p += chunk) {
+            const size_t nbytes = std::min(chunk, recs.size() - p);
+            CK(ctx, mfkc_fc_add_records(ctx, recs.data() + p, nbytes / 10));
+        }
+        std::string stem = base_name(kf);
+        if (ends_with_ci(stem, ".kmers.bin")) stem.resize(stem.size() - 10);
+        print_vectors(stem, base_name(kf));
+    }
+    mfkc_destroy(ctx);
+    return 0;
+}
+
+// ---- gen-reads: synthetic FASTQ / FASTA for tests (BASELINE.md section 4 generator)
+int tool_gen(int argc, char **argv) {
+    // mfkc_cli gen-reads <out.fastq|out.fa> <n_reads> [sample] [total_genome_bp] [n_genomes]
+    if (argc < 4) die("usage: mfkc_cli gen-reads <out.fastq|.fa> <n_reads> [sample] [total_genome_bp] [n_genomes]");
+    mfkc_synth_cfg c; mfkc_synth_defaults(&c);
+    const std::string out = argv[2];
+    const uint64_t n = strtoull(argv[3], nullptr, 10);
+    if (argc > 4) c.sample = (uint32_t)atoi(argv[4]);
+    if (argc > 5) c.total_genome_bp = strtoull(argv[5], nullptr, 10);
+    if (argc > 6) c.n_genomes = (uint32_t)atoi(argv[6]);
+    const bool fq = ends_with_ci(out, ".fastq") || ends_with_ci(out, ".fq");
+    FILE *f = fopen(out.c_str(), "w"); if (!f) die("Can't write %s", out.c_str());
+    std::vector<uint8_t> buf((size_t)std::min<uint64_t>(n, 1u << 16) * c.read_len);
+    const std::string qual(c.read_len, 'I');
+    for (uint64_t s = 0; s < n; s += 1u << 16) {
+        const uint64_t m = std::min<uint64_t>(1u << 16, n - s);
+        if (mfkc_synth_reads_host(&c, s, m, buf.data()) != MFKC_OK) die("generator failed");
+        for (uint64_t i = 0; i < m; i++) {
+            const char *r = (const char *)buf.data() + i * c.read_len;
+            if (fq) {
+                std::string q = qual;
+                q[(s + i) % c.read_len] = '5';                              // a char < 64: forces Sanger detection
+                for (uint32_t j = 0; j < c.read_len; j++) if (r[j] == 'N') q[j] = '!';
+                fprintf(f, "@read_%llu\n%.*s\n+\n%s\n", (unsigned long long)(s + i), (int)c.read_len, r, q.c_str());
+            } else fprintf(f, ">read_%llu\n%.*s\n", (unsigned long long)(s + i), (int)c.read_len, r);
+        }
+    }
+    fclose(f);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc > 1 && !strcmp(argv[1], "gen-reads")) return tool_gen(argc, argv);
+    const Args a = parse_args(argc, argv);
+    if (a.tool == "kmer-counter-many") return tool_counter(a, true);
+    if (a.tool == "kmer-counter") return tool_counter(a, false);
+    if (a.tool == "features-calculator") return tool_features(a);
+    die("Tool '%s' is outside the hot path this build replaces (kmer-counter-many, kmer-counter, features-calculator)", a.tool.c_str());
+}

@@ -492,6 +492,7 @@ static int reserve_staging(mfkc_ctx *ctx, uint64_t add) {
         if (!ctx->cfg.staging_bytes && ctx->cfg.expected_kmers)
             want = std::max<uint64_t>(want, ctx->cfg.expected_kmers + ctx->cfg.expected_kmers / 50 + (uint64_t)MAX_REGIONS * 64);
         if (!ctx->cfg.staging_bytes && want > ctx->rb_cap_max) want = std::max<uint64_t>(ctx->rb_cap_max, add);
+        if (!ctx->cfg.staging_bytes && want > ctx->rb_cap_max) want = std::max<uint64_t>(ctx->rb_cap_max, add);
         if (want < add) want = add;
         cudaError_t e = big_alloc(ctx, (void **)&ctx->rb_keys, want * 8);
         if (e != cudaSuccess) return fail(ctx, MFKC_E_OOM, "cannot allocate the key staging buffer");

@@ -1,0 +1,111 @@
+"""GPU tests of the native host tool (mfkc_cli): MetaFast's own command lines end to end --
+files in, .kmers.bin / .stat.txt / .vec / .breadth out -- against the oracle, byte for byte."""
+import gzip
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import metafast_b200 as m
+from oracle import oracle as orc
+from tests.conftest import INPUTS, ROOT
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "metafast_b200", "bin", "mfkc_cli")
+
+
+def run_cli(*args, ok=True):
+    r = subprocess.run([CLI] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if ok:
+        assert r.returncode == 0, r.stderr
+    return r
+
+
+@pytest.mark.parametrize("variant", ["hash", "sort", "direct"])
+def test_kmer_counter_many_config1(built, tmp_path, variant):
+    """BASELINE config 1 through the CLI: default -b (1), default output locations."""
+    files = [os.path.join(INPUTS, "meta_test_%d.fa" % n) for n in (3, 1, 2)]
+    wd = tmp_path / "wd"
+    r = run_cli("-t", "kmer-counter-many", "-k", 31, "-i", *files, "-w", wd, "--gpu-variant", variant)
+    want = orc.kmer_counter_many(files, 31, 1)
+    assert r.stdout.split() == [str(wd / "kmers" / ("meta_test_%d.kmers.bin" % n)) for n in (1, 2, 3)]
+    for name, (rec, stat, counts) in want.items():
+        assert open(wd / "kmers" / (name + ".kmers.bin"), "rb").read() == rec
+        assert open(wd / "stats" / (name + ".stat.txt")).read() == stat
+    assert "17'063 k-mers found, 16'918 (99.2%) of them is good (not erroneous)" in r.stderr
+
+
+def test_paired_gz_fastq_and_naming(built, tmp_path):
+    """_R1/_R2 pairing into one sample, gzip input, Sanger sniffing, N-read dropping."""
+    for tag, sample in (("R1", 0), ("R2", 1)):
+        fq = tmp_path / ("lib_%s.fastq" % tag)
+        run_cli("gen-reads", fq, 3000, sample, 200000, 5)
+        with open(fq, "rb") as f, gzip.open(str(fq) + ".gz", "wb") as g:
+            shutil.copyfileobj(f, g)
+        os.remove(fq)
+    single = tmp_path / "other.fa"
+    run_cli("gen-reads", single, 1000, 2, 200000, 5)
+    files = [str(tmp_path / "lib_R2.fastq.gz"), str(single), str(tmp_path / "lib_R1.fastq.gz")]
+    out, st = tmp_path / "o", tmp_path / "s"
+    run_cli("-t", "kmer-counter-many", "-k", 23, "-b", 2, "-i", *files, "--output-dir", out, "--stats-dir", st)
+    want = orc.kmer_counter_many(files, 23, 2)
+    assert sorted(want) == ["lib", "other"]
+    for name, (rec, stat, counts) in want.items():
+        assert open(out / (name + ".kmers.bin"), "rb").read() == rec
+        assert open(st / (name + ".stat.txt")).read() == stat
+    # kmer-counter (single sample) naming: two unpaired files -> "<first>+"
+    run_cli("-t", "kmer-counter", "-k", 23, "-i", str(single), files[0], "-w", tmp_path / "w2")
+    reads = orc.parse_reads(str(single)) + orc.parse_reads(files[0])
+    assert open(tmp_path / "w2" / "kmers" / "other+.kmers.bin", "rb").read() == orc.kmers_bin(orc.count_reads(reads, 23), 1, 23)
+
+
+def test_cli_errors(built, tmp_path):
+    f = os.path.join(INPUTS, "meta_test_2.fa")
+    assert run_cli("-t", "kmer-counter-many", "-k", 32, "-i", f, ok=False).returncode == 1     # KmersCounterMain.java:70-73
+    assert run_cli("-t", "kmer-counter-many", "-k", 0, "-i", f, ok=False).returncode == 1
+    assert run_cli("-t", "kmer-counter-many", "-i", f, ok=False).returncode == 1               # -k is mandatory
+    bad = tmp_path / "bad.fa"
+    bad.write_text(">a\nACGTXXACGT\n")
+    assert run_cli("-t", "kmer-counter-many", "-k", 5, "-i", bad, ok=False).returncode == 1
+    assert run_cli("-t", "seq-builder", "-k", 5, ok=False).returncode == 1
+
+
+def test_features_calculator_cli(built, tmp_path):
+    rng = np.random.default_rng(17)
+    files = [os.path.join(INPUTS, "meta_test_%d.fa" % n) for n in (1, 2, 3)]
+    wd = tmp_path / "wd"
+    run_cli("-t", "kmer-counter-many", "-k", 31, "-i", *files, "-w", wd)
+    per_sample = orc.kmer_counter_many(files, 31, 1)
+    all_keys = sorted(set().union(*[set(c) for _, _, c in per_sample.values()]))
+    comps = []
+    for _ in range(60):
+        size = int(rng.integers(1, 400))
+        comps.append((int(rng.integers(0, 1000)), [all_keys[int(i)] for i in rng.integers(0, len(all_keys), size)]))
+    comps.append((0, []))
+    comps.append((5, [int(x) for x in rng.integers(0, 1 << 62, 7)]))          # k-mers no sample contains
+    cm = tmp_path / "components.bin"
+    cm.write_bytes(orc.save_components(comps))
+    kfiles = [str(wd / "kmers" / ("meta_test_%d.kmers.bin" % n)) for n in (1, 2, 3)]
+    fw = tmp_path / "fw"
+    r = run_cli("-t", "features-calculator", "-k", 31, "-cm", cm, "-ka", *kfiles, "-w", fw)
+    for n in (1, 2, 3):
+        rec = per_sample["meta_test_%d" % n][0]
+        acc = orc.presence_for_kmers([k for _, c in comps for k in c], orc.load_kmers_bin(rec))
+        vec, breadth, _, _ = orc.features(comps, acc, 0)
+        assert open(fw / "vectors" / ("meta_test_%d.vec" % n)).read() == orc.vec_text(vec)
+        assert open(fw / "vectors" / ("meta_test_%d.breadth" % n)).read() == orc.breadth_text(breadth)
+    # --threshold, --selected and reads mode (-i)
+    fw2 = tmp_path / "fw2"
+    run_cli("-t", "features-calculator", "-k", 31, "-cm", cm, "-ka", kfiles[0], "-i", files[1], "--selected", kfiles[2],
+            "--threshold", 3, "-w", fw2)
+    selected = orc.load_kmers([per_sample["meta_test_3"][0]], 0)
+    acc = orc.presence_for_kmers([k for _, c in comps for k in c], orc.load_kmers_bin(per_sample["meta_test_1"][0]))
+    vec, breadth, _, _ = orc.features(comps, acc, 3, selected)
+    assert open(fw2 / "vectors" / "meta_test_1.vec").read() == orc.vec_text(vec)
+    assert open(fw2 / "vectors" / "meta_test_1.breadth").read() == orc.breadth_text(breadth)
+    acc = orc.presence_for_reads([k for _, c in comps for k in c], orc.parse_reads(files[1]), 31)
+    vec, breadth, _, _ = orc.features(comps, acc, 3, selected)
+    assert open(fw2 / "vectors" / "meta_test_2.vec").read() == orc.vec_text(vec)
+    assert open(fw2 / "vectors" / "meta_test_2.breadth").read() == orc.breadth_text(breadth)

@@ -1,0 +1,176 @@
+"""CPU tests of the host side of libmfkc (parsers, naming, writers, generator) and of the C ABI
+surface.  No GPU: no compute entry point is called."""
+import ctypes as C
+import gzip
+import os
+import re
+
+import numpy as np
+import pytest
+
+import metafast_b200 as m
+from metafast_b200 import _abi
+from oracle import oracle as orc
+from tests import _oracle_c
+from tests.conftest import INPUTS, ROOT, has_gpu
+
+
+def test_abi_exports_every_declared_symbol(built):
+    """include/mfkc.h is the contract: every function it declares is exported and bound."""
+    hdr = open(os.path.join(ROOT, "include", "mfkc.h")).read()
+    declared = set(re.findall(r"\b(mfkc_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"mfkc_cfg", "mfkc_synth_cfg"}
+    lib = m.load()
+    assert declared == set(_abi.SIGNATURES), declared ^ set(_abi.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.mfkc_abi_version() == 1
+    assert C.sizeof(_abi.MfkcCfg) == 88 and C.sizeof(_abi.SynthCfg) == 80
+
+
+def test_no_cpu_fallback(built):
+    if has_gpu():
+        pytest.skip("GPU present")
+    with pytest.raises(m.MfkcError) as e:
+        m.KmerCounter(31)
+    assert e.value.code == _abi.E_CUDA and "no CPU fallback" in e.value.msg
+
+
+def test_product_does_not_touch_the_oracle():
+    """the product path must never import, link or execute anything under oracle/"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "metafast_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.lower().replace("oracle/ref_cpu.c", "").replace("the oracle", "") or f == "counter.py", f
+
+
+def _write(p, text, gz=False):
+    if gz:
+        with gzip.open(p, "wb") as f:
+            f.write(text.encode("latin-1"))
+    else:
+        with open(p, "wb") as f:
+            f.write(text.encode("latin-1"))
+
+
+FASTA_TRICKY = (">r1 multi-line\nACGTAC\nGTTTGA\n;comment line\nGGGCCC\r\n>r2 with N\nACGTNACGT\n>r3 lower\nacgtacgtaa\n"
+                ">empty\n>r4\n\nAC\n\nGT\n>r5 n\nacgtn\n>last no newline\nTTTTGGGG")
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_fasta_parser_rules(built, tmp_path, gz):
+    p = str(tmp_path / ("x.fa.gz" if gz else "x.fasta"))
+    _write(p, FASTA_TRICKY, gz)
+    want = ["ACGTACGTTTGA", "GGGCCC", "acgtacgtaa", "ACGT", "TTTTGGGG"]
+    assert orc.parse_reads(p) == want
+    assert m.read_file_reads(p) == want
+    b, o = _oracle_c.parse_file(p)
+    assert [bytes(b[int(o[i]):int(o[i + 1])]).decode() for i in range(len(o) - 1)] == want
+    assert m.reader_name(p) == "x" == orc.library_name(p)
+
+
+def _fastq(records):
+    return "".join("@%s\n%s\n+%s\n%s\n" % (n, s, n, q) for n, s, q in records)
+
+
+def test_fastq_parser_rules(built, tmp_path):
+    recs = [("a", "ACGTACGT", "IIIIIII5"),       # '5' < 64 -> the file is Sanger
+            ("b", "ACGTNCGT", "IIII!III"),       # N -> dropped
+            ("c", "ACGTACGT", "IIII!III"),       # phred 0 under a real base -> dropped
+            ("d", "acgtacgt", "IIIIIIII"),
+            ("e", "ACGT.CGT", "IIIIIIII"),       # '.' -> dropped
+            ("f", "ACGTACGT", "IIIaIIII"),       # 'a' = phred 64 -> 6-bit alias of 0 -> dropped (DnaQ.java:140-150)
+            ("g", "", ""),
+            ("h", "TTTT", "@@@@")]               # '@' in Sanger = phred 31: kept
+    text = _fastq(recs[:3]) + "\n\n" + _fastq(recs[3:])             # empty lines between records are skipped
+    p = str(tmp_path / "s_R1.fastq")
+    _write(p, text)
+    want = ["ACGTACGT", "acgtacgt", "", "TTTT"]
+    assert orc.parse_reads(p) == want
+    assert m.read_file_reads(p) == want
+    b, o = _oracle_c.parse_file(p)
+    assert [bytes(b[int(o[i]):int(o[i + 1])]).decode() for i in range(len(o) - 1)] == want
+    # Illumina (+64) file: every quality char >= 64 in the first 1000 reads; '@' is then phred 0
+    ill = _fastq([("a", "ACGT", "hhhh"), ("b", "ACGT", "hh@h"), ("c", "GGGG", "efgh")])
+    p2 = str(tmp_path / "ill.fq.gz")
+    _write(p2, ill, gz=True)
+    assert orc.parse_reads(p2) == ["ACGT", "GGGG"] == m.read_file_reads(p2)
+    assert m.reader_name(p2) == "ill"
+    # CRLF line ends
+    p3 = str(tmp_path / "crlf.fastq")
+    _write(p3, _fastq([("a", "ACGT", "II5I")]).replace("\n", "\r\n"))
+    assert m.read_file_reads(p3) == ["ACGT"] == orc.parse_reads(p3)
+
+
+def test_parser_errors(built, tmp_path):
+    cases = {"bad_struct.fastq": "ACGT\nIIII\n", "len.fastq": "@a\nACGT\n+\nIII\n", "trunc.fastq": "@a\nACGT\n+\n",
+             "badchar.fa": ">a\nACGTXACGT\n", "iupac.fa": ">a\nACGTRACGT\n", "qual.fastq": "@a\nACGT\n+\nII\x1fI\n"}
+    for name, text in cases.items():
+        p = str(tmp_path / name)
+        _write(p, text)
+        with pytest.raises(Exception):
+            orc.parse_reads(p)
+        with pytest.raises(m.MfkcError) as e:
+            m.read_file_reads(p)
+        assert e.value.code == _abi.E_FORMAT, name
+    with pytest.raises(m.MfkcError):
+        m.read_file_reads(str(tmp_path / "unknown.txt"))
+    with pytest.raises(m.MfkcError):
+        m.read_file_reads(str(tmp_path / "missing.fa"))
+
+
+def test_reader_matches_oracle_on_fixtures(built):
+    for f in ("meta_test_1.fa", "meta_test_2.fa", "meta_test_3.fa", "tinytest_A.fastq", "tinytest_B.fastq"):
+        p = os.path.join(INPUTS, f)
+        assert m.read_file_reads(p) == orc.parse_reads(p)
+    # small batches exercise the carry-over of a read that does not fit
+    got = []
+    for b, o in m.read_file(os.path.join(INPUTS, "meta_test_2.fa"), batch_reads=7, batch_bases=1000):
+        s = b.tobytes().decode()
+        got += [s[int(o[i]):int(o[i + 1])] for i in range(len(o) - 1)]
+    assert got == orc.parse_reads(os.path.join(INPUTS, "meta_test_2.fa"))
+
+
+def test_sample_grouping():
+    """src/tools/KmersCounterForManyFilesMain.java:73-108, KmersCounterMain.java:122-137"""
+    files = ["/d/b_R2.fq.gz", "/d/a.fa", "/d/b_R1.fq.gz", "/d/c_r1.fastq", "/d/c_r2.fastq", "/d/z_R1.fq", "/d/x_R2.fq"]
+    got = orc.group_samples(files)
+    assert got == [("a", ["/d/a.fa"]), ("b", ["/d/b_R1.fq.gz", "/d/b_R2.fq.gz"]), ("c", ["/d/c_r1.fastq", "/d/c_r2.fastq"]),
+                   ("x_R2", ["/d/x_R2.fq"]), ("z_R1", ["/d/z_R1.fq"])]
+
+
+def test_stat_file_writer(built, tmp_path):
+    counts = {1: 3, 2: 3, 3: 1, 9: 32767}
+    hist = np.zeros(m.HIST_BINS, dtype=np.uint64)
+    for c in counts.values():
+        hist[c] += 1
+    p = str(tmp_path / "x.stat.txt")
+    m.write_stat_file(p, hist)
+    assert open(p).read() == orc.stat_txt(counts) == "# k-mer frequency\tnumber of such k-mers\n1\t1\n3\t2\n32767\t1\n\n"
+
+
+def test_synth_generator_is_deterministic(built):
+    cfg = m.synth_cfg(total_genome_bp=500000, n_genomes=6)
+    a = m.synth_reads_host(cfg, 0, 5000)
+    b = m.synth_reads_host(cfg, 1000, 1000)
+    assert (a[1000:2000] == b).all()                                  # counter-based: read i does not depend on the range
+    assert set(np.unique(a)) <= set(b"ACGTN")
+    other = m.synth_reads_host(m.synth_cfg(total_genome_bp=500000, n_genomes=6, sample=1), 0, 1000)
+    assert not (other == a[:1000]).all()                              # per-sample abundances / reads
+    # coverage makes k-mers repeat: far fewer distinct than instances
+    keep = ~(a == ord("N")).any(axis=1)
+    reads = [bytes(r).decode() for r in a[keep][:1500]]
+    counts = orc.count_reads(reads, 31)
+    assert len(counts) < 0.9 * sum(len(r) - 30 for r in reads)
+
+
+def test_owner_shard_is_a_partition(built):
+    lib = m.load()
+    rng = np.random.default_rng(1)
+    keys = [int(x) for x in rng.integers(0, 1 << 62, 2000)] + [0, 1, (1 << 62) - 1]
+    for g in (1, 2, 3, 8):
+        owners = [lib.mfkc_owner_shard(k, g) for k in keys]
+        assert all(0 <= o < g for o in owners)
+        if g > 1:
+            assert len(set(owners)) == g and max(np.bincount(owners)) < 2.0 * len(keys) / g

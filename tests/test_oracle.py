@@ -1,0 +1,132 @@
+"""CPU tests: the oracle against the golden vectors / known answers, and the two independent
+restatements (numpy + C) against each other.  No GPU."""
+import gzip
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import _oracle_c
+from tests.conftest import GOLDEN, INPUTS
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_config1_golden(built, n):
+    """BASELINE.md section 3 known answers for test_data/meta_test_{1,2,3}.fa, k=31, -b 1."""
+    gold = json.load(open(os.path.join(GOLDEN, "config1.json")))["meta_test_%d" % n]
+    survey = {1: (1917, 115020, 17063, 16918, 169180, "e660671016d5d1db", 15),
+              2: (540, 32400, 8176, 7321, 73210, "c90d8b0b553e2701", 13),
+              3: (1080, 64800, 14042, 11351, 113510, "591d0e32821afd8d", 15)}[n]
+    path = os.path.join(INPUTS, "meta_test_%d.fa" % n)
+    res = orc.kmer_counter_many([path], 31, 1)
+    (name, (rec, stat, counts)), = res.items()
+    assert name == "meta_test_%d" % n
+    reads = orc.parse_reads(path)
+    got = (len(reads), sum(len(r) - 30 for r in reads), len(counts), len(rec) // 10, len(rec),
+           orc.sha256_hex(rec)[:16], max(counts.values()))
+    assert got == survey                                             # SURVEY.md 8c / BASELINE.md 3
+    assert orc.sha256_hex(rec) == gold["sha256_sorted_records"]
+    assert {str(c): v for c, v in orc.histogram(counts).items()} == gold["hist"]
+    assert orc.sha256_hex(stat.encode()) == gold["stat_txt_sha256"]
+    assert stat.startswith("# k-mer frequency\tnumber of such k-mers\n1\t") and stat.endswith("\n\n")
+    # the C restatement (threads + striped maps) gives the same file, whatever -p is
+    bases, offsets = _oracle_c.parse_file(path)
+    for P in (1, 3, 8):
+        c_rec, c_hist, c_distinct, st = _oracle_c.count(bases, offsets, 31, 1, P=P)
+        assert c_rec == rec and c_distinct == len(counts)
+        assert st == [len(reads), len(reads), 90 * len(reads), 90 * len(reads)]
+    # reference iteration order differs from key order but holds the same multiset
+    u_rec, _, _, _ = _oracle_c.count(bases, offsets, 31, 1, P=4, sort=False)
+    assert u_rec != rec and orc.sorted_records(u_rec) == rec
+
+
+def test_micro_known_answers():
+    """A0 G1 C2 T3, first base most significant, key = min(fw, rc)."""
+    k5 = lambda s: orc.canonical_kmers(s, 5)[0]
+    assert k5("AAAAA") == 0 and k5("TTTTT") == 0
+    assert k5("GGGGG") == 341 and k5("CCCCC") == 341
+    assert k5("ACGTA") == 156 and k5("AACAT") == 35
+    assert orc.kmer_to_string(156, 5) in ("ACGTA", "TACGT")
+    for k in (1, 5, 21, 31, 32, 55, 63):                             # rolling rc == KmerUtils.reverseComplement
+        rng = np.random.default_rng(k)
+        s = "".join(rng.choice(list("ACGT"), 200))
+        mask = (1 << (2 * k)) - 1
+        for i, key in enumerate(orc.canonical_kmers(s, k)):
+            fw = 0
+            for ch in s[i:i + k]:
+                fw = (fw << 2) | orc.code(ch)
+            assert key == min(fw & mask, orc.reverse_complement(fw, k))
+
+
+def test_tinytest_fastq():
+    reads = orc.parse_reads(os.path.join(INPUTS, "tinytest_A.fastq"))
+    assert reads == ["AACATAAGC", "GAAGCCAAC"]                       # '#' < 64 -> Sanger, phred 2: kept
+    assert sorted(orc.count_reads(reads, 5)) == [26, 35, 104, 140, 193, 262, 416, 444, 501, 560]
+
+
+@pytest.mark.parametrize("k", [1, 4, 13, 16, 17, 31])
+def test_numpy_vs_scalar_vs_c(built, k):
+    rng = np.random.default_rng(100 + k)
+    reads = ["".join(rng.choice(list("ACGTacgt"), int(L))) for L in rng.integers(0, 120, 400)]
+    reads += ["A" * 50] * 300 + ["ACGT" * 10]
+    want = {}
+    for r in reads:
+        for key in orc.canonical_kmers(r, k):
+            want[key] = min(want.get(key, 0) + 1, 32767)
+    assert orc.count_reads(reads, k) == want
+    bases = np.frombuffer("".join(reads).encode(), dtype=np.uint8).copy()
+    offsets = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+    for b in (0, 1, 3):
+        rec, hist, distinct, st = _oracle_c.count(bases, offsets, k, b, P=3)
+        assert rec == orc.kmers_bin(want, b, k) and distinct == len(want)
+        assert {int(c): int(hist[c]) for c in np.nonzero(hist)[0]} == orc.histogram(want)
+    rec, _, _, st = _oracle_c.count(bases, offsets, k, 0, min_len=60, P=2)
+    assert rec == orc.kmers_bin(orc.count_reads(reads, k, 60), 0, k)
+    assert tuple(st) == orc.read_stats(reads, 60)
+
+
+def test_saturation_cpu(built):
+    reads = ["ACGTTGCA"] * 40000
+    counts = orc.count_reads(reads, 5)
+    assert set(counts.values()) == {32767}
+    bases = np.frombuffer("".join(reads).encode(), dtype=np.uint8).copy()
+    offsets = (np.arange(len(reads) + 1) * 8).astype(np.uint64)
+    rec, hist, _, _ = _oracle_c.count(bases, offsets, 5, 1, P=4)
+    assert rec == orc.kmers_bin(counts, 1, 5) and hist[32767] == len(counts)
+
+
+def test_records_roundtrip():
+    counts = {0: 5, 7: 1, (1 << 62) - 1: 32767, 12345678901234: 2}
+    rec = orc.kmers_bin(counts, 1)
+    assert len(rec) == 30 and rec[:10] == struct.pack(">qh", 0, 5)
+    assert orc.load_kmers_bin(rec) == [(0, 5), (12345678901234, 2), ((1 << 62) - 1, 32767)]
+    assert orc.load_kmers([rec, rec], 0) == {0: 10, 12345678901234: 4, (1 << 62) - 1: 32767}
+    comps = [(7, [1, 2, 3]), (0, []), (-1, [5])]
+    assert orc.load_components(orc.save_components(comps)) == comps
+
+
+def test_java_double_to_string():
+    f = orc.java_double_to_string
+    assert [f(x) for x in (0.0, 1.0, 0.5, 1 / 3, 2 / 3, 0.001, 5e-4, 1e7, 1234567.0, 0.1, float("nan"))] == \
+        ["0.0", "1.0", "0.5", "0.3333333333333333", "0.6666666666666666", "0.001", "5.0E-4", "1.0E7", "1234567.0", "0.1", "NaN"]
+
+
+def test_features_oracle_agreement(built):
+    rng = np.random.default_rng(3)
+    counts = orc.count_reads(orc.parse_reads(os.path.join(INPUTS, "meta_test_2.fa")), 31)
+    keys = sorted(counts)
+    comps = [[keys[int(i)] for i in rng.integers(0, len(keys), int(rng.integers(0, 40)))] + [int(rng.integers(0, 1 << 62))]
+             for _ in range(30)] + [[]]
+    rec = orc.kmers_bin(counts, 1)
+    sel = orc.kmers_bin({k: c for k, c in counts.items() if k % 2}, 0)
+    for thr, s in ((0, None), (4, None), (0, sel), (1, b"")):
+        acc = orc.presence_for_kmers([k for c in comps for k in c], orc.load_kmers_bin(rec))
+        wv, wb, wf, wc = orc.features([(0, c) for c in comps], acc, thr, None if s is None else orc.load_kmers([s], 0))
+        cv, cf, cc = _oracle_c.features_kmers(comps, rec, s, thr)
+        assert list(cv) == wv and list(cf) == wf and list(cc) == wc
+    assert orc.breadth_text([0.5, float("nan")]) == "0.5\nNaN\n" and orc.vec_text([3, -1]) == "3\n-1\n"
+    # Java's addAndBound(long,long) with a negative increment saturates (NumUtils.java:27-32 quirk)
+    assert orc._java_add_and_bound64(5, -1) == (1 << 63) - 1 and orc._java_add_and_bound64(5, 7) == 12

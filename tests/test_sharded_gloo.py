@@ -1,0 +1,34 @@
+"""N>1 host logic on CPU: world_size 2, gloo backend (the GPU kernels are covered by
+tests/test_gpu_parity.py::test_logical_shards_equal_unsharded and by bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+
+from oracle import oracle as orc
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_two_rank_exchange_and_merge(built, tmp_path):
+    import torch.multiprocessing as mp
+    from tests import _gloo_worker
+    import metafast_b200 as m
+    from metafast_b200 import sharded
+    world = 2
+    mp.spawn(_gloo_worker.run, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [open(os.path.join(tmp_path, "shard%d.bin" % r), "rb").read() for r in range(world)]
+    merged = sharded.merge_sorted_records(parts)
+    cfg = m.synth_cfg(total_genome_bp=60000, n_genomes=3, n_read_ppm=0, read_len=100)
+    reads = [bytes(r).decode() for r in m.synth_reads_host(cfg, 0, 1500)]
+    counts = orc.count_reads(reads, 21)
+    assert merged == orc.kmers_bin(counts, 1, 21)                # identical to the unsharded result
+    assert all(len(p) > 0 for p in parts)
+    hist = np.load(os.path.join(tmp_path, "hist.npy"))
+    assert {int(c): int(hist[c]) for c in np.nonzero(hist)[0]} == orc.histogram(counts)
