@@ -82,8 +82,7 @@ mark_read_ends_kernel(const uint64_t *__restrict__ offsets, uint32_t n_reads, ui
 // count += 1 for `key` (Long2ShortHashMap.addAndBound with inc = 1).  Thread-per-key linear
 // probing; one 128-bit load brings key and count of a slot (same sector).  Returns true when
 // this call claimed a new slot.
-__device__ __forceinline__ bool table_upsert1(Slot *__restrict__ tab, uint64_t cap, uint64_t key) {
-    uint64_t i = home_slot(key, cap);
+__device__ __forceinline__ bool table_upsert1_at(Slot *__restrict__ tab, uint64_t cap, uint64_t i, uint64_t key) {
     for (;;) {
         const ulonglong2 s = ld_cg_u64x2(&tab[i]);
         if (s.x == key) {
@@ -99,10 +98,12 @@ __device__ __forceinline__ bool table_upsert1(Slot *__restrict__ tab, uint64_t c
         if (++i == cap) i = 0;
     }
 }
+__device__ __forceinline__ bool table_upsert1(Slot *__restrict__ tab, uint64_t cap, uint64_t key) {
+    return table_upsert1_at(tab, cap, home_slot(key, cap), key);
+}
 
 // count = sat_add(count, inc) for arbitrary inc (rehash, pre-aggregated (key,count) pairs).
-__device__ __forceinline__ bool table_upsert_n(Slot *__restrict__ tab, uint64_t cap, uint64_t key, uint32_t inc) {
-    uint64_t i = home_slot(key, cap);
+__device__ __forceinline__ bool table_upsert_n_at(Slot *__restrict__ tab, uint64_t cap, uint64_t i, uint64_t key, uint32_t inc) {
     bool claimed = false;
     for (;;) {
         unsigned long long cur = ld_cg_u64x2(&tab[i]).x;
@@ -124,6 +125,48 @@ __device__ __forceinline__ bool table_upsert_n(Slot *__restrict__ tab, uint64_t 
         if (++i == cap) i = 0;
     }
 }
+__device__ __forceinline__ bool table_upsert_n(Slot *__restrict__ tab, uint64_t cap, uint64_t key, uint32_t inc) {
+    return table_upsert_n_at(tab, cap, home_slot(key, cap), key, inc);
+}
+
+// ------------------------------------------------------------------------------------------
+// Minimizer placement (region-blocked variant).  The table is n_regions x 2^region_shift slots;
+// a k-mer lives in the region chosen by the smallest hash among its canonical m-mers
+// (m = min(k, 12)) and, inside the region, at mix64(key) mod 2^region_shift (linear probing may
+// run on into the next region).  Both strands of a k-mer have the same canonical m-mers, so the
+// region is a function of the canonical key alone; consecutive k-mers of a read mostly share
+// their minimizer, which is what lets the extraction kernel stage whole runs ("super-k-mers")
+// per region instead of single keys.
+// ------------------------------------------------------------------------------------------
+constexpr int MINI_M = 12;
+__host__ __device__ __forceinline__ int minimizer_len(int k) { return k < MINI_M ? k : MINI_M; }
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {       // MurmurHash3 fmix32
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t region_of_minhash(uint32_t mh, uint32_t n_regions) {
+    return (uint32_t)(((uint64_t)hash32(mh ^ 0x7f4a7c15u) * n_regions) >> 32);
+}
+__host__ __device__ __forceinline__ uint32_t owner_of_minhash(uint32_t mh, uint32_t n_shards) {
+    return (uint32_t)(((uint64_t)hash32(mh ^ 0x1b873593u) * n_shards) >> 32);
+}
+// minimizer hash of a canonical key (slow path: rehash, keys that arrive without their read)
+__host__ __device__ __forceinline__ uint32_t minhash_of_key(uint64_t key, int k) {
+    const int m = minimizer_len(k);
+    const uint32_t mask = m == 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    uint32_t best = 0xFFFFFFFFu;
+    uint32_t fw = 0, rc = 0;
+    for (int i = 0; i < k; i++) {                       // bases from the most significant pair down
+        const uint32_t c = (uint32_t)(key >> (2 * (k - 1 - i))) & 3u;
+        fw = ((fw << 2) | c) & mask;
+        rc = (rc >> 2) | ((3u - c) << (2 * m - 2));
+        if (i >= m - 1) { const uint32_t h = hash32(fw < rc ? fw : rc); best = h < best ? h : best; }
+    }
+    return best;
+}
+__host__ __device__ __forceinline__ uint64_t mini_home(uint64_t key, uint32_t region, int region_shift) {
+    return ((uint64_t)region << region_shift) | (mix64(key) & ((1ull << region_shift) - 1ull));
+}
 
 __global__ void __launch_bounds__(256)
 table_clear_kernel(Slot *__restrict__ tab, uint64_t cap) {
@@ -133,12 +176,25 @@ table_clear_kernel(Slot *__restrict__ tab, uint64_t cap) {
         reinterpret_cast<uint4 *>(tab)[i] = e;
 }
 
+// table geometry + placement rule, passed by value to kernels
+struct TableGeom {
+    uint64_t cap;
+    uint32_t n_regions;
+    int region_shift;
+    int k;
+    int minimizer;          // 1: minimizer placement, 0: plain hash placement
+};
+__device__ __forceinline__ uint64_t geom_home(const TableGeom &g, uint64_t key) {
+    if (!g.minimizer) return home_slot(key, g.cap);
+    return mini_home(key, region_of_minhash(minhash_of_key(key, g.k), g.n_regions), g.region_shift);
+}
+
 __global__ void __launch_bounds__(256)
-rehash_kernel(const Slot *__restrict__ old_tab, uint64_t old_cap, Slot *__restrict__ new_tab, uint64_t new_cap) {
+rehash_kernel(const Slot *__restrict__ old_tab, uint64_t old_cap, Slot *__restrict__ new_tab, TableGeom g) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 s = ld_nc_u128(&old_tab[i]);
         const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
-        if (key != EMPTY_KEY) table_upsert_n(new_tab, new_cap, key, s.z < MAX_COUNT ? s.z : MAX_COUNT);
+        if (key != EMPTY_KEY) table_upsert_n_at(new_tab, g.cap, geom_home(g, key), key, s.z < MAX_COUNT ? s.z : MAX_COUNT);
     }
 }
 
@@ -663,24 +719,208 @@ drain_regions_kernel(RegionStage rs, uint32_t blocks_per_region, Slot *__restric
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
 
-// receive side of the shard exchange / generic "count these keys"
-__global__ void __launch_bounds__(256)
-count_keys_kernel(const unsigned long long *__restrict__ keys, uint64_t n, Slot *__restrict__ tab, uint64_t cap,
-                  Counters *__restrict__ ctr) {
+// ------------------------------------------------------------------------------------------
+// Super-k-mer staging (default flavour of the region-blocked variant).
+// Phase A: per thread, the 16 k-mers starting in its word are cut into runs of consecutive valid
+// k-mers whose minimizers fall in the same table region; each run becomes ONE 16-byte record
+//   x,y,z = the run's bases, 2 bits each, first base in bit 31 of x (len + k - 1 <= 46 bases);
+//           the low 4 bits of z hold len - 1 (len = 1..16 k-mers)
+//   w     = the minimizer hash (region / owner shard derive from it)
+// appended to the region's segment (one returning atomic on the region cursor per RECORD, i.e. per
+// ~6 k-mers, instead of per key).  Phase B expands the records again next to the table region.
+// Staging traffic drops from 8 B to ~2.7 B per k-mer instance and the scatter work by the run length.
+// ------------------------------------------------------------------------------------------
+struct SkmStage {
+    uint4 *recs;                  // region r owns recs[r*seg_cap, (r+1)*seg_cap)
+    unsigned int *cursor;
+    uint64_t seg_cap;             // records per region, < 2^31
+    uint32_t n_regions;
+    int region_shift;
+};
+
+__device__ __forceinline__ uint32_t kmers_of_word(uint32_t w0, uint32_t w1, uint32_t w2, uint64_t flag_bits,
+                                                  long long limit, int k, uint64_t (&keys)[16]);
+
+// a record that found its region segment full: count its k-mers straight into the table
+__device__ __noinline__ uint32_t skm_count_direct(uint4 rec, uint32_t region, int region_shift, int k,
+                                                  Slot *__restrict__ tab, uint64_t cap) {
+    uint64_t keys[16];
+    const uint32_t len = (rec.z & 15u) + 1u;
+    kmers_of_word(rec.x, rec.y, rec.z & ~15u, 0ull, 63, k, keys);
     uint32_t claimed = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        claimed += table_upsert1(tab, cap, keys[i]) ? 1u : 0u;
+#pragma unroll
+    for (uint32_t t = 0; t < 16; t++)
+        if (t < len) claimed += table_upsert1_at(tab, cap, mini_home(keys[t], region, region_shift), keys[t]) ? 1u : 0u;
+    return claimed;
+}
+
+// minimizer hash of each of the 16 k-mers that start in word 0 of the 48-base window
+__device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32_t w2, int k, uint32_t (&mh)[16]) {
+    const int m = minimizer_len(k);
+    const int w = k - m + 1;                              // m-mers per k-mer, <= 20
+    const int rs = 32 - 2 * m;
+    const int top = 2 * m - 2;
+    uint32_t h[36];                                       // m-mer hashes at base offsets 0..35
+    uint32_t rc = 0;
+#pragma unroll
+    for (int q = 0; q < 36; q++) {
+        const uint32_t lo_w = q < 16 ? w0 : (q < 32 ? w1 : w2);
+        const uint32_t hi_w = q < 16 ? w1 : (q < 32 ? w2 : 0u);
+        const int sh = 2 * (q & 15);
+        const uint32_t v = sh ? __funnelshift_l(hi_w, lo_w, sh) : lo_w;      // 16 bases starting at offset q
+        const uint32_t fw = v >> rs;
+        if (q == 0) {
+            uint32_t x = __brev(fw);
+            x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+            rc = (~x) >> rs;
+        } else {
+            rc = (rc >> 2) | (((~fw) & 3u) << top);
+        }
+        h[q] = hash32(fw < rc ? fw : rc);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+        for (int q = 0; q < 20; q++) if (q < w) best = min(best, h[j + q]);
+        mh[j] = best;
+    }
+}
+
+__global__ void __launch_bounds__(EX_THREADS)
+extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
+                   int k, SkmStage st, Slot *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr) {
+    __shared__ uint32_t s_words[EX_THREADS + 2];
+    __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t n_words = (n_bases + 15) >> 4;
+    const uint64_t n_tiles = (n_words + EX_THREADS - 1) / EX_THREADS;
+    const uint64_t n_flag_words = (n_bases + 31) >> 5;
+    uint32_t claimed = 0, bad = 0;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t w_base = tile * EX_THREADS;
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            if (rep == 1 && tid >= 2) break;
+            const uint32_t slot = rep ? EX_THREADS + tid : tid;
+            const uint64_t w = w_base + slot;
+            uint32_t word = 0;
+            const uint64_t b0 = w << 4;
+            if (b0 + 16 <= n_bases) {
+                const uint4 v = ld_nc_u128(bases + b0);
+                word = pack16(v);
+                bad |= bad4(v.x) | bad4(v.y) | bad4(v.z) | bad4(v.w);
+            } else if (b0 < n_bases) {
+                for (uint32_t j = 0; j < 16 && b0 + j < n_bases; j++) {
+                    const uint32_t c = bases[b0 + j];
+                    bad |= bad4(c | 0x41414100u);
+                    word |= pack4(c) >> 6 << (30 - 2 * j);
+                }
+            }
+            s_words[slot] = word;
+        }
+        if (tid < EX_THREADS / 2 + 2) {
+            const uint64_t fw = (w_base >> 1) + tid;
+            s_flags[tid] = fw < n_flag_words ? flags[fw] : 0u;
+        }
+        __syncthreads();
+        const uint64_t w = w_base + tid;
+        if ((w << 4) < n_bases) {
+            const uint32_t w0 = s_words[tid], w1 = s_words[tid + 1], w2 = s_words[tid + 2];
+            const uint32_t f0 = s_flags[tid >> 1], f1 = s_flags[(tid >> 1) + 1], f2 = s_flags[(tid >> 1) + 2];
+            const uint64_t fbits = (tid & 1) ? (((uint64_t)f0 >> 16) | ((uint64_t)f1 << 16) | ((uint64_t)f2 << 48))
+                                             : ((uint64_t)f0 | ((uint64_t)f1 << 32));
+            // validity of the 16 start positions (same rule as kmers_of_word)
+            const uint64_t span = (k > 1) ? ((1ULL << (k - 1)) - 1ULL) : 1ULL;
+            const long long limit = (long long)n_bases - k - (long long)(w << 4);
+            uint32_t valid = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) valid |= ((((fbits >> j) & span) == 0 && (long long)j <= limit) ? 1u : 0u) << j;
+            if (valid) {
+                uint32_t mh[16];
+                minhash_of_word(w0, w1, w2, k, mh);
+                // cut into runs of consecutive valid k-mers with the same region (fully unrolled: all
+                // register arrays keep compile-time indices)
+                uint32_t run_start = 0, run_region = 0, run_mh = 0;
+                bool in_run = false;
+                auto emit = [&](uint32_t j0, uint32_t len) {
+                    const int sh = 2 * (int)j0;                     // normalise: first base of the run -> base 0
+                    uint4 rec;
+                    rec.x = sh ? __funnelshift_l(w1, w0, sh) : w0;
+                    rec.y = sh ? __funnelshift_l(w2, w1, sh) : w1;
+                    rec.z = ((sh ? (w2 << sh) : w2) & ~15u) | (len - 1);
+                    rec.w = run_mh;
+                    const uint32_t pos = atomicAdd(&st.cursor[run_region], 1u);
+                    if (pos < st.seg_cap) {
+                        st.recs[(uint64_t)run_region * st.seg_cap + pos] = rec;
+                    } else {                                        // segment full: count the run directly (slow, exact)
+                        claimed += skm_count_direct(rec, run_region, st.region_shift, k, tab, cap);
+                    }
+                };
+#pragma unroll
+                for (int j = 0; j <= 16; j++) {
+                    const bool v = j < 16 && ((valid >> j) & 1);
+                    const uint32_t reg = v ? region_of_minhash(mh[j < 16 ? j : 15], st.n_regions) : 0xFFFFFFFFu;
+                    if (in_run && (!v || reg != run_region)) { emit(run_start, (uint32_t)j - run_start); in_run = false; }
+                    if (v && !in_run) { in_run = true; run_start = (uint32_t)j; run_region = reg; run_mh = mh[j < 16 ? j : 15]; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+    if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
+}
+
+// Phase B for super-k-mer records: blocks_per_region consecutive CTAs own one region (CTAs start in
+// index order, so only a few regions are live in L2 at a time); a thread re-expands one record into
+// its canonical k-mers (funnel shift + rolled reverse complement) and upserts them into the region.
+__global__ void __launch_bounds__(256)
+drain_skm_kernel(SkmStage st, uint32_t blocks_per_region, int k, Slot *__restrict__ tab, uint64_t cap,
+                 Counters *__restrict__ ctr) {
+    const uint32_t region = blockIdx.x / blocks_per_region;
+    const uint32_t sub = blockIdx.x % blocks_per_region;
+    uint64_t n = st.cursor[region];
+    if (n > st.seg_cap) n = st.seg_cap;
+    const uint4 *__restrict__ recs = st.recs + (uint64_t)region * st.seg_cap;
+    const uint64_t region_base = (uint64_t)region << st.region_shift;
+    const uint64_t slot_mask = (1ull << st.region_shift) - 1ull;
+    const int rs = 64 - 2 * k;
+    const int top = 2 * k - 2;
+    uint32_t claimed = 0;
+    for (uint64_t i = (uint64_t)sub * 256 + threadIdx.x; i < n; i += (uint64_t)blocks_per_region * 256) {
+        const uint4 r = ld_nc_u128(&recs[i]);
+        const uint32_t len = (r.z & 15u) + 1u;
+        const uint32_t w0 = r.x, w1 = r.y, w2 = r.z & ~15u;
+        uint64_t rc = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if ((uint32_t)j < len) {
+                const uint32_t hi = j ? __funnelshift_l(w1, w0, 2 * j) : w0;
+                const uint32_t lo = j ? __funnelshift_l(w2, w1, 2 * j) : w1;
+                const uint64_t fw = (((uint64_t)hi << 32) | lo) >> rs;
+                if (j == 0) rc = revcomp64(fw, k);
+                else rc = (rc >> 2) | ((uint64_t)((~(uint32_t)fw) & 3u) << top);
+                const uint64_t key = fw < rc ? fw : rc;
+                claimed += table_upsert1_at(tab, cap, region_base | (mix64(key) & slot_mask), key) ? 1u : 0u;
+            }
+        }
+    }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
 
-// (key,count) pairs -> table (used by tests of table_upsert_n and by pre-aggregated inputs)
+// receive side of the shard exchange / generic "count these keys" (direct random upserts)
 __global__ void __launch_bounds__(256)
-count_pairs_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ counts, uint64_t n,
-                   Slot *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr) {
+count_keys_kernel(const unsigned long long *__restrict__ keys, uint64_t n, Slot *__restrict__ tab, TableGeom g,
+                  Counters *__restrict__ ctr) {
     uint32_t claimed = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        claimed += table_upsert_n(tab, cap, keys[i], counts[i]) ? 1u : 0u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[i];
+        claimed += table_upsert1_at(tab, g.cap, geom_home(g, key), key) ? 1u : 0u;
+    }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }

@@ -58,6 +58,7 @@ struct mfkc_ctx {
     uint64_t rb_cap_max = 0;           // adaptive growth limit
     uint64_t staged_ub = 0;            // upper bound of keys staged since the last drain
     uint32_t n_regions = 1; int region_shift = 19;
+    int place = 0;                     // 1: minimizer placement + super-k-mer staging (default for MFKC_VARIANT_HASH)
     cudaEvent_t ev_drain = nullptr; bool drain_pending = false; uint64_t kmers_at_drain = 0;
 
     // sort variant
@@ -272,6 +273,10 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     CR_TRY(cudaMemGetInfo(&free_b, &total_b));
     ctx->max_table_bytes = cfg->max_table_bytes ? cfg->max_table_bytes : (uint64_t)(free_b * 0.8);
 
+    if (cfg->variant == MFKC_VARIANT_HASH) {
+        const char *sm = getenv("MFKC_STAGE");            // 0 = stage single keys (hash placement), default = super-k-mers
+        ctx->place = (sm && atoi(sm) == 0) ? 0 : 1;
+    }
     if (cfg->variant != MFKC_VARIANT_SORT) {
         uint64_t slots = cfg->table_slots;
         if (!slots && cfg->expected_distinct) slots = cfg->expected_distinct * 2;      // load 0.5
@@ -409,7 +414,8 @@ static int grow_table(mfkc_ctx *ctx, uint64_t need_slots) {
     TRY(table_alloc(ctx, new_cap, &nt));
     {
         ProfScope ps(ctx, P_REHASH, ctx->compute);
-        rehash_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap, nt, new_cap);
+        TableGeom ng; ng.cap = new_cap; ng.n_regions = nr; ng.region_shift = sh; ng.k = ctx->cfg.k; ng.minimizer = ctx->place;
+        rehash_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap, nt, ng);
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(ctx->compute));
@@ -462,15 +468,43 @@ static RegionStage region_stage(const mfkc_ctx *ctx) {
     return rs;
 }
 
+static TableGeom table_geom(const mfkc_ctx *ctx) {
+    TableGeom g;
+    g.cap = ctx->cap; g.n_regions = ctx->n_regions; g.region_shift = ctx->region_shift; g.k = ctx->cfg.k; g.minimizer = ctx->place;
+    return g;
+}
+static SkmStage skm_stage(const mfkc_ctx *ctx) {
+    SkmStage st;
+    st.recs = reinterpret_cast<uint4 *>(ctx->rb_keys); st.cursor = ctx->rb_cursor;
+    st.n_regions = ctx->n_regions; st.region_shift = ctx->region_shift;
+    uint64_t seg = (ctx->rb_cap / 2) / ctx->n_regions;
+    if (seg > 0x7fffffffull) seg = 0x7fffffffull;
+    st.seg_cap = seg;
+    return st;
+}
+// staging demand of `kmers` k-mer instances in 8-byte units.  Super-k-mer records are 16 bytes and
+// hold (k - m + 2) / 2 k-mers on average for random sequence, capped at 16 by the thread tile; the
+// estimate is deliberately high, and a full segment only costs speed (direct upserts), never results.
+static uint64_t stage_units(const mfkc_ctx *ctx, uint64_t kmers) {
+    if (!ctx->place) return kmers;
+    const int w = ctx->cfg.k - minimizer_len(ctx->cfg.k) + 1;
+    const int div = std::max(1, std::min(4, w / 4));
+    return 2 * (kmers / div + 1);
+}
+
 // phase B: upsert every staged key, region by region (asynchronous on the compute stream)
 static int drain_regions(mfkc_ctx *ctx) {
     if (ctx->cfg.variant != MFKC_VARIANT_HASH || ctx->staged_ub == 0 || !ctx->rb_keys) return MFKC_OK;
-    const RegionStage rs = region_stage(ctx);
-    const uint64_t per_region = ctx->staged_ub / ctx->n_regions + 1;
-    uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 2048));
+    const uint64_t per_region = ctx->staged_ub / ctx->n_regions + 1;       // 8-byte units
     {
         ProfScope ps(ctx, P_DRAIN, ctx->compute);
-        drain_regions_kernel<<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(rs, bpr, ctx->tab, ctx->cap, ctx->d_ctr);
+        if (ctx->place) {
+            const uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 2 / 512));
+            drain_skm_kernel<<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(skm_stage(ctx), bpr, ctx->cfg.k, ctx->tab, ctx->cap, ctx->d_ctr);
+        } else {
+            const uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 2048));
+            drain_regions_kernel<<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(region_stage(ctx), bpr, ctx->tab, ctx->cap, ctx->d_ctr);
+        }
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS * sizeof(unsigned int), ctx->compute));
@@ -485,12 +519,13 @@ static int drain_regions(mfkc_ctx *ctx) {
 }
 
 // make room for `add` more staged keys (drains, and grows the adaptive staging buffer)
-static int reserve_staging(mfkc_ctx *ctx, uint64_t add) {
+static int reserve_staging(mfkc_ctx *ctx, uint64_t add_kmers) {
+    const uint64_t add = stage_units(ctx, add_kmers);
     const uint64_t hard = 4000000000ull;          // cursors are 32-bit
     if (!ctx->rb_keys) {
         uint64_t want = ctx->cfg.staging_bytes ? ctx->cfg.staging_bytes / 8 : std::max<uint64_t>(4 * add, 1ull << 22);
         if (!ctx->cfg.staging_bytes && ctx->cfg.expected_kmers)
-            want = std::max<uint64_t>(want, ctx->cfg.expected_kmers + ctx->cfg.expected_kmers / 50 + (uint64_t)MAX_REGIONS * 64);
+            want = std::max<uint64_t>(want, stage_units(ctx, ctx->cfg.expected_kmers + ctx->cfg.expected_kmers / 50) + (uint64_t)MAX_REGIONS * 64);
         if (!ctx->cfg.staging_bytes && want > ctx->rb_cap_max) want = std::max<uint64_t>(ctx->rb_cap_max, add);
         if (!ctx->cfg.staging_bytes && want > ctx->rb_cap_max) want = std::max<uint64_t>(ctx->rb_cap_max, add);
         if (want < add) want = add;
@@ -567,14 +602,17 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
     const uint64_t kmers_ub = n_bases >= (uint64_t)k ? n_bases - k + 1 : 0;
     if (ctx->cfg.variant == MFKC_VARIANT_SORT) TRY(sort_variant_reserve(ctx, kmers_ub));
     else TRY(reserve_slots(ctx, kmers_ub));
-    if (ctx->cfg.variant == MFKC_VARIANT_HASH) { TRY(reserve_staging(ctx, kmers_ub)); ctx->staged_ub += kmers_ub; }
+    if (ctx->cfg.variant == MFKC_VARIANT_HASH) { TRY(reserve_staging(ctx, kmers_ub)); ctx->staged_ub += stage_units(ctx, kmers_ub); }
     ctx->kmers_ub_total += kmers_ub;
     TRY(launch_mark(ctx, s, d_offsets, n_reads, n_bases, ctx->cfg.min_seq_len, 1, ctx->d_ctr));
     if (n_bases >= (uint64_t)k) {
         if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
             ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
-            static const int stage_mode = getenv("MFKC_STAGE") ? atoi(getenv("MFKC_STAGE")) : 0;
-            if (stage_mode == 0) {            // shared-memory histogram flavour
+            static const int stage_mode = getenv("MFKC_STAGE") ? atoi(getenv("MFKC_STAGE")) : 2;
+            if (ctx->place) {                 // super-k-mer records, minimizer placement
+                extract_skm_kernel<<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                    d_bases, n_bases, s.d_flags, k, skm_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr);
+            } else if (stage_mode == 0) {     // single keys, shared-memory histogram flavour
                 const uint64_t tiles = ((n_bases + 15) / 16 + PT_THREADS - 1) / PT_THREADS;
                 const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 2);
                 extract_partition_kernel<<<grid, PT_THREADS, 0, ctx->compute>>>(
@@ -1052,11 +1090,12 @@ extern "C" int mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uin
     if (n == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(reserve_slots(ctx, n));
-    if (ctx->cfg.variant == MFKC_VARIANT_HASH) { TRY(reserve_staging(ctx, n)); ctx->staged_ub += n; }
+    const bool stage_keys = ctx->cfg.variant == MFKC_VARIANT_HASH && !ctx->place;
+    if (stage_keys) { TRY(reserve_staging(ctx, n)); ctx->staged_ub += n; }
     ctx->kmers_ub_total += n;
     Staging &s = ctx->st[ctx->next_buf];
     ctx->next_buf ^= 1;
-    if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
+    if (stage_keys) {
         ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
         const uint64_t tiles = (n + PT_THREADS * 16 - 1) / (PT_THREADS * 16);
         const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 2);
@@ -1065,7 +1104,7 @@ extern "C" int mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uin
     } else {
         ProfScope ps(ctx, P_COUNT_KEYS, ctx->compute);
         count_keys_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->compute>>>(
-            reinterpret_cast<const unsigned long long *>(d_keys), n, ctx->tab, ctx->cap, ctx->d_ctr);
+            reinterpret_cast<const unsigned long long *>(d_keys), n, ctx->tab, table_geom(ctx), ctx->d_ctr);
     }
     CU_TRY(cudaGetLastError());
     if (ctx->cfg.variant == MFKC_VARIANT_HASH_DIRECT)
@@ -1139,7 +1178,8 @@ extern "C" int mfkc_fc_set_selected(mfkc_ctx *ctx, const uint8_t *be_records, ui
         Slot *nt = nullptr;
         TRY(table_alloc(ctx, need, &nt));
         if (ctx->fc_sel) {
-            rehash_kernel<<<grid_for(ctx, ctx->fc_sel_cap, 256, 8), 256, 0, st>>>(ctx->fc_sel, ctx->fc_sel_cap, nt, need);
+            TableGeom pg; pg.cap = need; pg.n_regions = 1; pg.region_shift = 0; pg.k = ctx->cfg.k; pg.minimizer = 0;
+            rehash_kernel<<<grid_for(ctx, ctx->fc_sel_cap, 256, 8), 256, 0, st>>>(ctx->fc_sel, ctx->fc_sel_cap, nt, pg);
             CU_TRY(cudaStreamSynchronize(st));
             cudaFree(ctx->fc_sel);
         }
