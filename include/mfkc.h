@@ -139,6 +139,17 @@ int  mfkc_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, const uint64_t
 int  mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uint64_t n);
 /* owner shard of a key (host helper, identical to the device function). */
 uint32_t mfkc_owner_shard(uint64_t key, uint32_t n_shards);
+/* Super-k-mer flavour of the exchange (what bench.py uses for N > 1): the extraction kernel cuts every
+ * read into runs of consecutive k-mers that share the owner of their minimizer and ships each run as ONE
+ * 16-byte record (up to 16 k-mers: ~2.7 B per k-mer over NVLink instead of 8 B).
+ * d_recs_out = n_shards segments of seg_cap records; rec_counts / kmer_counts (host, n_shards entries) =
+ * records / k-mer instances per destination.  Returns 1 when a segment overflowed (retry with fewer reads). */
+int  mfkc_skm_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets,
+                               uint32_t n_reads, uint64_t n_bases, void *d_recs_out, uint64_t seg_cap,
+                               uint64_t *rec_counts, uint64_t *kmer_counts);
+/* Receive side: file n_recs records (device pointer; n_kmers k-mer instances in total) under their table
+ * regions; they are counted at the next drain (mfkc_flush at the latest). */
+int  mfkc_skm_count_device(mfkc_ctx *ctx, const void *d_recs, uint64_t n_recs, uint64_t n_kmers);
 
 /* ---- features-calculator: replaces the BigLong2LongHashMap set-up
  * (src/tools/FeaturesCalculatorMain.java:97-103), IOUtils.calculatePresenceForKmers /

@@ -213,6 +213,20 @@ class KmerCounter(_Ctx):
     def count_keys_device(self, d_keys: int, n: int):
         self._ck(self.lib.mfkc_count_keys_device(self.h, C.c_void_p(d_keys), n))
 
+    def skm_extract_bucketed(self, d_bases: int, d_offsets: int, n_reads: int, n_bases: int, d_recs_out: int,
+                             seg_cap: int, n_shards: int):
+        """-> (overflowed, records per shard, k-mer instances per shard)"""
+        rc_ = (C.c_uint64 * max(n_shards, 1))()
+        kc_ = (C.c_uint64 * max(n_shards, 1))()
+        rc = self.lib.mfkc_skm_extract_bucketed(self.h, C.c_void_p(d_bases), C.c_void_p(d_offsets), n_reads, n_bases,
+                                                C.c_void_p(d_recs_out), seg_cap, rc_, kc_)
+        if rc not in (0, 1):
+            self._ck(rc)
+        return rc == 1, list(rc_), list(kc_)
+
+    def skm_count_device(self, d_recs: int, n_recs: int, n_kmers: int):
+        self._ck(self.lib.mfkc_skm_count_device(self.h, C.c_void_p(d_recs), n_recs, n_kmers))
+
 
 class FeaturesCalculator(_Ctx):
     """features-calculator on the device (K6/K7/K8)."""

@@ -290,62 +290,73 @@ __device__ __forceinline__ uint32_t kmers_of_word(uint32_t w0, uint32_t w1, uint
     return valid;
 }
 
+// Shared front end of every extraction kernel: K1 (ASCII -> 2-bit words in shared memory, 2 halo
+// words, boundary flags) and the 48-base window + validity inputs of the calling thread.
+struct TileWord {
+    uint32_t w0, w1, w2;      // own word + two successors (base 0 in bit 31 of w0)
+    uint64_t fbits;           // 64 boundary flags starting at the thread's first base
+    long long limit;          // last start offset j with p + k <= n_bases
+    bool active;              // the thread's word lies inside the batch
+};
+template <int NT>
+__device__ __forceinline__ TileWord load_tile_word(const uint8_t *__restrict__ bases, uint64_t n_bases,
+                                                   const uint32_t *__restrict__ flags, uint64_t tile, int k,
+                                                   uint32_t *s_words /* NT+2 */, uint32_t *s_flags /* NT/2+2 */,
+                                                   uint32_t &bad) {
+    const uint32_t tid = threadIdx.x;
+    const uint64_t n_flag_words = (n_bases + 31) >> 5;
+    const uint64_t w_base = tile * NT;
+#pragma unroll
+    for (int rep = 0; rep < 2; rep++) {
+        if (rep == 1 && tid >= 2) break;
+        const uint32_t slot = rep ? NT + tid : tid;
+        const uint64_t w = w_base + slot;
+        uint32_t word = 0;
+        const uint64_t b0 = w << 4;
+        if (b0 + 16 <= n_bases) {
+            const uint4 v = ld_nc_u128(bases + b0);
+            word = pack16(v);
+            bad |= bad4(v.x) | bad4(v.y) | bad4(v.z) | bad4(v.w);
+        } else if (b0 < n_bases) {                      // ragged tail of the batch
+            for (uint32_t j = 0; j < 16 && b0 + j < n_bases; j++) {
+                const uint32_t c = bases[b0 + j];
+                bad |= bad4(c | 0x41414100u);
+                word |= pack4(c) >> 6 << (30 - 2 * j);
+            }
+        }
+        s_words[slot] = word;
+    }
+    // boundary flags for positions [16*w_base, 16*w_base + 16*NT + 64)
+    if (tid < NT / 2 + 2) {
+        const uint64_t fw = (w_base >> 1) + tid;
+        s_flags[tid] = fw < n_flag_words ? flags[fw] : 0u;
+    }
+    __syncthreads();
+    TileWord t;
+    const uint64_t w = w_base + tid;
+    t.active = (w << 4) < n_bases;
+    t.w0 = s_words[tid]; t.w1 = s_words[tid + 1]; t.w2 = s_words[tid + 2];
+    const uint32_t f0 = s_flags[tid >> 1], f1 = s_flags[(tid >> 1) + 1], f2 = s_flags[(tid >> 1) + 2];
+    t.fbits = (tid & 1) ? (((uint64_t)f0 >> 16) | ((uint64_t)f1 << 16) | ((uint64_t)f2 << 48))
+                        : ((uint64_t)f0 | ((uint64_t)f1 << 32));
+    t.limit = (long long)n_bases - k - (long long)(w << 4);
+    return t;
+}
+
 template <class Sink>
 __global__ void __launch_bounds__(EX_THREADS)
 extract_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
                int k, Sink sink, Counters *__restrict__ ctr) {
     __shared__ uint32_t s_words[EX_THREADS + 2];
     __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
-    const uint32_t tid = threadIdx.x;
-    const uint64_t n_words = (n_bases + 15) >> 4;
-    const uint64_t n_tiles = (n_words + EX_THREADS - 1) / EX_THREADS;
-    const uint64_t n_flag_words = (n_bases + 31) >> 5;
-    uint32_t claimed = 0;
-    uint32_t bad = 0;
-
+    const uint64_t n_tiles = (((n_bases + 15) >> 4) + EX_THREADS - 1) / EX_THREADS;
+    uint32_t claimed = 0, bad = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t w_base = tile * EX_THREADS;
-        // ---- K1: pack own word (+ 2 halo words by threads 0,1)
-#pragma unroll
-        for (int rep = 0; rep < 2; rep++) {
-            if (rep == 1 && tid >= 2) break;
-            const uint32_t slot = rep ? EX_THREADS + tid : tid;
-            const uint64_t w = w_base + slot;
-            uint32_t word = 0;
-            const uint64_t b0 = w << 4;
-            if (b0 + 16 <= n_bases) {
-                const uint4 v = ld_nc_u128(bases + b0);
-                word = pack16(v);
-                bad |= bad4(v.x) | bad4(v.y) | bad4(v.z) | bad4(v.w);
-            } else if (b0 < n_bases) {                      // ragged tail of the batch
-                for (uint32_t j = 0; j < 16 && b0 + j < n_bases; j++) {
-                    const uint32_t c = bases[b0 + j];
-                    bad |= bad4(c | 0x41414100u);
-                    word |= pack4(c) >> 6 << (30 - 2 * j);
-                }
-            }
-            s_words[slot] = word;
-        }
-        // boundary flags for positions [16*w_base, 16*w_base + 16*EX_THREADS + 64)
-        if (tid < EX_THREADS / 2 + 2) {
-            const uint64_t fw = (w_base >> 1) + tid;
-            s_flags[tid] = fw < n_flag_words ? flags[fw] : 0u;
-        }
-        __syncthreads();
-
-        // ---- K2: canonical k-mers starting in my word
-        const uint64_t w = w_base + tid;
-        if ((w << 4) < n_bases) {
-            const uint32_t w0 = s_words[tid], w1 = s_words[tid + 1], w2 = s_words[tid + 2];
-            const uint32_t f0 = s_flags[tid >> 1], f1 = s_flags[(tid >> 1) + 1], f2 = s_flags[(tid >> 1) + 2];
-            // 64 flag bits starting at position 16*w
-            const uint64_t fbits = (tid & 1) ? (((uint64_t)f0 >> 16) | ((uint64_t)f1 << 16) | ((uint64_t)f2 << 48))
-                                             : ((uint64_t)f0 | ((uint64_t)f1 << 32));
+        const TileWord t = load_tile_word<EX_THREADS>(bases, n_bases, flags, tile, k, s_words, s_flags, bad);
+        if (t.active) {                                  // K2: canonical k-mers starting in my word
             uint64_t keys[16];
-            const long long limit = (long long)n_bases - k - (long long)(w << 4);
-            const uint32_t valid = kmers_of_word(w0, w1, w2, fbits, limit, k, keys);
-            // ---- K3: sink
-            if (Sink::kPrefetch) {
+            const uint32_t valid = kmers_of_word(t.w0, t.w1, t.w2, t.fbits, t.limit, k, keys);
+            if (Sink::kPrefetch) {                       // K3: sink
 #pragma unroll
                 for (int j = 0; j < 16; j++) if (valid >> j & 1) sink.prefetch(keys[j]);
             }
@@ -377,49 +388,19 @@ extract_bucket_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const
     __shared__ uint32_t s_words[EX_THREADS + 2];
     __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
     const uint32_t tid = threadIdx.x;
-    const uint64_t n_words = (n_bases + 15) >> 4;
-    const uint64_t n_tiles = (n_words + EX_THREADS - 1) / EX_THREADS;
-    const uint64_t n_flag_words = (n_bases + 31) >> 5;
+    const uint64_t n_tiles = (((n_bases + 15) >> 4) + EX_THREADS - 1) / EX_THREADS;
     uint32_t bad = 0;
     unsigned long long overflow = 0;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t w_base = tile * EX_THREADS;
-#pragma unroll
-        for (int rep = 0; rep < 2; rep++) {
-            if (rep == 1 && tid >= 2) break;
-            const uint32_t slot = rep ? EX_THREADS + tid : tid;
-            const uint64_t w = w_base + slot;
-            uint32_t word = 0;
-            const uint64_t b0 = w << 4;
-            if (b0 + 16 <= n_bases) {
-                const uint4 v = ld_nc_u128(bases + b0);
-                word = pack16(v);
-                bad |= bad4(v.x) | bad4(v.y) | bad4(v.z) | bad4(v.w);
-            } else if (b0 < n_bases) {
-                for (uint32_t j = 0; j < 16 && b0 + j < n_bases; j++) {
-                    const uint32_t c = bases[b0 + j];
-                    bad |= bad4(c | 0x41414100u);
-                    word |= pack4(c) >> 6 << (30 - 2 * j);
-                }
-            }
-            s_words[slot] = word;
-        }
-        if (tid < EX_THREADS / 2 + 2) {
-            const uint64_t fw = (w_base >> 1) + tid;
-            s_flags[tid] = fw < n_flag_words ? flags[fw] : 0u;
-        }
-        __syncthreads();
+        const TileWord t = load_tile_word<EX_THREADS>(bases, n_bases, flags, tile, k, s_words, s_flags, bad);
 
-        const uint64_t w = w_base + tid;
         uint64_t keys[16];
         uint32_t valid = 0;
-        if ((w << 4) < n_bases) {
-            const uint32_t w0 = s_words[tid], w1 = s_words[tid + 1], w2 = s_words[tid + 2];
-            const uint32_t f0 = s_flags[tid >> 1], f1 = s_flags[(tid >> 1) + 1], f2 = s_flags[(tid >> 1) + 2];
-            const uint64_t fbits = (tid & 1) ? (((uint64_t)f0 >> 16) | ((uint64_t)f1 << 16) | ((uint64_t)f2 << 48))
-                                             : ((uint64_t)f0 | ((uint64_t)f1 << 32));
-            const long long limit = (long long)n_bases - k - (long long)(w << 4);
+        if (t.active) {
+            const uint32_t w0 = t.w0, w1 = t.w1, w2 = t.w2;
+            const uint64_t fbits = t.fbits;
+            const long long limit = t.limit;
             valid = kmers_of_word(w0, w1, w2, fbits, limit, k, keys);
         }
         // all 32 lanes take part in the warp-level position claims
@@ -519,48 +500,18 @@ extract_partition_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, co
     __shared__ uint32_t s_flags[PT_THREADS / 2 + 2];
     __shared__ uint32_t s_hist[MAX_REGIONS];
     const uint32_t tid = threadIdx.x;
-    const uint64_t n_words = (n_bases + 15) >> 4;
-    const uint64_t n_tiles = (n_words + PT_THREADS - 1) / PT_THREADS;
-    const uint64_t n_flag_words = (n_bases + 31) >> 5;
+    const uint64_t n_tiles = (((n_bases + 15) >> 4) + PT_THREADS - 1) / PT_THREADS;
     uint32_t claimed = 0, bad = 0;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t w_base = tile * PT_THREADS;
         for (uint32_t r = tid; r < rs.n_regions; r += PT_THREADS) s_hist[r] = 0;
-#pragma unroll
-        for (int rep = 0; rep < 2; rep++) {
-            if (rep == 1 && tid >= 2) break;
-            const uint32_t slot = rep ? PT_THREADS + tid : tid;
-            const uint64_t w = w_base + slot;
-            uint32_t word = 0;
-            const uint64_t b0 = w << 4;
-            if (b0 + 16 <= n_bases) {
-                const uint4 v = ld_nc_u128(bases + b0);
-                word = pack16(v);
-                bad |= bad4(v.x) | bad4(v.y) | bad4(v.z) | bad4(v.w);
-            } else if (b0 < n_bases) {
-                for (uint32_t j = 0; j < 16 && b0 + j < n_bases; j++) {
-                    const uint32_t c = bases[b0 + j];
-                    bad |= bad4(c | 0x41414100u);
-                    word |= pack4(c) >> 6 << (30 - 2 * j);
-                }
-            }
-            s_words[slot] = word;
-        }
-        if (tid < PT_THREADS / 2 + 2) {
-            const uint64_t fw = (w_base >> 1) + tid;
-            s_flags[tid] = fw < n_flag_words ? flags[fw] : 0u;
-        }
-        __syncthreads();
-        const uint64_t w = w_base + tid;
+        const TileWord t = load_tile_word<PT_THREADS>(bases, n_bases, flags, tile, k, s_words, s_flags, bad);
         uint64_t keys[16];
         uint32_t valid = 0;
-        if ((w << 4) < n_bases) {
-            const uint32_t w0 = s_words[tid], w1 = s_words[tid + 1], w2 = s_words[tid + 2];
-            const uint32_t f0 = s_flags[tid >> 1], f1 = s_flags[(tid >> 1) + 1], f2 = s_flags[(tid >> 1) + 2];
-            const uint64_t fbits = (tid & 1) ? (((uint64_t)f0 >> 16) | ((uint64_t)f1 << 16) | ((uint64_t)f2 << 48))
-                                             : ((uint64_t)f0 | ((uint64_t)f1 << 32));
-            const long long limit = (long long)n_bases - k - (long long)(w << 4);
+        if (t.active) {
+            const uint32_t w0 = t.w0, w1 = t.w1, w2 = t.w2;
+            const uint64_t fbits = t.fbits;
+            const long long limit = t.limit;
             valid = kmers_of_word(w0, w1, w2, fbits, limit, k, keys);
         }
         claimed += stage_keys_block<PT_THREADS>(keys, valid, rs, tab, cap, s_hist);
@@ -582,46 +533,16 @@ extract_stage_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const 
     __shared__ uint32_t s_words[EX_THREADS + 2];
     __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
     const uint32_t tid = threadIdx.x;
-    const uint64_t n_words = (n_bases + 15) >> 4;
-    const uint64_t n_tiles = (n_words + EX_THREADS - 1) / EX_THREADS;
-    const uint64_t n_flag_words = (n_bases + 31) >> 5;
+    const uint64_t n_tiles = (((n_bases + 15) >> 4) + EX_THREADS - 1) / EX_THREADS;
     uint32_t claimed = 0, bad = 0;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t w_base = tile * EX_THREADS;
-#pragma unroll
-        for (int rep = 0; rep < 2; rep++) {
-            if (rep == 1 && tid >= 2) break;
-            const uint32_t slot = rep ? EX_THREADS + tid : tid;
-            const uint64_t w = w_base + slot;
-            uint32_t word = 0;
-            const uint64_t b0 = w << 4;
-            if (b0 + 16 <= n_bases) {
-                const uint4 v = ld_nc_u128(bases + b0);
-                word = pack16(v);
-                bad |= bad4(v.x) | bad4(v.y) | bad4(v.z) | bad4(v.w);
-            } else if (b0 < n_bases) {
-                for (uint32_t j = 0; j < 16 && b0 + j < n_bases; j++) {
-                    const uint32_t c = bases[b0 + j];
-                    bad |= bad4(c | 0x41414100u);
-                    word |= pack4(c) >> 6 << (30 - 2 * j);
-                }
-            }
-            s_words[slot] = word;
-        }
-        if (tid < EX_THREADS / 2 + 2) {
-            const uint64_t fw = (w_base >> 1) + tid;
-            s_flags[tid] = fw < n_flag_words ? flags[fw] : 0u;
-        }
-        __syncthreads();
-        const uint64_t w = w_base + tid;
-        if ((w << 4) < n_bases) {
-            const uint32_t w0 = s_words[tid], w1 = s_words[tid + 1], w2 = s_words[tid + 2];
-            const uint32_t f0 = s_flags[tid >> 1], f1 = s_flags[(tid >> 1) + 1], f2 = s_flags[(tid >> 1) + 2];
-            const uint64_t fbits = (tid & 1) ? (((uint64_t)f0 >> 16) | ((uint64_t)f1 << 16) | ((uint64_t)f2 << 48))
-                                             : ((uint64_t)f0 | ((uint64_t)f1 << 32));
+        const TileWord t = load_tile_word<EX_THREADS>(bases, n_bases, flags, tile, k, s_words, s_flags, bad);
+        if (t.active) {
+            const uint32_t w0 = t.w0, w1 = t.w1, w2 = t.w2;
+            const uint64_t fbits = t.fbits;
             uint64_t keys[16];
-            const long long limit = (long long)n_bases - k - (long long)(w << 4);
+            const long long limit = t.limit;
             const uint32_t valid = kmers_of_word(w0, w1, w2, fbits, limit, k, keys);
             uint32_t pos[16];
 #pragma unroll
@@ -787,62 +708,41 @@ __device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32
     }
 }
 
+// BY_OWNER = false: bucket = table region of this GPU (single-GPU path, full segments fall back to
+//                   direct upserts);
+// BY_OWNER = true : bucket = owner shard (multi-GPU send buffer; st.n_regions = number of shards,
+//                   kmer_count[b] receives the k-mer instances sent to shard b; a full segment is
+//                   reported through the cursor overshoot and the caller retries with a smaller batch).
+template <bool BY_OWNER>
 __global__ void __launch_bounds__(EX_THREADS)
 extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
-                   int k, SkmStage st, Slot *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr) {
+                   int k, SkmStage st, Slot *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr,
+                   unsigned long long *__restrict__ kmer_count) {
     __shared__ uint32_t s_words[EX_THREADS + 2];
     __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
     const uint32_t tid = threadIdx.x;
-    const uint64_t n_words = (n_bases + 15) >> 4;
-    const uint64_t n_tiles = (n_words + EX_THREADS - 1) / EX_THREADS;
-    const uint64_t n_flag_words = (n_bases + 31) >> 5;
+    const uint64_t n_tiles = (((n_bases + 15) >> 4) + EX_THREADS - 1) / EX_THREADS;
     uint32_t claimed = 0, bad = 0;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t w_base = tile * EX_THREADS;
-#pragma unroll
-        for (int rep = 0; rep < 2; rep++) {
-            if (rep == 1 && tid >= 2) break;
-            const uint32_t slot = rep ? EX_THREADS + tid : tid;
-            const uint64_t w = w_base + slot;
-            uint32_t word = 0;
-            const uint64_t b0 = w << 4;
-            if (b0 + 16 <= n_bases) {
-                const uint4 v = ld_nc_u128(bases + b0);
-                word = pack16(v);
-                bad |= bad4(v.x) | bad4(v.y) | bad4(v.z) | bad4(v.w);
-            } else if (b0 < n_bases) {
-                for (uint32_t j = 0; j < 16 && b0 + j < n_bases; j++) {
-                    const uint32_t c = bases[b0 + j];
-                    bad |= bad4(c | 0x41414100u);
-                    word |= pack4(c) >> 6 << (30 - 2 * j);
-                }
-            }
-            s_words[slot] = word;
-        }
-        if (tid < EX_THREADS / 2 + 2) {
-            const uint64_t fw = (w_base >> 1) + tid;
-            s_flags[tid] = fw < n_flag_words ? flags[fw] : 0u;
-        }
-        __syncthreads();
-        const uint64_t w = w_base + tid;
-        if ((w << 4) < n_bases) {
-            const uint32_t w0 = s_words[tid], w1 = s_words[tid + 1], w2 = s_words[tid + 2];
-            const uint32_t f0 = s_flags[tid >> 1], f1 = s_flags[(tid >> 1) + 1], f2 = s_flags[(tid >> 1) + 2];
-            const uint64_t fbits = (tid & 1) ? (((uint64_t)f0 >> 16) | ((uint64_t)f1 << 16) | ((uint64_t)f2 << 48))
-                                             : ((uint64_t)f0 | ((uint64_t)f1 << 32));
+        const TileWord t = load_tile_word<EX_THREADS>(bases, n_bases, flags, tile, k, s_words, s_flags, bad);
+        if (t.active) {
+            const uint32_t w0 = t.w0, w1 = t.w1, w2 = t.w2;
+            const uint64_t fbits = t.fbits;
             // validity of the 16 start positions (same rule as kmers_of_word)
             const uint64_t span = (k > 1) ? ((1ULL << (k - 1)) - 1ULL) : 1ULL;
-            const long long limit = (long long)n_bases - k - (long long)(w << 4);
+            const long long limit = t.limit;
             uint32_t valid = 0;
 #pragma unroll
             for (int j = 0; j < 16; j++) valid |= ((((fbits >> j) & span) == 0 && (long long)j <= limit) ? 1u : 0u) << j;
             if (valid) {
                 uint32_t mh[16];
                 minhash_of_word(w0, w1, w2, k, mh);
-                // cut into runs of consecutive valid k-mers with the same region (fully unrolled: all
-                // register arrays keep compile-time indices)
-                uint32_t run_start = 0, run_region = 0, run_mh = 0;
+                // Cut into runs of consecutive valid k-mers (fully unrolled: every register array keeps
+                // compile-time indices).  Local staging: a run = same table REGION.  Send buffer
+                // (BY_OWNER): a run = same MINIMIZER HASH, because the receiver derives the region of
+                // the whole record from that one hash, under a table geometry the sender does not know.
+                uint32_t run_start = 0, run_key = 0, run_mh = 0;
                 bool in_run = false;
                 auto emit = [&](uint32_t j0, uint32_t len) {
                     const int sh = 2 * (int)j0;                     // normalise: first base of the run -> base 0
@@ -851,19 +751,22 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                     rec.y = sh ? __funnelshift_l(w2, w1, sh) : w1;
                     rec.z = ((sh ? (w2 << sh) : w2) & ~15u) | (len - 1);
                     rec.w = run_mh;
-                    const uint32_t pos = atomicAdd(&st.cursor[run_region], 1u);
+                    const uint32_t bucket = BY_OWNER ? owner_of_minhash(run_mh, st.n_regions) : run_key;
+                    const uint32_t pos = atomicAdd(&st.cursor[bucket], 1u);
                     if (pos < st.seg_cap) {
-                        st.recs[(uint64_t)run_region * st.seg_cap + pos] = rec;
-                    } else {                                        // segment full: count the run directly (slow, exact)
-                        claimed += skm_count_direct(rec, run_region, st.region_shift, k, tab, cap);
+                        st.recs[(uint64_t)bucket * st.seg_cap + pos] = rec;
+                        if (BY_OWNER) atomicAdd(&kmer_count[bucket], (unsigned long long)len);
+                    } else if (!BY_OWNER) {                         // segment full: count the run directly (slow, exact)
+                        claimed += skm_count_direct(rec, bucket, st.region_shift, k, tab, cap);
                     }
                 };
 #pragma unroll
                 for (int j = 0; j <= 16; j++) {
                     const bool v = j < 16 && ((valid >> j) & 1);
-                    const uint32_t reg = v ? region_of_minhash(mh[j < 16 ? j : 15], st.n_regions) : 0xFFFFFFFFu;
-                    if (in_run && (!v || reg != run_region)) { emit(run_start, (uint32_t)j - run_start); in_run = false; }
-                    if (v && !in_run) { in_run = true; run_start = (uint32_t)j; run_region = reg; run_mh = mh[j < 16 ? j : 15]; }
+                    const uint32_t mhj = mh[j < 16 ? j : 15];
+                    const uint32_t key = !v ? 0xFFFFFFFFu : (BY_OWNER ? mhj : region_of_minhash(mhj, st.n_regions));
+                    if (in_run && (!v || key != run_key)) { emit(run_start, (uint32_t)j - run_start); in_run = false; }
+                    if (v && !in_run) { in_run = true; run_start = (uint32_t)j; run_key = key; run_mh = mhj; }
                 }
             }
         }
@@ -872,6 +775,126 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
     if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
+}
+
+// Send side for up to 8 owner shards with block-level aggregation.  With only G <= 8 destination
+// cursors, one returning atomic per record serialises on G addresses in L2 (measured: 46 ms for
+// 4.8e8 k-mers on 2 shards).  Here a tile counts its records per owner first (packed 16-bit fields,
+// warp scan + shared prefix), reserves ONE range per (tile, owner) and then writes the records:
+// ~90x fewer global atomics, and each owner's records of a tile leave as one contiguous burst.
+__device__ __forceinline__ void pk_add(unsigned long long &lo, unsigned long long &hi, uint32_t o, uint32_t v) {
+    if (o < 4) lo += (unsigned long long)v << (16 * o); else hi += (unsigned long long)v << (16 * (o - 4));
+}
+__device__ __forceinline__ uint32_t pk_get(unsigned long long lo, unsigned long long hi, uint32_t o) {
+    return (uint32_t)((o < 4 ? lo >> (16 * o) : hi >> (16 * (o - 4))) & 0xFFFFu);
+}
+
+__global__ void __launch_bounds__(EX_THREADS)
+extract_skm_owner8_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
+                          int k, SkmStage st, Counters *__restrict__ ctr, unsigned long long *__restrict__ kmer_count) {
+    __shared__ uint32_t s_words[EX_THREADS + 2];
+    __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
+    __shared__ unsigned long long s_wrec[EX_THREADS / 32][2];    // per-warp record totals (packed)
+    __shared__ unsigned long long s_wkm[EX_THREADS / 32][2];     // per-warp k-mer totals (packed)
+    __shared__ uint32_t s_base[8];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t G = st.n_regions;
+    const uint64_t n_tiles = (((n_bases + 15) >> 4) + EX_THREADS - 1) / EX_THREADS;
+    uint32_t bad = 0;
+
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileWord t = load_tile_word<EX_THREADS>(bases, n_bases, flags, tile, k, s_words, s_flags, bad);
+        const uint32_t w0 = t.w0, w1 = t.w1, w2 = t.w2;
+        uint32_t valid = 0;
+        uint32_t mh[16];
+        if (t.active) {
+            const uint64_t span = (k > 1) ? ((1ULL << (k - 1)) - 1ULL) : 1ULL;
+#pragma unroll
+            for (int j = 0; j < 16; j++) valid |= ((((t.fbits >> j) & span) == 0 && (long long)j <= t.limit) ? 1u : 0u) << j;
+        }
+        if (valid) minhash_of_word(w0, w1, w2, k, mh);
+        // runs of consecutive valid k-mers with the same minimizer hash; f(j0, len, minhash)
+        auto for_each_run = [&](auto f) {
+            uint32_t run_start = 0, run_mh = 0;
+            bool in_run = false;
+#pragma unroll
+            for (int j = 0; j <= 16; j++) {
+                const bool v = j < 16 && ((valid >> j) & 1);
+                const uint32_t mhj = mh[j < 16 ? j : 15];
+                if (in_run && (!v || mhj != run_mh)) { f(run_start, (uint32_t)j - run_start, run_mh); in_run = false; }
+                if (v && !in_run) { in_run = true; run_start = (uint32_t)j; run_mh = mhj; }
+            }
+        };
+        // pass 1: records and k-mers per owner
+        unsigned long long rc_lo = 0, rc_hi = 0, km_lo = 0, km_hi = 0;
+        if (valid) for_each_run([&](uint32_t, uint32_t len, uint32_t mhv) {
+            const uint32_t o = owner_of_minhash(mhv, G);
+            pk_add(rc_lo, rc_hi, o, 1u); pk_add(km_lo, km_hi, o, len);
+        });
+        unsigned long long in_lo = rc_lo, in_hi = rc_hi;               // inclusive warp scan of the record counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long a = __shfl_up_sync(0xffffffffu, in_lo, o), b = __shfl_up_sync(0xffffffffu, in_hi, o);
+            if (lane >= (uint32_t)o) { in_lo += a; in_hi += b; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { km_lo += __shfl_xor_sync(0xffffffffu, km_lo, o); km_hi += __shfl_xor_sync(0xffffffffu, km_hi, o); }
+        if (lane == 31) { s_wrec[warp][0] = in_lo; s_wrec[warp][1] = in_hi; }
+        if (lane == 0) { s_wkm[warp][0] = km_lo; s_wkm[warp][1] = km_hi; }
+        __syncthreads();
+        unsigned long long wb_lo = 0, wb_hi = 0, tot_lo = 0, tot_hi = 0, kt_lo = 0, kt_hi = 0;
+#pragma unroll
+        for (int wv = 0; wv < EX_THREADS / 32; wv++) {
+            if (wv < (int)warp) { wb_lo += s_wrec[wv][0]; wb_hi += s_wrec[wv][1]; }
+            tot_lo += s_wrec[wv][0]; tot_hi += s_wrec[wv][1];
+            kt_lo += s_wkm[wv][0]; kt_hi += s_wkm[wv][1];
+        }
+        if (tid < G) {                                                  // one reservation per (tile, owner)
+            const uint32_t n = pk_get(tot_lo, tot_hi, tid);
+            s_base[tid] = n ? atomicAdd(&st.cursor[tid], n) : 0u;
+            const uint32_t km = pk_get(kt_lo, kt_hi, tid);
+            if (km) atomicAdd(&kmer_count[tid], (unsigned long long)km);
+        }
+        __syncthreads();
+        // pass 2: write the records
+        if (valid) {
+            const unsigned long long ex_lo = wb_lo + in_lo - rc_lo, ex_hi = wb_hi + in_hi - rc_hi;   // exclusive prefix of this thread
+            unsigned long long run_lo = 0, run_hi = 0;
+            for_each_run([&](uint32_t j0, uint32_t len, uint32_t mhv) {
+                const uint32_t o = owner_of_minhash(mhv, G);
+                const uint64_t pos = (uint64_t)s_base[o] + pk_get(ex_lo, ex_hi, o) + pk_get(run_lo, run_hi, o);
+                pk_add(run_lo, run_hi, o, 1u);
+                if (pos < st.seg_cap) {
+                    const int sh = 2 * (int)j0;
+                    uint4 rec;
+                    rec.x = sh ? __funnelshift_l(w1, w0, sh) : w0;
+                    rec.y = sh ? __funnelshift_l(w2, w1, sh) : w1;
+                    rec.z = ((sh ? (w2 << sh) : w2) & ~15u) | (len - 1);
+                    rec.w = mhv;
+                    st.recs[(uint64_t)o * st.seg_cap + pos] = rec;
+                }
+            });
+        }
+        __syncthreads();
+    }
+    if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
+}
+
+// Receive side of the shard exchange: records that arrived from other GPUs are filed under the
+// table region of their minimizer (streaming: 16 B in, one cursor atomic, 16 B out).
+__global__ void __launch_bounds__(256)
+skm_restage_kernel(const uint4 *__restrict__ in, uint64_t n, int k, SkmStage st, Slot *__restrict__ tab, uint64_t cap,
+                   Counters *__restrict__ ctr) {
+    uint32_t claimed = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 rec = ld_nc_u128(&in[i]);
+        const uint32_t region = region_of_minhash(rec.w, st.n_regions);
+        const uint32_t pos = atomicAdd(&st.cursor[region], 1u);
+        if (pos < st.seg_cap) st.recs[(uint64_t)region * st.seg_cap + pos] = rec;
+        else claimed += skm_count_direct(rec, region, st.region_shift, k, tab, cap);
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
 
 // Phase B for super-k-mer records: blocks_per_region consecutive CTAs own one region (CTAs start in

@@ -610,8 +610,8 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
             ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
             static const int stage_mode = getenv("MFKC_STAGE") ? atoi(getenv("MFKC_STAGE")) : 2;
             if (ctx->place) {                 // super-k-mer records, minimizer placement
-                extract_skm_kernel<<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
-                    d_bases, n_bases, s.d_flags, k, skm_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr);
+                extract_skm_kernel<false><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                    d_bases, n_bases, s.d_flags, k, skm_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr, nullptr);
             } else if (stage_mode == 0) {     // single keys, shared-memory histogram flavour
                 const uint64_t tiles = ((n_bases + 15) / 16 + PT_THREADS - 1) / PT_THREADS;
                 const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 2);
@@ -1111,6 +1111,83 @@ extern "C" int mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uin
         CU_TRY(cudaMemcpyAsync(s.h_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
     CU_TRY(cudaEventRecord(s.ev_done, ctx->compute));
     s.pending = ctx->cfg.variant == MFKC_VARIANT_HASH_DIRECT; s.kmers_submitted_at_end = ctx->kmers_ub_total;
+    ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
+    return MFKC_OK;
+}
+
+// ---- super-k-mer flavour of the shard exchange (the default for MFKC_VARIANT_HASH) ----------
+// Send side: records bucketed by owner shard.  d_recs_out holds n_shards segments of seg_cap records
+// (16 bytes each); rec_counts[s] / kmer_counts[s] (host) = records / k-mer instances for shard s.
+// Returns 1 (not an error) when a segment overflowed: nothing may be used, retry with fewer reads.
+extern "C" int mfkc_skm_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t n_reads,
+                                         uint64_t n_bases, void *d_recs_out, uint64_t seg_cap, uint64_t *rec_counts,
+                                         uint64_t *kmer_counts) {
+    if (!ctx || !d_bases || !d_offsets || !d_recs_out || !rec_counts || !kmer_counts) return fail(ctx, MFKC_E_BADARG, "null argument");
+    const uint32_t ns = ctx->cfg.n_shards > 1 ? (uint32_t)ctx->cfg.n_shards : 1u;
+    if (seg_cap == 0 || seg_cap > 0x7fffffffull) return fail(ctx, MFKC_E_BADARG, "bad segment capacity");
+    CU_TRY(cudaSetDevice(ctx->device));
+    Staging &s = ctx->st[0];
+    TRY(ensure_staging(ctx, s, n_bases, 0, false));
+    for (uint32_t i = 0; i < ns; i++) { rec_counts[i] = 0; kmer_counts[i] = 0; }
+    if (n_reads == 0) return MFKC_OK;
+    const int k = ctx->cfg.k;
+    // the read statistics are taken once per read, also when the caller has to retry a batch in halves:
+    // statistics are accumulated only by the successful attempt (count_stats below), so snapshot + restore
+    CU_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->compute));
+    TRY(launch_mark(ctx, s, d_offsets, n_reads, n_bases, ctx->cfg.min_seq_len, 1, ctx->d_ctr));
+    if (n_bases < (uint64_t)k) { CU_TRY(cudaStreamSynchronize(ctx->compute)); return MFKC_OK; }
+    unsigned int *d_cur = reinterpret_cast<unsigned int *>(ctx->d_bucket_cursor);        // 64 x u64 scratch: cursors (u32) ...
+    unsigned long long *d_kc = reinterpret_cast<unsigned long long *>(ctx->d_bucket_base);                                       // ... and k-mer counts (u64)
+    CU_TRY(cudaMemsetAsync(ctx->d_bucket_cursor, 0, 64 * sizeof(unsigned long long), ctx->compute));
+    CU_TRY(cudaMemsetAsync(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t), ctx->compute));
+    SkmStage st;
+    st.recs = reinterpret_cast<uint4 *>(d_recs_out); st.cursor = d_cur; st.seg_cap = seg_cap; st.n_regions = ns; st.region_shift = 0;
+    {
+        ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
+        if (ns <= 8)
+            extract_skm_owner8_kernel<<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                d_bases, n_bases, s.d_flags, k, st, ctx->d_ctr, d_kc);
+        else
+            extract_skm_kernel<true><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                d_bases, n_bases, s.d_flags, k, st, nullptr, 0, ctx->d_ctr, d_kc);
+    }
+    CU_TRY(cudaGetLastError());
+    unsigned int h_cur[64];
+    CU_TRY(cudaMemcpyAsync(h_cur, d_cur, ns * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaMemcpyAsync(ctx->h_bucket, d_kc, ns * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
+    bool overflow = false;
+    for (uint32_t i = 0; i < ns; i++) { rec_counts[i] = h_cur[i]; kmer_counts[i] = ctx->h_bucket[i]; if (h_cur[i] > seg_cap) overflow = true; }
+    CU_TRY(cudaMemset(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t)));                    // bucket 0 of the sort variant starts at 0
+    if (overflow) {
+        // undo this attempt's statistics; the caller re-submits the same reads in smaller pieces
+        CU_TRY(cudaMemcpy(ctx->d_ctr, ctx->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice));
+        return 1;
+    }
+    return MFKC_OK;
+}
+
+// Receive side: n records (device pointer) with n_kmers k-mer instances in total are filed into this
+// context's region staging; they are counted at the next drain (mfkc_flush at the latest).
+extern "C" int mfkc_skm_count_device(mfkc_ctx *ctx, const void *d_recs, uint64_t n_recs, uint64_t n_kmers) {
+    if (!ctx || (!d_recs && n_recs)) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (ctx->cfg.variant != MFKC_VARIANT_HASH || !ctx->place) return fail(ctx, MFKC_E_STATE, "mfkc_skm_count_device needs the region-blocked hash variant");
+    if (n_recs == 0) return MFKC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(reserve_slots(ctx, n_kmers));
+    // reserve staging by records (2 units each), not by the k-mer estimate
+    {
+        const uint64_t units = 2 * n_recs;
+        if (!ctx->rb_keys || ctx->staged_ub + units > std::min<uint64_t>(ctx->rb_cap, 4000000000ull)) TRY(reserve_staging(ctx, n_kmers));
+        ctx->staged_ub += units;
+    }
+    ctx->kmers_ub_total += n_kmers;
+    {
+        ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
+        skm_restage_kernel<<<grid_for(ctx, n_recs, 256, 8), 256, 0, ctx->compute>>>(
+            reinterpret_cast<const uint4 *>(d_recs), n_recs, ctx->cfg.k, skm_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr);
+    }
+    CU_TRY(cudaGetLastError());
     ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
     return MFKC_OK;
 }

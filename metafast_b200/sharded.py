@@ -4,9 +4,10 @@ No reference analogue (the reference is one JVM).  Layout:
 
     reads        -> split between ranks (any split is valid: counting is order-free)
     keys         -> owner(key) = mfkc_owner_shard(key, G): a hash independent of the table hash
-    per batch    -> rank r: extract + bucket by owner (mfkc_extract_bucketed, CUDA)
-                    all-to-all of the bucket sizes, then of the keys (NCCL over NVLink)
-                    owner: count the received keys (mfkc_count_keys_device, CUDA)
+    per batch    -> rank r: extract super-k-mer records bucketed by owner (mfkc_skm_extract_bucketed, CUDA)
+                    all-to-all of the bucket sizes, then of the records (NCCL over NVLink)
+                    owner: file the records under its table regions (mfkc_skm_count_device, CUDA)
+                    (a key-at-a-time flavour exists too: mfkc_extract_bucketed / mfkc_count_keys_device)
     results      -> per-shard histogram summed; per-shard key-sorted records merged by key
                     (shards hold disjoint key sets, so the merge is an interleave)
 
@@ -73,28 +74,75 @@ def merge_sorted_records(parts: Sequence[bytes], record_size: int = 10) -> bytes
     return b"".join(heapq.merge(*[recs(p) for p in parts]))
 
 
+def exchange_table(dist, rows: Sequence[Sequence[int]], device=None):
+    """all-to-all of one small int64 row per destination -> one row per source."""
+    import torch
+    world = dist.get_world_size()
+    width = len(rows[0])
+    send = torch.tensor([list(r) for r in rows], dtype=torch.int64, device=device).reshape(world, width)
+    if dist.get_backend() == "nccl":
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        return [[int(x) for x in row] for row in recv.tolist()]
+    gathered = [torch.empty(world, width, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gathered, send.cpu())
+    me = dist.get_rank()
+    return [[int(x) for x in gathered[src][me].tolist()] for src in range(world)]
+
+
 class ShardedStep:
-    """Per-rank driver of the sharded counting pass used by bench.py (N > 1)."""
+    """Per-rank driver of the sharded counting pass used by bench.py (N > 1).
+
+    Every round: extract super-k-mer records bucketed by owner shard (CUDA) -> exchange the
+    per-destination sizes -> all-to-all of the records (NCCL over NVLink, 16 B per ~6 k-mers) ->
+    file the received records under their table regions (CUDA).  The region-blocked drain and
+    the emit run per shard afterwards, exactly as on one GPU."""
 
     def __init__(self, kc, dist, world: int, rank: int, batch_reads: int, read_len: int, k: int):
         import torch
         self.kc, self.dist, self.world, self.rank = kc, dist, world, rank
         self.batch_reads, self.read_len, self.k = batch_reads, read_len, k
         self.torch = torch
-        cap = batch_reads * (read_len - k + 1)
-        self.send = torch.empty(cap, dtype=torch.int64, device="cuda")
-        self.recv = torch.empty(int(cap * 1.5) + 4096, dtype=torch.int64, device="cuda")
+        kmers = batch_reads * (read_len - k + 1)
+        # ~5-6 k-mers per record on Illumina-like reads; 3x slack per destination, retry in halves beyond
+        self.seg_cap = int(3.0 * kmers / 5 / world) + 65536
+        self.send = torch.empty(world * self.seg_cap * 2, dtype=torch.int64, device="cuda")     # 2 x int64 = one record
+        self.recv = torch.empty(world * self.seg_cap * 2, dtype=torch.int64, device="cuda")
         self.stage_b = torch.empty(batch_reads * read_len + 64, dtype=torch.uint8, device="cuda")
         self.stage_o = torch.empty(batch_reads + 1, dtype=torch.int64, device="cuda")
 
-    def _batch(self, d_bases: int, d_offs: int, n: int):
-        kc, torch, dist = self.kc, self.torch, self.dist
-        counts = kc.extract_bucketed(d_bases, d_offs, n, n * self.read_len, self.send.data_ptr(), self.send.numel(), self.world)
-        rcounts = exchange_counts(dist, counts, device="cuda")
-        kc.sync()                                  # the previous batch's count kernel has released self.recv
-        n_recv = exchange_keys(dist, self.send, counts, self.recv, rcounts)
-        torch.cuda.current_stream().synchronize()  # keys have landed before libmfkc's stream reads them
-        kc.count_keys_device(self.recv.data_ptr(), n_recv)
+    def _exchange(self, rec_counts, kmer_counts, overflow):
+        """one exchange round; returns True when some rank overflowed a segment (nothing was used)"""
+        kc, torch, dist, world = self.kc, self.torch, self.dist, self.world
+        rows = exchange_table(dist, [[rec_counts[d], kmer_counts[d], 1 if overflow else 0] for d in range(world)], device="cuda")
+        if any(r[2] for r in rows):
+            return True
+        kc.sync()                                  # the previous round's restage kernel has released self.recv
+        ins, outs, off = [], [], 0
+        for d in range(world):
+            ins.append(self.send[d * self.seg_cap * 2: d * self.seg_cap * 2 + 2 * rec_counts[d]])
+        for src in range(world):
+            outs.append(self.recv[off: off + 2 * rows[src][0]])
+            off += 2 * rows[src][0]
+        dist.all_to_all(outs, ins)
+        torch.cuda.current_stream().synchronize()  # records have landed before libmfkc's stream reads them
+        n_recs = sum(r[0] for r in rows)
+        if n_recs:
+            kc.skm_count_device(self.recv.data_ptr(), n_recs, sum(r[1] for r in rows))
+        return False
+
+    def _batch(self, d_bases: int, d_offs: int, n: int, h_offs=None, first=0):
+        """reads [first, first+n) of the staged batch; splits in halves when a send segment overflows"""
+        kc = self.kc
+        if n:
+            over, rc, kmc = kc.skm_extract_bucketed(d_bases + first * self.read_len, d_offs + first * 8, n, n * self.read_len,
+                                                    self.send.data_ptr(), self.seg_cap, self.world)
+        else:
+            over, rc, kmc = False, [0] * self.world, [0] * self.world
+        if self._exchange(rc, kmc, over):
+            half = n // 2                          # every rank splits (also those that did not overflow): rounds stay aligned
+            self._batch(d_bases, d_offs, half, h_offs, first)
+            self._batch(d_bases, d_offs, n - half, h_offs, first + half)
 
     def _rounds(self, n_reads: int) -> int:
         """Ranks may hold slightly different numbers of reads (N-reads are dropped per rank): agree on
@@ -104,33 +152,18 @@ class ShardedStep:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return int(t.item())
 
-    def _empty_batch(self):
-        torch, dist = self.torch, self.dist
-        zeros = [0] * self.world
-        rcounts = exchange_counts(dist, zeros, device="cuda")
-        self.kc.sync()
-        n_recv = exchange_keys(dist, self.send, zeros, self.recv, rcounts)
-        torch.cuda.current_stream().synchronize()
-        if n_recv:
-            self.kc.count_keys_device(self.recv.data_ptr(), n_recv)
-
     def run_device(self, d_bases: int, d_offs: int, n_reads: int):
         for r in range(self._rounds(n_reads)):
             s = r * self.batch_reads
-            if s >= n_reads:
-                self._empty_batch()
-                continue
             e = min(n_reads, s + self.batch_reads)
-            self._batch(d_bases + s * self.read_len, d_offs + s * 8, e - s)
+            self._batch(d_bases + s * self.read_len, d_offs + s * 8, max(0, e - s))
 
     def run_host(self, h_bases: np.ndarray, h_offs: np.ndarray, n_reads: int):
         for r in range(self._rounds(n_reads)):
             s = r * self.batch_reads
-            if s >= n_reads:
-                self._empty_batch()
-                continue
             e = min(n_reads, s + self.batch_reads)
-            b0, b1 = int(h_offs[s]), int(h_offs[e])
-            self.kc.h2d(self.stage_b.data_ptr(), h_bases[b0:b1])
-            self.kc.h2d(self.stage_o.data_ptr(), h_offs[s:e + 1])
-            self._batch(self.stage_b.data_ptr(), self.stage_o.data_ptr(), e - s)
+            if e > s:
+                b0, b1 = int(h_offs[s]), int(h_offs[e])
+                self.kc.h2d(self.stage_b.data_ptr(), h_bases[b0:b1])
+                self.kc.h2d(self.stage_o.data_ptr(), h_offs[s:e + 1])
+            self._batch(self.stage_b.data_ptr(), self.stage_o.data_ptr(), max(0, e - s))

@@ -248,6 +248,50 @@ def test_logical_shards_equal_unsharded(built, n_shards):
             s.close()
 
 
+@pytest.mark.parametrize("n_shards", [2, 5])
+def test_logical_shards_superkmer_exchange(built, n_shards):
+    """The super-k-mer flavour of the exchange with G logical shards on one GPU: records bucketed by the
+    owner of their minimizer -> 'exchange' -> filed under table regions -> drained; plus the overflow
+    signal of a send segment that is too small."""
+    cfg = m.synth_cfg(total_genome_bp=100000, n_genomes=4, n_read_ppm=0)
+    n = 4000
+    raw = m.synth_reads_host(cfg, 0, n)
+    bases = np.ascontiguousarray(raw).reshape(-1)
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(cfg.read_len)
+    want_rec, want_hist, _, want_stats = _oracle_c.count(bases, offsets, 31, 1, P=2)
+    shards = [m.KmerCounter(31, n_shards=n_shards, shard_id=s, table_slots=1 << 16, region_shift=9) for s in range(n_shards)]
+    try:
+        src = shards[0]
+        d_b = src.device_alloc(bases.nbytes); d_o = src.device_alloc(offsets.nbytes)
+        src.h2d(d_b, bases); src.h2d(d_o, offsets)
+        seg_cap = n * 120
+        d_recs = src.device_alloc(n_shards * seg_cap * 16)
+        over, _, _ = src.skm_extract_bucketed(d_b, d_o, n, bases.size, d_recs, 100, n_shards)
+        assert over                                                   # 100 records per segment cannot hold 480 k k-mers
+        over, rc, kmc = src.skm_extract_bucketed(d_b, d_o, n, bases.size, d_recs, seg_cap, n_shards)
+        assert not over and sum(kmc) == n * (cfg.read_len - 30) and sum(rc) < sum(kmc) / 3
+        st = src.stats()
+        assert [st["total_seq"], st["good_seq"], st["total_len"], st["good_len"]] == want_stats   # counted once, not twice
+        merged, hist = [], np.zeros(m.HIST_BINS, dtype=np.uint64)
+        for s in range(n_shards):
+            part = np.empty(rc[s] * 2, dtype=np.uint64)
+            src.d2h(part, d_recs + s * seg_cap * 16)
+            d_part = shards[s].device_alloc(max(part.nbytes, 16))
+            shards[s].h2d(d_part, part)
+            shards[s].skm_count_device(d_part, rc[s], kmc[s])
+            shards[s].flush()
+            merged.append(shards[s].emit(1))
+            hist += shards[s].histogram()
+            shards[s].device_free(d_part)
+        from metafast_b200.sharded import merge_sorted_records
+        assert merge_sorted_records(merged) == want_rec
+        assert (hist == want_hist).all()
+        src.device_free(d_b); src.device_free(d_o); src.device_free(d_recs)
+    finally:
+        for s in shards:
+            s.close()
+
+
 # ---------------------------------------------------------------- features-calculator
 def _components_from(counts, rng, n_comp=40):
     keys = sorted(counts)
