@@ -742,31 +742,50 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                 // compile-time indices).  Local staging: a run = same table REGION.  Send buffer
                 // (BY_OWNER): a run = same MINIMIZER HASH, because the receiver derives the region of
                 // the whole record from that one hash, under a table geometry the sender does not know.
-                uint32_t run_start = 0, run_key = 0, run_mh = 0;
-                bool in_run = false;
-                auto emit = [&](uint32_t j0, uint32_t len) {
-                    const int sh = 2 * (int)j0;                     // normalise: first base of the run -> base 0
-                    uint4 rec;
-                    rec.x = sh ? __funnelshift_l(w1, w0, sh) : w0;
-                    rec.y = sh ? __funnelshift_l(w2, w1, sh) : w1;
-                    rec.z = ((sh ? (w2 << sh) : w2) & ~15u) | (len - 1);
-                    rec.w = run_mh;
-                    const uint32_t bucket = BY_OWNER ? owner_of_minhash(run_mh, st.n_regions) : run_key;
-                    const uint32_t pos = atomicAdd(&st.cursor[bucket], 1u);
-                    if (pos < st.seg_cap) {
-                        st.recs[(uint64_t)bucket * st.seg_cap + pos] = rec;
-                        if (BY_OWNER) atomicAdd(&kmer_count[bucket], (unsigned long long)len);
-                    } else if (!BY_OWNER) {                         // segment full: count the run directly (slow, exact)
-                        claimed += skm_count_direct(rec, bucket, st.region_shift, k, tab, cap);
-                    }
-                };
+                // Two passes over the same state machine: pass 1 issues every cursor atomic of the
+                // thread back to back (their ~1 us round trips overlap), pass 2 writes the records.
+                auto bucket_of = [&](uint32_t mhv, uint32_t key) { return BY_OWNER ? owner_of_minhash(mhv, st.n_regions) : key; };
+                uint32_t pos[17];
+                {
+                    uint32_t run_key = 0, run_mh = 0;
+                    bool in_run = false;
 #pragma unroll
-                for (int j = 0; j <= 16; j++) {
-                    const bool v = j < 16 && ((valid >> j) & 1);
-                    const uint32_t mhj = mh[j < 16 ? j : 15];
-                    const uint32_t key = !v ? 0xFFFFFFFFu : (BY_OWNER ? mhj : region_of_minhash(mhj, st.n_regions));
-                    if (in_run && (!v || key != run_key)) { emit(run_start, (uint32_t)j - run_start); in_run = false; }
-                    if (v && !in_run) { in_run = true; run_start = (uint32_t)j; run_key = key; run_mh = mhj; }
+                    for (int j = 0; j <= 16; j++) {
+                        const bool v = j < 16 && ((valid >> j) & 1);
+                        const uint32_t mhj = mh[j < 16 ? j : 15];
+                        const uint32_t key = !v ? 0xFFFFFFFFu : (BY_OWNER ? mhj : region_of_minhash(mhj, st.n_regions));
+                        pos[j] = 0;
+                        if (in_run && (!v || key != run_key)) { pos[j] = atomicAdd(&st.cursor[bucket_of(run_mh, run_key)], 1u); in_run = false; }
+                        if (v && !in_run) { in_run = true; run_key = key; run_mh = mhj; }
+                    }
+                }
+                {
+                    uint32_t run_start = 0, run_key = 0, run_mh = 0;
+                    bool in_run = false;
+#pragma unroll
+                    for (int j = 0; j <= 16; j++) {
+                        const bool v = j < 16 && ((valid >> j) & 1);
+                        const uint32_t mhj = mh[j < 16 ? j : 15];
+                        const uint32_t key = !v ? 0xFFFFFFFFu : (BY_OWNER ? mhj : region_of_minhash(mhj, st.n_regions));
+                        if (in_run && (!v || key != run_key)) {
+                            const uint32_t len = (uint32_t)j - run_start;
+                            const int sh = 2 * (int)run_start;      // normalise: first base of the run -> base 0
+                            uint4 rec;
+                            rec.x = sh ? __funnelshift_l(w1, w0, sh) : w0;
+                            rec.y = sh ? __funnelshift_l(w2, w1, sh) : w1;
+                            rec.z = ((sh ? (w2 << sh) : w2) & ~15u) | (len - 1);
+                            rec.w = run_mh;
+                            const uint32_t bucket = bucket_of(run_mh, run_key);
+                            if (pos[j] < st.seg_cap) {
+                                st.recs[(uint64_t)bucket * st.seg_cap + pos[j]] = rec;
+                                if (BY_OWNER) atomicAdd(&kmer_count[bucket], (unsigned long long)len);
+                            } else if (!BY_OWNER) {                 // segment full: count the run directly (slow, exact)
+                                claimed += skm_count_direct(rec, bucket, st.region_shift, k, tab, cap);
+                            }
+                            in_run = false;
+                        }
+                        if (v && !in_run) { in_run = true; run_start = (uint32_t)j; run_key = key; run_mh = mhj; }
+                    }
                 }
             }
         }

@@ -60,6 +60,9 @@ struct mfkc_ctx {
     uint32_t n_regions = 1; int region_shift = 19;
     int place = 0;                     // 1: minimizer placement + super-k-mer staging (default for MFKC_VARIANT_HASH)
     cudaEvent_t ev_drain = nullptr; bool drain_pending = false; uint64_t kmers_at_drain = 0;
+    // tight bound for the region-blocked variant: exact values at the last synchronisation point
+    uint64_t distinct_base = 0, kmers_base = 0, recv_since_base = 0;
+    unsigned long long *h_drain_snap = nullptr;
 
     // sort variant
     unsigned long long *sv_keys = nullptr; uint64_t sv_cap = 0, sv_ub = 0;
@@ -240,6 +243,7 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     }
     CR_TRY(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
     CR_TRY(cudaEventCreateWithFlags(&ctx->ev_drain, cudaEventDisableTiming));
+    CR_TRY(cudaMallocHost(&ctx->h_drain_snap, sizeof(unsigned long long)));
     CR_TRY(cudaEventCreate(&ctx->t0));
     CR_TRY(cudaEventCreate(&ctx->t1));
     CR_TRY(cudaMalloc(&ctx->d_ctr, sizeof(Counters)));
@@ -331,6 +335,7 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     cudaFree(ctx->fc_tab); cudaFree(ctx->fc_keys); cudaFree(ctx->fc_off); cudaFree(ctx->fc_sel);
     cudaFree(ctx->d_synth);
     if (ctx->ev_drain) cudaEventDestroy(ctx->ev_drain);
+    if (ctx->h_drain_snap) cudaFreeHost(ctx->h_drain_snap);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     for (void *p : ctx->pinned) cudaFreeHost(p);
@@ -349,6 +354,7 @@ extern "C" int mfkc_reset(mfkc_ctx *ctx) {
     if (ctx->rb_cursor) CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS * sizeof(unsigned int), ctx->compute));
     CU_TRY(cudaStreamSynchronize(ctx->compute));
     ctx->staged_ub = 0;
+    ctx->distinct_base = ctx->kmers_base = ctx->recv_since_base = 0;
     ctx->distinct_ub = 0; ctx->kmers_ub_total = 0; ctx->sv_ub = 0; ctx->svs_n = 0;
     TMP_FREE(ctx->svs_keys); TMP_FREE(ctx->svs_counts); ctx->svs_keys = nullptr; ctx->svs_counts = nullptr;
     ctx->hist_valid = false; ctx->dirty = false;
@@ -384,8 +390,25 @@ static constexpr double kHardLoad = 0.92;    // region-blocked variant: distinct
 static void poll_snapshots(mfkc_ctx *ctx) {
     if (ctx->drain_pending && cudaEventQuery(ctx->ev_drain) == cudaSuccess) {
         ctx->drain_pending = false;
-        const uint64_t cand = *ctx->st[0].h_snap + (ctx->kmers_ub_total - ctx->kmers_at_drain);
+        const uint64_t cand = *ctx->h_drain_snap + (ctx->kmers_ub_total - ctx->kmers_at_drain);
         if (cand < ctx->distinct_ub) ctx->distinct_ub = cand;
+    }
+    if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
+        // per-batch snapshots of the EXACT number of k-mer instances extracted so far (the host only
+        // knows the loose bound bases - k + 1 per batch, which over-counts by ~25 % on 150 bp reads)
+        for (int i = 0; i < 2; i++) {
+            Staging &s = ctx->st[i];
+            if (s.pending && cudaEventQuery(s.ev_done) == cudaSuccess) {
+                s.pending = false;
+                const uint64_t exact = *s.h_snap;
+                if (exact >= ctx->kmers_base) {
+                    const uint64_t cand = ctx->distinct_base + (exact - ctx->kmers_base) + ctx->recv_since_base +
+                                          (ctx->kmers_ub_total - s.kmers_submitted_at_end);
+                    if (cand < ctx->distinct_ub) ctx->distinct_ub = cand;
+                }
+            }
+        }
+        return;
     }
     if (ctx->cfg.variant != MFKC_VARIANT_HASH_DIRECT) return;
     for (int i = 0; i < 2; i++) {
@@ -439,10 +462,11 @@ static int reserve_slots(mfkc_ctx *ctx, uint64_t add) {
     TRY(drain_regions(ctx));              // staged keys must be in the table before it is measured / rehashed
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
-    ctx->distinct_ub = ctx->h_ctr->distinct;
-    // after a forced drain leave room for a whole staging buffer so that the next one is far away
-    const uint64_t room = blocked ? std::max<uint64_t>(add, ctx->rb_cap) : add;
-    if ((double)(ctx->distinct_ub + room) > kMaxLoad * (double)ctx->cap) {
+    ctx->distinct_ub = ctx->distinct_base = ctx->h_ctr->distinct;
+    ctx->kmers_base = ctx->h_ctr->kmers; ctx->recv_since_base = 0;
+    // grow when the table is really filling up: after growth there is room for as many new keys again
+    const uint64_t room = blocked ? std::max<uint64_t>(add, ctx->distinct_ub) : add;
+    if ((double)(ctx->distinct_ub + add) > kMaxLoad * (double)ctx->cap) {
         const uint64_t need = (uint64_t)((double)(ctx->distinct_ub + room) / (blocked ? kMaxLoad : kGrowLoad)) + 1024;
         const int r = grow_table(ctx, need);
         if ((double)(ctx->distinct_ub + add) > kHardLoad * (double)ctx->cap) {
@@ -509,8 +533,7 @@ static int drain_regions(mfkc_ctx *ctx) {
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS * sizeof(unsigned int), ctx->compute));
     // distinct is exact for everything submitted so far once this point of the stream is reached
-    Staging &s0 = ctx->st[0];
-    CU_TRY(cudaMemcpyAsync(s0.h_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaMemcpyAsync(ctx->h_drain_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
     CU_TRY(cudaEventRecord(ctx->ev_drain, ctx->compute));
     ctx->drain_pending = true;
     ctx->kmers_at_drain = ctx->kmers_ub_total;
@@ -636,8 +659,10 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
     }
     if (ctx->cfg.variant == MFKC_VARIANT_HASH_DIRECT)
         CU_TRY(cudaMemcpyAsync(s.h_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
+    else if (ctx->cfg.variant == MFKC_VARIANT_HASH)
+        CU_TRY(cudaMemcpyAsync(s.h_snap, &ctx->d_ctr->kmers, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
     CU_TRY(cudaEventRecord(s.ev_done, ctx->compute));
-    s.pending = ctx->cfg.variant == MFKC_VARIANT_HASH_DIRECT;
+    s.pending = ctx->cfg.variant != MFKC_VARIANT_SORT;
     s.kmers_submitted_at_end = ctx->kmers_ub_total;
     ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
     return MFKC_OK;
@@ -682,7 +707,10 @@ extern "C" int mfkc_flush(mfkc_ctx *ctx) {
     TRY(drain_regions(ctx));
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
-    if (ctx->cfg.variant != MFKC_VARIANT_SORT) ctx->distinct_ub = ctx->h_ctr->distinct;
+    if (ctx->cfg.variant != MFKC_VARIANT_SORT) {
+        ctx->distinct_ub = ctx->distinct_base = ctx->h_ctr->distinct;
+        ctx->kmers_base = ctx->h_ctr->kmers; ctx->recv_since_base = 0;
+    }
     ctx->dirty = false;
     if (ctx->h_ctr->bad_chars) return fail(ctx, MFKC_E_FORMAT, "Incorrect nucleotide char in submitted reads (only AaCcGgTt are accepted)");
     if (ctx->h_ctr->overflow) return fail(ctx, MFKC_E_STATE, "internal key buffer overflow");
@@ -1092,7 +1120,7 @@ extern "C" int mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uin
     TRY(reserve_slots(ctx, n));
     const bool stage_keys = ctx->cfg.variant == MFKC_VARIANT_HASH && !ctx->place;
     if (stage_keys) { TRY(reserve_staging(ctx, n)); ctx->staged_ub += n; }
-    ctx->kmers_ub_total += n;
+    ctx->kmers_ub_total += n; ctx->recv_since_base += n;
     Staging &s = ctx->st[ctx->next_buf];
     ctx->next_buf ^= 1;
     if (stage_keys) {
@@ -1181,7 +1209,7 @@ extern "C" int mfkc_skm_count_device(mfkc_ctx *ctx, const void *d_recs, uint64_t
         if (!ctx->rb_keys || ctx->staged_ub + units > std::min<uint64_t>(ctx->rb_cap, 4000000000ull)) TRY(reserve_staging(ctx, n_kmers));
         ctx->staged_ub += units;
     }
-    ctx->kmers_ub_total += n_kmers;
+    ctx->kmers_ub_total += n_kmers; ctx->recv_since_base += n_kmers;
     {
         ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
         skm_restage_kernel<<<grid_for(ctx, n_recs, 256, 8), 256, 0, ctx->compute>>>(
