@@ -150,6 +150,9 @@ int  mfkc_skm_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, const uint
 /* Receive side: file n_recs records (device pointer; n_kmers k-mer instances in total) under their table
  * regions; they are counted at the next drain (mfkc_flush at the latest). */
 int  mfkc_skm_count_device(mfkc_ctx *ctx, const void *d_recs, uint64_t n_recs, uint64_t n_kmers);
+/* Block until every mfkc_skm_count_device issued so far has finished reading its d_recs buffer (they run on
+ * a side stream so that the next extraction overlaps them; call this before overwriting a receive buffer). */
+int  mfkc_skm_count_wait(mfkc_ctx *ctx);
 
 /* ---- features-calculator: replaces the BigLong2LongHashMap set-up
  * (src/tools/FeaturesCalculatorMain.java:97-103), IOUtils.calculatePresenceForKmers /

@@ -87,6 +87,7 @@ SIGNATURES = {
     "mfkc_skm_extract_bucketed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64,
                                             C.c_void_p, C.c_uint64, u64p, u64p]),
     "mfkc_skm_count_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
+    "mfkc_skm_count_wait": (C.c_int, [C.c_void_p]),
     "mfkc_fc_load_components": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "mfkc_fc_set_selected": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "mfkc_fc_reset_values": (C.c_int, [C.c_void_p]),

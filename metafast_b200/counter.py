@@ -227,6 +227,9 @@ class KmerCounter(_Ctx):
     def skm_count_device(self, d_recs: int, n_recs: int, n_kmers: int):
         self._ck(self.lib.mfkc_skm_count_device(self.h, C.c_void_p(d_recs), n_recs, n_kmers))
 
+    def skm_count_wait(self):
+        self._ck(self.lib.mfkc_skm_count_wait(self.h))
+
 
 class FeaturesCalculator(_Ctx):
     """features-calculator on the device (K6/K7/K8)."""

@@ -44,7 +44,9 @@ struct mfkc_ctx {
     int device = 0, sm_count = 148;
     std::string err;
     Staging st[2];                     // copy streams + staging buffers (double-buffered H2D)
-    cudaStream_t compute = nullptr;    // every kernel runs here, in submission order
+    cudaStream_t compute = nullptr;    // every kernel runs here, in submission order ...
+    cudaStream_t aux = nullptr;        // ... except the receive side of the shard exchange, which overlaps the next extraction
+    cudaEvent_t ev_aux = nullptr; bool aux_pending = false;
     int next_buf = 0;
 
     // hash variant
@@ -151,8 +153,9 @@ static int grid_for(const mfkc_ctx *ctx, uint64_t work_items, int threads, int b
 static int sync_all(mfkc_ctx *ctx) {
     CU_TRY(cudaStreamSynchronize(ctx->st[0].stream));
     CU_TRY(cudaStreamSynchronize(ctx->st[1].stream));
+    CU_TRY(cudaStreamSynchronize(ctx->aux));
     CU_TRY(cudaStreamSynchronize(ctx->compute));
-    ctx->st[0].pending = ctx->st[1].pending = false; ctx->drain_pending = false;
+    ctx->st[0].pending = ctx->st[1].pending = false; ctx->drain_pending = false; ctx->aux_pending = false;
     return MFKC_OK;
 }
 
@@ -242,6 +245,8 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
         CR_TRY(cudaMallocHost(&ctx->st[i].h_snap, sizeof(unsigned long long)));
     }
     CR_TRY(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    CR_TRY(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+    CR_TRY(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
     CR_TRY(cudaEventCreateWithFlags(&ctx->ev_drain, cudaEventDisableTiming));
     CR_TRY(cudaMallocHost(&ctx->h_drain_snap, sizeof(unsigned long long)));
     CR_TRY(cudaEventCreate(&ctx->t0));
@@ -325,6 +330,8 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     }
     free_emit(ctx);
     if (ctx->compute) { cudaStreamSynchronize(ctx->compute); cudaStreamDestroy(ctx->compute); ctx->compute = nullptr; }
+    if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); ctx->aux = nullptr; }
+    if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
     cudaFree(ctx->rb_keys); cudaFree(ctx->rb_cursor);
     cudaFree(ctx->tab); cudaFree(ctx->sv_keys); cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts);
     cudaFree(ctx->d_bucket_cursor); cudaFree(ctx->d_bucket_base);
@@ -519,6 +526,7 @@ static uint64_t stage_units(const mfkc_ctx *ctx, uint64_t kmers) {
 // phase B: upsert every staged key, region by region (asynchronous on the compute stream)
 static int drain_regions(mfkc_ctx *ctx) {
     if (ctx->cfg.variant != MFKC_VARIANT_HASH || ctx->staged_ub == 0 || !ctx->rb_keys) return MFKC_OK;
+    if (ctx->aux_pending) { CU_TRY(cudaStreamWaitEvent(ctx->compute, ctx->ev_aux, 0)); ctx->aux_pending = false; }
     const uint64_t per_region = ctx->staged_ub / ctx->n_regions + 1;       // 8-byte units
     {
         ProfScope ps(ctx, P_DRAIN, ctx->compute);
@@ -1211,12 +1219,22 @@ extern "C" int mfkc_skm_count_device(mfkc_ctx *ctx, const void *d_recs, uint64_t
     }
     ctx->kmers_ub_total += n_kmers; ctx->recv_since_base += n_kmers;
     {
-        ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
-        skm_restage_kernel<<<grid_for(ctx, n_recs, 256, 8), 256, 0, ctx->compute>>>(
+        // on the aux stream: the next round's extraction (compute stream) overlaps this kernel
+        ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->aux);
+        skm_restage_kernel<<<grid_for(ctx, n_recs, 256, 4), 256, 0, ctx->aux>>>(
             reinterpret_cast<const uint4 *>(d_recs), n_recs, ctx->cfg.k, skm_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr);
     }
     CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(ctx->ev_aux, ctx->aux));
+    ctx->aux_pending = true;
     ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_skm_count_wait(mfkc_ctx *ctx) {
+    if (!ctx) return MFKC_E_BADARG;
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaStreamSynchronize(ctx->aux));
     return MFKC_OK;
 }
 

@@ -107,7 +107,10 @@ class ShardedStep:
         # ~5-6 k-mers per record on Illumina-like reads; 3x slack per destination, retry in halves beyond
         self.seg_cap = int(3.0 * kmers / 5 / world) + 65536
         self.send = torch.empty(world * self.seg_cap * 2, dtype=torch.int64, device="cuda")     # 2 x int64 = one record
-        self.recv = torch.empty(world * self.seg_cap * 2, dtype=torch.int64, device="cuda")
+        # two receive buffers: the restage kernel of round r (side stream) reads one while the all-to-all of
+        # round r+1 fills the other and the extraction of round r+1 runs on the main stream
+        self.recv2 = [torch.empty(world * self.seg_cap * 2, dtype=torch.int64, device="cuda") for _ in range(2)]
+        self.round = 0
         self.stage_b = torch.empty(batch_reads * read_len + 64, dtype=torch.uint8, device="cuda")
         self.stage_o = torch.empty(batch_reads + 1, dtype=torch.int64, device="cuda")
 
@@ -117,18 +120,20 @@ class ShardedStep:
         rows = exchange_table(dist, [[rec_counts[d], kmer_counts[d], 1 if overflow else 0] for d in range(world)], device="cuda")
         if any(r[2] for r in rows):
             return True
-        kc.sync()                                  # the previous round's restage kernel has released self.recv
+        recv = self.recv2[self.round & 1]
+        self.round += 1
+        kc.skm_count_wait()                        # the restage kernels that read the receive buffers are done
         ins, outs, off = [], [], 0
         for d in range(world):
             ins.append(self.send[d * self.seg_cap * 2: d * self.seg_cap * 2 + 2 * rec_counts[d]])
         for src in range(world):
-            outs.append(self.recv[off: off + 2 * rows[src][0]])
+            outs.append(recv[off: off + 2 * rows[src][0]])
             off += 2 * rows[src][0]
         dist.all_to_all(outs, ins)
         torch.cuda.current_stream().synchronize()  # records have landed before libmfkc's stream reads them
         n_recs = sum(r[0] for r in rows)
         if n_recs:
-            kc.skm_count_device(self.recv.data_ptr(), n_recs, sum(r[1] for r in rows))
+            kc.skm_count_device(recv.data_ptr(), n_recs, sum(r[1] for r in rows))
         return False
 
     def _batch(self, d_bases: int, d_offs: int, n: int, h_offs=None, first=0):
