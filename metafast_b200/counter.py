@@ -53,6 +53,7 @@ class _Ctx:
             raise _abi.MfkcError(rc, self.lib.mfkc_last_error(None).decode())
         self.h = h
         self.k = k
+        self.rec_size = 18 if k > 31 else 10      # 16-byte BE key for 128-bit keys (extension)
 
     def _ck(self, rc: int):
         if rc != 0:
@@ -171,7 +172,8 @@ class KmerCounter(_Ctx):
     def emit(self, threshold: int, chunk_bytes: int = 16777200) -> bytes:
         """All records (big-endian, ascending key) as one bytes object."""
         n = self.emit_begin(threshold)
-        out = np.empty(n * 10, dtype=np.uint8) if n else np.empty(0, dtype=np.uint8)
+        rs = self.rec_size
+        out = np.empty(n * rs, dtype=np.uint8) if n else np.empty(0, dtype=np.uint8)
         pos = 0
         w = C.c_size_t()
         while True:
@@ -180,17 +182,18 @@ class KmerCounter(_Ctx):
             if w.value == 0:
                 break
             pos += w.value
-        assert pos == n * 10
+        assert pos == n * rs
         return out.tobytes()
 
     def emit_into(self, threshold: int, out: np.ndarray) -> int:
         """Records into a caller-provided (ideally pinned) uint8 buffer; returns bytes written."""
         n = self.emit_begin(threshold)
-        if n * 10 > out.nbytes:
-            raise ValueError("output buffer too small: need %d bytes" % (n * 10))
+        rs = self.rec_size
+        if n * rs > out.nbytes:
+            raise ValueError("output buffer too small: need %d bytes" % (n * rs))
         pos = 0
         w = C.c_size_t()
-        while pos < n * 10:
+        while pos < n * rs:
             self._ck(self.lib.mfkc_emit_next(self.h, C.c_void_p(out.ctypes.data + pos), out.nbytes - pos, C.byref(w)))
             if w.value == 0:
                 break

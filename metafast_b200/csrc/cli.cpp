@@ -6,7 +6,8 @@
 //   mfkc_cli -t kmer-counter       -k K [-b B] -i reads...            (one sample: all files into one table)
 //   mfkc_cli -t features-calculator -k K -cm components.bin [-ka kmers.bin...] [-i reads...]
 //                                   [--selected kmers.bin...] [--threshold T] [-w workDir]
-//   extras (optional, old command lines keep working): --gpu N, --gpu-variant hash|sort|direct
+//   extras (optional, old command lines keep working): --gpu N, --gpu-variant hash|sort|direct,
+//   --long-kmers (accept 32 <= k <= 63: 128-bit keys, <name>.kmers128.bin with 18-byte records)
 //
 // Mirrors src/tools/KmersCounterForManyFilesMain.java:26-120, src/tools/KmersCounterMain.java:28-137,
 // src/tools/FeaturesCalculatorMain.java:30-236 and src/structures/ConnectedComponent.java:95-122:
@@ -106,7 +107,7 @@ Args parse_args(int argc, char **argv) {
         {"-cm", "components-file"}, {"--components-file", "components-file"}, {"-ka", "kmers"}, {"--kmers", "kmers"},
         {"--selected", "selected"}, {"--threshold", "threshold"}, {"-p", "available-processors"},
         {"--available-processors", "available-processors"}, {"--gpu", "gpu"}, {"--gpu-variant", "gpu-variant"},
-        {"--force", "force"}, {"-v", "verbose"}, {"--verbose", "verbose"}};
+        {"--force", "force"}, {"-v", "verbose"}, {"--verbose", "verbose"}, {"--long-kmers", "long-kmers"}};
     Args a;
     std::string cur;
     for (int i = 1; i < argc; i++) {
@@ -196,7 +197,8 @@ std::string count_sample(mfkc_ctx *ctx, int k, int b, const std::vector<std::str
         for_each_batch(ctx, f, [&](const uint8_t *bases, const uint64_t *offs, uint32_t n) { CK(ctx, mfkc_submit_reads(ctx, bases, offs, n)); });
     CK(ctx, mfkc_flush(ctx));
     mkdirs(out_dir); mkdirs(st_dir);
-    const std::string out_file = out_dir + "/" + name + ".kmers.bin", st_file = st_dir + "/" + name + ".stat.txt";
+    // k > 31 (--long-kmers, 18-byte records) gets its own extension so that no reference tool misreads the file
+    const std::string out_file = out_dir + "/" + name + (k > 31 ? ".kmers128.bin" : ".kmers.bin"), st_file = st_dir + "/" + name + ".stat.txt";
     uint64_t good = 0;
     CK(ctx, mfkc_emit_begin(ctx, b, &good));
     FILE *f = fopen(out_file.c_str(), "wb");
@@ -221,16 +223,17 @@ std::string count_sample(mfkc_ctx *ctx, int k, int b, const std::vector<std::str
     if (size == 0) warn("No k-mers found in reads! Perhaps you reads file is empty or k-mer size is too big");
     else if (good == 0 || good < (uint64_t)(size * 0.03))
         warn("Too few good k-mers were found! Perhaps you should decrease k-mer size or --maximal-bad-frequency value");
-    const uint64_t all = (1ull << (2 * k)) / 2;
+    const uint64_t all = k > 31 ? ~0ull : (1ull << (2 * k)) / 2;
     if (size == all) warn("All possible k-mers were found in reads! Perhaps you should increase k-mer size");
     else if (size >= (uint64_t)(all * 0.99)) warn("Almost all possible k-mers were found in reads! Perhaps you should increase k-mer size");
     info("Good k-mers printed to %s", out_file.c_str());
     return out_file;
 }
 
-mfkc_ctx *make_ctx(int k, const Gpu &g, uint64_t expected_kmers) {
+mfkc_ctx *make_ctx(int k, const Gpu &g, uint64_t expected_kmers, bool long_kmers = false) {
     if (k <= 0) die("The size of k-mer must be at least 1.");               // KmersCounterMain.java:66-69
-    if (k > 31) die("The size of k-mer must be no more than 31.");          // KmersCounterMain.java:70-73
+    if (k > 31 && !long_kmers) die("The size of k-mer must be no more than 31.");   // KmersCounterMain.java:70-73
+    if (k > 63) die("The size of k-mer must be no more than 63.");
     mfkc_cfg cfg; memset(&cfg, 0, sizeof cfg);
     cfg.struct_size = sizeof cfg; cfg.k = k; cfg.device = g.device; cfg.variant = g.variant;
     cfg.expected_kmers = expected_kmers;
@@ -286,7 +289,7 @@ int tool_counter(const Args &a, bool many) {
     }
     uint64_t biggest = 0;
     for (const auto &s : samples) biggest = std::max(biggest, estimate_bases(s.second));
-    mfkc_ctx *ctx = make_ctx(k, g, biggest);
+    mfkc_ctx *ctx = make_ctx(k, g, biggest, a.has("long-kmers"));
     std::vector<std::string> outs;
     for (const auto &s : samples) outs.push_back(count_sample(ctx, k, b, s.second, s.first, out_dir, st_dir));
     mfkc_destroy(ctx);

@@ -9,6 +9,7 @@
 
 #include "../../include/mfkc.h"
 #include "kernels.cuh"
+#include "kernels128.cuh"
 #include "radix_sort.cuh"
 #include "synth.h"
 
@@ -51,6 +52,7 @@ struct mfkc_ctx {
 
     // hash variant
     Slot *tab = nullptr; uint64_t cap = 0;
+    Slot128 *tab128 = nullptr; bool k128 = false;   // 32 <= k <= 63: 128-bit keys, 32-byte slots (same cap / regions)
     uint64_t distinct_ub = 0;          // host-side upper bound of occupied slots
     uint64_t kmers_ub_total = 0;       // cumulative upper bound of submitted k-mer instances
     uint64_t max_table_bytes = 0;
@@ -200,13 +202,16 @@ static void plan_regions(const mfkc_ctx *ctx, uint64_t slots, uint64_t *cap, uin
     *cap = n << sh; *n_regions = (uint32_t)n; *shift = sh;
 }
 
+static size_t slot_bytes(const mfkc_ctx *ctx) { return ctx->k128 ? sizeof(Slot128) : sizeof(Slot); }
+
 static int table_alloc(mfkc_ctx *ctx, uint64_t slots, Slot **out) {
     Slot *t = nullptr;
-    cudaError_t e = big_alloc(ctx, (void **)&t, slots * sizeof(Slot));
+    cudaError_t e = big_alloc(ctx, (void **)&t, slots * slot_bytes(ctx));
     if (e != cudaSuccess) { ctx->err = "cannot allocate k-mer table"; return MFKC_E_OOM; }
     {
         ProfScope ps(ctx, P_CLEAR, ctx->compute);
-        table_clear_kernel<<<grid_for(ctx, slots, 256, 16), 256, 0, ctx->compute>>>(t, slots);
+        if (ctx->k128) table128_clear_kernel<<<grid_for(ctx, 2 * slots, 256, 16), 256, 0, ctx->compute>>>(reinterpret_cast<Slot128 *>(t), slots);
+        else table_clear_kernel<<<grid_for(ctx, slots, 256, 16), 256, 0, ctx->compute>>>(t, slots);
     }
     CU_TRY(cudaGetLastError());
     *out = t;
@@ -217,7 +222,10 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     if (!cfg || !out) { g_create_err = "null argument"; return MFKC_E_BADARG; }
     if (cfg->struct_size != sizeof(mfkc_cfg)) { g_create_err = "mfkc_cfg.struct_size mismatch"; return MFKC_E_BADARG; }
     if (cfg->k <= 0) { g_create_err = "The size of k-mer must be at least 1."; return MFKC_E_BADARG; }        // KmersCounterMain.java:66-69
-    if (cfg->k > 31) { g_create_err = "The size of k-mer must be no more than 31."; return MFKC_E_BADARG; }   // KmersCounterMain.java:70-73
+    if (cfg->k > 63) { g_create_err = "The size of k-mer must be no more than 63 (31 in the reference)."; return MFKC_E_BADARG; }
+    if (cfg->k > 31 && cfg->variant != MFKC_VARIANT_HASH) {        // the reference stops at 31 (KmersCounterMain.java:70-73)
+        g_create_err = "k > 31 (128-bit keys) is only available with MFKC_VARIANT_HASH"; return MFKC_E_BADARG;
+    }
     if (cfg->variant != MFKC_VARIANT_HASH && cfg->variant != MFKC_VARIANT_SORT && cfg->variant != MFKC_VARIANT_HASH_DIRECT) {
         g_create_err = "unknown variant"; return MFKC_E_BADARG;
     }
@@ -285,19 +293,21 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     if (cfg->variant == MFKC_VARIANT_HASH) {
         const char *sm = getenv("MFKC_STAGE");            // 0 = stage single keys (hash placement), default = super-k-mers
         ctx->place = (sm && atoi(sm) == 0) ? 0 : 1;
+        if (cfg->k > 31) { ctx->place = 1; ctx->k128 = true; }
     }
     if (cfg->variant != MFKC_VARIANT_SORT) {
         uint64_t slots = cfg->table_slots;
         if (!slots && cfg->expected_distinct) slots = cfg->expected_distinct * 2;      // load 0.5
         if (!slots && cfg->expected_kmers && cfg->variant == MFKC_VARIANT_HASH)
-            slots = std::min<uint64_t>((uint64_t)(cfg->expected_kmers / 0.85) + 1024, (uint64_t)(total_b * 0.35) / sizeof(Slot));
+            slots = std::min<uint64_t>((uint64_t)(cfg->expected_kmers / 0.85) + 1024, (uint64_t)(total_b * 0.35) / slot_bytes(ctx));
         if (!slots) slots = 1ull << 22;                                                // 64 MiB, grows on demand
         if (slots < 1024) slots = 1024;
-        if (slots * sizeof(Slot) > ctx->max_table_bytes) slots = ctx->max_table_bytes / sizeof(Slot);
+        if (slots * slot_bytes(ctx) > ctx->max_table_bytes) slots = ctx->max_table_bytes / slot_bytes(ctx);
         plan_regions(ctx, slots, &slots, &ctx->n_regions, &ctx->region_shift);
         int r = table_alloc(ctx, slots, &ctx->tab);
         if (r != MFKC_OK) return bail(r);
         ctx->cap = slots;
+        ctx->tab128 = reinterpret_cast<Slot128 *>(ctx->tab);
         CR_TRY(cudaMalloc(&ctx->rb_cursor, MAX_REGIONS * sizeof(unsigned int)));
         CR_TRY(cudaMemset(ctx->rb_cursor, 0, MAX_REGIONS * sizeof(unsigned int)));
         ctx->rb_cap_max = (uint64_t)(total_b * 0.25) / 8;
@@ -355,7 +365,8 @@ extern "C" int mfkc_reset(mfkc_ctx *ctx) {
     TRY(sync_all(ctx));
     if (ctx->tab) {
         ProfScope ps(ctx, P_CLEAR, ctx->compute);
-        table_clear_kernel<<<grid_for(ctx, ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap);
+        if (ctx->k128) table128_clear_kernel<<<grid_for(ctx, 2 * ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab128, ctx->cap);
+        else table_clear_kernel<<<grid_for(ctx, ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap);
     }
     CU_TRY(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->compute));
     if (ctx->rb_cursor) CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS * sizeof(unsigned int), ctx->compute));
@@ -430,10 +441,10 @@ static void poll_snapshots(mfkc_ctx *ctx) {
 
 static int grow_table(mfkc_ctx *ctx, uint64_t need_slots) {
     uint64_t new_cap = std::max<uint64_t>(ctx->cap * 2, need_slots);
-    const uint64_t limit = ctx->max_table_bytes / sizeof(Slot);
+    const uint64_t limit = ctx->max_table_bytes / slot_bytes(ctx);
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t fit = (uint64_t)(free_b * 0.95) / sizeof(Slot);          // old table stays alive during the rehash
+    const uint64_t fit = (uint64_t)(free_b * 0.95) / slot_bytes(ctx);       // old table stays alive during the rehash
     if (new_cap > limit) new_cap = limit;
     if (new_cap > fit) new_cap = fit;
     uint32_t nr = 1; int sh = 19;
@@ -444,13 +455,18 @@ static int grow_table(mfkc_ctx *ctx, uint64_t need_slots) {
     TRY(table_alloc(ctx, new_cap, &nt));
     {
         ProfScope ps(ctx, P_REHASH, ctx->compute);
-        TableGeom ng; ng.cap = new_cap; ng.n_regions = nr; ng.region_shift = sh; ng.k = ctx->cfg.k; ng.minimizer = ctx->place;
-        rehash_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap, nt, ng);
+        if (ctx->k128) {
+            TableGeom128 ng; ng.cap = new_cap; ng.n_regions = nr; ng.region_shift = sh; ng.k = ctx->cfg.k;
+            rehash128_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(ctx->tab128, ctx->cap, reinterpret_cast<Slot128 *>(nt), ng);
+        } else {
+            TableGeom ng; ng.cap = new_cap; ng.n_regions = nr; ng.region_shift = sh; ng.k = ctx->cfg.k; ng.minimizer = ctx->place;
+            rehash_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap, nt, ng);
+        }
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(ctx->compute));
     CU_TRY(cudaFree(ctx->tab));
-    ctx->tab = nt; ctx->cap = new_cap;
+    ctx->tab = nt; ctx->cap = new_cap; ctx->tab128 = reinterpret_cast<Slot128 *>(nt);
     ctx->n_regions = nr; ctx->region_shift = sh;
     return MFKC_OK;
 }
@@ -520,7 +536,16 @@ static uint64_t stage_units(const mfkc_ctx *ctx, uint64_t kmers) {
     if (!ctx->place) return kmers;
     const int w = ctx->cfg.k - minimizer_len(ctx->cfg.k) + 1;
     const int div = std::max(1, std::min(4, w / 4));
-    return 2 * (kmers / div + 1);
+    return (ctx->k128 ? 4 : 2) * (kmers / div + 1);               // 32-byte records for 128-bit keys
+}
+static SkmStage128 skm_stage128(const mfkc_ctx *ctx) {
+    SkmStage128 st;
+    st.recs = reinterpret_cast<uint4 *>(ctx->rb_keys); st.cursor = ctx->rb_cursor;
+    st.n_regions = ctx->n_regions; st.region_shift = ctx->region_shift;
+    uint64_t seg = (ctx->rb_cap / 4) / ctx->n_regions;
+    if (seg > 0x7fffffffull) seg = 0x7fffffffull;
+    st.seg_cap = seg;
+    return st;
 }
 
 // phase B: upsert every staged key, region by region (asynchronous on the compute stream)
@@ -530,7 +555,10 @@ static int drain_regions(mfkc_ctx *ctx) {
     const uint64_t per_region = ctx->staged_ub / ctx->n_regions + 1;       // 8-byte units
     {
         ProfScope ps(ctx, P_DRAIN, ctx->compute);
-        if (ctx->place) {
+        if (ctx->k128) {
+            const uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 4 / 512));
+            drain_skm128_kernel<<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(skm_stage128(ctx), bpr, ctx->cfg.k, ctx->tab128, ctx->cap, ctx->d_ctr);
+        } else if (ctx->place) {
             const uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 2 / 512));
             drain_skm_kernel<<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(skm_stage(ctx), bpr, ctx->cfg.k, ctx->tab, ctx->cap, ctx->d_ctr);
         } else {
@@ -640,7 +668,10 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
         if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
             ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
             static const int stage_mode = getenv("MFKC_STAGE") ? atoi(getenv("MFKC_STAGE")) : 2;
-            if (ctx->place) {                 // super-k-mer records, minimizer placement
+            if (ctx->k128) {                  // 128-bit keys: 32-byte super-k-mer records
+                extract_skm128_kernel<<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                    d_bases, n_bases, s.d_flags, k, skm_stage128(ctx), ctx->tab128, ctx->cap, ctx->d_ctr);
+            } else if (ctx->place) {          // super-k-mer records, minimizer placement
                 extract_skm_kernel<false><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
                     d_bases, n_bases, s.d_flags, k, skm_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr, nullptr);
             } else if (stage_mode == 0) {     // single keys, shared-memory histogram flavour
@@ -900,7 +931,9 @@ static int compute_hist(mfkc_ctx *ctx) {
     CU_TRY(cudaMemsetAsync(ctx->d_hist, 0, MFKC_HIST_BINS * sizeof(unsigned long long), st));
     {
         ProfScope ps(ctx, P_HIST, st);
-        if (ctx->cfg.variant != MFKC_VARIANT_SORT)
+        if (ctx->k128)
+            table128_scan_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, st>>>(ctx->tab128, ctx->cap, 0xFFFFFFFFu, ctx->d_hist, nullptr, nullptr, 0, ctx->d_ctr);
+        else if (ctx->cfg.variant != MFKC_VARIANT_SORT)
             table_hist_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, st>>>(ctx->tab, ctx->cap, ctx->d_hist);
         else if (ctx->svs_n)
             pairs_hist_kernel<<<grid_for(ctx, ctx->svs_n, 256, 8), 256, 0, st>>>(ctx->svs_counts, ctx->svs_n, ctx->d_hist);
@@ -977,6 +1010,46 @@ extern "C" int mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_goo
     const uint32_t thr_u = threshold < 0 ? 0u : (uint32_t)threshold;
     cudaStream_t st = ctx->compute;
     uint64_t good = 0;
+    if (ctx->k128) {
+        TRY(read_counters(ctx));
+        const uint64_t distinct = ctx->h_ctr->distinct;
+        CU_TRY(cudaMemsetAsync(ctx->d_hist, 0, MFKC_HIST_BINS * sizeof(unsigned long long), st));
+        CU_TRY(cudaMemsetAsync(&ctx->d_ctr->n_good, 0, sizeof(unsigned long long), st));
+        unsigned long long *k1 = nullptr, *k2 = nullptr; HiCount *v1 = nullptr, *v2 = nullptr;
+        TMP_ALLOC(k1, (size_t)std::max<uint64_t>(distinct, 1) * 8);
+        TMP_ALLOC(v1, (size_t)std::max<uint64_t>(distinct, 1) * sizeof(HiCount));
+        {
+            ProfScope ps(ctx, P_COMPACT, st);
+            table128_scan_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, st>>>(ctx->tab128, ctx->cap, thr_u, ctx->d_hist, k1, v1, distinct, ctx->d_ctr);
+        }
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, MFKC_HIST_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&ctx->h_ctr->n_good, &ctx->d_ctr->n_good, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        ctx->hist_valid = true;
+        good = ctx->h_ctr->n_good;
+        if (good) {
+            TMP_ALLOC(k2, (size_t)good * 8);
+            TMP_ALLOC(v2, (size_t)good * sizeof(HiCount));
+            int r = radix_sort<HiCount, true>(ctx, st, k1, k2, v1, v2, good, 64);                       // by the low word ...
+            if (r == MFKC_OK) {
+                swap_key_words_kernel<<<grid_for(ctx, good, 256, 8), 256, 0, st>>>(k1, v1, good);
+                r = radix_sort<HiCount, true>(ctx, st, k1, k2, v1, v2, good, 2 * ctx->cfg.k - 64);      // ... then (stable) by the high word
+            }
+            if (r != MFKC_OK) { TMP_FREE(k1); TMP_FREE(k2); TMP_FREE(v1); TMP_FREE(v2); return r; }
+            TMP_ALLOC(ctx->em_records, (size_t)good * 18);
+            {
+                ProfScope ps(ctx, P_RECORDS, st);
+                records128_kernel<<<grid_for(ctx, good, 256, 8), 256, 0, st>>>(k1, v1, good, reinterpret_cast<uint16_t *>(ctx->em_records));
+            }
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaStreamSynchronize(st));
+        }
+        TMP_FREE(k1); TMP_FREE(k2); TMP_FREE(v1); TMP_FREE(v2);
+        ctx->em_n = good; ctx->em_cursor = 0; ctx->em_valid = true;
+        if (n_good) *n_good = good;
+        return MFKC_OK;
+    }
     if (ctx->cfg.variant != MFKC_VARIANT_SORT) {
         // one pass over the table: histogram + compaction (buffers sized by the exact distinct count)
         TRY(read_counters(ctx));
@@ -1057,17 +1130,19 @@ extern "C" int mfkc_emit_next(mfkc_ctx *ctx, uint8_t *out, size_t cap, size_t *w
     if (!ctx->em_valid) return fail(ctx, MFKC_E_STATE, "mfkc_emit_next without mfkc_emit_begin");
     CU_TRY(cudaSetDevice(ctx->device));
     const uint64_t left = ctx->em_n - ctx->em_cursor;
-    uint64_t take = std::min<uint64_t>(left, cap / 10);
+    const size_t rs = ctx->k128 ? 18 : 10;
+    uint64_t take = std::min<uint64_t>(left, cap / rs);
     if (take && !out) return MFKC_E_BADARG;
-    if (take) CU_TRY(cudaMemcpy(out, ctx->em_records + ctx->em_cursor * 10, (size_t)take * 10, cudaMemcpyDeviceToHost));
+    if (take) CU_TRY(cudaMemcpy(out, ctx->em_records + ctx->em_cursor * rs, (size_t)take * rs, cudaMemcpyDeviceToHost));
     ctx->em_cursor += take;
-    *written = (size_t)take * 10;
+    *written = (size_t)take * rs;
     return MFKC_OK;
 }
 
 extern "C" int mfkc_emit_device(mfkc_ctx *ctx, const uint64_t **d_keys, const uint16_t **d_counts, uint64_t *n) {
     if (!ctx) return MFKC_E_BADARG;
     if (!ctx->em_valid) return fail(ctx, MFKC_E_STATE, "mfkc_emit_device without mfkc_emit_begin");
+    if (ctx->k128) return fail(ctx, MFKC_E_STATE, "mfkc_emit_device serves 64-bit keys only");
     if (d_keys) *d_keys = reinterpret_cast<const uint64_t *>(ctx->em_keys);
     if (d_counts) *d_counts = ctx->em_counts;
     if (n) *n = ctx->em_n;
@@ -1082,6 +1157,7 @@ extern "C" uint32_t mfkc_owner_shard(uint64_t key, uint32_t n_shards) { return n
 extern "C" int mfkc_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t n_reads,
                                      uint64_t n_bases, uint64_t *d_keys_out, uint64_t cap_keys, uint64_t *bucket_counts) {
     if (!ctx || !d_bases || !d_offsets || !d_keys_out || !bucket_counts) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (ctx->k128) return fail(ctx, MFKC_E_STATE, "the shard exchange is not available for k > 31 yet");
     const uint32_t ns = ctx->cfg.n_shards > 1 ? (uint32_t)ctx->cfg.n_shards : 1u;
     CU_TRY(cudaSetDevice(ctx->device));
     Staging &s = ctx->st[0];
@@ -1123,6 +1199,7 @@ extern "C" int mfkc_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, cons
 extern "C" int mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uint64_t n) {
     if (!ctx || (!d_keys && n)) return fail(ctx, MFKC_E_BADARG, "null argument");
     if (ctx->cfg.variant == MFKC_VARIANT_SORT) return fail(ctx, MFKC_E_STATE, "mfkc_count_keys_device needs a hash variant");
+    if (ctx->k128) return fail(ctx, MFKC_E_STATE, "the shard exchange is not available for k > 31 yet");
     if (n == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(reserve_slots(ctx, n));
@@ -1159,6 +1236,7 @@ extern "C" int mfkc_skm_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, 
                                          uint64_t n_bases, void *d_recs_out, uint64_t seg_cap, uint64_t *rec_counts,
                                          uint64_t *kmer_counts) {
     if (!ctx || !d_bases || !d_offsets || !d_recs_out || !rec_counts || !kmer_counts) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (ctx->k128) return fail(ctx, MFKC_E_STATE, "the shard exchange is not available for k > 31 yet");
     const uint32_t ns = ctx->cfg.n_shards > 1 ? (uint32_t)ctx->cfg.n_shards : 1u;
     if (seg_cap == 0 || seg_cap > 0x7fffffffull) return fail(ctx, MFKC_E_BADARG, "bad segment capacity");
     CU_TRY(cudaSetDevice(ctx->device));
@@ -1207,7 +1285,7 @@ extern "C" int mfkc_skm_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, 
 // context's region staging; they are counted at the next drain (mfkc_flush at the latest).
 extern "C" int mfkc_skm_count_device(mfkc_ctx *ctx, const void *d_recs, uint64_t n_recs, uint64_t n_kmers) {
     if (!ctx || (!d_recs && n_recs)) return fail(ctx, MFKC_E_BADARG, "null argument");
-    if (ctx->cfg.variant != MFKC_VARIANT_HASH || !ctx->place) return fail(ctx, MFKC_E_STATE, "mfkc_skm_count_device needs the region-blocked hash variant");
+    if (ctx->cfg.variant != MFKC_VARIANT_HASH || !ctx->place || ctx->k128) return fail(ctx, MFKC_E_STATE, "mfkc_skm_count_device needs the region-blocked hash variant with k <= 31");
     if (n_recs == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(reserve_slots(ctx, n_kmers));
@@ -1243,6 +1321,7 @@ extern "C" int mfkc_skm_count_wait(mfkc_ctx *ctx) {
 // ------------------------------------------------------------------------------------------
 extern "C" int mfkc_fc_load_components(mfkc_ctx *ctx, const int64_t *keys, const uint64_t *comp_offsets, uint32_t n_comp) {
     if (!ctx || !comp_offsets || (n_comp && comp_offsets[n_comp] && !keys)) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (ctx->k128) return fail(ctx, MFKC_E_BADARG, "features-calculator works on 64-bit keys (k <= 31), like the reference");
     CU_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->compute;
     cudaFree(ctx->fc_tab); cudaFree(ctx->fc_keys); cudaFree(ctx->fc_off);

@@ -157,10 +157,28 @@ def test_bad_nucleotide_is_an_error(built):
 
 
 def test_bad_arguments(built):
-    for k in (0, -3, 32, 64):
+    for k in (0, -3, 64, 100):
         with pytest.raises(m.MfkcError) as e:
             m.KmerCounter(k)
         assert e.value.code == -1
+    for variant in (m.VARIANT_SORT, m.VARIANT_HASH_DIRECT):            # k > 31 exists for the default variant only
+        with pytest.raises(m.MfkcError):
+            m.KmerCounter(32, variant=variant)
+
+
+@pytest.mark.parametrize("k", [32, 33, 47, 48, 55, 62, 63])
+def test_long_kmers_128bit(built, k):
+    """32 <= k <= 63 (128-bit keys, 18-byte records): no reference behaviour exists
+    (KmersCounterMain.java:70-73); checked against the oracle's definition of the extension."""
+    rng = np.random.default_rng(500 + k)
+    genome = "".join(rng.choice(list("ACGT"), 6000))
+    reads = [genome[int(i):int(i) + int(L)] for i, L in zip(rng.integers(0, 5800, 1500), rng.integers(20, 200, 1500))]
+    reads += ["A" * 150, "T" * 150, "acgt" * 40, "AC" * 90, "G" * 64, "", "ACGT"]
+    rc = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    reads += ["".join(rc[c] for c in reversed(r.upper())) for r in reads[:200]]     # both strands -> same keys
+    check_against_oracle(reads, k, 0, m.VARIANT_HASH)
+    check_against_oracle(reads, k, 1, m.VARIANT_HASH, batches=5, table_slots=2048, region_shift=6)
+    check_against_oracle(reads, k, 2, m.VARIANT_HASH, min_len=100, batches=3, staging_bytes=32 * 50)
 
 
 def test_reset_between_samples(built):

@@ -9,9 +9,10 @@ variant = {"sort": m.VARIANT_SORT, "direct": m.VARIANT_HASH_DIRECT}.get(sys.argv
 batch = int(sys.argv[3]) if len(sys.argv) > 3 else 1_000_000
 hint = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 cfg = m.synth_cfg()
+KK = int(os.environ.get('MFKC_K', 31))
 stg = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 slots = int(sys.argv[6]) if len(sys.argv) > 6 else 0
-with m.KmerCounter(31, variant=variant, expected_distinct=hint, staging_bytes=stg, table_slots=slots) as kc:
+with m.KmerCounter(KK, variant=variant, expected_distinct=hint, staging_bytes=stg, table_slots=slots) as kc:
     for gb in ():
         for dep in (False, True):
             nupd = 1 << 29
