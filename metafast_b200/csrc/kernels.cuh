@@ -1299,7 +1299,28 @@ __global__ void __launch_bounds__(256)
 gups_kernel(unsigned long long *__restrict__ tab, uint64_t n_sectors, uint64_t n_updates, uint64_t seed, int mode,
             uint64_t window_sectors, uint32_t blocks_per_window) {
     unsigned long long sink = 0;
-    if (mode == 3) {
+    if (mode == 4 || mode == 5) {
+        // split layout experiment: keys (8 B) in the first half of the buffer, counts (4 B) in the second;
+        // windowed like mode 3.  mode 4: ld key + red count (different sectors); mode 5: ld key only + CAS key
+        const uint64_t n_slots = n_sectors * 2;                   // 16 B of buffer per slot: 8 B key + 4 B count (+4 unused)
+        unsigned long long *keys = tab;
+        unsigned int *counts = reinterpret_cast<unsigned int *>(tab + n_slots);
+        const uint64_t win_slots = window_sectors * 2;
+        const uint64_t n_windows = (n_slots + win_slots - 1) / win_slots;
+        const uint64_t per_block = n_updates / ((uint64_t)n_windows * blocks_per_window) + 1;
+        for (uint64_t win = blockIdx.x / blocks_per_window; win < n_windows; win += gridDim.x / blocks_per_window) {
+            const uint64_t w0 = win * win_slots;
+            const uint64_t wn = w0 + win_slots <= n_slots ? win_slots : n_slots - w0;
+            const uint64_t salt = (win * blocks_per_window + blockIdx.x % blocks_per_window) * per_block;
+            for (uint64_t i = threadIdx.x; i < per_block; i += blockDim.x) {
+                const uint64_t sl = w0 + mulhi64(mix64(salt + i + seed), wn);
+                unsigned long long v;
+                asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(keys + sl));
+                if (mode == 4) { if (v != 0x123456789ULL) atomicAdd(&counts[sl], 1u); else sink += v; }
+                else { if (v == 0) atomicCAS(&keys[sl], 0ull, sl + 1); else sink += v; }
+            }
+        }
+    } else if (mode == 3) {
         const uint64_t n_windows = (n_sectors + window_sectors - 1) / window_sectors;
         const uint64_t per_block = n_updates / ((uint64_t)n_windows * blocks_per_window) + 1;
         for (uint64_t win = blockIdx.x / blocks_per_window; win < n_windows; win += gridDim.x / blocks_per_window) {

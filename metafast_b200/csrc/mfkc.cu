@@ -1595,7 +1595,7 @@ extern "C" const char *mfkc_profile_name(int slot) { return slot >= 0 && slot < 
 
 extern "C" int mfkc_gups_ex(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, int mode, uint64_t window_bytes,
                             uint32_t blocks_per_window, float *ms) {
-    if (!ctx || !ms || bytes < 32 || mode < 0 || mode > 3) return MFKC_E_BADARG;
+    if (!ctx || !ms || bytes < 32 || mode < 0 || mode > 5) return MFKC_E_BADARG;
     CU_TRY(cudaSetDevice(ctx->device));
     unsigned long long *tab = nullptr;
     CU_TRY(cudaMalloc(&tab, bytes));
@@ -1606,7 +1606,7 @@ extern "C" int mfkc_gups_ex(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, i
     if (win == 0 || win > n_sectors) win = n_sectors;
     if (blocks_per_window == 0) blocks_per_window = 1;
     int grid = ctx->sm_count * 8;
-    if (mode == 3) {
+    if (mode >= 3) {
         grid = (int)std::min<uint64_t>((n_sectors + win - 1) / win * blocks_per_window, 1u << 30);
         if (grid < (int)blocks_per_window) grid = blocks_per_window;
         grid -= grid % blocks_per_window;
