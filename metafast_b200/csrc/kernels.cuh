@@ -130,6 +130,87 @@ __device__ __forceinline__ bool table_upsert_n(Slot *__restrict__ tab, uint64_t 
 }
 
 // ------------------------------------------------------------------------------------------
+// Split (structure-of-arrays) table of the region-blocked variant: keys[cap] (8 B) and counts[cap]
+// (4 B) in two arrays.  When every upsert hits L2, the 16-byte slot's "key and count share a
+// sector" rule buys nothing, and measured on B200 an 8-byte key load + red.add on a different
+// sector runs at 136 G upserts/s against 74-87 G/s for the 16-byte-slot pattern (mfkc_gups_ex
+// modes 4 vs 3).  Increments are blind red.adds (no count load); counts are clamped to 32767 when
+// read, and the host clamps the array between drains and keeps the k-mers of one drain below
+// 4.0e9, so the u32 can never wrap.  The direct variant keeps the 16-byte slots (one DRAM sector).
+// ------------------------------------------------------------------------------------------
+struct TabSoA {
+    unsigned long long *keys;
+    uint32_t *counts;
+    uint64_t cap;
+};
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ bool soa_upsert1_at(const TabSoA &t, uint64_t i, uint64_t key) {
+    for (;;) {
+        const unsigned long long cur = ld_cg_u64(&t.keys[i]);
+        if (cur == key) { atomicAdd(&t.counts[i], 1u); return false; }
+        if (cur == EMPTY_KEY) {
+            const unsigned long long prev = atomicCAS(&t.keys[i], EMPTY_KEY, (unsigned long long)key);
+            if (prev == EMPTY_KEY) { atomicAdd(&t.counts[i], 1u); return true; }
+            if (prev == key) { atomicAdd(&t.counts[i], 1u); return false; }
+        }
+        if (++i == t.cap) i = 0;
+    }
+}
+__device__ __forceinline__ bool soa_upsert_n_at(const TabSoA &t, uint64_t i, uint64_t key, uint32_t inc) {
+    bool claimed = false;
+    for (;;) {
+        unsigned long long cur = ld_cg_u64(&t.keys[i]);
+        if (cur == EMPTY_KEY) {
+            cur = atomicCAS(&t.keys[i], EMPTY_KEY, (unsigned long long)key);
+            if (cur == EMPTY_KEY) { claimed = true; cur = key; }
+        }
+        if (cur == key) {
+            uint32_t old = *(volatile uint32_t *)&t.counts[i];
+            for (;;) {
+                if (old >= MAX_COUNT) break;
+                uint32_t nv = old + inc; if (nv > MAX_COUNT || nv < old) nv = MAX_COUNT;
+                const uint32_t seen = atomicCAS(&t.counts[i], old, nv);
+                if (seen == old) break;
+                old = seen;
+            }
+            return claimed;
+        }
+        if (++i == t.cap) i = 0;
+    }
+}
+// counts[i] = min(counts[i], 32767): run between two drains (see above)
+__global__ void __launch_bounds__(256)
+soa_clamp_kernel(uint32_t *__restrict__ counts, uint64_t cap) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x)
+        if (counts[i] > MAX_COUNT) counts[i] = MAX_COUNT;
+}
+
+// table accessors so that the super-k-mer kernels can be instantiated for either layout
+struct TabAoS {
+    Slot *tab; uint64_t cap;
+    __device__ __forceinline__ bool upsert1_at(uint64_t i, uint64_t key) const { return table_upsert1_at(tab, cap, i, key); }
+    __device__ __forceinline__ void prefetch_region(uint64_t first_slot, int shift, uint32_t t, uint32_t nt) const {
+        const char *b = reinterpret_cast<const char *>(tab + first_slot);
+        const uint64_t bytes = sizeof(Slot) << shift;
+        for (uint64_t off = (uint64_t)t * 128; off < bytes; off += (uint64_t)nt * 128) prefetch_l2(b + off);
+    }
+};
+struct TabSoAOps {
+    TabSoA t;
+    __device__ __forceinline__ bool upsert1_at(uint64_t i, uint64_t key) const { return soa_upsert1_at(t, i, key); }
+    __device__ __forceinline__ void prefetch_region(uint64_t first_slot, int shift, uint32_t th, uint32_t nt) const {
+        const char *kb = reinterpret_cast<const char *>(t.keys + first_slot);
+        const char *cb = reinterpret_cast<const char *>(t.counts + first_slot);
+        for (uint64_t off = (uint64_t)th * 128; off < (8ull << shift); off += (uint64_t)nt * 128) prefetch_l2(kb + off);
+        for (uint64_t off = (uint64_t)th * 128; off < (4ull << shift); off += (uint64_t)nt * 128) prefetch_l2(cb + off);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
 // Minimizer placement (region-blocked variant).  The table is n_regions x 2^region_shift slots;
 // a k-mer lives in the region chosen by the smallest hash among its canonical m-mers
 // (m = min(k, 12)) and, inside the region, at mix64(key) mod 2^region_shift (linear probing may
@@ -446,7 +527,8 @@ extract_bucket_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const
 // A region segment that is full sends its keys straight to the table (slow but exact), so the
 // staging buffer never needs exact sizing.
 // ------------------------------------------------------------------------------------------
-constexpr int MAX_REGIONS = 2048;
+constexpr int MAX_REGIONS = 2048;          // single-key staging flavour (shared-memory histogram of the regions)
+constexpr int MAX_REGIONS_SKM = 65536;     // super-k-mer flavour (one cursor per region)
 constexpr int PT_THREADS = 512;
 
 struct RegionStage {
@@ -663,15 +745,15 @@ __device__ __forceinline__ uint32_t kmers_of_word(uint32_t w0, uint32_t w1, uint
                                                   long long limit, int k, uint64_t (&keys)[16]);
 
 // a record that found its region segment full: count its k-mers straight into the table
-__device__ __noinline__ uint32_t skm_count_direct(uint4 rec, uint32_t region, int region_shift, int k,
-                                                  Slot *__restrict__ tab, uint64_t cap) {
+template <class Tab>
+__device__ __noinline__ uint32_t skm_count_direct(uint4 rec, uint32_t region, int region_shift, int k, Tab tb) {
     uint64_t keys[16];
     const uint32_t len = (rec.z & 15u) + 1u;
     kmers_of_word(rec.x, rec.y, rec.z & ~15u, 0ull, 63, k, keys);
     uint32_t claimed = 0;
 #pragma unroll
     for (uint32_t t = 0; t < 16; t++)
-        if (t < len) claimed += table_upsert1_at(tab, cap, mini_home(keys[t], region, region_shift), keys[t]) ? 1u : 0u;
+        if (t < len) claimed += tb.upsert1_at(mini_home(keys[t], region, region_shift), keys[t]) ? 1u : 0u;
     return claimed;
 }
 
@@ -713,10 +795,10 @@ __device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32
 // BY_OWNER = true : bucket = owner shard (multi-GPU send buffer; st.n_regions = number of shards,
 //                   kmer_count[b] receives the k-mer instances sent to shard b; a full segment is
 //                   reported through the cursor overshoot and the caller retries with a smaller batch).
-template <bool BY_OWNER>
+template <bool BY_OWNER, class Tab>
 __global__ void __launch_bounds__(EX_THREADS)
 extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
-                   int k, SkmStage st, Slot *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr,
+                   int k, SkmStage st, Tab tb, Counters *__restrict__ ctr,
                    unsigned long long *__restrict__ kmer_count) {
     __shared__ uint32_t s_words[EX_THREADS + 2];
     __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
@@ -780,7 +862,7 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                                 st.recs[(uint64_t)bucket * st.seg_cap + pos[j]] = rec;
                                 if (BY_OWNER) atomicAdd(&kmer_count[bucket], (unsigned long long)len);
                             } else if (!BY_OWNER) {                 // segment full: count the run directly (slow, exact)
-                                claimed += skm_count_direct(rec, bucket, st.region_shift, k, tab, cap);
+                                claimed += skm_count_direct(rec, bucket, st.region_shift, k, tb);
                             }
                             in_run = false;
                         }
@@ -901,16 +983,16 @@ extract_skm_owner8_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, c
 
 // Receive side of the shard exchange: records that arrived from other GPUs are filed under the
 // table region of their minimizer (streaming: 16 B in, one cursor atomic, 16 B out).
+template <class Tab>
 __global__ void __launch_bounds__(256)
-skm_restage_kernel(const uint4 *__restrict__ in, uint64_t n, int k, SkmStage st, Slot *__restrict__ tab, uint64_t cap,
-                   Counters *__restrict__ ctr) {
+skm_restage_kernel(const uint4 *__restrict__ in, uint64_t n, int k, SkmStage st, Tab tb, Counters *__restrict__ ctr) {
     uint32_t claimed = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 rec = ld_nc_u128(&in[i]);
         const uint32_t region = region_of_minhash(rec.w, st.n_regions);
         const uint32_t pos = atomicAdd(&st.cursor[region], 1u);
         if (pos < st.seg_cap) st.recs[(uint64_t)region * st.seg_cap + pos] = rec;
-        else claimed += skm_count_direct(rec, region, st.region_shift, k, tab, cap);
+        else claimed += skm_count_direct(rec, region, st.region_shift, k, tb);
     }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
@@ -919,39 +1001,59 @@ skm_restage_kernel(const uint4 *__restrict__ in, uint64_t n, int k, SkmStage st,
 // Phase B for super-k-mer records: blocks_per_region consecutive CTAs own one region (CTAs start in
 // index order, so only a few regions are live in L2 at a time); a thread re-expands one record into
 // its canonical k-mers (funnel shift + rolled reverse complement) and upserts them into the region.
+template <class Tab>
 __global__ void __launch_bounds__(256)
-drain_skm_kernel(SkmStage st, uint32_t blocks_per_region, int k, Slot *__restrict__ tab, uint64_t cap,
-                 Counters *__restrict__ ctr) {
+drain_skm_kernel(SkmStage st, uint32_t blocks_per_region, int k, Tab tb, Counters *__restrict__ ctr) {
+    // Work-balanced expansion.  Records hold 1..16 k-mers (6 on average); expanding "one record per
+    // thread" leaves most lanes idle behind the longest record of the warp and serialises up to 16
+    // dependent load->atomic round trips.  Instead a warp takes 32 records, prefix-sums their lengths
+    // and deals the k-mer instances out evenly: every lane has one independent upsert per step.
+    __shared__ uint4 s_rec[8][32];
+    __shared__ uint32_t s_pre[8][33];
     const uint32_t region = blockIdx.x / blocks_per_region;
     const uint32_t sub = blockIdx.x % blocks_per_region;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t n = st.cursor[region];
     if (n > st.seg_cap) n = st.seg_cap;
     const uint4 *__restrict__ recs = st.recs + (uint64_t)region * st.seg_cap;
     const uint64_t region_base = (uint64_t)region << st.region_shift;
     const uint64_t slot_mask = (1ull << st.region_shift) - 1ull;
     const int rs = 64 - 2 * k;
-    const int top = 2 * k - 2;
     uint32_t claimed = 0;
-    for (uint64_t i = (uint64_t)sub * 256 + threadIdx.x; i < n; i += (uint64_t)blocks_per_region * 256) {
-        const uint4 r = ld_nc_u128(&recs[i]);
-        const uint32_t len = (r.z & 15u) + 1u;
-        const uint32_t w0 = r.x, w1 = r.y, w2 = r.z & ~15u;
-        uint64_t rc = 0;
+    for (uint64_t base = ((uint64_t)sub * 8 + warp) * 32; base < n; base += (uint64_t)blocks_per_region * 256) {
+        const uint64_t i = base + lane;
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t len = 0;
+        if (i < n) { r = ld_nc_u128(&recs[i]); len = (r.z & 15u) + 1u; }
+        uint32_t incl = len;
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            if ((uint32_t)j < len) {
-                const uint32_t hi = j ? __funnelshift_l(w1, w0, 2 * j) : w0;
-                const uint32_t lo = j ? __funnelshift_l(w2, w1, 2 * j) : w1;
-                const uint64_t fw = (((uint64_t)hi << 32) | lo) >> rs;
-                if (j == 0) rc = revcomp64(fw, k);
-                else rc = (rc >> 2) | ((uint64_t)((~(uint32_t)fw) & 3u) << top);
-                const uint64_t key = fw < rc ? fw : rc;
-                claimed += table_upsert1_at(tab, cap, region_base | (mix64(key) & slot_mask), key) ? 1u : 0u;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+        s_rec[warp][lane] = r;
+        s_pre[warp][lane + 1] = incl;
+        if (lane == 0) s_pre[warp][0] = 0;
+        __syncwarp();
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t t = lane; t < total; t += 32) {
+            uint32_t lo = 0, hi = 31;                       // largest record index with prefix <= t
+#pragma unroll
+            for (int step = 0; step < 5; step++) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (s_pre[warp][mid] <= t) lo = mid; else hi = mid - 1;
             }
+            const uint32_t off = t - s_pre[warp][lo];
+            const uint4 q = s_rec[warp][lo];
+            const uint32_t w2 = q.z & ~15u;
+            const uint32_t h32 = __funnelshift_l(q.y, q.x, 2 * off);
+            const uint32_t l32 = __funnelshift_l(w2, q.y, 2 * off);
+            const uint64_t fw = (((uint64_t)h32 << 32) | l32) >> rs;
+            const uint64_t rc = revcomp64(fw, k);
+            const uint64_t key = fw < rc ? fw : rc;
+            claimed += tb.upsert1_at(region_base | (mix64(key) & slot_mask), key) ? 1u : 0u;
         }
+        __syncwarp();
     }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
-    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+    if (lane == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
 
 // receive side of the shard exchange / generic "count these keys" (direct random upserts)
@@ -967,18 +1069,51 @@ count_keys_kernel(const unsigned long long *__restrict__ keys, uint64_t n, Slot 
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
 
+// SoA (minimizer-placed) flavours of the generic table kernels
+__global__ void __launch_bounds__(256)
+count_keys_soa_kernel(const unsigned long long *__restrict__ keys, uint64_t n, TabSoA tb, TableGeom g, Counters *__restrict__ ctr) {
+    uint32_t claimed = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[i];
+        claimed += soa_upsert1_at(tb, geom_home(g, key), key) ? 1u : 0u;
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+}
+__global__ void __launch_bounds__(256)
+rehash_soa_kernel(TabSoA old_t, TabSoA new_t, TableGeom g) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_t.cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = old_t.keys[i];
+        if (key != EMPTY_KEY) {
+            const uint32_t c = old_t.counts[i];
+            soa_upsert_n_at(new_t, geom_home(g, key), key, c < MAX_COUNT ? c : MAX_COUNT);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K4: histogram over ALL entries (src/io/IOUtils.java:59), filter count > b, compaction
 // ------------------------------------------------------------------------------------------
 constexpr int HIST_SMEM_BINS = 2048;
 
+// one slot as (key lo, key hi, count) whatever the layout
+template <bool SOA>
+__device__ __forceinline__ uint4 load_slot(const Slot *__restrict__ tab, const TabSoA &tb, uint64_t i) {
+    if (SOA) {
+        const unsigned long long k = tb.keys[i];
+        return make_uint4((uint32_t)k, (uint32_t)(k >> 32), tb.counts[i], 0u);
+    }
+    return ld_nc_u128(&tab[i]);
+}
+
+template <bool SOA>
 __global__ void __launch_bounds__(256)
-table_hist_kernel(const Slot *__restrict__ tab, uint64_t cap, unsigned long long *__restrict__ hist) {
+table_hist_kernel(const Slot *__restrict__ tab, TabSoA tb, uint64_t cap, unsigned long long *__restrict__ hist) {
     __shared__ uint32_t s_hist[HIST_SMEM_BINS];
     for (int i = threadIdx.x; i < HIST_SMEM_BINS; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 s = ld_nc_u128(&tab[i]);
+        const uint4 s = load_slot<SOA>(tab, tb, i);
         if ((s.x & s.y) != 0xFFFFFFFFu) {
             const uint32_t c = s.z < MAX_COUNT ? s.z : MAX_COUNT;
             if (c < HIST_SMEM_BINS) atomicAdd(&s_hist[c], 1u);
@@ -1021,8 +1156,9 @@ table_compact_kernel(const Slot *__restrict__ tab, uint64_t cap, uint32_t thresh
 // One pass over the table: histogram of ALL entries + compaction of the entries with
 // count > threshold.  Output positions are reserved with ONE global atomic per block iteration
 // (warp ballots -> shared prefix), so the cursor is not a serialisation point.
+template <bool SOA>
 __global__ void __launch_bounds__(256)
-table_scan_kernel(const Slot *__restrict__ tab, uint64_t cap, uint32_t threshold, unsigned long long *__restrict__ hist,
+table_scan_kernel(const Slot *__restrict__ tab, TabSoA tb, uint64_t cap, uint32_t threshold, unsigned long long *__restrict__ hist,
                   unsigned long long *__restrict__ out_keys, uint16_t *__restrict__ out_counts, uint64_t out_cap,
                   Counters *__restrict__ ctr) {
     constexpr int U = 8;                                   // slots per thread per round: 8 x 16 B in flight
@@ -1038,7 +1174,7 @@ table_scan_kernel(const Slot *__restrict__ tab, uint64_t cap, uint32_t threshold
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint64_t i = base + (uint64_t)u * 256 + threadIdx.x;
-            s[u] = i < cap ? ld_nc_u128(&tab[i]) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+            s[u] = i < cap ? load_slot<SOA>(tab, tb, i) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
         }
         uint32_t good_mask = 0;
 #pragma unroll

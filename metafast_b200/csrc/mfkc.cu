@@ -53,6 +53,8 @@ struct mfkc_ctx {
     // hash variant
     Slot *tab = nullptr; uint64_t cap = 0;
     Slot128 *tab128 = nullptr; bool k128 = false;   // 32 <= k <= 63: 128-bit keys, 32-byte slots (same cap / regions)
+    bool soa = false;                  // region-blocked super-k-mer path, k <= 31: keys[cap] + counts[cap] in ctx->tab
+    uint64_t kmers_since_drain = 0; uint32_t drains_since_clear = 0;
     uint64_t distinct_ub = 0;          // host-side upper bound of occupied slots
     uint64_t kmers_ub_total = 0;       // cumulative upper bound of submitted k-mer instances
     uint64_t max_table_bytes = 0;
@@ -194,24 +196,40 @@ static cudaError_t big_alloc(mfkc_ctx *ctx, void **p, size_t bytes) {
 
 // Round a requested capacity to whole regions: cap = n_regions << shift, n_regions <= MAX_REGIONS.
 static void plan_regions(const mfkc_ctx *ctx, uint64_t slots, uint64_t *cap, uint32_t *n_regions, int *shift) {
-    int sh = ctx->cfg.region_shift ? (int)ctx->cfg.region_shift : 19;
+    // default region: 2^17 slots (2 MiB of 16-byte slots).  Measured on cfg2: the drain time does not depend on the
+    // region size between 1 and 32 MiB (it is bound by the L2 load->atomic rate, not by capacity), while more,
+    // smaller regions spread the cursor atomics of the staging kernel (26.6 ms vs 31 ms at 8 MiB regions).
+    // The single-key staging flavour keeps a shared-memory histogram of the regions and is limited to MAX_REGIONS.
+    static const int env_shift = getenv("MFKC_REGION_SHIFT") ? atoi(getenv("MFKC_REGION_SHIFT")) : 0;
+    int sh = ctx->cfg.region_shift ? (int)ctx->cfg.region_shift : (env_shift ? env_shift : 17);
     if (slots < (1ull << sh) && !ctx->cfg.region_shift) { sh = 10; while ((1ull << sh) < slots) sh++; }
     uint64_t n = (slots + (1ull << sh) - 1) >> sh;
-    while (n > (uint64_t)MAX_REGIONS) { sh++; n = (slots + (1ull << sh) - 1) >> sh; }
+    const uint64_t max_regions = ctx->place ? (uint64_t)MAX_REGIONS_SKM : (uint64_t)MAX_REGIONS;
+    while (n > max_regions) { sh++; n = (slots + (1ull << sh) - 1) >> sh; }
     if (n < 1) n = 1;
     *cap = n << sh; *n_regions = (uint32_t)n; *shift = sh;
 }
 
-static size_t slot_bytes(const mfkc_ctx *ctx) { return ctx->k128 ? sizeof(Slot128) : sizeof(Slot); }
+static size_t slot_bytes(const mfkc_ctx *ctx) { return ctx->k128 ? sizeof(Slot128) : (ctx->soa ? 12 : sizeof(Slot)); }
+static TabSoA tab_soa_of(void *base, uint64_t cap) {
+    TabSoA t; t.keys = reinterpret_cast<unsigned long long *>(base); t.counts = reinterpret_cast<uint32_t *>(t.keys + cap); t.cap = cap; return t;
+}
+static TabSoA tab_soa(const mfkc_ctx *ctx) { return tab_soa_of(ctx->tab, ctx->cap); }
+static TabSoAOps tab_soa_ops(const mfkc_ctx *ctx) { TabSoAOps o; o.t = tab_soa(ctx); return o; }
+static TabAoS tab_aos(const mfkc_ctx *ctx) { TabAoS o; o.tab = ctx->tab; o.cap = ctx->cap; return o; }
 
-static int table_alloc(mfkc_ctx *ctx, uint64_t slots, Slot **out) {
+// plain_aos: a 16-byte-slot helper table (the --selected set) whatever the layout of the main table
+static int table_alloc(mfkc_ctx *ctx, uint64_t slots, Slot **out, bool plain_aos = false) {
     Slot *t = nullptr;
-    cudaError_t e = big_alloc(ctx, (void **)&t, slots * slot_bytes(ctx));
+    cudaError_t e = big_alloc(ctx, (void **)&t, slots * (plain_aos ? sizeof(Slot) : slot_bytes(ctx)));
     if (e != cudaSuccess) { ctx->err = "cannot allocate k-mer table"; return MFKC_E_OOM; }
     {
         ProfScope ps(ctx, P_CLEAR, ctx->compute);
         if (ctx->k128) table128_clear_kernel<<<grid_for(ctx, 2 * slots, 256, 16), 256, 0, ctx->compute>>>(reinterpret_cast<Slot128 *>(t), slots);
-        else table_clear_kernel<<<grid_for(ctx, slots, 256, 16), 256, 0, ctx->compute>>>(t, slots);
+        else if (ctx->soa && !plain_aos) {
+            cudaMemsetAsync(t, 0xFF, slots * 8, ctx->compute);                                         // keys = EMPTY
+            cudaMemsetAsync(reinterpret_cast<unsigned long long *>(t) + slots, 0, slots * 4, ctx->compute);   // counts = 0
+        } else table_clear_kernel<<<grid_for(ctx, slots, 256, 16), 256, 0, ctx->compute>>>(t, slots);
     }
     CU_TRY(cudaGetLastError());
     *out = t;
@@ -294,6 +312,8 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
         const char *sm = getenv("MFKC_STAGE");            // 0 = stage single keys (hash placement), default = super-k-mers
         ctx->place = (sm && atoi(sm) == 0) ? 0 : 1;
         if (cfg->k > 31) { ctx->place = 1; ctx->k128 = true; }
+        // MFKC_SOA=1: experimental split key/count layout (faster in the microbenchmark, slower in the real drain)
+        { const char *so = getenv("MFKC_SOA"); ctx->soa = ctx->place == 1 && !ctx->k128 && so && atoi(so) == 1; }
     }
     if (cfg->variant != MFKC_VARIANT_SORT) {
         uint64_t slots = cfg->table_slots;
@@ -308,8 +328,8 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
         if (r != MFKC_OK) return bail(r);
         ctx->cap = slots;
         ctx->tab128 = reinterpret_cast<Slot128 *>(ctx->tab);
-        CR_TRY(cudaMalloc(&ctx->rb_cursor, MAX_REGIONS * sizeof(unsigned int)));
-        CR_TRY(cudaMemset(ctx->rb_cursor, 0, MAX_REGIONS * sizeof(unsigned int)));
+        CR_TRY(cudaMalloc(&ctx->rb_cursor, MAX_REGIONS_SKM * sizeof(unsigned int)));
+        CR_TRY(cudaMemset(ctx->rb_cursor, 0, MAX_REGIONS_SKM * sizeof(unsigned int)));
         ctx->rb_cap_max = (uint64_t)(total_b * 0.25) / 8;
     }
     CR_TRY(cudaDeviceSynchronize());
@@ -359,17 +379,50 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     delete ctx;
 }
 
+// kmer-counter-many runs many samples of one study through the same context: size the next sample's table
+// from what the previous one needed (its distinct count at load ~0.4) unless the caller fixed the size.
+// A denser table is not only smaller to clear and scan: the region-blocked drain touches fewer sectors per
+// k-mer and keeps a higher L2 hit rate.
+static int resize_for_next_sample(mfkc_ctx *ctx) {
+    if (ctx->cfg.variant == MFKC_VARIANT_SORT || ctx->cfg.table_slots || !ctx->tab) return MFKC_OK;
+    static const bool off = getenv("MFKC_NO_RESIZE") != nullptr;
+    if (off) return MFKC_OK;
+    if (read_counters(ctx) != MFKC_OK) return MFKC_OK;
+    const uint64_t distinct = ctx->h_ctr->distinct;
+    if (distinct < (1u << 20)) return MFKC_OK;
+    uint64_t want = (uint64_t)((double)distinct * 1.25 / 0.5);
+    if ((double)ctx->cap <= 1.5 * (double)want && (double)ctx->cap >= 0.8 * (double)want) return MFKC_OK;
+    uint32_t nr = 1; int sh = 19;
+    plan_regions(ctx, want, &want, &nr, &sh);
+    if (want * slot_bytes(ctx) > ctx->max_table_bytes) return MFKC_OK;
+    CU_TRY(cudaFree(ctx->tab));
+    ctx->tab = nullptr; ctx->tab128 = nullptr; ctx->cap = 0;
+    Slot *nt = nullptr;
+    int r = table_alloc(ctx, want, &nt);
+    if (r != MFKC_OK) {                                   // should not happen (smaller than what was just freed)
+        plan_regions(ctx, 1ull << 22, &want, &nr, &sh);
+        TRY(table_alloc(ctx, want, &nt));
+    }
+    ctx->tab = nt; ctx->tab128 = reinterpret_cast<Slot128 *>(nt); ctx->cap = want; ctx->n_regions = nr; ctx->region_shift = sh;
+    return MFKC_OK;
+}
+
 extern "C" int mfkc_reset(mfkc_ctx *ctx) {
     if (!ctx) return MFKC_E_BADARG;
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(sync_all(ctx));
+    TRY(resize_for_next_sample(ctx));
     if (ctx->tab) {
         ProfScope ps(ctx, P_CLEAR, ctx->compute);
         if (ctx->k128) table128_clear_kernel<<<grid_for(ctx, 2 * ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab128, ctx->cap);
-        else table_clear_kernel<<<grid_for(ctx, ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap);
+        else if (ctx->soa) {
+            CU_TRY(cudaMemsetAsync(ctx->tab, 0xFF, ctx->cap * 8, ctx->compute));
+            CU_TRY(cudaMemsetAsync(tab_soa(ctx).counts, 0, ctx->cap * 4, ctx->compute));
+        } else table_clear_kernel<<<grid_for(ctx, ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap);
     }
+    ctx->kmers_since_drain = 0; ctx->drains_since_clear = 0;
     CU_TRY(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->compute));
-    if (ctx->rb_cursor) CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS * sizeof(unsigned int), ctx->compute));
+    if (ctx->rb_cursor) CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS_SKM * sizeof(unsigned int), ctx->compute));
     CU_TRY(cudaStreamSynchronize(ctx->compute));
     ctx->staged_ub = 0;
     ctx->distinct_base = ctx->kmers_base = ctx->recv_since_base = 0;
@@ -460,7 +513,8 @@ static int grow_table(mfkc_ctx *ctx, uint64_t need_slots) {
             rehash128_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(ctx->tab128, ctx->cap, reinterpret_cast<Slot128 *>(nt), ng);
         } else {
             TableGeom ng; ng.cap = new_cap; ng.n_regions = nr; ng.region_shift = sh; ng.k = ctx->cfg.k; ng.minimizer = ctx->place;
-            rehash_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap, nt, ng);
+            if (ctx->soa) rehash_soa_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(tab_soa(ctx), tab_soa_of(nt, new_cap), ng);
+            else rehash_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap, nt, ng);
         }
     }
     CU_TRY(cudaGetLastError());
@@ -559,21 +613,26 @@ static int drain_regions(mfkc_ctx *ctx) {
             const uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 4 / 512));
             drain_skm128_kernel<<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(skm_stage128(ctx), bpr, ctx->cfg.k, ctx->tab128, ctx->cap, ctx->d_ctr);
         } else if (ctx->place) {
-            const uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 2 / 512));
-            drain_skm_kernel<<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(skm_stage(ctx), bpr, ctx->cfg.k, ctx->tab, ctx->cap, ctx->d_ctr);
+            static const int env_bpr = getenv("MFKC_BPR") ? atoi(getenv("MFKC_BPR")) : 0;
+            uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 2 / 512));
+            if (env_bpr > 0 && per_region / 2 > 256) bpr = (uint32_t)env_bpr;
+            if (ctx->soa && ctx->drains_since_clear)       // keep the blind u32 increments from ever wrapping (see TabSoA)
+                soa_clamp_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(tab_soa(ctx).counts, ctx->cap);
+            if (ctx->soa) drain_skm_kernel<TabSoAOps><<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(skm_stage(ctx), bpr, ctx->cfg.k, tab_soa_ops(ctx), ctx->d_ctr);
+            else drain_skm_kernel<TabAoS><<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(skm_stage(ctx), bpr, ctx->cfg.k, tab_aos(ctx), ctx->d_ctr);
         } else {
             const uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 2048));
             drain_regions_kernel<<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(region_stage(ctx), bpr, ctx->tab, ctx->cap, ctx->d_ctr);
         }
     }
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS * sizeof(unsigned int), ctx->compute));
+    CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS_SKM * sizeof(unsigned int), ctx->compute));
     // distinct is exact for everything submitted so far once this point of the stream is reached
     CU_TRY(cudaMemcpyAsync(ctx->h_drain_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
     CU_TRY(cudaEventRecord(ctx->ev_drain, ctx->compute));
     ctx->drain_pending = true;
     ctx->kmers_at_drain = ctx->kmers_ub_total;
-    ctx->staged_ub = 0;
+    ctx->staged_ub = 0; ctx->kmers_since_drain = 0; ctx->drains_since_clear++;
     return MFKC_OK;
 }
 
@@ -584,7 +643,7 @@ static int reserve_staging(mfkc_ctx *ctx, uint64_t add_kmers) {
     if (!ctx->rb_keys) {
         uint64_t want = ctx->cfg.staging_bytes ? ctx->cfg.staging_bytes / 8 : std::max<uint64_t>(4 * add, 1ull << 22);
         if (!ctx->cfg.staging_bytes && ctx->cfg.expected_kmers)
-            want = std::max<uint64_t>(want, stage_units(ctx, ctx->cfg.expected_kmers + ctx->cfg.expected_kmers / 50) + (uint64_t)MAX_REGIONS * 64);
+            want = std::max<uint64_t>(want, stage_units(ctx, ctx->cfg.expected_kmers + ctx->cfg.expected_kmers / 50) + (uint64_t)MAX_REGIONS_SKM * 64);
         if (!ctx->cfg.staging_bytes && want > ctx->rb_cap_max) want = std::max<uint64_t>(ctx->rb_cap_max, add);
         if (!ctx->cfg.staging_bytes && want > ctx->rb_cap_max) want = std::max<uint64_t>(ctx->rb_cap_max, add);
         if (want < add) want = add;
@@ -661,7 +720,10 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
     const uint64_t kmers_ub = n_bases >= (uint64_t)k ? n_bases - k + 1 : 0;
     if (ctx->cfg.variant == MFKC_VARIANT_SORT) TRY(sort_variant_reserve(ctx, kmers_ub));
     else TRY(reserve_slots(ctx, kmers_ub));
-    if (ctx->cfg.variant == MFKC_VARIANT_HASH) { TRY(reserve_staging(ctx, kmers_ub)); ctx->staged_ub += stage_units(ctx, kmers_ub); }
+    if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
+        if (ctx->soa && ctx->kmers_since_drain + kmers_ub > 4000000000ull) TRY(drain_regions(ctx));    // u32 counts cannot wrap
+        TRY(reserve_staging(ctx, kmers_ub)); ctx->staged_ub += stage_units(ctx, kmers_ub); ctx->kmers_since_drain += kmers_ub;
+    }
     ctx->kmers_ub_total += kmers_ub;
     TRY(launch_mark(ctx, s, d_offsets, n_reads, n_bases, ctx->cfg.min_seq_len, 1, ctx->d_ctr));
     if (n_bases >= (uint64_t)k) {
@@ -672,8 +734,10 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
                 extract_skm128_kernel<<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
                     d_bases, n_bases, s.d_flags, k, skm_stage128(ctx), ctx->tab128, ctx->cap, ctx->d_ctr);
             } else if (ctx->place) {          // super-k-mer records, minimizer placement
-                extract_skm_kernel<false><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
-                    d_bases, n_bases, s.d_flags, k, skm_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr, nullptr);
+                if (ctx->soa) extract_skm_kernel<false, TabSoAOps><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                    d_bases, n_bases, s.d_flags, k, skm_stage(ctx), tab_soa_ops(ctx), ctx->d_ctr, nullptr);
+                else extract_skm_kernel<false, TabAoS><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                    d_bases, n_bases, s.d_flags, k, skm_stage(ctx), tab_aos(ctx), ctx->d_ctr, nullptr);
             } else if (stage_mode == 0) {     // single keys, shared-memory histogram flavour
                 const uint64_t tiles = ((n_bases + 15) / 16 + PT_THREADS - 1) / PT_THREADS;
                 const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->sm_count * 2);
@@ -934,7 +998,8 @@ static int compute_hist(mfkc_ctx *ctx) {
         if (ctx->k128)
             table128_scan_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, st>>>(ctx->tab128, ctx->cap, 0xFFFFFFFFu, ctx->d_hist, nullptr, nullptr, 0, ctx->d_ctr);
         else if (ctx->cfg.variant != MFKC_VARIANT_SORT)
-            table_hist_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, st>>>(ctx->tab, ctx->cap, ctx->d_hist);
+            if (ctx->soa) table_hist_kernel<true><<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, st>>>(nullptr, tab_soa(ctx), ctx->cap, ctx->d_hist);
+            else table_hist_kernel<false><<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, st>>>(ctx->tab, TabSoA{nullptr, nullptr, 0}, ctx->cap, ctx->d_hist);
         else if (ctx->svs_n)
             pairs_hist_kernel<<<grid_for(ctx, ctx->svs_n, 256, 8), 256, 0, st>>>(ctx->svs_counts, ctx->svs_n, ctx->d_hist);
     }
@@ -1062,8 +1127,8 @@ extern "C" int mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_goo
             CU_TRY(cudaMemsetAsync(&ctx->d_ctr->n_good, 0, sizeof(unsigned long long), st));
             {
                 ProfScope ps(ctx, P_COMPACT, st);
-                table_scan_kernel<<<grid_for(ctx, (ctx->cap + 7) / 8, 256, 8), 256, 0, st>>>(
-                    ctx->tab, ctx->cap, thr_u, ctx->d_hist, k1, c1, distinct, ctx->d_ctr);
+                if (ctx->soa) table_scan_kernel<true><<<grid_for(ctx, (ctx->cap + 7) / 8, 256, 8), 256, 0, st>>>(nullptr, tab_soa(ctx), ctx->cap, thr_u, ctx->d_hist, k1, c1, distinct, ctx->d_ctr);
+                else table_scan_kernel<false><<<grid_for(ctx, (ctx->cap + 7) / 8, 256, 8), 256, 0, st>>>(ctx->tab, TabSoA{nullptr, nullptr, 0}, ctx->cap, thr_u, ctx->d_hist, k1, c1, distinct, ctx->d_ctr);
             }
             CU_TRY(cudaGetLastError());
             CU_TRY(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, MFKC_HIST_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -1216,8 +1281,14 @@ extern "C" int mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uin
             reinterpret_cast<const unsigned long long *>(d_keys), n, region_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr);
     } else {
         ProfScope ps(ctx, P_COUNT_KEYS, ctx->compute);
-        count_keys_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->compute>>>(
-            reinterpret_cast<const unsigned long long *>(d_keys), n, ctx->tab, table_geom(ctx), ctx->d_ctr);
+        if (ctx->soa) {
+            if (ctx->kmers_since_drain + n > 4000000000ull) TRY(drain_regions(ctx));
+            ctx->kmers_since_drain += n;
+            count_keys_soa_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->compute>>>(
+                reinterpret_cast<const unsigned long long *>(d_keys), n, tab_soa(ctx), table_geom(ctx), ctx->d_ctr);
+        } else
+            count_keys_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->compute>>>(
+                reinterpret_cast<const unsigned long long *>(d_keys), n, ctx->tab, table_geom(ctx), ctx->d_ctr);
     }
     CU_TRY(cudaGetLastError());
     if (ctx->cfg.variant == MFKC_VARIANT_HASH_DIRECT)
@@ -1262,8 +1333,8 @@ extern "C" int mfkc_skm_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, 
             extract_skm_owner8_kernel<<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
                 d_bases, n_bases, s.d_flags, k, st, ctx->d_ctr, d_kc);
         else
-            extract_skm_kernel<true><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
-                d_bases, n_bases, s.d_flags, k, st, nullptr, 0, ctx->d_ctr, d_kc);
+            extract_skm_kernel<true, TabAoS><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                d_bases, n_bases, s.d_flags, k, st, TabAoS{nullptr, 0}, ctx->d_ctr, d_kc);
     }
     CU_TRY(cudaGetLastError());
     unsigned int h_cur[64];
@@ -1289,6 +1360,8 @@ extern "C" int mfkc_skm_count_device(mfkc_ctx *ctx, const void *d_recs, uint64_t
     if (n_recs == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(reserve_slots(ctx, n_kmers));
+    if (ctx->soa && ctx->kmers_since_drain + n_kmers > 4000000000ull) TRY(drain_regions(ctx));
+    ctx->kmers_since_drain += n_kmers;
     // reserve staging by records (2 units each), not by the k-mer estimate
     {
         const uint64_t units = 2 * n_recs;
@@ -1299,8 +1372,10 @@ extern "C" int mfkc_skm_count_device(mfkc_ctx *ctx, const void *d_recs, uint64_t
     {
         // on the aux stream: the next round's extraction (compute stream) overlaps this kernel
         ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->aux);
-        skm_restage_kernel<<<grid_for(ctx, n_recs, 256, 4), 256, 0, ctx->aux>>>(
-            reinterpret_cast<const uint4 *>(d_recs), n_recs, ctx->cfg.k, skm_stage(ctx), ctx->tab, ctx->cap, ctx->d_ctr);
+        if (ctx->soa) skm_restage_kernel<TabSoAOps><<<grid_for(ctx, n_recs, 256, 4), 256, 0, ctx->aux>>>(
+            reinterpret_cast<const uint4 *>(d_recs), n_recs, ctx->cfg.k, skm_stage(ctx), tab_soa_ops(ctx), ctx->d_ctr);
+        else skm_restage_kernel<TabAoS><<<grid_for(ctx, n_recs, 256, 4), 256, 0, ctx->aux>>>(
+            reinterpret_cast<const uint4 *>(d_recs), n_recs, ctx->cfg.k, skm_stage(ctx), tab_aos(ctx), ctx->d_ctr);
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(ctx->ev_aux, ctx->aux));
@@ -1378,7 +1453,7 @@ extern "C" int mfkc_fc_set_selected(mfkc_ctx *ctx, const uint8_t *be_records, ui
     const uint64_t need = (ctx->fc_sel_n + n_records) * 2 + 1024;
     if (need > ctx->fc_sel_cap) {
         Slot *nt = nullptr;
-        TRY(table_alloc(ctx, need, &nt));
+        TRY(table_alloc(ctx, need, &nt, true));
         if (ctx->fc_sel) {
             TableGeom pg; pg.cap = need; pg.n_regions = 1; pg.region_shift = 0; pg.k = ctx->cfg.k; pg.minimizer = 0;
             rehash_kernel<<<grid_for(ctx, ctx->fc_sel_cap, 256, 8), 256, 0, st>>>(ctx->fc_sel, ctx->fc_sel_cap, nt, pg);
