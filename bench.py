@@ -52,6 +52,19 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic():
+    """DRAM bytes (read + write) of the counting kernels per step, from the committed ncu --set full capture
+    (profiles/r1_traffic.json: 20 extract_skm launches + the drain of one cfg2 step); None if absent or if the
+    run is not the configuration the capture was taken on."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if N_READS != 20_000_000 or os.environ.get("MFKC_BENCH_VARIANT") or not os.path.exists(p):
+        return None
+    try:
+        return float(json.load(open(p))["per_step_bytes"]["total_counting"])
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------ clocks under load
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -304,9 +317,10 @@ def main():
     gups_rate = (1 << 28) / (gups_ms / 1e3)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": load_traffic(), "peak_source": peak_src,
         "kernel": "+".join(count_kernels), "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER,
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
+        "kernel_launches_per_step": {k: v[1] / args.steps for k, v in prof.items() if v[1]},
         "gups_random_sector_upserts_per_s": gups_rate,
         "gups_algorithmic_gbs": gups_rate * 64 / 1e9,
         "frac_of_gups": (kmers_per_step / (t_count_ms / 1e3)) / gups_rate if t_count_ms else None,

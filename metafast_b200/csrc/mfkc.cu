@@ -722,7 +722,11 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
     else TRY(reserve_slots(ctx, kmers_ub));
     if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
         if (ctx->soa && ctx->kmers_since_drain + kmers_ub > 4000000000ull) TRY(drain_regions(ctx));    // u32 counts cannot wrap
-        TRY(reserve_staging(ctx, kmers_ub)); ctx->staged_ub += stage_units(ctx, kmers_ub); ctx->kmers_since_drain += kmers_ub;
+        // staging is sized by an ESTIMATE (a full segment only costs speed): bases - reads*(k-1) is exact when
+        // every read is at least k-1 long, and 25 % tighter than the guaranteed bound on 150 bp reads
+        uint64_t kmers_est = n_bases >= (uint64_t)n_reads * (uint64_t)(k - 1) ? n_bases - (uint64_t)n_reads * (uint64_t)(k - 1) : 0;
+        kmers_est = std::max<uint64_t>(kmers_est, kmers_ub / 4);
+        TRY(reserve_staging(ctx, kmers_est)); ctx->staged_ub += stage_units(ctx, kmers_est); ctx->kmers_since_drain += kmers_ub;
     }
     ctx->kmers_ub_total += kmers_ub;
     TRY(launch_mark(ctx, s, d_offsets, n_reads, n_bases, ctx->cfg.min_seq_len, 1, ctx->d_ctr));
