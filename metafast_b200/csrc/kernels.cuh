@@ -225,6 +225,12 @@ __host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {       // Murmu
     x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
     return x;
 }
+// order of the m-mers inside a k-mer: a bijective multiply-xorshift (3 instructions; the minimizer
+// only needs a fixed pseudo-random ORDER, the spreading over regions / shards re-mixes with fmix32)
+__host__ __device__ __forceinline__ uint32_t mmer_hash(uint32_t x) {
+    x *= 0x9E3779B1u;
+    return x ^ (x >> 15);
+}
 __host__ __device__ __forceinline__ uint32_t region_of_minhash(uint32_t mh, uint32_t n_regions) {
     return (uint32_t)(((uint64_t)hash32(mh ^ 0x7f4a7c15u) * n_regions) >> 32);
 }
@@ -241,7 +247,7 @@ __host__ __device__ __forceinline__ uint32_t minhash_of_key(uint64_t key, int k)
         const uint32_t c = (uint32_t)(key >> (2 * (k - 1 - i))) & 3u;
         fw = ((fw << 2) | c) & mask;
         rc = (rc >> 2) | ((3u - c) << (2 * m - 2));
-        if (i >= m - 1) { const uint32_t h = hash32(fw < rc ? fw : rc); best = h < best ? h : best; }
+        if (i >= m - 1) { const uint32_t h = mmer_hash(fw < rc ? fw : rc); best = h < best ? h : best; }
     }
     return best;
 }
@@ -757,7 +763,28 @@ __device__ __noinline__ uint32_t skm_count_direct(uint4 rec, uint32_t region, in
     return claimed;
 }
 
-// minimizer hash of each of the 16 k-mers that start in word 0 of the 48-base window
+// minimizer hash of each of the 16 k-mers that start in word 0 of the 48-base window.
+// h[q] = hash of the canonical m-mer at base offset q; window of k-mer j = h[j .. j+w-1], w = k-m+1.
+// For w >= 16 (k >= 27) every window contains h[j..15] and h[16..w-1], so
+//   min(window j) = min(suffix[j], middle, prefix[j])   (van Herk / Gil-Werman split at 15|16)
+// costs ~70 min operations instead of 16 x w; the split needs w at compile time, hence the dispatch.
+template <int W>
+__device__ __forceinline__ void window_mins_static(const uint32_t (&h)[36], uint32_t (&mh)[16]) {
+    uint32_t suf[16];
+    uint32_t run = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 15; j >= 0; j--) { run = min(run, h[j]); suf[j] = run; }
+    uint32_t mid = 0xFFFFFFFFu;
+#pragma unroll
+    for (int q = 16; q < W; q++) mid = min(mid, h[q]);
+    run = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (j) run = min(run, h[W - 1 + j]);
+        mh[j] = min(min(suf[j], mid), run);
+    }
+}
+
 __device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32_t w2, int k, uint32_t (&mh)[16]) {
     const int m = minimizer_len(k);
     const int w = k - m + 1;                              // m-mers per k-mer, <= 20
@@ -779,13 +806,21 @@ __device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32
         } else {
             rc = (rc >> 2) | (((~fw) & 3u) << top);
         }
-        h[q] = hash32(fw < rc ? fw : rc);
+        h[q] = mmer_hash(fw < rc ? fw : rc);
+    }
+    switch (w) {                                          // uniform branch
+        case 20: window_mins_static<20>(h, mh); return;   // k = 31
+        case 19: window_mins_static<19>(h, mh); return;
+        case 18: window_mins_static<18>(h, mh); return;
+        case 17: window_mins_static<17>(h, mh); return;
+        case 16: window_mins_static<16>(h, mh); return;
+        default: break;
     }
 #pragma unroll
     for (int j = 0; j < 16; j++) {
         uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
-        for (int q = 0; q < 20; q++) if (q < w) best = min(best, h[j + q]);
+        for (int q = 0; q < 15; q++) if (q < w) best = min(best, h[j + q]);
         mh[j] = best;
     }
 }
@@ -827,6 +862,9 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                 // Two passes over the same state machine: pass 1 issues every cursor atomic of the
                 // thread back to back (their ~1 us round trips overlap), pass 2 writes the records.
                 auto bucket_of = [&](uint32_t mhv, uint32_t key) { return BY_OWNER ? owner_of_minhash(mhv, st.n_regions) : key; };
+                uint32_t rkey[16];                                  // run key of every start position, computed once
+#pragma unroll
+                for (int j = 0; j < 16; j++) rkey[j] = BY_OWNER ? mh[j] : region_of_minhash(mh[j], st.n_regions);
                 uint32_t pos[17];
                 {
                     uint32_t run_key = 0, run_mh = 0;
@@ -835,7 +873,7 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                     for (int j = 0; j <= 16; j++) {
                         const bool v = j < 16 && ((valid >> j) & 1);
                         const uint32_t mhj = mh[j < 16 ? j : 15];
-                        const uint32_t key = !v ? 0xFFFFFFFFu : (BY_OWNER ? mhj : region_of_minhash(mhj, st.n_regions));
+                        const uint32_t key = rkey[j < 16 ? j : 15];
                         pos[j] = 0;
                         if (in_run && (!v || key != run_key)) { pos[j] = atomicAdd(&st.cursor[bucket_of(run_mh, run_key)], 1u); in_run = false; }
                         if (v && !in_run) { in_run = true; run_key = key; run_mh = mhj; }
@@ -848,7 +886,7 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                     for (int j = 0; j <= 16; j++) {
                         const bool v = j < 16 && ((valid >> j) & 1);
                         const uint32_t mhj = mh[j < 16 ? j : 15];
-                        const uint32_t key = !v ? 0xFFFFFFFFu : (BY_OWNER ? mhj : region_of_minhash(mhj, st.n_regions));
+                        const uint32_t key = rkey[j < 16 ? j : 15];
                         if (in_run && (!v || key != run_key)) {
                             const uint32_t len = (uint32_t)j - run_start;
                             const int sh = 2 * (int)run_start;      // normalise: first base of the run -> base 0

@@ -3,7 +3,7 @@
 // The reference stops at k = 31 (src/tools/KmersCounterMain.java:70-73); this is the natural
 // extension SURVEY.md 8c defines: key = min(fw, rc) as unsigned 2k-bit integers in the same
 // A0 G1 C2 T3 encoding, first base most significant; record = 16-byte BE key + 2-byte BE count.
-// Validated against the repository's own oracle only (oracle/oracle.py, Python ints) -- parity
+// Validated against the Python-int restatement kept with the tests only -- parity
 // unpinned.  Same design as the 64-bit path: super-k-mer staging by minimizer region, L2-resident
 // drain, 128-bit atomicCAS (ATOMG.E.CAS.128) to claim a slot.
 #pragma once
@@ -80,7 +80,7 @@ __device__ __forceinline__ uint32_t minhash_of_key128(K128 key, int k) {
         const uint32_t c = (uint32_t)(sh >= 64 ? key.hi >> (sh - 64) : key.lo >> sh) & 3u;
         fw = ((fw << 2) | c) & mask;
         rc = (rc >> 2) | ((3u - c) << (2 * m - 2));
-        if (i >= m - 1) { const uint32_t h = hash32(fw < rc ? fw : rc); best = h < best ? h : best; }
+        if (i >= m - 1) { const uint32_t h = mmer_hash(fw < rc ? fw : rc); best = h < best ? h : best; }
     }
     return best;
 }
@@ -221,7 +221,7 @@ __device__ __forceinline__ void minhash128_of_word(const uint32_t (&w5)[5], int 
         uint32_t x = __brev(fw);
         x = ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
         const uint32_t rc = (~x) >> rs;
-        return hash32(fw < rc ? fw : rc);
+        return mmer_hash(fw < rc ? fw : rc);
     };
     uint32_t suf[16];
     uint32_t run = 0xFFFFFFFFu;
