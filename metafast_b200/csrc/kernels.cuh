@@ -130,6 +130,58 @@ __device__ __forceinline__ bool table_upsert_n(Slot *__restrict__ tab, uint64_t 
 }
 
 // ------------------------------------------------------------------------------------------
+// Windowed placement (tables drained in shared memory, see drain_smem_kernel).  With small regions
+// (2^12 slots) the minimizer skew makes some regions overfull, and linear probing that runs on into
+// the neighbouring regions would cascade.  So a key lives either
+//   (1) in its PRIMARY window: the first `win` slots from its home slot, wrapping inside its region, or
+//   (2) if that window held `win` other keys when it arrived, at its SECONDARY position: ordinary
+//       linear probing over the whole table from home_slot(key ^ SALT), i.e. in the free slots of
+//       uniformly chosen regions.
+// Slots never become empty again, so the rule is stable: a key that went to (2) finds its primary
+// window full for ever, and a key placed in (1) is met before any empty slot of its window.
+// win == 0 selects the plain rule (linear probing from the home slot, running on).
+// ------------------------------------------------------------------------------------------
+constexpr unsigned long long SECONDARY_SALT = 0x9ddfea08eb382d69ULL;
+__device__ __forceinline__ uint64_t secondary_home(uint64_t key, uint64_t cap) { return home_slot(key ^ SECONDARY_SALT, cap); }
+
+template <bool ONE>
+__device__ __forceinline__ bool placed_upsert_at(Slot *__restrict__ tab, uint64_t cap, int shift, uint32_t win,
+                                                 uint64_t home, uint64_t key, uint32_t inc) {
+    if (win) {
+        const uint64_t mask = (1ull << shift) - 1ull;
+        const uint64_t rbase = home & ~mask;
+        uint64_t off = home & mask;
+        const uint32_t steps = (uint64_t)win < mask + 1 ? win : (uint32_t)(mask + 1);
+        for (uint32_t st = 0; st < steps; st++, off = (off + 1) & mask) {
+            const uint64_t i = rbase | off;
+            const ulonglong2 sl = ld_cg_u64x2(&tab[i]);
+            unsigned long long cur = sl.x;
+            bool claimed = false;
+            if (cur == EMPTY_KEY) {
+                cur = atomicCAS(&tab[i].key, EMPTY_KEY, (unsigned long long)key);
+                if (cur == EMPTY_KEY) { claimed = true; cur = key; }
+            }
+            if (cur == key) {
+                if (ONE) { if (claimed || (uint32_t)sl.y < MAX_COUNT) atomicAdd(&tab[i].count, 1u); }
+                else {
+                    uint32_t old = *(volatile uint32_t *)&tab[i].count;
+                    for (;;) {
+                        if (old >= MAX_COUNT) break;
+                        uint32_t nv = old + inc; if (nv > MAX_COUNT || nv < old) nv = MAX_COUNT;
+                        const uint32_t seen = atomicCAS(&tab[i].count, old, nv);
+                        if (seen == old) break;
+                        old = seen;
+                    }
+                }
+                return claimed;
+            }
+        }
+        home = secondary_home(key, cap);
+    }
+    return ONE ? table_upsert1_at(tab, cap, home, key) : table_upsert_n_at(tab, cap, home, key, inc);
+}
+
+// ------------------------------------------------------------------------------------------
 // Split (structure-of-arrays) table of the region-blocked variant: keys[cap] (8 B) and counts[cap]
 // (4 B) in two arrays.  When every upsert hits L2, the 16-byte slot's "key and count share a
 // sector" rule buys nothing, and measured on B200 an 8-byte key load + red.add on a different
@@ -192,7 +244,8 @@ soa_clamp_kernel(uint32_t *__restrict__ counts, uint64_t cap) {
 // table accessors so that the super-k-mer kernels can be instantiated for either layout
 struct TabAoS {
     Slot *tab; uint64_t cap;
-    __device__ __forceinline__ bool upsert1_at(uint64_t i, uint64_t key) const { return table_upsert1_at(tab, cap, i, key); }
+    // shift / win: region size and primary window of the windowed placement (win = 0: plain rule), see placed_upsert_at
+    __device__ __forceinline__ bool upsert1_at(uint64_t i, uint64_t key, int shift, uint32_t win) const { return placed_upsert_at<true>(tab, cap, shift, win, i, key, 1u); }
     __device__ __forceinline__ void prefetch_region(uint64_t first_slot, int shift, uint32_t t, uint32_t nt) const {
         const char *b = reinterpret_cast<const char *>(tab + first_slot);
         const uint64_t bytes = sizeof(Slot) << shift;
@@ -201,7 +254,7 @@ struct TabAoS {
 };
 struct TabSoAOps {
     TabSoA t;
-    __device__ __forceinline__ bool upsert1_at(uint64_t i, uint64_t key) const { return soa_upsert1_at(t, i, key); }
+    __device__ __forceinline__ bool upsert1_at(uint64_t i, uint64_t key, int, uint32_t) const { return soa_upsert1_at(t, i, key); }
     __device__ __forceinline__ void prefetch_region(uint64_t first_slot, int shift, uint32_t th, uint32_t nt) const {
         const char *kb = reinterpret_cast<const char *>(t.keys + first_slot);
         const char *cb = reinterpret_cast<const char *>(t.counts + first_slot);
@@ -270,6 +323,7 @@ struct TableGeom {
     int region_shift;
     int k;
     int minimizer;          // 1: minimizer placement, 0: plain hash placement
+    uint32_t win;           // > 0: windowed placement (placed_upsert_at)
 };
 __device__ __forceinline__ uint64_t geom_home(const TableGeom &g, uint64_t key) {
     if (!g.minimizer) return home_slot(key, g.cap);
@@ -281,7 +335,7 @@ rehash_kernel(const Slot *__restrict__ old_tab, uint64_t old_cap, Slot *__restri
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_cap; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 s = ld_nc_u128(&old_tab[i]);
         const unsigned long long key = ((unsigned long long)s.y << 32) | s.x;
-        if (key != EMPTY_KEY) table_upsert_n_at(new_tab, g.cap, geom_home(g, key), key, s.z < MAX_COUNT ? s.z : MAX_COUNT);
+        if (key != EMPTY_KEY) placed_upsert_at<false>(new_tab, g.cap, g.region_shift, g.minimizer ? g.win : 0u, geom_home(g, key), key, s.z < MAX_COUNT ? s.z : MAX_COUNT);
     }
 }
 
@@ -534,7 +588,7 @@ extract_bucket_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const
 // staging buffer never needs exact sizing.
 // ------------------------------------------------------------------------------------------
 constexpr int MAX_REGIONS = 2048;          // single-key staging flavour (shared-memory histogram of the regions)
-constexpr int MAX_REGIONS_SKM = 65536;     // super-k-mer flavour (one cursor per region)
+constexpr int MAX_REGIONS_SKM = 1 << 22;   // super-k-mer flavour (one cursor per region; 2^22 regions of 2^12 slots = 256 GiB)
 constexpr int PT_THREADS = 512;
 
 struct RegionStage {
@@ -745,6 +799,7 @@ struct SkmStage {
     uint64_t seg_cap;             // records per region, < 2^31
     uint32_t n_regions;
     int region_shift;
+    uint32_t win;                 // primary window of the windowed placement (0 = plain linear probing), see placed_upsert_at
 };
 
 __device__ __forceinline__ uint32_t kmers_of_word(uint32_t w0, uint32_t w1, uint32_t w2, uint64_t flag_bits,
@@ -752,14 +807,21 @@ __device__ __forceinline__ uint32_t kmers_of_word(uint32_t w0, uint32_t w1, uint
 
 // a record that found its region segment full: count its k-mers straight into the table
 template <class Tab>
-__device__ __noinline__ uint32_t skm_count_direct(uint4 rec, uint32_t region, int region_shift, int k, Tab tb) {
-    uint64_t keys[16];
+__device__ __noinline__ uint32_t skm_count_direct(uint4 rec, uint32_t region, int region_shift, uint32_t win, int k, Tab tb) {
+    // rare path: rolled loop, no register arrays (its register need adds to the calling kernel's)
     const uint32_t len = (rec.z & 15u) + 1u;
-    kmers_of_word(rec.x, rec.y, rec.z & ~15u, 0ull, 63, k, keys);
+    const uint32_t w2 = rec.z & ~15u;
+    const int rs = 64 - 2 * k;
     uint32_t claimed = 0;
-#pragma unroll
-    for (uint32_t t = 0; t < 16; t++)
-        if (t < len) claimed += tb.upsert1_at(mini_home(keys[t], region, region_shift), keys[t]) ? 1u : 0u;
+#pragma unroll 1
+    for (uint32_t t = 0; t < len; t++) {
+        const uint32_t h32 = __funnelshift_l(rec.y, rec.x, 2 * t);
+        const uint32_t l32 = __funnelshift_l(w2, rec.y, 2 * t);
+        const uint64_t fw = (((uint64_t)h32 << 32) | l32) >> rs;
+        const uint64_t rc = revcomp64(fw, k);
+        const uint64_t key = fw < rc ? fw : rc;
+        claimed += tb.upsert1_at(mini_home(key, region, region_shift), key, region_shift, win) ? 1u : 0u;
+    }
     return claimed;
 }
 
@@ -900,7 +962,7 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                                 st.recs[(uint64_t)bucket * st.seg_cap + pos[j]] = rec;
                                 if (BY_OWNER) atomicAdd(&kmer_count[bucket], (unsigned long long)len);
                             } else if (!BY_OWNER) {                 // segment full: count the run directly (slow, exact)
-                                claimed += skm_count_direct(rec, bucket, st.region_shift, k, tb);
+                                claimed += skm_count_direct(rec, bucket, st.region_shift, st.win, k, tb);
                             }
                             in_run = false;
                         }
@@ -1030,35 +1092,22 @@ skm_restage_kernel(const uint4 *__restrict__ in, uint64_t n, int k, SkmStage st,
         const uint32_t region = region_of_minhash(rec.w, st.n_regions);
         const uint32_t pos = atomicAdd(&st.cursor[region], 1u);
         if (pos < st.seg_cap) st.recs[(uint64_t)region * st.seg_cap + pos] = rec;
-        else claimed += skm_count_direct(rec, region, st.region_shift, k, tb);
+        else claimed += skm_count_direct(rec, region, st.region_shift, st.win, k, tb);
     }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
 
-// Phase B for super-k-mer records: blocks_per_region consecutive CTAs own one region (CTAs start in
-// index order, so only a few regions are live in L2 at a time); a thread re-expands one record into
-// its canonical k-mers (funnel shift + rolled reverse complement) and upserts them into the region.
-template <class Tab>
-__global__ void __launch_bounds__(256)
-drain_skm_kernel(SkmStage st, uint32_t blocks_per_region, int k, Tab tb, Counters *__restrict__ ctr) {
-    // Work-balanced expansion.  Records hold 1..16 k-mers (6 on average); expanding "one record per
-    // thread" leaves most lanes idle behind the longest record of the warp and serialises up to 16
-    // dependent load->atomic round trips.  Instead a warp takes 32 records, prefix-sums their lengths
-    // and deals the k-mer instances out evenly: every lane has one independent upsert per step.
-    __shared__ uint4 s_rec[8][32];
-    __shared__ uint32_t s_pre[8][33];
-    const uint32_t region = blockIdx.x / blocks_per_region;
-    const uint32_t sub = blockIdx.x % blocks_per_region;
+// Phase B for super-k-mer records, L2 flavour: blocks_per_region consecutive CTAs own one region (CTAs
+// start in index order, so only a few regions are live in L2 at a time); the k-mer instances of 32 records
+// are dealt out evenly over the lanes of a warp (records hold 1..16 k-mers, 6 on average) and every lane
+// upserts one instance per step with global atomics.  `put(home_slot, key)` is the table operation.
+template <class Put>
+__device__ __forceinline__ void skm_expand_records(const uint4 *__restrict__ recs, uint64_t n, uint64_t first, uint64_t stride,
+                                                   int k, uint4 (*s_rec)[32], uint32_t (*s_pre)[33], Put put) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t n = st.cursor[region];
-    if (n > st.seg_cap) n = st.seg_cap;
-    const uint4 *__restrict__ recs = st.recs + (uint64_t)region * st.seg_cap;
-    const uint64_t region_base = (uint64_t)region << st.region_shift;
-    const uint64_t slot_mask = (1ull << st.region_shift) - 1ull;
     const int rs = 64 - 2 * k;
-    uint32_t claimed = 0;
-    for (uint64_t base = ((uint64_t)sub * 8 + warp) * 32; base < n; base += (uint64_t)blocks_per_region * 256) {
+    for (uint64_t base = first + (uint64_t)warp * 32; base < n; base += stride) {
         const uint64_t i = base + lane;
         uint4 r = make_uint4(0u, 0u, 0u, 0u);
         uint32_t len = 0;
@@ -1085,13 +1134,167 @@ drain_skm_kernel(SkmStage st, uint32_t blocks_per_region, int k, Tab tb, Counter
             const uint32_t l32 = __funnelshift_l(w2, q.y, 2 * off);
             const uint64_t fw = (((uint64_t)h32 << 32) | l32) >> rs;
             const uint64_t rc = revcomp64(fw, k);
-            const uint64_t key = fw < rc ? fw : rc;
-            claimed += tb.upsert1_at(region_base | (mix64(key) & slot_mask), key) ? 1u : 0u;
+            put(fw < rc ? fw : rc);
         }
         __syncwarp();
     }
+}
+
+template <class Tab>
+__global__ void __launch_bounds__(256)
+drain_skm_kernel(SkmStage st, uint32_t blocks_per_region, int k, Tab tb, Counters *__restrict__ ctr) {
+    __shared__ uint4 s_rec[8][32];
+    __shared__ uint32_t s_pre[8][33];
+    const uint32_t region = blockIdx.x / blocks_per_region;
+    const uint32_t sub = blockIdx.x % blocks_per_region;
+    uint64_t n = st.cursor[region];
+    if (n > st.seg_cap) n = st.seg_cap;
+    const uint64_t region_base = (uint64_t)region << st.region_shift;
+    const uint64_t slot_mask = (1ull << st.region_shift) - 1ull;
+    uint32_t claimed = 0;
+    skm_expand_records(st.recs + (uint64_t)region * st.seg_cap, n, (uint64_t)sub * 256, (uint64_t)blocks_per_region * 256, k, s_rec, s_pre,
+                       [&](uint64_t key) { claimed += tb.upsert1_at(region_base | (mix64(key) & slot_mask), key, st.region_shift, st.win) ? 1u : 0u; });
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
-    if (lane == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+}
+
+// ------------------------------------------------------------------------------------------
+// Phase B, shared-memory flavour (default for k <= 31): regions are small enough (<= 2^13 slots,
+// 2^12 = 64 KiB by default) for ONE CTA to hold the whole region of the table in shared memory.
+// The CTA streams the region in (coalesced 16-byte loads), expands the region's super-k-mer records
+// and upserts them with shared-memory atomics (no L2 round trip per k-mer), then streams the region
+// back.  HBM sees pure streaming traffic: the table once in and once out per drain, the records once.
+//
+// Placement is the windowed rule of placed_upsert_at: a k-mer whose primary window (SMEM_WIN slots,
+// wrapping inside the region) is full of other keys belongs at its secondary position somewhere else
+// in the table, which this CTA cannot touch.  Such instances are SPILLED: up to SMEM_SPILL_MAX keys
+// per CTA go to a global list; a CTA with more (an overfull region: minimizer skew) commits what it
+// counted and reports the region as DIRTY instead.  drain_fallback_kernel, launched right behind on
+// the same stream, upserts the listed keys at their secondary positions and re-expands the records
+// of dirty regions: an instance whose key now sits in its primary window was counted here (a window
+// never gets free slots back, so either all instances of a key were counted in shared memory or
+// none), every other instance goes to the secondary position.  Skew costs speed, never results.
+// ------------------------------------------------------------------------------------------
+constexpr int SMEM_MAX_SHIFT = 13;
+constexpr uint32_t SMEM_SPILL_MAX = 256;       // spilled instances a CTA may list
+constexpr uint32_t SMEM_WIN = 64;              // primary window of the windowed placement
+
+struct SpillBuf {
+    unsigned long long *keys;   // spilled instances (their secondary position derives from the key)
+    unsigned int *cursor;       // entries used
+    unsigned int *n_dirty;
+    uint32_t *dirty;            // region ids, n_regions entries
+    uint32_t cap;
+};
+
+__global__ void __launch_bounds__(256, 3)
+drain_smem_kernel(SkmStage st, int k, Slot *__restrict__ tab, SpillBuf sp, Counters *__restrict__ ctr) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint4 *s_tab = reinterpret_cast<uint4 *>(smem_raw);                       // the region: x,y = key, z = count
+    const uint32_t S = 1u << st.region_shift;
+    unsigned long long *s_spill = reinterpret_cast<unsigned long long *>(s_tab + S);
+    __shared__ uint4 s_rec[8][32];
+    __shared__ uint32_t s_pre[8][33];
+    __shared__ uint32_t s_nspill, s_claimed, s_base;
+    __shared__ int s_mode;                            // 0: no spills, 1: spills listed, 2: region dirty
+    const uint32_t region = blockIdx.x, tid = threadIdx.x;
+    uint64_t n = st.cursor[region];
+    if (n == 0) return;
+    if (n > st.seg_cap) n = st.seg_cap;
+    const uint64_t region_base = (uint64_t)region << st.region_shift;
+    uint4 *__restrict__ g_tab = reinterpret_cast<uint4 *>(tab + region_base);
+    for (uint32_t i = tid; i < S; i += 256) s_tab[i] = ld_nc_u128(&g_tab[i]);
+    if (tid == 0) { s_nspill = 0; s_claimed = 0; }
+    __syncthreads();
+
+    uint32_t claimed = 0;
+    const uint32_t slot_mask = S - 1u;
+    const uint32_t win = SMEM_WIN < S ? SMEM_WIN : S;
+    skm_expand_records(st.recs + (uint64_t)region * st.seg_cap, n, 0, 256, k, s_rec, s_pre, [&](uint64_t key) {
+        const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+        uint32_t i = (uint32_t)mix64(key) & slot_mask;
+        for (uint32_t step = 0; step < win; step++, i = (i + 1) & slot_mask) {
+            const uint4 v = s_tab[i];
+            if (v.x == klo && v.y == khi) { if (v.z < MAX_COUNT) atomicAdd(&s_tab[i].z, 1u); return; }
+            if ((v.x & v.y) == 0xFFFFFFFFu) {
+                const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&s_tab[i]), EMPTY_KEY, (unsigned long long)key);
+                if (prev == EMPTY_KEY) { atomicAdd(&s_tab[i].z, 1u); claimed++; return; }
+                if (prev == key) { atomicAdd(&s_tab[i].z, 1u); return; }
+            }
+        }
+        const uint32_t at = atomicAdd(&s_nspill, 1u);
+        if (at < SMEM_SPILL_MAX) s_spill[at] = key;
+    });
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if ((tid & 31) == 0 && claimed) atomicAdd(&s_claimed, claimed);
+    __syncthreads();
+
+    if (tid == 0) {
+        const uint32_t ns = s_nspill;
+        int mode = ns ? 2 : 0;
+        uint32_t base = 0;
+        if (ns && ns <= SMEM_SPILL_MAX) {             // reserve room in the global list (all or nothing)
+            unsigned int old = *(volatile unsigned int *)sp.cursor;
+            for (;;) {
+                if (old + ns > sp.cap) break;
+                const unsigned int seen = atomicCAS(sp.cursor, old, old + ns);
+                if (seen == old) { base = old; mode = 1; break; }
+                old = seen;
+            }
+        }
+        if (mode == 2) sp.dirty[atomicAdd(sp.n_dirty, 1u)] = region;
+        else st.cursor[region] = 0;
+        if (s_claimed) atomicAdd(&ctr->distinct, (unsigned long long)s_claimed);
+        s_mode = mode; s_base = base;
+    }
+    __syncthreads();
+    if (s_mode == 1) { const uint32_t ns = s_nspill; for (uint32_t i = tid; i < ns; i += 256) sp.keys[s_base + i] = s_spill[i]; }
+    for (uint32_t i = tid; i < S; i += 256) {
+        uint4 v = s_tab[i];
+        if (v.z > MAX_COUNT) v.z = MAX_COUNT;
+        g_tab[i] = v;
+    }
+}
+
+// Runs right after drain_smem_kernel on the same stream (every region is back in HBM): listed spills
+// go to their secondary positions; the records of dirty regions are expanded again and the instances
+// that were NOT counted in shared memory (key absent from its primary window) follow them.
+__global__ void __launch_bounds__(256)
+drain_fallback_kernel(SkmStage st, int k, Slot *__restrict__ tab, uint64_t cap, SpillBuf sp, Counters *__restrict__ ctr) {
+    __shared__ uint4 s_rec[8][32];
+    __shared__ uint32_t s_pre[8][33];
+    uint32_t claimed = 0;
+    uint32_t ns = *sp.cursor;
+    if (ns > sp.cap) ns = sp.cap;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < ns; i += gridDim.x * 256) {
+        const unsigned long long key = sp.keys[i];
+        claimed += table_upsert1_at(tab, cap, secondary_home(key, cap), key) ? 1u : 0u;
+    }
+    const uint32_t nd = *sp.n_dirty;
+    const uint64_t slot_mask = (1ull << st.region_shift) - 1ull;
+    const uint32_t win = (uint64_t)SMEM_WIN < slot_mask + 1 ? SMEM_WIN : (uint32_t)(slot_mask + 1);
+    for (uint32_t f = blockIdx.x; f < nd; f += gridDim.x) {
+        const uint32_t region = sp.dirty[f];
+        uint64_t n = st.cursor[region];
+        if (n > st.seg_cap) n = st.seg_cap;
+        const uint64_t region_base = (uint64_t)region << st.region_shift;
+        skm_expand_records(st.recs + (uint64_t)region * st.seg_cap, n, 0, 256, k, s_rec, s_pre, [&](uint64_t key) {
+            uint64_t off = mix64(key) & slot_mask;
+            for (uint32_t step = 0; step < win; step++, off = (off + 1) & slot_mask) {
+                const unsigned long long cur = ld_cg_u64x2(&tab[region_base | off]).x;
+                if (cur == key) return;                               // counted in shared memory
+                if (cur == EMPTY_KEY) {                               // cannot happen after a drain; stay exact anyway
+                    claimed += placed_upsert_at<true>(tab, cap, st.region_shift, SMEM_WIN, region_base | off, key, 1u) ? 1u : 0u;
+                    return;
+                }
+            }
+            claimed += table_upsert1_at(tab, cap, secondary_home(key, cap), key) ? 1u : 0u;
+        });
+        __syncthreads();
+        if (threadIdx.x == 0) st.cursor[region] = 0;
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
 
 // receive side of the shard exchange / generic "count these keys" (direct random upserts)
@@ -1101,7 +1304,7 @@ count_keys_kernel(const unsigned long long *__restrict__ keys, uint64_t n, Slot 
     uint32_t claimed = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const unsigned long long key = keys[i];
-        claimed += table_upsert1_at(tab, g.cap, geom_home(g, key), key) ? 1u : 0u;
+        claimed += placed_upsert_at<true>(tab, g.cap, g.region_shift, g.minimizer ? g.win : 0u, geom_home(g, key), key, 1u) ? 1u : 0u;
     }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);

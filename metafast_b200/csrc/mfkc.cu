@@ -29,6 +29,8 @@ static const char *kProfNames[P_NSLOTS] = {
 
 struct PendingTiming { int slot; cudaEvent_t a, b; };
 
+static constexpr int N_STAGE = 4;
+
 struct Staging {
     uint8_t *d_bases = nullptr; size_t cap_bases = 0;
     uint64_t *d_offsets = nullptr; size_t cap_offsets = 0;
@@ -44,7 +46,8 @@ struct mfkc_ctx {
     mfkc_cfg cfg{};
     int device = 0, sm_count = 148;
     std::string err;
-    Staging st[2];                     // copy streams + staging buffers (double-buffered H2D)
+    Staging st[N_STAGE];               // copy streams + staging buffers: the H2D copies run up to N_STAGE batches ahead
+                                       // of the kernels (a drain on the compute stream must not stall the copy engine)
     cudaStream_t compute = nullptr;    // every kernel runs here, in submission order ...
     cudaStream_t aux = nullptr;        // ... except the receive side of the shard exchange, which overlaps the next extraction
     cudaEvent_t ev_aux = nullptr; bool aux_pending = false;
@@ -55,6 +58,8 @@ struct mfkc_ctx {
     Slot128 *tab128 = nullptr; bool k128 = false;   // 32 <= k <= 63: 128-bit keys, 32-byte slots (same cap / regions)
     bool soa = false;                  // region-blocked super-k-mer path, k <= 31: keys[cap] + counts[cap] in ctx->tab
     uint64_t kmers_since_drain = 0; uint32_t drains_since_clear = 0;
+    bool host_fed = false;            // the current sample arrives through mfkc_submit_reads (host buffers)
+    uint64_t prev_sample_kmers = 0;   // k-mer instances of the previous sample of this context (drain cadence without hints)
     uint64_t distinct_ub = 0;          // host-side upper bound of occupied slots
     uint64_t kmers_ub_total = 0;       // cumulative upper bound of submitted k-mer instances
     uint64_t max_table_bytes = 0;
@@ -65,6 +70,9 @@ struct mfkc_ctx {
     uint64_t staged_ub = 0;            // upper bound of keys staged since the last drain
     uint32_t n_regions = 1; int region_shift = 19;
     int place = 0;                     // 1: minimizer placement + super-k-mer staging (default for MFKC_VARIANT_HASH)
+    bool smem_drain = false;           // regions of <= 2^13 slots drained in shared memory (drain_smem_kernel)
+    unsigned long long *sp_ent = nullptr; unsigned int *sp_cursor = nullptr; uint32_t *sp_failed = nullptr;   // spill buffer of the smem drain
+    uint32_t sp_cap = 0, sp_failed_cap = 0;
     cudaEvent_t ev_drain = nullptr; bool drain_pending = false; uint64_t kmers_at_drain = 0;
     // tight bound for the region-blocked variant: exact values at the last synchronisation point
     uint64_t distinct_base = 0, kmers_base = 0, recv_since_base = 0;
@@ -155,11 +163,11 @@ static int grid_for(const mfkc_ctx *ctx, uint64_t work_items, int threads, int b
 }
 
 static int sync_all(mfkc_ctx *ctx) {
-    CU_TRY(cudaStreamSynchronize(ctx->st[0].stream));
-    CU_TRY(cudaStreamSynchronize(ctx->st[1].stream));
+    for (int i = 0; i < N_STAGE; i++) CU_TRY(cudaStreamSynchronize(ctx->st[i].stream));
     CU_TRY(cudaStreamSynchronize(ctx->aux));
     CU_TRY(cudaStreamSynchronize(ctx->compute));
-    ctx->st[0].pending = ctx->st[1].pending = false; ctx->drain_pending = false; ctx->aux_pending = false;
+    for (int i = 0; i < N_STAGE; i++) ctx->st[i].pending = false;
+    ctx->drain_pending = false; ctx->aux_pending = false;
     return MFKC_OK;
 }
 
@@ -201,8 +209,8 @@ static void plan_regions(const mfkc_ctx *ctx, uint64_t slots, uint64_t *cap, uin
     // smaller regions spread the cursor atomics of the staging kernel (26.6 ms vs 31 ms at 8 MiB regions).
     // The single-key staging flavour keeps a shared-memory histogram of the regions and is limited to MAX_REGIONS.
     static const int env_shift = getenv("MFKC_REGION_SHIFT") ? atoi(getenv("MFKC_REGION_SHIFT")) : 0;
-    int sh = ctx->cfg.region_shift ? (int)ctx->cfg.region_shift : (env_shift ? env_shift : 17);
-    if (slots < (1ull << sh) && !ctx->cfg.region_shift) { sh = 10; while ((1ull << sh) < slots) sh++; }
+    int sh = ctx->cfg.region_shift ? (int)ctx->cfg.region_shift : (env_shift ? env_shift : (ctx->smem_drain ? 12 : 17));
+    if (slots < (1ull << sh) && !ctx->cfg.region_shift && !ctx->smem_drain) { sh = 10; while ((1ull << sh) < slots) sh++; }
     uint64_t n = (slots + (1ull << sh) - 1) >> sh;
     const uint64_t max_regions = ctx->place ? (uint64_t)MAX_REGIONS_SKM : (uint64_t)MAX_REGIONS;
     while (n > max_regions) { sh++; n = (slots + (1ull << sh) - 1) >> sh; }
@@ -216,6 +224,7 @@ static TabSoA tab_soa_of(void *base, uint64_t cap) {
 }
 static TabSoA tab_soa(const mfkc_ctx *ctx) { return tab_soa_of(ctx->tab, ctx->cap); }
 static TabSoAOps tab_soa_ops(const mfkc_ctx *ctx) { TabSoAOps o; o.t = tab_soa(ctx); return o; }
+static uint32_t table_win(const mfkc_ctx *ctx) { return ctx->smem_drain && ctx->place && !ctx->k128 ? SMEM_WIN : 0u; }
 static TabAoS tab_aos(const mfkc_ctx *ctx) { TabAoS o; o.tab = ctx->tab; o.cap = ctx->cap; return o; }
 
 // plain_aos: a 16-byte-slot helper table (the --selected set) whatever the layout of the main table
@@ -264,7 +273,7 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     cudaDeviceProp prop;
     CR_TRY(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->sm_count = prop.multiProcessorCount;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < N_STAGE; i++) {
         CR_TRY(cudaStreamCreateWithFlags(&ctx->st[i].stream, cudaStreamNonBlocking));
         CR_TRY(cudaEventCreateWithFlags(&ctx->st[i].ev_copy, cudaEventDisableTiming));
         CR_TRY(cudaEventCreateWithFlags(&ctx->st[i].ev_done, cudaEventDisableTiming));
@@ -314,6 +323,11 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
         if (cfg->k > 31) { ctx->place = 1; ctx->k128 = true; }
         // MFKC_SOA=1: experimental split key/count layout (faster in the microbenchmark, slower in the real drain)
         { const char *so = getenv("MFKC_SOA"); ctx->soa = ctx->place == 1 && !ctx->k128 && so && atoi(so) == 1; }
+        // MFKC_DRAIN=smem: regions small enough (2^12 slots) for one CTA to drain them in shared memory, windowed
+        // placement (drain_smem_kernel).  Measured on cfg2 it does not beat the L2-resident drain yet.
+        { const char *dm = getenv("MFKC_DRAIN");
+          ctx->smem_drain = ctx->place == 1 && !ctx->k128 && !ctx->soa && dm && !strcmp(dm, "smem") &&
+                            (cfg->region_shift == 0 || (int)cfg->region_shift <= SMEM_MAX_SHIFT); }
     }
     if (cfg->variant != MFKC_VARIANT_SORT) {
         uint64_t slots = cfg->table_slots;
@@ -331,6 +345,14 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
         CR_TRY(cudaMalloc(&ctx->rb_cursor, MAX_REGIONS_SKM * sizeof(unsigned int)));
         CR_TRY(cudaMemset(ctx->rb_cursor, 0, MAX_REGIONS_SKM * sizeof(unsigned int)));
         ctx->rb_cap_max = (uint64_t)(total_b * 0.25) / 8;
+        if (ctx->smem_drain) {
+            ctx->sp_cap = 1u << 22;                                     // 4 M spilled instances per drain (64 MiB)
+            CR_TRY(cudaMalloc(&ctx->sp_ent, (size_t)ctx->sp_cap * sizeof(unsigned long long)));
+            CR_TRY(cudaMalloc(&ctx->sp_cursor, 2 * sizeof(unsigned int)));
+            CR_TRY(cudaMemset(ctx->sp_cursor, 0, 2 * sizeof(unsigned int)));
+            CR_TRY(cudaFuncSetAttribute(drain_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((16u << SMEM_MAX_SHIFT) + SMEM_SPILL_MAX * sizeof(unsigned long long))));
+        }
     }
     CR_TRY(cudaDeviceSynchronize());
 #undef CR_TRY
@@ -350,7 +372,7 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     cudaDeviceSynchronize();
     for (auto &p : ctx->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < N_STAGE; i++) {
         Staging &s = ctx->st[i];
         cudaFree(s.d_bases); cudaFree(s.d_offsets); cudaFree(s.d_flags);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -363,6 +385,7 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); ctx->aux = nullptr; }
     if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
     cudaFree(ctx->rb_keys); cudaFree(ctx->rb_cursor);
+    cudaFree(ctx->sp_ent); cudaFree(ctx->sp_cursor); cudaFree(ctx->sp_failed);
     cudaFree(ctx->tab); cudaFree(ctx->sv_keys); cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts);
     cudaFree(ctx->d_bucket_cursor); cudaFree(ctx->d_bucket_base);
     if (ctx->h_bucket) cudaFreeHost(ctx->h_bucket);
@@ -390,7 +413,11 @@ static int resize_for_next_sample(mfkc_ctx *ctx) {
     if (read_counters(ctx) != MFKC_OK) return MFKC_OK;
     const uint64_t distinct = ctx->h_ctr->distinct;
     if (distinct < (1u << 20)) return MFKC_OK;
-    uint64_t want = (uint64_t)((double)distinct * 1.25 / 0.5);
+    // load 0.4 for device-resident input; host-fed samples get more room (load 0.29): their drains are asynchronous and
+    // the bound of reserve_slots must hold with a distinct-count snapshot that lags one drain behind (see count_batch_device)
+    static const double env_factor = getenv("MFKC_RESIZE_FACTOR") ? atof(getenv("MFKC_RESIZE_FACTOR")) : 0.0;
+    const double factor = env_factor > 0 ? env_factor : (ctx->host_fed ? 3.5 : 2.5);
+    uint64_t want = (uint64_t)((double)distinct * factor);
     if ((double)ctx->cap <= 1.5 * (double)want && (double)ctx->cap >= 0.8 * (double)want) return MFKC_OK;
     uint32_t nr = 1; int sh = 19;
     plan_regions(ctx, want, &want, &nr, &sh);
@@ -421,9 +448,10 @@ extern "C" int mfkc_reset(mfkc_ctx *ctx) {
         } else table_clear_kernel<<<grid_for(ctx, ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap);
     }
     ctx->kmers_since_drain = 0; ctx->drains_since_clear = 0;
+    if (ctx->kmers_ub_total) ctx->prev_sample_kmers = ctx->kmers_ub_total;
     CU_TRY(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->compute));
     if (ctx->rb_cursor) CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS_SKM * sizeof(unsigned int), ctx->compute));
-    CU_TRY(cudaStreamSynchronize(ctx->compute));
+    // no synchronisation: the clear runs in the shadow of the first host-to-device copy of the next sample
     ctx->staged_ub = 0;
     ctx->distinct_base = ctx->kmers_base = ctx->recv_since_base = 0;
     ctx->distinct_ub = 0; ctx->kmers_ub_total = 0; ctx->sv_ub = 0; ctx->svs_n = 0;
@@ -467,7 +495,7 @@ static void poll_snapshots(mfkc_ctx *ctx) {
     if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
         // per-batch snapshots of the EXACT number of k-mer instances extracted so far (the host only
         // knows the loose bound bases - k + 1 per batch, which over-counts by ~25 % on 150 bp reads)
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < N_STAGE; i++) {
             Staging &s = ctx->st[i];
             if (s.pending && cudaEventQuery(s.ev_done) == cudaSuccess) {
                 s.pending = false;
@@ -482,7 +510,7 @@ static void poll_snapshots(mfkc_ctx *ctx) {
         return;
     }
     if (ctx->cfg.variant != MFKC_VARIANT_HASH_DIRECT) return;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < N_STAGE; i++) {
         Staging &s = ctx->st[i];
         if (s.pending && cudaEventQuery(s.ev_done) == cudaSuccess) {
             s.pending = false;
@@ -512,7 +540,7 @@ static int grow_table(mfkc_ctx *ctx, uint64_t need_slots) {
             TableGeom128 ng; ng.cap = new_cap; ng.n_regions = nr; ng.region_shift = sh; ng.k = ctx->cfg.k;
             rehash128_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(ctx->tab128, ctx->cap, reinterpret_cast<Slot128 *>(nt), ng);
         } else {
-            TableGeom ng; ng.cap = new_cap; ng.n_regions = nr; ng.region_shift = sh; ng.k = ctx->cfg.k; ng.minimizer = ctx->place;
+            TableGeom ng; ng.cap = new_cap; ng.n_regions = nr; ng.region_shift = sh; ng.k = ctx->cfg.k; ng.minimizer = ctx->place; ng.win = table_win(ctx);
             if (ctx->soa) rehash_soa_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(tab_soa(ctx), tab_soa_of(nt, new_cap), ng);
             else rehash_kernel<<<grid_for(ctx, ctx->cap, 256, 8), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap, nt, ng);
         }
@@ -571,13 +599,13 @@ static RegionStage region_stage(const mfkc_ctx *ctx) {
 
 static TableGeom table_geom(const mfkc_ctx *ctx) {
     TableGeom g;
-    g.cap = ctx->cap; g.n_regions = ctx->n_regions; g.region_shift = ctx->region_shift; g.k = ctx->cfg.k; g.minimizer = ctx->place;
+    g.cap = ctx->cap; g.n_regions = ctx->n_regions; g.region_shift = ctx->region_shift; g.k = ctx->cfg.k; g.minimizer = ctx->place; g.win = table_win(ctx);
     return g;
 }
 static SkmStage skm_stage(const mfkc_ctx *ctx) {
     SkmStage st;
     st.recs = reinterpret_cast<uint4 *>(ctx->rb_keys); st.cursor = ctx->rb_cursor;
-    st.n_regions = ctx->n_regions; st.region_shift = ctx->region_shift;
+    st.n_regions = ctx->n_regions; st.region_shift = ctx->region_shift; st.win = table_win(ctx);
     uint64_t seg = (ctx->rb_cap / 2) / ctx->n_regions;
     if (seg > 0x7fffffffull) seg = 0x7fffffffull;
     st.seg_cap = seg;
@@ -612,6 +640,30 @@ static int drain_regions(mfkc_ctx *ctx) {
         if (ctx->k128) {
             const uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 4 / 512));
             drain_skm128_kernel<<<ctx->n_regions * bpr, 256, 0, ctx->compute>>>(skm_stage128(ctx), bpr, ctx->cfg.k, ctx->tab128, ctx->cap, ctx->d_ctr);
+        } else if (ctx->smem_drain && ctx->region_shift <= SMEM_MAX_SHIFT) {
+            if (ctx->sp_failed_cap < ctx->n_regions) {
+                CU_TRY(cudaStreamSynchronize(ctx->compute));
+                cudaFree(ctx->sp_failed); ctx->sp_failed = nullptr;
+                CU_TRY(cudaMalloc(&ctx->sp_failed, (size_t)ctx->n_regions * sizeof(uint32_t)));
+                ctx->sp_failed_cap = ctx->n_regions;
+            }
+            SpillBuf sp; sp.keys = ctx->sp_ent; sp.cursor = ctx->sp_cursor; sp.n_dirty = ctx->sp_cursor + 1; sp.dirty = ctx->sp_failed; sp.cap = ctx->sp_cap;
+            const size_t smem = ((size_t)16 << ctx->region_shift) + SMEM_SPILL_MAX * sizeof(unsigned long long);
+            static const bool dbg = getenv("MFKC_DEBUG_DRAIN") != nullptr;
+            cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+            if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventRecord(e0, ctx->compute); }
+            drain_smem_kernel<<<ctx->n_regions, 256, smem, ctx->compute>>>(skm_stage(ctx), ctx->cfg.k, ctx->tab, sp, ctx->d_ctr);
+            if (dbg) cudaEventRecord(e1, ctx->compute);
+            drain_fallback_kernel<<<ctx->sm_count * 8, 256, 0, ctx->compute>>>(skm_stage(ctx), ctx->cfg.k, ctx->tab, ctx->cap, sp, ctx->d_ctr);
+            if (dbg) {
+                cudaEventRecord(e2, ctx->compute); cudaEventSynchronize(e2);
+                float ma = 0, mb = 0; cudaEventElapsedTime(&ma, e0, e1); cudaEventElapsedTime(&mb, e1, e2);
+                unsigned int h[2] = {0, 0}; cudaMemcpy(h, ctx->sp_cursor, sizeof h, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[drain] regions %u (shift %d) seg_cap %llu  smem %.2f ms  fallback %.2f ms  spilled %u  dirty regions %u\n",
+                        ctx->n_regions, ctx->region_shift, (unsigned long long)skm_stage(ctx).seg_cap, ma, mb, h[0], h[1]);
+                cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+            }
+            cudaMemsetAsync(ctx->sp_cursor, 0, 2 * sizeof(unsigned int), ctx->compute);
         } else if (ctx->place) {
             static const int env_bpr = getenv("MFKC_BPR") ? atoi(getenv("MFKC_BPR")) : 0;
             uint32_t bpr = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, per_region / 2 / 512));
@@ -643,7 +695,7 @@ static int reserve_staging(mfkc_ctx *ctx, uint64_t add_kmers) {
     if (!ctx->rb_keys) {
         uint64_t want = ctx->cfg.staging_bytes ? ctx->cfg.staging_bytes / 8 : std::max<uint64_t>(4 * add, 1ull << 22);
         if (!ctx->cfg.staging_bytes && ctx->cfg.expected_kmers)
-            want = std::max<uint64_t>(want, stage_units(ctx, ctx->cfg.expected_kmers + ctx->cfg.expected_kmers / 50) + (uint64_t)MAX_REGIONS_SKM * 64);
+            want = std::max<uint64_t>(want, stage_units(ctx, ctx->cfg.expected_kmers + ctx->cfg.expected_kmers / 50) + (uint64_t)std::max<uint32_t>(ctx->n_regions, 65536u) * 64);
         if (!ctx->cfg.staging_bytes && want > ctx->rb_cap_max) want = std::max<uint64_t>(ctx->rb_cap_max, add);
         if (!ctx->cfg.staging_bytes && want > ctx->rb_cap_max) want = std::max<uint64_t>(ctx->rb_cap_max, add);
         if (want < add) want = add;
@@ -715,7 +767,7 @@ static int sort_variant_reserve(mfkc_ctx *ctx, uint64_t add);
 
 // count a device-resident batch (bases/offsets already on the device, visible to the compute stream)
 static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases, const uint64_t *d_offsets,
-                              uint32_t n_reads, uint64_t n_bases) {
+                              uint32_t n_reads, uint64_t n_bases, bool host_fed = false) {
     const int k = ctx->cfg.k;
     const uint64_t kmers_ub = n_bases >= (uint64_t)k ? n_bases - k + 1 : 0;
     if (ctx->cfg.variant == MFKC_VARIANT_SORT) TRY(sort_variant_reserve(ctx, kmers_ub));
@@ -772,6 +824,17 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
     s.pending = ctx->cfg.variant != MFKC_VARIANT_SORT;
     s.kmers_submitted_at_end = ctx->kmers_ub_total;
     ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
+    // Host-fed batches arrive at PCIe speed (~3 ms per million reads), several times slower than the kernels
+    // consume them: drain early and often, asynchronously, in the shadow of the copies.  Every drain leaves an
+    // exact snapshot of the distinct count (poll_snapshots), which keeps the table bound of reserve_slots tight
+    // without ever blocking the submitting thread, and leaves only the last interval for mfkc_flush.
+    ctx->host_fed = host_fed;
+    if (host_fed && ctx->cfg.variant == MFKC_VARIANT_HASH && ctx->place) {
+        static const double frac = getenv("MFKC_DRAIN_EVERY") ? atof(getenv("MFKC_DRAIN_EVERY")) : 0.2;
+        const uint64_t expect = ctx->cfg.expected_kmers ? ctx->cfg.expected_kmers : ctx->prev_sample_kmers;
+        const uint64_t every = std::max<uint64_t>((uint64_t)(frac * (double)expect), 64ull << 20);
+        if (frac > 0 && ctx->kmers_since_drain >= every) TRY(drain_regions(ctx));
+    }
     return MFKC_OK;
 }
 
@@ -783,7 +846,7 @@ extern "C" int mfkc_submit_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint
     if (offsets[n_reads] < base0) return fail(ctx, MFKC_E_BADARG, "offsets must be non-decreasing");
     const uint64_t n_bases = offsets[n_reads] - base0;
     Staging &s = ctx->st[ctx->next_buf];
-    ctx->next_buf ^= 1;
+    ctx->next_buf = (ctx->next_buf + 1) % N_STAGE;
     TRY(ensure_staging(ctx, s, n_bases, (uint64_t)n_reads + 1, true));
     // the staging buffer is free once the kernels of the batch that used it last are done
     CU_TRY(cudaStreamWaitEvent(s.stream, s.ev_done, 0));
@@ -791,7 +854,7 @@ extern "C" int mfkc_submit_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint
     CU_TRY(cudaMemcpyAsync(s.d_offsets, offsets, ((size_t)n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaEventRecord(s.ev_copy, s.stream));
     CU_TRY(cudaStreamWaitEvent(ctx->compute, s.ev_copy, 0));
-    int r = count_batch_device(ctx, s, s.d_bases, s.d_offsets, n_reads, n_bases);
+    int r = count_batch_device(ctx, s, s.d_bases, s.d_offsets, n_reads, n_bases, true);
     // the caller may refill its buffers once the copies are done
     CU_TRY(cudaEventSynchronize(s.ev_copy));
     return r;
@@ -803,7 +866,7 @@ extern "C" int mfkc_submit_reads_device(mfkc_ctx *ctx, const uint8_t *d_bases, c
     if (n_reads == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
     Staging &s = ctx->st[ctx->next_buf];
-    ctx->next_buf ^= 1;
+    ctx->next_buf = (ctx->next_buf + 1) % N_STAGE;
     TRY(ensure_staging(ctx, s, n_bases, 0, false));
     return count_batch_device(ctx, s, d_bases, d_offsets, n_reads, n_bases);
 }
@@ -1276,7 +1339,7 @@ extern "C" int mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uin
     if (stage_keys) { TRY(reserve_staging(ctx, n)); ctx->staged_ub += n; }
     ctx->kmers_ub_total += n; ctx->recv_since_base += n;
     Staging &s = ctx->st[ctx->next_buf];
-    ctx->next_buf ^= 1;
+    ctx->next_buf = (ctx->next_buf + 1) % N_STAGE;
     if (stage_keys) {
         ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
         const uint64_t tiles = (n + PT_THREADS * 16 - 1) / (PT_THREADS * 16);
@@ -1330,7 +1393,7 @@ extern "C" int mfkc_skm_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, 
     CU_TRY(cudaMemsetAsync(ctx->d_bucket_cursor, 0, 64 * sizeof(unsigned long long), ctx->compute));
     CU_TRY(cudaMemsetAsync(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t), ctx->compute));
     SkmStage st;
-    st.recs = reinterpret_cast<uint4 *>(d_recs_out); st.cursor = d_cur; st.seg_cap = seg_cap; st.n_regions = ns; st.region_shift = 0;
+    st.recs = reinterpret_cast<uint4 *>(d_recs_out); st.cursor = d_cur; st.seg_cap = seg_cap; st.n_regions = ns; st.region_shift = 0; st.win = 0;
     {
         ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
         if (ns <= 8)
@@ -1459,7 +1522,7 @@ extern "C" int mfkc_fc_set_selected(mfkc_ctx *ctx, const uint8_t *be_records, ui
         Slot *nt = nullptr;
         TRY(table_alloc(ctx, need, &nt, true));
         if (ctx->fc_sel) {
-            TableGeom pg; pg.cap = need; pg.n_regions = 1; pg.region_shift = 0; pg.k = ctx->cfg.k; pg.minimizer = 0;
+            TableGeom pg; pg.cap = need; pg.n_regions = 1; pg.region_shift = 0; pg.k = ctx->cfg.k; pg.minimizer = 0; pg.win = 0;
             rehash_kernel<<<grid_for(ctx, ctx->fc_sel_cap, 256, 8), 256, 0, st>>>(ctx->fc_sel, ctx->fc_sel_cap, nt, pg);
             CU_TRY(cudaStreamSynchronize(st));
             cudaFree(ctx->fc_sel);
@@ -1484,7 +1547,7 @@ extern "C" int mfkc_fc_add_records(mfkc_ctx *ctx, const uint8_t *be_records, uin
     if (n_records == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
     Staging &s = ctx->st[ctx->next_buf];
-    ctx->next_buf ^= 1;
+    ctx->next_buf = (ctx->next_buf + 1) % N_STAGE;
     CU_TRY(cudaStreamWaitEvent(s.stream, s.ev_done, 0));
     TRY(stage_records(ctx, s, be_records, n_records));
     CU_TRY(cudaEventRecord(s.ev_copy, s.stream));
@@ -1507,7 +1570,7 @@ extern "C" int mfkc_fc_add_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint
     const uint64_t base0 = offsets[0];
     const uint64_t n_bases = offsets[n_reads] - base0;
     Staging &s = ctx->st[ctx->next_buf];
-    ctx->next_buf ^= 1;
+    ctx->next_buf = (ctx->next_buf + 1) % N_STAGE;
     TRY(ensure_staging(ctx, s, n_bases, (uint64_t)n_reads + 1, true));
     CU_TRY(cudaStreamWaitEvent(s.stream, s.ev_done, 0));
     CU_TRY(cudaMemcpyAsync(s.d_bases, bases + base0, n_bases, cudaMemcpyHostToDevice, s.stream));
