@@ -174,7 +174,7 @@ def workload_config(n_gpus):
     return {"workload": "configs[1]: synthetic Illumina 150bp reads, %d reads per GPU (single sample), k=31, -b 2" % N_READS,
             "k": K, "b": B_THRESHOLD, "read_len": READ_LEN, "reads_per_gpu": N_READS, "batch_reads": BATCH_READS,
             "variant": os.environ.get("MFKC_BENCH_VARIANT", "hash (region-blocked)"),
-            "parallelism": "1 GPU" if n_gpus == 1 else "hash-range sharded over %d GPUs, NCCL all-to-all" % n_gpus,
+            "parallelism": "1 GPU" if n_gpus == 1 else "hash-range sharded over %d GPUs, %s" % (n_gpus, "NCCL all-to-all + restage" if os.environ.get("MFKC_EXCHANGE") == "nccl" else "records drained straight from peer HBM over NVLink (CUDA IPC), no data-path collective"),
             "l2": "inputs (3 GB reads, multi-GB table) are far larger than the 126 MB L2; no explicit flush"}
 
 
@@ -220,14 +220,20 @@ def main():
     n_bases = n_reads * READ_LEN
     kmers_per_step = n_reads * (READ_LEN - K + 1)
 
+    exchange = os.environ.get("MFKC_EXCHANGE", "p2p")                # "p2p": peer-memory drain (default); "nccl": all-to-all + restage
     if world > 1:
-        from metafast_b200.sharded import ShardedStep
-        sharded = ShardedStep(kc, dist, world, rank, BATCH_READS, READ_LEN, K)
+        from metafast_b200.sharded import ShardedStep, P2PShardedStep
+        if exchange == "p2p":
+            sharded = P2PShardedStep(kc, dist, world, rank, BATCH_READS, READ_LEN, K, N_READS)
+        else:
+            sharded = ShardedStep(kc, dist, world, rank, BATCH_READS, READ_LEN, K)
 
     def step_device():
         """one whole pass, inputs resident in HBM"""
         kc.reset()
         if world > 1:
+            if exchange == "p2p":
+                sharded.begin()
             sharded.run_device(d_bases, d_offs, n_reads)
         else:
             for s in range(0, n_reads, BATCH_READS):
@@ -279,6 +285,8 @@ def main():
     def step_e2e():
         kc.reset()
         if world > 1:
+            if exchange == "p2p":
+                sharded.begin()
             sharded.run_host(h_bases, h_offs, n_reads)
         else:
             for s in range(0, n_reads, BATCH_READS):
@@ -289,7 +297,8 @@ def main():
         kc.histogram()
         return nbytes
 
-    step_e2e()
+    for _ in range(2):                       # the first host-fed samples re-size the table for asynchronous drains
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -309,7 +318,7 @@ def main():
     count_kernels = {"hash (region-blocked)": ["extract_partition", "drain_regions"], "direct": ["extract_count"],
                      "sort": ["extract_bucket", "radix_sort", "rle"]}[workload_config(1)["variant"]]
     if world > 1:
-        count_kernels = ["extract_bucket", "extract_partition", "drain_regions"]
+        count_kernels = ["extract_bucket", "extract_partition", "drain_regions"]      # p2p: extract_bucket + drain_regions (NVLink reads inside)
     t_count_ms = sum(prof[k][0] for k in count_kernels if k in prof) / args.steps
     launches = sum(v[1] for v in prof.values())
     achieved = ALGO_BYTES_PER_KMER * kmers_per_step / (t_count_ms / 1e3) / 1e9 if t_count_ms else None

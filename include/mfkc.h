@@ -154,6 +154,32 @@ int  mfkc_skm_count_device(mfkc_ctx *ctx, const void *d_recs, uint64_t n_recs, u
  * a side stream so that the next extraction overlaps them; call this before overwriting a receive buffer). */
 int  mfkc_skm_count_wait(mfkc_ctx *ctx);
 
+/* Peer-memory flavour of the exchange (default of bench.py for N > 1; no reference analogue):
+ * every GPU stages its super-k-mer records in its OWN memory, bucketed by (owner shard, coarse bucket of the
+ * minimizer hash); the owner's drain kernel then reads its segments straight out of every peer's staging
+ * buffer over NVLink (CUDA IPC pointers) while it upserts -- one kernel does transfer + counting, no NCCL
+ * call on the data path, no receive buffer, no re-staging.  Call sequence per sample, on every rank:
+ *   mfkc_p2p_stage_create  once: (n_shards << log2_buckets) segments of seg_cap 16-byte records
+ *   mfkc_p2p_export        -> 128 opaque bytes (two CUDA IPC handles); exchange them between the processes
+ *   mfkc_p2p_attach        once per peer (own rank included); mfkc_p2p_attach_ctx for contexts of the same process
+ *   [barrier] mfkc_p2p_stage_reset
+ *   mfkc_p2p_extract ...   any number of batches (device-resident reads)
+ *   mfkc_p2p_counts        -> k-mer instances staged for every owner so far; exchange them (this is also the
+ *                             barrier: a rank's counts exist only after its extraction has finished)
+ *   mfkc_p2p_drain(n_in)   n_in = k-mer instances staged for this rank on all ranks together
+ *   mfkc_flush / mfkc_emit_* as on one GPU.
+ * A staging segment that overflows is reported by mfkc_flush (MFKC_E_STATE); nothing is dropped silently. */
+int  mfkc_p2p_stage_create(mfkc_ctx *ctx, uint32_t log2_buckets, uint64_t seg_cap);
+int  mfkc_p2p_export(mfkc_ctx *ctx, uint8_t handles[128]);
+int  mfkc_p2p_attach(mfkc_ctx *ctx, uint32_t rank, const uint8_t handles[128]);
+int  mfkc_p2p_attach_ctx(mfkc_ctx *ctx, uint32_t rank, mfkc_ctx *peer);
+int  mfkc_p2p_stage_reset(mfkc_ctx *ctx);
+int  mfkc_p2p_extract(mfkc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t n_reads, uint64_t n_bases);
+/* host-buffer version of mfkc_p2p_extract: same arguments, copies and overlap as mfkc_submit_reads */
+int  mfkc_p2p_submit_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads);
+int  mfkc_p2p_counts(mfkc_ctx *ctx, uint64_t *kmers_per_owner /* n_shards entries */);
+int  mfkc_p2p_drain(mfkc_ctx *ctx, uint64_t n_kmers_in);
+
 /* ---- features-calculator: replaces the BigLong2LongHashMap set-up
  * (src/tools/FeaturesCalculatorMain.java:97-103), IOUtils.calculatePresenceForKmers /
  * ...ForReads (src/io/IOUtils.java:577-597, 806-834) and buildAndPrintVector

@@ -88,6 +88,15 @@ SIGNATURES = {
                                             C.c_void_p, C.c_uint64, u64p, u64p]),
     "mfkc_skm_count_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "mfkc_skm_count_wait": (C.c_int, [C.c_void_p]),
+    "mfkc_p2p_stage_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
+    "mfkc_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mfkc_p2p_attach": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "mfkc_p2p_attach_ctx": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "mfkc_p2p_stage_reset": (C.c_int, [C.c_void_p]),
+    "mfkc_p2p_extract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]),
+    "mfkc_p2p_submit_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "mfkc_p2p_counts": (C.c_int, [C.c_void_p, u64p]),
+    "mfkc_p2p_drain": (C.c_int, [C.c_void_p, C.c_uint64]),
     "mfkc_fc_load_components": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "mfkc_fc_set_selected": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "mfkc_fc_reset_values": (C.c_int, [C.c_void_p]),

@@ -233,6 +233,39 @@ class KmerCounter(_Ctx):
     def skm_count_wait(self):
         self._ck(self.lib.mfkc_skm_count_wait(self.h))
 
+    # ---- peer-memory flavour of the exchange (mfkc_p2p_*)
+    def p2p_stage_create(self, log2_buckets: int, seg_cap: int):
+        self._ck(self.lib.mfkc_p2p_stage_create(self.h, log2_buckets, seg_cap))
+
+    def p2p_export(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self._ck(self.lib.mfkc_p2p_export(self.h, buf))
+        return bytes(buf)
+
+    def p2p_attach(self, rank: int, handles: Optional[bytes]):
+        buf = (C.c_uint8 * 128).from_buffer_copy(handles) if handles is not None else None
+        self._ck(self.lib.mfkc_p2p_attach(self.h, rank, buf))
+
+    def p2p_attach_ctx(self, rank: int, peer: "KmerCounter"):
+        self._ck(self.lib.mfkc_p2p_attach_ctx(self.h, rank, peer.h))
+
+    def p2p_stage_reset(self):
+        self._ck(self.lib.mfkc_p2p_stage_reset(self.h))
+
+    def p2p_extract(self, d_bases: int, d_offsets: int, n_reads: int, n_bases: int):
+        self._ck(self.lib.mfkc_p2p_extract(self.h, C.c_void_p(d_bases), C.c_void_p(d_offsets), n_reads, n_bases))
+
+    def p2p_submit(self, bases: np.ndarray, offsets: np.ndarray):
+        self._ck(self.lib.mfkc_p2p_submit_reads(self.h, _ptr(bases), _ptr(offsets), len(offsets) - 1))
+
+    def p2p_counts(self, n_shards: int) -> List[int]:
+        out = (C.c_uint64 * max(n_shards, 1))()
+        self._ck(self.lib.mfkc_p2p_counts(self.h, out))
+        return list(out)
+
+    def p2p_drain(self, n_kmers_in: int):
+        self._ck(self.lib.mfkc_p2p_drain(self.h, n_kmers_in))
+
 
 class FeaturesCalculator(_Ctx):
     """features-calculator on the device (K6/K7/K8)."""

@@ -887,12 +887,18 @@ __device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32
     }
 }
 
-// BY_OWNER = false: bucket = table region of this GPU (single-GPU path, full segments fall back to
-//                   direct upserts);
-// BY_OWNER = true : bucket = owner shard (multi-GPU send buffer; st.n_regions = number of shards,
-//                   kmer_count[b] receives the k-mer instances sent to shard b; a full segment is
-//                   reported through the cursor overshoot and the caller retries with a smaller batch).
-template <bool BY_OWNER, class Tab>
+// MODE 0: bucket = table region of this GPU (single-GPU path, full segments fall back to direct upserts);
+// MODE 1: bucket = owner shard (send buffer of the NCCL exchange; st.n_regions = number of shards,
+//         kmer_count[b] receives the k-mer instances sent to shard b; a full segment is reported
+//         through the cursor overshoot and the caller retries with a smaller batch);
+// MODE 2: bucket = owner shard x coarse bucket of the minimizer hash (peer-memory exchange: the owner
+//         drains these segments straight from this GPU's memory, see drain_p2p_kernel).
+//         st.n_regions = number of shards, st.region_shift = log2(coarse buckets per shard);
+//         kmer_count[owner] as in mode 1 (warp-aggregated: 8 hot addresses would serialise in L2).
+__host__ __device__ __forceinline__ uint32_t coarse_of_minhash(uint32_t mh, int log2_buckets) {
+    return log2_buckets ? hash32(mh ^ 0x7f4a7c15u) >> (32 - log2_buckets) : 0u;     // monotone in the region index
+}
+template <int MODE, class Tab>
 __global__ void __launch_bounds__(EX_THREADS)
 extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
                    int k, SkmStage st, Tab tb, Counters *__restrict__ ctr,
@@ -901,10 +907,11 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
     __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
     const uint32_t tid = threadIdx.x;
     const uint64_t n_tiles = (((n_bases + 15) >> 4) + EX_THREADS - 1) / EX_THREADS;
-    uint32_t claimed = 0, bad = 0;
+    uint32_t claimed = 0, bad = 0, dropped = 0;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const TileWord t = load_tile_word<EX_THREADS>(bases, n_bases, flags, tile, k, s_words, s_flags, bad);
+        unsigned long long km_lo = 0, km_hi = 0;                // MODE 2: k-mers per owner of this tile, 16-bit fields
         if (t.active) {
             const uint32_t w0 = t.w0, w1 = t.w1, w2 = t.w2;
             const uint64_t fbits = t.fbits;
@@ -923,7 +930,12 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                 // the whole record from that one hash, under a table geometry the sender does not know.
                 // Two passes over the same state machine: pass 1 issues every cursor atomic of the
                 // thread back to back (their ~1 us round trips overlap), pass 2 writes the records.
-                auto bucket_of = [&](uint32_t mhv, uint32_t key) { return BY_OWNER ? owner_of_minhash(mhv, st.n_regions) : key; };
+                constexpr bool BY_OWNER = MODE != 0;
+                auto bucket_of = [&](uint32_t mhv, uint32_t key) {
+                    if (MODE == 0) return key;
+                    const uint32_t o = owner_of_minhash(mhv, st.n_regions);
+                    return MODE == 1 ? o : ((o << st.region_shift) | coarse_of_minhash(mhv, st.region_shift));
+                };
                 uint32_t rkey[16];                                  // run key of every start position, computed once
 #pragma unroll
                 for (int j = 0; j < 16; j++) rkey[j] = BY_OWNER ? mh[j] : region_of_minhash(mh[j], st.n_regions);
@@ -960,10 +972,15 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                             const uint32_t bucket = bucket_of(run_mh, run_key);
                             if (pos[j] < st.seg_cap) {
                                 st.recs[(uint64_t)bucket * st.seg_cap + pos[j]] = rec;
-                                if (BY_OWNER) atomicAdd(&kmer_count[bucket], (unsigned long long)len);
+                                if (MODE == 1) atomicAdd(&kmer_count[bucket], (unsigned long long)len);
+                                if (MODE == 2) {
+                                    const uint32_t o = bucket >> st.region_shift;
+                                    if (st.n_regions <= 8) { if (o < 4) km_lo += (unsigned long long)len << (16 * o); else km_hi += (unsigned long long)len << (16 * (o - 4)); }
+                                    else atomicAdd(&kmer_count[o], (unsigned long long)len);
+                                }
                             } else if (!BY_OWNER) {                 // segment full: count the run directly (slow, exact)
                                 claimed += skm_count_direct(rec, bucket, st.region_shift, st.win, k, tb);
-                            }
+                            } else if (MODE == 2) dropped++;        // reported as an error by mfkc_flush (segments are sized with 2x slack)
                             in_run = false;
                         }
                         if (v && !in_run) { in_run = true; run_start = (uint32_t)j; run_key = key; run_mh = mhj; }
@@ -971,11 +988,21 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                 }
             }
         }
+        if (MODE == 2 && st.n_regions <= 8) {                   // one atomic per (warp, owner) and tile
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { km_lo += __shfl_xor_sync(0xffffffffu, km_lo, o); km_hi += __shfl_xor_sync(0xffffffffu, km_hi, o); }
+            const uint32_t l = lane_id();
+            if (l < st.n_regions) {
+                const uint32_t c = (uint32_t)((l < 4 ? km_lo >> (16 * l) : km_hi >> (16 * (l - 4))) & 0xFFFFu);
+                if (c) atomicAdd(&kmer_count[l], (unsigned long long)c);
+            }
+        }
         __syncthreads();
     }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
     if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
+    if (MODE == 2 && dropped) atomicAdd(&ctr->overflow, (unsigned long long)dropped);
 }
 
 // Send side for up to 8 owner shards with block-level aggregation.  With only G <= 8 destination
@@ -1107,11 +1134,14 @@ __device__ __forceinline__ void skm_expand_records(const uint4 *__restrict__ rec
                                                    int k, uint4 (*s_rec)[32], uint32_t (*s_pre)[33], Put put) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rs = 64 - 2 * k;
-    for (uint64_t base = first + (uint64_t)warp * 32; base < n; base += stride) {
-        const uint64_t i = base + lane;
-        uint4 r = make_uint4(0u, 0u, 0u, 0u);
-        uint32_t len = 0;
-        if (i < n) { r = ld_nc_u128(&recs[i]); len = (r.z & 15u) + 1u; }
+    uint64_t base = first + (uint64_t)warp * 32;
+    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+    if (base + lane < n) nxt = ld_nc_u128(&recs[base + lane]);         // software pipeline: the next 32 records are in
+    for (; base < n; base += stride) {                                   // flight while these are expanded (the records
+        const uint64_t i = base + lane;                                  // may live in a peer GPU's memory)
+        const uint4 r = nxt;
+        const uint32_t len = i < n ? (r.z & 15u) + 1u : 0u;
+        if (i + stride < n) nxt = ld_nc_u128(&recs[i + stride]);
         uint32_t incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
@@ -1134,7 +1164,7 @@ __device__ __forceinline__ void skm_expand_records(const uint4 *__restrict__ rec
             const uint32_t l32 = __funnelshift_l(w2, q.y, 2 * off);
             const uint64_t fw = (((uint64_t)h32 << 32) | l32) >> rs;
             const uint64_t rc = revcomp64(fw, k);
-            put(fw < rc ? fw : rc);
+            put(fw < rc ? fw : rc, q.w);
         }
         __syncwarp();
     }
@@ -1153,7 +1183,7 @@ drain_skm_kernel(SkmStage st, uint32_t blocks_per_region, int k, Tab tb, Counter
     const uint64_t slot_mask = (1ull << st.region_shift) - 1ull;
     uint32_t claimed = 0;
     skm_expand_records(st.recs + (uint64_t)region * st.seg_cap, n, (uint64_t)sub * 256, (uint64_t)blocks_per_region * 256, k, s_rec, s_pre,
-                       [&](uint64_t key) { claimed += tb.upsert1_at(region_base | (mix64(key) & slot_mask), key, st.region_shift, st.win) ? 1u : 0u; });
+                       [&](uint64_t key, uint32_t) { claimed += tb.upsert1_at(region_base | (mix64(key) & slot_mask), key, st.region_shift, st.win) ? 1u : 0u; });
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
@@ -1210,7 +1240,7 @@ drain_smem_kernel(SkmStage st, int k, Slot *__restrict__ tab, SpillBuf sp, Count
     uint32_t claimed = 0;
     const uint32_t slot_mask = S - 1u;
     const uint32_t win = SMEM_WIN < S ? SMEM_WIN : S;
-    skm_expand_records(st.recs + (uint64_t)region * st.seg_cap, n, 0, 256, k, s_rec, s_pre, [&](uint64_t key) {
+    skm_expand_records(st.recs + (uint64_t)region * st.seg_cap, n, 0, 256, k, s_rec, s_pre, [&](uint64_t key, uint32_t) {
         const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
         uint32_t i = (uint32_t)mix64(key) & slot_mask;
         for (uint32_t step = 0; step < win; step++, i = (i + 1) & slot_mask) {
@@ -1278,7 +1308,7 @@ drain_fallback_kernel(SkmStage st, int k, Slot *__restrict__ tab, uint64_t cap, 
         uint64_t n = st.cursor[region];
         if (n > st.seg_cap) n = st.seg_cap;
         const uint64_t region_base = (uint64_t)region << st.region_shift;
-        skm_expand_records(st.recs + (uint64_t)region * st.seg_cap, n, 0, 256, k, s_rec, s_pre, [&](uint64_t key) {
+        skm_expand_records(st.recs + (uint64_t)region * st.seg_cap, n, 0, 256, k, s_rec, s_pre, [&](uint64_t key, uint32_t) {
             uint64_t off = mix64(key) & slot_mask;
             for (uint32_t step = 0; step < win; step++, off = (off + 1) & slot_mask) {
                 const unsigned long long cur = ld_cg_u64x2(&tab[region_base | off]).x;
@@ -1292,6 +1322,52 @@ drain_fallback_kernel(SkmStage st, int k, Slot *__restrict__ tab, uint64_t cap, 
         });
         __syncthreads();
         if (threadIdx.x == 0) st.cursor[region] = 0;
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+}
+
+// ------------------------------------------------------------------------------------------
+// Peer-memory shard exchange (multi-GPU): compute + collective in ONE kernel.
+// Every GPU stages its super-k-mer records in its OWN memory, bucketed by (owner shard, coarse
+// bucket of the minimizer hash) -- extract_skm_kernel<2>.  The owner's drain then reads "its"
+// segments straight out of every peer's staging buffer with P2P loads over NVLink/NVSwitch
+// (pointers opened with CUDA IPC) and upserts them into its table: no send/receive buffers, no
+// NCCL data path, no re-staging pass, and the transfer overlaps the upserts record by record
+// (skm_expand_records keeps the next 32 records of the warp in flight).
+// The coarse bucket is the top bits of the same hash the table region derives from, so the records
+// of bucket b fall into a contiguous 1/B of the owner's table whatever its size: consecutive CTAs
+// work on the same bucket and its table slice stays L2-resident, as in drain_skm_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int P2P_MAX_PEERS = 16;
+struct P2PPeers {
+    const uint4 *recs[P2P_MAX_PEERS];             // peer s: segment (owner << log2_buckets | bucket) of seg_cap records
+    const unsigned int *cursor[P2P_MAX_PEERS];
+    uint64_t seg_cap;
+    uint32_t n_peers, me;
+    int log2_buckets;
+};
+
+template <class Tab>
+__global__ void __launch_bounds__(256)
+drain_p2p_kernel(P2PPeers pp, uint32_t bucket0, uint32_t blocks_per_bucket, int k, Tab tb, uint32_t n_regions, int region_shift, uint32_t win,
+                 Counters *__restrict__ ctr) {
+    __shared__ uint4 s_rec[8][32];
+    __shared__ uint32_t s_pre[8][33];
+    const uint32_t bucket = bucket0 + blockIdx.x / blocks_per_bucket;
+    const uint32_t sub = blockIdx.x % blocks_per_bucket;
+    const uint64_t seg = ((uint64_t)pp.me << pp.log2_buckets) | bucket;
+    const uint64_t slot_mask = (1ull << region_shift) - 1ull;
+    uint32_t claimed = 0;
+    for (uint32_t j = 0; j < pp.n_peers; j++) {
+        const uint32_t s = (pp.me + j) % pp.n_peers;            // start at home, then round the peers: spreads the NVLink load
+        uint64_t n = pp.cursor[s][seg];
+        if (n > pp.seg_cap) n = pp.seg_cap;
+        skm_expand_records(pp.recs[s] + seg * pp.seg_cap, n, (uint64_t)sub * 256, (uint64_t)blocks_per_bucket * 256, k, s_rec, s_pre,
+                           [&](uint64_t key, uint32_t mh) {
+                               const uint64_t region = region_of_minhash(mh, n_regions);
+                               claimed += tb.upsert1_at((region << region_shift) | (mix64(key) & slot_mask), key, region_shift, win) ? 1u : 0u;
+                           });
     }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);

@@ -78,6 +78,12 @@ struct mfkc_ctx {
     uint64_t distinct_base = 0, kmers_base = 0, recv_since_base = 0;
     unsigned long long *h_drain_snap = nullptr;
 
+    // peer-memory shard exchange
+    uint4 *p2p_recs = nullptr; unsigned int *p2p_cursor = nullptr; unsigned long long *p2p_kc = nullptr;
+    uint64_t p2p_seg_cap = 0; int p2p_log2 = 0;
+    const uint4 *p2p_peer_recs[P2P_MAX_PEERS] = {nullptr}; const unsigned int *p2p_peer_cursor[P2P_MAX_PEERS] = {nullptr};
+    bool p2p_ipc[P2P_MAX_PEERS] = {false};
+
     // sort variant
     unsigned long long *sv_keys = nullptr; uint64_t sv_cap = 0, sv_ub = 0;
     unsigned long long *svs_keys = nullptr; uint32_t *svs_counts = nullptr; uint64_t svs_n = 0;   // compacted state
@@ -386,6 +392,8 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
     cudaFree(ctx->rb_keys); cudaFree(ctx->rb_cursor);
     cudaFree(ctx->sp_ent); cudaFree(ctx->sp_cursor); cudaFree(ctx->sp_failed);
+    for (int i = 0; i < P2P_MAX_PEERS; i++) if (ctx->p2p_ipc[i]) { cudaIpcCloseMemHandle((void *)ctx->p2p_peer_recs[i]); cudaIpcCloseMemHandle((void *)ctx->p2p_peer_cursor[i]); }
+    cudaFree(ctx->p2p_recs); cudaFree(ctx->p2p_cursor); cudaFree(ctx->p2p_kc);
     cudaFree(ctx->tab); cudaFree(ctx->sv_keys); cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts);
     cudaFree(ctx->d_bucket_cursor); cudaFree(ctx->d_bucket_base);
     if (ctx->h_bucket) cudaFreeHost(ctx->h_bucket);
@@ -790,9 +798,9 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
                 extract_skm128_kernel<<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
                     d_bases, n_bases, s.d_flags, k, skm_stage128(ctx), ctx->tab128, ctx->cap, ctx->d_ctr);
             } else if (ctx->place) {          // super-k-mer records, minimizer placement
-                if (ctx->soa) extract_skm_kernel<false, TabSoAOps><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                if (ctx->soa) extract_skm_kernel<0, TabSoAOps><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
                     d_bases, n_bases, s.d_flags, k, skm_stage(ctx), tab_soa_ops(ctx), ctx->d_ctr, nullptr);
-                else extract_skm_kernel<false, TabAoS><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                else extract_skm_kernel<0, TabAoS><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
                     d_bases, n_bases, s.d_flags, k, skm_stage(ctx), tab_aos(ctx), ctx->d_ctr, nullptr);
             } else if (stage_mode == 0) {     // single keys, shared-memory histogram flavour
                 const uint64_t tiles = ((n_bases + 15) / 16 + PT_THREADS - 1) / PT_THREADS;
@@ -838,7 +846,14 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
     return MFKC_OK;
 }
 
+static int p2p_extract_batch(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t n_reads, uint64_t n_bases);
+static int submit_host(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, bool p2p);
+
 extern "C" int mfkc_submit_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads) {
+    return submit_host(ctx, bases, offsets, n_reads, false);
+}
+
+static int submit_host(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads, bool p2p) {
     if (!ctx || (!bases && n_reads) || !offsets) return fail(ctx, MFKC_E_BADARG, "null argument");
     if (n_reads == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
@@ -854,7 +869,8 @@ extern "C" int mfkc_submit_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint
     CU_TRY(cudaMemcpyAsync(s.d_offsets, offsets, ((size_t)n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
     CU_TRY(cudaEventRecord(s.ev_copy, s.stream));
     CU_TRY(cudaStreamWaitEvent(ctx->compute, s.ev_copy, 0));
-    int r = count_batch_device(ctx, s, s.d_bases, s.d_offsets, n_reads, n_bases, true);
+    int r = p2p ? p2p_extract_batch(ctx, s, s.d_bases, s.d_offsets, n_reads, n_bases)
+                : count_batch_device(ctx, s, s.d_bases, s.d_offsets, n_reads, n_bases, true);
     // the caller may refill its buffers once the copies are done
     CU_TRY(cudaEventSynchronize(s.ev_copy));
     return r;
@@ -1400,7 +1416,7 @@ extern "C" int mfkc_skm_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, 
             extract_skm_owner8_kernel<<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
                 d_bases, n_bases, s.d_flags, k, st, ctx->d_ctr, d_kc);
         else
-            extract_skm_kernel<true, TabAoS><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+            extract_skm_kernel<1, TabAoS><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
                 d_bases, n_bases, s.d_flags, k, st, TabAoS{nullptr, 0}, ctx->d_ctr, d_kc);
     }
     CU_TRY(cudaGetLastError());
@@ -1455,6 +1471,179 @@ extern "C" int mfkc_skm_count_wait(mfkc_ctx *ctx) {
     if (!ctx) return MFKC_E_BADARG;
     CU_TRY(cudaSetDevice(ctx->device));
     CU_TRY(cudaStreamSynchronize(ctx->aux));
+    return MFKC_OK;
+}
+
+// ---- peer-memory flavour of the shard exchange (see include/mfkc.h and drain_p2p_kernel) ----
+static int p2p_check(mfkc_ctx *ctx) {
+    if (!ctx) return MFKC_E_BADARG;
+    if (ctx->cfg.variant != MFKC_VARIANT_HASH || !ctx->place || ctx->k128 || ctx->soa)
+        return fail(ctx, MFKC_E_STATE, "the peer-memory exchange needs the region-blocked hash variant with k <= 31");
+    if (ctx->cfg.n_shards < 1 || ctx->cfg.n_shards > P2P_MAX_PEERS) return fail(ctx, MFKC_E_STATE, "the peer-memory exchange serves 1..16 shards");
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_p2p_stage_create(mfkc_ctx *ctx, uint32_t log2_buckets, uint64_t seg_cap) {
+    TRY(p2p_check(ctx));
+    if (log2_buckets > 16 || seg_cap == 0 || seg_cap > 0x7fffffffull) return fail(ctx, MFKC_E_BADARG, "bad p2p staging geometry");
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(sync_all(ctx));
+    cudaFree(ctx->p2p_recs); cudaFree(ctx->p2p_cursor); cudaFree(ctx->p2p_kc);
+    ctx->p2p_recs = nullptr; ctx->p2p_cursor = nullptr; ctx->p2p_kc = nullptr;
+    const uint64_t n_seg = (uint64_t)std::max(1, ctx->cfg.n_shards) << log2_buckets;
+    // plain cudaMalloc: CUDA IPC cannot export memory of the stream-ordered pool
+    if (big_alloc(ctx, (void **)&ctx->p2p_recs, n_seg * seg_cap * sizeof(uint4)) != cudaSuccess) return fail(ctx, MFKC_E_OOM, "cannot allocate the p2p staging buffer");
+    CU_TRY(cudaMalloc(&ctx->p2p_cursor, n_seg * sizeof(unsigned int)));
+    CU_TRY(cudaMalloc(&ctx->p2p_kc, P2P_MAX_PEERS * sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(ctx->p2p_cursor, 0, n_seg * sizeof(unsigned int)));
+    CU_TRY(cudaMemset(ctx->p2p_kc, 0, P2P_MAX_PEERS * sizeof(unsigned long long)));
+    ctx->p2p_seg_cap = seg_cap; ctx->p2p_log2 = (int)log2_buckets;
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_p2p_export(mfkc_ctx *ctx, uint8_t handles[128]) {
+    TRY(p2p_check(ctx));
+    if (!handles || !ctx->p2p_recs) return fail(ctx, MFKC_E_STATE, "mfkc_p2p_export before mfkc_p2p_stage_create");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, ctx->p2p_recs)); memcpy(handles, &h, 64);
+    CU_TRY(cudaIpcGetMemHandle(&h, ctx->p2p_cursor)); memcpy(handles + 64, &h, 64);
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_p2p_attach(mfkc_ctx *ctx, uint32_t rank, const uint8_t handles[128]) {
+    TRY(p2p_check(ctx));
+    if (rank >= (uint32_t)std::max(1, ctx->cfg.n_shards)) return fail(ctx, MFKC_E_BADARG, "bad peer rank");
+    CU_TRY(cudaSetDevice(ctx->device));
+    if ((int)rank == ctx->cfg.shard_id) {
+        if (!ctx->p2p_recs) return fail(ctx, MFKC_E_STATE, "mfkc_p2p_attach before mfkc_p2p_stage_create");
+        ctx->p2p_peer_recs[rank] = ctx->p2p_recs; ctx->p2p_peer_cursor[rank] = ctx->p2p_cursor; ctx->p2p_ipc[rank] = false;
+        return MFKC_OK;
+    }
+    if (!handles) return fail(ctx, MFKC_E_BADARG, "null argument");
+    cudaIpcMemHandle_t h; void *p = nullptr;
+    memcpy(&h, handles, 64);
+    CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess)); ctx->p2p_peer_recs[rank] = reinterpret_cast<const uint4 *>(p);
+    memcpy(&h, handles + 64, 64);
+    CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess)); ctx->p2p_peer_cursor[rank] = reinterpret_cast<const unsigned int *>(p);
+    ctx->p2p_ipc[rank] = true;
+    return MFKC_OK;
+}
+
+// contexts of the same process (logical shards on one GPU in the tests, or one process driving several GPUs)
+extern "C" int mfkc_p2p_attach_ctx(mfkc_ctx *ctx, uint32_t rank, mfkc_ctx *peer) {
+    TRY(p2p_check(ctx));
+    if (!peer || !peer->p2p_recs || rank >= (uint32_t)std::max(1, ctx->cfg.n_shards)) return fail(ctx, MFKC_E_BADARG, "bad peer");
+    if (peer->p2p_seg_cap != ctx->p2p_seg_cap || peer->p2p_log2 != ctx->p2p_log2) return fail(ctx, MFKC_E_BADARG, "peer staging geometry differs");
+    if (peer->device != ctx->device) {
+        CU_TRY(cudaSetDevice(ctx->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return fail(ctx, MFKC_E_CUDA, "peer access between the two devices is not available"); }
+        cudaGetLastError();
+    }
+    ctx->p2p_peer_recs[rank] = peer->p2p_recs; ctx->p2p_peer_cursor[rank] = peer->p2p_cursor; ctx->p2p_ipc[rank] = false;
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_p2p_stage_reset(mfkc_ctx *ctx) {
+    TRY(p2p_check(ctx));
+    if (!ctx->p2p_recs) return MFKC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const uint64_t n_seg = (uint64_t)std::max(1, ctx->cfg.n_shards) << ctx->p2p_log2;
+    CU_TRY(cudaMemsetAsync(ctx->p2p_cursor, 0, n_seg * sizeof(unsigned int), ctx->compute));
+    CU_TRY(cudaMemsetAsync(ctx->p2p_kc, 0, P2P_MAX_PEERS * sizeof(unsigned long long), ctx->compute));
+    return MFKC_OK;
+}
+
+static int p2p_extract_batch(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t n_reads, uint64_t n_bases) {
+    const int k = ctx->cfg.k;
+    TRY(launch_mark(ctx, s, d_offsets, n_reads, n_bases, ctx->cfg.min_seq_len, 1, ctx->d_ctr));
+    if (n_bases >= (uint64_t)k) {
+        SkmStage st;
+        st.recs = ctx->p2p_recs; st.cursor = ctx->p2p_cursor; st.seg_cap = ctx->p2p_seg_cap;
+        st.n_regions = (uint32_t)std::max(1, ctx->cfg.n_shards); st.region_shift = ctx->p2p_log2; st.win = 0;
+        ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
+        extract_skm_kernel<2, TabAoS><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+            d_bases, n_bases, s.d_flags, k, st, TabAoS{nullptr, 0}, ctx->d_ctr, ctx->p2p_kc);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(s.ev_done, ctx->compute));
+    ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_p2p_extract(mfkc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t n_reads, uint64_t n_bases) {
+    TRY(p2p_check(ctx));
+    if (!d_bases || !d_offsets) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (!ctx->p2p_recs) return fail(ctx, MFKC_E_STATE, "mfkc_p2p_extract before mfkc_p2p_stage_create");
+    if (n_reads == 0) return MFKC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    Staging &s = ctx->st[ctx->next_buf];
+    ctx->next_buf = (ctx->next_buf + 1) % N_STAGE;
+    TRY(ensure_staging(ctx, s, n_bases, 0, false));
+    return p2p_extract_batch(ctx, s, d_bases, d_offsets, n_reads, n_bases);
+}
+
+// host buffers: same copy pipeline as mfkc_submit_reads (N_STAGE batches in flight), extraction into the p2p staging
+extern "C" int mfkc_p2p_submit_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads) {
+    TRY(p2p_check(ctx));
+    if (!ctx->p2p_recs) return fail(ctx, MFKC_E_STATE, "mfkc_p2p_submit_reads before mfkc_p2p_stage_create");
+    return submit_host(ctx, bases, offsets, n_reads, true);
+}
+
+extern "C" int mfkc_p2p_counts(mfkc_ctx *ctx, uint64_t *kmers_per_owner) {
+    TRY(p2p_check(ctx));
+    if (!kmers_per_owner || !ctx->p2p_kc) return fail(ctx, MFKC_E_BADARG, "null argument");
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int ns = std::max(1, ctx->cfg.n_shards);
+    CU_TRY(cudaMemcpyAsync(ctx->h_bucket, ctx->p2p_kc, ns * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaStreamSynchronize(ctx->compute));          // every record of this rank is in its staging buffer
+    for (int i = 0; i < ns; i++) kmers_per_owner[i] = ctx->h_bucket[i];
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_p2p_drain(mfkc_ctx *ctx, uint64_t n_kmers_in) {
+    TRY(p2p_check(ctx));
+    const uint32_t ns = (uint32_t)std::max(1, ctx->cfg.n_shards);
+    for (uint32_t i = 0; i < ns; i++) if (!ctx->p2p_peer_recs[i]) return fail(ctx, MFKC_E_STATE, "mfkc_p2p_drain: not every peer is attached");
+    if (n_kmers_in == 0) return MFKC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    P2PPeers pp;
+    for (uint32_t i = 0; i < (uint32_t)P2P_MAX_PEERS; i++) { pp.recs[i] = i < ns ? ctx->p2p_peer_recs[i] : nullptr; pp.cursor[i] = i < ns ? ctx->p2p_peer_cursor[i] : nullptr; }
+    pp.seg_cap = ctx->p2p_seg_cap; pp.n_peers = ns; pp.me = (uint32_t)ctx->cfg.shard_id; pp.log2_buckets = ctx->p2p_log2;
+    const uint64_t n_buckets = 1ull << ctx->p2p_log2;
+    const uint64_t recs_per_bucket = n_kmers_in / 4 / n_buckets + 1;
+    static const int env_bpb = getenv("MFKC_P2P_BPB") ? atoi(getenv("MFKC_P2P_BPB")) : 0;
+    uint32_t bpb = (uint32_t)std::min<uint64_t>(592, std::max<uint64_t>(1, recs_per_bucket / 512));
+    if (env_bpb > 0) bpb = (uint32_t)env_bpb;
+    // The buckets are drained in a few chunks.  A chunk is a fixed fraction of the minimizer-hash space, so it holds
+    // that fraction of the incoming k-mers (thousands of minimizers per chunk: +-1 %, covered by the 10 % margin and
+    // the 8 % of the table the load limit keeps free).  reserve_slots() thereby sees the exact distinct count of the
+    // chunks before (it synchronises only when its bound is exceeded) and a right-sized table is not grown on the
+    // strength of "every incoming k-mer could be new".  The records are geometry-free, so growth in between is fine.
+    static const int env_chunks = getenv("MFKC_P2P_CHUNKS") ? atoi(getenv("MFKC_P2P_CHUNKS")) : 0;
+    // chunk size: 15 % of the table, so that "distinct so far + chunk" stays below the growth threshold of a table that
+    // was sized for load 0.4
+    uint64_t chunks = env_chunks > 0 ? (uint64_t)env_chunks : (uint64_t)((double)n_kmers_in * 1.1 / (0.15 * (double)ctx->cap)) + 1;
+    if ((double)(ctx->distinct_ub + n_kmers_in) <= kMaxLoad * (double)ctx->cap) chunks = 1;      // fits as a whole
+    chunks = std::min<uint64_t>(chunks, n_buckets);
+    for (uint64_t c = 0; c < chunks; c++) {
+        const uint64_t b0 = n_buckets * c / chunks, b1 = n_buckets * (c + 1) / chunks;
+        const uint64_t share = chunks == 1 ? n_kmers_in : (uint64_t)((double)n_kmers_in * (double)(b1 - b0) / (double)n_buckets * 1.1) + 1024;
+        TRY(reserve_slots(ctx, share));                   // may drain local staging and grow the table
+        ctx->kmers_ub_total += share; ctx->recv_since_base += share;
+        {
+            ProfScope ps(ctx, P_DRAIN, ctx->compute);
+            drain_p2p_kernel<TabAoS><<<(unsigned)((b1 - b0) * bpb), 256, 0, ctx->compute>>>(
+                pp, (uint32_t)b0, bpb, ctx->cfg.k, tab_aos(ctx), ctx->n_regions, ctx->region_shift, table_win(ctx), ctx->d_ctr);
+        }
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaMemcpyAsync(ctx->h_drain_snap, &ctx->d_ctr->distinct, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaEventRecord(ctx->ev_drain, ctx->compute));
+    ctx->drain_pending = true; ctx->kmers_at_drain = ctx->kmers_ub_total;
+    ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
     return MFKC_OK;
 }
 

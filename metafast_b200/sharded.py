@@ -172,3 +172,65 @@ class ShardedStep:
                 self.kc.h2d(self.stage_b.data_ptr(), h_bases[b0:b1])
                 self.kc.h2d(self.stage_o.data_ptr(), h_offs[s:e + 1])
             self._batch(self.stage_b.data_ptr(), self.stage_o.data_ptr(), max(0, e - s))
+
+
+def p2p_geometry(kmers_per_rank: int, world: int, table_bytes_per_rank: int = 0):
+    """(log2 coarse buckets, records per segment) of the peer-memory staging: a bucket's slice of the owner's
+    table (table / buckets) should be a few MiB so that it stays L2-resident while it is drained; segments get
+    2x the expected fill (~5 k-mers per record on Illumina-like reads; the minimizer skew averages out over the
+    ~500 minimizers of a segment)."""
+    tb = table_bytes_per_rank or 16 * 3 * max(kmers_per_rank // 4, 1)
+    log2 = 4
+    while log2 < 14 and (tb >> log2) > (8 << 20):
+        log2 += 1
+    seg_cap = int(2.0 * kmers_per_rank / 5 / (world << log2)) + 256
+    return log2, seg_cap
+
+
+class P2PShardedStep:
+    """Per-rank driver of the sharded counting pass over peer memory (default of bench.py for N > 1).
+
+    Every rank stages its super-k-mer records in its own HBM, bucketed by (owner, coarse bucket); after the
+    (tiny) exchange of the per-owner k-mer totals -- which doubles as the barrier -- every owner drains its
+    segments straight out of all peers' staging buffers over NVLink inside the counting kernel
+    (mfkc_p2p_drain -> drain_p2p_kernel).  torch.distributed only moves the 128-byte IPC handles and the
+    per-owner totals."""
+
+    def __init__(self, kc, dist, world: int, rank: int, batch_reads: int, read_len: int, k: int, reads_per_rank: int):
+        import torch
+        self.kc, self.dist, self.world, self.rank, self.torch = kc, dist, world, rank, torch
+        self.batch_reads, self.read_len, self.k = batch_reads, read_len, k
+        kmers = reads_per_rank * (read_len - k + 1)
+        self.log2, self.seg_cap = p2p_geometry(kmers, world)
+        kc.p2p_stage_create(self.log2, self.seg_cap)
+        mine = torch.frombuffer(bytearray(kc.p2p_export()), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda()
+        handles = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(handles, mine)
+        for r in range(world):
+            kc.p2p_attach(r, None if r == rank else bytes(handles[r].cpu().numpy().tobytes()))
+
+    def begin(self):
+        """call after kc.reset(): every rank has finished draining the previous sample before any staging buffer
+        is cleared"""
+        self.dist.barrier()
+        self.kc.p2p_stage_reset()
+
+    def _finish(self):
+        kc, world = self.kc, self.world
+        counts = kc.p2p_counts(world)                                        # synchronises this rank's extraction
+        rows = exchange_table(self.dist, [[counts[d]] for d in range(world)], device="cuda" if self.dist.get_backend() == "nccl" else None)
+        kc.p2p_drain(sum(r[0] for r in rows))
+
+    def run_device(self, d_bases: int, d_offs: int, n_reads: int):
+        for s in range(0, n_reads, self.batch_reads):
+            e = min(n_reads, s + self.batch_reads)
+            self.kc.p2p_extract(d_bases + s * self.read_len, d_offs + s * 8, e - s, (e - s) * self.read_len)
+        self._finish()
+
+    def run_host(self, h_bases: np.ndarray, h_offs: np.ndarray, n_reads: int):
+        for s in range(0, n_reads, self.batch_reads):
+            e = min(n_reads, s + self.batch_reads)
+            self.kc.p2p_submit(h_bases, h_offs[s:e + 1])
+        self._finish()

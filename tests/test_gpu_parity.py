@@ -310,6 +310,89 @@ def test_logical_shards_superkmer_exchange(built, n_shards):
             s.close()
 
 
+@pytest.mark.parametrize("n_shards,log2_buckets", [(1, 3), (2, 0), (4, 5), (8, 2), (11, 4)])
+def test_logical_shards_peer_memory_exchange(built, n_shards, log2_buckets):
+    """Peer-memory flavour of the exchange (mfkc_p2p_*) with G contexts on one GPU: every shard extracts ITS
+    slice of the reads into its own staging buffer, every owner drains its segments out of all G staging
+    buffers (same kernels as across GPUs; the pointers are attached directly instead of through CUDA IPC).
+    Merged records, summed histogram and summed read statistics must equal the unsharded result."""
+    cfg = m.synth_cfg(total_genome_bp=100000, n_genomes=4, n_read_ppm=0)
+    n = 6000
+    raw = m.synth_reads_host(cfg, 0, n)
+    bases = np.ascontiguousarray(raw).reshape(-1)
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(cfg.read_len)
+    want_rec, want_hist, _, want_stats = _oracle_c.count(bases, offsets, 31, 1, P=2)
+    from metafast_b200.sharded import merge_sorted_records
+    shards = [m.KmerCounter(31, n_shards=n_shards, shard_id=s, table_slots=1 << 15) for s in range(n_shards)]   # small tables: growth on the way
+    try:
+        seg_cap = 2 * n * 120 // 5 // (n_shards << log2_buckets) + 64
+        for s in shards:
+            s.p2p_stage_create(log2_buckets, seg_cap)
+        for s in shards:
+            for r, peer in enumerate(shards):
+                s.p2p_attach_ctx(r, peer)
+        bounds = np.linspace(0, n, n_shards + 1).astype(int) // 8 * 8
+        bounds[-1] = n
+        for rep in range(2):                                   # second pass: reset + reuse of the staging buffers
+            for s in shards:
+                s.reset()
+            for s in shards:
+                s.p2p_stage_reset()
+            bufs = []
+            for r, s in enumerate(shards):
+                lo, hi = int(bounds[r]), int(bounds[r + 1])
+                part_b = bases[lo * cfg.read_len: hi * cfg.read_len]
+                part_o = offsets[lo: hi + 1]
+                d_b = s.device_alloc(max(part_b.nbytes, 16)); d_o = s.device_alloc(part_o.nbytes)
+                if hi > lo and rep == 1:                        # host buffers through the copy pipeline
+                    s.p2p_submit(bases, offsets[lo: (lo + hi) // 2 + 1])
+                    s.p2p_submit(bases, offsets[(lo + hi) // 2: hi + 1])
+                elif hi > lo:
+                    s.h2d(d_b, part_b); s.h2d(d_o, part_o)
+                    half = (hi - lo) // 2 // 8 * 8              # two batches per shard (device batches start 16-byte aligned)
+                    s.p2p_extract(d_b, d_o, half, half * cfg.read_len)
+                    s.p2p_extract(d_b + half * cfg.read_len, d_o + half * 8, hi - lo - half, (hi - lo - half) * cfg.read_len)
+                bufs.append((s, d_b, d_o))
+            counts = [s.p2p_counts(n_shards) for s in shards]
+            assert sum(sum(c) for c in counts) == n * (cfg.read_len - 30)
+            merged, hist, stats = [], np.zeros(m.HIST_BINS, dtype=np.uint64), np.zeros(4, dtype=np.int64)
+            for r, s in enumerate(shards):
+                s.p2p_drain(sum(c[r] for c in counts))
+                s.flush()
+            for s in shards:
+                merged.append(s.emit(1))
+                hist += s.histogram()
+                st = s.stats()
+                stats += np.array([st["total_seq"], st["good_seq"], st["total_len"], st["good_len"]])
+            assert merge_sorted_records(merged) == want_rec
+            assert (hist == want_hist).all()
+            assert stats.tolist() == want_stats
+            for s, d_b, d_o in bufs:
+                s.device_free(d_b); s.device_free(d_o)
+    finally:
+        for s in shards:
+            s.close()
+
+
+def test_peer_memory_exchange_reports_overflow(built):
+    """a staging segment that is too small must surface as an error at flush, never as a silently short count"""
+    cfg = m.synth_cfg(total_genome_bp=100000, n_genomes=4, n_read_ppm=0)
+    n = 2000
+    bases = np.ascontiguousarray(m.synth_reads_host(cfg, 0, n)).reshape(-1)
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(cfg.read_len)
+    with m.KmerCounter(31, n_shards=2, shard_id=0) as a, m.KmerCounter(31, n_shards=2, shard_id=1) as b:
+        for s in (a, b):
+            s.p2p_stage_create(1, 50)
+        for s in (a, b):
+            s.p2p_attach_ctx(0, a); s.p2p_attach_ctx(1, b)
+        d_b = a.device_alloc(bases.nbytes); d_o = a.device_alloc(offsets.nbytes)
+        a.h2d(d_b, bases); a.h2d(d_o, offsets)
+        a.p2p_extract(d_b, d_o, n, bases.size)
+        with pytest.raises(m.MfkcError):
+            a.flush()
+        a.device_free(d_b); a.device_free(d_o)
+
+
 # ---------------------------------------------------------------- features-calculator
 def _components_from(counts, rng, n_comp=40):
     keys = sorted(counts)
