@@ -130,55 +130,75 @@ __device__ __forceinline__ bool table_upsert_n(Slot *__restrict__ tab, uint64_t 
 }
 
 // ------------------------------------------------------------------------------------------
-// Windowed placement (tables drained in shared memory, see drain_smem_kernel).  With small regions
-// (2^12 slots) the minimizer skew makes some regions overfull, and linear probing that runs on into
-// the neighbouring regions would cascade.  So a key lives either
+// Windowed placement of the minimizer-placed tables.  A heavy minimizer (poly-A tails, low-complexity
+// sequence; or plain skew when regions are small) can own more distinct k-mers than its region has
+// slots, and linear probing that runs on into the neighbouring regions would build one huge cluster
+// that every later insert walks.  So a key lives either
 //   (1) in its PRIMARY window: the first `win` slots from its home slot, wrapping inside its region, or
-//   (2) if that window held `win` other keys when it arrived, at its SECONDARY position: ordinary
-//       linear probing over the whole table from home_slot(key ^ SALT), i.e. in the free slots of
-//       uniformly chosen regions.
-// Slots never become empty again, so the rule is stable: a key that went to (2) finds its primary
-// window full for ever, and a key placed in (1) is met before any empty slot of its window.
+//   (2) if that window held `win` other keys when it arrived, in the first of its SECONDARY windows
+//       with room: `win` slots at home_slot(key ^ SALT * a), a = 1, 2, ... (a fresh, uniformly
+//       distributed position per attempt, i.e. the free slots of arbitrary regions).
+// Slots never become empty again, so the rule is stable: a key that went to (2) finds its earlier
+// windows full for ever, and a key placed in a window is met before any empty slot of that window.
 // win == 0 selects the plain rule (linear probing from the home slot, running on).
 // ------------------------------------------------------------------------------------------
 constexpr unsigned long long SECONDARY_SALT = 0x9ddfea08eb382d69ULL;
-__device__ __forceinline__ uint64_t secondary_home(uint64_t key, uint64_t cap) { return home_slot(key ^ SECONDARY_SALT, cap); }
+__device__ __forceinline__ uint64_t secondary_home(uint64_t key, uint64_t cap, uint32_t attempt) {
+    return home_slot(key ^ (SECONDARY_SALT * (unsigned long long)attempt), cap);
+}
+
+// one slot of a probe sequence: returns true when the key was found or placed there
+template <bool ONE>
+__device__ __forceinline__ bool slot_try(Slot *__restrict__ tab, uint64_t i, uint64_t key, uint32_t inc, bool &claimed) {
+    const ulonglong2 sl = ld_cg_u64x2(&tab[i]);
+    unsigned long long cur = sl.x;
+    bool mine = false;
+    if (cur == EMPTY_KEY) {
+        cur = atomicCAS(&tab[i].key, EMPTY_KEY, (unsigned long long)key);
+        if (cur == EMPTY_KEY) { mine = true; cur = key; }
+    }
+    if (cur != key) return false;
+    if (ONE) { if (mine || (uint32_t)sl.y < MAX_COUNT) atomicAdd(&tab[i].count, 1u); }
+    else {
+        uint32_t old = *(volatile uint32_t *)&tab[i].count;
+        for (;;) {
+            if (old >= MAX_COUNT) break;
+            uint32_t nv = old + inc; if (nv > MAX_COUNT || nv < old) nv = MAX_COUNT;
+            const uint32_t seen = atomicCAS(&tab[i].count, old, nv);
+            if (seen == old) break;
+            old = seen;
+        }
+    }
+    claimed = mine;
+    return true;
+}
+
+// Secondary positions: windows of `win` slots at home_slot(key ^ SALT * a), a = 1, 2, ... -- a fresh uniform position per
+// attempt, so that a key never has to walk through a long run of full slots (an overfull region is one).
+template <bool ONE>
+__device__ __forceinline__ bool secondary_upsert(Slot *__restrict__ tab, uint64_t cap, uint32_t win, uint64_t key, uint32_t inc) {
+    bool claimed = false;
+    for (uint32_t a = 1;; a++) {
+        uint64_t i = secondary_home(key, cap, a);
+        for (uint32_t st = 0; st < win; st++) {
+            if (slot_try<ONE>(tab, i, key, inc, claimed)) return claimed;
+            if (++i == cap) i = 0;
+        }
+    }
+}
 
 template <bool ONE>
 __device__ __forceinline__ bool placed_upsert_at(Slot *__restrict__ tab, uint64_t cap, int shift, uint32_t win,
                                                  uint64_t home, uint64_t key, uint32_t inc) {
-    if (win) {
-        const uint64_t mask = (1ull << shift) - 1ull;
-        const uint64_t rbase = home & ~mask;
-        uint64_t off = home & mask;
-        const uint32_t steps = (uint64_t)win < mask + 1 ? win : (uint32_t)(mask + 1);
-        for (uint32_t st = 0; st < steps; st++, off = (off + 1) & mask) {
-            const uint64_t i = rbase | off;
-            const ulonglong2 sl = ld_cg_u64x2(&tab[i]);
-            unsigned long long cur = sl.x;
-            bool claimed = false;
-            if (cur == EMPTY_KEY) {
-                cur = atomicCAS(&tab[i].key, EMPTY_KEY, (unsigned long long)key);
-                if (cur == EMPTY_KEY) { claimed = true; cur = key; }
-            }
-            if (cur == key) {
-                if (ONE) { if (claimed || (uint32_t)sl.y < MAX_COUNT) atomicAdd(&tab[i].count, 1u); }
-                else {
-                    uint32_t old = *(volatile uint32_t *)&tab[i].count;
-                    for (;;) {
-                        if (old >= MAX_COUNT) break;
-                        uint32_t nv = old + inc; if (nv > MAX_COUNT || nv < old) nv = MAX_COUNT;
-                        const uint32_t seen = atomicCAS(&tab[i].count, old, nv);
-                        if (seen == old) break;
-                        old = seen;
-                    }
-                }
-                return claimed;
-            }
-        }
-        home = secondary_home(key, cap);
-    }
-    return ONE ? table_upsert1_at(tab, cap, home, key) : table_upsert_n_at(tab, cap, home, key, inc);
+    if (!win) return ONE ? table_upsert1_at(tab, cap, home, key) : table_upsert_n_at(tab, cap, home, key, inc);
+    const uint64_t mask = (1ull << shift) - 1ull;
+    const uint64_t rbase = home & ~mask;
+    uint64_t off = home & mask;
+    const uint32_t steps = (uint64_t)win < mask + 1 ? win : (uint32_t)(mask + 1);
+    bool claimed = false;
+    for (uint32_t st = 0; st < steps; st++, off = (off + 1) & mask)
+        if (slot_try<ONE>(tab, rbase | off, key, inc, claimed)) return claimed;
+    return secondary_upsert<ONE>(tab, cap, win, key, inc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1298,7 +1318,7 @@ drain_fallback_kernel(SkmStage st, int k, Slot *__restrict__ tab, uint64_t cap, 
     if (ns > sp.cap) ns = sp.cap;
     for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < ns; i += gridDim.x * 256) {
         const unsigned long long key = sp.keys[i];
-        claimed += table_upsert1_at(tab, cap, secondary_home(key, cap), key) ? 1u : 0u;
+        claimed += secondary_upsert<true>(tab, cap, SMEM_WIN, key, 1u) ? 1u : 0u;
     }
     const uint32_t nd = *sp.n_dirty;
     const uint64_t slot_mask = (1ull << st.region_shift) - 1ull;
@@ -1318,7 +1338,7 @@ drain_fallback_kernel(SkmStage st, int k, Slot *__restrict__ tab, uint64_t cap, 
                     return;
                 }
             }
-            claimed += table_upsert1_at(tab, cap, secondary_home(key, cap), key) ? 1u : 0u;
+            claimed += secondary_upsert<true>(tab, cap, SMEM_WIN, key, 1u) ? 1u : 0u;
         });
         __syncthreads();
         if (threadIdx.x == 0) st.cursor[region] = 0;

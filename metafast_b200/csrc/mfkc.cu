@@ -230,7 +230,15 @@ static TabSoA tab_soa_of(void *base, uint64_t cap) {
 }
 static TabSoA tab_soa(const mfkc_ctx *ctx) { return tab_soa_of(ctx->tab, ctx->cap); }
 static TabSoAOps tab_soa_ops(const mfkc_ctx *ctx) { TabSoAOps o; o.t = tab_soa(ctx); return o; }
-static uint32_t table_win(const mfkc_ctx *ctx) { return ctx->smem_drain && ctx->place && !ctx->k128 ? SMEM_WIN : 0u; }
+// Windowed placement for every minimizer-placed table (see placed_upsert_at): a heavy minimizer (poly-A tails, low-complexity
+// sequence) can own far more distinct k-mers than one region has slots; with plain linear probing they form one huge cluster
+// running through the following regions and every insert walks it (measured: 700 ms for one drain on the GPU that owns poly-A
+// at 8 x 20 M reads).  With the window the surplus goes to uniformly spread secondary positions instead.
+static uint32_t table_win(const mfkc_ctx *ctx) {
+    static const int env_win = getenv("MFKC_WIN") ? atoi(getenv("MFKC_WIN")) : -1;
+    if (!ctx->place || ctx->k128 || ctx->soa) return 0u;
+    return env_win >= 0 ? (uint32_t)env_win : SMEM_WIN;
+}
 static TabAoS tab_aos(const mfkc_ctx *ctx) { TabAoS o; o.tab = ctx->tab; o.cap = ctx->cap; return o; }
 
 // plain_aos: a 16-byte-slot helper table (the --selected set) whatever the layout of the main table
