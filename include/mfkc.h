@@ -200,6 +200,35 @@ int  mfkc_fc_add_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offs
  * breadth = (double)found / cnt is left to the host (Java formatting). */
 int  mfkc_fc_features(mfkc_ctx *ctx, int64_t threshold, int64_t *vec, uint64_t *found, uint64_t *cnt);
 
+/* ---- set algebra over .kmers.bin files: the (k-mer -> short) maps behind kmers-filter,
+ * unique-kmers-multi and kmers-samples-counter, kept on the device as key-sorted arrays ----------------------------
+ * mfkc_kset = one BigLong2ShortHashMap of those tools.  Values are Java shorts with Java's arithmetic: addAndBound
+ * saturates at 32767 ([itmo]/utils/NumUtils.java:21-26), put(get + x) wraps, getWithZero reads an absent key and a
+ * stored -1 as 0 ([itmo]/structures/map/Long2ShortHashMap.java:160-183).  Output is in ascending key order (the
+ * reference writes hash-map iteration order; the order is not part of the format). */
+typedef struct mfkc_kset mfkc_kset;
+int  mfkc_kset_create(mfkc_ctx *ctx, mfkc_kset **out);
+void mfkc_kset_destroy(mfkc_kset *ks);
+/* IOUtils.loadKmers (src/io/IOUtils.java:369-401; Kmers2HMWorker.processKmer :249-257): records with freq >
+ * freq_threshold are added with addAndBound.  Any chunking and any number of files; mfkc_kset_load_finish after the last. */
+int  mfkc_kset_load_records(mfkc_kset *ks, const uint8_t *be_records, uint64_t n_records, int32_t freq_threshold);
+int  mfkc_kset_load_finish(mfkc_kset *ks);
+int  mfkc_kset_size(mfkc_kset *ks, uint64_t *n);                     /* hm.size() */
+int  mfkc_kset_reset_values(mfkc_kset *ks);                          /* hm.resetValues(), src/tools/KmersSamplesCounter.java:92 */
+/* The entry loops of the tools, for every (key, v) of src with v > thr:
+ *   MFKC_KSET_ADD   dst.put(key, (short)(dst.getWithZero(key) + v))   src/tools/UniqueKmersMultipleSamplesFinder.java:106-108
+ *   MFKC_KSET_INC   dst.put(key, (short)(dst.getWithZero(key) + 1))   same :109; src/tools/KmersSamplesCounter.java:102-105
+ *   MFKC_KSET_ZERO  if (dst.get(key) > thr) dst.put(key, 0)            src/tools/UniqueKmersMultipleSamplesFinder.java:126-129 */
+enum { MFKC_KSET_ADD = 0, MFKC_KSET_INC = 1, MFKC_KSET_ZERO = 2 };
+int  mfkc_kset_update(mfkc_kset *dst, const mfkc_kset *src, int op, int32_t thr);
+/* IOUtils.filterAndPrintKmers (src/io/IOUtils.java:101-123): entries of hm with value > threshold and
+ * filter.getWithZero(key) > filter_threshold; filter = NULL keeps only the first condition (the selection of
+ * IOUtils.printKmers, src/io/IOUtils.java:61).  *n_good = how many; fetch them as 10-byte BE records with _next. */
+int  mfkc_kset_select_begin(mfkc_kset *hm, const mfkc_kset *filter, int32_t threshold, int32_t filter_threshold, uint64_t *n_good);
+int  mfkc_kset_select_next(mfkc_kset *hm, uint8_t *out, size_t cap, size_t *written);
+/* hist[v] = number of entries with value v, all entries (the statistics of IOUtils.printKmers, src/io/IOUtils.java:59) */
+int  mfkc_kset_histogram(mfkc_kset *ks, uint64_t hist[MFKC_HIST_BINS]);
+
 /* ---- host side of the path (CPU; no GPU needed): the parser rules of
  * [itmo]/io/ReadersUtils.java:27-102, readers/FastaReader.java:54-108,
  * readers/FastqReader.java:53-114, readers/FastaReaderFromXQSource.java:62-85 and the

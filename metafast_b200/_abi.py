@@ -103,6 +103,16 @@ SIGNATURES = {
     "mfkc_fc_add_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "mfkc_fc_add_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "mfkc_fc_features": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mfkc_kset_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mfkc_kset_destroy": (None, [C.c_void_p]),
+    "mfkc_kset_load_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32]),
+    "mfkc_kset_load_finish": (C.c_int, [C.c_void_p]),
+    "mfkc_kset_size": (C.c_int, [C.c_void_p, u64p]),
+    "mfkc_kset_reset_values": (C.c_int, [C.c_void_p]),
+    "mfkc_kset_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int32]),
+    "mfkc_kset_select_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, u64p]),
+    "mfkc_kset_select_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "mfkc_kset_histogram": (C.c_int, [C.c_void_p, u64p]),
     "mfkc_reader_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),
     "mfkc_reader_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     "mfkc_reader_counters": (C.c_int, [C.c_void_p, u64p]),

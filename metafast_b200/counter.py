@@ -267,6 +267,106 @@ class KmerCounter(_Ctx):
         self._ck(self.lib.mfkc_p2p_drain(self.h, n_kmers_in))
 
 
+class KmerSet:
+    """One (k-mer -> short) map of the .kmers.bin set-algebra tools on the device (mfkc_kset_*): the
+    BigLong2ShortHashMap of src/tools/KmersFilter.java, UniqueKmersMultipleSamplesFinder.java and
+    KmersSamplesCounter.java.  `ctx` is any KmerCounter / FeaturesCalculator context (device + streams)."""
+    ADD, INC, ZERO = 0, 1, 2
+
+    def __init__(self, ctx: "_Ctx"):
+        self.ctx, self.lib = ctx, ctx.lib
+        h = C.c_void_p()
+        ctx._ck(self.lib.mfkc_kset_create(ctx.h, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mfkc_kset_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @classmethod
+    def load(cls, ctx: "_Ctx", datas: Sequence[bytes], threshold: int, chunk: int = 16777200) -> "KmerSet":
+        """IOUtils.loadKmers(files, threshold) (src/io/IOUtils.java:369-401)"""
+        ks = cls(ctx)
+        for d in datas:
+            a = np.frombuffer(d, dtype=np.uint8)
+            for s in range(0, len(d), chunk):
+                part = a[s:s + chunk]
+                ctx._ck(ks.lib.mfkc_kset_load_records(ks.h, _ptr(part), part.nbytes // 10, threshold))
+        ctx._ck(ks.lib.mfkc_kset_load_finish(ks.h))
+        return ks
+
+    def size(self) -> int:
+        n = C.c_uint64()
+        self.ctx._ck(self.lib.mfkc_kset_size(self.h, C.byref(n)))
+        return n.value
+
+    def reset_values(self):
+        self.ctx._ck(self.lib.mfkc_kset_reset_values(self.h))
+
+    def update(self, src: "KmerSet", op: int, thr: int):
+        self.ctx._ck(self.lib.mfkc_kset_update(self.h, src.h, op, thr))
+
+    def select(self, filt: Optional["KmerSet"], threshold: int, filter_threshold: int = 0, chunk: int = 16777200) -> bytes:
+        """IOUtils.filterAndPrintKmers (src/io/IOUtils.java:101-123); records in ascending key order"""
+        n = C.c_uint64()
+        self.ctx._ck(self.lib.mfkc_kset_select_begin(self.h, filt.h if filt is not None else None, threshold, filter_threshold, C.byref(n)))
+        out = np.empty(n.value * 10, dtype=np.uint8)
+        pos, w = 0, C.c_size_t()
+        while pos < out.nbytes:
+            self.ctx._ck(self.lib.mfkc_kset_select_next(self.h, C.c_void_p(out.ctypes.data + pos), min(chunk, out.nbytes - pos), C.byref(w)))
+            if w.value == 0:
+                break
+            pos += w.value
+        assert pos == out.nbytes
+        return out.tobytes()
+
+    def histogram(self) -> np.ndarray:
+        h = np.zeros(_abi.HIST_BINS, dtype=np.uint64)
+        self.ctx._ck(self.lib.mfkc_kset_histogram(self.h, h.ctypes.data_as(_abi.u64p)))
+        return h
+
+
+def kmers_filter(ctx: "_Ctx", inputs: Sequence[bytes], filters: Sequence[bytes], b: int = 1, max_thresh: int = 0):
+    """kmers-filter (src/tools/KmersFilter.java:94-110): per input file -> (hm.size(), filtered records)"""
+    out = []
+    with KmerSet.load(ctx, filters, b) as flt:
+        for data in inputs:
+            with KmerSet.load(ctx, [data], b) as hm:
+                out.append((hm.size(), hm.select(flt, b, max_thresh * len(filters))))
+    return out
+
+
+def unique_kmers_multi(ctx: "_Ctx", inputs: Sequence[bytes], filters: Sequence[bytes], b: int = 1, min_samples: int = 1,
+                       max_samples: int = 1):
+    """unique-kmers-multi (src/tools/UniqueKmersMultipleSamplesFinder.java:97-148) -> (hm.size(), {i: records})"""
+    with KmerSet(ctx) as hm, KmerSet(ctx) as cnt:
+        for data in inputs:
+            with KmerSet.load(ctx, [data], b) as tmp:
+                hm.update(tmp, KmerSet.ADD, b)
+                cnt.update(tmp, KmerSet.INC, b)
+        for data in filters:
+            with KmerSet.load(ctx, [data], b) as flt:
+                hm.update(flt, KmerSet.ZERO, b)
+        return hm.size(), {i: hm.select(cnt, b, i - 1) for i in range(min_samples, max_samples + 1)}
+
+
+def kmers_samples_counter(ctx: "_Ctx", inputs: Sequence[bytes], b: int = 1):
+    """kmers-samples-counter (src/tools/KmersSamplesCounter.java:90-119) -> (hm.size(), records, histogram)"""
+    with KmerSet.load(ctx, inputs, b) as hm:
+        hm.reset_values()
+        for data in inputs:
+            with KmerSet.load(ctx, [data], b) as one:
+                hm.update(one, KmerSet.INC, b)
+        return hm.size(), hm.select(None, 0), hm.histogram()
+
+
 class FeaturesCalculator(_Ctx):
     """features-calculator on the device (K6/K7/K8)."""
 

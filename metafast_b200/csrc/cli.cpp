@@ -107,7 +107,9 @@ Args parse_args(int argc, char **argv) {
         {"-cm", "components-file"}, {"--components-file", "components-file"}, {"-ka", "kmers"}, {"--kmers", "kmers"},
         {"--selected", "selected"}, {"--threshold", "threshold"}, {"-p", "available-processors"},
         {"--available-processors", "available-processors"}, {"--gpu", "gpu"}, {"--gpu-variant", "gpu-variant"},
-        {"--force", "force"}, {"-v", "verbose"}, {"--verbose", "verbose"}, {"--long-kmers", "long-kmers"}};
+        {"--force", "force"}, {"-v", "verbose"}, {"--verbose", "verbose"}, {"--long-kmers", "long-kmers"},
+        {"--k-mers", "reads"}, {"--filter-kmers", "filter-kmers"}, {"--max-thresh", "max-thresh"},
+        {"--min-samples", "min-samples"}, {"--max-samples", "max-samples"}, {"--min-seq-len", "min-seq-len"}, {"-l", "min-seq-len"}};
     Args a;
     std::string cur;
     for (int i = 1; i < argc; i++) {
@@ -230,13 +232,13 @@ std::string count_sample(mfkc_ctx *ctx, int k, int b, const std::vector<std::str
     return out_file;
 }
 
-mfkc_ctx *make_ctx(int k, const Gpu &g, uint64_t expected_kmers, bool long_kmers = false) {
+mfkc_ctx *make_ctx(int k, const Gpu &g, uint64_t expected_kmers, bool long_kmers = false, int min_seq_len = 0) {
     if (k <= 0) die("The size of k-mer must be at least 1.");               // KmersCounterMain.java:66-69
     if (k > 31 && !long_kmers) die("The size of k-mer must be no more than 31.");   // KmersCounterMain.java:70-73
     if (k > 63) die("The size of k-mer must be no more than 63.");
     mfkc_cfg cfg; memset(&cfg, 0, sizeof cfg);
     cfg.struct_size = sizeof cfg; cfg.k = k; cfg.device = g.device; cfg.variant = g.variant;
-    cfg.expected_kmers = expected_kmers;
+    cfg.expected_kmers = expected_kmers; cfg.min_seq_len = min_seq_len;
     mfkc_ctx *ctx = nullptr;
     const int rc = mfkc_create(&cfg, &ctx);
     if (rc != MFKC_OK) die("%s (libmfkc %d)", mfkc_last_error(nullptr), rc);
@@ -289,7 +291,9 @@ int tool_counter(const Args &a, bool many) {
     }
     uint64_t biggest = 0;
     for (const auto &s : samples) biggest = std::max(biggest, estimate_bases(s.second));
-    mfkc_ctx *ctx = make_ctx(k, g, biggest, a.has("long-kmers"));
+    // -l / --min-seq-len: the counting call of component-cutter's front half, IOUtils.loadReads(sequences, k, minLen)
+    // (src/tools/ComponentCutterMain.java:81-82, src/io/IOUtils.java:761); kmer-counter itself passes 0
+    mfkc_ctx *ctx = make_ctx(k, g, biggest, a.has("long-kmers"), parse_int(a, "min-seq-len", false, 0));
     std::vector<std::string> outs;
     for (const auto &s : samples) outs.push_back(count_sample(ctx, k, b, s.second, s.first, out_dir, st_dir));
     mfkc_destroy(ctx);
@@ -388,6 +392,156 @@ int tool_features(const Args &a) {
     return 0;
 }
 
+// ---- set algebra over .kmers.bin files: kmers-filter, unique-kmers-multi, kmers-samples-counter.
+// "-i" / "--k-mers" = input k-mer files (the shared "-i" alias stores them under "reads").
+struct KSet {                                                            // one BigLong2ShortHashMap on the device
+    mfkc_ctx *ctx; mfkc_kset *h = nullptr;
+    explicit KSet(mfkc_ctx *c) : ctx(c) { CK(ctx, mfkc_kset_create(ctx, &h)); }
+    ~KSet() { mfkc_kset_destroy(h); }
+    KSet(const KSet &) = delete;
+    // IOUtils.loadKmers (src/io/IOUtils.java:369-401) incl. its debug lines' data
+    void load(const std::vector<std::string> &files, int thr) {
+        for (const auto &f : files) {
+            info("Loading file %s...", base_name(f).c_str());
+            const auto recs = slurp(f);
+            const size_t chunk = 16777200;                                  // src/io/IOUtils.java:30
+            for (size_t p = 0; p < recs.size(); p += chunk) CK(ctx, mfkc_kset_load_records(h, recs.data() + p, std::min(chunk, recs.size() - p) / 10, thr));
+        }
+        CK(ctx, mfkc_kset_load_finish(h));
+    }
+    uint64_t size() const { uint64_t n = 0; mfkc_kset_size(h, &n); return n; }
+    // IOUtils.filterAndPrintKmers (src/io/IOUtils.java:101-123) -> number written
+    uint64_t print(const KSet *filter, int thr, int fthr, const std::string &out_file) {
+        uint64_t good = 0;
+        CK(ctx, mfkc_kset_select_begin(h, filter ? filter->h : nullptr, thr, fthr, &good));
+        FILE *f = fopen(out_file.c_str(), "wb");
+        if (!f) die("Can't write %s", out_file.c_str());
+        std::vector<uint8_t> buf(16777200);
+        for (;;) {
+            size_t w = 0;
+            CK(ctx, mfkc_kset_select_next(h, buf.data(), buf.size(), &w));
+            if (!w) break;
+            if (fwrite(buf.data(), 1, w, f) != w) die("Can't write %s", out_file.c_str());
+        }
+        fclose(f);
+        return good;
+    }
+};
+
+std::vector<std::string> kmers_inputs(const Args &a) {
+    auto v = a.many("reads");
+    if (v.empty()) die("Missing mandatory parameter --k-mers");
+    return v;
+}
+void check_k(int k) {
+    if (k <= 0) die("The size of k-mer must be at least 1.");
+    if (k > 31) die("The size of k-mer must be no more than 31.");
+}
+
+// src/tools/KmersFilter.java:76-116
+int tool_kmers_filter(const Args &a) {
+    const int k = parse_int(a, "k", true, 0); check_k(k);
+    const auto inputs = kmers_inputs(a);
+    const auto filters = a.many("filter-kmers");
+    if (filters.empty()) die("Missing mandatory parameter --filter-kmers");
+    const int b = parse_int(a, "maximal-bad-frequence", false, 1), max_thresh = parse_int(a, "max-thresh", false, 0);
+    const std::string work = a.one("work-dir", "workDir"), out_dir = a.one("output-dir", work + "/kmers");
+    mkdirs(out_dir);
+    mfkc_ctx *ctx = make_ctx(k, gpu_opts(a), 0);
+    {
+        KSet filter_hm(ctx);
+        filter_hm.load(filters, b);
+        for (const auto &file : inputs) {
+            KSet hm(ctx);
+            hm.load({file}, b);
+            std::string name = base_name(file);
+            for (size_t p; (p = name.find(".kmers.bin")) != std::string::npos;) name.erase(p, 10);   // replaceAll(".kmers.bin", "")
+            const std::string out_file = out_dir + "/" + name + ".kmers.bin";
+            const uint64_t c = hm.print(&filter_hm, b, max_thresh * (int)filters.size(), out_file);
+            info("%s k-mers found, %s (%.1f%%) of them survived after filtering", group_digits(hm.size()).c_str(), group_digits(c).c_str(),
+                 c * 100.0 / hm.size());
+            info("Filtered k-mers printed to %s", out_file.c_str());
+            printf("%s\n", out_file.c_str());
+        }
+    }
+    mfkc_destroy(ctx);
+    return 0;
+}
+
+// src/tools/UniqueKmersMultipleSamplesFinder.java:82-166
+int tool_unique_kmers_multi(const Args &a) {
+    const int k = parse_int(a, "k", true, 0); check_k(k);
+    const auto inputs = kmers_inputs(a);
+    const auto filters = a.many("filter-kmers");
+    if (filters.empty()) die("Missing mandatory parameter --filter-kmers");
+    const int b = parse_int(a, "maximal-bad-frequence", false, 1);
+    const int min_s = parse_int(a, "min-samples", false, 1), max_s = parse_int(a, "max-samples", false, 1);
+    if (min_s > max_s) die("--min-samples parameter cannot be greater than --max-samples parameter.");
+    const std::string work = a.one("work-dir", "workDir"), out_dir = a.one("output-dir", work + "/kmers"), st_dir = a.one("stats-dir", work + "/stats");
+    mfkc_ctx *ctx = make_ctx(k, gpu_opts(a), 0);
+    {
+        KSet hm(ctx), hm_cnt(ctx);
+        for (const auto &file : inputs) {
+            KSet tmp(ctx);
+            tmp.load({file}, b);
+            CK(ctx, mfkc_kset_update(hm.h, tmp.h, MFKC_KSET_ADD, b));
+            CK(ctx, mfkc_kset_update(hm_cnt.h, tmp.h, MFKC_KSET_INC, b));
+        }
+        for (const auto &file : filters) {
+            KSet filt(ctx);
+            filt.load({file}, b);
+            CK(ctx, mfkc_kset_update(hm.h, filt.h, MFKC_KSET_ZERO, b));
+        }
+        mkdirs(out_dir); mkdirs(st_dir);
+        for (int i = min_s; i < max_s + 1; i++) {
+            const std::string out_file = out_dir + "/filtered_" + std::to_string(i) + ".kmers.bin";
+            const uint64_t c = hm.print(&hm_cnt, b, i - 1, out_file);
+            info("%s k-mers found, %s (%.1f%%) of them is good (present in one dataset and missing in other)", group_digits(hm.size()).c_str(),
+                 group_digits(c).c_str(), c * 100.0 / hm.size());
+            info("Good k-mers printed to %s", out_file.c_str());
+            printf("%s\n", out_file.c_str());
+        }
+    }
+    mfkc_destroy(ctx);
+    return 0;
+}
+
+// src/tools/KmersSamplesCounter.java:66-131
+int tool_kmers_samples_counter(const Args &a) {
+    const int k = parse_int(a, "k", true, 0); check_k(k);
+    const auto inputs = kmers_inputs(a);
+    const int b = parse_int(a, "maximal-bad-frequence", false, 1);
+    const std::string work = a.one("work-dir", "workDir"), out_dir = a.one("output-dir", work + "/kmers"), st_dir = a.one("stats-dir", work + "/stats");
+    mkdirs(out_dir); mkdirs(st_dir);
+    mfkc_ctx *ctx = make_ctx(k, gpu_opts(a), 0);
+    {
+        KSet hm(ctx);
+        hm.load(inputs, b);
+        CK(ctx, mfkc_kset_reset_values(hm.h));
+        for (const auto &file : inputs) {
+            KSet one(ctx);
+            one.load({file}, b);
+            CK(ctx, mfkc_kset_update(hm.h, one.h, MFKC_KSET_INC, b));
+        }
+        const std::string out_file = out_dir + "/n_samples.kmers.bin", st_file = st_dir + "/n_samples.stat.txt";
+        const uint64_t c = hm.print(nullptr, 0, 0, out_file);               // IOUtils.printKmers(hm, 0, outFile, stFile)
+        static uint64_t hist[MFKC_HIST_BINS];
+        CK(ctx, mfkc_kset_histogram(hm.h, hist));
+        if (mfkc_write_stat_file(st_file.c_str(), hist) != MFKC_OK) die("Can't write %s", st_file.c_str());
+        const uint64_t size = hm.size();
+        info("%s k-mers found, %s (%.1f%%) of them is good (not erroneous)", group_digits(size).c_str(), group_digits(c).c_str(), c * 100.0 / size);
+        if (size == 0) warn("No k-mers found in reads! Perhaps you reads file is empty or k-mer size is too big");
+        else if (c == 0 || c < (uint64_t)(size * 0.03)) warn("Too few good k-mers were found! Perhaps you should decrease k-mer size or --maximal-bad-frequency value");
+        const uint64_t all = (1ull << (2 * k)) / 2;
+        if (size == all) warn("All possible k-mers were found in reads! Perhaps you should increase k-mer size");
+        else if (size >= (uint64_t)(all * 0.99)) warn("Almost all possible k-mers were found in reads! Perhaps you should increase k-mer size");
+        info("Good k-mers printed to %s", out_file.c_str());
+        printf("%s\n", out_file.c_str());
+    }
+    mfkc_destroy(ctx);
+    return 0;
+}
+
 // ---- gen-reads: synthetic FASTQ / FASTA for tests (BASELINE.md section 4 generator)
 int tool_gen(int argc, char **argv) {
     // mfkc_cli gen-reads <out.fastq|out.fa> <n_reads> [sample] [total_genome_bp] [n_genomes]
@@ -427,5 +581,9 @@ int main(int argc, char **argv) {
     if (a.tool == "kmer-counter-many") return tool_counter(a, true);
     if (a.tool == "kmer-counter") return tool_counter(a, false);
     if (a.tool == "features-calculator") return tool_features(a);
-    die("Tool '%s' is outside the hot path this build replaces (kmer-counter-many, kmer-counter, features-calculator)", a.tool.c_str());
+    if (a.tool == "kmers-filter") return tool_kmers_filter(a);
+    if (a.tool == "unique-kmers-multi") return tool_unique_kmers_multi(a);
+    if (a.tool == "kmers-samples-counter") return tool_kmers_samples_counter(a);
+    die("Tool '%s' is outside the hot path this build replaces (kmer-counter-many, kmer-counter, features-calculator, kmers-filter, "
+        "unique-kmers-multi, kmers-samples-counter)", a.tool.c_str());
 }

@@ -11,6 +11,7 @@
 #include "kernels.cuh"
 #include "kernels128.cuh"
 #include "radix_sort.cuh"
+#include "kset.cuh"
 #include "synth.h"
 
 using namespace mfkc;
@@ -1969,3 +1970,5 @@ extern "C" int mfkc_gups_ex(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, i
 extern "C" int mfkc_gups(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, float *ms) {
     return mfkc_gups_ex(ctx, bytes, n_updates, 1, 0, 0, ms);
 }
+
+#include "kset_api.inl"

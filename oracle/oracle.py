@@ -419,6 +419,74 @@ def load_kmers(datas: Sequence[bytes], threshold: int, k: int = 31) -> Dict[int,
 
 
 # --------------------------------------------------------------------------
+# set algebra over .kmers.bin files
+# --------------------------------------------------------------------------
+def _java_short(x: int) -> int:
+    """(short) cast: wraps to 16 bits, signed."""
+    x &= 0xFFFF
+    return x - 0x10000 if x >= 0x8000 else x
+
+
+def _get(hm: Dict[int, int], key: int) -> int:
+    """Long2ShortHashMap.get ([itmo]/structures/map/Long2ShortHashMap.java:160-175): -1 when absent."""
+    return hm.get(key, -1)
+
+
+def _get_with_zero(hm: Dict[int, int], key: int) -> int:
+    """Long2ShortHashMap.getWithZero (:178-183): an absent key AND a stored -1 read as 0."""
+    v = _get(hm, key)
+    return 0 if v == -1 else v
+
+
+def _records_of(entries: Iterable[Tuple[int, int]]) -> bytes:
+    """10-byte BE records in ascending key order (the reference writes iteration order; compare sorted)."""
+    return b"".join(struct.pack(">Qh", key, v) for key, v in sorted(entries))
+
+
+def filter_and_print_kmers(hm: Dict[int, int], filter_hm: Dict[int, int], threshold: int, filter_threshold: int) -> bytes:
+    """src/io/IOUtils.java:101-123."""
+    return _records_of((key, v) for key, v in hm.items() if v > threshold and _get_with_zero(filter_hm, key) > filter_threshold)
+
+
+def kmers_filter(inputs: Sequence[bytes], filters: Sequence[bytes], b: int = 1, max_thresh: int = 0) -> List[Tuple[int, bytes]]:
+    """src/tools/KmersFilter.java:94-110: per input file -> (hm.size(), filtered records)."""
+    filter_hm = load_kmers(filters, b)
+    out = []
+    for data in inputs:
+        hm = load_kmers([data], b)
+        out.append((len(hm), filter_and_print_kmers(hm, filter_hm, b, max_thresh * len(filters))))
+    return out
+
+
+def unique_kmers_multi(inputs: Sequence[bytes], filters: Sequence[bytes], b: int = 1, min_samples: int = 1,
+                       max_samples: int = 1) -> Tuple[int, Dict[int, bytes]]:
+    """src/tools/UniqueKmersMultipleSamplesFinder.java:97-148 -> (hm.size(), {i: records of filtered_i.kmers.bin})."""
+    hm: Dict[int, int] = {}
+    hm_cnt: Dict[int, int] = {}
+    for data in inputs:
+        for key, value in load_kmers([data], b).items():
+            if value > b:
+                hm[key] = _java_short(_get_with_zero(hm, key) + value)              # :107-108, (short) wraps
+                hm_cnt[key] = _java_short(_get_with_zero(hm_cnt, key) + 1)          # :109
+    for data in filters:
+        for key, value in load_kmers([data], b).items():
+            if value > b and _get(hm, key) > b:                                      # :127-129
+                hm[key] = 0
+    return len(hm), {i: filter_and_print_kmers(hm, hm_cnt, b, i - 1) for i in range(min_samples, max_samples + 1)}
+
+
+def kmers_samples_counter(inputs: Sequence[bytes], b: int = 1) -> Tuple[int, bytes, str]:
+    """src/tools/KmersSamplesCounter.java:90-119 -> (hm.size(), n_samples.kmers.bin, n_samples.stat.txt)."""
+    hm = {key: 0 for key in load_kmers(inputs, b)}                                   # loadKmers + resetValues
+    for data in inputs:
+        for key, value in load_kmers([data], b).items():
+            if value > b:
+                hm[key] = _java_short(_get_with_zero(hm, key) + 1)
+    records = _records_of((key, v) for key, v in hm.items() if v > 0)                # printKmers(hm, 0, ...)
+    return len(hm), records, stat_txt(hm)
+
+
+# --------------------------------------------------------------------------
 # features-calculator (a10-a13)
 # --------------------------------------------------------------------------
 def load_components(data: bytes, k: int = 31) -> List[Tuple[int, List[int]]]:

@@ -109,3 +109,48 @@ def test_features_calculator_cli(built, tmp_path):
     vec, breadth, _, _ = orc.features(comps, acc, 3, selected)
     assert open(fw2 / "vectors" / "meta_test_2.vec").read() == orc.vec_text(vec)
     assert open(fw2 / "vectors" / "meta_test_2.breadth").read() == orc.breadth_text(breadth)
+
+
+def test_set_algebra_tools_cli(built, tmp_path):
+    """kmers-filter, unique-kmers-multi, kmers-samples-counter on the .kmers.bin files the counter wrote:
+    same options, default locations, output names and log lines as the reference tools."""
+    files = [os.path.join(INPUTS, "meta_test_%d.fa" % n) for n in (1, 2, 3)]
+    wd = tmp_path / "wd"
+    run_cli("-t", "kmer-counter-many", "-k", 31, "-b", 0, "-i", *files, "-w", wd)
+    kf = [str(wd / "kmers" / ("meta_test_%d.kmers.bin" % n)) for n in (1, 2, 3)]
+    data = [open(f, "rb").read() for f in kf]
+    # kmers-filter: test set = sample 1 and 2, known samples = sample 3
+    w1 = tmp_path / "w1"
+    r = run_cli("-t", "kmers-filter", "-k", 31, "-i", kf[0], kf[1], "--filter-kmers", kf[2], "-b", 2, "-w", w1)
+    want = orc.kmers_filter(data[:2], [data[2]], 2, 0)
+    for n, (size, rec) in zip((1, 2), want):
+        assert open(w1 / "kmers" / ("meta_test_%d.kmers.bin" % n), "rb").read() == rec and len(rec) > 0
+    assert "%s k-mers found" % f"{want[0][0]:,}".replace(",", "'") in r.stderr and "of them survived after filtering" in r.stderr
+    # unique-kmers-multi
+    w2 = tmp_path / "w2"
+    run_cli("-t", "unique-kmers-multi", "-k", 31, "-i", kf[0], kf[1], "--filter-kmers", kf[2], "--min-samples", 1, "--max-samples", 2, "-w", w2)
+    size, per_i = orc.unique_kmers_multi(data[:2], [data[2]], 1, 1, 2)
+    for i in (1, 2):
+        assert open(w2 / "kmers" / ("filtered_%d.kmers.bin" % i), "rb").read() == per_i[i]
+    assert len(per_i[1]) > len(per_i[2])
+    assert run_cli("-t", "unique-kmers-multi", "-k", 31, "-i", kf[0], "--filter-kmers", kf[2], "--min-samples", 3, "--max-samples", 2,
+                   ok=False).returncode == 1
+    # kmers-samples-counter
+    w3 = tmp_path / "w3"
+    r = run_cli("-t", "kmers-samples-counter", "-k", 31, "-i", *kf, "-w", w3)
+    size, rec, stat = orc.kmers_samples_counter(data, 1)
+    assert open(w3 / "kmers" / "n_samples.kmers.bin", "rb").read() == rec
+    assert open(w3 / "stats" / "n_samples.stat.txt").read() == stat
+    assert "of them is good (not erroneous)" in r.stderr
+
+
+def test_min_seq_len_cli(built, tmp_path):
+    """the counting call of component-cutter's front half: IOUtils.loadReads(sequences, k, minLen)"""
+    fa = tmp_path / "contigs.fa"
+    rng = np.random.default_rng(5)
+    seqs = ["".join(rng.choice(list("ACGT"), int(n))) for n in rng.integers(20, 400, 80)]
+    fa.write_text("".join(">c%d\n%s\n" % (i, s) for i, s in enumerate(seqs)))
+    run_cli("-t", "kmer-counter", "-k", 21, "-b", 0, "-l", 100, "-i", fa, "-w", tmp_path / "w")
+    want = orc.kmers_bin(orc.count_reads(seqs, 21, 100), 0, 21)
+    assert open(tmp_path / "w" / "kmers" / "contigs.kmers.bin", "rb").read() == want
+    assert want != orc.kmers_bin(orc.count_reads(seqs, 21, 0), 0, 21)

@@ -5,6 +5,7 @@ reference's threading + striped hash maps).  Golden numbers: tests/golden/config
 """
 import json
 import os
+import struct
 
 import numpy as np
 import pytest
@@ -451,3 +452,70 @@ def test_features_from_reads(built):
     acc = orc.presence_for_reads([k for c in comps for k in c], reads, 21)
     wv, wb, wf, wc = orc.features([(0, c) for c in comps], acc, 0)
     assert list(vec) == wv and list(found) == wf and list(cnt) == wc
+
+
+# ---------------------------------------------------------------- set algebra over .kmers.bin files
+def _random_kmers_files(rng, n_files, universe, per_file, hot):
+    """unsorted record files over a shared key universe: duplicates inside a file (addAndBound), values around the
+    threshold, and a few keys whose values sit at the short limits (saturation at 32767, (short) wrap, stored -1)"""
+    keys = rng.integers(0, 1 << 62, universe, dtype=np.uint64)
+    files = []
+    for f in range(n_files):
+        idx = rng.integers(0, universe, per_file)
+        vals = rng.choice([1, 2, 3, 5, 40, 1000, 20000, 32767], per_file)
+        recs = [(int(keys[i]), int(v)) for i, v in zip(idx, vals)]
+        recs += [(int(keys[j]), 32767) for j in range(hot)]                     # same hot keys in every file
+        if f == 2:
+            recs += [(int(keys[j]), 1) for j in range(hot)]                     # 32767 + 32767 + ... : exercises -1 and the wrap
+        rng.shuffle(recs)
+        files.append(b"".join(struct.pack(">Qh", k, v) for k, v in recs))
+    return files
+
+
+@pytest.mark.parametrize("b", [0, 1, 2])
+def test_kmer_set_tools(built, b):
+    import struct as _s  # noqa: F401
+    rng = np.random.default_rng(20 + b)
+    inputs = _random_kmers_files(rng, 4, 3000, 2500, 6)
+    filters = _random_kmers_files(np.random.default_rng(77), 2, 3000, 1500, 3)
+    filters = [f[: len(f) // 10 * 10] for f in filters]
+    # filter files share part of the key universe with the inputs
+    shared = inputs[0][:4000] + filters[0]
+    with m.KmerCounter(31) as ctx:
+        # loadKmers
+        for thr in (b, 5):
+            want = orc.load_kmers(inputs[:2], thr)
+            with m.KmerSet.load(ctx, inputs[:2], thr, chunk=7000) as ks:
+                assert ks.size() == len(want)
+                assert ks.select(None, -1) == orc._records_of(want.items())
+        # kmers-filter
+        want = orc.kmers_filter(inputs[:2], [shared, filters[1]], b, 0)
+        got = m.kmers_filter(ctx, inputs[:2], [shared, filters[1]], b, 0)
+        assert got == want and any(len(r) for _, r in want)
+        assert m.kmers_filter(ctx, inputs[:1], [shared], b, 3) == orc.kmers_filter(inputs[:1], [shared], b, 3)
+        # unique-kmers-multi (incl. the (short) wrap of the value sum and getWithZero's -1 rule)
+        want = orc.unique_kmers_multi(inputs, [shared], b, 1, 4)
+        got = m.unique_kmers_multi(ctx, inputs, [shared], b, 1, 4)
+        assert got[0] == want[0]
+        for i in range(1, 5):
+            assert got[1][i] == want[1][i], i
+        assert len(want[1][1]) > len(want[1][3]) > 0
+        # kmers-samples-counter
+        n, recs, stat = orc.kmers_samples_counter(inputs, b)
+        gn, grecs, ghist = m.kmers_samples_counter(ctx, inputs, b)
+        assert gn == n and grecs == recs
+        lines = ["# k-mer frequency\tnumber of such k-mers"] + ["%d\t%d" % (c, int(ghist[c])) for c in np.nonzero(ghist)[0]]
+        assert "\n".join(lines) + "\n\n" == stat
+
+
+def test_kmer_set_edge_cases(built):
+    with m.KmerCounter(31) as ctx:
+        with m.KmerSet.load(ctx, [b""], 1) as empty, m.KmerSet.load(ctx, [struct.pack(">Qh", 7, 5) + struct.pack(">Qh", 0, 9)], 1) as two:
+            assert empty.size() == 0 and empty.select(None, 0) == b""
+            assert two.size() == 2 and two.select(empty, 1, 0) == b"" and two.select(empty, 1, -1) == two.select(None, 1)
+            two.update(empty, m.KmerSet.ADD, 1)
+            assert two.size() == 2
+            empty.update(two, m.KmerSet.INC, 1)
+            assert empty.select(None, 0) == struct.pack(">Qh", 0, 1) + struct.pack(">Qh", 7, 1)     # key 0 (poly-A) is a legal key
+            two.update(empty, m.KmerSet.ZERO, 0)
+            assert two.select(None, -1) == struct.pack(">Qh", 0, 0) + struct.pack(">Qh", 7, 0)

@@ -130,3 +130,27 @@ def test_features_oracle_agreement(built):
     assert orc.breadth_text([0.5, float("nan")]) == "0.5\nNaN\n" and orc.vec_text([3, -1]) == "3\n-1\n"
     # Java's addAndBound(long,long) with a negative increment saturates (NumUtils.java:27-32 quirk)
     assert orc._java_add_and_bound64(5, -1) == (1 << 63) - 1 and orc._java_add_and_bound64(5, 7) == 12
+
+
+def test_set_algebra_known_answers():
+    """hand-derived from the cited lines: addAndBound saturates, put(get + x) wraps like a Java short, getWithZero reads
+    a stored -1 as 0 (src/io/IOUtils.java:249-257, src/tools/UniqueKmersMultipleSamplesFinder.java:106-129,
+    [itmo]/structures/map/Long2ShortHashMap.java:160-183)"""
+    import struct
+    rec = lambda k, v: struct.pack(">Qh", k, v)
+    # loadKmers: 3 + 32767 saturates, freq 1 is not > threshold 1
+    assert orc.load_kmers([rec(5, 3) + rec(5, 32767) + rec(9, 1)], 1) == {5: 32767}
+    # unique-kmers-multi, b = 0: 32767 + 32767 = 65534 -> (short) -2; -2 + 1 = -1; getWithZero(-1) = 0, so + 5 gives 5 again
+    files = [rec(5, 32767), rec(5, 32767), rec(5, 1), rec(5, 5)]
+    size, out = orc.unique_kmers_multi(files, [], 0, 1, 4)
+    assert size == 1 and out[4] == rec(5, 5) and out[1] == rec(5, 5)
+    # three files only: the sum is -1, which is not > b -> nothing printed although the k-mer is in 3 samples
+    assert orc.unique_kmers_multi(files[:3], [], 0, 1, 3)[1] == {1: b"", 2: b"", 3: b""}
+    # a filter sample that holds the k-mer zeroes it
+    assert orc.unique_kmers_multi([rec(7, 4), rec(7, 4) + rec(8, 9)], [rec(7, 2)], 1, 1, 2)[1] == {1: rec(8, 9), 2: b""}
+    # kmers-filter keeps what the known samples contain more than max-thresh * files times
+    assert orc.kmers_filter([rec(1, 5) + rec(2, 5) + rec(3, 1)], [rec(1, 2), rec(1, 2) + rec(2, 1)], 0, 1) == [(3, rec(1, 5))]
+    # kmers-samples-counter: number of samples a k-mer is good in
+    n, recs, stat = orc.kmers_samples_counter([rec(1, 5) + rec(2, 5), rec(1, 2), rec(3, 9) + rec(1, 1)], 1)
+    assert n == 3 and recs == rec(1, 2) + rec(2, 1) + rec(3, 1)
+    assert stat == "# k-mer frequency\tnumber of such k-mers\n1\t2\n2\t1\n\n"
