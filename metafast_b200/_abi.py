@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmfkc.so")
+LIB_PATH = os.environ.get("MFKC_LIBRARY") or os.path.join(_HERE, "lib", "libmfkc.so")     # MFKC_LIBRARY: A/B builds of the same ABI
 
 MFKC_OK = 0
 E_BADARG, E_CUDA, E_NCCL, E_TABLE_FULL, E_OOM, E_STATE, E_IO, E_FORMAT = -1, -2, -3, -4, -5, -6, -7, -8
