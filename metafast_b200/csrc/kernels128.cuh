@@ -257,13 +257,17 @@ __device__ __noinline__ uint32_t skm128_count_direct(const uint32_t (&w)[5], uin
     return claimed;
 }
 
+// MODE 0: bucket = table region of this GPU; MODE 2: peer-memory exchange, bucket = owner shard << log2B | coarse bucket
+// (st.n_regions = shards, st.region_shift = log2B; runs are cut by minimizer hash; kmer_count[owner] += run length)
+template <int MODE>
 __global__ void __launch_bounds__(EX_THREADS)
 extract_skm128_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
-                      int k, SkmStage128 st, Slot128 *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr) {
+                      int k, SkmStage128 st, Slot128 *__restrict__ tab, uint64_t cap, Counters *__restrict__ ctr,
+                      unsigned long long *__restrict__ kmer_count) {
     __shared__ uint32_t s_words[EX_THREADS + 4];
     __shared__ uint32_t s_flags[EX_THREADS / 2 + 4];
     const uint64_t n_tiles = (((n_bases + 15) >> 4) + EX_THREADS - 1) / EX_THREADS;
-    uint32_t claimed = 0, bad = 0;
+    uint32_t claimed = 0, bad = 0, dropped = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const TileWord5 t = load_tile_word5<EX_THREADS>(bases, n_bases, flags, tile, k, s_words, s_flags, bad);
         const uint32_t valid = t.active ? valid_starts128(t.f_lo, t.f_hi, t.limit, k) : 0u;
@@ -276,18 +280,23 @@ extract_skm128_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const
             for (int j = 0; j <= 16; j++) {
                 const bool v = j < 16 && ((valid >> j) & 1);
                 const uint32_t mhj = mh[j < 16 ? j : 15];
-                const uint32_t key = v ? region_of_minhash(mhj, st.n_regions) : 0xFFFFFFFFu;
+                const uint32_t key = MODE == 2 ? mhj : (v ? region_of_minhash(mhj, st.n_regions) : 0xFFFFFFFFu);
                 if (in_run && (!v || key != run_key)) {
                     const uint32_t len = (uint32_t)j - run_start;
                     const int sh = 2 * (int)run_start;
                     uint32_t r[5];
 #pragma unroll
                     for (int i = 0; i < 5; i++) r[i] = sh ? __funnelshift_l(i < 4 ? t.w[i + 1] : 0u, t.w[i], sh) : t.w[i];
-                    const uint32_t pos = atomicAdd(&st.cursor[run_key], 1u);
+                    const uint32_t owner = MODE == 2 ? owner_of_minhash(run_mh, st.n_regions) : 0u;
+                    const uint32_t bucket = MODE == 2 ? ((owner << st.region_shift) | coarse_of_minhash(run_mh, st.region_shift)) : run_key;
+                    const uint32_t pos = atomicAdd(&st.cursor[bucket], 1u);
                     if (pos < st.seg_cap) {
-                        uint4 *dst = st.recs + 2 * ((uint64_t)run_key * st.seg_cap + pos);
+                        uint4 *dst = st.recs + 2 * ((uint64_t)bucket * st.seg_cap + pos);
                         dst[0] = make_uint4(r[0], r[1], r[2], r[3]);
                         dst[1] = make_uint4((r[4] & ~15u) | (len - 1), run_mh, 0u, 0u);
+                        if (MODE == 2) atomicAdd(&kmer_count[owner], (unsigned long long)len);
+                    } else if (MODE == 2) {
+                        dropped++;                           // reported as an error by mfkc_flush
                     } else {
                         r[4] &= ~15u;
                         claimed += skm128_count_direct(r, len, run_key, st.region_shift, k, tab, cap);
@@ -302,6 +311,38 @@ extract_skm128_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
     if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
+    if (MODE == 2 && dropped) atomicAdd(&ctr->overflow, (unsigned long long)dropped);
+}
+
+// peer-memory drain for 128-bit keys (see drain_p2p_kernel): one 32-byte record per thread, read from the peers' staging
+struct P2PPeers;
+__global__ void __launch_bounds__(256)
+drain_p2p128_kernel(const uint4 *const *__restrict__ peer_recs, const unsigned int *const *__restrict__ peer_cursor, uint32_t n_peers,
+                    uint32_t me, int log2_buckets, uint64_t seg_cap, uint32_t bucket0, uint32_t blocks_per_bucket, int k,
+                    Slot128 *__restrict__ tab, uint64_t cap, uint32_t n_regions, int region_shift, Counters *__restrict__ ctr) {
+    const uint32_t bucket = bucket0 + blockIdx.x / blocks_per_bucket;
+    const uint32_t sub = blockIdx.x % blocks_per_bucket;
+    const uint64_t seg = ((uint64_t)me << log2_buckets) | bucket;
+    uint32_t claimed = 0;
+    for (uint32_t j = 0; j < n_peers; j++) {
+        const uint32_t s = (me + j) % n_peers;
+        uint64_t n = peer_cursor[s][seg];
+        if (n > seg_cap) n = seg_cap;
+        const uint4 *__restrict__ recs = peer_recs[s] + 2 * seg * seg_cap;
+        for (uint64_t i = (uint64_t)sub * 256 + threadIdx.x; i < n; i += (uint64_t)blocks_per_bucket * 256) {
+            const uint4 a = ld_nc_u128(&recs[2 * i]), b = ld_nc_u128(&recs[2 * i + 1]);
+            const uint32_t len = (b.x & 15u) + 1u;
+            const uint32_t region = region_of_minhash(b.y, n_regions);
+            const uint32_t w[5] = {a.x, a.y, a.z, a.w, b.x & ~15u};
+            K128 keys[16];
+            kmers128_of_word(w, k, keys);
+#pragma unroll
+            for (uint32_t t = 0; t < 16; t++)
+                if (t < len) claimed += table128_upsert_at(tab, cap, home128(region, region_shift, keys[t]), keys[t], 1u) ? 1u : 0u;
+        }
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
 
 __global__ void __launch_bounds__(256)

@@ -84,6 +84,7 @@ struct mfkc_ctx {
     uint64_t p2p_seg_cap = 0; int p2p_log2 = 0;
     const uint4 *p2p_peer_recs[P2P_MAX_PEERS] = {nullptr}; const unsigned int *p2p_peer_cursor[P2P_MAX_PEERS] = {nullptr};
     bool p2p_ipc[P2P_MAX_PEERS] = {false};
+    const uint4 **d_peer_recs = nullptr; const unsigned int **d_peer_cursor = nullptr;    // device copies of the pointer tables (128-bit drain)
 
     // sort variant
     unsigned long long *sv_keys = nullptr; uint64_t sv_cap = 0, sv_ub = 0;
@@ -402,7 +403,7 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     cudaFree(ctx->rb_keys); cudaFree(ctx->rb_cursor);
     cudaFree(ctx->sp_ent); cudaFree(ctx->sp_cursor); cudaFree(ctx->sp_failed);
     for (int i = 0; i < P2P_MAX_PEERS; i++) if (ctx->p2p_ipc[i]) { cudaIpcCloseMemHandle((void *)ctx->p2p_peer_recs[i]); cudaIpcCloseMemHandle((void *)ctx->p2p_peer_cursor[i]); }
-    cudaFree(ctx->p2p_recs); cudaFree(ctx->p2p_cursor); cudaFree(ctx->p2p_kc);
+    cudaFree(ctx->p2p_recs); cudaFree(ctx->p2p_cursor); cudaFree(ctx->p2p_kc); cudaFree(ctx->d_peer_recs); cudaFree(ctx->d_peer_cursor);
     cudaFree(ctx->tab); cudaFree(ctx->sv_keys); cudaFree(ctx->svs_keys); cudaFree(ctx->svs_counts);
     cudaFree(ctx->d_bucket_cursor); cudaFree(ctx->d_bucket_base);
     if (ctx->h_bucket) cudaFreeHost(ctx->h_bucket);
@@ -804,8 +805,8 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
             ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
             static const int stage_mode = getenv("MFKC_STAGE") ? atoi(getenv("MFKC_STAGE")) : 2;
             if (ctx->k128) {                  // 128-bit keys: 32-byte super-k-mer records
-                extract_skm128_kernel<<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
-                    d_bases, n_bases, s.d_flags, k, skm_stage128(ctx), ctx->tab128, ctx->cap, ctx->d_ctr);
+                extract_skm128_kernel<0><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                    d_bases, n_bases, s.d_flags, k, skm_stage128(ctx), ctx->tab128, ctx->cap, ctx->d_ctr, nullptr);
             } else if (ctx->place) {          // super-k-mer records, minimizer placement
                 if (ctx->soa) extract_skm_kernel<0, TabSoAOps><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
                     d_bases, n_bases, s.d_flags, k, skm_stage(ctx), tab_soa_ops(ctx), ctx->d_ctr, nullptr);
@@ -1486,8 +1487,8 @@ extern "C" int mfkc_skm_count_wait(mfkc_ctx *ctx) {
 // ---- peer-memory flavour of the shard exchange (see include/mfkc.h and drain_p2p_kernel) ----
 static int p2p_check(mfkc_ctx *ctx) {
     if (!ctx) return MFKC_E_BADARG;
-    if (ctx->cfg.variant != MFKC_VARIANT_HASH || !ctx->place || ctx->k128 || ctx->soa)
-        return fail(ctx, MFKC_E_STATE, "the peer-memory exchange needs the region-blocked hash variant with k <= 31");
+    if (ctx->cfg.variant != MFKC_VARIANT_HASH || !ctx->place || ctx->soa)
+        return fail(ctx, MFKC_E_STATE, "the peer-memory exchange needs the region-blocked hash variant");
     if (ctx->cfg.n_shards < 1 || ctx->cfg.n_shards > P2P_MAX_PEERS) return fail(ctx, MFKC_E_STATE, "the peer-memory exchange serves 1..16 shards");
     return MFKC_OK;
 }
@@ -1501,7 +1502,7 @@ extern "C" int mfkc_p2p_stage_create(mfkc_ctx *ctx, uint32_t log2_buckets, uint6
     ctx->p2p_recs = nullptr; ctx->p2p_cursor = nullptr; ctx->p2p_kc = nullptr;
     const uint64_t n_seg = (uint64_t)std::max(1, ctx->cfg.n_shards) << log2_buckets;
     // plain cudaMalloc: CUDA IPC cannot export memory of the stream-ordered pool
-    if (big_alloc(ctx, (void **)&ctx->p2p_recs, n_seg * seg_cap * sizeof(uint4)) != cudaSuccess) return fail(ctx, MFKC_E_OOM, "cannot allocate the p2p staging buffer");
+    if (big_alloc(ctx, (void **)&ctx->p2p_recs, n_seg * seg_cap * sizeof(uint4) * (ctx->k128 ? 2 : 1)) != cudaSuccess) return fail(ctx, MFKC_E_OOM, "cannot allocate the p2p staging buffer");
     CU_TRY(cudaMalloc(&ctx->p2p_cursor, n_seg * sizeof(unsigned int)));
     CU_TRY(cudaMalloc(&ctx->p2p_kc, P2P_MAX_PEERS * sizeof(unsigned long long)));
     CU_TRY(cudaMemset(ctx->p2p_cursor, 0, n_seg * sizeof(unsigned int)));
@@ -1573,6 +1574,11 @@ static int p2p_extract_batch(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases, 
         st.recs = ctx->p2p_recs; st.cursor = ctx->p2p_cursor; st.seg_cap = ctx->p2p_seg_cap;
         st.n_regions = (uint32_t)std::max(1, ctx->cfg.n_shards); st.region_shift = ctx->p2p_log2; st.win = 0;
         ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
+        if (ctx->k128) {
+            SkmStage128 s8; s8.recs = st.recs; s8.cursor = st.cursor; s8.seg_cap = st.seg_cap; s8.n_regions = st.n_regions; s8.region_shift = st.region_shift;
+            extract_skm128_kernel<2><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                d_bases, n_bases, s.d_flags, k, s8, nullptr, 0, ctx->d_ctr, ctx->p2p_kc);
+        } else
         extract_skm_kernel<2, TabAoS><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
             d_bases, n_bases, s.d_flags, k, st, TabAoS{nullptr, 0}, ctx->d_ctr, ctx->p2p_kc);
     }
@@ -1644,6 +1650,18 @@ extern "C" int mfkc_p2p_drain(mfkc_ctx *ctx, uint64_t n_kmers_in) {
         ctx->kmers_ub_total += share; ctx->recv_since_base += share;
         {
             ProfScope ps(ctx, P_DRAIN, ctx->compute);
+            if (ctx->k128) {
+                if (!ctx->d_peer_recs) {
+                    CU_TRY(cudaMalloc(&ctx->d_peer_recs, P2P_MAX_PEERS * sizeof(void *)));
+                    CU_TRY(cudaMalloc(&ctx->d_peer_cursor, P2P_MAX_PEERS * sizeof(void *)));
+                }
+                CU_TRY(cudaMemcpyAsync(ctx->d_peer_recs, pp.recs, P2P_MAX_PEERS * sizeof(void *), cudaMemcpyHostToDevice, ctx->compute));
+                CU_TRY(cudaMemcpyAsync(ctx->d_peer_cursor, pp.cursor, P2P_MAX_PEERS * sizeof(void *), cudaMemcpyHostToDevice, ctx->compute));
+                CU_TRY(cudaStreamSynchronize(ctx->compute));              // pp lives on this stack frame
+                drain_p2p128_kernel<<<(unsigned)((b1 - b0) * bpb), 256, 0, ctx->compute>>>(
+                    ctx->d_peer_recs, ctx->d_peer_cursor, ns, pp.me, pp.log2_buckets, pp.seg_cap, (uint32_t)b0, bpb, ctx->cfg.k,
+                    ctx->tab128, ctx->cap, ctx->n_regions, ctx->region_shift, ctx->d_ctr);
+            } else
             drain_p2p_kernel<TabAoS><<<(unsigned)((b1 - b0) * bpb), 256, 0, ctx->compute>>>(
                 pp, (uint32_t)b0, bpb, ctx->cfg.k, tab_aos(ctx), ctx->n_regions, ctx->region_shift, table_win(ctx), ctx->d_ctr);
         }

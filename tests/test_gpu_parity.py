@@ -375,6 +375,43 @@ def test_logical_shards_peer_memory_exchange(built, n_shards, log2_buckets):
             s.close()
 
 
+@pytest.mark.parametrize("k,n_shards", [(55, 3), (33, 8)])
+def test_peer_memory_exchange_long_kmers(built, k, n_shards):
+    """BASELINE config 5 layout in small: 128-bit keys through the peer-memory exchange (18-byte records merged by key)."""
+    rng = np.random.default_rng(k)
+    genome = "".join(rng.choice(list("ACGT"), 20000))
+    L = 144                                                    # 16-byte aligned device batches
+    reads = [genome[int(i):int(i) + L] for i in rng.integers(0, 20000 - L, 1600)]
+    reads[5] = "A" * L; reads[6] = "T" * L
+    want = orc.kmers_bin(orc.count_reads(reads, k), 1, k)
+    from metafast_b200.sharded import merge_sorted_records
+    bases = np.frombuffer("".join(reads).encode(), dtype=np.uint8).copy()
+    offsets = np.arange(len(reads) + 1, dtype=np.uint64) * np.uint64(L)
+    shards = [m.KmerCounter(k, n_shards=n_shards, shard_id=s, table_slots=1 << 14) for s in range(n_shards)]
+    try:
+        for s in shards:
+            s.p2p_stage_create(3, 4 * len(reads) * (L - k + 1) // 5 // (n_shards << 3) + 64)
+        for s in shards:
+            for r, peer in enumerate(shards):
+                s.p2p_attach_ctx(r, peer)
+            s.p2p_stage_reset()
+        per = len(reads) // n_shards // 8 * 8
+        for r, s in enumerate(shards):
+            lo, hi = r * per, (len(reads) if r == n_shards - 1 else (r + 1) * per)
+            s.p2p_submit(bases, offsets[lo: hi + 1])
+        counts = [s.p2p_counts(n_shards) for s in shards]
+        assert sum(sum(c) for c in counts) == len(reads) * (L - k + 1)
+        merged = []
+        for r, s in enumerate(shards):
+            s.p2p_drain(sum(c[r] for c in counts))
+            s.flush()
+            merged.append(s.emit(1))
+        assert merge_sorted_records(merged, 18) == want
+    finally:
+        for s in shards:
+            s.close()
+
+
 def test_peer_memory_exchange_reports_overflow(built):
     """a staging segment that is too small must surface as an error at flush, never as a silently short count"""
     cfg = m.synth_cfg(total_genome_bp=100000, n_genomes=4, n_read_ppm=0)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-rank host timeline of the sharded (peer-memory) step; run under torchrun."""
+"""Per-rank host timeline of the sharded (peer-memory) step; run under torchrun.
+MFKC_BENCH_READS = reads per GPU, MFKC_BENCH_K = k (k = 55: the 128-bit layout of BASELINE config 5)."""
 import ctypes as C, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
@@ -9,7 +10,7 @@ from metafast_b200.sharded import P2PShardedStep, exchange_table
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-N, L, K, B = int(os.environ.get("MFKC_BENCH_READS", 20_000_000)), 150, 31, 1_000_000
+N, L, K, B = int(os.environ.get("MFKC_BENCH_READS", 20_000_000)), 150, int(os.environ.get("MFKC_BENCH_K", 31)), 1_000_000
 kc = m.KmerCounter(K, device=lr, expected_kmers=N * (L - K + 1), n_shards=world, shard_id=rank)
 cfg = m.synth_cfg(sample=rank)
 d_b = kc.device_alloc(N * L); d_o = kc.device_alloc((N + 1) * 8)
