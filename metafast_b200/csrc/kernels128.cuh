@@ -32,34 +32,50 @@ __device__ __forceinline__ K128 cas128(void *addr, K128 cmp, K128 val) {
     return old;
 }
 
-// count = sat_add(count, inc); returns true when the slot was claimed by this call
-__device__ __forceinline__ bool table128_upsert_at(Slot128 *__restrict__ tab, uint64_t cap, uint64_t i, K128 key, uint32_t inc) {
+// one slot of a probe sequence: returns true when the key was found or placed there (count = sat_add(count, inc))
+__device__ __forceinline__ bool slot128_try(Slot128 *__restrict__ tab, uint64_t i, K128 key, uint32_t inc, bool &claimed) {
     const K128 empty{~0ull, ~0ull};
-    for (;;) {
-        const ulonglong2 kk = ld_cg_u64x2(&tab[i]);                   // lo, hi
-        K128 cur{kk.x, kk.y};
-        bool claimed = false;
-        if (k128_eq(cur, empty)) {
-            cur = cas128(&tab[i], empty, key);
-            if (k128_eq(cur, empty)) { claimed = true; cur = key; }
+    const ulonglong2 kk = ld_cg_u64x2(&tab[i]);                   // lo, hi
+    K128 cur{kk.x, kk.y};
+    bool mine = false;
+    if (k128_eq(cur, empty)) {
+        cur = cas128(&tab[i], empty, key);
+        if (k128_eq(cur, empty)) { mine = true; cur = key; }
+    }
+    if (!k128_eq(cur, key)) return false;
+    if (inc == 1) {
+        const uint32_t c = *(volatile uint32_t *)&tab[i].count;
+        if (c < MAX_COUNT) atomicAdd(&tab[i].count, 1u);
+    } else {
+        uint32_t old = *(volatile uint32_t *)&tab[i].count;
+        for (;;) {
+            if (old >= MAX_COUNT) break;
+            uint32_t nv = old + inc; if (nv > MAX_COUNT || nv < old) nv = MAX_COUNT;
+            const uint32_t seen = atomicCAS(&tab[i].count, old, nv);
+            if (seen == old) break;
+            old = seen;
         }
-        if (k128_eq(cur, key)) {
-            if (inc == 1) {
-                const uint32_t c = *(volatile uint32_t *)&tab[i].count;
-                if (c < MAX_COUNT) atomicAdd(&tab[i].count, 1u);
-            } else {
-                uint32_t old = *(volatile uint32_t *)&tab[i].count;
-                for (;;) {
-                    if (old >= MAX_COUNT) break;
-                    uint32_t nv = old + inc; if (nv > MAX_COUNT || nv < old) nv = MAX_COUNT;
-                    const uint32_t seen = atomicCAS(&tab[i].count, old, nv);
-                    if (seen == old) break;
-                    old = seen;
-                }
-            }
-            return claimed;
+    }
+    claimed = mine;
+    return true;
+}
+
+// Windowed placement, as for the 64-bit tables (placed_upsert_at in kernels.cuh): primary window of SMEM_WIN slots from
+// the home slot, wrapping inside the region; then windows at fresh uniform positions.  Returns true when a slot was claimed.
+__device__ __forceinline__ bool table128_upsert_at(Slot128 *__restrict__ tab, uint64_t cap, int region_shift, uint64_t home, K128 key, uint32_t inc) {
+    const uint64_t mask = (1ull << region_shift) - 1ull;
+    const uint64_t rbase = home & ~mask;
+    uint64_t off = home & mask;
+    const uint32_t steps = (uint64_t)SMEM_WIN < mask + 1 ? SMEM_WIN : (uint32_t)(mask + 1);
+    bool claimed = false;
+    for (uint32_t st = 0; st < steps; st++, off = (off + 1) & mask)
+        if (slot128_try(tab, rbase | off, key, inc, claimed)) return claimed;
+    for (uint32_t a = 1;; a++) {
+        uint64_t i = mulhi64(mix128(key.lo ^ (SECONDARY_SALT * a), key.hi), cap);
+        for (uint32_t st = 0; st < SMEM_WIN; st++) {
+            if (slot128_try(tab, i, key, inc, claimed)) return claimed;
+            if (++i == cap) i = 0;
         }
-        if (++i == cap) i = 0;
     }
 }
 
@@ -98,7 +114,7 @@ rehash128_kernel(const Slot128 *__restrict__ old_tab, uint64_t old_cap, Slot128 
         const K128 key{kk.x, kk.y};
         const uint32_t c = old_tab[i].count;
         const uint32_t region = region_of_minhash(minhash_of_key128(key, g.k), g.n_regions);
-        table128_upsert_at(new_tab, g.cap, home128(region, g.region_shift, key), key, c < MAX_COUNT ? c : MAX_COUNT);
+        table128_upsert_at(new_tab, g.cap, g.region_shift, home128(region, g.region_shift, key), key, c < MAX_COUNT ? c : MAX_COUNT);
     }
 }
 
@@ -253,7 +269,7 @@ __device__ __noinline__ uint32_t skm128_count_direct(const uint32_t (&w)[5], uin
     uint32_t claimed = 0;
 #pragma unroll
     for (uint32_t t = 0; t < 16; t++)
-        if (t < len) claimed += table128_upsert_at(tab, cap, home128(region, region_shift, keys[t]), keys[t], 1u) ? 1u : 0u;
+        if (t < len) claimed += table128_upsert_at(tab, cap, region_shift, home128(region, region_shift, keys[t]), keys[t], 1u) ? 1u : 0u;
     return claimed;
 }
 
@@ -338,7 +354,7 @@ drain_p2p128_kernel(const uint4 *const *__restrict__ peer_recs, const unsigned i
             kmers128_of_word(w, k, keys);
 #pragma unroll
             for (uint32_t t = 0; t < 16; t++)
-                if (t < len) claimed += table128_upsert_at(tab, cap, home128(region, region_shift, keys[t]), keys[t], 1u) ? 1u : 0u;
+                if (t < len) claimed += table128_upsert_at(tab, cap, region_shift, home128(region, region_shift, keys[t]), keys[t], 1u) ? 1u : 0u;
         }
     }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
@@ -362,7 +378,7 @@ drain_skm128_kernel(SkmStage128 st, uint32_t blocks_per_region, int k, Slot128 *
         kmers128_of_word(w, k, keys);
 #pragma unroll
         for (uint32_t t = 0; t < 16; t++)
-            if (t < len) claimed += table128_upsert_at(tab, cap, home128(region, st.region_shift, keys[t]), keys[t], 1u) ? 1u : 0u;
+            if (t < len) claimed += table128_upsert_at(tab, cap, st.region_shift, home128(region, st.region_shift, keys[t]), keys[t], 1u) ? 1u : 0u;
     }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
