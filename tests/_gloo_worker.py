@@ -53,3 +53,78 @@ def run(rank, world, port, out_dir):
         np.save(os.path.join(out_dir, "hist.npy"), t.numpy())
     dist.barrier()
     dist.destroy_process_group()
+
+
+class _StubCounter:
+    """Stands in for KmerCounter in the peer-memory protocol test: "staging buffers" are files in a shared directory
+    (every rank can read every rank's, like peer HBM), "kernels" are the oracle's CPU arithmetic."""
+
+    def __init__(self, rank, world, k, share_dir, lib):
+        self.rank, self.world, self.k, self.dir, self.lib = rank, world, k, share_dir, lib
+        self.attached, self.counts, self.log = {}, {}, []
+
+    def p2p_stage_create(self, log2_buckets, seg_cap):
+        self.log.append(("create", log2_buckets, seg_cap))
+
+    def p2p_export(self):
+        return (b"rank%03d" % self.rank).ljust(128, b".")
+
+    def p2p_attach(self, r, handle):
+        assert (handle is None) == (r == self.rank)
+        if handle is not None:
+            assert handle == (b"rank%03d" % r).ljust(128, b".")
+        self.attached[r] = True
+
+    def p2p_stage_reset(self):
+        import numpy as np
+        self.staged = [np.zeros(0, dtype=np.uint64) for _ in range(self.world)]
+
+    def p2p_submit(self, bases, offsets):
+        import numpy as np
+        from oracle import oracle as orc
+        reads = [bytes(bases[int(offsets[i]):int(offsets[i + 1])]).decode() for i in range(len(offsets) - 1)]
+        keys = orc.canonical_kmers_np(reads, self.k)
+        owners = np.array([self.lib.mfkc_owner_shard(int(x), self.world) for x in keys], dtype=np.int64)
+        for d in range(self.world):
+            self.staged[d] = np.concatenate([self.staged[d], keys[owners == d]])
+
+    def p2p_counts(self, world):
+        import numpy as np
+        for d in range(world):                                # "every record of this rank is in its staging buffer"
+            np.save("%s/stage_%d_to_%d.npy" % (self.dir, self.rank, d), self.staged[d])
+        return [len(x) for x in self.staged]
+
+    def p2p_drain(self, n_in):
+        import numpy as np
+        got = 0
+        for src in range(self.world):                         # read "peer memory"
+            for x in np.load("%s/stage_%d_to_%d.npy" % (self.dir, src, self.rank)):
+                self.counts[int(x)] = min(self.counts.get(int(x), 0) + 1, 32767)
+                got += 1
+        assert got == n_in                                    # the exchanged totals are exact
+
+
+def run_p2p(rank, world, port, out_dir):
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import metafast_b200 as m
+    from metafast_b200 import sharded
+    from oracle import oracle as orc
+    k, b, L = 21, 1, 100
+    cfg = m.synth_cfg(total_genome_bp=60000, n_genomes=3, n_read_ppm=0, read_len=L)
+    n = 1200
+    raw = m.synth_reads_host(cfg, 0, n)
+    mine = np.ascontiguousarray(raw[rank::world])
+    kc = _StubCounter(rank, world, k, out_dir, m.load())
+    step = sharded.P2PShardedStep(kc, dist, world, rank, 250, L, k, len(mine))
+    assert sorted(kc.attached) == list(range(world)) and kc.log[0][0] == "create"
+    for sample in range(2):                                   # two samples: begin() is the barrier before the staging is cleared
+        kc.counts = {}
+        step.begin()
+        step.run_host(mine.reshape(-1), np.arange(len(mine) + 1, dtype=np.uint64) * np.uint64(L), len(mine))
+    with open(os.path.join(out_dir, "p2p_shard%d.bin" % rank), "wb") as f:
+        f.write(orc.kmers_bin(kc.counts, b, k))
+    dist.barrier()
+    dist.destroy_process_group()

@@ -32,3 +32,20 @@ def test_two_rank_exchange_and_merge(built, tmp_path):
     assert all(len(p) > 0 for p in parts)
     hist = np.load(os.path.join(tmp_path, "hist.npy"))
     assert {int(c): int(hist[c]) for c in np.nonzero(hist)[0]} == orc.histogram(counts)
+
+
+def test_peer_memory_protocol_two_ranks(built, tmp_path):
+    """P2PShardedStep's host protocol (handle exchange -> attach, staging reset behind a barrier, per-owner totals as
+    the barrier before the drain) with 2 gloo ranks and a stub in place of the CUDA context."""
+    import torch.multiprocessing as mp
+    from tests import _gloo_worker
+    import metafast_b200 as m
+    from metafast_b200 import sharded
+    world = 2
+    mp.spawn(_gloo_worker.run_p2p, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [open(os.path.join(tmp_path, "p2p_shard%d.bin" % r), "rb").read() for r in range(world)]
+    cfg = m.synth_cfg(total_genome_bp=60000, n_genomes=3, n_read_ppm=0, read_len=100)
+    reads = [bytes(r).decode() for r in m.synth_reads_host(cfg, 0, 1200)]
+    assert sharded.merge_sorted_records(parts) == orc.kmers_bin(orc.count_reads(reads, 21), 1, 21)
+    log2, seg_cap = sharded.p2p_geometry(20_000_000 * 120, 8)
+    assert 8 <= log2 <= 14 and (8 << log2) * seg_cap * 16 < 20e9         # cfg2 at 8 GPUs: staging fits comfortably
