@@ -167,11 +167,16 @@ std::string reader_name(const std::string &path) {
 #define CK(ctx, call) do { int rc__ = (call); if (rc__ != MFKC_OK) die("%s (libmfkc %d)", mfkc_last_error(ctx), rc__); } while (0)
 
 // ---- IOUtils.loadReads for one file: stream batches of kept reads into `submit`
-template <class F>
-void for_each_batch(mfkc_ctx *ctx, const std::string &file, F submit) {
-    info("Loading file %s...", base_name(file).c_str());
+mfkc_reader *open_reader(const std::string &file) {
     mfkc_reader *r = nullptr; char err[512] = "";
     if (mfkc_reader_open(file.c_str(), &r, err, sizeof err) != MFKC_OK) die("%s", err);
+    return r;
+}
+// `r`: a reader opened earlier (its producer / parser threads have been running since), or nullptr
+template <class F>
+void for_each_batch(mfkc_ctx *ctx, const std::string &file, F submit, mfkc_reader *r = nullptr) {
+    info("Loading file %s...", base_name(file).c_str());
+    if (!r) r = open_reader(file);
     const size_t cap_bases = 256u << 20; const uint32_t cap_reads = 1u << 21;
     static void *h_bases = nullptr, *h_offs = nullptr;
     if (!h_bases) { CK(ctx, mfkc_pinned_alloc(ctx, cap_bases, &h_bases)); CK(ctx, mfkc_pinned_alloc(ctx, ((size_t)cap_reads + 1) * 8, &h_offs)); }
@@ -195,8 +200,12 @@ void for_each_batch(mfkc_ctx *ctx, const std::string &file, F submit) {
 std::string count_sample(mfkc_ctx *ctx, int k, int b, const std::vector<std::string> &files, const std::string &name,
                          const std::string &out_dir, const std::string &st_dir) {
     CK(ctx, mfkc_reset(ctx));
-    for (const auto &f : files)
-        for_each_batch(ctx, f, [&](const uint8_t *bases, const uint64_t *offs, uint32_t n) { CK(ctx, mfkc_submit_reads(ctx, bases, offs, n)); });
+    // open every file of the sample first: the readers inflate and parse in the background (mfkc_reader_open starts their
+    // threads), so the files of a pair are decompressed side by side while the first one is being submitted
+    std::vector<mfkc_reader *> readers;
+    for (const auto &f : files) readers.push_back(open_reader(f));
+    for (size_t i = 0; i < files.size(); i++)
+        for_each_batch(ctx, files[i], [&](const uint8_t *bases, const uint64_t *offs, uint32_t n) { CK(ctx, mfkc_submit_reads(ctx, bases, offs, n)); }, readers[i]);
     CK(ctx, mfkc_flush(ctx));
     mkdirs(out_dir); mkdirs(st_dir);
     // k > 31 (--long-kmers, 18-byte records) gets its own extension so that no reference tool misreads the file

@@ -8,9 +8,15 @@
 //   * the synthetic read generator's host half (synth.h)
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -138,22 +144,38 @@ const CodeTable kCode;
 
 }  // namespace
 
-struct mfkc_reader {
-    std::string path, name, err;
+// The same line rules over a block of text that is already in memory (a chunk of whole records).
+class MemLineReader {
+public:
+    MemLineReader(const char *p, size_t n) : p_(p), end_(p + n) {}
+    bool failed() const { return false; }
+    bool next(const char *&line, size_t &len) {
+        if (p_ == end_) return false;
+        const char *q = p_;
+        while (q < end_ && *q != '\n' && *q != '\r') q++;
+        line = p_; len = (size_t)(q - p_);
+        if (q == end_) { p_ = end_; return true; }               // last line without a terminator
+        p_ = q + 1;
+        if (*q == '\r' && p_ < end_ && *p_ == '\n') p_++;        // \r\n
+        return true;
+    }
+private:
+    const char *p_, *end_;
+};
+
+// Record-level rules of the reference parsers over any line source.
+template <class LR>
+struct RecordParser {
     Format fmt = F_UNKNOWN;
-    LineReader lr;
     int phred_lo = 64;                     // Illumina (64) unless the sniff says Sanger (33)
     uint64_t all_reads = 0, skipped = 0;
-    bool done = false;
-    std::string cur;                       // next kept read, not yet handed out
-    bool have_cur = false;
-    // FASTA record assembly
-    std::string sb;
+    std::string err;
+    std::string sb;                        // FASTA record assembly
     bool fasta_eof = false;
 
     // ---- FASTA: FastaReader.java:82-104 (readNextDataLine) + :54-66 (N-drop)
     // returns 1 = record in `out`, 0 = end, <0 error
-    int fasta_next(std::string &out) {
+    int fasta_next(LR &lr, std::string &out) {
         for (;;) {
             if (fasta_eof) return 0;
             sb.clear();
@@ -178,7 +200,7 @@ struct mfkc_reader {
     }
 
     // ---- FASTQ: FastqReader.java:84-110; 1 = line, 0 = EOF, <0 error
-    int fastq_data_line(LineReader &r, const char *&l, size_t &n) {
+    int fastq_data_line(LR &r, const char *&l, size_t &n) {
         bool ok = r.next(l, n);
         while (ok && n == 0) ok = r.next(l, n);           // skipping empty lines
         if (!ok) return 0;
@@ -193,7 +215,7 @@ struct mfkc_reader {
 
     // One FASTQ record (FastqReader.java:53-82 + FastaReaderFromXQSource.java:62-69).
     // returns 1 = record parsed (kept says whether it survives), 0 = end, <0 error (-100 = illegal quality)
-    int fastq_record(LineReader &r, int lo, std::string *out, bool &kept) {
+    int fastq_record(LR &r, int lo, std::string *out, bool &kept) {
         const char *l; size_t n;
         int s = fastq_data_line(r, l, n);
         if (s <= 0) return s;
@@ -221,44 +243,215 @@ struct mfkc_reader {
         return 1;
     }
 
-    // ReadersUtils.determineQualityFormat :63-77
-    int sniff_quality() {
-        LineReader r;
-        if (!r.open(path)) { err = "can't open " + path; return MFKC_E_IO; }
-        for (int i = 0; i < 1000; i++) {
-            bool kept;
-            const int s = fastq_record(r, 64, nullptr, kept);
-            if (s == 0) break;
-            if (s == -100) { phred_lo = 33; err.clear(); return MFKC_OK; }
-            if (s < 0) return s;
-        }
-        phred_lo = 64;
-        return MFKC_OK;
-    }
-
     // next kept read into cur; 1 / 0 / <0
-    int advance() {
-        if (done) return 0;
+    int next_read(LR &lr, std::string &cur) {
         int s;
-        if (fmt == F_FASTA || fmt == F_FASTA_GZ) s = fasta_next(cur);
-        else {
-            for (;;) {
-                bool kept = false;
-                s = fastq_record(lr, phred_lo, &cur, kept);
-                if (s == -100) s = MFKC_E_FORMAT;
-                if (s <= 0) break;
-                all_reads++;
-                if (kept) break;
-                skipped++;
-            }
-            if (s == 0 && lr.failed()) { err = "read error (corrupt gzip stream?)"; s = MFKC_E_IO; }
+        if (fmt == F_FASTA || fmt == F_FASTA_GZ) return fasta_next(lr, cur);
+        for (;;) {
+            bool kept = false;
+            s = fastq_record(lr, phred_lo, &cur, kept);
+            if (s == -100) s = MFKC_E_FORMAT;
+            if (s <= 0) break;
+            all_reads++;
+            if (kept) return 1;
+            skipped++;
         }
-        if (s <= 0) done = true;
+        if (s == 0 && lr.failed()) { err = "read error (corrupt gzip stream?)"; s = MFKC_E_IO; }
         return s;
     }
 
 private:
     std::string data_;
+};
+
+// ------------------------------------------------------------------------------------------
+// Parallel ingest.  The reference parses inside the synchronized dispatcher: one thread
+// gunzips, splits and validates while the workers wait (src/io/ReadsDispatcher.java:34-38).  Here one producer
+// thread reads / inflates the file and cuts the text into chunks of WHOLE records with a line-level state machine
+// (FASTQ: [empty lines] header, data, [empty lines] '+' line, quality; FASTA: cut in front of a header line);
+// P worker threads run the unchanged record rules (RecordParser) on their chunks; mfkc_reader_next hands the
+// chunks out in file order.  Results -- kept reads, their order, counters, the first error -- are those of
+// the serial parser; MFKC_READER_THREADS=1 selects the serial path.
+// ------------------------------------------------------------------------------------------
+struct IngestChunk {
+    std::vector<char> text;
+    std::vector<uint8_t> bases; std::vector<uint64_t> offs;     // offs[0] = 0
+    uint64_t all = 0, skipped = 0;
+    int status = 0; std::string err;                            // status < 0: the error follows the reads of this chunk
+    bool parsed = false, last = false;
+};
+
+// offset of the last record boundary in [p, p+n) (0 = none); `eof`: the text ends here
+static size_t last_boundary(const char *p, size_t n, bool fastq, bool eof) {
+    size_t pos = 0, cut = 0;
+    int state = 0;                                              // FASTQ: 0 header, 1 data, 2 '+' line, 3 quality
+    while (pos < n) {
+        // line terminators: \n, \r\n and a lone \r (BufferedReader.readLine); memchr does the scanning
+        const char *nl = (const char *)memchr(p + pos, '\n', n - pos);
+        const size_t lim = nl ? (size_t)(nl - p) : n;
+        const char *cr = (const char *)memchr(p + pos, '\r', lim - pos);
+        size_t q, next;
+        if (cr) {
+            q = (size_t)(cr - p); next = q + 1;
+            if (next == n && !eof) break;                       // a '\n' may still follow
+            if (next < n && p[next] == '\n') next++;
+        } else {
+            if (!nl) break;                                     // unterminated line: belongs to the next chunk
+            q = lim; next = q + 1;
+        }
+        const size_t len = q - pos;
+        if (fastq) {
+            if (state == 0) { if (len) state = 1; }
+            else if (state == 1) state = 2;
+            else if (state == 2) { if (len) state = 3; }
+            else { state = 0; cut = next; }
+        } else if (len && (p[pos] == '>' || p[pos] == ';') && pos) cut = pos;
+        pos = next;
+    }
+    return cut;
+}
+
+struct mfkc_reader {
+    std::string path, name, err;
+    Format fmt = F_UNKNOWN;
+    int phred_lo = 64;
+    uint64_t all_reads = 0, skipped = 0;
+    bool done = false;
+    // serial path
+    LineReader lr;
+    RecordParser<LineReader> sp;
+    std::string cur; bool have_cur = false;
+    // parallel path
+    int n_threads = 1;
+    std::vector<std::thread> threads;
+    std::mutex mu; std::condition_variable cv_work, cv_done, cv_space;
+    std::deque<std::shared_ptr<IngestChunk>> ordered;            // chunks in file order (consumer pops the front)
+    std::deque<std::shared_ptr<IngestChunk>> todo;               // not parsed yet
+    bool producer_done = false, stop = false;
+    std::shared_ptr<IngestChunk> cur_chunk; size_t cur_read = 0;
+    static constexpr size_t kChunkText = 4u << 20, kMaxQueued = 48;
+
+    bool is_fastq() const { return fmt == F_FASTQ || fmt == F_FASTQ_GZ; }
+
+    // ReadersUtils.determineQualityFormat :63-77
+    int sniff_quality() {
+        LineReader r;
+        if (!r.open(path)) { err = "can't open " + path; return MFKC_E_IO; }
+        RecordParser<LineReader> p; p.fmt = fmt;
+        for (int i = 0; i < 1000; i++) {
+            bool kept;
+            const int s = p.fastq_record(r, 64, nullptr, kept);
+            if (s == 0) break;
+            if (s == -100) { phred_lo = 33; return MFKC_OK; }
+            if (s < 0) { err = p.err; return s; }
+        }
+        phred_lo = 64;
+        return MFKC_OK;
+    }
+
+    // serial: next kept read into cur; 1 / 0 / <0
+    int advance() {
+        if (done) return 0;
+        const int s = sp.next_read(lr, cur);
+        all_reads = sp.all_reads; skipped = sp.skipped;
+        if (s < 0) err = sp.err;
+        if (s <= 0) done = true;
+        return s;
+    }
+
+    // ---- parallel path
+    void producer() {
+        const bool gz = fmt == F_FASTA_GZ || fmt == F_FASTQ_GZ;
+        gzFile f = gz ? gzopen(path.c_str(), "rb") : nullptr;       // plain files: no zlib layer in between
+        FILE *pf = gz ? nullptr : fopen(path.c_str(), "rb");
+        std::vector<char> carry;
+        bool eof = !f && !pf, io_error = eof;
+        if (f) gzbuffer(f, 1 << 20);
+        while (!eof) {
+            auto ch = std::make_shared<IngestChunk>();
+            ch->text.resize(carry.size() + kChunkText);
+            if (!carry.empty()) memcpy(ch->text.data(), carry.data(), carry.size());
+            size_t have = carry.size();
+            carry.clear();
+            size_t cut = 0;
+            for (;;) {                                          // read until the block holds at least one whole record
+                if (ch->text.size() < have + kChunkText) ch->text.resize(have + kChunkText);
+                int r;
+                if (gz) r = gzread(f, ch->text.data() + have, (unsigned)kChunkText);
+                else { r = (int)fread(ch->text.data() + have, 1, kChunkText, pf); if (r == 0 && ferror(pf)) r = -1; }
+                if (r < 0) { io_error = true; eof = true; }
+                else if (r == 0) eof = true;
+                else have += (size_t)r;
+                cut = eof ? have : last_boundary(ch->text.data(), have, is_fastq(), false);
+                if (cut || eof) break;
+            }
+            if (!eof) carry.assign(ch->text.data() + cut, ch->text.data() + have);
+            ch->text.resize(cut);
+            ch->last = eof;
+            if (io_error) { ch->status = MFKC_E_IO; ch->err = "read error (corrupt gzip stream?)"; }
+            std::unique_lock<std::mutex> lk(mu);
+            cv_space.wait(lk, [&] { return stop || ordered.size() < kMaxQueued; });
+            if (stop) break;
+            ordered.push_back(ch); todo.push_back(ch);
+            cv_work.notify_one();
+        }
+        if (f) gzclose(f);
+        if (pf) fclose(pf);
+        std::lock_guard<std::mutex> lk(mu);
+        producer_done = true;
+        cv_work.notify_all(); cv_done.notify_all();
+    }
+
+    void worker() {
+        for (;;) {
+            std::shared_ptr<IngestChunk> ch;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stop || !todo.empty() || producer_done; });
+                if (stop || (todo.empty() && producer_done)) return;
+                ch = todo.front(); todo.pop_front();
+            }
+            RecordParser<MemLineReader> p; p.fmt = fmt; p.phred_lo = phred_lo;
+            MemLineReader mlr(ch->text.data(), ch->text.size());
+            ch->bases.reserve(ch->text.size() / 2 + 64);
+            ch->offs.push_back(0);
+            std::string rd;
+            int s;
+            while ((s = p.next_read(mlr, rd)) > 0) {
+                ch->bases.insert(ch->bases.end(), rd.begin(), rd.end());
+                ch->offs.push_back(ch->bases.size());
+            }
+            if (s < 0 && ch->status == 0) { ch->status = s; ch->err = p.err; }
+            ch->all = p.all_reads; ch->skipped = p.skipped;
+            std::vector<char>().swap(ch->text);
+            std::lock_guard<std::mutex> lk(mu);
+            ch->parsed = true;
+            cv_done.notify_all();
+        }
+    }
+
+    void start_threads() {
+        threads.emplace_back([this] { producer(); });
+        for (int i = 0; i < n_threads; i++) threads.emplace_back([this] { worker(); });
+    }
+    void stop_threads() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_work.notify_all(); cv_space.notify_all(); cv_done.notify_all();
+        for (auto &t : threads) t.join();
+        threads.clear();
+    }
+    ~mfkc_reader() { if (!threads.empty()) stop_threads(); }
+
+    // next parsed chunk in file order into cur_chunk; 1 / 0 (end)
+    int next_chunk() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return (!ordered.empty() && ordered.front()->parsed) || (ordered.empty() && producer_done); });
+        if (ordered.empty()) return 0;
+        cur_chunk = ordered.front(); ordered.pop_front();
+        cur_read = 0;
+        cv_space.notify_one();
+        return 1;
+    }
 };
 
 extern "C" int mfkc_reader_open(const char *path, mfkc_reader **out, char *errbuf, size_t err_cap) {
@@ -270,11 +463,23 @@ extern "C" int mfkc_reader_open(const char *path, mfkc_reader **out, char *errbu
     if (r->fmt == F_UNKNOWN) { set_err("Can't detect file format for file '" + base_name(path) + "'"); delete r; return MFKC_E_FORMAT; }
     if (r->fmt == F_OTHER) { set_err("BINQ / bzip2 inputs are out of scope for libmfkc: " + base_name(path)); delete r; return MFKC_E_FORMAT; }
     r->name = library_name(r->path, r->fmt);
-    if (r->fmt == F_FASTQ || r->fmt == F_FASTQ_GZ) {
+    if (r->is_fastq()) {
         const int s = r->sniff_quality();
         if (s != MFKC_OK) { set_err(r->err); delete r; return s; }
     }
-    if (!r->lr.open(r->path)) { set_err(std::string("can't open ") + path); delete r; return MFKC_E_IO; }
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char *e = getenv("MFKC_READER_THREADS")) nt = (unsigned)atoi(e);
+    if (nt > 32) nt = 32;
+    r->n_threads = nt < 1 ? 1 : (int)nt;
+    if (r->n_threads == 1) {
+        if (!r->lr.open(r->path)) { set_err(std::string("can't open ") + path); delete r; return MFKC_E_IO; }
+        r->sp.fmt = r->fmt; r->sp.phred_lo = r->phred_lo;
+    } else {
+        gzFile probe = gzopen(path, "rb");
+        if (!probe) { set_err(std::string("can't open ") + path); delete r; return MFKC_E_IO; }
+        gzclose(probe);
+        r->start_threads();
+    }
     *out = r;
     return MFKC_OK;
 }
@@ -285,6 +490,41 @@ extern "C" int mfkc_reader_next(mfkc_reader *r, uint8_t *bases, size_t cap_bases
     uint32_t n = 0;
     size_t used = 0;
     offsets[0] = 0;
+    if (r->n_threads > 1) {
+        while (n < cap_reads && !r->done) {
+            if (!r->cur_chunk) {
+                if (r->next_chunk() == 0) { r->done = true; break; }
+                r->all_reads += r->cur_chunk->all; r->skipped += r->cur_chunk->skipped;
+            }
+            IngestChunk &c = *r->cur_chunk;
+            const size_t n_in = c.offs.size() - 1;
+            bool full = false;
+            // whole runs of reads at once: the offsets of a chunk are already a prefix sum
+            while (r->cur_read < n_in && n < cap_reads) {
+                size_t take = std::min<size_t>(n_in - r->cur_read, cap_reads - n);
+                const uint64_t b0 = c.offs[r->cur_read];
+                while (take && c.offs[r->cur_read + take] - b0 > cap_bases - used) take = take > 64 ? take / 2 : take - 1;
+                if (!take) {
+                    if (n == 0) { r->err = "read longer than the batch buffer"; return MFKC_E_BADARG; }
+                    full = true; break;
+                }
+                const uint64_t nb = c.offs[r->cur_read + take] - b0;
+                memcpy(bases + used, c.bases.data() + b0, nb);
+                for (size_t i = 1; i <= take; i++) offsets[n + i] = used + (c.offs[r->cur_read + i] - b0);
+                used += nb; n += (uint32_t)take; r->cur_read += take;
+            }
+            if (full || n == cap_reads) break;
+            if (c.status < 0) {                              // the error sits behind the reads of this chunk
+                if (n) break;                                // hand the reads out first; the error comes with the next call
+                r->err = c.err; r->done = true; *n_reads = 0;
+                return c.status;
+            }
+            if (c.last) { r->done = true; }
+            r->cur_chunk.reset();
+        }
+        *n_reads = n;
+        return MFKC_OK;
+    }
     while (n < cap_reads) {
         if (!r->have_cur) {
             const int s = r->advance();
