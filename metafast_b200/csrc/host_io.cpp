@@ -329,7 +329,8 @@ struct mfkc_reader {
     std::deque<std::shared_ptr<IngestChunk>> todo;               // not parsed yet
     bool producer_done = false, stop = false;
     std::shared_ptr<IngestChunk> cur_chunk; size_t cur_read = 0;
-    static constexpr size_t kChunkText = 4u << 20, kMaxQueued = 48;
+    size_t kChunkText = 4u << 20;                               // MFKC_READER_CHUNK (bytes): small chunks for the tests
+    static constexpr size_t kMaxQueued = 48;
 
     bool is_fastq() const { return fmt == F_FASTQ || fmt == F_FASTQ_GZ; }
 
@@ -471,6 +472,7 @@ extern "C" int mfkc_reader_open(const char *path, mfkc_reader **out, char *errbu
     if (const char *e = getenv("MFKC_READER_THREADS")) nt = (unsigned)atoi(e);
     if (nt > 32) nt = 32;
     r->n_threads = nt < 1 ? 1 : (int)nt;
+    if (const char *e = getenv("MFKC_READER_CHUNK")) r->kChunkText = std::max<size_t>(16, (size_t)atoll(e));
     if (r->n_threads == 1) {
         if (!r->lr.open(r->path)) { set_err(std::string("can't open ") + path); delete r; return MFKC_E_IO; }
         r->sp.fmt = r->fmt; r->sp.phred_lo = r->phred_lo;

@@ -174,3 +174,59 @@ def test_owner_shard_is_a_partition(built):
         assert all(0 <= o < g for o in owners)
         if g > 1:
             assert len(set(owners)) == g and max(np.bincount(owners)) < 2.0 * len(keys) / g
+
+
+def _read_all(path, threads, chunk=None, monkeypatch=None):
+    monkeypatch.setenv("MFKC_READER_THREADS", str(threads))
+    if chunk:
+        monkeypatch.setenv("MFKC_READER_CHUNK", str(chunk))
+    else:
+        monkeypatch.delenv("MFKC_READER_CHUNK", raising=False)
+    try:
+        return ("ok", m.read_file_reads(path))
+    except m.MfkcError as e:
+        return ("error", e.code, e.msg)
+
+
+def test_parallel_reader_equals_serial(built, tmp_path, monkeypatch):
+    """the chunked multi-threaded ingest must hand out exactly what the serial parser does --
+    kept reads in file order, and the same error for a malformed file -- whatever the chunk size."""
+    import gzip
+    rng = np.random.default_rng(3)
+    seq = lambda n: "".join(rng.choice(list("ACGT"), n))
+    fq, fa = [], []
+    for i in range(400):
+        s = seq(int(rng.integers(1, 120)))
+        if i % 37 == 0:
+            s = s[: len(s) // 2] + "N" + s[len(s) // 2 + 1:]
+        q = "".join(rng.choice(list("#5?FI"), len(s)))
+        fq.append("@r%d extra\n%s\n+\n%s\n" % (i, s, q) + ("\n" if i % 11 == 0 else ""))     # empty lines between records
+        fa.append((">c%d\n" if i % 5 else ";c%d\n") % i + "\n".join(s[j:j + 30] for j in range(0, len(s), 30)) + "\n")
+    cases = {
+        "a.fastq": "".join(fq),
+        "crlf.fastq": "".join(fq).replace("\n", "\r\n"),
+        "cr.fastq": "".join(fq[:50]).replace("\n", "\r"),
+        "notail.fastq": "".join(fq).rstrip("\n"),
+        "trunc.fastq": "".join(fq)[: len("".join(fq)) // 2],
+        "badchar.fastq": "".join(fq[:200]) + "@x\nACGTXACGT\n+\nIIIIIIIII\n" + "".join(fq[200:]),
+        "badlen.fastq": "".join(fq[:100]) + "@x\nACGT\n+\nIII\n" + "".join(fq[100:]),
+        "a.fa": "".join(fa),
+        "lead.fa": "ACGTACGT\nACGT\n" + "".join(fa),                      # data before the first header is a record too
+        "crlf.fa": "".join(fa).replace("\n", "\r\n"),
+        "iupac.fa": "".join(fa[:100]) + ">bad\nACGTRYACGT\n" + "".join(fa[100:]),
+        "empty.fa": "",
+    }
+    for name, text in cases.items():
+        p = tmp_path / name
+        p.write_bytes(text.encode())
+        want = _read_all(str(p), 1, monkeypatch=monkeypatch)
+        for threads, chunk in ((2, 64), (4, 1000), (3, None)):
+            assert _read_all(str(p), threads, chunk, monkeypatch) == want, (name, threads, chunk)
+        if name in ("a.fastq", "a.fa"):
+            assert want[0] == "ok" and len(want[1]) > 300
+            gz = tmp_path / (name + ".gz")
+            with gzip.open(gz, "wb") as f:
+                f.write(text.encode())
+            assert _read_all(str(gz), 4, 777, monkeypatch) == want
+        if name in ("trunc.fastq", "badchar.fastq", "badlen.fastq", "iupac.fa"):
+            assert want[0] == "error"
