@@ -56,6 +56,7 @@ struct mfkc_ctx {
 
     // hash variant
     Slot *tab = nullptr; uint64_t cap = 0;
+    uint64_t tab_alloc_slots = 0;      // size of the allocation behind `tab` (>= cap: a smaller next sample re-uses it)
     Slot128 *tab128 = nullptr; bool k128 = false;   // 32 <= k <= 63: 128-bit keys, 32-byte slots (same cap / regions)
     bool soa = false;                  // region-blocked super-k-mer path, k <= 31: keys[cap] + counts[cap] in ctx->tab
     uint64_t kmers_since_drain = 0; uint32_t drains_since_clear = 0;
@@ -356,7 +357,7 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
         plan_regions(ctx, slots, &slots, &ctx->n_regions, &ctx->region_shift);
         int r = table_alloc(ctx, slots, &ctx->tab);
         if (r != MFKC_OK) return bail(r);
-        ctx->cap = slots;
+        ctx->cap = slots; ctx->tab_alloc_slots = slots;
         ctx->tab128 = reinterpret_cast<Slot128 *>(ctx->tab);
         CR_TRY(cudaMalloc(&ctx->rb_cursor, MAX_REGIONS_SKM * sizeof(unsigned int)));
         CR_TRY(cudaMemset(ctx->rb_cursor, 0, MAX_REGIONS_SKM * sizeof(unsigned int)));
@@ -440,8 +441,12 @@ static int resize_for_next_sample(mfkc_ctx *ctx) {
     uint32_t nr = 1; int sh = 19;
     plan_regions(ctx, want, &want, &nr, &sh);
     if (want * slot_bytes(ctx) > ctx->max_table_bytes) return MFKC_OK;
+    if (want <= ctx->tab_alloc_slots) {                   // fits the allocation we hold: no cudaFree / cudaMalloc of several GB
+        ctx->cap = want; ctx->n_regions = nr; ctx->region_shift = sh;      // (100-150 ms per sample in batch mode); mfkc_reset clears it
+        return MFKC_OK;
+    }
     CU_TRY(cudaFree(ctx->tab));
-    ctx->tab = nullptr; ctx->tab128 = nullptr; ctx->cap = 0;
+    ctx->tab = nullptr; ctx->tab128 = nullptr; ctx->cap = 0; ctx->tab_alloc_slots = 0;
     Slot *nt = nullptr;
     int r = table_alloc(ctx, want, &nt);
     if (r != MFKC_OK) {                                   // should not happen (smaller than what was just freed)
@@ -449,6 +454,7 @@ static int resize_for_next_sample(mfkc_ctx *ctx) {
         TRY(table_alloc(ctx, want, &nt));
     }
     ctx->tab = nt; ctx->tab128 = reinterpret_cast<Slot128 *>(nt); ctx->cap = want; ctx->n_regions = nr; ctx->region_shift = sh;
+    ctx->tab_alloc_slots = want;
     return MFKC_OK;
 }
 
@@ -566,7 +572,7 @@ static int grow_table(mfkc_ctx *ctx, uint64_t need_slots) {
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(ctx->compute));
     CU_TRY(cudaFree(ctx->tab));
-    ctx->tab = nt; ctx->cap = new_cap; ctx->tab128 = reinterpret_cast<Slot128 *>(nt);
+    ctx->tab = nt; ctx->cap = new_cap; ctx->tab_alloc_slots = new_cap; ctx->tab128 = reinterpret_cast<Slot128 *>(nt);
     ctx->n_regions = nr; ctx->region_shift = sh;
     return MFKC_OK;
 }
