@@ -229,6 +229,16 @@ int  mfkc_kset_select_next(mfkc_kset *hm, uint8_t *out, size_t cap, size_t *writ
 /* hist[v] = number of entries with value v, all entries (the statistics of IOUtils.printKmers, src/io/IOUtils.java:59) */
 int  mfkc_kset_histogram(mfkc_kset *ks, uint64_t hist[MFKC_HIST_BINS]);
 
+/* seq-builder on a map: SequencesFinders.thresholdStrategy + AddSequencesShiftingRightTask
+ * (src/algo/SequencesFinders.java:13-31, src/algo/AddSequencesShiftingRightTask.java:39-123,
+ * src/algo/HashMapOperations.java:13-47): the simple paths of the de Bruijn graph of the k-mers with value >
+ * freq_threshold that are at least len_threshold bases long, each once (the orientation whose start k-mer is the
+ * smaller one).  Output order = ascending (start k-mer, orientation); the reference's order is thread timing.
+ * _begin computes them (*n_sequences, *n_bases = total length); _fetch copies them out and releases them:
+ * offsets[n+1] into `bases` ('A','G','C','T'), av/min/max_weight as in structures.Sequence (may be NULL). */
+int  mfkc_kset_sequences_begin(mfkc_kset *hm, int32_t freq_threshold, int32_t len_threshold, uint64_t *n_sequences, uint64_t *n_bases);
+int  mfkc_kset_sequences_fetch(mfkc_kset *hm, uint64_t *offsets, char *bases, uint32_t *av_weight, uint32_t *min_weight, uint32_t *max_weight);
+
 /* ---- host side of the path (CPU; no GPU needed): the parser rules of
  * [itmo]/io/ReadersUtils.java:27-102, readers/FastaReader.java:54-108,
  * readers/FastqReader.java:53-114, readers/FastaReaderFromXQSource.java:62-85 and the

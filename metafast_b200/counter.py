@@ -332,6 +332,18 @@ class KmerSet:
         self.ctx._ck(self.lib.mfkc_kset_histogram(self.h, h.ctypes.data_as(_abi.u64p)))
         return h
 
+    def sequences(self, freq_threshold: int, len_threshold: int):
+        """seq-builder (src/algo/SequencesFinders.java:13-31): [(sequence, av_weight, min_weight, max_weight)]"""
+        ns, nb = C.c_uint64(), C.c_uint64()
+        self.ctx._ck(self.lib.mfkc_kset_sequences_begin(self.h, freq_threshold, len_threshold, C.byref(ns), C.byref(nb)))
+        n = ns.value
+        off = np.zeros(n + 1, dtype=np.uint64)
+        bases = np.zeros(max(nb.value, 1), dtype=np.uint8)
+        av, lo, hi = (np.zeros(max(n, 1), dtype=np.uint32) for _ in range(3))
+        self.ctx._ck(self.lib.mfkc_kset_sequences_fetch(self.h, off.ctypes.data_as(_abi.u64p), _ptr(bases), _ptr(av), _ptr(lo), _ptr(hi)))
+        text = bases.tobytes().decode("latin-1")
+        return [(text[int(off[i]):int(off[i + 1])], int(av[i]), int(lo[i]), int(hi[i])) for i in range(n)]
+
 
 def kmers_filter(ctx: "_Ctx", inputs: Sequence[bytes], filters: Sequence[bytes], b: int = 1, max_thresh: int = 0):
     """kmers-filter (src/tools/KmersFilter.java:94-110): per input file -> (hm.size(), filtered records)"""

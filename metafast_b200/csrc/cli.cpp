@@ -109,7 +109,9 @@ Args parse_args(int argc, char **argv) {
         {"--available-processors", "available-processors"}, {"--gpu", "gpu"}, {"--gpu-variant", "gpu-variant"},
         {"--force", "force"}, {"-v", "verbose"}, {"--verbose", "verbose"}, {"--long-kmers", "long-kmers"},
         {"--k-mers", "reads"}, {"--filter-kmers", "filter-kmers"}, {"--max-thresh", "max-thresh"},
-        {"--min-samples", "min-samples"}, {"--max-samples", "max-samples"}, {"--min-seq-len", "min-seq-len"}, {"-l", "min-seq-len"}};
+        {"--min-samples", "min-samples"}, {"--max-samples", "max-samples"}, {"--min-seq-len", "min-seq-len"}, {"-l", "l"},
+        {"--maximal-bad-frequency", "maximal-bad-frequence"}, {"-bp", "bottom-cut-percent"}, {"--bottom-cut-percent", "bottom-cut-percent"},
+        {"--sequence-len", "sequence-len"}, {"-o", "output-dir"}};
     Args a;
     std::string cur;
     for (int i = 1; i < argc; i++) {
@@ -302,7 +304,7 @@ int tool_counter(const Args &a, bool many) {
     for (const auto &s : samples) biggest = std::max(biggest, estimate_bases(s.second));
     // -l / --min-seq-len: the counting call of component-cutter's front half, IOUtils.loadReads(sequences, k, minLen)
     // (src/tools/ComponentCutterMain.java:81-82, src/io/IOUtils.java:761); kmer-counter itself passes 0
-    mfkc_ctx *ctx = make_ctx(k, g, biggest, a.has("long-kmers"), parse_int(a, "min-seq-len", false, 0));
+    mfkc_ctx *ctx = make_ctx(k, g, biggest, a.has("long-kmers"), parse_int(a, a.has("min-seq-len") ? "min-seq-len" : "l", false, 0));
     std::vector<std::string> outs;
     for (const auto &s : samples) outs.push_back(count_sample(ctx, k, b, s.second, s.first, out_dir, st_dir));
     mfkc_destroy(ctx);
@@ -551,6 +553,63 @@ int tool_kmers_samples_counter(const Args &a) {
     return 0;
 }
 
+// ---- seq-builder (src/tools/SeqBuilderMain.java:76-168), SURVEY 8f rank 2
+int tool_seq_builder(const Args &a) {
+    const int k = parse_int(a, "k", true, 0); check_k(k);
+    const auto inputs = kmers_inputs(a);
+    int b = parse_int(a, "maximal-bad-frequence", false, 1);
+    const int len = parse_int(a, a.has("sequence-len") ? "sequence-len" : "l", true, 0);
+    const std::string work = a.one("work-dir", "workDir"), out_dir = a.one("output-dir", work + "/sequences");
+    mfkc_ctx *ctx = make_ctx(k, gpu_opts(a), 0);
+    {
+        KSet hm(ctx);
+        hm.load(inputs, b);
+        static uint64_t hist[MFKC_HIST_BINS];
+        CK(ctx, mfkc_kset_histogram(hm.h, hist));
+        const int STAT_LEN = 1024;                                         // SeqBuilderMain.java:29
+        std::vector<unsigned long long> stat(STAT_LEN, 0);
+        unsigned long long total_kmers = 0;
+        for (int v = 0; v < MFKC_HIST_BINS; v++) { total_kmers += (unsigned long long)v * hist[v]; stat[std::min(v, STAT_LEN - 1)] += hist[v]; }
+        mkdirs(work);
+        const std::string dist = work + "/distribution";
+        FILE *df = fopen(dist.c_str(), "w"); if (!df) die("Can't write %s", dist.c_str());
+        for (int i = 1; i < STAT_LEN; i++) fprintf(df, "%d %llu\n", i, stat[i]);                 // dumpStat :170-176
+        fclose(df);
+        if (a.has("bottom-cut-percent")) {                                                       // :97-110
+            const int bp = parse_int(a, "bottom-cut-percent", true, 0);
+            info("Using bottom cut percent = %d", bp);
+            const unsigned long long to_cut = total_kmers * (unsigned long long)bp / 100;
+            unsigned long long cur = 0;
+            for (int i = 0; i < STAT_LEN - 1; i++) {
+                if (cur >= to_cut) { b = i; break; }
+                cur += (unsigned long long)i * stat[i];
+            }
+        }
+        info("Using maximal bad frequency = %d", b);
+        mkdirs(out_dir);
+        std::string stem = base_name(inputs[0]);
+        if (ends_with(stem, ".kmers.bin")) stem.resize(stem.size() - 10);
+        const std::string out_file = out_dir + "/" + stem + (inputs.size() > 1 ? "+" : "") + ".seq.fasta";
+        uint64_t ns = 0, nb = 0;
+        CK(ctx, mfkc_kset_sequences_begin(hm.h, b, len, &ns, &nb));
+        std::vector<uint64_t> off(ns + 1); std::vector<char> bases(nb + 1); std::vector<uint32_t> av(ns + 1), lo(ns + 1), hi(ns + 1);
+        CK(ctx, mfkc_kset_sequences_fetch(hm.h, off.data(), bases.data(), av.data(), lo.data(), hi.data()));
+        info("%s sequences found", group_digits(ns).c_str());
+        if (ns == 0) warn("No sequences were found! Perhaps you should decrease --min-seq-len or --maximal-bad-frequency values");
+        FILE *f = fopen(out_file.c_str(), "w"); if (!f) die("Can't write sequences to file");
+        for (uint64_t i = 0; i < ns; i++) {                                                      // Sequence.printSequences + FastaDedicatedWriter (70 per line)
+            const uint64_t L = off[i + 1] - off[i];
+            fprintf(f, ">%llu length=%llu av_weight=%u min_weight=%u max_weight=%u\n", (unsigned long long)(i + 1), (unsigned long long)L, av[i], lo[i], hi[i]);
+            for (uint64_t j = 0; j < L; j += 70) { fwrite(bases.data() + off[i] + j, 1, (size_t)std::min<uint64_t>(70, L - j), f); fputc('\n', f); }
+        }
+        fclose(f);
+        info("Sequences printed to %s", out_file.c_str());
+        printf("%s\n", out_file.c_str());
+    }
+    mfkc_destroy(ctx);
+    return 0;
+}
+
 // ---- gen-reads: synthetic FASTQ / FASTA for tests (BASELINE.md section 4 generator)
 int tool_gen(int argc, char **argv) {
     // mfkc_cli gen-reads <out.fastq|out.fa> <n_reads> [sample] [total_genome_bp] [n_genomes]
@@ -593,6 +652,7 @@ int main(int argc, char **argv) {
     if (a.tool == "kmers-filter") return tool_kmers_filter(a);
     if (a.tool == "unique-kmers-multi") return tool_unique_kmers_multi(a);
     if (a.tool == "kmers-samples-counter") return tool_kmers_samples_counter(a);
+    if (a.tool == "seq-builder") return tool_seq_builder(a);
     die("Tool '%s' is outside the hot path this build replaces (kmer-counter-many, kmer-counter, features-calculator, kmers-filter, "
-        "unique-kmers-multi, kmers-samples-counter)", a.tool.c_str());
+        "unique-kmers-multi, kmers-samples-counter, seq-builder)", a.tool.c_str());
 }

@@ -195,3 +195,144 @@ kset_fill_kernel(uint32_t *__restrict__ vals, uint64_t n, uint32_t v) {
 }
 
 }  // namespace mfkc
+
+// ------------------------------------------------------------------------------------------
+// seq-builder: simple paths ("sequences") of the de Bruijn graph of the k-mers with count >
+// threshold -- SequencesFinders.thresholdStrategy / AddSequencesShiftingRightTask (src/algo/SequencesFinders.java:13-31,
+// src/algo/AddSequencesShiftingRightTask.java:39-123) and HashMapOperations.get{Left,Right}Nucleotide
+// (src/algo/HashMapOperations.java:13-47).  The map is the key-sorted array pair of a mfkc_kset plus a hash index over
+// it (key -> value) for the neighbour queries; one thread owns one map entry and tries both orientations, forward
+// first, exactly like one iteration of the reference's entry loop (which is what makes its `used` rule deterministic).
+// ------------------------------------------------------------------------------------------
+namespace mfkc {
+
+struct SeqIndex { const Slot *tab; uint64_t cap; int k; int thr; };
+
+__global__ void __launch_bounds__(256)
+seq_index_build_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n,
+                       Slot *__restrict__ tab, uint64_t cap) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[t];
+        uint64_t i = home_slot(key, cap);
+        for (;;) {                                            // keys are unique: claim the first free slot
+            if (atomicCAS(&tab[i].key, EMPTY_KEY, key) == EMPTY_KEY) { tab[i].count = vals[t] & 0xFFFFu; break; }
+            if (++i == cap) i = 0;
+        }
+    }
+}
+
+// hm.get(key): the stored short, -1 when absent ([itmo]/structures/map/Long2ShortHashMap.java:160-175)
+__device__ __forceinline__ int seq_get(const SeqIndex &ix, unsigned long long key) {
+    uint64_t i = home_slot(key, ix.cap);
+    for (;;) {
+        const ulonglong2 s = ld_cg_u64x2(&ix.tab[i]);
+        if (s.x == key) return kset_short((uint32_t)s.y);
+        if (s.x == EMPTY_KEY) return -1;
+        if (++i == ix.cap) i = 0;
+    }
+}
+__device__ __forceinline__ unsigned long long seq_canon(unsigned long long fw, int k) {
+    const unsigned long long rc = revcomp64(fw, k);
+    return fw < rc ? fw : rc;
+}
+__device__ __forceinline__ unsigned long long seq_shift_right(unsigned long long fw, uint32_t nuc, int k) {
+    return ((fw << 2) | nuc) & (k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull));
+}
+__device__ __forceinline__ unsigned long long seq_shift_left(unsigned long long fw, uint32_t nuc, int k) {
+    return (fw >> 2) | ((unsigned long long)nuc << (2 * k - 2));
+}
+// unique extension nucleotide, -1 = none, -2 = several
+__device__ __forceinline__ int seq_left_nuc(const SeqIndex &ix, unsigned long long fw) {
+    int ans = -1;
+#pragma unroll
+    for (uint32_t nuc = 0; nuc < 4; nuc++)
+        if (seq_get(ix, seq_canon(seq_shift_left(fw, nuc, ix.k), ix.k)) > ix.thr) { if (ans > -1) return -2; ans = (int)nuc; }
+    return ans;
+}
+__device__ __forceinline__ int seq_right_nuc(const SeqIndex &ix, unsigned long long fw) {
+    int ans = -1;
+#pragma unroll
+    for (uint32_t nuc = 0; nuc < 4; nuc++)
+        if (seq_get(ix, seq_canon(seq_shift_right(fw, nuc, ix.k), ix.k)) > ix.thr) { if (ans > -1) return -2; ans = (int)nuc; }
+    return ans;
+}
+
+struct SeqRecord {                 // one accepted sequence
+    unsigned long long start_fw;   // its first k-mer, as read (directed)
+    unsigned long long order;      // entry index * 2 + orientation: the deterministic output order
+    uint32_t length, av_weight, min_weight, max_weight;
+};
+
+// processSequence (AddSequencesShiftingRightTask.java:75-122) without materialising the bases; out_bases != nullptr
+// writes them ('A','G','C','T' for codes 0..3, ShortKmer.toString)
+__device__ __forceinline__ void seq_walk(const SeqIndex &ix, unsigned long long fw, uint32_t &length, unsigned long long &weight,
+                                         int &lo, int &hi, unsigned long long &end_fw, char *out_bases) {
+    const int k = ix.k;
+    int value = seq_get(ix, seq_canon(fw, k));
+    if (value == -1) value = 0;                              // getWithZero
+    weight = (unsigned long long)(long long)value; lo = hi = value;
+    length = (uint32_t)k;
+    if (out_bases)
+        for (int i = 0; i < k; i++) out_bases[i] = "AGCT"[(fw >> (2 * (k - 1 - i))) & 3ull];
+    unsigned long long cur = fw;
+    for (;;) {
+        const int r = seq_right_nuc(ix, cur);
+        if (r < 0) break;
+        const unsigned long long nxt = seq_shift_right(cur, (uint32_t)r, k);
+        if (seq_left_nuc(ix, nxt) < 0) break;
+        cur = nxt;
+        if (out_bases) out_bases[length] = "AGCT"[r];
+        length++;
+        value = seq_get(ix, seq_canon(cur, k));
+        if (value == -1) value = 0;
+        weight += (unsigned long long)(long long)value;
+        lo = value < lo ? value : lo; hi = value > hi ? value : hi;
+    }
+    end_fw = cur;
+}
+
+// One thread per map entry: both orientations (forward first).  recs == nullptr: count only.
+__global__ void __launch_bounds__(256)
+seq_find_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals, uint64_t n, SeqIndex ix,
+                uint32_t len_threshold, SeqRecord *__restrict__ recs, unsigned long long *__restrict__ cursor /* [0] sequences, [1] bases */) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        if (kset_short(vals[t]) <= ix.thr) continue;
+        const unsigned long long key = keys[t];
+        bool used = false;                                    // `used` set of the reference, restricted to this key
+#pragma unroll 1
+        for (int o = 0; o < 2; o++) {
+            const unsigned long long fw = o ? revcomp64(key, ix.k) : key;
+            const int nuc = seq_left_nuc(ix, fw);
+            bool is_left = nuc < 0;
+            if (!is_left) is_left = seq_right_nuc(ix, seq_shift_left(fw, (uint32_t)nuc, ix.k)) < 0;
+            if (!is_left) continue;
+            uint32_t length; unsigned long long weight, end_fw; int lo, hi;
+            seq_walk(ix, fw, length, weight, lo, hi, end_fw, nullptr);
+            if (length < len_threshold) continue;
+            const unsigned long long st = seq_canon(fw, ix.k), en = seq_canon(end_fw, ix.k);
+            if (st > en) continue;                            // the walk from the other end prints it
+            if (st == en) { if (used) continue; used = true; }
+            const unsigned long long at = atomicAdd(&cursor[0], 1ULL);
+            atomicAdd(&cursor[1], (unsigned long long)length);
+            if (recs) {
+                SeqRecord r;
+                r.start_fw = fw; r.order = 2 * t + (unsigned long long)o; r.length = length;
+                r.av_weight = (uint32_t)(weight / (unsigned long long)(length - ix.k + 1));
+                r.min_weight = (uint32_t)lo; r.max_weight = (uint32_t)hi;
+                recs[at] = r;
+            }
+        }
+    }
+}
+
+// One thread per accepted sequence (records sorted by `order`, base offsets prefix-summed on the host): walk again, write bases
+__global__ void __launch_bounds__(128)
+seq_write_kernel(const SeqRecord *__restrict__ recs, const unsigned long long *__restrict__ base_off, uint64_t n_seq, SeqIndex ix,
+                 char *__restrict__ bases) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_seq; t += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t length; unsigned long long weight, end_fw; int lo, hi;
+        seq_walk(ix, recs[t].start_fw, length, weight, lo, hi, end_fw, bases + base_off[t]);
+    }
+}
+
+}  // namespace mfkc

@@ -1,6 +1,8 @@
 // kset_api.inl -- C ABI of the device-side (k-mer -> short) maps (include/mfkc.h, "set algebra"); included by mfkc.cu.
 // Kernels: kset.cuh.  Every function cites the reference lines it replaces in include/mfkc.h.
 
+static void kset_drop_sequences(mfkc_kset *ks);
+
 struct mfkc_kset {
     mfkc_ctx *ctx = nullptr;
     unsigned long long *keys = nullptr; uint32_t *vals = nullptr; uint64_t n = 0;     // finalized: ascending unique keys
@@ -38,6 +40,7 @@ extern "C" void mfkc_kset_destroy(mfkc_kset *ks) {
     cudaSetDevice(ks->ctx->device);
     cudaStreamSynchronize(ks->ctx->compute);
     cudaFree(ks->keys); cudaFree(ks->vals); cudaFree(ks->pk); cudaFree(ks->pv); cudaFree(ks->d_cursor); cudaFree(ks->sel);
+    kset_drop_sequences(ks);
     delete ks;
 }
 
@@ -250,5 +253,107 @@ extern "C" int mfkc_kset_histogram(mfkc_kset *ks, uint64_t hist[MFKC_HIST_BINS])
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(hist, ctx->d_hist, MFKC_HIST_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    return MFKC_OK;
+}
+
+// ---- seq-builder on a k-mer map (kernels at the end of kset.cuh) ----------------------------------
+struct SeqResult {
+    std::vector<SeqRecord> recs;             // accepted sequences in output order
+    std::vector<unsigned long long> off;     // base offsets, n + 1 entries
+    char *d_bases = nullptr;
+};
+static std::map<mfkc_kset *, SeqResult> g_seq_results;      // keyed by map handle; freed by _fetch / the next _begin
+static std::mutex g_seq_mu;
+static void kset_drop_sequences(mfkc_kset *ks) {
+    std::lock_guard<std::mutex> lk(g_seq_mu);
+    auto it = g_seq_results.find(ks);
+    if (it != g_seq_results.end()) { cudaFree(it->second.d_bases); g_seq_results.erase(it); }
+}
+
+extern "C" int mfkc_kset_sequences_begin(mfkc_kset *hm, int32_t freq_threshold, int32_t len_threshold, uint64_t *n_sequences, uint64_t *n_bases) {
+    if (!hm || !n_sequences || !n_bases) return MFKC_E_BADARG;
+    mfkc_ctx *ctx = hm->ctx;
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->compute;
+    SeqResult res;
+    {
+        std::lock_guard<std::mutex> lk(g_seq_mu);
+        auto it = g_seq_results.find(hm);
+        if (it != g_seq_results.end()) { cudaFree(it->second.d_bases); g_seq_results.erase(it); }
+    }
+    *n_sequences = 0; *n_bases = 0;
+    res.off.assign(1, 0);
+    if (hm->n) {
+        Slot *tab = nullptr;
+        const uint64_t cap = hm->n * 2 + 64;
+        TRY(table_alloc(ctx, cap, &tab, true));
+        seq_index_build_kernel<<<grid_for(ctx, hm->n, 256, 8), 256, 0, st>>>(hm->keys, hm->vals, hm->n, tab, cap);
+        SeqIndex ix; ix.tab = tab; ix.cap = cap; ix.k = ctx->cfg.k; ix.thr = freq_threshold;
+        unsigned long long *d_cur = nullptr; unsigned long long h_cur[2] = {0, 0};
+        TMP_ALLOC(d_cur, 2 * sizeof(unsigned long long));
+        CU_TRY(cudaMemsetAsync(d_cur, 0, 2 * sizeof(unsigned long long), st));
+        const uint32_t len_thr = len_threshold < 0 ? 0u : (uint32_t)len_threshold;
+        seq_find_kernel<<<grid_for(ctx, hm->n, 256, 8), 256, 0, st>>>(hm->keys, hm->vals, hm->n, ix, len_thr, nullptr, d_cur);      // count
+        CU_TRY(cudaMemcpyAsync(h_cur, d_cur, sizeof h_cur, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        const uint64_t ns = h_cur[0], nb = h_cur[1];
+        int r = MFKC_OK;
+        if (ns) {
+            SeqRecord *d_recs = nullptr; unsigned long long *d_off = nullptr;
+            TMP_ALLOC(d_recs, ns * sizeof(SeqRecord));
+            TMP_ALLOC(d_off, ns * sizeof(unsigned long long));
+            CU_TRY(cudaMemsetAsync(d_cur, 0, 2 * sizeof(unsigned long long), st));
+            seq_find_kernel<<<grid_for(ctx, hm->n, 256, 8), 256, 0, st>>>(hm->keys, hm->vals, hm->n, ix, len_thr, d_recs, d_cur);   // records
+            res.recs.resize(ns);
+            CU_TRY(cudaMemcpyAsync(res.recs.data(), d_recs, ns * sizeof(SeqRecord), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            // deterministic order: ascending (start key, orientation); the reference's order is thread timing
+            std::sort(res.recs.begin(), res.recs.end(), [](const SeqRecord &a, const SeqRecord &b) { return a.order < b.order; });
+            res.off.resize(ns + 1);
+            for (uint64_t i = 0; i < ns; i++) res.off[i + 1] = res.off[i] + res.recs[i].length;
+            if (res.off[ns] != nb) r = fail(ctx, MFKC_E_STATE, "internal: sequence length mismatch");
+            if (r == MFKC_OK && big_alloc(ctx, (void **)&res.d_bases, nb) != cudaSuccess) r = fail(ctx, MFKC_E_OOM, "cannot allocate the sequence buffer");
+            if (r == MFKC_OK) {
+                CU_TRY(cudaMemcpyAsync(d_recs, res.recs.data(), ns * sizeof(SeqRecord), cudaMemcpyHostToDevice, st));
+                CU_TRY(cudaMemcpyAsync(d_off, res.off.data(), ns * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+                seq_write_kernel<<<grid_for(ctx, ns, 128, 16), 128, 0, st>>>(d_recs, d_off, ns, ix, res.d_bases);
+                if (cudaStreamSynchronize(st) != cudaSuccess) r = fail(ctx, MFKC_E_CUDA, "sequence kernel failed");
+            }
+            TMP_FREE(d_recs); TMP_FREE(d_off);
+        }
+        TMP_FREE(d_cur);
+        CU_TRY(cudaStreamSynchronize(st));
+        cudaFree(tab);
+        if (r != MFKC_OK) { cudaFree(res.d_bases); return r; }
+        *n_sequences = ns; *n_bases = nb;
+    }
+    std::lock_guard<std::mutex> lk(g_seq_mu);
+    g_seq_results[hm] = std::move(res);
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_kset_sequences_fetch(mfkc_kset *hm, uint64_t *offsets, char *bases, uint32_t *av_weight, uint32_t *min_weight, uint32_t *max_weight) {
+    if (!hm || !offsets) return MFKC_E_BADARG;
+    mfkc_ctx *ctx = hm->ctx;
+    SeqResult res;
+    {
+        std::lock_guard<std::mutex> lk(g_seq_mu);
+        auto it = g_seq_results.find(hm);
+        if (it == g_seq_results.end()) return fail(ctx, MFKC_E_STATE, "mfkc_kset_sequences_fetch without mfkc_kset_sequences_begin");
+        res = std::move(it->second);
+        g_seq_results.erase(it);
+    }
+    CU_TRY(cudaSetDevice(ctx->device));
+    const uint64_t ns = res.recs.size();
+    for (uint64_t i = 0; i <= ns; i++) offsets[i] = res.off[i];
+    for (uint64_t i = 0; i < ns; i++) {
+        if (av_weight) av_weight[i] = res.recs[i].av_weight;
+        if (min_weight) min_weight[i] = res.recs[i].min_weight;
+        if (max_weight) max_weight[i] = res.recs[i].max_weight;
+    }
+    cudaError_t e = cudaSuccess;
+    if (ns && bases) e = cudaMemcpy(bases, res.d_bases, res.off[ns], cudaMemcpyDeviceToHost);
+    cudaFree(res.d_bases);
+    if (e != cudaSuccess) return fail(ctx, MFKC_E_CUDA, "copy of the sequences failed");
     return MFKC_OK;
 }

@@ -487,6 +487,114 @@ def kmers_samples_counter(inputs: Sequence[bytes], b: int = 1) -> Tuple[int, byt
 
 
 # --------------------------------------------------------------------------
+# seq-builder: simple paths of the de Bruijn graph of the counted k-mers
+# --------------------------------------------------------------------------
+def _shift_right(fw: int, nuc: int, k: int) -> int:
+    """ShortKmer.shiftRight ([itmo]/dna/kmers/ShortKmer.java:68-71), forward strand only"""
+    return ((fw << 2) | nuc) & ((1 << (2 * k)) - 1)
+
+
+def _shift_left(fw: int, nuc: int, k: int) -> int:
+    """ShortKmer.shiftLeft (:89-92)"""
+    return (fw >> 2) | (nuc << (2 * k - 2))
+
+
+def _canon(fw: int, k: int) -> int:
+    return min(fw, reverse_complement(fw, k))
+
+
+def _left_nucleotide(hm: Dict[int, int], fw: int, k: int, thr: int) -> int:
+    """HashMapOperations.getLeftNucleotide (src/algo/HashMapOperations.java:13-29): the unique nucleotide that extends
+    the k-mer to the left into a k-mer with count > thr; -1 = none, -2 = several"""
+    ans = -1
+    for nuc in range(4):
+        if _get(hm, _canon(_shift_left(fw, nuc, k), k)) > thr:
+            if ans > -1:
+                return -2
+            ans = nuc
+    return ans
+
+
+def _right_nucleotide(hm: Dict[int, int], fw: int, k: int, thr: int) -> int:
+    """HashMapOperations.getRightNucleotide (:31-47)"""
+    ans = -1
+    for nuc in range(4):
+        if _get(hm, _canon(_shift_right(fw, nuc, k), k)) > thr:
+            if ans > -1:
+                return -2
+            ans = nuc
+    return ans
+
+
+def seq_builder(hm: Dict[int, int], k: int, freq_threshold: int, len_threshold: int) -> List[Tuple[str, int, int, int]]:
+    """SequencesFinders.thresholdStrategy + AddSequencesShiftingRightTask (src/algo/SequencesFinders.java:13-31,
+    src/algo/AddSequencesShiftingRightTask.java:39-123) -> [(sequence, av_weight, min_weight, max_weight)], in ascending
+    order of (start k-mer key, orientation) -- the reference fills a concurrent deque in thread order, so only the SET
+    is defined; both orientations of one key are visited by one thread, forward first (:52-53), which makes the
+    `used` rule for start == end deterministic."""
+    out = []
+    used = set()
+    for key in sorted(hm):
+        if hm[key] <= freq_threshold:
+            continue
+        for fw in (key, reverse_complement(key, k)):
+            nuc = _left_nucleotide(hm, fw, k, freq_threshold)
+            is_left = nuc < 0
+            if not is_left:
+                if _right_nucleotide(hm, _shift_left(fw, nuc, k), k, freq_threshold) < 0:
+                    is_left = True
+            if not is_left:
+                continue
+            value = _get_with_zero(hm, _canon(fw, k))                               # processSequence :75-122
+            seq = [kmer_to_string(fw, k)]
+            weight, lo, hi = value, value, value
+            cur = fw
+            while True:
+                r = _right_nucleotide(hm, cur, k, freq_threshold)
+                if r < 0:
+                    break
+                nxt = _shift_right(cur, r, k)
+                if _left_nucleotide(hm, nxt, k, freq_threshold) < 0:
+                    break
+                cur = nxt
+                seq.append("AGCT"[r])
+                value = _get_with_zero(hm, _canon(cur, k))
+                weight += value
+                lo, hi = min(lo, value), max(hi, value)
+            text = "".join(seq)
+            if len(text) < len_threshold:
+                continue
+            st, end = _canon(fw, k), _canon(cur, k)
+            if st > end:
+                continue
+            if st == end:
+                if st in used:
+                    continue
+                used.add(st)
+            out.append((text, weight // (len(text) - k + 1), lo, hi))
+    return out
+
+
+def sequences_fasta(seqs: Sequence[Tuple[str, int, int, int]]) -> str:
+    """Sequence.printSequences (src/structures/Sequence.java:26-37) + FastaDedicatedWriter.writeData
+    ([itmo]/io/writers/FastaDedicatedWriter.java:34-52): 70 bases per line"""
+    out = []
+    for i, (text, av, lo, hi) in enumerate(seqs, 1):
+        out.append(">%d length=%d av_weight=%d min_weight=%d max_weight=%d\n" % (i, len(text), av, lo, hi))
+        for j in range(0, len(text), 70):
+            out.append(text[j:j + 70] + "\n")
+    return "".join(out)
+
+
+def seq_builder_distribution(hm: Dict[int, int], stat_len: int = 1024) -> str:
+    """SeqBuilderMain.runImpl :83-101 + dumpStat :170-176: "<count> <number of k-mers>" for count 1..1023 (last bin = rest)"""
+    stat = [0] * stat_len
+    for v in hm.values():
+        stat[min(v, stat_len - 1)] += 1
+    return "".join("%d %d\n" % (i, stat[i]) for i in range(1, stat_len))
+
+
+# --------------------------------------------------------------------------
 # features-calculator (a10-a13)
 # --------------------------------------------------------------------------
 def load_components(data: bytes, k: int = 31) -> List[Tuple[int, List[int]]]:

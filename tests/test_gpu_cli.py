@@ -69,7 +69,7 @@ def test_cli_errors(built, tmp_path):
     bad = tmp_path / "bad.fa"
     bad.write_text(">a\nACGTXXACGT\n")
     assert run_cli("-t", "kmer-counter-many", "-k", 5, "-i", bad, ok=False).returncode == 1
-    assert run_cli("-t", "seq-builder", "-k", 5, ok=False).returncode == 1
+    assert run_cli("-t", "component-cutter", "-k", 5, ok=False).returncode == 1
 
 
 def test_features_calculator_cli(built, tmp_path):
@@ -154,3 +154,36 @@ def test_min_seq_len_cli(built, tmp_path):
     want = orc.kmers_bin(orc.count_reads(seqs, 21, 100), 0, 21)
     assert open(tmp_path / "w" / "kmers" / "contigs.kmers.bin", "rb").read() == want
     assert want != orc.kmers_bin(orc.count_reads(seqs, 21, 0), 0, 21)
+
+
+def test_seq_builder_cli(built, tmp_path):
+    """seq-builder (SURVEY 8f rank 2) on the counter's output: same options, output names and FASTA layout as the reference;
+    the sequences (the reference emits them in thread order) come in ascending start-k-mer order."""
+    files = [os.path.join(INPUTS, "meta_test_%d.fa" % n) for n in (1, 3)]
+    wd = tmp_path / "wd"
+    run_cli("-t", "kmer-counter-many", "-k", 31, "-b", 0, "-i", *files, "-w", wd)
+    kf = [str(wd / "kmers" / ("meta_test_%d.kmers.bin" % n)) for n in (1, 3)]
+    data = [open(f, "rb").read() for f in kf]
+    w1 = tmp_path / "w1"
+    r = run_cli("-t", "seq-builder", "-k", 31, "-i", kf[0], "-b", 2, "-l", 100, "-w", w1)
+    hm = orc.load_kmers(data[:1], 2)
+    seqs = orc.seq_builder(hm, 31, 2, 100)
+    assert len(seqs) > 3
+    assert open(w1 / "sequences" / "meta_test_1.seq.fasta").read() == orc.sequences_fasta(seqs)
+    assert open(w1 / "distribution").read() == orc.seq_builder_distribution(hm)
+    assert "%d sequences found" % len(seqs) in r.stderr.replace("'", "")
+    # two inputs ("+" name), --bottom-cut-percent instead of -b
+    w2 = tmp_path / "w2"
+    r = run_cli("-t", "seq-builder", "-k", 31, "-i", *kf, "-bp", 10, "--sequence-len", 60, "-o", w2 / "out", "-w", w2)
+    hm = orc.load_kmers(data, 1)
+    total = sum(hm.values()); stat = [0] * 1024
+    for v in hm.values():
+        stat[min(v, 1023)] += 1
+    b, cur = 1, 0
+    for i in range(1023):
+        if cur >= total * 10 // 100:
+            b = i
+            break
+        cur += i * stat[i]
+    assert "Using maximal bad frequency = %d" % b in r.stderr
+    assert open(w2 / "out" / "meta_test_1+.seq.fasta").read() == orc.sequences_fasta(orc.seq_builder(hm, 31, b, 60))

@@ -556,3 +556,25 @@ def test_kmer_set_edge_cases(built):
             assert empty.select(None, 0) == struct.pack(">Qh", 0, 1) + struct.pack(">Qh", 7, 1)     # key 0 (poly-A) is a legal key
             two.update(empty, m.KmerSet.ZERO, 0)
             assert two.select(None, -1) == struct.pack(">Qh", 0, 0) + struct.pack(">Qh", 7, 0)
+
+
+@pytest.mark.parametrize("k,thr,min_len", [(21, 1, 30), (15, 0, 15), (31, 2, 100), (5, 0, 5)])
+def test_seq_builder(built, k, thr, min_len):
+    """simple paths of the de Bruijn graph (src/algo/AddSequencesShiftingRightTask.java) against the
+    oracle: branching genome (repeats), both strands, palindromic k-mers, isolated k-mers, erroneous low-count k-mers"""
+    rng = np.random.default_rng(100 + k)
+    unit = "".join(rng.choice(list("ACGT"), 400))
+    genome = unit + "".join(rng.choice(list("ACGT"), 1500)) + unit[:250] + "".join(rng.choice(list("ACGT"), 800)) + "ACGT" * 12 + "AT" * 15
+    rc = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    reads = [genome[int(i):int(i) + 90] for i in rng.integers(0, len(genome) - 90, 900)]
+    reads += ["".join(rc[c] for c in reversed(r)) for r in reads[:300]]
+    for j in range(0, 60, 7):                                      # sequencing errors: low-count tips and bubbles
+        r = list(reads[j]); r[45] = rc[r[45]]; reads.append("".join(r))
+    counts = orc.count_reads(reads, k)
+    data = orc.kmers_bin(counts, 0, k)
+    want = orc.seq_builder(orc.load_kmers([data], thr, k), k, thr, min_len)
+    with m.KmerCounter(k) as ctx, m.KmerSet.load(ctx, [data], thr) as ks:
+        got = ks.sequences(thr, min_len)
+        assert got == want
+        assert ks.sequences(thr, 10 ** 6) == []                   # nothing is that long
+    assert len(want) >= 1
