@@ -1,7 +1,11 @@
 // kset_api.inl -- C ABI of the device-side (k-mer -> short) maps (include/mfkc.h, "set algebra"); included by mfkc.cu.
 // Kernels: kset.cuh.  Every function cites the reference lines it replaces in include/mfkc.h.
 
-static void kset_drop_sequences(mfkc_kset *ks);
+struct SeqResult {                           // result of mfkc_kset_sequences_begin, handed out by _fetch
+    std::vector<mfkc::SeqRecord> recs;       // accepted sequences in output order
+    std::vector<unsigned long long> off;     // base offsets, n + 1 entries
+    char *d_bases = nullptr;
+};
 
 struct mfkc_kset {
     mfkc_ctx *ctx = nullptr;
@@ -9,7 +13,12 @@ struct mfkc_kset {
     unsigned long long *pk = nullptr; uint32_t *pv = nullptr; uint64_t p_cap = 0, p_ub = 0;   // records loaded, not merged yet
     unsigned long long *d_cursor = nullptr;
     uint8_t *sel = nullptr; uint64_t sel_n = 0, sel_cursor = 0; bool sel_valid = false;
+    SeqResult *seq = nullptr;                // no global state: the pending sequences belong to the map
 };
+
+static void kset_drop_sequences(mfkc_kset *ks) {
+    if (ks->seq) { cudaFree(ks->seq->d_bases); delete ks->seq; ks->seq = nullptr; }
+}
 
 static int kset_block_scan(mfkc_ctx *ctx, cudaStream_t st, unsigned long long *d_blk, int grid, unsigned long long *total) {
     std::vector<unsigned long long> h(grid);
@@ -257,30 +266,13 @@ extern "C" int mfkc_kset_histogram(mfkc_kset *ks, uint64_t hist[MFKC_HIST_BINS])
 }
 
 // ---- seq-builder on a k-mer map (kernels at the end of kset.cuh) ----------------------------------
-struct SeqResult {
-    std::vector<SeqRecord> recs;             // accepted sequences in output order
-    std::vector<unsigned long long> off;     // base offsets, n + 1 entries
-    char *d_bases = nullptr;
-};
-static std::map<mfkc_kset *, SeqResult> g_seq_results;      // keyed by map handle; freed by _fetch / the next _begin
-static std::mutex g_seq_mu;
-static void kset_drop_sequences(mfkc_kset *ks) {
-    std::lock_guard<std::mutex> lk(g_seq_mu);
-    auto it = g_seq_results.find(ks);
-    if (it != g_seq_results.end()) { cudaFree(it->second.d_bases); g_seq_results.erase(it); }
-}
-
 extern "C" int mfkc_kset_sequences_begin(mfkc_kset *hm, int32_t freq_threshold, int32_t len_threshold, uint64_t *n_sequences, uint64_t *n_bases) {
     if (!hm || !n_sequences || !n_bases) return MFKC_E_BADARG;
     mfkc_ctx *ctx = hm->ctx;
     CU_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->compute;
     SeqResult res;
-    {
-        std::lock_guard<std::mutex> lk(g_seq_mu);
-        auto it = g_seq_results.find(hm);
-        if (it != g_seq_results.end()) { cudaFree(it->second.d_bases); g_seq_results.erase(it); }
-    }
+    kset_drop_sequences(hm);
     *n_sequences = 0; *n_bases = 0;
     res.off.assign(1, 0);
     if (hm->n) {
@@ -327,22 +319,16 @@ extern "C" int mfkc_kset_sequences_begin(mfkc_kset *hm, int32_t freq_threshold, 
         if (r != MFKC_OK) { cudaFree(res.d_bases); return r; }
         *n_sequences = ns; *n_bases = nb;
     }
-    std::lock_guard<std::mutex> lk(g_seq_mu);
-    g_seq_results[hm] = std::move(res);
+    hm->seq = new SeqResult(std::move(res));
     return MFKC_OK;
 }
 
 extern "C" int mfkc_kset_sequences_fetch(mfkc_kset *hm, uint64_t *offsets, char *bases, uint32_t *av_weight, uint32_t *min_weight, uint32_t *max_weight) {
     if (!hm || !offsets) return MFKC_E_BADARG;
     mfkc_ctx *ctx = hm->ctx;
-    SeqResult res;
-    {
-        std::lock_guard<std::mutex> lk(g_seq_mu);
-        auto it = g_seq_results.find(hm);
-        if (it == g_seq_results.end()) return fail(ctx, MFKC_E_STATE, "mfkc_kset_sequences_fetch without mfkc_kset_sequences_begin");
-        res = std::move(it->second);
-        g_seq_results.erase(it);
-    }
+    if (!hm->seq) return fail(ctx, MFKC_E_STATE, "mfkc_kset_sequences_fetch without mfkc_kset_sequences_begin");
+    SeqResult res = std::move(*hm->seq);
+    delete hm->seq; hm->seq = nullptr;
     CU_TRY(cudaSetDevice(ctx->device));
     const uint64_t ns = res.recs.size();
     for (uint64_t i = 0; i <= ns; i++) offsets[i] = res.off[i];
