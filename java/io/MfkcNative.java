@@ -50,6 +50,30 @@ public final class MfkcNative {
     static final MethodHandle READER_NEXT = h("mfkc_reader_next", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, ADDRESS));
     static final MethodHandle READER_CLOSE = h("mfkc_reader_close", FunctionDescriptor.ofVoid(ADDRESS));
 
+    // ---- the .kmers.bin consumers (kmers-filter, unique-kmers-multi, kmers-samples-counter, seq-builder): one mfkc_kset per
+    // BigLong2ShortHashMap of src/tools/KmersFilter.java:94-110, UniqueKmersMultipleSamplesFinder.java:97-158,
+    // KmersSamplesCounter.java:90-119, SeqBuilderMain.java:78-144
+    static final MethodHandle KSET_CREATE = h("mfkc_kset_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle KSET_DESTROY = h("mfkc_kset_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+    static final MethodHandle KSET_LOAD_RECORDS = h("mfkc_kset_load_records", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, JAVA_INT));
+    static final MethodHandle KSET_LOAD_FINISH = h("mfkc_kset_load_finish", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle KSET_SIZE = h("mfkc_kset_size", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle KSET_RESET_VALUES = h("mfkc_kset_reset_values", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle KSET_UPDATE = h("mfkc_kset_update", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
+    static final MethodHandle KSET_SELECT_BEGIN = h("mfkc_kset_select_begin", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
+    static final MethodHandle KSET_SELECT_NEXT = h("mfkc_kset_select_next", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+    static final MethodHandle KSET_HISTOGRAM = h("mfkc_kset_histogram", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle KSET_SEQ_BEGIN = h("mfkc_kset_sequences_begin", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle KSET_SEQ_FETCH = h("mfkc_kset_sequences_fetch", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+
+    // ---- multi-GPU: one context per GPU (cfg.n_shards / shard_id); a single JVM attaches the contexts to each other directly
+    static final MethodHandle P2P_STAGE_CREATE = h("mfkc_p2p_stage_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG));
+    static final MethodHandle P2P_ATTACH_CTX = h("mfkc_p2p_attach_ctx", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    static final MethodHandle P2P_STAGE_RESET = h("mfkc_p2p_stage_reset", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle P2P_SUBMIT_READS = h("mfkc_p2p_submit_reads", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT));
+    static final MethodHandle P2P_COUNTS = h("mfkc_p2p_counts", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle P2P_DRAIN = h("mfkc_p2p_drain", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG));
+
     /** rc != 0 -> ExecutionFailedException with mfkc_last_error(ctx), like the tools' IOException wrapping (Tool.java:286-287). */
     static void check(MemorySegment ctx, int rc) throws ru.ifmo.genetics.utils.tool.ExecutionFailedException {
         if (rc == 0) return;
