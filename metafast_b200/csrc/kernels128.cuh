@@ -287,6 +287,7 @@ extract_skm128_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const TileWord5 t = load_tile_word5<EX_THREADS>(bases, n_bases, flags, tile, k, s_words, s_flags, bad);
         const uint32_t valid = t.active ? valid_starts128(t.f_lo, t.f_hi, t.limit, k) : 0u;
+        unsigned long long km_lo = 0, km_hi = 0;                // MODE 2: k-mers per owner of this tile, 16-bit fields
         if (valid) {
             uint32_t mh[16];
             minhash128_of_word(t.w, k, mh);
@@ -310,7 +311,10 @@ extract_skm128_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const
                         uint4 *dst = st.recs + 2 * ((uint64_t)bucket * st.seg_cap + pos);
                         dst[0] = make_uint4(r[0], r[1], r[2], r[3]);
                         dst[1] = make_uint4((r[4] & ~15u) | (len - 1), run_mh, 0u, 0u);
-                        if (MODE == 2) atomicAdd(&kmer_count[owner], (unsigned long long)len);
+                        if (MODE == 2) {
+                            if (st.n_regions <= 8) { if (owner < 4) km_lo += (unsigned long long)len << (16 * owner); else km_hi += (unsigned long long)len << (16 * (owner - 4)); }
+                            else atomicAdd(&kmer_count[owner], (unsigned long long)len);
+                        }
                     } else if (MODE == 2) {
                         dropped++;                           // reported as an error by mfkc_flush
                     } else {
@@ -322,12 +326,72 @@ extract_skm128_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const
                 if (v && !in_run) { in_run = true; run_start = (uint32_t)j; run_key = key; run_mh = mhj; }
             }
         }
+        if (MODE == 2 && st.n_regions <= 8) {                   // one atomic per (warp, owner) and tile: G hot addresses would serialise in L2
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { km_lo += __shfl_xor_sync(0xffffffffu, km_lo, o); km_hi += __shfl_xor_sync(0xffffffffu, km_hi, o); }
+            const uint32_t l = lane_id();
+            if (l < st.n_regions) {
+                const uint32_t c = (uint32_t)((l < 4 ? km_lo >> (16 * l) : km_hi >> (16 * (l - 4))) & 0xFFFFu);
+                if (c) atomicAdd(&kmer_count[l], (unsigned long long)c);
+            }
+        }
         __syncthreads();
     }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
     if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
     if (MODE == 2 && dropped) atomicAdd(&ctr->overflow, (unsigned long long)dropped);
+}
+
+// canonical key of the k-mer that starts `off` bases into a 5-word window (the j-th key of kmers128_of_word, computed alone)
+__device__ __forceinline__ K128 kmer128_at(const uint32_t (&w)[5], uint32_t off, int k) {
+    const int s = 128 - 2 * k;
+    uint32_t v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] = __funnelshift_l(w[i + 1], w[i], 2 * off);          // off = 0: shift 0 returns w[i]
+    const K128 x{((unsigned long long)v[2] << 32) | v[3], ((unsigned long long)v[0] << 32) | v[1]};
+    const K128 fw = shr128(x, s);
+    const K128 r{~revpairs64(fw.hi), ~revpairs64(fw.lo)};
+    const K128 rc = shr128(r, s);
+    return k128_less(fw, rc) ? fw : rc;
+}
+
+// Work-balanced expansion of 32-byte records (the 128-bit twin of skm_expand_records): a warp takes 32 records, prefix-sums
+// their lengths and deals the k-mer instances out evenly; the next 32 records are in flight meanwhile.
+template <class Put>
+__device__ __forceinline__ void skm128_expand_records(const uint4 *__restrict__ recs, uint64_t n, uint64_t first, uint64_t stride, int k,
+                                                      uint4 (*s_a)[32], uint4 (*s_b)[32], uint32_t (*s_pre)[33], Put put) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t base = first + (uint64_t)warp * 32;
+    uint4 na = make_uint4(0u, 0u, 0u, 0u), nb = na;
+    if (base + lane < n) { na = ld_nc_u128(&recs[2 * (base + lane)]); nb = ld_nc_u128(&recs[2 * (base + lane) + 1]); }
+    for (; base < n; base += stride) {
+        const uint64_t i = base + lane;
+        const uint4 a = na, b = nb;
+        const uint32_t len = i < n ? (b.x & 15u) + 1u : 0u;
+        if (i + stride < n) { na = ld_nc_u128(&recs[2 * (i + stride)]); nb = ld_nc_u128(&recs[2 * (i + stride) + 1]); }
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+        s_a[warp][lane] = a; s_b[warp][lane] = b;
+        s_pre[warp][lane + 1] = incl;
+        if (lane == 0) s_pre[warp][0] = 0;
+        __syncwarp();
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t t = lane; t < total; t += 32) {
+            uint32_t lo = 0, hi = 31;
+#pragma unroll
+            for (int step = 0; step < 5; step++) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (s_pre[warp][mid] <= t) lo = mid; else hi = mid - 1;
+            }
+            const uint32_t off = t - s_pre[warp][lo];
+            const uint4 qa = s_a[warp][lo], qb = s_b[warp][lo];
+            const uint32_t w[5] = {qa.x, qa.y, qa.z, qa.w, qb.x & ~15u};
+            put(kmer128_at(w, off, k), qb.y);
+        }
+        __syncwarp();
+    }
 }
 
 // peer-memory drain for 128-bit keys (see drain_p2p_kernel): one 32-byte record per thread, read from the peers' staging
@@ -339,23 +403,18 @@ drain_p2p128_kernel(const uint4 *const *__restrict__ peer_recs, const unsigned i
     const uint32_t bucket = bucket0 + blockIdx.x / blocks_per_bucket;
     const uint32_t sub = blockIdx.x % blocks_per_bucket;
     const uint64_t seg = ((uint64_t)me << log2_buckets) | bucket;
+    __shared__ uint4 s_a[8][32], s_b[8][32];
+    __shared__ uint32_t s_pre[8][33];
     uint32_t claimed = 0;
     for (uint32_t j = 0; j < n_peers; j++) {
         const uint32_t s = (me + j) % n_peers;
         uint64_t n = peer_cursor[s][seg];
         if (n > seg_cap) n = seg_cap;
-        const uint4 *__restrict__ recs = peer_recs[s] + 2 * seg * seg_cap;
-        for (uint64_t i = (uint64_t)sub * 256 + threadIdx.x; i < n; i += (uint64_t)blocks_per_bucket * 256) {
-            const uint4 a = ld_nc_u128(&recs[2 * i]), b = ld_nc_u128(&recs[2 * i + 1]);
-            const uint32_t len = (b.x & 15u) + 1u;
-            const uint32_t region = region_of_minhash(b.y, n_regions);
-            const uint32_t w[5] = {a.x, a.y, a.z, a.w, b.x & ~15u};
-            K128 keys[16];
-            kmers128_of_word(w, k, keys);
-#pragma unroll
-            for (uint32_t t = 0; t < 16; t++)
-                if (t < len) claimed += table128_upsert_at(tab, cap, region_shift, home128(region, region_shift, keys[t]), keys[t], 1u) ? 1u : 0u;
-        }
+        skm128_expand_records(peer_recs[s] + 2 * seg * seg_cap, n, (uint64_t)sub * 256, (uint64_t)blocks_per_bucket * 256, k, s_a, s_b, s_pre,
+                              [&](K128 key, uint32_t mh) {
+                                  const uint32_t region = region_of_minhash(mh, n_regions);
+                                  claimed += table128_upsert_at(tab, cap, region_shift, home128(region, region_shift, key), key, 1u) ? 1u : 0u;
+                              });
     }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
@@ -369,17 +428,12 @@ drain_skm128_kernel(SkmStage128 st, uint32_t blocks_per_region, int k, Slot128 *
     uint64_t n = st.cursor[region];
     if (n > st.seg_cap) n = st.seg_cap;
     const uint4 *__restrict__ recs = st.recs + 2 * (uint64_t)region * st.seg_cap;
+    __shared__ uint4 s_a[8][32], s_b[8][32];
+    __shared__ uint32_t s_pre[8][33];
     uint32_t claimed = 0;
-    for (uint64_t i = (uint64_t)sub * 256 + threadIdx.x; i < n; i += (uint64_t)blocks_per_region * 256) {
-        const uint4 a = ld_nc_u128(&recs[2 * i]), b = ld_nc_u128(&recs[2 * i + 1]);
-        const uint32_t len = (b.x & 15u) + 1u;
-        const uint32_t w[5] = {a.x, a.y, a.z, a.w, b.x & ~15u};
-        K128 keys[16];
-        kmers128_of_word(w, k, keys);
-#pragma unroll
-        for (uint32_t t = 0; t < 16; t++)
-            if (t < len) claimed += table128_upsert_at(tab, cap, st.region_shift, home128(region, st.region_shift, keys[t]), keys[t], 1u) ? 1u : 0u;
-    }
+    skm128_expand_records(recs, n, (uint64_t)sub * 256, (uint64_t)blocks_per_region * 256, k, s_a, s_b, s_pre, [&](K128 key, uint32_t) {
+        claimed += table128_upsert_at(tab, cap, st.region_shift, home128(region, st.region_shift, key), key, 1u) ? 1u : 0u;
+    });
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
