@@ -168,7 +168,8 @@ int  mfkc_skm_count_wait(mfkc_ctx *ctx);
  *                             barrier: a rank's counts exist only after its extraction has finished)
  *   mfkc_p2p_drain(n_in)   n_in = k-mer instances staged for this rank on all ranks together
  *   mfkc_flush / mfkc_emit_* as on one GPU.
- * A staging segment that overflows is reported by mfkc_flush (MFKC_E_STATE); nothing is dropped silently. */
+ * A staging segment that overflows is reported by mfkc_flush (MFKC_E_STATE); nothing is dropped silently.
+ * Works for 64-bit and 128-bit keys (k <= 63; 32-byte records for k > 31); up to 16 shards. */
 int  mfkc_p2p_stage_create(mfkc_ctx *ctx, uint32_t log2_buckets, uint64_t seg_cap);
 int  mfkc_p2p_export(mfkc_ctx *ctx, uint8_t handles[128]);
 int  mfkc_p2p_attach(mfkc_ctx *ctx, uint32_t rank, const uint8_t handles[128]);

@@ -1323,7 +1323,7 @@ extern "C" uint32_t mfkc_owner_shard(uint64_t key, uint32_t n_shards) { return n
 extern "C" int mfkc_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t n_reads,
                                      uint64_t n_bases, uint64_t *d_keys_out, uint64_t cap_keys, uint64_t *bucket_counts) {
     if (!ctx || !d_bases || !d_offsets || !d_keys_out || !bucket_counts) return fail(ctx, MFKC_E_BADARG, "null argument");
-    if (ctx->k128) return fail(ctx, MFKC_E_STATE, "the shard exchange is not available for k > 31 yet");
+    if (ctx->k128) return fail(ctx, MFKC_E_STATE, "this flavour of the shard exchange serves k <= 31; use mfkc_p2p_* for 128-bit keys");
     const uint32_t ns = ctx->cfg.n_shards > 1 ? (uint32_t)ctx->cfg.n_shards : 1u;
     CU_TRY(cudaSetDevice(ctx->device));
     Staging &s = ctx->st[0];
@@ -1365,7 +1365,7 @@ extern "C" int mfkc_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, cons
 extern "C" int mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uint64_t n) {
     if (!ctx || (!d_keys && n)) return fail(ctx, MFKC_E_BADARG, "null argument");
     if (ctx->cfg.variant == MFKC_VARIANT_SORT) return fail(ctx, MFKC_E_STATE, "mfkc_count_keys_device needs a hash variant");
-    if (ctx->k128) return fail(ctx, MFKC_E_STATE, "the shard exchange is not available for k > 31 yet");
+    if (ctx->k128) return fail(ctx, MFKC_E_STATE, "this flavour of the shard exchange serves k <= 31; use mfkc_p2p_* for 128-bit keys");
     if (n == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(reserve_slots(ctx, n));
@@ -1408,7 +1408,7 @@ extern "C" int mfkc_skm_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, 
                                          uint64_t n_bases, void *d_recs_out, uint64_t seg_cap, uint64_t *rec_counts,
                                          uint64_t *kmer_counts) {
     if (!ctx || !d_bases || !d_offsets || !d_recs_out || !rec_counts || !kmer_counts) return fail(ctx, MFKC_E_BADARG, "null argument");
-    if (ctx->k128) return fail(ctx, MFKC_E_STATE, "the shard exchange is not available for k > 31 yet");
+    if (ctx->k128) return fail(ctx, MFKC_E_STATE, "this flavour of the shard exchange serves k <= 31; use mfkc_p2p_* for 128-bit keys");
     const uint32_t ns = ctx->cfg.n_shards > 1 ? (uint32_t)ctx->cfg.n_shards : 1u;
     if (seg_cap == 0 || seg_cap > 0x7fffffffull) return fail(ctx, MFKC_E_BADARG, "bad segment capacity");
     CU_TRY(cudaSetDevice(ctx->device));
