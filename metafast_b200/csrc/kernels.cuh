@@ -304,8 +304,17 @@ __host__ __device__ __forceinline__ uint32_t mmer_hash(uint32_t x) {
     x *= 0x9E3779B1u;
     return x ^ (x >> 15);
 }
+// spreading of the minimizer hash over the table regions (and, with its top bits, over the coarse buckets of the
+// peer-memory staging).  The minimum of ~20 hashes is concentrated near 0, so it is re-mixed: multiply - xorshift -
+// multiply, the high bits are the ones used (4 instructions; the extraction kernel evaluates it for all 16 start
+// positions of a thread).  The owner shard keeps the full, independent fmix32.
+__host__ __device__ __forceinline__ uint32_t region_hash(uint32_t mh) {
+    uint32_t x = mh * 0x85ebca6bu;
+    x ^= x >> 15;
+    return x * 0xc2b2ae35u;
+}
 __host__ __device__ __forceinline__ uint32_t region_of_minhash(uint32_t mh, uint32_t n_regions) {
-    return (uint32_t)(((uint64_t)hash32(mh ^ 0x7f4a7c15u) * n_regions) >> 32);
+    return (uint32_t)(((uint64_t)region_hash(mh) * n_regions) >> 32);
 }
 __host__ __device__ __forceinline__ uint32_t owner_of_minhash(uint32_t mh, uint32_t n_shards) {
     return (uint32_t)(((uint64_t)hash32(mh ^ 0x1b873593u) * n_shards) >> 32);
@@ -916,7 +925,7 @@ __device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32
 //         st.n_regions = number of shards, st.region_shift = log2(coarse buckets per shard);
 //         kmer_count[owner] as in mode 1 (warp-aggregated: 8 hot addresses would serialise in L2).
 __host__ __device__ __forceinline__ uint32_t coarse_of_minhash(uint32_t mh, int log2_buckets) {
-    return log2_buckets ? hash32(mh ^ 0x7f4a7c15u) >> (32 - log2_buckets) : 0u;     // monotone in the region index
+    return log2_buckets ? region_hash(mh) >> (32 - log2_buckets) : 0u;              // monotone in the region index
 }
 template <int MODE, class Tab>
 __global__ void __launch_bounds__(EX_THREADS)
@@ -935,12 +944,18 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
         if (t.active) {
             const uint32_t w0 = t.w0, w1 = t.w1, w2 = t.w2;
             const uint64_t fbits = t.fbits;
-            // validity of the 16 start positions (same rule as kmers_of_word)
-            const uint64_t span = (k > 1) ? ((1ULL << (k - 1)) - 1ULL) : 1ULL;
+            // validity of the 16 start positions (same rule as kmers_of_word: no boundary flag in [j, j + k - 2] and
+            // j <= limit), computed for all positions at once: smear the flags down by the window length with
+            // doubling shifts (bit j of `inv` = OR of the flags j .. j + span_len - 1), ~45 instructions instead of 130
             const long long limit = t.limit;
-            uint32_t valid = 0;
-#pragma unroll
-            for (int j = 0; j < 16; j++) valid |= ((((fbits >> j) & span) == 0 && (long long)j <= limit) ? 1u : 0u) << j;
+            uint32_t valid;
+            {
+                const int span_len = k > 1 ? k - 1 : 1;
+                uint64_t inv = fbits;
+                for (int have = 1; have < span_len;) { const int step = have < span_len - have ? have : span_len - have; inv |= inv >> step; have += step; }
+                const uint32_t lim_mask = limit >= 15 ? 0xFFFFu : (limit < 0 ? 0u : ((2u << (int)limit) - 1u));
+                valid = ~(uint32_t)inv & lim_mask;
+            }
             if (valid) {
                 uint32_t mh[16];
                 minhash_of_word(w0, w1, w2, k, mh);
@@ -956,6 +971,7 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                     const uint32_t o = owner_of_minhash(mhv, st.n_regions);
                     return MODE == 1 ? o : ((o << st.region_shift) | coarse_of_minhash(mhv, st.region_shift));
                 };
+                const uint32_t seg32 = (uint32_t)st.seg_cap;
                 uint32_t rkey[16];                                  // run key of every start position, computed once
 #pragma unroll
                 for (int j = 0; j < 16; j++) rkey[j] = BY_OWNER ? mh[j] : region_of_minhash(mh[j], st.n_regions);
@@ -990,8 +1006,9 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                             rec.z = ((sh ? (w2 << sh) : w2) & ~15u) | (len - 1);
                             rec.w = run_mh;
                             const uint32_t bucket = bucket_of(run_mh, run_key);
-                            if (pos[j] < st.seg_cap) {
-                                st.recs[(uint64_t)bucket * st.seg_cap + pos[j]] = rec;
+                            if (pos[j] < seg32) {
+                                // local staging holds < 2^32 records (reserve_staging caps it): 32-bit index arithmetic
+                                if (MODE == 0) st.recs[bucket * seg32 + pos[j]] = rec; else st.recs[(uint64_t)bucket * seg32 + pos[j]] = rec;
                                 if (MODE == 1) atomicAdd(&kmer_count[bucket], (unsigned long long)len);
                                 if (MODE == 2) {
                                     const uint32_t o = bucket >> st.region_shift;
