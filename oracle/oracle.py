@@ -8,13 +8,17 @@ It restates, line by line, the semantics of the reference Java code.  Citation
 prefixes: ``src/`` = /root/reference/src/, ``[itmo]/`` = the ITMO assembler
 source jar (/root/reference/lib/itmo-assembler-src.jar!/ru/ifmo/genetics/).
 
-Parity status: the reference holds NO golden vector or unit test for this path
-(SURVEY.md section 4), and no JVM exists in the build image, so the oracle is
-pinned by (a) the micro known-answers derived by hand from the cited lines
-(tests/test_oracle.py) and (b) agreement between this module and the
-independent C restatement ``oracle/ref_cpu.c``.  For k > 31 (128-bit keys) the
-reference has no behaviour at all (src/tools/KmersCounterMain.java:70-73):
-parity unpinned.
+Parity status: PINNED, transitively, by the reference's own fixture.  The reference holds no unit test for this path
+ and no JVM exists in the build image, but it ships one golden output:
+test_data/meta_test_matrix.txt, the Bray-Curtis matrix of `matrix-builder -k 31` over test_data/meta_test_{1,2,3}.fa
+(README.md:90-99).  This module restates the whole pipeline behind it (kmer-counter-many -> seq-builder ->
+component-cutter -> features-calculator -> dist-matrix-calculator, `matrix_builder` below) and reproduces the three
+distances to the last bit of the doubles (tests/test_oracle.py::test_reference_matrix_golden; the same test shows that
+an off-by-one in the -b filter moves all of them).  What the fixture does NOT pin: FASTQ parsing (the fixture is
+FASTA), saturation at 32767 and minSeqLen effects (not reached by these inputs), output ORDER (hash-map order in the
+reference), the set tools.  Those stay pinned by (a) hand-derived micro known-answers and (b) agreement with the
+independent C restatement ``oracle/ref_cpu.c``.  For k > 31 (128-bit keys) the reference has no behaviour at all
+(src/tools/KmersCounterMain.java:70-73): parity unpinned.
 """
 from __future__ import annotations
 
@@ -726,6 +730,131 @@ def vec_text(vec: Sequence[int]) -> str:
 
 def breadth_text(breadth: Sequence[float]) -> str:
     return "".join(java_double_to_string(b) + "\n" for b in breadth)
+
+
+# --------------------------------------------------------------------------
+# component-cutter and dist-matrix-calculator: the rest of the reference's default `matrix-builder` pipeline.
+# NOT on the accelerated path; restated here only because the reference's single golden output,
+# test_data/meta_test_matrix.txt, is the result of the WHOLE pipeline -- with these two stages the oracle can be
+# pinned against it (tests/test_oracle.py::test_reference_matrix_golden).
+# --------------------------------------------------------------------------
+def possible_neighbours(key: int, k: int) -> List[int]:
+    """KmerOperations.possibleNeighbours (src/algo/KmerOperations.java:9-26): the canonical forms of the 4 right and
+    4 left extensions of a (canonical) k-mer"""
+    out = []
+    for nuc in range(4):
+        out.append(_canon(_shift_right(key, nuc, k), k))
+        out.append(_canon(_shift_left(key, nuc, k), k))
+    return out
+
+
+def _find_all_components(hm: Dict[int, int], k: int) -> List[List[int]]:
+    """ComponentsBuilder.findAllComponents + bfs (src/algo/ComponentsBuilder.java:198-269): connected components of
+    the k-mers of `hm` under the neighbour relation.  The reference walks `hm` in hash-map order and marks visited
+    k-mers by negating their value; a component larger than b2 is still walked to its end (:244-262), so the SET of
+    components does not depend on the order"""
+    seen = set()
+    comps = []
+    for start in sorted(hm):
+        if start in seen:
+            continue
+        seen.add(start)
+        comp = [start]
+        head = 0
+        while head < len(comp):
+            kmer = comp[head]
+            head += 1
+            for nb in possible_neighbours(kmer, k):
+                if nb in hm and nb not in seen:
+                    seen.add(nb)
+                    comp.append(nb)
+        comps.append(comp)
+    return comps
+
+
+def component_cutter(hm: Dict[int, int], k: int, b1: int = 1000, b2: int = 10000) -> List[Tuple[int, List[int], int]]:
+    """ComponentsBuilder.splitStrategy / run / Task.run (src/algo/ComponentsBuilder.java:24-31,58-84,157-181) ->
+    [(weight, keys, usedFreqThreshold)]: components of fewer than b1 k-mers are dropped, b1..b2 are kept, larger ones
+    are split again among their k-mers of value >= threshold + 1 (`nextHM`, :246-260).  Sorted as
+    ConnectedComponent.compareTo (src/structures/ConnectedComponent.java:125-136: threshold ascending, weight
+    descending, size descending); ties and the order of the keys inside a component are hash-map / thread order in
+    the reference, here ascending smallest key / ascending key"""
+    ans = []
+    work = [(hm, 1)]
+    while work:
+        cur, thr = work.pop()
+        for comp in _find_all_components(cur, k):
+            if len(comp) < b1:
+                continue
+            if len(comp) <= b2:
+                ans.append((sum(cur[x] for x in comp), sorted(comp), thr))
+            else:
+                work.append(({x: cur[x] for x in comp if cur[x] >= thr + 1}, thr + 1))
+    ans.sort(key=lambda c: (c[2], -c[0], -len(c[1]), c[1][0]))
+    return ans
+
+
+def components_stat_txt(comps: Sequence[Tuple[int, Sequence[int], int]]) -> str:
+    """src/algo/ComponentsBuilder.java:144-152"""
+    out = ["# component.no\tcomponent.size\tcomponent.weight\tusedFreqThreshold\n"]
+    for i, (weight, keys, thr) in enumerate(comps, 1):
+        out.append("%d\t%d\t%d\t%d\n" % (i, len(keys), weight, thr))
+    return "".join(out)
+
+
+def bray_curtis(v1: Sequence[float], v2: Sequence[float]) -> float:
+    """DistanceMatrixCalculatorMain.brayCurtisDistance (src/tools/DistanceMatrixCalculatorMain.java:140-153), in
+    doubles and in the reference's summation order"""
+    sumdiff = 0.0
+    total = 0.0
+    for a, b in zip(v1, v2):
+        a, b = float(a), float(b)
+        sumdiff += abs(a - b)
+        total += abs(a) + abs(b)
+    return sumdiff / total
+
+
+def matrix_builder(paths: Sequence[str], k: int = 31, b: int = 1, min_seq_len: int = 100, b1: int = 1000,
+                   b2: int = 10000) -> Tuple[List[str], List[List[float]], dict]:
+    """``matrix-builder -k K -b B -l L -i paths`` up to the distance matrix in original order
+    (src/tools/DistanceMatrixBuilderMain.java:88-137,170-175): kmer-counter-many -> seq-builder-many (one run per
+    .kmers.bin, src/tools/SeqBuilderForManyFilesMain.java:80-92) -> component-cutter (loadReads over ALL sequence
+    files with minSeqLen, src/tools/ComponentCutterMain.java:81-82) -> features-calculator on the .kmers.bin files
+    (threshold 0) -> Bray-Curtis.  Returns (sample names, matrix, intermediates)."""
+    counted = kmer_counter_many(paths, k, b)
+    names = list(counted)
+    seqs = {}
+    for name in names:
+        hm = load_kmers([counted[name][0]], b, k)                          # SeqBuilderMain.java:79-80
+        seqs[name] = seq_builder(hm, k, b, min_seq_len)
+    seq_hm = count_reads([s[0] for name in names for s in seqs[name]], k, min_seq_len)
+    comps3 = component_cutter(seq_hm, k, b1, b2)
+    comps = [(w, keys) for w, keys, _thr in comps3]
+    all_keys = [key for _w, keys in comps for key in keys]
+    vecs = {}
+    for name in names:
+        acc = presence_for_kmers(all_keys, load_kmers_bin(counted[name][0], k))
+        vecs[name] = features(comps, acc, 0)[0]
+    n = len(names)
+    matrix = [[0.0] * n for _ in range(n)]
+    for i in range(n):
+        for j in range(i + 1, n):
+            matrix[i][j] = matrix[j][i] = bray_curtis(vecs[names[i]], vecs[names[j]])
+    return names, matrix, {"counted": counted, "sequences": seqs, "sequence_kmers": seq_hm, "components": comps3,
+                           "vectors": vecs}
+
+
+def load_matrix_txt(text: str) -> Dict[Tuple[str, str], float]:
+    """Parses DistanceMatrixCalculatorMain.printMatrix output (src/tools/DistanceMatrixCalculatorMain.java:91-121)
+    into {(row name, column name): value}; the heat-map step may have permuted rows and columns"""
+    lines = [ln for ln in text.splitlines() if ln.strip()]
+    cols = lines[0].split("\t")[1:]
+    out = {}
+    for ln in lines[1:]:
+        cells = ln.split("\t")
+        for c, v in zip(cols, cells[1:]):
+            out[(cells[0], c)] = float(v)
+    return out
 
 
 # --------------------------------------------------------------------------

@@ -15,8 +15,14 @@
  * Citations: src/ = /root/reference/src/ ; [itmo]/ =
  * /root/reference/lib/itmo-assembler-src.jar!/ru/ifmo/genetics/ .
  *
- * Parity status: no reference test or golden vector pins this path and no JVM
- * is available -- "parity pinned by source semantics only".
+ * Parity status: pinned, transitively, by the reference's own fixture
+ * test_data/meta_test_matrix.txt (the matrix-builder result on
+ * test_data/meta_test_{1,2,3}.fa): with this file doing the parse + count +
+ * filtered emit of every sample, the minSeqLen count of component-cutter and the
+ * feature sums, the pipeline reproduces the reference's three Bray-Curtis
+ * distances to the last bit (tests/test_oracle.py::test_reference_matrix_golden;
+ * see oracle/oracle.py's header for what the fixture does not reach).  No JVM is
+ * available, so the reference itself cannot be run.
  * fastutil's HashCommon.murmurHash3 (binary-only dependency, version not pinned
  * in the tree) is restated from the public MurmurHash3 finalizers; it affects
  * slot placement only, never the (key,count) set.

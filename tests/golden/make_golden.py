@@ -6,6 +6,10 @@ oracle/oracle.py (numpy) and oracle/ref_cpu.c (threads + striped maps, like the 
 Inputs: tests/golden/inputs/meta_test_{1,2,3}.fa = /root/reference/test_data/meta_test_*.fa
 (verbatim copies of the reference's own fixtures).
 
+tests/golden/meta_test_matrix.txt is NOT generated: it is a verbatim copy of the reference's checked-in result
+/root/reference/test_data/meta_test_matrix.txt (the matrix-builder output for the same three files), the fixture that
+pins the oracle (tests/test_oracle.py::test_reference_matrix_golden).
+
     python tests/golden/make_golden.py
 """
 import json

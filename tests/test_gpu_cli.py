@@ -187,3 +187,39 @@ def test_seq_builder_cli(built, tmp_path):
         cur += i * stat[i]
     assert "Using maximal bad frequency = %d" % b in r.stderr
     assert open(w2 / "out" / "meta_test_1+.seq.fasta").read() == orc.sequences_fasta(orc.seq_builder(hm, 31, b, 60))
+
+
+def test_matrix_builder_pipeline_reference_golden(built, tmp_path):
+    """The reference's own checked-in result, test_data/meta_test_matrix.txt (= tests/golden/meta_test_matrix.txt): the
+    Bray-Curtis matrix of `matrix-builder -k 31 -i meta_test_{1,2,3}.fa` (README.md:90-99).  Every stage that is in
+    scope runs on the GPU through mfkc_cli -- kmer-counter-many, seq-builder per sample, component-cutter's counting call
+    (kmer-counter -l 100 over the three sequence files), features-calculator -- and only the component split
+    (ComponentsBuilder, out of scope) and the distance formula come from the checker.  The three distances must equal
+    the reference's to the last bit."""
+    from tests.conftest import GOLDEN
+    gold = orc.load_matrix_txt(open(os.path.join(GOLDEN, "meta_test_matrix.txt")).read())
+    files = [os.path.join(INPUTS, "meta_test_%d.fa" % n) for n in (1, 2, 3)]
+    names = ["meta_test_%d" % n for n in (1, 2, 3)]
+    wd = tmp_path / "wd"
+    run_cli("-t", "kmer-counter-many", "-k", 31, "-i", *files, "-w", wd)                       # default -b 1
+    kfiles = [str(wd / "kmers" / (name + ".kmers.bin")) for name in names]
+    for kf in kfiles:
+        run_cli("-t", "seq-builder", "-k", 31, "-b", 1, "-l", 100, "-i", kf, "-o", wd / "sequences", "-w", wd / "sub-builder")
+    sfiles = [str(wd / "sequences" / (name + ".seq.fasta")) for name in names]
+    run_cli("-t", "kmer-counter", "-k", 31, "-b", 0, "-l", 100, "-i", *sfiles, "-w", wd / "cutter")
+    (seq_kmers,) = os.listdir(wd / "cutter" / "kmers")
+    seq_hm = dict(orc.load_kmers_bin(open(wd / "cutter" / "kmers" / seq_kmers, "rb").read()))
+    assert len(seq_hm) == 17061
+    comps3 = orc.component_cutter(seq_hm, 31, 1000, 10000)
+    assert [(len(keys), w, thr) for w, keys, thr in comps3] == \
+        [(6240, 12783, 1), (5713, 11265, 1), (3020, 5977, 1), (2088, 4260, 1)]
+    cm = wd / "components.bin"
+    cm.write_bytes(orc.save_components([(w, keys) for w, keys, _ in comps3]))
+    run_cli("-t", "features-calculator", "-k", 31, "-cm", cm, "-ka", *kfiles, "-w", wd)
+    vecs = [[float(x) for x in open(wd / "vectors" / (name + ".vec")).read().split()] for name in names]
+    assert [int(x) for x in vecs[1]] == [20208, 0, 0, 11337]
+    for i in range(3):
+        for j in range(3):
+            if i != j:
+                assert orc.bray_curtis(vecs[i], vecs[j]) == gold[(names[i], names[j])]
+    assert orc.java_double_to_string(orc.bray_curtis(vecs[0], vecs[2])) == "0.2981399448537721"

@@ -578,3 +578,36 @@ def test_seq_builder(built, k, thr, min_len):
         assert got == want
         assert ks.sequences(thr, 10 ** 6) == []                   # nothing is that long
     assert len(want) >= 1
+
+
+def test_reference_matrix_golden(built):
+    """The reference's only golden output for this path, test_data/meta_test_matrix.txt (the matrix-builder result on
+    meta_test_{1,2,3}.fa, k=31, -b 1, -l 100; copied verbatim to tests/golden/), reproduced with the device doing every
+    in-scope stage through the C ABI: counting + filtered emit, seq-builder, component-cutter's minSeqLen counting call,
+    features.  The component split and the Bray-Curtis formula (out of scope) are the checker's.
+    Exact doubles."""
+    gold = orc.load_matrix_txt(open(os.path.join(GOLDEN, "meta_test_matrix.txt")).read())
+    names = ["meta_test_%d" % n for n in (1, 2, 3)]
+    recs, seq_reads = {}, []
+    for name in names:
+        reads = m.read_file_reads(os.path.join(INPUTS, name + ".fa"))
+        recs[name], _, _ = run_counter([reads], 31, 1, m.VARIANT_HASH)
+        with m.KmerCounter(31) as ctx, m.KmerSet.load(ctx, [recs[name]], 1) as ks:
+            seq_reads += [s[0] for s in ks.sequences(1, 100)]
+    assert len(seq_reads) == 15 + 29 + 25
+    seq_rec, _, st = run_counter([seq_reads], 31, 0, m.VARIANT_HASH, min_len=100)
+    seq_hm = dict(orc.load_kmers_bin(seq_rec))
+    assert st["distinct"] == len(seq_hm) == 17061
+    comps3 = orc.component_cutter(seq_hm, 31, 1000, 10000)
+    vecs = {}
+    with m.FeaturesCalculator(31) as fc:
+        fc.load_components([keys for _w, keys, _thr in comps3])
+        for name in names:
+            fc.reset_values()
+            fc.add_records(recs[name])
+            vecs[name] = [int(x) for x in fc.features(0)[0]]
+    assert vecs["meta_test_1"] == [41935, 38354, 20375, 14211]
+    for a in names:
+        for b in names:
+            if a != b:
+                assert orc.bray_curtis(vecs[a], vecs[b]) == gold[(a, b)], (a, b)

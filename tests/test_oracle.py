@@ -154,3 +154,87 @@ def test_set_algebra_known_answers():
     n, recs, stat = orc.kmers_samples_counter([rec(1, 5) + rec(2, 5), rec(1, 2), rec(3, 9) + rec(1, 1)], 1)
     assert n == 3 and recs == rec(1, 2) + rec(2, 1) + rec(3, 1)
     assert stat == "# k-mer frequency\tnumber of such k-mers\n1\t2\n2\t1\n\n"
+
+
+def test_reference_matrix_golden(built):
+    """PINS THE ORACLE AGAINST THE REFERENCE'S OWN FIXTURE.  test_data/meta_test_matrix.txt (copied verbatim to
+    tests/golden/meta_test_matrix.txt) is the output the reference's authors checked in for
+    `matrix-builder -k 31 -i test_data/meta_test_{1,2,3}.fa` (README.md:90-99; defaults -b 1, -l 100): the Bray-Curtis
+    distances between the three samples' feature vectors, printed with all 16-17 digits.  Every stage of the path
+    feeds it: ~37 000 k-mer counts (parser, 2-bit code, canonical form, saturating count), the `count > b` filter of
+    .kmers.bin, seq-builder, the minSeqLen counting call of component-cutter, the component split, and the
+    features-calculator sums.  The oracle's restatement of that pipeline must reproduce the three distances to the
+    last bit."""
+    paths = [os.path.join(INPUTS, "meta_test_%d.fa" % n) for n in (1, 2, 3)]
+    gold = orc.load_matrix_txt(open(os.path.join(GOLDEN, "meta_test_matrix.txt")).read())
+    assert len(gold) == 9
+    names, matrix, mid = orc.matrix_builder(paths, k=31, b=1, min_seq_len=100)
+    assert names == ["meta_test_1", "meta_test_2", "meta_test_3"]
+    for i, a in enumerate(names):
+        for j, b in enumerate(names):
+            assert matrix[i][j] == gold[(a, b)], (a, b, matrix[i][j], gold[(a, b)])      # exact doubles
+    assert orc.java_double_to_string(matrix[0][1]) == "0.5691162409506898"
+    assert orc.java_double_to_string(matrix[0][2]) == "0.2981399448537721"
+    assert orc.java_double_to_string(matrix[1][2]) == "0.8448331091037222"
+    # intermediates, for the record (they are what the GPU pipeline test compares stage by stage)
+    assert [len(mid["sequences"][n]) for n in names] == [15, 29, 25]
+    assert len(mid["sequence_kmers"]) == 17061
+    assert [(len(keys), w, thr) for w, keys, thr in mid["components"]] == \
+        [(6240, 12783, 1), (5713, 11265, 1), (3020, 5977, 1), (2088, 4260, 1)]
+    assert mid["vectors"]["meta_test_2"] == [20208, 0, 0, 11337]
+    # the C restatement (oracle/ref_cpu.c: threads, striped maps) in place of the Python stages it covers -- parser + count
+    # + filtered emit per sample, the minSeqLen count over the sequences, the feature sums -- gives the same matrix
+    c_recs = []
+    for p in paths:
+        bases, offsets = _oracle_c.parse_file(p)
+        c_recs.append(_oracle_c.count(bases, offsets, 31, 1, P=4)[0])
+    seq_reads = [s[0] for n in names for s in mid["sequences"][n]]
+    sb = np.frombuffer("".join(seq_reads).encode(), dtype=np.uint8).copy()
+    so = np.zeros(len(seq_reads) + 1, dtype=np.uint64)
+    so[1:] = np.cumsum([len(r) for r in seq_reads])
+    c_seq = dict(orc.load_kmers_bin(_oracle_c.count(sb, so, 31, 0, min_len=100, P=3)[0]))
+    assert c_seq == mid["sequence_kmers"]
+    comps = [keys for _w, keys, _thr in orc.component_cutter(c_seq, 31)]
+    c_vecs = [[int(x) for x in _oracle_c.features_kmers(comps, rec, None, 0)[0]] for rec in c_recs]
+    for i in range(3):
+        for j in range(3):
+            if i != j:
+                assert orc.bray_curtis(c_vecs[i], c_vecs[j]) == gold[(names[i], names[j])]
+    # the fixture discriminates: the off-by-one reading of the -b filter (count >= b) moves every distance
+    keep = orc.kmers_bin
+    try:
+        orc.kmers_bin = lambda counts, threshold, k=31: keep(counts, threshold - 1, k)
+        _, wrong, _ = orc.matrix_builder(paths, k=31, b=1, min_seq_len=100)
+    finally:
+        orc.kmers_bin = keep
+    assert all(wrong[i][j] != matrix[i][j] for i in range(3) for j in range(3) if i != j)
+
+
+def test_component_cutter_known_answers():
+    """ComponentsBuilder on a hand-made graph: size limits b1/b2, and the re-split of a big component at threshold + 1"""
+    k = 11
+    a = "TGGCCAAAATGTGGTGGGGTCTGACTGATGTAATAGACCCCAAAAGGGCGTCCTTTCGTG"
+    b = "TGGCTAGGTGCCCCGTATGCGGCCGGGCTCCTCAG"
+    hm = orc.count_reads([a, a, b], k)                     # two separate paths; the k-mers of `a` have count 2
+    keys_a, keys_b = set(orc.canonical_kmers(a, k)), set(orc.canonical_kmers(b, k))
+    assert len(keys_a) == 50 and len(keys_b) == 25
+    assert not any(n in keys_b for x in keys_a for n in orc.possible_neighbours(x, k))
+    shape = lambda comps: [(set(c[1]), c[0], c[2]) for c in comps]
+    assert shape(orc.component_cutter(hm, k, b1=1, b2=1000)) == [(keys_a, 100, 1), (keys_b, 25, 1)]
+    assert shape(orc.component_cutter(hm, k, b1=26, b2=1000)) == [(keys_a, 100, 1)]           # size < b1 is dropped
+    assert shape(orc.component_cutter(hm, k, b1=25, b2=50)) == [(keys_a, 100, 1), (keys_b, 25, 1)]   # size == b2 is kept
+    # b2 = 49: `a` (50 k-mers, all of count 2) is big at threshold 1, still big at threshold 2, and has no k-mer of count
+    # >= 3: it vanishes.  b2 = 24: `b` is big too and has no k-mer of count >= 2
+    assert shape(orc.component_cutter(hm, k, b1=1, b2=49)) == [(keys_b, 25, 1)]
+    assert orc.component_cutter(hm, k, b1=1, b2=24) == []
+    # a path whose two ends were seen twice: too big as a whole, its ends survive the re-split at threshold 2
+    hm2 = orc.count_reads([a, a[:30], a[40:], b], k)
+    head, tail = set(orc.canonical_kmers(a[:30], k)), set(orc.canonical_kmers(a[40:], k))
+    assert shape(orc.component_cutter(hm2, k, b1=1, b2=49)) == [(keys_b, 25, 1), (head, 40, 2), (tail, 20, 2)]
+    assert shape(orc.component_cutter(hm2, k, b1=11, b2=49)) == [(keys_b, 25, 1), (head, 40, 2)]
+    comps = orc.component_cutter(hm, k, b1=1, b2=1000)
+    assert orc.components_stat_txt(comps).splitlines()[1:] == ["1\t50\t100\t1", "2\t25\t25\t1"]
+    assert orc.load_components(orc.save_components([(w, keys) for w, keys, _ in comps], k), k) == \
+        [(w, keys) for w, keys, _ in comps]
+    assert orc.bray_curtis([1, 2, 3], [1, 2, 3]) == 0.0 and orc.bray_curtis([1, 0], [0, 1]) == 1.0
+    assert orc.bray_curtis([3, 1], [1, 1]) == 2.0 / 6.0
