@@ -240,6 +240,19 @@ int  mfkc_kset_histogram(mfkc_kset *ks, uint64_t hist[MFKC_HIST_BINS]);
 int  mfkc_kset_sequences_begin(mfkc_kset *hm, int32_t freq_threshold, int32_t len_threshold, uint64_t *n_sequences, uint64_t *n_bases);
 int  mfkc_kset_sequences_fetch(mfkc_kset *hm, uint64_t *offsets, char *bases, uint32_t *av_weight, uint32_t *min_weight, uint32_t *max_weight);
 
+/* component-cutter's graph half on a map (the main caller's next stage): ComponentsBuilder.splitStrategy
+ * (src/algo/ComponentsBuilder.java:24-31,58-84,157-181,198-269; neighbours: src/algo/KmerOperations.java:9-26) over the
+ * map that IOUtils.loadReads(sequences, k, minLen) returns (src/tools/ComponentCutterMain.java:81-97).  Connected
+ * components of the k-mers with value > 0; fewer than min_component_size k-mers: dropped; up to max_component_size:
+ * kept with usedFreqThreshold = the level that found them (1 first); larger: split again among their k-mers of value >=
+ * level + 1.  Order = ConnectedComponent.compareTo (src/structures/ConnectedComponent.java:125-136: threshold ascending,
+ * weight descending, size descending), ties by ascending smallest k-mer; k-mers ascending inside a component (the
+ * reference's BFS / hash-map order is not part of the format).  _begin computes (*n_components, *n_kmers = total
+ * members); _fetch copies out and releases: comp_offsets[n_components + 1] into keys, weights[n] =
+ * ConnectedComponent.weight, thresholds[n] = usedFreqThreshold (either may be NULL).  Maps of up to 2^32 - 2 entries. */
+int  mfkc_kset_components_begin(mfkc_kset *hm, int64_t min_component_size, int64_t max_component_size, uint64_t *n_components, uint64_t *n_kmers);
+int  mfkc_kset_components_fetch(mfkc_kset *hm, uint64_t *comp_offsets, int64_t *keys, int64_t *weights, int32_t *thresholds);
+
 /* ---- host side of the path (CPU; no GPU needed): the parser rules of
  * [itmo]/io/ReadersUtils.java:27-102, readers/FastaReader.java:54-108,
  * readers/FastqReader.java:53-114, readers/FastaReaderFromXQSource.java:62-85 and the

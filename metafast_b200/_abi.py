@@ -115,6 +115,8 @@ SIGNATURES = {
     "mfkc_kset_histogram": (C.c_int, [C.c_void_p, u64p]),
     "mfkc_kset_sequences_begin": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, u64p, u64p]),
     "mfkc_kset_sequences_fetch": (C.c_int, [C.c_void_p, u64p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mfkc_kset_components_begin": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, u64p, u64p]),
+    "mfkc_kset_components_fetch": (C.c_int, [C.c_void_p, u64p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mfkc_reader_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),
     "mfkc_reader_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
     "mfkc_reader_counters": (C.c_int, [C.c_void_p, u64p]),

@@ -345,6 +345,20 @@ class KmerSet:
         return [(text[int(off[i]):int(off[i + 1])], int(av[i]), int(lo[i]), int(hi[i])) for i in range(n)]
 
 
+    def components(self, min_component_size: int = 1000, max_component_size: int = 10000):
+        """component-cutter's graph half (src/algo/ComponentsBuilder.java:24-31): [(weight, [k-mers ascending], usedFreqThreshold)]
+        in ConnectedComponent.compareTo order"""
+        nc, nk = C.c_uint64(), C.c_uint64()
+        self.ctx._ck(self.lib.mfkc_kset_components_begin(self.h, min_component_size, max_component_size, C.byref(nc), C.byref(nk)))
+        n = nc.value
+        off = np.zeros(n + 1, dtype=np.uint64)
+        keys = np.zeros(max(nk.value, 1), dtype=np.int64)
+        weight = np.zeros(max(n, 1), dtype=np.int64)
+        thr = np.zeros(max(n, 1), dtype=np.int32)
+        self.ctx._ck(self.lib.mfkc_kset_components_fetch(self.h, off.ctypes.data_as(_abi.u64p), _ptr(keys), _ptr(weight), _ptr(thr)))
+        return [(int(weight[i]), [int(x) for x in keys[int(off[i]):int(off[i + 1])]], int(thr[i])) for i in range(n)]
+
+
 def kmers_filter(ctx: "_Ctx", inputs: Sequence[bytes], filters: Sequence[bytes], b: int = 1, max_thresh: int = 0):
     """kmers-filter (src/tools/KmersFilter.java:94-110): per input file -> (hm.size(), filtered records)"""
     out = []

@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <string>
 #include <vector>
@@ -86,6 +87,10 @@ std::string java_double(double d) {
     return sign + digits.substr(0, 1) + "." + frac + "E" + std::to_string(exp10);
 }
 
+int g_ctx_gen = 0;                                        // bumped by make_ctx: function-local caches of pinned buffers follow it
+bool g_sub_tool = false;                                  // inside matrix-builder: sub-tools do not print their output values
+#define OUT_VALUE(...) do { if (!g_sub_tool) printf(__VA_ARGS__); } while (0)
+
 struct Args {
     std::string tool;
     std::map<std::string, std::vector<std::string>> opt;    // canonical long name -> values
@@ -111,7 +116,13 @@ Args parse_args(int argc, char **argv) {
         {"--k-mers", "reads"}, {"--filter-kmers", "filter-kmers"}, {"--max-thresh", "max-thresh"},
         {"--min-samples", "min-samples"}, {"--max-samples", "max-samples"}, {"--min-seq-len", "min-seq-len"}, {"-l", "l"},
         {"--maximal-bad-frequency", "maximal-bad-frequence"}, {"-bp", "bottom-cut-percent"}, {"--bottom-cut-percent", "bottom-cut-percent"},
-        {"--sequence-len", "sequence-len"}, {"-o", "output-dir"}};
+        {"--sequence-len", "sequence-len"}, {"-o", "output-dir"},
+        {"--sequences", "reads"}, {"-b1", "min-component-size"}, {"--min-component-size", "min-component-size"},
+        {"-b2", "max-component-size"}, {"--max-component-size", "max-component-size"}, {"--features", "features"},
+        {"-wn", "without-names"}, {"--without-names", "without-names"}, {"--matrix-file", "matrix-file"},
+        {"--output-format", "output-format"}, {"--newMatrix-file", "newMatrix-file"}, {"-wr", "without-renumbering"},
+        {"--without-renumbering", "without-renumbering"}, {"--heatmap-file", "heatmap-file"},
+        {"--use-reads-for-calculating-features", "use-reads-for-calculating-features"}};
     Args a;
     std::string cur;
     for (int i = 1; i < argc; i++) {
@@ -180,7 +191,8 @@ void for_each_batch(mfkc_ctx *ctx, const std::string &file, F submit, mfkc_reade
     info("Loading file %s...", base_name(file).c_str());
     if (!r) r = open_reader(file);
     const size_t cap_bases = 256u << 20; const uint32_t cap_reads = 1u << 21;
-    static void *h_bases = nullptr, *h_offs = nullptr;
+    static void *h_bases = nullptr, *h_offs = nullptr; static int owner_gen = -1;      // pinned buffers die with their context
+    if (owner_gen != g_ctx_gen) { h_bases = h_offs = nullptr; owner_gen = g_ctx_gen; }
     if (!h_bases) { CK(ctx, mfkc_pinned_alloc(ctx, cap_bases, &h_bases)); CK(ctx, mfkc_pinned_alloc(ctx, ((size_t)cap_reads + 1) * 8, &h_offs)); }
     unsigned long long reads = 0;
     for (;;) {
@@ -217,6 +229,8 @@ std::string count_sample(mfkc_ctx *ctx, int k, int b, const std::vector<std::str
     FILE *f = fopen(out_file.c_str(), "wb");
     if (!f) die("Can't write %s", out_file.c_str());
     static void *h_out = nullptr; const size_t chunk = 16777200;       // KMERS_WORK_RANGE_SIZE, src/io/IOUtils.java:30
+    static int owner_gen = -1;
+    if (owner_gen != g_ctx_gen) { h_out = nullptr; owner_gen = g_ctx_gen; }
     if (!h_out) CK(ctx, mfkc_pinned_alloc(ctx, chunk, &h_out));
     for (;;) {
         size_t w = 0;
@@ -253,6 +267,7 @@ mfkc_ctx *make_ctx(int k, const Gpu &g, uint64_t expected_kmers, bool long_kmers
     mfkc_ctx *ctx = nullptr;
     const int rc = mfkc_create(&cfg, &ctx);
     if (rc != MFKC_OK) die("%s (libmfkc %d)", mfkc_last_error(nullptr), rc);
+    g_ctx_gen++;
     return ctx;
 }
 
@@ -308,7 +323,7 @@ int tool_counter(const Args &a, bool many) {
     std::vector<std::string> outs;
     for (const auto &s : samples) outs.push_back(count_sample(ctx, k, b, s.second, s.first, out_dir, st_dir));
     mfkc_destroy(ctx);
-    for (const auto &o : outs) printf("%s\n", o.c_str());                 // "resulting-kmers-files"
+    for (const auto &o : outs) OUT_VALUE("%s\n", o.c_str());              // "resulting-kmers-files"
     return 0;
 }
 
@@ -379,7 +394,7 @@ int tool_features(const Args &a) {
         fclose(f);
         info("Features for file %s printed to %s", shown.c_str(), vf.c_str());
         info("Components breadth coverage for file %s printed to %s", shown.c_str(), bf.c_str());
-        printf("%s\n", vf.c_str());                                        // "features-files"
+        OUT_VALUE("%s\n", vf.c_str());                                     // "features-files"
     };
     for (const auto &rf : a.many("reads")) {                               // :120-134
         CK(ctx, mfkc_fc_reset_values(ctx));
@@ -604,9 +619,308 @@ int tool_seq_builder(const Args &a) {
         }
         fclose(f);
         info("Sequences printed to %s", out_file.c_str());
-        printf("%s\n", out_file.c_str());
+        OUT_VALUE("%s\n", out_file.c_str());
     }
     mfkc_destroy(ctx);
+    return 0;
+}
+
+// ---- seq-builder-many (src/tools/SeqBuilderForManyFilesMain.java:76-92): one seq-builder run per input file, sub-builder
+// work directory workDir/sub-builder
+int tool_seq_builder_many(const Args &a) {
+    if (a.has("maximal-bad-frequence") && a.has("bottom-cut-percent")) die("-b and -bp can not be set both");
+    const std::string work = a.one("work-dir", "workDir");
+    for (const auto &f : kmers_inputs(a)) {
+        Args sub = a;
+        sub.tool = "seq-builder";
+        sub.opt["reads"] = {f};
+        sub.opt["work-dir"] = {work + "/sub-builder"};
+        sub.opt["output-dir"] = {a.one("output-dir", work + "/sequences")};
+        tool_seq_builder(sub);
+    }
+    return 0;
+}
+
+// ---- component-cutter (src/tools/ComponentCutterMain.java:77-123): IOUtils.loadReads(sequences, k, minLen) on the device,
+// the records handed to a device map, ComponentsBuilder.splitStrategy on the device (mfkc_kset_components_*),
+// ConnectedComponent.saveComponents (src/structures/ConnectedComponent.java:80-93) + components-stat-<b1>-<b2>.txt
+int tool_component_cutter(const Args &a) {
+    const int k = parse_int(a, "k", true, 0); check_k(k);
+    const int min_len = parse_int(a, a.has("min-seq-len") ? "min-seq-len" : "l", false, 100);
+    const int b1 = parse_int(a, "min-component-size", false, 1000), b2 = parse_int(a, "max-component-size", false, 10000);
+    const auto files = a.many("reads");
+    if (files.empty()) die("Missing mandatory parameter --sequences");
+    const std::string work = a.one("work-dir", "workDir");
+    const std::string comp_file = a.one("components-file", work + "/components.bin");
+    mfkc_ctx *ctx = make_ctx(k, gpu_opts(a), estimate_bases(files), false, min_len);
+    for (const auto &f : files)
+        for_each_batch(ctx, f, [&](const uint8_t *bases, const uint64_t *offs, uint32_t n) { CK(ctx, mfkc_submit_reads(ctx, bases, offs, n)); });
+    CK(ctx, mfkc_flush(ctx));
+    uint64_t good = 0;
+    CK(ctx, mfkc_emit_begin(ctx, 0, &good));                               // every k-mer of the sequences (count > 0)
+    if (good == 0) die("No sequences were found in input files! The following steps will be useless");
+    std::vector<uint8_t> recs((size_t)good * 10);
+    for (size_t p = 0; p < recs.size();) {
+        size_t w = 0;
+        CK(ctx, mfkc_emit_next(ctx, recs.data() + p, recs.size() - p, &w));
+        if (!w) break;
+        p += w;
+    }
+    info("Searching for components...");
+    uint64_t nc = 0, nk = 0;
+    std::vector<uint64_t> off; std::vector<int64_t> keys, weight; std::vector<int32_t> thr;
+    {
+        KSet hm(ctx);
+        const size_t chunk = 16777200;
+        for (size_t p = 0; p < recs.size(); p += chunk) CK(ctx, mfkc_kset_load_records(hm.h, recs.data() + p, std::min(chunk, recs.size() - p) / 10, 0));
+        CK(ctx, mfkc_kset_load_finish(hm.h));
+        CK(ctx, mfkc_kset_components_begin(hm.h, b1, b2, &nc, &nk));
+        off.resize(nc + 1); keys.resize(nk + 1); weight.resize(nc + 1); thr.resize(nc + 1);
+        CK(ctx, mfkc_kset_components_fetch(hm.h, off.data(), keys.data(), weight.data(), thr.data()));
+    }
+    mfkc_destroy(ctx);
+    mkdirs(work);
+    const std::string stat_file = work + "/components-stat-" + std::to_string(b1) + "-" + std::to_string(b2) + ".txt";
+    FILE *sf = fopen(stat_file.c_str(), "w"); if (!sf) die("Can't write %s", stat_file.c_str());
+    fprintf(sf, "# component.no\tcomponent.size\tcomponent.weight\tusedFreqThreshold\n");        // ComponentsBuilder.java:146-151
+    for (uint64_t i = 0; i < nc; i++)
+        fprintf(sf, "%llu\t%llu\t%lld\t%d\n", (unsigned long long)(i + 1), (unsigned long long)(off[i + 1] - off[i]), (long long)weight[i], thr[i]);
+    fclose(sf);
+    info("Total %s components were found", group_digits(nc).c_str());
+    if (nc == 0) warn("No components were extracted! Perhaps you should decrease --min-component-size value");
+    const size_t slash = comp_file.find_last_of('/');
+    if (slash != std::string::npos) mkdirs(comp_file.substr(0, slash));
+    FILE *f = fopen(comp_file.c_str(), "wb"); if (!f) die("Can't write %s", comp_file.c_str());
+    auto be = [&](uint64_t v, int bytes) { for (int i = bytes - 1; i >= 0; i--) fputc((int)((v >> (8 * i)) & 0xFF), f); };
+    be((uint32_t)nc, 4);
+    for (uint64_t i = 0; i < nc; i++) {
+        be((uint32_t)(off[i + 1] - off[i]), 4);
+        be((uint64_t)weight[i], 8);
+        for (uint64_t j = off[i]; j < off[i + 1]; j++) be((uint64_t)keys[j], 8);
+    }
+    fclose(f);
+    info("Components saved to %s", comp_file.c_str());
+    OUT_VALUE("%s\n", comp_file.c_str());                                   // "components-file"
+    return 0;
+}
+
+// ---- java.util.Formatter for a double: "%.Nf" (FormattedFloatingDecimal: the shortest round-trip digits, rounded HALF_UP
+// to N places) and "%s" (Double.toString)
+std::string java_format(const std::string &fmt, double d) {
+    if (fmt == "%s") return java_double(d);
+    int prec = -1;
+    if (fmt.size() >= 4 && fmt[0] == '%' && fmt[1] == '.' && fmt.back() == 'f') {
+        prec = 0;
+        for (size_t i = 2; i + 1 < fmt.size(); i++) { if (fmt[i] < '0' || fmt[i] > '9') { prec = -1; break; } prec = prec * 10 + (fmt[i] - '0'); }
+    } else if (fmt == "%f") prec = 6;
+    if (prec < 0 || prec > 300) die("--output-format: only %%.<N>f, %%f and %%s are supported here, not '%s'", fmt.c_str());
+    if (std::isnan(d)) return "NaN";
+    if (std::isinf(d)) return d > 0 ? "Infinity" : "-Infinity";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, std::fabs(d), std::chars_format::scientific);
+    std::string sci(buf, r.ptr);
+    const size_t e = sci.find('e');
+    std::string digits = sci.substr(0, e);
+    int point = atoi(sci.c_str() + e + 1) + 1;                              // value = 0.digits x 10^point
+    digits.erase(std::remove(digits.begin(), digits.end(), '.'), digits.end());
+    // digits wanted = point + prec (may be <= 0)
+    const int keep = point + prec;
+    std::string kept;
+    if (keep < 0) kept = "";
+    else if ((size_t)keep >= digits.size()) kept = digits + std::string((size_t)keep - digits.size(), '0');
+    else {
+        kept = digits.substr(0, (size_t)keep);
+        if (digits[(size_t)keep] >= '5') {                                 // HALF_UP
+            int i = keep - 1;
+            while (i >= 0 && kept[(size_t)i] == '9') { kept[(size_t)i] = '0'; i--; }
+            if (i >= 0) kept[(size_t)i]++;
+            else { kept = "1" + kept; point++; }
+        }
+    }
+    if (keep < 0) { kept = ""; }
+    // kept holds `point` integer digits (if point > 0) followed by prec fraction digits
+    std::string ip, fp;
+    if (point > 0) { ip = kept.substr(0, (size_t)point); fp = kept.substr((size_t)point); }
+    else { ip = "0"; fp = std::string((size_t)std::min(-point, prec), '0') + kept; }
+    if ((int)fp.size() < prec) fp += std::string((size_t)prec - fp.size(), '0');
+    fp.resize((size_t)prec);
+    return std::string(d < 0 || std::signbit(d) ? "-" : "") + ip + (prec ? "." + fp : "");
+}
+
+std::string timestamp() {                                                   // Tool.startTimestamp: yyyy.MM.dd_HH.mm.ss
+    static std::string ts;
+    if (ts.empty()) { char b[64]; time_t t = time(nullptr); struct tm tmv; localtime_r(&t, &tmv); strftime(b, sizeof b, "%Y.%m.%d_%H.%M.%S", &tmv); ts = b; }
+    return ts;
+}
+std::string with_dt(std::string p) { const size_t i = p.find("$DT"); if (i != std::string::npos) p.replace(i, 3, timestamp()); return p; }
+std::string remove_ext_ci(const std::string &s, const std::string &ext) { return ends_with_ci(s, ext) ? s.substr(0, s.size() - ext.size()) : s; }
+
+// DistanceMatrixCalculatorMain.printMatrix (src/tools/DistanceMatrixCalculatorMain.java:91-121)
+void print_matrix(const std::vector<std::vector<double>> &m, const std::string &path, const std::vector<std::string> *names, const std::vector<int> *perm,
+                  const std::string &fmt) {
+    const size_t slash = path.find_last_of('/');
+    if (slash != std::string::npos) mkdirs(path.substr(0, slash));
+    FILE *f = fopen(path.c_str(), "w"); if (!f) die("Failed to print matrix to %s", path.c_str());
+    const size_t n = m.size();
+    auto at = [&](size_t i) { return perm ? (size_t)(*perm)[i] : i; };
+    if (names) { fputc('#', f); for (size_t i = 0; i < n; i++) fprintf(f, "\t%s", (*names)[at(i)].c_str()); fputc('\n', f); }
+    for (size_t i = 0; i < n; i++) {
+        if (names) fprintf(f, "%s\t", (*names)[at(i)].c_str());
+        for (size_t j = 0; j < n; j++) fprintf(f, "%s%s", j ? "\t" : "", java_format(fmt, m[at(i)][at(j)]).c_str());
+        fputc('\n', f);
+    }
+    fclose(f);
+}
+
+// ---- dist-matrix-calculator (src/tools/DistanceMatrixCalculatorMain.java:51-153): Bray-Curtis between the .vec files.
+// Host arithmetic on n_samples x n_components doubles -- nothing for a GPU here.
+std::string tool_dist_matrix(const Args &a) {
+    const auto files = a.many("features");
+    if (files.empty()) die("Missing mandatory parameter --features");
+    std::vector<std::vector<double>> feats;
+    for (const auto &ff : files) {                                          // readVector :123-138
+        FILE *f = fopen(ff.c_str(), "r"); if (!f) die("Failed to read features from %s", ff.c_str());
+        std::vector<double> v; char line[256];
+        while (fgets(line, sizeof line, f)) { if (line[0] != '\n' && line[0] != '\r' && line[0]) v.push_back(strtod(line, nullptr)); }
+        fclose(f);
+        feats.push_back(v);
+    }
+    const size_t n = feats.size();
+    std::vector<std::vector<double>> m(n, std::vector<double>(n, 0.0));
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = i + 1; j < n; j++) {                                // brayCurtisDistance :140-153, same summation order
+            double sumdiff = 0, sum = 0;
+            for (size_t p = 0; p < feats[i].size() && p < feats[j].size(); p++) { sumdiff += std::fabs(feats[i][p] - feats[j][p]); sum += std::fabs(feats[i][p]) + std::fabs(feats[j][p]); }
+            m[i][j] = m[j][i] = sumdiff / sum;
+        }
+    const std::string path = with_dt(a.one("matrix-file", a.one("work-dir", "workDir") + "/dist_matrix_$DT_original_order.txt"));
+    std::vector<std::string> names;
+    for (const auto &ff : files) names.push_back(remove_ext_ci(base_name(ff), ".vec"));
+    print_matrix(m, path, a.has("without-names") ? nullptr : &names, nullptr, a.one("output-format", "%.4f"));
+    info("Distance matrix printed to %s", path.c_str());
+    OUT_VALUE("%s\n", path.c_str());
+    return path;
+}
+
+// ---- heatmap-maker (src/tools/HeatMapMakerMain.java:91-166), the part that feeds the pipeline's result: parse the matrix
+// file (:169-234), cluster the samples by average linkage (FullHeatMap.clusterObjects, src/algo/FullHeatMap.java:218-289),
+// renumber them in leaf order (renumber :321-333) and print the renumbered matrix.  The PNG / SVG drawing is out of scope.
+std::string tool_heatmap(const Args &a) {
+    const std::string in = a.has("matrix-file") ? a.one("matrix-file") : a.one("reads");
+    if (in.empty()) die("Missing mandatory parameter --matrix-file");
+    FILE *f = fopen(in.c_str(), "r"); if (!f) die("Can't read matrix file %s", in.c_str());
+    std::vector<std::vector<std::string>> rows; char *line = nullptr; size_t cap = 0;
+    while (getline(&line, &cap, f) >= 0) {
+        std::vector<std::string> cells; std::string cur;
+        for (char *c = line; *c && *c != '\n' && *c != '\r'; c++) { if (*c == '\t') { if (!cur.empty()) cells.push_back(cur); cur.clear(); } else cur += *c; }
+        if (!cur.empty()) cells.push_back(cur);                            // StringTokenizer: empty tokens vanish
+        rows.push_back(cells);
+    }
+    free(line); fclose(f);
+    if (rows.empty()) die("No data to read in matrix file %s", in.c_str());
+    const size_t fn = rows[0].size();
+    if (fn > rows.size()) die("Can't parse matrix, columns' number > rows' number");
+    for (size_t i = 0; i < fn; i++) if (rows[i].size() != fn) die("Can't parse matrix, columns' number is different for different rows");
+    for (size_t i = fn; i < rows.size(); i++) if (!rows[i].empty()) die("Can't parse matrix, too much rows");
+    const bool with_names = fn && rows[0][0] == "#";
+    const size_t n = with_names ? fn - 1 : fn, dx = with_names ? 1 : 0;
+    std::vector<std::string> names(n);
+    std::vector<std::vector<double>> m(n, std::vector<double>(n));
+    for (size_t i = 0; i < n; i++) names[i] = with_names ? rows[0][i + 1] : std::to_string(i + 1) + " library";
+    for (size_t i = 0; i < n; i++) for (size_t j = 0; j < n; j++) m[i][j] = strtod(rows[i + dx][j + dx].c_str(), nullptr);
+    // clusterObjects: repeatedly merge the closest pair (first minimum in (i, j) order), group distance = mean over pairs
+    struct Node { int no, left, right; };
+    std::vector<Node> nodes; std::vector<int> slot(n);
+    for (size_t i = 0; i < n; i++) { nodes.push_back(Node{(int)i, -1, -1}); slot[i] = (int)i; }
+    std::vector<std::vector<int>> group(n);
+    for (size_t i = 0; i < n; i++) group[i] = {(int)i};
+    auto gdist = [&](const std::vector<int> &g1, const std::vector<int> &g2) {
+        if (g1.empty() || g2.empty()) return -1.0;
+        double sum = 0;
+        for (int x : g1) for (int y : g2) sum += m[(size_t)x][(size_t)y];
+        return sum / (double)g1.size() / (double)g2.size();
+    };
+    std::vector<std::vector<double>> dist(n, std::vector<double>(n, 0.0));
+    for (size_t i = 0; i < n; i++) for (size_t j = i + 1; j < n; j++) dist[i][j] = dist[j][i] = gdist(group[i], group[j]);
+    int root = n ? 0 : -1;
+    for (size_t count = n; count > 1; count--) {
+        double best = 1.7976931348623157e308; int bi = -1, bj = -1;
+        for (size_t i = 0; i < n; i++) for (size_t j = i + 1; j < n; j++)
+            if (slot[i] >= 0 && slot[j] >= 0 && dist[i][j] < best) { best = dist[i][j]; bi = (int)i; bj = (int)j; }
+        if (bi < 0 || best < 0) die("Internal error. Wrong minDist index.");
+        nodes.push_back(Node{-1, slot[(size_t)bi], slot[(size_t)bj]});
+        root = (int)nodes.size() - 1;
+        slot[(size_t)bi] = root; slot[(size_t)bj] = -1;
+        group[(size_t)bi].insert(group[(size_t)bi].end(), group[(size_t)bj].begin(), group[(size_t)bj].end());   // getGroup: left leaves, then right
+        group[(size_t)bj].clear();
+        for (size_t i = 0; i < n; i++) {
+            dist[i][(size_t)bj] = dist[(size_t)bj][i] = -1;
+            if ((int)i != bi) dist[i][(size_t)bi] = dist[(size_t)bi][i] = gdist(group[(size_t)bi], group[i]);
+        }
+    }
+    std::vector<int> perm;
+    if (root >= 0) {                                                        // renumber: leaves left to right
+        std::vector<int> stack{root};
+        while (!stack.empty()) {
+            const Node nd = nodes[(size_t)stack.back()]; stack.pop_back();
+            if (nd.no >= 0) perm.push_back(nd.no);
+            else { stack.push_back(nd.right); stack.push_back(nd.left); }
+        }
+    }
+    std::string out = a.has("newMatrix-file") ? with_dt(a.one("newMatrix-file")) : remove_ext_ci(in, ".txt") + "_renumbered.txt";
+    if (a.has("without-renumbering")) out = in;
+    else {
+        print_matrix(m, out, &names, &perm, a.one("output-format", "%.4f"));
+        info("Renumbered matrix saved to %s", out.c_str());
+    }
+    warn("The heat map image is not drawn by this build (only the renumbered matrix is produced)");
+    OUT_VALUE("%s\n", out.c_str());
+    return out;
+}
+
+// ---- matrix-builder (src/tools/DistanceMatrixBuilderMain.java:88-176): the reference's default pipeline
+//   kmer-counter-many -> seq-builder-many -> component-cutter -> features-calculator -> dist-matrix-calculator -> heatmap-maker
+// with the reference's wiring of parameters and default locations.  --output-format is an extra (the reference fixes "%.4f";
+// "%s" prints Double.toString, which is what test_data/meta_test_matrix.txt holds).
+int tool_matrix_builder(const Args &a) {
+    const auto reads = a.many("reads");
+    info("Found %zu libraries to process", reads.size());
+    if (reads.empty()) die("No libraries to process!!! Can't continue the calculations.");
+    const std::string work = a.one("work-dir", "workDir");
+    const std::string k = a.one("k", "31"), b = a.one("maximal-bad-frequence", "1");
+    const std::string l = a.has("min-seq-len") ? a.one("min-seq-len") : a.one("l", "100");
+    const std::string fmt = a.one("output-format", "%.4f");
+    auto base = [&]() { Args s; s.opt["k"] = {k}; s.opt["work-dir"] = {work}; if (a.has("gpu")) s.opt["gpu"] = a.many("gpu"); return s; };
+    g_sub_tool = true;
+    // sample names as kmer-counter-many derives them (sorted paths, _R1/_R2 pairs)
+    std::vector<std::string> files = reads; std::sort(files.begin(), files.end());
+    std::vector<std::string> names;
+    {
+        std::vector<std::string> nm; for (const auto &f : files) nm.push_back(reader_name(f));
+        for (size_t i = 0; i < nm.size();) {
+            const bool pair = i + 1 < nm.size() && ((ends_with(nm[i], "_r1") && ends_with(nm[i + 1], "_r2")) || (ends_with(nm[i], "_R1") && ends_with(nm[i + 1], "_R2")));
+            names.push_back(pair ? nm[i].substr(0, nm[i].size() - 3) : nm[i]); i += pair ? 2 : 1;
+        }
+    }
+    { Args s = base(); s.tool = "kmer-counter-many"; s.opt["reads"] = reads; s.opt["maximal-bad-frequence"] = {b}; tool_counter(s, true); }
+    std::vector<std::string> kfiles, sfiles;
+    for (const auto &nme : names) { kfiles.push_back(work + "/kmers/" + nme + ".kmers.bin"); sfiles.push_back(work + "/sequences/" + nme + ".seq.fasta"); }
+    { Args s = base(); s.tool = "seq-builder-many"; s.opt["reads"] = kfiles; s.opt["maximal-bad-frequence"] = {b}; s.opt["sequence-len"] = {l}; tool_seq_builder_many(s); }
+    { Args s = base(); s.tool = "component-cutter"; s.opt["reads"] = sfiles; s.opt["min-seq-len"] = {l}; tool_component_cutter(s); }
+    {
+        Args s = base(); s.tool = "features-calculator"; s.opt["components-file"] = {work + "/components.bin"};
+        if (a.has("use-reads-for-calculating-features")) s.opt["reads"] = reads; else s.opt["kmers"] = kfiles;
+        tool_features(s);
+    }
+    std::vector<std::string> vfiles;
+    if (a.has("use-reads-for-calculating-features")) for (const auto &f : reads) vfiles.push_back(work + "/vectors/" + reader_name(f) + ".vec");
+    else for (const auto &nme : names) vfiles.push_back(work + "/vectors/" + nme + ".vec");
+    std::string orig;
+    { Args s = base(); s.opt["features"] = vfiles; s.opt["matrix-file"] = {work + "/matrices/dist_matrix_$DT_original_order.txt"}; s.opt["output-format"] = {fmt}; orig = tool_dist_matrix(s); }
+    std::string final_matrix;
+    { Args s = base(); s.opt["matrix-file"] = {orig}; s.opt["newMatrix-file"] = {a.one("matrix-file", work + "/matrices/dist_matrix_$DT.txt")}; s.opt["output-format"] = {fmt}; final_matrix = tool_heatmap(s); }
+    g_sub_tool = false;
+    OUT_VALUE("%s\n", final_matrix.c_str());
     return 0;
 }
 
@@ -653,6 +967,12 @@ int main(int argc, char **argv) {
     if (a.tool == "unique-kmers-multi") return tool_unique_kmers_multi(a);
     if (a.tool == "kmers-samples-counter") return tool_kmers_samples_counter(a);
     if (a.tool == "seq-builder") return tool_seq_builder(a);
-    die("Tool '%s' is outside the hot path this build replaces (kmer-counter-many, kmer-counter, features-calculator, kmers-filter, "
-        "unique-kmers-multi, kmers-samples-counter, seq-builder)", a.tool.c_str());
+    if (a.tool == "seq-builder-many") return tool_seq_builder_many(a);
+    if (a.tool == "component-cutter") return tool_component_cutter(a);
+    if (a.tool == "dist-matrix-calculator") { tool_dist_matrix(a); return 0; }
+    if (a.tool == "heatmap-maker") { tool_heatmap(a); return 0; }
+    if (a.tool == "matrix-builder") return tool_matrix_builder(a);
+    die("Tool '%s' is outside the path this build replaces (matrix-builder, kmer-counter-many, kmer-counter, seq-builder, seq-builder-many, "
+        "component-cutter, features-calculator, dist-matrix-calculator, heatmap-maker, kmers-filter, unique-kmers-multi, "
+        "kmers-samples-counter)", a.tool.c_str());
 }

@@ -14,11 +14,13 @@ struct mfkc_kset {
     unsigned long long *d_cursor = nullptr;
     uint8_t *sel = nullptr; uint64_t sel_n = 0, sel_cursor = 0; bool sel_valid = false;
     SeqResult *seq = nullptr;                // no global state: the pending sequences belong to the map
+    mfkc::CcResult *comps = nullptr;         // pending components (mfkc_kset_components_begin -> _fetch)
 };
 
 static void kset_drop_sequences(mfkc_kset *ks) {
     if (ks->seq) { cudaFree(ks->seq->d_bases); delete ks->seq; ks->seq = nullptr; }
 }
+static void kset_drop_components(mfkc_kset *ks) { delete ks->comps; ks->comps = nullptr; }
 
 static int kset_block_scan(mfkc_ctx *ctx, cudaStream_t st, unsigned long long *d_blk, int grid, unsigned long long *total) {
     std::vector<unsigned long long> h(grid);
@@ -50,6 +52,7 @@ extern "C" void mfkc_kset_destroy(mfkc_kset *ks) {
     cudaStreamSynchronize(ks->ctx->compute);
     cudaFree(ks->keys); cudaFree(ks->vals); cudaFree(ks->pk); cudaFree(ks->pv); cudaFree(ks->d_cursor); cudaFree(ks->sel);
     kset_drop_sequences(ks);
+    kset_drop_components(ks);
     delete ks;
 }
 
@@ -341,5 +344,85 @@ extern "C" int mfkc_kset_sequences_fetch(mfkc_kset *hm, uint64_t *offsets, char 
     if (ns && bases) e = cudaMemcpy(bases, res.d_bases, res.off[ns], cudaMemcpyDeviceToHost);
     cudaFree(res.d_bases);
     if (e != cudaSuccess) return fail(ctx, MFKC_E_CUDA, "copy of the sequences failed");
+    return MFKC_OK;
+}
+
+// ---- component-cutter's graph half on a k-mer map (kernels: components.cuh, grouping: components_host.h) --------------
+// Device buffers of one run; freed on every exit path
+struct CcBuffers {
+    Slot *tab = nullptr; uint8_t *active = nullptr; uint32_t *label = nullptr, *thr_of = nullptr, *parent = nullptr, *size = nullptr;
+    unsigned long long *counters = nullptr;
+    ~CcBuffers() { cudaFree(tab); cudaFree(active); cudaFree(label); cudaFree(thr_of); cudaFree(parent); cudaFree(size); cudaFree(counters); }
+};
+
+extern "C" int mfkc_kset_components_begin(mfkc_kset *hm, int64_t min_component_size, int64_t max_component_size, uint64_t *n_components,
+                                          uint64_t *n_kmers) {
+    if (!hm || !n_components || !n_kmers) return MFKC_E_BADARG;
+    mfkc_ctx *ctx = hm->ctx;
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->compute;
+    kset_drop_components(hm);
+    *n_components = 0; *n_kmers = 0;
+    const uint64_t n = hm->n;
+    if (n >= 0xFFFFFFFFull) return fail(ctx, MFKC_E_BADARG, "mfkc_kset_components: the map has more than 2^32 - 2 entries");
+    mfkc::CcResult *res = new mfkc::CcResult();
+    res->off.assign(1, 0);
+    if (n) {
+        const int k = ctx->cfg.k;
+        const uint64_t cap = n * 2 + 64;
+        CcBuffers b;
+        bool oom = big_alloc(ctx, (void **)&b.tab, cap * sizeof(Slot)) != cudaSuccess;
+        oom = oom || big_alloc(ctx, (void **)&b.active, n) != cudaSuccess;
+        oom = oom || big_alloc(ctx, (void **)&b.label, n * 4) != cudaSuccess || big_alloc(ctx, (void **)&b.thr_of, n * 4) != cudaSuccess;
+        oom = oom || big_alloc(ctx, (void **)&b.parent, n * 4) != cudaSuccess || big_alloc(ctx, (void **)&b.size, n * 4) != cudaSuccess;
+        oom = oom || cudaMalloc((void **)&b.counters, 2 * sizeof(unsigned long long)) != cudaSuccess;
+        if (oom) { delete res; return fail(ctx, MFKC_E_OOM, "cannot allocate the component buffers"); }
+        const int grid = grid_for(ctx, n, 256, 8);
+        cudaError_t e = cudaMemsetAsync(b.tab, 0xFF, cap * sizeof(Slot), st);                   // every key = EMPTY_KEY
+        cc_index_build_kernel<<<grid, 256, 0, st>>>(hm->keys, n, b.tab, cap);
+        cc_begin_kernel<<<grid, 256, 0, st>>>(hm->vals, n, b.active, b.label, b.thr_of);
+        CcIndex ix; ix.tab = b.tab; ix.cap = cap;
+        // one level per frequency threshold (Task.run: curFreqThreshold = usedFreqThreshold + 1); values are shorts, so
+        // nothing can stay active past 32767
+        for (int thr = 1; thr <= 32767 && e == cudaSuccess; thr++) {
+            unsigned long long counters[2] = {0, 0};
+            e = cudaMemsetAsync(b.counters, 0, sizeof counters, st);
+            cc_level_init_kernel<<<grid, 256, 0, st>>>(n, b.parent, b.size);
+            cc_union_kernel<<<grid, 256, 0, st>>>(hm->keys, n, b.active, ix, k, b.parent);
+            cc_count_kernel<<<grid, 256, 0, st>>>(n, b.active, b.parent, b.size);
+            cc_classify_kernel<<<grid, 256, 0, st>>>(hm->vals, n, b.active, b.parent, b.size, (long long)min_component_size,
+                                                      (long long)max_component_size, thr, b.label, b.thr_of, b.counters);
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(counters, b.counters, sizeof counters, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess || !counters[0]) break;
+        }
+        std::vector<unsigned long long> h_keys(n);
+        std::vector<uint32_t> h_vals(n), h_label(n), h_thr(n);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_keys.data(), hm->keys, n * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_vals.data(), hm->vals, n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_label.data(), b.label, n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_thr.data(), b.thr_of, n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { delete res; return fail(ctx, MFKC_E_CUDA, cudaGetErrorString(e)); }
+        mfkc::cc_group(h_keys.data(), h_vals.data(), h_label.data(), h_thr.data(), n, *res);
+    }
+    *n_components = res->weight.size(); *n_kmers = res->keys.size();
+    hm->comps = res;
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_kset_components_fetch(mfkc_kset *hm, uint64_t *comp_offsets, int64_t *keys, int64_t *weights, int32_t *thresholds) {
+    if (!hm || !comp_offsets) return MFKC_E_BADARG;
+    mfkc_ctx *ctx = hm->ctx;
+    if (!hm->comps) return fail(ctx, MFKC_E_STATE, "mfkc_kset_components_fetch without mfkc_kset_components_begin");
+    const mfkc::CcResult &res = *hm->comps;
+    const size_t nc = res.weight.size();
+    if (!keys && !res.keys.empty()) return MFKC_E_BADARG;
+    memcpy(comp_offsets, res.off.data(), (nc + 1) * sizeof(uint64_t));
+    if (!res.keys.empty()) memcpy(keys, res.keys.data(), res.keys.size() * sizeof(int64_t));
+    if (weights && nc) memcpy(weights, res.weight.data(), nc * sizeof(int64_t));
+    if (thresholds && nc) memcpy(thresholds, res.thr.data(), nc * sizeof(int32_t));
+    kset_drop_components(hm);
     return MFKC_OK;
 }

@@ -14,6 +14,8 @@
 #include "kernels128.cuh"
 #include "radix_sort.cuh"
 #include "kset.cuh"
+#include "components.cuh"
+#include "components_host.h"
 #include "synth.h"
 
 using namespace mfkc;

@@ -844,6 +844,56 @@ def matrix_builder(paths: Sequence[str], k: int = 31, b: int = 1, min_seq_len: i
                            "vectors": vecs}
 
 
+def java_format_fixed(d: float, prec: int = 4) -> str:
+    """java.util.Formatter "%.<prec>f" for a double: the shortest round-trip digits (FormattedFloatingDecimal), rounded
+    HALF_UP -- not C's exact-binary half-even (0.125 -> "0.13" in Java, "0.12" in C)"""
+    from decimal import Decimal, ROUND_HALF_UP
+    q = Decimal(1).scaleb(-prec)
+    return format(Decimal(repr(float(d))).quantize(q, rounding=ROUND_HALF_UP), "f")
+
+
+def heatmap_order(matrix: Sequence[Sequence[float]]) -> List[int]:
+    """FullHeatMap.clusterObjects + renumber (src/algo/FullHeatMap.java:218-289,321-333): average-linkage clustering,
+    the first minimum in (i, j) order is merged into slot i; the new order of the samples = leaves left to right"""
+    n = len(matrix)
+    groups: List[Optional[List[int]]] = [[i] for i in range(n)]
+
+    def gdist(g1, g2):
+        total = 0.0
+        for x in g1:
+            for y in g2:
+                total += matrix[x][y]
+        return total / len(g1) / len(g2)
+
+    for _ in range(n - 1):
+        best, bi, bj = float("inf"), -1, -1
+        for i in range(n):
+            for j in range(i + 1, n):
+                if groups[i] is not None and groups[j] is not None:
+                    dij = gdist(groups[i], groups[j])
+                    if dij < best:
+                        best, bi, bj = dij, i, j
+        groups[bi] = groups[bi] + groups[bj]
+        groups[bj] = None
+    return [g for g in groups if g is not None][0] if n else []
+
+
+def matrix_txt(matrix: Sequence[Sequence[float]], names: Optional[Sequence[str]], perm: Optional[Sequence[int]] = None,
+               fmt: str = "%.4f") -> str:
+    """DistanceMatrixCalculatorMain.printMatrix (src/tools/DistanceMatrixCalculatorMain.java:91-121); fmt "%.<N>f" or
+    "%s" (Double.toString)"""
+    n = len(matrix)
+    at = (lambda i: perm[i]) if perm is not None else (lambda i: i)
+    cell = java_double_to_string if fmt == "%s" else (lambda d: java_format_fixed(d, int(fmt[2:-1])))
+    out = []
+    if names is not None:
+        out.append("#" + "".join("\t" + names[at(i)] for i in range(n)) + "\n")
+    for i in range(n):
+        row = "\t".join(cell(matrix[at(i)][at(j)]) for j in range(n))
+        out.append((names[at(i)] + "\t" if names is not None else "") + row + "\n")
+    return "".join(out)
+
+
 def load_matrix_txt(text: str) -> Dict[Tuple[str, str], float]:
     """Parses DistanceMatrixCalculatorMain.printMatrix output (src/tools/DistanceMatrixCalculatorMain.java:91-121)
     into {(row name, column name): value}; the heat-map step may have permuted rows and columns"""

@@ -223,3 +223,43 @@ def test_matrix_builder_pipeline_reference_golden(built, tmp_path):
             if i != j:
                 assert orc.bray_curtis(vecs[i], vecs[j]) == gold[(names[i], names[j])]
     assert orc.java_double_to_string(orc.bray_curtis(vecs[0], vecs[2])) == "0.2981399448537721"
+
+
+def test_matrix_builder_cli_reproduces_the_reference_file(built, tmp_path):
+    """ONE command, the reference's default pipeline (src/tools/DistanceMatrixBuilderMain.java:88-176) on its own test
+    samples: the final matrix file equals test_data/meta_test_matrix.txt (tests/golden/) byte for byte.  Counting,
+    seq-builder, component-cutter (count + graph split) and features run on the GPU; the distances and the renumbering
+    are host arithmetic on 3 x 4 numbers."""
+    import glob
+    from tests.conftest import GOLDEN
+    files = [os.path.join(INPUTS, "meta_test_%d.fa" % n) for n in (2, 3, 1)]
+    wd = tmp_path / "wd"
+    r = run_cli("-t", "matrix-builder", "-k", 31, "-i", *files, "-w", wd, "--output-format", "%s")
+    (out,) = r.stdout.split()
+    assert out.startswith(str(wd / "matrices" / "dist_matrix_")) and not out.endswith("_original_order.txt")
+    assert open(out).read() == open(os.path.join(GOLDEN, "meta_test_matrix.txt")).read()
+    (orig,) = glob.glob(str(wd / "matrices" / "*_original_order.txt"))
+    assert open(orig).read().splitlines()[0] == "#\tmeta_test_1\tmeta_test_2\tmeta_test_3"
+    # the stages' files, at the reference's default locations
+    assert open(wd / "components-stat-1000-10000.txt").read() == (
+        "# component.no\tcomponent.size\tcomponent.weight\tusedFreqThreshold\n"
+        "1\t6240\t12783\t1\n2\t5713\t11265\t1\n3\t3020\t5977\t1\n4\t2088\t4260\t1\n")
+    comps = orc.load_components(open(wd / "components.bin", "rb").read())
+    assert [(w, len(keys)) for w, keys in comps] == [(12783, 6240), (11265, 5713), (5977, 3020), (4260, 2088)]
+    assert all(keys == sorted(keys) for _, keys in comps)
+    assert open(wd / "vectors" / "meta_test_2.vec").read() == "20208\n0\n0\n11337\n"
+    assert os.path.exists(wd / "sub-builder" / "distribution") and os.path.exists(wd / "sequences" / "meta_test_3.seq.fasta")
+    assert "Total 4 components were found" in r.stderr and "Found 3 libraries to process" in r.stderr
+    # default format = the README's table (README.md:96-99); the component-cutter tool on its own with other limits
+    r = run_cli("-t", "matrix-builder", "-i", *files, "-w", tmp_path / "w2")
+    assert open(r.stdout.split()[0]).read().splitlines()[1] == "meta_test_1\t0.0000\t0.2981\t0.5691"
+    sfiles = sorted(glob.glob(str(wd / "sequences" / "*.seq.fasta")))
+    run_cli("-t", "component-cutter", "-k", 31, "-i", *sfiles, "-b1", 100, "-b2", 3000, "-l", 100, "-w", tmp_path / "w3",
+            "--components-file", tmp_path / "w3" / "c.bin")
+    seq_reads = []
+    for f in sfiles:
+        seq_reads += orc.parse_reads(f)
+    want = orc.component_cutter(orc.count_reads(seq_reads, 31, 100), 31, 100, 3000)
+    assert len(want) == 34
+    assert open(tmp_path / "w3" / "c.bin", "rb").read() == orc.save_components([(w, keys) for w, keys, _ in want])
+    assert open(tmp_path / "w3" / "components-stat-100-3000.txt").read() == orc.components_stat_txt(want)

@@ -611,3 +611,22 @@ def test_reference_matrix_golden(built):
         for b in names:
             if a != b:
                 assert orc.bray_curtis(vecs[a], vecs[b]) == gold[(a, b)], (a, b)
+
+
+@pytest.mark.parametrize("k,b1,b2", [(31, 50, 800), (21, 1, 100), (11, 30, 2000), (5, 1, 20), (31, 1000, 10000)])
+def test_component_cutter(built, k, b1, b2):
+    """component-cutter's graph half (mfkc_kset_components_*, csrc/components.cuh) against the restatement of
+    ComponentsBuilder (src/algo/ComponentsBuilder.java:24-31): size window, re-split of big components level by level
+    (up to 264 levels at k = 5), weights, thresholds, order"""
+    reads = []
+    for n in ((1, 2, 3) if b1 == 1000 else (2,)):
+        reads += orc.parse_reads(os.path.join(INPUTS, "meta_test_%d.fa" % n))
+    counts = orc.count_reads(reads, k)
+    want = orc.component_cutter(counts, k, b1, b2)
+    assert len(want) >= 2
+    with m.KmerCounter(k) as ctx, m.KmerSet.load(ctx, [orc.kmers_bin(counts, 0, k)], 0) as ks:
+        assert ks.components(b1, b2) == want
+        assert ks.components(10 ** 9, 10 ** 9 + 1) == []            # everything is "small"
+        assert ks.components(b1, b2) == want                        # repeatable on the same map
+    with m.KmerCounter(k) as ctx, m.KmerSet(ctx) as empty:
+        assert empty.components(1, 10) == []

@@ -230,3 +230,95 @@ def test_parallel_reader_equals_serial(built, tmp_path, monkeypatch):
             assert _read_all(str(gz), 4, 777, monkeypatch) == want
         if name in ("trunc.fastq", "badchar.fastq", "badlen.fastq", "iupac.fa"):
             assert want[0] == "error"
+
+
+# ---------------------------------------------------------------- the main caller's remaining stages (matrix-builder)
+def _emulated_components(hm, k, b1, b2):
+    """tests/emu/cc_emu.cpp: the kernels of metafast_b200/csrc/components.cuh compiled for the host"""
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libcc_emu.so"))
+    keys = np.array(sorted(hm), dtype=np.uint64)
+    vals = np.array([hm[int(x)] & 0xFFFF for x in keys], dtype=np.uint32)
+    nc, nk, lv, res = C.c_uint64(), C.c_uint64(), C.c_int(), C.c_void_p()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.cc_emu_components(vp(keys), vp(vals), C.c_uint64(len(keys)), C.c_int(k), C.c_longlong(b1), C.c_longlong(b2),
+                          C.byref(nc), C.byref(nk), C.byref(lv), C.byref(res))
+    off = np.zeros(nc.value + 1, dtype=np.uint64)
+    ks = np.zeros(max(nk.value, 1), dtype=np.int64)
+    w = np.zeros(max(nc.value, 1), dtype=np.int64)
+    t = np.zeros(max(nc.value, 1), dtype=np.int32)
+    lib.cc_emu_fetch(res, vp(off), vp(ks), vp(w), vp(t))
+    return [(int(w[i]), [int(x) for x in ks[int(off[i]):int(off[i + 1])]], int(t[i])) for i in range(nc.value)], lv.value
+
+
+def test_component_kernels_emulated_on_host(built):
+    """component-cutter's graph half: the CUDA kernels (union-find levels, classification) and the host grouping, run as
+    one emulated thread on the CPU, against the restatement of ComponentsBuilder -- size window, re-split levels, order"""
+    reads = orc.parse_reads(os.path.join(INPUTS, "meta_test_2.fa"))
+    for k, b1, b2, min_levels in ((31, 50, 800, 3), (21, 1, 100, 5), (11, 30, 2000, 5), (5, 1, 20, 100)):
+        hm = orc.count_reads(reads, k)
+        want = orc.component_cutter(hm, k, b1, b2)
+        got, levels = _emulated_components(hm, k, b1, b2)
+        assert got == want and len(want) > 5
+        assert levels >= min_levels                                   # big components were re-split level after level
+    assert _emulated_components({}, 31, 1, 10) == ([], 0)
+    # values <= 0 are no vertices (`getValue() > 0`); key 0 (poly-A) is its own neighbour
+    assert _emulated_components({0: 3, 5: 0xFFFE}, 3, 1, 10)[0] == [(3, [0], 1)] == orc.component_cutter({0: 3}, 3, 1, 10)
+
+
+CLI = os.path.join(ROOT, "metafast_b200", "bin", "mfkc_cli")
+GOLDEN_VECS = {"meta_test_1": [41935, 38354, 20375, 14211], "meta_test_2": [20208, 0, 0, 11337],
+               "meta_test_3": [6517, 34484, 20359, 749]}            # tests/test_oracle.py::test_reference_matrix_golden
+
+
+def _cli(*args):
+    import subprocess
+    r = subprocess.run([CLI] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    return r
+
+
+def test_dist_matrix_and_renumbering_reproduce_the_reference_file(built, tmp_path):
+    """dist-matrix-calculator + heatmap-maker's renumbering (host tools of mfkc_cli, no GPU involved) on the feature vectors
+    of the three test samples: test_data/meta_test_matrix.txt byte for byte with --output-format %s, README.md:96-99 with
+    the default %.4f"""
+    vfiles = []
+    for name, vec in GOLDEN_VECS.items():
+        (tmp_path / (name + ".vec")).write_text(orc.vec_text(vec))
+        vfiles.append(tmp_path / (name + ".vec"))
+    r = _cli("-t", "dist-matrix-calculator", "--features", *vfiles, "--matrix-file", tmp_path / "m.txt", "--output-format", "%s")
+    assert r.stdout.split() == [str(tmp_path / "m.txt")]
+    r = _cli("-t", "heatmap-maker", "-i", tmp_path / "m.txt", "--output-format", "%s")
+    assert r.stdout.split() == [str(tmp_path / "m_renumbered.txt")]
+    golden = open(os.path.join(ROOT, "tests", "golden", "meta_test_matrix.txt")).read()
+    assert (tmp_path / "m_renumbered.txt").read_text() == golden
+    r = _cli("-t", "dist-matrix-calculator", "--features", *vfiles, "-w", tmp_path / "w")
+    (out,) = r.stdout.split()
+    assert re.fullmatch(r".*/w/dist_matrix_\d{4}\.\d\d\.\d\d_\d\d\.\d\d\.\d\d_original_order\.txt", out)
+    assert open(out).read() == ("#\tmeta_test_1\tmeta_test_2\tmeta_test_3\nmeta_test_1\t0.0000\t0.5691\t0.2981\n"
+                                "meta_test_2\t0.5691\t0.0000\t0.8448\nmeta_test_3\t0.2981\t0.8448\t0.0000\n")
+    _cli("-t", "dist-matrix-calculator", "--features", *vfiles, "--matrix-file", tmp_path / "nn.txt", "-wn")
+    assert (tmp_path / "nn.txt").read_text().splitlines()[0] == "0.0000\t0.5691\t0.2981"
+
+
+def test_renumbering_and_java_number_format(built, tmp_path):
+    """average-linkage order and java.util.Formatter's HALF_UP rounding of the shortest digits, against the restatement"""
+    rng = np.random.default_rng(8)
+    for n in (1, 2, 5, 9):
+        a = rng.random((n, n))
+        mat = (a + a.T) / 2
+        np.fill_diagonal(mat, 0.0)
+        if n >= 5:
+            mat[0, 1] = mat[1, 0] = 0.125            # "%.2f": Java 0.13, C 0.12
+            mat[2, 3] = mat[3, 2] = 0.99995          # carries into the integer part at %.4f
+            mat[0, 4] = mat[4, 0] = 1.5e-7
+            mat[1, 4] = mat[4, 1] = 12345.678
+        names = ["s%d" % i for i in range(n)]
+        src = tmp_path / ("in%d.txt" % n)
+        src.write_text(orc.matrix_txt(mat.tolist(), names, None, "%s"))
+        perm = orc.heatmap_order(mat.tolist())
+        for fmt in ("%s", "%.4f", "%.2f", "%.0f"):
+            out = tmp_path / ("out%d.txt" % n)
+            _cli("-t", "heatmap-maker", "-i", src, "--newMatrix-file", out, "--output-format", fmt)
+            want = orc.matrix_txt(mat.tolist(), names, perm, fmt)
+            assert out.read_text() == want, (n, fmt)
+    assert orc.java_format_fixed(0.125, 2) == "0.13" and orc.java_format_fixed(0.99995, 4) == "1.0000"

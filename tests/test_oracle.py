@@ -176,6 +176,11 @@ def test_reference_matrix_golden(built):
     assert orc.java_double_to_string(matrix[0][1]) == "0.5691162409506898"
     assert orc.java_double_to_string(matrix[0][2]) == "0.2981399448537721"
     assert orc.java_double_to_string(matrix[1][2]) == "0.8448331091037222"
+    # and the file itself, byte for byte: heatmap-maker's average-linkage renumbering puts meta_test_3 next to meta_test_1
+    perm = orc.heatmap_order(matrix)
+    assert perm == [0, 2, 1]
+    assert orc.matrix_txt(matrix, names, perm, "%s") == open(os.path.join(GOLDEN, "meta_test_matrix.txt")).read()
+    assert orc.matrix_txt(matrix, names, None, "%.4f").splitlines()[1] == "meta_test_1\t0.0000\t0.5691\t0.2981"   # README.md:97
     # intermediates, for the record (they are what the GPU pipeline test compares stage by stage)
     assert [len(mid["sequences"][n]) for n in names] == [15, 29, 25]
     assert len(mid["sequence_kmers"]) == 17061
