@@ -65,6 +65,9 @@ public final class MfkcNative {
     static final MethodHandle KSET_HISTOGRAM = h("mfkc_kset_histogram", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle KSET_SEQ_BEGIN = h("mfkc_kset_sequences_begin", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle KSET_SEQ_FETCH = h("mfkc_kset_sequences_fetch", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    // ComponentsBuilder.splitStrategy(hm, k, b1, b2, ...) (src/algo/ComponentsBuilder.java:24-31) on a device map
+    static final MethodHandle KSET_COMP_BEGIN = h("mfkc_kset_components_begin", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS));
+    static final MethodHandle KSET_COMP_FETCH = h("mfkc_kset_components_fetch", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
 
     // ---- multi-GPU: one context per GPU (cfg.n_shards / shard_id); a single JVM attaches the contexts to each other directly
     static final MethodHandle P2P_STAGE_CREATE = h("mfkc_p2p_stage_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG));

@@ -6,6 +6,8 @@
 //   mfkc_cli -t kmer-counter       -k K [-b B] -i reads...            (one sample: all files into one table)
 //   mfkc_cli -t features-calculator -k K -cm components.bin [-ka kmers.bin...] [-i reads...]
 //                                   [--selected kmers.bin...] [--threshold T] [-w workDir]
+//   mfkc_cli -t seq-builder | seq-builder-many | component-cutter | dist-matrix-calculator | heatmap-maker | matrix-builder ...
+//   mfkc_cli -t kmers-filter | unique-kmers-multi | kmers-samples-counter ...        
 //   extras (optional, old command lines keep working): --gpu N, --gpu-variant hash|sort|direct,
 //   --long-kmers (accept 32 <= k <= 63: 128-bit keys, <name>.kmers128.bin with 18-byte records)
 //
