@@ -6,7 +6,14 @@
 //       [itmo]/io/formats/Illumina.java:7-12, Sanger.java:7-12, [itmo]/dna/DnaQ.java:140-150
 //   * .stat.txt writer ([itmo]/statistics/QuickQuantitativeStatistics.java:38-72)
 //   * the synthetic read generator's host half (synth.h)
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -22,6 +29,7 @@
 #include <vector>
 
 #include "../../include/mfkc.h"
+#include "fast_inflate.h"
 #include "synth.h"
 
 namespace {
@@ -68,9 +76,50 @@ std::string library_name(const std::string &path, Format f) {
     }
 }
 
+// first '\n' or '\r' in [q, end), or end
+static inline const char *find_eol(const char *q, const char *end) {
+#if defined(__x86_64__)
+    const __m128i nl = _mm_set1_epi8('\n'), cr = _mm_set1_epi8('\r');
+    while (q + 16 <= end) {
+        const __m128i v = _mm_loadu_si128((const __m128i *)q);
+        const unsigned m = (unsigned)_mm_movemask_epi8(_mm_or_si128(_mm_cmpeq_epi8(v, nl), _mm_cmpeq_epi8(v, cr)));
+        if (m) return q + __builtin_ctz(m);
+        q += 16;
+    }
+#endif
+    while (q < end && *q != '\n' && *q != '\r') q++;
+    return q;
+}
+
+// FASTQ record fast path: true when every base is one of AaCcGgTt and every quality char q has lo < q <= 126 and
+// q != lo + 64, i.e. the per-character rules of RecordParser::fastq_record raise no error and keep the read (phred != 0
+// everywhere, no N).  Anything else -- N, '.', phred 0, bad characters -- is left to the exact scalar loop.
+static inline bool fastq_record_is_clean(const char *d, const char *q, size_t n, int lo) {
+    size_t i = 0;
+#if defined(__x86_64__)
+    const __m128i up = _mm_set1_epi8((char)0xDF), A = _mm_set1_epi8('A'), Cc = _mm_set1_epi8('C'), G = _mm_set1_epi8('G'), T = _mm_set1_epi8('T');
+    const __m128i vlo = _mm_set1_epi8((char)lo), v127 = _mm_set1_epi8(127), vz = _mm_set1_epi8((char)(lo + 64));
+    for (; i + 16 <= n; i += 16) {
+        const __m128i x = _mm_and_si128(_mm_loadu_si128((const __m128i *)(d + i)), up);
+        const __m128i okb = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(x, A), _mm_cmpeq_epi8(x, Cc)), _mm_or_si128(_mm_cmpeq_epi8(x, G), _mm_cmpeq_epi8(x, T)));
+        const __m128i v = _mm_loadu_si128((const __m128i *)(q + i));
+        // signed compares: bytes >= 128 are negative and fail v > lo
+        const __m128i okq = _mm_andnot_si128(_mm_cmpeq_epi8(v, vz), _mm_and_si128(_mm_cmpgt_epi8(v, vlo), _mm_cmpgt_epi8(v127, v)));
+        if (_mm_movemask_epi8(_mm_and_si128(okb, okq)) != 0xFFFF) return false;
+    }
+#endif
+    for (; i < n; i++) {
+        const unsigned char b = (unsigned char)d[i] & 0xDFu, c = (unsigned char)q[i];
+        if (!(b == 'A' || b == 'C' || b == 'G' || b == 'T')) return false;
+        if (!(c > lo && c <= 126 && c != lo + 64)) return false;
+    }
+    return true;
+}
+
 // BufferedReader.readLine over a (possibly gzip) stream: terminators \n, \r\n, \r.
 class LineReader {
 public:
+    static constexpr bool kStableLines = false;      // a line is valid until the next call only
     bool open(const std::string &path) {
         close();
         f_ = gzopen(path.c_str(), "rb");           // transparent for plain files (GZIPInputStream otherwise)
@@ -101,8 +150,7 @@ public:
             }
             const char *p = buf_.data() + pos_;
             const size_t avail = len_ - pos_;
-            size_t i = 0;
-            while (i < avail && p[i] != '\n' && p[i] != '\r') i++;
+            const size_t i = (size_t)(find_eol(p, p + avail) - p);
             if (i < avail) {
                 const bool cr = p[i] == '\r';
                 if (have_acc) { acc_.append(p, i); line = acc_.data(); len = acc_.size(); }
@@ -147,12 +195,12 @@ const CodeTable kCode;
 // The same line rules over a block of text that is already in memory (a chunk of whole records).
 class MemLineReader {
 public:
+    static constexpr bool kStableLines = true;       // lines point into the block
     MemLineReader(const char *p, size_t n) : p_(p), end_(p + n) {}
     bool failed() const { return false; }
     bool next(const char *&line, size_t &len) {
         if (p_ == end_) return false;
-        const char *q = p_;
-        while (q < end_ && *q != '\n' && *q != '\r') q++;
+        const char *q = find_eol(p_, end_);
         line = p_; len = (size_t)(q - p_);
         if (q == end_) { p_ = end_; return true; }               // last line without a terminator
         p_ = q + 1;
@@ -215,41 +263,51 @@ struct RecordParser {
 
     // One FASTQ record (FastqReader.java:53-82 + FastaReaderFromXQSource.java:62-69).
     // returns 1 = record parsed (kept says whether it survives), 0 = end, <0 error (-100 = illegal quality)
-    int fastq_record(LR &r, int lo, std::string *out, bool &kept) {
+    int fastq_record(LR &r, int lo, std::string *out, bool &kept, std::vector<uint8_t> *append = nullptr) {
         const char *l; size_t n;
         int s = fastq_data_line(r, l, n);
         if (s <= 0) return s;
-        data_.assign(l, n);
+        const char *d = l; const size_t dn = n;
+        if (!LR::kStableLines) { data_.assign(l, n); d = data_.data(); }
         s = fastq_data_line(r, l, n);
         if (s == 0) { err = "Unexpected end of file. File is corrupted/Format mismatch."; return MFKC_E_FORMAT; }
         if (s < 0) return s;
-        if (n != data_.size()) {
+        if (n != dn) {
             err = "Bad DnaQ record: length of chars and quality is not the same. File is corrupted/Format mismatch.";
             return MFKC_E_FORMAT;
         }
         kept = true;
-        for (size_t i = 0; i < n; i++) {
-            const unsigned char ch = (unsigned char)data_[i];
-            if (ch == 'N' || ch == 'n' || ch == '.') { kept = false; continue; }    // appendUnknown: phred 0
-            if (!kCode.ok[ch]) { err = std::string("Incorrect nucleotide char: \"") + (char)ch + "\""; return MFKC_E_FORMAT; }
-            const int q = (unsigned char)l[i];
-            if (q < lo || q > 126) {                                                // Illumina.java:8 / Sanger.java:8
-                err = std::string("Invalid quality code char: \"") + (char)q + "\"";
-                return -100;
+        if (!fastq_record_is_clean(d, l, n, lo))
+            for (size_t i = 0; i < n; i++) {
+                const unsigned char ch = (unsigned char)d[i];
+                if (ch == 'N' || ch == 'n' || ch == '.') { kept = false; continue; }    // appendUnknown: phred 0
+                if (!kCode.ok[ch]) { err = std::string("Incorrect nucleotide char: \"") + (char)ch + "\""; return MFKC_E_FORMAT; }
+                const int q = (unsigned char)l[i];
+                if (q < lo || q > 126) {                                                // Illumina.java:8 / Sanger.java:8
+                    err = std::string("Invalid quality code char: \"") + (char)q + "\"";
+                    return -100;
+                }
+                if (((q - lo) & 63) == 0) kept = false;       // 6-bit phred (DnaQ.java:140-150) == 0 -> read dropped
             }
-            if (((q - lo) & 63) == 0) kept = false;       // 6-bit phred (DnaQ.java:140-150) == 0 -> read dropped
+        if (kept) {
+            if (append) append->insert(append->end(), (const uint8_t *)d, (const uint8_t *)d + dn);
+            else if (out) out->assign(d, dn);
         }
-        if (out && kept) out->swap(data_);
         return 1;
     }
 
     // next kept read into cur; 1 / 0 / <0
-    int next_read(LR &lr, std::string &cur) {
+    // `append`: the kept read goes to the end of that vector instead of `cur` (the chunk workers: no per-read string)
+    int next_read(LR &lr, std::string &cur, std::vector<uint8_t> *append = nullptr) {
         int s;
-        if (fmt == F_FASTA || fmt == F_FASTA_GZ) return fasta_next(lr, cur);
+        if (fmt == F_FASTA || fmt == F_FASTA_GZ) {
+            s = fasta_next(lr, cur);
+            if (s > 0 && append) append->insert(append->end(), cur.begin(), cur.end());
+            return s;
+        }
         for (;;) {
             bool kept = false;
-            s = fastq_record(lr, phred_lo, &cur, kept);
+            s = fastq_record(lr, phred_lo, &cur, kept, append);
             if (s == -100) s = MFKC_E_FORMAT;
             if (s <= 0) break;
             all_reads++;
@@ -274,15 +332,50 @@ private:
 // the serial parser; MFKC_READER_THREADS=1 selects the serial path.
 // ------------------------------------------------------------------------------------------
 struct IngestChunk {
-    std::vector<char> text;
+    std::vector<char> text;                                     // owned text buffer (inflated / read data); its size is a capacity
+    const char *tptr = nullptr; size_t tlen = 0;                // the chunk's text: inside `text`, or a view of the mapped file
     std::vector<uint8_t> bases; std::vector<uint64_t> offs;     // offs[0] = 0
     uint64_t all = 0, skipped = 0;
     int status = 0; std::string err;                            // status < 0: the error follows the reads of this chunk
     bool parsed = false, last = false;
 };
 
+// FASTQ fast path of last_boundary.  A block that starts at a record boundary and holds nothing but non-empty lines ending
+// in '\n' (no '\r' anywhere, no empty line) leaves the state machine below in state (line number mod 4), so the last
+// boundary follows from the NUMBER of lines: one vectorised pass instead of two memchr calls per line.  Returns false when
+// the block is not of that shape (CRLF files, blank lines, ...): the exact machine then decides.
+static bool fastq_boundary_by_line_count(const char *p, size_t n, size_t *cut) {
+    if (!n || p[0] == '\n') return false;
+    size_t lines = 0, i = 0;
+    unsigned prev_nl = 0;                                       // was the byte before position i a '\n'?
+#if defined(__x86_64__)
+    const __m128i nl = _mm_set1_epi8('\n'), cr = _mm_set1_epi8('\r');
+    for (; i + 16 <= n; i += 16) {
+        const __m128i v = _mm_loadu_si128((const __m128i *)(p + i));
+        if (_mm_movemask_epi8(_mm_cmpeq_epi8(v, cr))) return false;
+        const unsigned m = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, nl));
+        if (m & ((m << 1) | prev_nl)) return false;             // "\n\n": an empty line
+        prev_nl = (m >> 15) & 1u;
+        lines += (size_t)__builtin_popcount(m);
+    }
+#endif
+    for (; i < n; i++) {
+        const char c = p[i];
+        if (c == '\r') return false;
+        if (c == '\n') { if (prev_nl) return false; prev_nl = 1; lines++; } else prev_nl = 0;
+    }
+    if (lines < 4) { *cut = 0; return true; }
+    // the cut is just behind the newline that ends line 4 * (lines / 4): step back over the surplus newlines
+    const char *q = (const char *)memrchr(p, '\n', n);
+    for (size_t r = lines & 3; r; r--) q = (const char *)memrchr(p, '\n', (size_t)(q - p));
+    *cut = (size_t)(q - p) + 1;
+    return true;
+}
+
 // offset of the last record boundary in [p, p+n) (0 = none); `eof`: the text ends here
 static size_t last_boundary(const char *p, size_t n, bool fastq, bool eof) {
+    size_t fast_cut = 0;
+    if (fastq && !eof && fastq_boundary_by_line_count(p, n, &fast_cut)) return fast_cut;
     size_t pos = 0, cut = 0;
     int state = 0;                                              // FASTQ: 0 header, 1 data, 2 '+' line, 3 quality
     while (pos < n) {
@@ -361,16 +454,94 @@ struct mfkc_reader {
     }
 
     // ---- parallel path
+    // Chunk objects are recycled (their vectors keep their capacity): a fresh 4-MB vector per chunk costs a page fault
+    // per page and an munmap when the worker drops it, which was a third of the producer's time.
+    std::vector<std::shared_ptr<IngestChunk>> pool;
+    std::shared_ptr<IngestChunk> fresh_chunk() {
+        std::shared_ptr<IngestChunk> ch;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!pool.empty()) { ch = pool.back(); pool.pop_back(); }
+        }
+        if (!ch) ch = std::make_shared<IngestChunk>();
+        ch->tptr = nullptr; ch->tlen = 0; ch->bases.clear(); ch->offs.clear();
+        ch->all = ch->skipped = 0; ch->status = 0; ch->err.clear(); ch->parsed = ch->last = false;
+        return ch;
+    }
+    void recycle(std::shared_ptr<IngestChunk> &ch) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (pool.size() < kMaxQueued + 8) pool.push_back(std::move(ch));
+        ch.reset();
+    }
+    // hands a finished chunk to the workers; false = the reader is being closed
+    bool publish(const std::shared_ptr<IngestChunk> &ch) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_space.wait(lk, [&] { return stop || ordered.size() < kMaxQueued; });
+        if (stop) return false;
+        ordered.push_back(ch); todo.push_back(ch);
+        cv_work.notify_one();
+        return true;
+    }
+
+    const uint8_t *map = nullptr; size_t map_len = 0;           // the input file (unmapped when the reader closes)
+
     void producer() {
         const bool gz = fmt == F_FASTA_GZ || fmt == F_FASTQ_GZ;
-        gzFile f = gz ? gzopen(path.c_str(), "rb") : nullptr;       // plain files: no zlib layer in between
+        // The file is mapped.  Plain text: the chunks are views of the mapping (no read, no copy; the producer only looks
+        // for record boundaries).  .gz: decoded by FastInflate (fast_inflate.h) into pooled buffers.  MFKC_INFLATE=zlib, a
+        // file that cannot be mapped, or a .gz name without the gzip magic (gzopen reads those "transparently") go
+        // through zlib's gzread / fread as before.
+        std::unique_ptr<mfkc::FastInflate> fi;
+        const char *inflate_env = getenv("MFKC_INFLATE");
+        const bool old_path = inflate_env && !strcmp(inflate_env, "zlib");
+        if (!old_path) {
+            const int fd = open(path.c_str(), O_RDONLY);
+            struct stat sb;
+            if (fd >= 0 && fstat(fd, &sb) == 0 && sb.st_size > 0) {
+                void *m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (m != MAP_FAILED) {
+                    if (!gz || mfkc::FastInflate::looks_like_gzip((const uint8_t *)m, (size_t)sb.st_size)) {
+                        map = (const uint8_t *)m; map_len = (size_t)sb.st_size;
+                        madvise(m, map_len, MADV_SEQUENTIAL);
+                    } else munmap(m, (size_t)sb.st_size);
+                }
+            }
+            if (fd >= 0) close(fd);
+        }
+        if (map && !gz) {                                       // plain text, zero copy
+            const char *base = (const char *)map;
+            size_t pos = 0;
+            bool more = true;
+            while (more) {
+                size_t want = kChunkText, cut = 0;
+                bool eof = false;
+                for (;;) {                                      // widen until the block holds at least one whole record
+                    const size_t have = std::min(want, map_len - pos);
+                    eof = pos + have == map_len;
+                    cut = eof ? have : last_boundary(base + pos, have, is_fastq(), false);
+                    if (cut || eof) break;
+                    want += kChunkText;
+                }
+                auto ch = fresh_chunk();
+                ch->tptr = base + pos; ch->tlen = cut; ch->last = eof;
+                pos += cut;
+                more = !eof;
+                if (!publish(ch)) break;
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            producer_done = true;
+            cv_work.notify_all(); cv_done.notify_all();
+            return;
+        }
+        if (map && gz) { fi.reset(new mfkc::FastInflate()); fi->reset(map, map_len); }
+        gzFile f = gz && !fi ? gzopen(path.c_str(), "rb") : nullptr;       // plain files: no zlib layer in between
         FILE *pf = gz ? nullptr : fopen(path.c_str(), "rb");
         std::vector<char> carry;
-        bool eof = !f && !pf, io_error = eof;
+        bool eof = !f && !pf && !fi, io_error = eof;
         if (f) gzbuffer(f, 1 << 20);
         while (!eof) {
-            auto ch = std::make_shared<IngestChunk>();
-            ch->text.resize(carry.size() + kChunkText);
+            auto ch = fresh_chunk();
+            if (ch->text.size() < carry.size() + kChunkText) ch->text.resize(carry.size() + kChunkText);
             if (!carry.empty()) memcpy(ch->text.data(), carry.data(), carry.size());
             size_t have = carry.size();
             carry.clear();
@@ -378,7 +549,8 @@ struct mfkc_reader {
             for (;;) {                                          // read until the block holds at least one whole record
                 if (ch->text.size() < have + kChunkText) ch->text.resize(have + kChunkText);
                 int r;
-                if (gz) r = gzread(f, ch->text.data() + have, (unsigned)kChunkText);
+                if (fi) r = (int)fi->read(ch->text.data() + have, kChunkText);
+                else if (gz) r = gzread(f, ch->text.data() + have, (unsigned)kChunkText);
                 else { r = (int)fread(ch->text.data() + have, 1, kChunkText, pf); if (r == 0 && ferror(pf)) r = -1; }
                 if (r < 0) { io_error = true; eof = true; }
                 else if (r == 0) eof = true;
@@ -387,14 +559,10 @@ struct mfkc_reader {
                 if (cut || eof) break;
             }
             if (!eof) carry.assign(ch->text.data() + cut, ch->text.data() + have);
-            ch->text.resize(cut);
+            ch->tptr = ch->text.data(); ch->tlen = cut;
             ch->last = eof;
-            if (io_error) { ch->status = MFKC_E_IO; ch->err = "read error (corrupt gzip stream?)"; }
-            std::unique_lock<std::mutex> lk(mu);
-            cv_space.wait(lk, [&] { return stop || ordered.size() < kMaxQueued; });
-            if (stop) break;
-            ordered.push_back(ch); todo.push_back(ch);
-            cv_work.notify_one();
+            if (io_error) { ch->status = MFKC_E_IO; ch->err = fi && fi->failed() ? "read error (corrupt gzip stream: " + fi->error() + ")" : "read error (corrupt gzip stream?)"; }
+            if (!publish(ch)) break;
         }
         if (f) gzclose(f);
         if (pf) fclose(pf);
@@ -413,18 +581,14 @@ struct mfkc_reader {
                 ch = todo.front(); todo.pop_front();
             }
             RecordParser<MemLineReader> p; p.fmt = fmt; p.phred_lo = phred_lo;
-            MemLineReader mlr(ch->text.data(), ch->text.size());
-            ch->bases.reserve(ch->text.size() / 2 + 64);
+            MemLineReader mlr(ch->tptr, ch->tlen);
+            ch->bases.reserve(ch->tlen / 2 + 64);
             ch->offs.push_back(0);
             std::string rd;
             int s;
-            while ((s = p.next_read(mlr, rd)) > 0) {
-                ch->bases.insert(ch->bases.end(), rd.begin(), rd.end());
-                ch->offs.push_back(ch->bases.size());
-            }
+            while ((s = p.next_read(mlr, rd, &ch->bases)) > 0) ch->offs.push_back(ch->bases.size());
             if (s < 0 && ch->status == 0) { ch->status = s; ch->err = p.err; }
             ch->all = p.all_reads; ch->skipped = p.skipped;
-            std::vector<char>().swap(ch->text);
             std::lock_guard<std::mutex> lk(mu);
             ch->parsed = true;
             cv_done.notify_all();
@@ -441,7 +605,10 @@ struct mfkc_reader {
         for (auto &t : threads) t.join();
         threads.clear();
     }
-    ~mfkc_reader() { if (!threads.empty()) stop_threads(); }
+    ~mfkc_reader() {
+        if (!threads.empty()) stop_threads();
+        if (map) munmap((void *)map, map_len);
+    }
 
     // next parsed chunk in file order into cur_chunk; 1 / 0 (end)
     int next_chunk() {
@@ -522,7 +689,7 @@ extern "C" int mfkc_reader_next(mfkc_reader *r, uint8_t *bases, size_t cap_bases
                 return c.status;
             }
             if (c.last) { r->done = true; }
-            r->cur_chunk.reset();
+            r->recycle(r->cur_chunk);
         }
         *n_reads = n;
         return MFKC_OK;

@@ -322,3 +322,159 @@ def test_renumbering_and_java_number_format(built, tmp_path):
             want = orc.matrix_txt(mat.tolist(), names, perm, fmt)
             assert out.read_text() == want, (n, fmt)
     assert orc.java_format_fixed(0.125, 2) == "0.13" and orc.java_format_fixed(0.99995, 4) == "1.0000"
+
+
+# ---------------------------------------------------------------- gzip decoder of the host ingest path (fast_inflate.h)
+def _fast_inflate(data: bytes, piece: int = 1 << 20, cap: int = 1 << 26):
+    import ctypes as C
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libinflate_harness.so"))
+    lib.fi_inflate.restype = C.c_long
+    lib.fi_inflate.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64)]
+    out = np.zeros(cap, dtype=np.uint8)
+    err = C.create_string_buffer(256)
+    members = C.c_uint64()
+    n = lib.fi_inflate(data, len(data), out.ctypes.data_as(C.c_void_p), cap, piece, err, 256, C.byref(members))
+    if n < 0:
+        return None, err.value.decode(), members.value
+    return out[:n].tobytes(), "", members.value
+
+
+def _zlib_gunzip(data: bytes):
+    """concatenated members like gzread; None when zlib rejects the stream"""
+    import zlib
+    out, pos = b"", 0
+    while pos < len(data):
+        if data[pos:pos + 2] != b"\x1f\x8b":
+            return out if pos else None                   # trailing garbage is ignored
+        d = zlib.decompressobj(31)
+        try:
+            out += d.decompress(data[pos:])
+        except zlib.error:
+            return None
+        if not d.eof:
+            return None
+        pos = len(data) - len(d.unused_data)
+    return out
+
+
+def test_fast_inflate_matches_zlib(built):
+    """every block type, code shape and member layout zlib can produce, read in pieces of several sizes"""
+    import zlib
+    rng = np.random.default_rng(21)
+
+    def gz(raw, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, wbits=31, memlevel=8):
+        c = zlib.compressobj(level, zlib.DEFLATED, wbits, memlevel, strategy)
+        return c.compress(raw) + c.flush()
+
+    texts = {
+        "empty": b"", "one": b"A", "dna": bytes(rng.choice(list(b"ACGT"), 300000).astype(np.uint8)),
+        "random": bytes(rng.integers(0, 256, 200000, dtype=np.uint8)), "zeros": bytes(100000),
+        "fastq": b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rng.choice(list(b"ACGTN"), 100, p=[.249, .249, .249, .249, .004]).astype(np.uint8)),
+                                                  bytes(rng.choice(list(b"#5?FI"), 100).astype(np.uint8))) for i in range(3000)),
+        "period3": b"ACG" * 50000, "period5": b"ACGTT" * 30000,
+    }
+    n_cases = 0
+    for name, raw in texts.items():
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                comp = gz(raw, level, strategy, memlevel=1 if level == 1 else 8)     # memLevel 1: many small blocks
+                for piece in (1 << 20, 4099, 1):
+                    if piece == 1 and len(raw) > 1000:
+                        continue
+                    got, err, members = _fast_inflate(comp, piece)
+                    assert got == raw, (name, level, strategy, piece, err)
+                    assert members == 1
+                    n_cases += 1
+    # concatenated members (bgzip / pigz -i / cat a.gz b.gz), an empty member in between, trailing garbage
+    multi = gz(texts["dna"]) + gz(b"") + gz(texts["fastq"], 1) + gz(texts["zeros"], 9)
+    got, err, members = _fast_inflate(multi, 65536)
+    assert got == texts["dna"] + texts["fastq"] + texts["zeros"] and members == 4
+    assert _fast_inflate(multi + b"\x00garbage", 65536)[0] == got
+    # header fields: FEXTRA + FNAME + FCOMMENT + FHCRC
+    body = gz(texts["fastq"])[10:]
+    hdr = b"\x1f\x8b\x08\x1e\0\0\0\0\0\x03" + b"\x06\x00BC\x02\x00\x12\x34" + b"name.fq\0" + b"a comment\0" + b"\xab\xcd"
+    assert _fast_inflate(hdr + body)[0] == texts["fastq"]
+    # a member must not reach into the previous member's text
+    assert n_cases > 100
+
+
+def test_fast_inflate_rejects_what_zlib_rejects(built):
+    """truncated and bit-flipped streams: an error (with zlib's wording where it has one), never silent garbage"""
+    import zlib
+    rng = np.random.default_rng(22)
+    raw = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rng.choice(list(b"ACGT"), 80).astype(np.uint8)), b"I" * 80) for i in range(800))
+    comp = zlib.compressobj(6, zlib.DEFLATED, 31)
+    comp = comp.compress(raw) + comp.flush()
+    assert _fast_inflate(comp)[0] == raw
+    assert _fast_inflate(b"not gzip at all")[1] == "not a gzip file"
+    assert _fast_inflate(comp[:-4] + b"\0\0\0\0")[1] == "incorrect length check"
+    assert _fast_inflate(comp[:-8] + b"\0\0\0\0" + comp[-4:])[1] == "incorrect data check"
+    agree = 0
+    for t in range(400):
+        bad = bytearray(comp)
+        if t % 4 == 0:
+            bad = bad[:int(rng.integers(0, len(bad)))]
+        else:
+            bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        want = _zlib_gunzip(bytes(bad))
+        got, err, _ = _fast_inflate(bytes(bad))
+        if want is None:
+            assert got is None and err, t
+        else:
+            assert got == want, t                        # a flip in MTIME / OS / a name: both accept
+        agree += 1
+    assert agree == 400
+
+
+def test_crc32_clmul_matches_zlib(built):
+    import ctypes as C
+    import zlib
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libinflate_harness.so"))
+    lib.fi_crc32.restype = C.c_uint32
+    lib.fi_crc32.argtypes = [C.c_uint32, C.c_char_p, C.c_size_t]
+    rng = np.random.default_rng(23)
+    for n in list(range(0, 200)) + [255, 256, 257, 1000, 4096, 65535, 1 << 20, (1 << 20) + 17]:
+        data = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        start = int(rng.integers(0, 1 << 32)) if n % 2 else 0
+        assert lib.fi_crc32(start, data, n) == zlib.crc32(data, start), n
+
+
+def test_gz_reader_fast_and_zlib_paths_agree(built, tmp_path, monkeypatch):
+    """the reader over .gz files: FastInflate (default) and MFKC_INFLATE=zlib hand out the same reads; a corrupt file is an
+    error in both; a '.gz' name on plain text is read transparently, like gzopen does"""
+    rng = np.random.default_rng(24)
+    recs = []
+    for i in range(5000):
+        n = int(rng.integers(30, 200))
+        seq = bytes(rng.choice(list(b"ACGTN"), n, p=[.2495, .2495, .2495, .2495, .002]).astype(np.uint8))
+        recs.append(b"@r%d\n%s\n+\n%s\n" % (i, seq, bytes(rng.choice(list(b"#5?FI"), n).astype(np.uint8))))
+    text = b"".join(recs)
+    one = tmp_path / "one.fastq.gz"
+    with gzip.open(one, "wb") as f:
+        f.write(text)
+    multi = tmp_path / "multi.fastq.gz"
+    with open(multi, "wb") as f:
+        for part in (text[:len(text) // 3], b"", text[len(text) // 3:]):
+            f.write(gzip.compress(part, 1))
+    plain_named_gz = tmp_path / "plain.fastq.gz"
+    plain_named_gz.write_bytes(text)
+    want = orc.parse_reads(str(one))
+    monkeypatch.setenv("MFKC_READER_CHUNK", "70000")
+    for path in (one, multi, plain_named_gz):
+        for mode in ("", "zlib"):
+            if mode:
+                monkeypatch.setenv("MFKC_INFLATE", mode)
+            else:
+                monkeypatch.delenv("MFKC_INFLATE", raising=False)
+            assert m.read_file_reads(str(path)) == want, (path, mode)
+    bad = bytearray(one.read_bytes())
+    bad[len(bad) // 2] ^= 0x10
+    corrupt = tmp_path / "corrupt.fastq.gz"
+    corrupt.write_bytes(bytes(bad))
+    for mode in ("", "zlib"):
+        if mode:
+            monkeypatch.setenv("MFKC_INFLATE", mode)
+        else:
+            monkeypatch.delenv("MFKC_INFLATE", raising=False)
+        with pytest.raises(m.MfkcError):
+            m.read_file_reads(str(corrupt))
