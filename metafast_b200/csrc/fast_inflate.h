@@ -120,7 +120,7 @@ public:
         return (long)done;
     }
 
-private:
+protected:
     static constexpr size_t kWindow = 32768, kBatch = 1u << 20, kSlack = 512;
     static constexpr int LIT_BITS = 11, DIST_BITS = 8;
     // table entry: value << 16 | kind << 13 | extra_bits << 8 | code bits to consume.  Bit 15 = a literal entry; K_LIT2 =

@@ -357,6 +357,7 @@ def _zlib_gunzip(data: bytes):
     return out
 
 
+@pytest.mark.timeout(600)
 def test_fast_inflate_matches_zlib(built):
     """every block type, code shape and member layout zlib can produce, read in pieces of several sizes"""
     import zlib
@@ -398,6 +399,7 @@ def test_fast_inflate_matches_zlib(built):
     assert n_cases > 100
 
 
+@pytest.mark.timeout(600)
 def test_fast_inflate_rejects_what_zlib_rejects(built):
     """truncated and bit-flipped streams: an error (with zlib's wording where it has one), never silent garbage"""
     import zlib
@@ -439,6 +441,7 @@ def test_crc32_clmul_matches_zlib(built):
         assert lib.fi_crc32(start, data, n) == zlib.crc32(data, start), n
 
 
+@pytest.mark.timeout(600)
 def test_gz_reader_fast_and_zlib_paths_agree(built, tmp_path, monkeypatch):
     """the reader over .gz files: FastInflate (default) and MFKC_INFLATE=zlib hand out the same reads; a corrupt file is an
     error in both; a '.gz' name on plain text is read transparently, like gzopen does"""
@@ -478,3 +481,126 @@ def test_gz_reader_fast_and_zlib_paths_agree(built, tmp_path, monkeypatch):
             monkeypatch.delenv("MFKC_INFLATE", raising=False)
         with pytest.raises(m.MfkcError):
             m.read_file_reads(str(corrupt))
+
+
+def _parallel_inflate(data: bytes, threads: int, segment: int, piece: int = 1 << 20, cap: int = 1 << 27):
+    import ctypes as C
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libinflate_harness.so"))
+    lib.pi_inflate.restype = C.c_long
+    lib.pi_inflate.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t]
+    out = np.zeros(cap, dtype=np.uint8)
+    err = C.create_string_buffer(256)
+    n = lib.pi_inflate(data, len(data), out.ctypes.data_as(C.c_void_p), cap, piece, threads, segment, err, 256)
+    if n == -3:
+        return "declined", "", 0
+    if n < 0:
+        return None, err.value.decode(), 0
+    return out[:n].tobytes(), "", n
+
+
+def _fastq_text(rng, n_reads, read_len=100):
+    """FASTQ with random bases, varied qualities and repeated reads (long-range copies, so that markers of the unknown
+    window travel far)"""
+    bases = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), (n_reads, read_len))
+    dup = rng.integers(0, n_reads, n_reads // 5)
+    bases[dup] = bases[(dup * 7 + 1) % n_reads]
+    quals = rng.choice(np.frombuffer(b"#5?FIII", dtype=np.uint8), (n_reads, read_len))
+    out = bytearray()
+    for i in range(n_reads):
+        out += b"@read_%d\n" % i + bases[i].tobytes() + b"\n+\n" + quals[i].tobytes() + b"\n"
+    return bytes(out)
+
+
+@pytest.mark.timeout(600)
+def test_parallel_inflate_is_exact(built):
+    """one gzip stream decoded by several threads (csrc/parallel_inflate.h): identical to zlib for every thread count and
+    segment size -- tiny segments put dozens of speculative starts, meetings and window hand-overs into a few megabytes"""
+    import zlib
+    rng = np.random.default_rng(31)
+    text = _fastq_text(rng, 60000)                                            # ~13 MB
+
+    def gz(raw, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, memlevel=8):
+        c = zlib.compressobj(level, zlib.DEFLATED, 31, memlevel, strategy)
+        return c.compress(raw) + c.flush()
+
+    for level, memlevel in ((6, 8), (1, 8), (9, 9), (6, 1)):
+        comp = gz(text, level, memlevel=memlevel)
+        for threads, segment in ((2, 1 << 20), (3, 1 << 18), (8, 1 << 16), (5, 40000), (8, 1 << 14)):
+            got, err, _ = _parallel_inflate(comp, threads, segment, piece=(1 << 20) + 13)
+            assert got == text, (level, memlevel, threads, segment, err)
+    assert _parallel_inflate(gz(text[:100000]), 4, 1 << 20)[0] == "declined"   # too small: the caller uses FastInflate
+    # no dynamic blocks to start from (fixed Huffman codes; stored blocks of random bytes): one run decodes everything
+    assert _parallel_inflate(gz(text[:3000000], 6, zlib.Z_FIXED), 4, 1 << 16)[0] == text[:3000000]
+    noise = bytes(rng.integers(0, 256, 3000000, dtype=np.uint8))
+    assert _parallel_inflate(gz(noise), 4, 1 << 16)[0] == noise
+    # text, then binary, then text again; full flushes in between (empty stored blocks, byte-aligned block starts)
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    mixed = c.compress(text[:4000000]) + c.flush(zlib.Z_FULL_FLUSH) + c.compress(noise[:500000]) + c.flush(zlib.Z_SYNC_FLUSH) + \
+        c.compress(text[4000000:9000000]) + c.flush()
+    assert _parallel_inflate(mixed, 6, 1 << 15)[0] == text[:4000000] + noise[:500000] + text[4000000:9000000]
+    # several members: parallel for the first, FastInflate for the rest; trailing garbage ignored
+    multi = gz(text[:8000000]) + gz(b"") + gz(text[8000000:], 1) + gz(noise[:1000])
+    assert _parallel_inflate(multi, 4, 1 << 17)[0] == text + noise[:1000]
+    assert _parallel_inflate(multi + b"\0\0\0trailing", 4, 1 << 17)[0] == text + noise[:1000]
+
+
+@pytest.mark.timeout(600)
+def test_parallel_inflate_reports_corruption(built):
+    """flipped bits and truncation in a big stream: an error (or, where zlib accepts the stream, zlib's bytes) -- never
+    silently different text.  The CRC-32 of the member is combined from the pieces' CRCs and checked like zlib does."""
+    import zlib
+    rng = np.random.default_rng(32)
+    text = _fastq_text(rng, 20000)
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    comp = c.compress(text) + c.flush()
+    assert _parallel_inflate(comp, 4, 1 << 16)[0] == text
+    assert _parallel_inflate(comp[:-8] + b"\1\2\3\4" + comp[-4:], 4, 1 << 16)[1] == "incorrect data check"
+    assert _parallel_inflate(comp[:-4] + b"\1\2\3\4", 4, 1 << 16)[1] == "incorrect length check"
+    for t in range(60):
+        bad = bytearray(comp)
+        if t % 5 == 0:
+            bad = bad[:int(rng.integers(len(bad) // 2, len(bad)))]
+        else:
+            bad[int(rng.integers(20, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        want = _zlib_gunzip(bytes(bad))
+        got, err, _ = _parallel_inflate(bytes(bad), 4, 1 << 16)
+        if want is None:
+            assert got is None and err, (t, err)
+        else:
+            assert got == want, t
+
+
+@pytest.mark.timeout(600)
+def test_gz_reader_parallel_inflate_path(built, tmp_path, monkeypatch):
+    """a .gz big enough for the multi-threaded decoder (>= 4 MB compressed): the reader hands out exactly the reads of the
+    zlib path and of the serial decoder, for several decoder thread counts"""
+    rng = np.random.default_rng(33)
+    text = _fastq_text(rng, 110000)
+    path = tmp_path / "big.fastq.gz"
+    with gzip.open(path, "wb", compresslevel=6) as f:
+        f.write(text)
+    assert os.path.getsize(path) > (4 << 20)
+
+    def digest():
+        import hashlib
+        h = hashlib.sha256()
+        n = 0
+        for bases, offs in m.read_file(str(path), batch_reads=1 << 16, batch_bases=1 << 24):
+            h.update(bases.tobytes()); h.update(np.diff(offs).tobytes()); n += len(offs) - 1
+        return n, h.hexdigest()
+
+    monkeypatch.setenv("MFKC_INFLATE", "zlib")
+    want = digest()
+    assert want[0] == 110000
+    monkeypatch.setenv("MFKC_INFLATE", "serial")
+    assert digest() == want
+    monkeypatch.delenv("MFKC_INFLATE")
+    for threads in ("2", "5", "8"):
+        monkeypatch.setenv("MFKC_INFLATE_THREADS", threads)
+        assert digest() == want
+    # a flipped bit in the middle of the big file: an error, after the reads in front of it
+    bad = bytearray(path.read_bytes())
+    bad[len(bad) // 2] ^= 4
+    path.write_bytes(bytes(bad))
+    with pytest.raises(m.MfkcError):
+        digest()
