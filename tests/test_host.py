@@ -598,6 +598,19 @@ def test_gz_reader_parallel_inflate_path(built, tmp_path, monkeypatch):
     for threads in ("2", "5", "8"):
         monkeypatch.setenv("MFKC_INFLATE_THREADS", threads)
         assert digest() == want
+    # closing a reader in mid-stream (decoder threads, parse workers and the producer are all busy) must not hang
+    lib = m.load()
+    for batches in (0, 1, 3):
+        h = C.c_void_p()
+        err = C.create_string_buffer(256)
+        assert lib.mfkc_reader_open(str(path).encode(), C.byref(h), err, 256) == 0
+        bases = np.zeros(1 << 22, dtype=np.uint8)
+        offs = np.zeros((1 << 14) + 1, dtype=np.uint64)
+        n = C.c_uint32()
+        for _ in range(batches):
+            assert lib.mfkc_reader_next(h, bases.ctypes.data_as(C.c_void_p), bases.size, offs.ctypes.data_as(C.c_void_p), 1 << 14, C.byref(n)) == 0
+            assert n.value == 1 << 14
+        lib.mfkc_reader_close(h)
     # a flipped bit in the middle of the big file: an error, after the reads in front of it
     bad = bytearray(path.read_bytes())
     bad[len(bad) // 2] ^= 4
