@@ -339,6 +339,7 @@ private:
             if (!r.pieces.empty()) {
                 cur_piece_ = r.pieces.front(); r.pieces.pop_front();
                 piece_pos_ = 0;
+                cv_.notify_all();                                  // a long run may be waiting for room (resolve_available)
                 if (cur_piece_->text.empty()) { cur_piece_.reset(); continue; }
                 return true;
             }
@@ -500,6 +501,7 @@ private:
         std::shared_ptr<Piece> piece = new_piece(nullptr, run.seg == 0);
         uint16_t *out = piece->sym.data() + WIN, *limit = out + kPieceSyms;
         std::vector<std::shared_ptr<Piece>> mine;                  // this run's pieces, for the resolve step
+        Resolver rs;
         auto close_piece = [&](bool last) {
             piece->n_sym = (size_t)(out - (piece->sym.data() + WIN));
             { std::lock_guard<std::mutex> lk(mu_); run.pieces.push_back(piece); if (last) run.decoded = true; }
@@ -525,6 +527,7 @@ private:
                 auto nxt = new_piece(nullptr, false);
                 memcpy(nxt->sym.data(), out - WIN, WIN * 2);
                 piece = nxt;
+                resolve_available(rs, run, mine);                 // (gives the closed piece's symbols back: copy the prefix first)
                 out = piece->sym.data() + WIN; limit = out + kPieceSyms;
             }
             if (!dec.decode_some(out, limit)) {
@@ -547,69 +550,93 @@ private:
             }
         }
         cv_.notify_all();
-        resolve_run(run, mine);
+        resolve_run(rs, run, mine);
     }
 
-    // replaces the markers of the run's pieces once the window in front of the run is known; publishes the next window
-    void resolve_run(Run &run, std::vector<std::shared_ptr<Piece>> &mine) {
+    // symbol -> byte once the window in front of a run is known: 0..255 themselves, 256 + k = byte k of that window.
+    // NOTHING, and every marker in the member's first run (it has no window), is a copy from in front of the member's
+    // first byte: an error.
+    struct Resolver {
+        std::vector<uint8_t> lut;
+        uint32_t bias = 0;                                         // v + bias >= 0x10000  <=>  v is not resolvable
+        std::vector<uint8_t> tail;                                 // running "last WIN bytes of the run's text so far"
+        bool ready = false;
+        size_t done = 0;                                           // pieces of the run resolved so far
+    };
+    void prepare(Resolver &rs, const Run &run) {                   // run.window_ready holds
+        rs.lut.assign(65536, 0);
+        for (int v = 0; v < 256; v++) rs.lut[(size_t)v] = (uint8_t)v;
+        const bool have_window = !run.window.empty();
+        if (have_window) memcpy(rs.lut.data() + 256, run.window.data(), WIN);
+        rs.bias = have_window ? 0x10000u - (256u + (uint32_t)WIN) : 0x10000u - 256u;
+        rs.tail = run.window;
+        rs.ready = true;
+    }
+    void resolve_piece(Resolver &rs, Run &run, Piece &p) {
+        take_buffer(p.text, p.n_sym);
+        const uint16_t *s = p.sym.data() + WIN;
+        uint8_t *t = p.text.data();
+        const uint8_t *lut = rs.lut.data();
+        const uint32_t bias = rs.bias;
+        uint32_t acc = 0;
+        size_t j = 0;
+        for (; j + 4 <= p.n_sym; j += 4) {
+            const uint32_t a = s[j], b = s[j + 1], c = s[j + 2], d = s[j + 3];
+            t[j] = lut[a]; t[j + 1] = lut[b]; t[j + 2] = lut[c]; t[j + 3] = lut[d];
+            acc |= (a + bias) | (b + bias) | (c + bias) | (d + bias);
+        }
+        for (; j < p.n_sym; j++) { t[j] = lut[s[j]]; acc |= s[j] + bias; }
+        const bool bad = (acc & 0x10000u) != 0;
+        give_buffer(p.sym);
+        p.crc = crc32_update(0, p.text.data(), p.text.size());
+        if (p.text.size() >= WIN) rs.tail.assign(p.text.end() - WIN, p.text.end());
+        else { rs.tail.insert(rs.tail.end(), p.text.begin(), p.text.end()); if (rs.tail.size() > WIN) rs.tail.erase(rs.tail.begin(), rs.tail.end() - WIN); }
+        std::lock_guard<std::mutex> lk(mu_);
+        if (bad && run.err.empty()) { run.err = "invalid distance too far back"; p.text.clear(); }
+        p.resolved = true;
+        cv_.notify_all();
+    }
+    // during the decode: resolve what can be resolved already (a long run must not pile up 16-bit pieces), and do not run
+    // away from a slow consumer
+    void resolve_available(Resolver &rs, Run &run, std::vector<std::shared_ptr<Piece>> &mine) {
+        if (!rs.ready) {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (!run.window_ready) return;
+        }
+        if (!rs.ready) prepare(rs, run);
+        for (; rs.done < mine.size(); rs.done++) resolve_piece(rs, run, *mine[rs.done]);
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || run.discarded || run.pieces.size() < 8; });
+    }
+
+    // after the decode: the rest of the pieces, once the window in front of the run is known; publishes the next window
+    void resolve_run(Resolver &rs, Run &run, std::vector<std::shared_ptr<Piece>> &mine) {
         {
             std::unique_lock<std::mutex> lk(mu_);
             cv_.wait(lk, [&] { return stop_ || run.discarded || run.window_ready; });
             if (stop_ || run.discarded) return;
         }
-        // symbol -> byte: 0..255 themselves, 256 + k = byte k of the window in front of the run; NOTHING (and every marker of
-        // the member's first run, which has no window) = a copy from in front of the member's start: an error
-        std::vector<uint8_t> lut(65536, 0);
-        for (int v = 0; v < 256; v++) lut[(size_t)v] = (uint8_t)v;
-        const bool have_window = !run.window.empty();
-        if (have_window) memcpy(lut.data() + 256, run.window.data(), WIN);
+        if (!rs.ready) prepare(rs, run);
         // The next run is waiting for its window = my last WIN bytes: resolve those first and hand them over, so that the
         // runs wait for 32 KiB of their predecessor, not for all of it
         bool next_served = false;
-        if (run.next && !mine.empty() && mine.back()->n_sym >= WIN) {
+        if (run.next && !mine.empty() && mine.back()->n_sym >= WIN && rs.done < mine.size()) {
             const Piece &lp = *mine.back();
             const uint16_t *s = lp.sym.data() + WIN + (lp.n_sym - WIN);
             std::vector<uint8_t> w(WIN);
-            for (size_t j = 0; j < WIN; j++) w[j] = lut[s[j]];
+            for (size_t j = 0; j < WIN; j++) w[j] = rs.lut[s[j]];
             std::lock_guard<std::mutex> lk(mu_);
             run.next->window.swap(w);
             run.next->window_ready = true;
             next_served = true;
             cv_.notify_all();
         }
-        std::vector<uint8_t> tail(run.window);                     // running "last WIN bytes of text so far"
-        for (size_t i = 0; i < mine.size(); i++) {
-            Piece &p = *mine[i];
-            take_buffer(p.text, p.n_sym);
-            const uint16_t *s = p.sym.data() + WIN;
-            uint8_t *t = p.text.data();
-            uint32_t worst = 0;                                    // largest symbol seen
-            size_t j = 0;
-            for (; j + 4 <= p.n_sym; j += 4) {
-                const uint32_t a = s[j], b = s[j + 1], c = s[j + 2], d = s[j + 3];
-                t[j] = lut[a]; t[j + 1] = lut[b]; t[j + 2] = lut[c]; t[j + 3] = lut[d];
-                worst |= a | b | c | d;
-            }
-            for (; j < p.n_sym; j++) { t[j] = lut[s[j]]; worst |= s[j]; }
-            bool bad = false;
-            if (worst >= 256 && (!have_window || worst >= 256 + WIN)) {        // rare: look properly
-                for (j = 0; j < p.n_sym; j++) if (s[j] >= 256 && (!have_window || s[j] >= 256 + WIN)) { bad = true; break; }
-            }
-            give_buffer(p.sym);
-            p.crc = crc32_update(0, p.text.data(), p.text.size());
-            // running tail
-            if (p.text.size() >= WIN) tail.assign(p.text.end() - WIN, p.text.end());
-            else { tail.insert(tail.end(), p.text.begin(), p.text.end()); if (tail.size() > WIN) tail.erase(tail.begin(), tail.end() - WIN); }
-            std::lock_guard<std::mutex> lk(mu_);
-            if (bad && run.err.empty()) { run.err = "invalid distance too far back"; p.text.clear(); }
-            p.resolved = true;
-            cv_.notify_all();
-        }
+        for (; rs.done < mine.size(); rs.done++) resolve_piece(rs, run, *mine[rs.done]);
         std::lock_guard<std::mutex> lk(mu_);
         if (run.next && !next_served) {
             // a window shorter than WIN (text so far < 32 KiB): right-align it, what lies in front does not exist
             run.next->window.assign(WIN, 0);
-            memcpy(run.next->window.data() + (WIN - tail.size()), tail.data(), tail.size());
+            memcpy(run.next->window.data() + (WIN - rs.tail.size()), rs.tail.data(), rs.tail.size());
             run.next->window_ready = true;
         }
         cv_.notify_all();

@@ -533,6 +533,10 @@ def test_parallel_inflate_is_exact(built):
     assert _parallel_inflate(gz(text[:3000000], 6, zlib.Z_FIXED), 4, 1 << 16)[0] == text[:3000000]
     noise = bytes(rng.integers(0, 256, 3000000, dtype=np.uint8))
     assert _parallel_inflate(gz(noise), 4, 1 << 16)[0] == noise
+    # one very long run (65 MB of text without a single dynamic block): pieces are resolved and handed over while the run
+    # is still decoding, and the decoder waits for the consumer instead of piling them up
+    long_text = text * 5
+    assert _parallel_inflate(gz(long_text, 1, zlib.Z_FIXED), 4, 1 << 20, piece=1 << 16)[0] == long_text
     # text, then binary, then text again; full flushes in between (empty stored blocks, byte-aligned block starts)
     c = zlib.compressobj(6, zlib.DEFLATED, 31)
     mixed = c.compress(text[:4000000]) + c.flush(zlib.Z_FULL_FLUSH) + c.compress(noise[:500000]) + c.flush(zlib.Z_SYNC_FLUSH) + \
