@@ -537,19 +537,24 @@ struct mfkc_reader {
         // big single-member files: several threads decode one stream (parallel_inflate.h); MFKC_INFLATE=serial or a small
         // file: one FastInflate
         std::unique_ptr<mfkc::ParallelInflate> pi;
+        std::unique_ptr<mfkc::BgzfInflate> bz;
         if (map && gz) {
             int it = std::max(2, std::min(8, (int)std::thread::hardware_concurrency() * 3 / 4));
             if (const char *e = getenv("MFKC_INFLATE_THREADS")) it = atoi(e);
             if (!(inflate_env && !strcmp(inflate_env, "serial")) && it >= 2) {
-                pi.reset(new mfkc::ParallelInflate());
-                if (!pi->open(map, map_len, it)) pi.reset();
+                bz.reset(new mfkc::BgzfInflate());                  // bgzip'ed input: member sizes are in the headers
+                if (!bz->open(map, map_len, it)) bz.reset();
+                if (!bz) {
+                    pi.reset(new mfkc::ParallelInflate());
+                    if (!pi->open(map, map_len, it)) pi.reset();
+                }
             }
-            if (!pi) { fi.reset(new mfkc::FastInflate()); fi->reset(map, map_len); }
+            if (!pi && !bz) { fi.reset(new mfkc::FastInflate()); fi->reset(map, map_len); }
         }
         gzFile f = gz && !fi ? gzopen(path.c_str(), "rb") : nullptr;       // plain files: no zlib layer in between
         FILE *pf = gz ? nullptr : fopen(path.c_str(), "rb");
         std::vector<char> carry;
-        bool eof = !f && !pf && !fi && !pi, io_error = eof;
+        bool eof = !f && !pf && !fi && !pi && !bz, io_error = eof;
         if (f) gzbuffer(f, 1 << 20);
         while (!eof) {
             auto ch = fresh_chunk();
@@ -561,7 +566,8 @@ struct mfkc_reader {
             for (;;) {                                          // read until the block holds at least one whole record
                 if (ch->text.size() < have + kChunkText) ch->text.resize(have + kChunkText);
                 int r;
-                if (pi) r = (int)pi->read(ch->text.data() + have, kChunkText);
+                if (bz) r = (int)bz->read(ch->text.data() + have, kChunkText);
+                else if (pi) r = (int)pi->read(ch->text.data() + have, kChunkText);
                 else if (fi) r = (int)fi->read(ch->text.data() + have, kChunkText);
                 else if (gz) r = gzread(f, ch->text.data() + have, (unsigned)kChunkText);
                 else { r = (int)fread(ch->text.data() + have, 1, kChunkText, pf); if (r == 0 && ferror(pf)) r = -1; }
@@ -574,7 +580,7 @@ struct mfkc_reader {
             if (!eof) carry.assign(ch->text.data() + cut, ch->text.data() + have);
             ch->tptr = ch->text.data(); ch->tlen = cut;
             ch->last = eof;
-            if (io_error) { ch->status = MFKC_E_IO; ch->err = pi && pi->failed() ? "read error (corrupt gzip stream: " + pi->error() + ")" : fi && fi->failed() ? "read error (corrupt gzip stream: " + fi->error() + ")" : "read error (corrupt gzip stream?)"; }
+            if (io_error) { ch->status = MFKC_E_IO; ch->err = bz && bz->failed() ? "read error (corrupt gzip stream: " + bz->error() + ")" : pi && pi->failed() ? "read error (corrupt gzip stream: " + pi->error() + ")" : fi && fi->failed() ? "read error (corrupt gzip stream: " + fi->error() + ")" : "read error (corrupt gzip stream?)"; }
             if (!publish(ch)) break;
         }
         if (f) gzclose(f);

@@ -643,4 +643,130 @@ private:
     }
 };
 
+// BGZF (bgzip, htslib; RFC 1952 members of at most 64 KiB whose extra field 'BC' holds the member's size): the member
+// boundaries are known without decoding, so groups of members go to the threads as they are -- each group is a small
+// multi-member gzip file for FastInflate (which checks every member's CRC-32 and ISIZE) -- and come back in order.
+class BgzfInflate {
+public:
+    ~BgzfInflate() { shutdown(); }
+
+    // size of the BGZF member at p (0 = not a BGZF member)
+    static size_t member_size(const uint8_t *p, size_t left) {
+        if (left < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
+        const size_t xlen = p[10] | (size_t)p[11] << 8;
+        if (left < 12 + xlen) return 0;
+        for (size_t q = 12; q + 4 <= 12 + xlen;) {
+            const size_t slen = p[q + 2] | (size_t)p[q + 3] << 8;
+            if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) {
+                const size_t bsize = (p[q + 4] | (size_t)p[q + 5] << 8) + 1;
+                return bsize >= 12 + xlen + 8 && bsize <= left ? bsize : 0;
+            }
+            q += 4 + slen;
+        }
+        return 0;
+    }
+
+    bool open(const uint8_t *in, size_t n, int threads, size_t group_bytes = 4u << 20) {
+        if (threads < 2 || n < 2 * group_bytes || !member_size(in, n)) return false;
+        in_ = in; n_ = n; group_bytes_ = group_bytes;
+        max_ahead_ = (size_t)threads * 2 + 2;
+        for (int t = 0; t < threads; t++) threads_.emplace_back([this] { worker(); });
+        return true;
+    }
+    const std::string &error() const { return err_; }
+    bool failed() const { return !err_.empty(); }
+
+    long read(char *dst, size_t n) {
+        size_t done = 0;
+        while (done < n && err_.empty() && !finished_) {
+            if (rest_) {                                           // something that is not BGZF follows: serial
+                const long r = rest_->read(dst + done, n - done);
+                if (r < 0) { err_ = rest_->error(); break; }
+                if (r == 0) { finished_ = true; break; }
+                done += (size_t)r;
+                continue;
+            }
+            if (!cur_) {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return (!groups_.empty() && groups_.front()->ready) || (groups_.empty() && walked_all_); });
+                if (groups_.empty()) {
+                    if (walk_pos_ < n_ && FastInflate::looks_like_gzip(in_ + walk_pos_, n_ - walk_pos_)) {
+                        rest_.reset(new FastInflate()); rest_->reset(in_ + walk_pos_, n_ - walk_pos_);
+                    } else finished_ = true;                       // end of file, or trailing garbage (ignored, like gzread)
+                    continue;
+                }
+                cur_ = groups_.front(); groups_.pop_front(); pos_ = 0;
+                consumed_++;
+                cv_.notify_all();
+                if (!cur_->err.empty()) { err_ = cur_->err; break; }
+            }
+            const size_t take = std::min(n - done, cur_->text.size() - pos_);
+            memcpy(dst + done, cur_->text.data() + pos_, take);
+            pos_ += take; done += take;
+            if (pos_ == cur_->text.size()) cur_.reset();
+        }
+        if (!err_.empty() && done == 0) return -1;
+        return (long)done;
+    }
+
+private:
+    struct Group { size_t begin = 0, end = 0; std::vector<char> text; std::string err; bool ready = false; };
+    const uint8_t *in_ = nullptr; size_t n_ = 0, group_bytes_ = 0;
+    std::mutex mu_; std::condition_variable cv_;
+    std::vector<std::thread> threads_;
+    std::deque<std::shared_ptr<Group>> groups_;                    // in file order
+    size_t walk_pos_ = 0, handed_ = 0, consumed_ = 0, max_ahead_ = 8;
+    bool walked_all_ = false, stop_ = false;
+    std::shared_ptr<Group> cur_; size_t pos_ = 0;
+    std::unique_ptr<FastInflate> rest_;
+    bool finished_ = false;
+    std::string err_;
+
+    void shutdown() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+        threads_.clear();
+    }
+    void worker() {
+        FastInflate fi;
+        for (;;) {
+            std::shared_ptr<Group> g;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || walked_all_ || handed_ < consumed_ + max_ahead_; });
+                if (stop_ || walked_all_) return;
+                // the next group: whole members from walk_pos_ on, about group_bytes_ of them
+                size_t p = walk_pos_;
+                while (p < n_ && p - walk_pos_ < group_bytes_) {
+                    const size_t sz = member_size(in_ + p, n_ - p);
+                    if (!sz) break;
+                    p += sz;
+                }
+                if (p == walk_pos_) { walked_all_ = true; cv_.notify_all(); return; }      // end of the BGZF part
+                g = std::make_shared<Group>();
+                g->begin = walk_pos_; g->end = p;
+                walk_pos_ = p; handed_++;
+                groups_.push_back(g);
+            }
+            fi.reset(in_ + g->begin, g->end - g->begin);
+            std::vector<char> text;
+            text.resize((g->end - g->begin) * 5 + (1u << 16));
+            size_t have = 0;
+            std::string err;
+            for (;;) {
+                if (text.size() - have < (1u << 20)) text.resize(text.size() * 2);
+                const long r = fi.read(text.data() + have, text.size() - have);
+                if (r < 0) { err = fi.error(); break; }
+                if (r == 0) break;
+                have += (size_t)r;
+            }
+            text.resize(have);
+            std::lock_guard<std::mutex> lk(mu_);
+            g->text.swap(text); g->err = err; g->ready = true;
+            cv_.notify_all();
+        }
+    }
+};
+
 }  // namespace mfkc

@@ -46,3 +46,23 @@ extern "C" long pi_inflate(const uint8_t *in, size_t n, uint8_t *out, size_t cap
     if (err && err_cap) snprintf(err, err_cap, "%s", pi.error().c_str());
     return rc < 0 ? rc : (long)total;
 }
+
+// the BGZF decoder; rc -3 = open() declined (not BGZF / too small)
+extern "C" long bz_inflate(const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t piece, int threads, size_t group_bytes,
+                           char *err, size_t err_cap) {
+    mfkc::BgzfInflate bz;
+    if (!bz.open(in, n, threads, group_bytes)) return -3;
+    size_t total = 0;
+    long rc = 0;
+    std::vector<char> buf(piece ? piece : 1);
+    for (;;) {
+        const long r = bz.read(buf.data(), buf.size());
+        if (r < 0) { rc = -1; break; }
+        if (r == 0) break;
+        if (total + (size_t)r > cap) { rc = -2; break; }
+        memcpy(out + total, buf.data(), (size_t)r);
+        total += (size_t)r;
+    }
+    if (err && err_cap) snprintf(err, err_cap, "%s", bz.error().c_str());
+    return rc < 0 ? rc : (long)total;
+}

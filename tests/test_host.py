@@ -621,3 +621,61 @@ def test_gz_reader_parallel_inflate_path(built, tmp_path, monkeypatch):
     path.write_bytes(bytes(bad))
     with pytest.raises(m.MfkcError):
         digest()
+
+
+def _bgzf(raw: bytes, block: int = 65280, level: int = 6) -> bytes:
+    """bgzip's container: gzip members with the 'BC' extra field = member size - 1, and the empty EOF member"""
+    import struct
+    import zlib
+    out = bytearray()
+    for pos in list(range(0, len(raw), block)) + [None]:
+        part = b"" if pos is None else raw[pos:pos + block]
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        body = c.compress(part) + c.flush()
+        size = 12 + 6 + len(body) + 8
+        out += b"\x1f\x8b\x08\x04\0\0\0\0\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, size - 1) + body + \
+            struct.pack("<II", zlib.crc32(part), len(part))
+    return bytes(out)
+
+
+@pytest.mark.timeout(600)
+def test_bgzf_inflate(built):
+    """bgzip'ed input: groups of members decoded side by side, handed out in order; errors and non-BGZF tails"""
+    import ctypes as C
+    import zlib
+    lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libinflate_harness.so"))
+    lib.bz_inflate.restype = C.c_long
+    lib.bz_inflate.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t]
+
+    def run(data, threads=4, group=1 << 16, piece=(1 << 18) + 7, cap=1 << 26):
+        out = np.zeros(cap, dtype=np.uint8)
+        err = C.create_string_buffer(256)
+        n = lib.bz_inflate(data, len(data), out.ctypes.data_as(C.c_void_p), cap, piece, threads, group, err, 256)
+        return ("declined" if n == -3 else None if n < 0 else out[:n].tobytes()), err.value.decode()
+
+    rng = np.random.default_rng(41)
+    text = _fastq_text(rng, 40000)
+    comp = _bgzf(text)
+    assert _zlib_gunzip(comp) == text                                   # the container is what zlib reads too
+    for threads, group in ((2, 1 << 16), (4, 1 << 18), (8, 1 << 15), (3, 100)):
+        assert run(comp, threads, group)[0] == text
+    assert run(gzip.compress(text))[0] == "declined"                    # ordinary gzip: ParallelInflate's job
+    # an ordinary member and garbage behind the BGZF part
+    assert run(comp + gzip.compress(b"tail text\n"))[0] == text + b"tail text\n"
+    assert run(comp + b"\0\1\2")[0] == text
+    # a flipped bit inside a member body: that member's CRC (or its codes) fail
+    bad = bytearray(comp)
+    bad[len(bad) // 2] ^= 0x20
+    got, err = run(bytes(bad))
+    assert got is None and err
+    # through the reader
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "reads.fastq.gz")
+        big = _fastq_text(rng, 130000)
+        open(path, "wb").write(_bgzf(big))
+        assert os.path.getsize(path) > (8 << 20)
+        got_reads = m.read_file_reads(path)
+        assert len(got_reads) == 130000
+        lines = big.split(b"\n")
+        assert got_reads[0] == lines[1].decode() and got_reads[-1] == lines[-4].decode()
