@@ -14,8 +14,10 @@ threshold filter + key-sorted big-endian records.
   e2e    the same step through the C ABI with HOST (pinned) buffers: every step copies the reads
          host->device and the records + histogram device->host inside the timed region.
   N > 1  one process per GPU (torchrun): every rank extracts the k-mers of ITS OWN 20 M reads
-         (weak scaling), buckets them by owner shard, exchanges them with an NCCL all-to-all and
-         counts only its own hash range (BASELINE.json configs[3] layout).
+         (weak scaling) and stages them per owner shard in its own HBM; every owner drains its
+         segments straight out of the peers' memory over NVLink inside the counting kernel
+         (CUDA IPC; MFKC_EXCHANGE=nccl selects the NCCL all-to-all + restage flavour) and counts
+         only its own hash range (BASELINE.json configs[3] layout).
 
 The JSON line also carries `roofline` (counting kernels vs the measured HBM peak, plus the
 random-sector GUPS peak measured in the same run) and `cpu_baseline` (the C restatement of the
