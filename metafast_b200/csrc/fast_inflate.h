@@ -25,7 +25,8 @@ namespace mfkc {
 
 #if defined(__x86_64__)
 // reflected CRC-32 (polynomial 0xEDB88320) by carry-less multiplication, 64 bytes per iteration (the folding scheme of
-// Intel's "Fast CRC computation using PCLMULQDQ"); len >= 64 and a multiple of 16; crc in / out = the raw register
+// Gopal et al., "Fast CRC Computation for Generic Polynomials Using PCLMULQDQ Instruction", Intel 2009, with the folding
+// constants for this polynomial as published there and used by zlib forks); len >= 64 and a multiple of 16; crc in / out = the raw register
 // (the complement of zlib's value).  Checked against zlib's crc32 in tests/test_host.py.
 __attribute__((target("pclmul,sse4.1")))
 inline uint32_t crc32_clmul_raw(const uint8_t *buf, size_t len, uint32_t crc) {
