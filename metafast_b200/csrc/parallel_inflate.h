@@ -517,7 +517,11 @@ private:
                     dropped = stop_ || run.discarded;
                     if (dropped) run.err = "discarded";
                 }
-                if (dropped) { close_piece(true); return; }              // (close_piece takes the lock itself)
+                if (dropped) {                                           // a false start (or the end): its pieces are of no use
+                    std::lock_guard<std::mutex> lk(mu_);
+                    run.pieces.clear(); run.decoded = true;
+                    return;
+                }
                 const uint64_t bit = dec.bitpos();
                 if ((size_t)((bit >> 3) / seg_bytes_) > run.seg && boundary_check(run, bit)) { close_piece(true); break; }
             }
@@ -614,7 +618,7 @@ private:
         {
             std::unique_lock<std::mutex> lk(mu_);
             cv_.wait(lk, [&] { return stop_ || run.discarded || run.window_ready; });
-            if (stop_ || run.discarded) return;
+            if (stop_ || run.discarded) { run.pieces.clear(); return; }
         }
         if (!rs.ready) prepare(rs, run);
         // The next run is waiting for its window = my last WIN bytes: resolve those first and hand them over, so that the
@@ -639,6 +643,7 @@ private:
             memcpy(run.next->window.data() + (WIN - rs.tail.size()), rs.tail.data(), rs.tail.size());
             run.next->window_ready = true;
         }
+        std::vector<uint8_t>().swap(run.window);                   // (a 100-GB file has 10^5 runs: do not keep 32 KiB for each)
         cv_.notify_all();
     }
 };
