@@ -679,3 +679,33 @@ def test_bgzf_inflate(built):
         assert len(got_reads) == 130000
         lines = big.split(b"\n")
         assert got_reads[0] == lines[1].decode() and got_reads[-1] == lines[-4].decode()
+
+
+def test_host_tools_error_paths(built, tmp_path):
+    """dist-matrix-calculator / heatmap-maker: the reference's messages and exit code 1 (Tool.java:450-462)"""
+    import subprocess
+
+    def fails(*args):
+        r = subprocess.run([CLI] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 1
+        return r.stderr
+
+    assert "Missing mandatory parameter --features" in fails("-t", "dist-matrix-calculator")
+    assert "Failed to read features from" in fails("-t", "dist-matrix-calculator", "--features", tmp_path / "nope.vec")
+    assert "Can't read matrix file" in fails("-t", "heatmap-maker", "-i", tmp_path / "nope.txt")
+    (tmp_path / "empty.txt").write_text("")
+    assert "No data to read in matrix file" in fails("-t", "heatmap-maker", "-i", tmp_path / "empty.txt")
+    (tmp_path / "wide.txt").write_text("#\ta\tb\tc\na\t0\t1\t2\n")
+    assert "columns' number > rows' number" in fails("-t", "heatmap-maker", "-i", tmp_path / "wide.txt")
+    (tmp_path / "ragged.txt").write_text("#\ta\tb\na\t0\t1\nb\t1\n")
+    assert "columns' number is different for different rows" in fails("-t", "heatmap-maker", "-i", tmp_path / "ragged.txt")
+    (tmp_path / "long.txt").write_text("#\ta\na\t0\nb\t1\n")
+    assert "too much rows" in fails("-t", "heatmap-maker", "-i", tmp_path / "long.txt")
+    (tmp_path / "ok.txt").write_text("0.0\t0.5\n0.5\t0.0\n")
+    assert "only %.<N>f, %f and %s are supported" in fails("-t", "heatmap-maker", "-i", tmp_path / "ok.txt", "--output-format", "%e")
+    assert "is outside the path this build replaces" in fails("-t", "view")
+    assert "Unrecognized option" in fails("-t", "heatmap-maker", "--nope")
+    # without names: "<i> library" labels are made up for the picture only, the renumbered matrix has names
+    r = subprocess.run([CLI, "-t", "heatmap-maker", "-i", str(tmp_path / "ok.txt")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0
+    assert (tmp_path / "ok_renumbered.txt").read_text() == "#\t1 library\t2 library\n1 library\t0.0000\t0.5000\n2 library\t0.5000\t0.0000\n"
