@@ -22,6 +22,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -241,6 +242,23 @@ public:
         seg_run_.assign(n_seg_, nullptr);
         for (size_t i = 0; i < n_seg_; i++) seg_state_[i].store(SEG_FREE);
         lookahead_ = (size_t)threads * 2 + 2;
+        // Is this a stream the block finder can work with (dynamic blocks of text)?  Two sample segments are probed now; their
+        // results are kept for the workers.  If neither has a start (binary data, stored or fixed blocks only), one thread
+        // would decode everything through the 16-bit path and wait for fruitless probes on the way: slower than FastInflate.
+        {
+            MarkerInflate dec;
+            bool any = false;
+            const size_t samples[8] = {1, n_seg_ / 2, 2, n_seg_ / 2 + 1, n_seg_ / 4, 3 * n_seg_ / 4, 3, n_seg_ / 2 + 2};
+            for (int i = 0; i < 8 && !(any && i >= 2); i++) {      // two samples; up to six more while nothing was found
+                const size_t sseg = samples[i];
+                if (sseg == 0 || sseg + 1 >= n_seg_ || preprobed_.count(sseg)) continue;
+                uint64_t start = 0;
+                const bool found = find_block_start(dec, sseg, &start);
+                preprobed_[sseg] = found ? start : ~0ull;
+                any = any || found;
+            }
+            if (!any) return false;
+        }
         for (int t = 0; t < threads; t++) threads_.emplace_back([this] { worker(); });
         return true;
     }
@@ -285,6 +303,7 @@ private:
     };
     struct Run {                                                   // one thread's decode from one block start
         size_t seg = 0; uint64_t start_bit = 0;
+        size_t settled = 0;                                        // boundary_check: segments up to here need no second look
         std::deque<std::shared_ptr<Piece>> pieces;                 // in order; guarded by mu_
         bool decoded = false;                                      // no more pieces will be added
         bool discarded = false;                                    // passed by the predecessor without a meeting: a false start
@@ -302,6 +321,7 @@ private:
     std::unique_ptr<std::atomic<int>[]> seg_state_;
     std::vector<uint64_t> seg_start_;
     std::vector<Run *> seg_run_;
+    std::map<size_t, uint64_t> preprobed_;                         // segment -> block start found by open() (~0 = none); read-only afterwards
     std::vector<std::unique_ptr<Run>> runs_;                       // ownership; guarded by mu_
     std::mutex mu_; std::condition_variable cv_;
     std::vector<std::thread> threads_;
@@ -379,6 +399,7 @@ private:
             uint64_t start = 0;
             bool found = false;
             if (seg == 0) { start = first_bit_; found = true; }
+            else if (preprobed_.count(seg)) { start = preprobed_[seg]; found = start != ~0ull; }
             else found = find_block_start(dec, seg, &start);
             Run *run = nullptr;
             {
@@ -386,7 +407,7 @@ private:
                 if (found) {
                     runs_.emplace_back(new Run());
                     run = runs_.back().get();
-                    run->seg = seg; run->start_bit = start;
+                    run->seg = seg; run->settled = seg; run->start_bit = start;
                     if (seg == 0) { run->confirmed = true; run->window_ready = true; }
                     seg_start_[seg] = start; seg_run_[seg] = run;
                     seg_state_[seg].store(SEG_STARTED);
@@ -400,7 +421,6 @@ private:
     bool find_block_start(MarkerInflate &dec, size_t seg, uint64_t *start) {
         const uint64_t lo = (uint64_t)seg * seg_bytes_ * 8, hi = std::min<uint64_t>((uint64_t)(seg + 1) * seg_bytes_, n_ - 16) * 8;
         for (uint64_t byte = lo >> 3; byte < (hi >> 3); byte++) {
-            if ((byte & 0xFFF) == 0 && seg_state_[seg].load() != SEG_PROBING) return false;       // (never happens: kept for symmetry)
             // cheap filters on the raw bits first: BFINAL = 0, BTYPE = 2, HLIT <= 29, HDIST <= 29 (one position in nine
             // passes), then the code-length code must be complete -- Kraft sum of its HCLEN + 4 three-bit lengths exactly 1
             // (one in a few hundred of those passes); only then the real header parser and the trial decode run
@@ -457,7 +477,9 @@ private:
     // what is at `bit` (a block boundary the decoder of `run` has reached)?  0 = nothing: go on; 1 = met the next run: stop
     int boundary_check(Run &run, uint64_t bit) {
         const size_t seg = (size_t)((bit >> 3) / seg_bytes_);
-        for (size_t s = run.seg + 1; s <= seg && s < n_seg_; s++) {
+        // segments up to run.settled are dealt with for good (no start, or a false one): a run that walks over many
+        // segments must not look at all of them again at every block
+        for (size_t s = run.settled + 1; s <= seg && s < n_seg_; s++) {
             int st = seg_state_[s].load();
             if (st == SEG_FREE) {
                 // Nobody has looked at this segment yet.  If the workers may take it (it is inside the look-ahead window),
@@ -467,7 +489,7 @@ private:
                 cv_.wait(lk, [&] { return stop_ || seg_state_[s].load() != SEG_FREE || s > consumed_seg_ + lookahead_; });
                 if (stop_) return 1;
                 int expect = SEG_FREE;
-                if (seg_state_[s].compare_exchange_strong(expect, SEG_NONE)) continue;
+                if (seg_state_[s].compare_exchange_strong(expect, SEG_NONE)) { run.settled = s; continue; }
                 st = seg_state_[s].load();
             }
             if (st == SEG_PROBING) {
@@ -484,13 +506,13 @@ private:
                     st = seg_state_[s].load();
                 }
             }
-            if (st == SEG_NONE) continue;
+            if (st == SEG_NONE) { run.settled = s; continue; }
             // SEG_STARTED
             std::lock_guard<std::mutex> lk(mu_);
             Run *other = seg_run_[s];
-            if (!other || other->discarded) continue;
+            if (!other || other->discarded) { run.settled = s; continue; }
             if (other->start_bit == bit) { other->confirmed = true; run.next = other; cv_.notify_all(); return 1; }
-            if (other->start_bit < bit) { other->discarded = true; cv_.notify_all(); continue; }   // passed without a meeting: a false start
+            if (other->start_bit < bit) { other->discarded = true; run.settled = s; cv_.notify_all(); continue; }   // passed without a meeting: a false start
             return 0;                                              // it starts further on: keep going
         }
         return 0;

@@ -529,14 +529,23 @@ def test_parallel_inflate_is_exact(built):
             got, err, _ = _parallel_inflate(comp, threads, segment, piece=(1 << 20) + 13)
             assert got == text, (level, memlevel, threads, segment, err)
     assert _parallel_inflate(gz(text[:100000]), 4, 1 << 20)[0] == "declined"   # too small: the caller uses FastInflate
-    # no dynamic blocks to start from (fixed Huffman codes; stored blocks of random bytes): one run decodes everything
-    assert _parallel_inflate(gz(text[:3000000], 6, zlib.Z_FIXED), 4, 1 << 16)[0] == text[:3000000]
+    # no dynamic blocks to start from (fixed Huffman codes; stored blocks of random bytes): the sample probes of open() find
+    # nothing and the decoder declines -- one FastInflate is faster than one run through the 16-bit path
+    assert _parallel_inflate(gz(text[:3000000], 6, zlib.Z_FIXED), 4, 1 << 16)[0] == "declined"
     noise = bytes(rng.integers(0, 256, 3000000, dtype=np.uint8))
-    assert _parallel_inflate(gz(noise), 4, 1 << 16)[0] == noise
-    # one very long run (65 MB of text without a single dynamic block): pieces are resolved and handed over while the run
-    # is still decoding, and the decoder waits for the consumer instead of piling them up
-    long_text = text * 5
-    assert _parallel_inflate(gz(long_text, 1, zlib.Z_FIXED), 4, 1 << 20, piece=1 << 16)[0] == long_text
+    assert _parallel_inflate(gz(noise), 4, 1 << 16)[0] == "declined"
+    # one very long run: 50 MB without a single dynamic block in the middle of a text stream.  Its pieces are resolved and
+    # handed over while the run is still decoding, and the decoder waits for the consumer instead of piling them up
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    parts = [c.compress(text) + c.flush(zlib.Z_FULL_FLUSH)]
+    c2 = zlib.compressobj(1, zlib.DEFLATED, -15, 8, zlib.Z_FIXED)          # raw deflate, fixed codes, spliced in
+    fixed = c2.compress(text * 4) + c2.flush(zlib.Z_FULL_FLUSH)
+    long_text = text + text * 4 + text
+    tail = c.compress(text) + c.flush()
+    import struct
+    spliced = parts[0] + fixed + tail[:-8] + struct.pack("<II", zlib.crc32(long_text), len(long_text) & 0xFFFFFFFF)
+    assert _zlib_gunzip(spliced) == long_text
+    assert _parallel_inflate(spliced, 4, 1 << 20, piece=1 << 16)[0] == long_text
     # text, then binary, then text again; full flushes in between (empty stored blocks, byte-aligned block starts)
     c = zlib.compressobj(6, zlib.DEFLATED, 31)
     mixed = c.compress(text[:4000000]) + c.flush(zlib.Z_FULL_FLUSH) + c.compress(noise[:500000]) + c.flush(zlib.Z_SYNC_FLUSH) + \
