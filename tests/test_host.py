@@ -718,3 +718,39 @@ def test_host_tools_error_paths(built, tmp_path):
     r = subprocess.run([CLI, "-t", "heatmap-maker", "-i", str(tmp_path / "ok.txt")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0
     assert (tmp_path / "ok_renumbered.txt").read_text() == "#\t1 library\t2 library\n1 library\t0.0000\t0.5000\n2 library\t0.5000\t0.0000\n"
+
+
+def test_compare_with_reference_tool(tmp_path):
+    """tools/compare_with_reference.py: a reference-style tree (records in hash-map order, components and sequences in thread
+    order) against a tree in this repository's order compares equal; a changed count does not"""
+    import subprocess
+    import sys
+    rng = np.random.default_rng(51)
+    reads = orc.parse_reads(os.path.join(INPUTS, "meta_test_2.fa"))
+    counts = orc.count_reads(reads, 31)
+    rec = orc.kmers_bin(counts, 1, 31)
+    ref, new = tmp_path / "ref", tmp_path / "new"
+    for d in (ref, new):
+        for sub in ("kmers", "stats", "matrices", "sequences"):
+            os.makedirs(d / sub)
+    recs = [rec[i:i + 10] for i in range(0, len(rec), 10)]
+    perm = rng.permutation(len(recs))
+    (ref / "kmers" / "s.kmers.bin").write_bytes(b"".join(recs[i] for i in perm))       # hash-map order
+    (new / "kmers" / "s.kmers.bin").write_bytes(rec)
+    for d in (ref, new):
+        (d / "stats" / "s.stat.txt").write_text(orc.stat_txt(counts))
+    comps = orc.component_cutter(orc.count_reads(reads, 21), 21, 50, 800)
+    (new / "components.bin").write_bytes(orc.save_components([(w, k) for w, k, _ in comps], 31))
+    (ref / "components.bin").write_bytes(orc.save_components([(w, list(rng.permutation(k))) for w, k, _ in reversed(comps)], 31))
+    (ref / "sequences" / "s.seq.fasta").write_text(">1 x\nACGT\nAC\n>2 y\nTTTT\n")
+    (new / "sequences" / "s.seq.fasta").write_text(">1 y\nTTTT\n>2 x\nACGTAC\n")
+    (ref / "matrices" / "dist_matrix_a_original_order.txt").write_text("#\ta\tb\na\t0.0000\t0.5000\nb\t0.5000\t0.0000\n")
+    (new / "matrices" / "dist_matrix_b_original_order.txt").write_text("#\ta\tb\na\t0.0000\t0.5000\nb\t0.5000\t0.0000\n")
+    tool = os.path.join(ROOT, "tools", "compare_with_reference.py")
+    r = subprocess.run([sys.executable, tool, str(ref), str(new)], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "5 compared, 0 differ" in r.stdout, r.stdout
+    bad = bytearray(rec)
+    bad[9] ^= 1
+    (new / "kmers" / "s.kmers.bin").write_bytes(bytes(bad))
+    r = subprocess.run([sys.executable, tool, str(ref), str(new)], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "DIFFERS  records (multiset)  kmers/s.kmers.bin" in r.stdout
