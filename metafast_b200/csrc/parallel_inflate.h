@@ -492,19 +492,11 @@ private:
                 if (seg_state_[s].compare_exchange_strong(expect, SEG_NONE)) { run.settled = s; continue; }
                 st = seg_state_[s].load();
             }
-            if (st == SEG_PROBING) {
-                if (s < seg) {                                     // I am past that whole segment: whatever it finds is behind me
-                    std::unique_lock<std::mutex> lk(mu_);
-                    cv_.wait(lk, [&] { return stop_ || seg_state_[s].load() != SEG_PROBING; });
-                    if (stop_) return 1;
-                    st = seg_state_[s].load();
-                } else {
-                    // the prober of my current segment may still find a start behind or in front of me: wait for it
-                    std::unique_lock<std::mutex> lk(mu_);
-                    cv_.wait(lk, [&] { return stop_ || seg_state_[s].load() != SEG_PROBING; });
-                    if (stop_) return 1;
-                    st = seg_state_[s].load();
-                }
+            if (st == SEG_PROBING) {                               // its prober may still find a start behind, at or in front of me
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || seg_state_[s].load() != SEG_PROBING; });
+                if (stop_) return 1;
+                st = seg_state_[s].load();
             }
             if (st == SEG_NONE) { run.settled = s; continue; }
             // SEG_STARTED
