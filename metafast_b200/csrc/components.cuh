@@ -18,8 +18,9 @@
 // slot = half a sector each) per active k-mer and level.
 //
 // This header uses no warp intrinsics, shared memory or inline PTX on purpose: tests/emu/cc_emu.cpp compiles it for
-// the host (one emulated thread) so that the level logic is checked against the oracle on CPU-only machines too; the
-// product path is the CUDA build in mfkc.cu (mfkc_kset_components_*).
+// the host (one emulated CUDA thread per host thread, real atomics) so that the level logic and the union-find under
+// contention are checked against the oracle on CPU-only machines too; the product path is the CUDA build in mfkc.cu
+// (mfkc_kset_components_*).
 #pragma once
 #include "device_common.cuh"
 

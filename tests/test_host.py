@@ -233,7 +233,7 @@ def test_parallel_reader_equals_serial(built, tmp_path, monkeypatch):
 
 
 # ---------------------------------------------------------------- the main caller's remaining stages (matrix-builder)
-def _emulated_components(hm, k, b1, b2):
+def _emulated_components(hm, k, b1, b2, grid=1):
     """tests/emu/cc_emu.cpp: the kernels of metafast_b200/csrc/components.cuh compiled for the host"""
     lib = C.CDLL(os.path.join(ROOT, "tests", "emu", "_build", "libcc_emu.so"))
     keys = np.array(sorted(hm), dtype=np.uint64)
@@ -241,7 +241,7 @@ def _emulated_components(hm, k, b1, b2):
     nc, nk, lv, res = C.c_uint64(), C.c_uint64(), C.c_int(), C.c_void_p()
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     lib.cc_emu_components(vp(keys), vp(vals), C.c_uint64(len(keys)), C.c_int(k), C.c_longlong(b1), C.c_longlong(b2),
-                          C.byref(nc), C.byref(nk), C.byref(lv), C.byref(res))
+                          C.byref(nc), C.byref(nk), C.byref(lv), C.byref(res), C.c_int(grid))
     off = np.zeros(nc.value + 1, dtype=np.uint64)
     ks = np.zeros(max(nk.value, 1), dtype=np.int64)
     w = np.zeros(max(nc.value, 1), dtype=np.int64)
@@ -260,6 +260,8 @@ def test_component_kernels_emulated_on_host(built):
         got, levels = _emulated_components(hm, k, b1, b2)
         assert got == want and len(want) > 5
         assert levels >= min_levels                                   # big components were re-split level after level
+        for rep in range(3):                                          # 8 concurrent emulated blocks: the union-find under contention
+            assert _emulated_components(hm, k, b1, b2, grid=8)[0] == want
     assert _emulated_components({}, 31, 1, 10) == ([], 0)
     # values <= 0 are no vertices (`getValue() > 0`); key 0 (poly-A) is its own neighbour
     assert _emulated_components({0: 3, 5: 0xFFFE}, 3, 1, 10)[0] == [(3, [0], 1)] == orc.component_cutter({0: 3}, 3, 1, 10)
