@@ -143,6 +143,66 @@ def cpu_reference_run(n_reads, threads, seed_first=0):
     return nk * (READ_LEN - K + 1), dt
 
 
+def host_ingest_numbers(n_reads=400_000):
+    """Throughput of the host ingest path (mfkc_reader_*: mapped input, parallel parsers, the repository's own multi-threaded
+    gzip decoder) on a synthetic FASTQ of the workload's reads, plain and .gz, with zlib's gzread beside it.  Informational:
+    real FASTQ(.gz)-to-.kmers.bin runs are bound by this, not by the GPU.  A few seconds, rank 0 at N = 1 only."""
+    import gzip
+    import shutil
+    import tempfile
+    import metafast_b200 as m
+    cli = os.path.join(ROOT, "metafast_b200", "bin", "mfkc_cli")
+    d = tempfile.mkdtemp(prefix="mfkc_ingest_")
+    try:
+        fq = os.path.join(d, "reads.fastq")
+        subprocess.run([cli, "gen-reads", fq, str(n_reads), "0"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        with open(fq, "rb") as f, gzip.open(fq + ".gz", "wb", compresslevel=1) as g:
+            shutil.copyfileobj(f, g, 1 << 24)
+
+        import numpy as np
+        lib = m.load()
+        cap_reads = 1 << 20
+        bases = np.ones(128 << 20, dtype=np.uint8)
+        offs = np.zeros(cap_reads + 1, dtype=np.uint64)
+        got = C.c_uint32()
+        err = C.create_string_buffer(256)
+
+        def rate(path, env):
+            best = None
+            for _ in range(3):
+                old = {k: os.environ.get(k) for k in env}
+                os.environ.update(env)
+                try:
+                    h = C.c_void_p()
+                    if lib.mfkc_reader_open(path.encode(), C.byref(h), err, 256) != 0:
+                        raise RuntimeError(err.value.decode())
+                    t0 = time.perf_counter()
+                    n = 0
+                    while True:                                       # the loop of mfkc_cli: the same buffers over and over
+                        if lib.mfkc_reader_next(h, bases.ctypes.data_as(C.c_void_p), bases.nbytes, offs.ctypes.data_as(C.c_void_p),
+                                                cap_reads, C.byref(got)) != 0:
+                            raise RuntimeError(lib.mfkc_reader_error(h).decode())
+                        if got.value == 0:
+                            break
+                        n += got.value
+                    dt = time.perf_counter() - t0
+                    lib.mfkc_reader_close(h)
+                finally:
+                    for k, v in old.items():
+                        if v is None:
+                            os.environ.pop(k, None)
+                        else:
+                            os.environ[k] = v
+                best = dt if best is None else min(best, dt)
+            return n / best
+        return {"unit": "reads/s", "cores": os.cpu_count(), "plain_fastq": rate(fq, {}), "fastq_gz": rate(fq + ".gz", {}),
+                "fastq_gz_zlib_gzread": rate(fq + ".gz", {"MFKC_INFLATE": "zlib"}),
+                "sample": "%d synthetic 150-bp reads as FASTQ (%d MB), gzip -1 (%d MB); best of 3 passes through mfkc_reader_*"
+                          % (n_reads, os.path.getsize(fq) >> 20, os.path.getsize(fq + ".gz") >> 20)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -350,6 +410,13 @@ def main():
         except Exception as ex:                                   # the checker is optional for the measurement itself
             cpu = {"value": None, "unit": "kmers/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
 
+    ingest = None
+    if world == 1 and not os.environ.get("MFKC_BENCH_NO_INGEST"):
+        try:
+            ingest = host_ingest_numbers()
+        except Exception as ex:                                   # informational only
+            ingest = {"failed": repr(ex)}
+
     line = {
         "metric": "canonical 31-mers counted/s", "value": value, "unit": "kmers/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -361,6 +428,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "host_ingest": ingest,
         "result": {"kmers_per_step_per_gpu": kmers_per_step, "distinct": st["distinct"], "records_gt_b": int(n_good),
                    "host_wall_ms_per_step": 1e3 * wall / args.steps},
     }
