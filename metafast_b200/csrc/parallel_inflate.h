@@ -399,7 +399,7 @@ private:
             uint64_t start = 0;
             bool found = false;
             if (seg == 0) { start = first_bit_; found = true; }
-            else if (preprobed_.count(seg)) { start = preprobed_[seg]; found = start != ~0ull; }
+            else if (preprobed_.count(seg)) { start = preprobed_.at(seg); found = start != ~0ull; }      // (const access: several workers read it)
             else found = find_block_start(dec, seg, &start);
             Run *run = nullptr;
             {
