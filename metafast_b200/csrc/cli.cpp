@@ -962,6 +962,15 @@ int tool_gen(int argc, char **argv) {
 int main(int argc, char **argv) {
     if (argc > 1 && !strcmp(argv[1], "gen-reads")) return tool_gen(argc, argv);
     const Args a = parse_args(argc, argv);
+    // -p / --available-processors (Tool.java:148-151): the reference sizes its worker pools with it; here it bounds the host
+    // threads of the readers (parse workers, gzip decoder threads) unless the MFKC_* variables say otherwise
+    if (a.has("available-processors") && !a.many("available-processors").empty()) {
+        const int p = parse_int(a, "available-processors", false, 0);
+        if (p >= 1) {
+            setenv("MFKC_READER_THREADS", std::to_string(p).c_str(), 0);
+            setenv("MFKC_INFLATE_THREADS", std::to_string(p >= 2 ? p : 1).c_str(), 0);
+        }
+    }
     if (a.tool == "kmer-counter-many") return tool_counter(a, true);
     if (a.tool == "kmer-counter") return tool_counter(a, false);
     if (a.tool == "features-calculator") return tool_features(a);
