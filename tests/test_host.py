@@ -756,3 +756,19 @@ def test_compare_with_reference_tool(tmp_path):
     (new / "kmers" / "s.kmers.bin").write_bytes(bytes(bad))
     r = subprocess.run([sys.executable, tool, str(ref), str(new)], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "DIFFERS  records (multiset)  kmers/s.kmers.bin" in r.stdout
+
+
+def test_fastq_ingest_of_the_golden_samples(built, tmp_path):
+    """the reference's test samples re-written as FASTQ (plain, .gz, bgzip): every reader path hands out exactly the reads of
+    the FASTA files the golden matrix is pinned on -- so the FASTQ / gzip ingest feeds the pinned pipeline unchanged"""
+    for n in (1, 2, 3):
+        fa = os.path.join(INPUTS, "meta_test_%d.fa" % n)
+        want = m.read_file_reads(fa)
+        assert want == orc.parse_reads(fa) and len(want) in (1917, 540, 1080)
+        text = "".join("@r%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)) for i, r in enumerate(want)).encode()
+        fq = tmp_path / ("s%d.fastq" % n)
+        fq.write_bytes(text)
+        (tmp_path / ("g%d.fastq.gz" % n)).write_bytes(gzip.compress(text))
+        (tmp_path / ("b%d.fastq.gz" % n)).write_bytes(_bgzf(text, block=5000))
+        for name in ("s%d.fastq", "g%d.fastq.gz", "b%d.fastq.gz"):
+            assert m.read_file_reads(str(tmp_path / (name % n))) == want, name
