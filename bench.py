@@ -235,7 +235,7 @@ def run_reference(args):
 def workload_config(n_gpus):
     return {"workload": "configs[1]: synthetic Illumina 150bp reads, %d reads per GPU (single sample), k=31, -b 2" % N_READS,
             "k": K, "b": B_THRESHOLD, "read_len": READ_LEN, "reads_per_gpu": N_READS, "batch_reads": BATCH_READS,
-            "variant": os.environ.get("MFKC_BENCH_VARIANT", "hash (region-blocked)"),
+            "variant": os.environ.get("MFKC_BENCH_VARIANT", "hash (bin-local)"),
             "parallelism": "1 GPU" if n_gpus == 1 else "hash-range sharded over %d GPUs, %s" % (n_gpus, "NCCL all-to-all + restage" if os.environ.get("MFKC_EXCHANGE") == "nccl" else "records drained straight from peer HBM over NVLink (CUDA IPC), no data-path collective"),
             "l2": "inputs (3 GB reads, multi-GB table) are far larger than the 126 MB L2; no explicit flush"}
 
@@ -267,7 +267,7 @@ def main():
     if m.load().mfkc_device_count() <= 0:
         raise SystemExit("bench.py needs a CUDA device (libmfkc has no CPU fallback)")
 
-    variant = {"sort": m.VARIANT_SORT, "direct": m.VARIANT_HASH_DIRECT}.get(os.environ.get("MFKC_BENCH_VARIANT", ""), m.VARIANT_HASH)
+    variant = {"sort": m.VARIANT_SORT, "direct": m.VARIANT_HASH_DIRECT, "table": m.VARIANT_HASH_TABLE}.get(os.environ.get("MFKC_BENCH_VARIANT", ""), m.VARIANT_HASH)
     kmers_ub = N_READS * (READ_LEN - K + 1)
     kc = m.KmerCounter(K, device=local_rank, variant=variant, expected_kmers=kmers_ub,
                        n_shards=world if world > 1 else 0, shard_id=rank if world > 1 else 0)
@@ -377,10 +377,10 @@ def main():
 
     # ---- roofline of the counting kernels (CUDA-event durations recorded around every launch)
     peak, peak_src = load_peaks()
-    count_kernels = {"hash (region-blocked)": ["extract_partition", "drain_regions"], "direct": ["extract_count"],
-                     "sort": ["extract_bucket", "radix_sort", "rle"]}[workload_config(1)["variant"]]
+    count_kernels = {"hash (bin-local)": ["extract_skm", "bin_count", "drain_heavy"], "table": ["extract_skm", "drain_skm"],
+                     "direct": ["extract_direct"], "sort": ["extract_keys", "radix_sort", "rle"]}[workload_config(1)["variant"]]
     if world > 1:
-        count_kernels = ["extract_bucket", "extract_partition", "drain_regions"]      # p2p: extract_bucket + drain_regions (NVLink reads inside)
+        count_kernels = ["extract_skm_shard", "extract_skm", "drain_skm"]      # p2p: extract_skm_shard + drain_skm (NVLink reads inside)
     t_count_ms = sum(prof[k][0] for k in count_kernels if k in prof) / args.steps
     launches = sum(v[1] for v in prof.values())
     achieved = ALGO_BYTES_PER_KMER * kmers_per_step / (t_count_ms / 1e3) / 1e9 if t_count_ms else None
@@ -429,7 +429,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "host_ingest": ingest,
-        "result": {"kmers_per_step_per_gpu": kmers_per_step, "distinct": st["distinct"], "records_gt_b": int(n_good),
+        "result": {"kmers_per_step_per_gpu": kmers_per_step, "distinct": st["distinct"], "records_gt_b": int(n_good), "bins": kc.bin_stats(),
                    "host_wall_ms_per_step": 1e3 * wall / args.steps},
     }
     print(json.dumps(line))

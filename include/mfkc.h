@@ -44,12 +44,18 @@ enum {
     MFKC_E_FORMAT = -8      /* malformed FASTA/FASTQ/.kmers.bin/components.bin, bad nucleotide */
 };
 
-/* HASH        = HBM-resident open-addressing table, region-blocked: keys are partitioned by table
- *               region and drained region by region so that every upsert hits L2 (default);
+/* HASH        = open-addressing hash counting, partitioned by minimizer (default).  k <= 31 on one GPU: the
+ *               sample's super-k-mer records are staged per minimizer BIN and every bin is counted by one
+ *               CTA in a SHARED-MEMORY table (records streamed in with TMA bulk copies), which emits
+ *               histogram + filtered (key,count) pairs directly; only bins that overflow go through the
+ *               HBM-resident table.  Samples that outgrow the staging buffer, k > 31 and sharded contexts
+ *               use HASH_TABLE's path;
+ * HASH_TABLE  = HBM-resident open-addressing table, region-blocked: keys are partitioned by table region
+ *               and drained region by region so that every upsert hits L2 (round 1's default);
  * SORT        = accumulate keys, radix sort, run-length encode;
  * HASH_DIRECT = the same table updated straight from the extraction kernel (one random DRAM
- *               sector per k-mer) -- kept as the measured baseline of the blocked design. */
-enum { MFKC_VARIANT_HASH = 0, MFKC_VARIANT_SORT = 1, MFKC_VARIANT_HASH_DIRECT = 2 };
+ *               sector per k-mer) -- kept as the measured baseline of the partitioned designs. */
+enum { MFKC_VARIANT_HASH = 0, MFKC_VARIANT_SORT = 1, MFKC_VARIANT_HASH_DIRECT = 2, MFKC_VARIANT_HASH_TABLE = 3 };
 
 #define MFKC_MAX_COUNT 32767        /* Short.MAX_VALUE: [itmo]/utils/NumUtils.java:21-26 */
 #define MFKC_HIST_BINS 32768        /* histogram index = count, 1..32767 */
@@ -63,11 +69,12 @@ typedef struct mfkc_cfg {
                                    32..63: 128-bit keys (extension, no reference behaviour) */
     int32_t  min_seq_len;       /* minSeqLen of IOUtils.loadReads (src/io/IOUtils.java:761); 0 for the counter */
     int32_t  device;            /* CUDA device ordinal */
-    int32_t  variant;           /* MFKC_VARIANT_HASH | MFKC_VARIANT_SORT | MFKC_VARIANT_HASH_DIRECT */
+    int32_t  variant;           /* MFKC_VARIANT_HASH | MFKC_VARIANT_SORT | MFKC_VARIANT_HASH_DIRECT | MFKC_VARIANT_HASH_TABLE */
     int32_t  n_shards;          /* hash-range sharding: number of key-space shards (GPUs); 0/1 = unsharded */
     int32_t  shard_id;          /* the shard this context owns */
     int32_t  reserved0;
-    uint64_t table_slots;       /* initial table capacity in slots; 0 = derive from expected_distinct / default */
+    uint64_t table_slots;       /* initial table capacity in slots; 0 = derive from expected_distinct / default.  Setting
+                                   table_slots, staging_bytes or region_shift pins the table geometry (HASH_TABLE's path) */
     uint64_t expected_distinct; /* sizing hint (distinct k-mers); 0 = unknown, table grows x2 on demand */
     uint64_t max_table_bytes;   /* growth limit; 0 = 80 % of free device memory */
     uint64_t staging_bytes;     /* HASH: key staging buffer; 0 = adaptive (starts at 4 batches, doubles when full) */
@@ -117,6 +124,11 @@ int  mfkc_stats(mfkc_ctx *ctx, uint64_t stats[6]);
 /* hist[c] = number of distinct k-mers with (saturated) count c, ALL entries
  * (QuickQuantitativeStatistics, src/io/IOUtils.java:59). */
 int  mfkc_histogram(mfkc_ctx *ctx, uint64_t hist[MFKC_HIST_BINS]);
+/* Diagnostics of MFKC_VARIANT_HASH's bin-local mode, valid after a result call (stats / histogram / emit_begin):
+ * out[0] = 1 if the current sample is counted bin-locally, 0 if it uses (or fell back to) the region-blocked table;
+ * [1] = bins, [2] = records per staging segment, [3] = heavy (bin, sub-range) entries counted through the table,
+ * [4] = their records, [5] = passes that were split, [6] = records in the overflow list, [7] = records staged. */
+int  mfkc_bin_stats(mfkc_ctx *ctx, uint64_t out[8]);
 /* Select entries with count > threshold (src/io/IOUtils.java:61), order them by ascending key;
  * *n_good = how many.  Also (re)computes the histogram. */
 int  mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_good);

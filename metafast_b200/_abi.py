@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("MFKC_LIBRARY") or os.path.join(_HERE, "lib", "libmfkc
 
 MFKC_OK = 0
 E_BADARG, E_CUDA, E_NCCL, E_TABLE_FULL, E_OOM, E_STATE, E_IO, E_FORMAT = -1, -2, -3, -4, -5, -6, -7, -8
-VARIANT_HASH, VARIANT_SORT, VARIANT_HASH_DIRECT = 0, 1, 2
+VARIANT_HASH, VARIANT_SORT, VARIANT_HASH_DIRECT, VARIANT_HASH_TABLE = 0, 1, 2, 3
 MAX_COUNT = 32767
 HIST_BINS = 32768
 
@@ -76,6 +76,7 @@ SIGNATURES = {
     "mfkc_submit_reads_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]),
     "mfkc_flush": (C.c_int, [C.c_void_p]),
     "mfkc_stats": (C.c_int, [C.c_void_p, u64p]),
+    "mfkc_bin_stats": (C.c_int, [C.c_void_p, u64p]),
     "mfkc_histogram": (C.c_int, [C.c_void_p, u64p]),
     "mfkc_emit_begin": (C.c_int, [C.c_void_p, C.c_int32, u64p]),
     "mfkc_emit_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -159,6 +159,12 @@ class KmerCounter(_Ctx):
         self._ck(self.lib.mfkc_stats(self.h, s))
         return dict(zip(("distinct", "kmers", "total_seq", "good_seq", "total_len", "good_len"), list(s)))
 
+    def bin_stats(self) -> dict:
+        """diagnostics of the bin-local mode (mfkc_bin_stats)"""
+        s = (C.c_uint64 * 8)()
+        self._ck(self.lib.mfkc_bin_stats(self.h, s))
+        return dict(zip(("bin_mode", "bins", "seg_cap", "heavy_entries", "heavy_recs", "split_passes", "overflow_recs", "staged_recs"), list(s)))
+
     def histogram(self) -> np.ndarray:
         h = np.zeros(_abi.HIST_BINS, dtype=np.uint64)
         self._ck(self.lib.mfkc_histogram(self.h, h.ctypes.data_as(_abi.u64p)))

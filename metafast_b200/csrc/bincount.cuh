@@ -1,0 +1,410 @@
+// bincount.cuh -- bin-local counting: the default counting kernels of MFKC_VARIANT_HASH for k <= 31.
+//
+// The extraction kernel files every super-k-mer record under the BIN of its minimizer (bin = a fixed
+// pseudo-random function of the canonical minimizer, hence of the canonical k-mer alone: every instance of a
+// k-mer lands in the same bin).  Bins are sized so that the distinct k-mers of one bin fit a hash table in
+// SHARED memory, so the count of a whole sample is
+//     for every bin (one CTA each, persistent CTAs fetch bins from an atomic counter):
+//         stream the bin's records into shared memory with TMA bulk copies (cp.async.bulk + mbarrier,
+//         one 512-byte copy per warp in flight), re-expand them into canonical k-mers, upsert them into
+//         the shared-memory table (LDS + ATOMS, no L2 round trip per k-mer), then sweep the table once:
+//         histogram, distinct count, compaction of the entries with count > threshold.
+// HBM sees the records once (2.7 B per k-mer instance) and the selected (key, count) pairs once: there is
+// no global table to clear, sweep or scan, and memory is 2.7 B per instance instead of 40-55 B per distinct
+// k-mer.  Replaces Long2ShortHashMap.addAndBound ([itmo]/structures/map/Long2ShortHashMap.java:119-157) and
+// the iteration + filter of IOUtils.printKmers (src/io/IOUtils.java:57-66) with identical results.
+//
+// Exactness under skew:
+//   * a bin whose records did not fit its staging segment (surplus in the overflow list) is HEAVY;
+//   * a (sub-)pass that fills the shared-memory table aborts without output and is split by key hash into
+//     2..32 sub-ranges that are counted one after the other (the records are re-read from L2); a sub-range
+//     that still does not fit at 32 parts is HEAVY;
+//   * heavy (bin, sub-range) entries and the overflow list are counted by drain_heavy_kernel /
+//     drain_ovf_kernel into the global table (the legacy path of kernels.cuh) and emitted by table_scan_kernel
+//     into the same output arrays.  A k-mer belongs to exactly one (bin, sub-range), so nothing is counted twice.
+#pragma once
+#include "kernels.cuh"
+
+namespace mfkc {
+
+constexpr int BC_LOG2S = 13;               // slots of the shared-memory table (8192 x (8 B key + 4 B count) = 96 KiB)
+constexpr int BC_THREADS = 512;            // 16 warps; 2 CTAs per SM
+constexpr int BC_HIST = 256;               // histogram bins kept in shared memory (higher counts: global atomics)
+constexpr int BC_MAX_SRC = P2P_MAX_PEERS;  // staging buffers one bin is gathered from (1 on one GPU, G with peer memory)
+constexpr uint32_t BC_MAXP = 32;           // most sub-ranges a bin is split into before it is declared heavy
+constexpr uint32_t BC_MAX_PROBE = 256;     // probes after which an upsert gives up (the pass aborts and is split)
+
+struct BinSrc {
+    const uint4 *recs[BC_MAX_SRC];             // source s: segment (seg0 + bin) of seg_cap records
+    const unsigned int *cursor[BC_MAX_SRC];    // records appended per segment (> seg_cap: the surplus is in the overflow list)
+    uint64_t seg_cap;
+    uint32_t n_src;
+    uint32_t seg0;                             // first segment of this shard in every source (shard * n_bins)
+    uint32_t rot;                              // source visited first (own GPU), spreads the NVLink load
+};
+struct HeavyEnt { uint32_t bin; uint16_t p, P; };             // keys of `bin` with (bc_hash & (P-1)) == p
+struct BinCtl {
+    unsigned int next_bin, n_heavy, heavy_overflow, n_split;     // per count pass (zeroed up to ovf_cursor before every pass)
+    unsigned long long heavy_recs, total_recs;
+    unsigned int ovf_cursor, pad0;                                // per sample: fill of the overflow list
+};
+struct BinCountArgs {
+    BinSrc src;
+    uint32_t n_bins;
+    int k;
+    uint32_t thr;                              // output entries with count > thr
+    uint32_t limit;                            // claimed slots at which a pass aborts (< 2^BC_LOG2S)
+    uint32_t max_recs;                         // bins with more records go straight to the heavy list
+    int use_tma;
+    unsigned long long *out_keys; uint16_t *out_counts; uint64_t out_cap;
+    unsigned long long *hist;
+    Counters *ctr;
+    BinCtl *ctl;
+    HeavyEnt *heavy; uint32_t heavy_cap;
+};
+
+// slot / sub-range hash of the shared-memory table: the top bits pick the slot, the low bits the sub-range
+__host__ __device__ __forceinline__ uint32_t bc_hash(uint64_t key) {
+    uint32_t h = (uint32_t)key * 0x9E3779B1u;
+    h ^= h >> 16;
+    h += (uint32_t)(key >> 32) * 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    return h ^ (h >> 16);
+}
+
+// ---- mbarrier / TMA bulk copy (PTX; SASS: SYNCS.*, UBLKCP) ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; spins++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 26)) asm volatile("trap;");         // a copy that never lands must not hang the device
+    }
+}
+
+template <int LOG2S, int NT>
+constexpr size_t bin_count_smem_bytes() {
+    return ((size_t)12 << LOG2S) + (size_t)(NT / 32) * (512 + 2 * 16 * 4) + BC_HIST * 4 + (size_t)(NT / 32) * 8 + (NT / 32) * 4 + 64 * 4 + 64;
+}
+
+template <int LOG2S, int NT>
+__global__ void __launch_bounds__(NT, 2)
+bin_count_kernel(const __grid_constant__ BinCountArgs a) {
+    constexpr uint32_t S = 1u << LOG2S, NW = NT / 32, U = S / NT;
+    constexpr uint32_t FULL = 0xffffffffu;
+    extern __shared__ __align__(128) uint8_t bc_smem[];
+    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(bc_smem);            // S x 8
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_keys + S);                               // S x 4
+    uint4 *s_ring = reinterpret_cast<uint4 *>(s_cnt + S);                                     // NW x 32 records (TMA destination)
+    uint32_t *s_w = reinterpret_cast<uint32_t *>(s_ring + NW * 32);                           // NW x 16: record-start bits
+    uint32_t *s_b = s_w + NW * 16;                                                            // NW x 16: records before word j
+    uint32_t *s_hist = s_b + NW * 16;                                                         // BC_HIST
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_hist + BC_HIST);     // NW mbarriers
+    uint32_t *s_wgood = reinterpret_cast<uint32_t *>(s_bar + NW);                             // NW
+    uint32_t *s_stack = s_wgood + NW;                                                         // 64 (p | P << 16)
+    uint32_t *s_ctl = s_stack + 64;                                                           // bin, sp, claimed, abort, done
+    volatile uint32_t *vs_ctl = s_ctl;
+    unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_ctl + 8);
+    enum { C_BIN = 0, C_SP, C_CLAIMED, C_ABORT, C_DONE };
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t lane_le = lanemask_lt() | (1u << lane);
+    const int rs = 64 - 2 * a.k;
+    for (uint32_t i = tid; i < S; i += NT) { s_keys[i] = EMPTY_KEY; s_cnt[i] = 0; }
+    for (uint32_t i = tid; i < BC_HIST; i += NT) s_hist[i] = 0;
+    const uint32_t bar = smem_u32(&s_bar[warp]);
+    const uint32_t ring = smem_u32(&s_ring[warp * 32]);
+    if (lane == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    uint32_t parity = 0;
+    unsigned long long occ_total = 0, recs_total = 0;
+
+    for (;;) {
+        if (tid == 0) s_ctl[C_BIN] = atomicAdd(&a.ctl->next_bin, 1u);
+        __syncthreads();
+        const uint32_t bin = vs_ctl[C_BIN];
+        if (bin >= a.n_bins) break;
+        // records of this bin in every source; a source whose segment overflowed makes the bin heavy
+        uint64_t n_recs = 0; bool light = true;
+        for (uint32_t s = 0; s < a.src.n_src; s++) {
+            const uint32_t c = a.src.cursor[s][a.src.seg0 + bin];
+            if (c > a.src.seg_cap) { light = false; n_recs += a.src.seg_cap; } else n_recs += c;
+        }
+        if (tid == 0) recs_total += n_recs;
+        if (n_recs == 0 && light) { __syncthreads(); continue; }
+        if (!light || n_recs > a.max_recs) {
+            if (tid == 0) {
+                const uint32_t i = atomicAdd(&a.ctl->n_heavy, 1u);
+                if (i < a.heavy_cap) { HeavyEnt e; e.bin = bin; e.p = 0; e.P = 1; a.heavy[i] = e; } else a.ctl->heavy_overflow = 1u;
+                atomicAdd(&a.ctl->heavy_recs, (unsigned long long)n_recs);
+            }
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0) { s_stack[0] = 0u | (1u << 16); s_ctl[C_SP] = 1; }
+        __syncthreads();
+
+        for (;;) {                                                   // sub-ranges of this bin, depth first
+            const uint32_t sp = vs_ctl[C_SP];
+            if (sp == 0) break;
+            const uint32_t item = s_stack[sp - 1];
+            __syncthreads();
+            if (tid == 0) { s_ctl[C_SP] = sp - 1; s_ctl[C_CLAIMED] = 0; s_ctl[C_ABORT] = 0; s_ctl[C_DONE] = 0; }
+            __syncthreads();
+            const uint32_t p = item & 0xFFFFu, P = item >> 16;
+            uint32_t n_batches_total = 0;
+
+            // ---- count pass: every warp takes batches of 32 records
+            for (uint32_t sj = 0; sj < a.src.n_src; sj++) {
+                const uint32_t s = (sj + a.src.rot) % a.src.n_src;
+                uint32_t n = a.src.cursor[s][a.src.seg0 + bin];
+                if (n > a.src.seg_cap) n = (uint32_t)a.src.seg_cap;
+                const uint4 *__restrict__ recs = a.src.recs[s] + (uint64_t)(a.src.seg0 + bin) * a.src.seg_cap;
+                const uint32_t nb = (n + 31) >> 5;
+                n_batches_total += nb;
+                uint32_t b = warp;
+                bool inflight = false;
+                uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+                if (b < nb) {
+                    if (a.use_tma) {
+                        if (lane == 0) {
+                            const uint32_t bytes = min(32u, n - b * 32) * 16u;
+                            mbar_expect_tx(bar, bytes);
+                            bulk_g2s(ring, recs + (size_t)b * 32, bytes, bar);
+                        }
+                        inflight = true;
+                    } else if (b * 32 + lane < n) nxt = ld_nc_u128(&recs[b * 32 + lane]);
+                }
+                for (; b < nb; b += NW) {
+                    const uint32_t ab = __shfl_sync(FULL, lane == 0 ? vs_ctl[C_ABORT] : 0u, 0);
+                    if (ab) break;
+                    const uint32_t cnt = min(32u, n - b * 32);
+                    uint4 r;
+                    const uint32_t b2 = b + NW;
+                    if (a.use_tma) {
+                        mbar_wait(bar, parity); parity ^= 1u; inflight = false;
+                        r = lane < cnt ? s_ring[warp * 32 + lane] : make_uint4(0u, 0u, 0u, 0u);
+                        __syncwarp();
+                        if (b2 < nb) {                               // the ring is free again: next copy flies during the expansion
+                            if (lane == 0) {
+                                const uint32_t bytes = min(32u, n - b2 * 32) * 16u;
+                                mbar_expect_tx(bar, bytes);
+                                bulk_g2s(ring, recs + (size_t)b2 * 32, bytes, bar);
+                            }
+                            inflight = true;
+                        }
+                    } else {
+                        r = nxt;
+                        if (b2 < nb && b2 * 32 + lane < n) nxt = ld_nc_u128(&recs[b2 * 32 + lane]);
+                    }
+                    const uint32_t len = lane < cnt ? (r.z & 15u) + 1u : 0u;
+                    uint32_t incl = len;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += v; }
+                    const uint32_t excl = incl - len;
+                    const uint32_t total = __shfl_sync(FULL, incl, 31);          // <= 512 instances
+                    // instance t belongs to the record whose start bit is the last one at or before t
+                    if (lane < 16) s_w[warp * 16 + lane] = 0u;
+                    __syncwarp();
+                    if (len) atomicOr(&s_w[warp * 16 + (excl >> 5)], 1u << (excl & 31));
+                    __syncwarp();
+                    {
+                        const uint32_t pc = lane < 16 ? __popc(s_w[warp * 16 + lane]) : 0u;
+                        uint32_t ip = pc;
+#pragma unroll
+                        for (int o = 1; o < 16; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, ip, o); if (lane >= (uint32_t)o) ip += v; }
+                        if (lane < 16) s_b[warp * 16 + lane] = ip - pc;
+                    }
+                    __syncwarp();
+                    uint32_t wclaimed = 0;
+                    for (uint32_t t0 = 0, j = 0; t0 < total; t0 += 32, j++) {
+                        const uint32_t t = t0 + lane;
+                        const uint32_t w = s_w[warp * 16 + j], bs = s_b[warp * 16 + j];
+                        const uint32_t lo = (bs + __popc(w & lane_le) - 1u) & 31u;
+                        const uint32_t qx = __shfl_sync(FULL, r.x, lo), qy = __shfl_sync(FULL, r.y, lo), qz = __shfl_sync(FULL, r.z, lo);
+                        const uint32_t qs = __shfl_sync(FULL, excl, lo);
+                        bool claimed_now = false;
+                        if (t < total) {
+                            const uint32_t off = 2u * (t - qs);
+                            const uint32_t w2 = qz & ~15u;
+                            const uint32_t h32 = __funnelshift_l(qy, qx, off);
+                            const uint32_t l32 = __funnelshift_l(w2, qy, off);
+                            const uint64_t fw = (((uint64_t)h32 << 32) | l32) >> rs;
+                            const uint64_t rc = revcomp64(fw, a.k);
+                            const unsigned long long key = fw < rc ? fw : rc;
+                            const uint32_t h = bc_hash(key);
+                            if ((h & (P - 1u)) == p) {
+                                uint32_t slot = h >> (32 - LOG2S);
+                                uint32_t probe = 0;
+                                for (;; probe++) {
+                                    const unsigned long long cur = s_keys[slot];
+                                    if (cur == key) { atomicAdd(&s_cnt[slot], 1u); break; }
+                                    if (cur == EMPTY_KEY) {
+                                        const unsigned long long prev = atomicCAS(&s_keys[slot], EMPTY_KEY, key);
+                                        if (prev == EMPTY_KEY) { atomicAdd(&s_cnt[slot], 1u); claimed_now = true; break; }
+                                        if (prev == key) { atomicAdd(&s_cnt[slot], 1u); break; }
+                                    }
+                                    if (probe >= BC_MAX_PROBE) { s_ctl[C_ABORT] = 1u; break; }      // pass is void; it will be split
+                                    slot = (slot + 1u) & (S - 1u);
+                                }
+                            }
+                        }
+                        wclaimed += __popc(__ballot_sync(FULL, claimed_now));
+                    }
+                    if (lane == 0) {
+                        if (wclaimed) { const uint32_t tot = atomicAdd(&s_ctl[C_CLAIMED], wclaimed) + wclaimed; if (tot > a.limit) s_ctl[C_ABORT] = 1u; }
+                        atomicAdd(&s_ctl[C_DONE], 1u);
+                    }
+                    __syncwarp();
+                }
+                if (inflight) { mbar_wait(bar, parity); parity ^= 1u; }       // a copy issued for a batch this warp no longer takes
+                __syncwarp();
+            }
+            __syncthreads();
+
+            if (vs_ctl[C_ABORT]) {
+                // the table filled up: forget this pass, split the sub-range by the next hash bits
+                for (uint32_t i = tid; i < S; i += NT) { s_keys[i] = EMPTY_KEY; s_cnt[i] = 0; }
+                if (tid == 0) {
+                    // batches done when the limit was hit -> how many parts the sub-range needs (x1.5 margin)
+                    const uint32_t done = max(1u, s_ctl[C_DONE]);
+                    uint32_t F = 2;
+                    while (F < BC_MAXP && (uint64_t)F * done * 2 < (uint64_t)n_batches_total * 3) F <<= 1;
+                    while (P * F > BC_MAXP && F > 1) F >>= 1;
+                    if (F < 2) {
+                        const uint32_t i = atomicAdd(&a.ctl->n_heavy, 1u);
+                        if (i < a.heavy_cap) { HeavyEnt e; e.bin = bin; e.p = (uint16_t)p; e.P = (uint16_t)P; a.heavy[i] = e; } else a.ctl->heavy_overflow = 1u;
+                        atomicAdd(&a.ctl->heavy_recs, (unsigned long long)n_recs);
+                    } else {
+                        uint32_t spn = s_ctl[C_SP];
+                        for (uint32_t i = 0; i < F; i++) s_stack[spn++] = (p + i * P) | ((P * F) << 16);
+                        s_ctl[C_SP] = spn;
+                        atomicAdd(&a.ctl->n_split, 1u);
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
+
+            // ---- sweep: histogram of all entries, compaction of count > thr, clear for the next pass
+            uint32_t good_mask = 0, n_occ = 0, h1 = 0, h2 = 0;
+#pragma unroll
+            for (uint32_t u = 0; u < U; u++) {
+                const uint32_t slot = u * NT + tid;
+                const bool occ = s_keys[slot] != EMPTY_KEY;
+                const uint32_t c = s_cnt[slot];
+                const uint32_t cc = c < MAX_COUNT ? c : MAX_COUNT;
+                n_occ += occ ? 1u : 0u;
+                h1 += __popc(__ballot_sync(FULL, occ && cc == 1u));
+                h2 += __popc(__ballot_sync(FULL, occ && cc == 2u));
+                if (occ && cc > 2u) { if (cc < (uint32_t)BC_HIST) atomicAdd(&s_hist[cc], 1u); else atomicAdd(&a.hist[cc], 1ULL); }
+                if (occ && cc > a.thr) good_mask |= 1u << u;
+            }
+            if (lane == 0) { if (h1) atomicAdd(&s_hist[1], h1); if (h2) atomicAdd(&s_hist[2], h2); }
+            occ_total += n_occ;
+            const uint32_t mine = __popc(good_mask);
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += v; }
+            if (lane == 31) s_wgood[warp] = incl;
+            __syncthreads();
+            uint32_t before = 0, total_good = 0;
+#pragma unroll
+            for (uint32_t wv = 0; wv < NW; wv++) { const uint32_t c = s_wgood[wv]; if (wv < warp) before += c; total_good += c; }
+            if (tid == 0 && total_good) *s_base = atomicAdd(&a.ctr->n_good, (unsigned long long)total_good);
+            __syncthreads();
+            uint64_t at = total_good ? *s_base + before + incl - mine : 0;
+#pragma unroll
+            for (uint32_t u = 0; u < U; u++) {
+                const uint32_t slot = u * NT + tid;
+                if ((good_mask >> u) & 1u) {
+                    if (at < a.out_cap) {
+                        const uint32_t c = s_cnt[slot];
+                        a.out_keys[at] = s_keys[slot];
+                        a.out_counts[at] = (uint16_t)(c < MAX_COUNT ? c : MAX_COUNT);
+                    }
+                    at++;
+                }
+                s_keys[slot] = EMPTY_KEY; s_cnt[slot] = 0;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < BC_HIST; i += NT) if (s_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)s_hist[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) occ_total += __shfl_xor_sync(FULL, occ_total, o);
+    if (lane == 0 && occ_total) atomicAdd(&a.ctr->bc_distinct, occ_total);
+    if (tid == 0 && recs_total) atomicAdd(&a.ctl->total_recs, recs_total);
+}
+
+// ------------------------------------------------------------------------------------------
+// Heavy (bin, sub-range) entries and the overflow list: counted into the global table.  Placement is a
+// function of the key alone (TableGeom: plain hash for the residual table of a bin-local count, the
+// minimizer regions when a sample falls back to the region-blocked table for good).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+drain_heavy_kernel(BinSrc src, const HeavyEnt *__restrict__ heavy, uint32_t n_heavy, uint32_t blocks_per_ent, int k,
+                   Slot *__restrict__ tab, TableGeom g, Counters *__restrict__ ctr) {
+    __shared__ uint4 s_rec[8][32];
+    __shared__ uint32_t s_pre[8][33];
+    const uint32_t e = blockIdx.x / blocks_per_ent, sub = blockIdx.x % blocks_per_ent;
+    if (e >= n_heavy) return;
+    const HeavyEnt ent = heavy[e];
+    const uint32_t p = ent.p, P = ent.P;
+    uint32_t claimed = 0;
+    for (uint32_t sj = 0; sj < src.n_src; sj++) {
+        const uint32_t s = (sj + src.rot) % src.n_src;
+        uint64_t n = src.cursor[s][src.seg0 + ent.bin];
+        if (n > src.seg_cap) n = src.seg_cap;
+        skm_expand_records(src.recs[s] + (uint64_t)(src.seg0 + ent.bin) * src.seg_cap, n, (uint64_t)sub * 256, (uint64_t)blocks_per_ent * 256, k, s_rec, s_pre,
+                           [&](uint64_t key, uint32_t) {
+                               if (P > 1 && (bc_hash(key) & (P - 1u)) != p) return;
+                               claimed += placed_upsert_at<true>(tab, g.cap, g.region_shift, g.minimizer ? g.win : 0u, geom_home(g, key), key, 1u) ? 1u : 0u;
+                           });
+    }
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+}
+
+// every bin of the shard as a heavy entry (a sample that leaves the bin-local mode drains all its bins into the table)
+__global__ void __launch_bounds__(256)
+heavy_all_bins_kernel(HeavyEnt *__restrict__ heavy, uint32_t n_bins) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bins; i += gridDim.x * blockDim.x) { HeavyEnt e; e.bin = i; e.p = 0; e.P = 1; heavy[i] = e; }
+}
+
+// overflow list: records that found their segment full.  With n_shards > 1 the list of a peer holds records of every
+// owner; `me` keeps the ones whose minimizer belongs to this shard (the record carries its minimizer hash in w).
+__global__ void __launch_bounds__(256)
+drain_ovf_kernel(const uint4 *__restrict__ ovf, const unsigned int *__restrict__ ovf_cursor, uint32_t ovf_cap, uint32_t n_shards, uint32_t me, int k,
+                 Slot *__restrict__ tab, TableGeom g, Counters *__restrict__ ctr) {
+    __shared__ uint4 s_rec[8][32];
+    __shared__ uint32_t s_pre[8][33];
+    uint64_t n = *ovf_cursor;
+    if (n > ovf_cap) n = ovf_cap;
+    uint32_t claimed = 0;
+    skm_expand_records(ovf, n, (uint64_t)blockIdx.x * 256, (uint64_t)gridDim.x * 256, k, s_rec, s_pre,
+                       [&](uint64_t key, uint32_t mh) {
+                           if (n_shards > 1 && owner_of_minhash(mh, n_shards) != me) return;
+                           claimed += placed_upsert_at<true>(tab, g.cap, g.region_shift, g.minimizer ? g.win : 0u, geom_home(g, key), key, 1u) ? 1u : 0u;
+                       });
+    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
+    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
+}
+
+}  // namespace mfkc

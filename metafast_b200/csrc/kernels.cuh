@@ -29,7 +29,8 @@ struct Counters {
     unsigned long long appended;      // sort variant / bucketing: keys written
     unsigned long long overflow;      // appended past capacity (keys dropped -> error)
     unsigned long long n_good;        // compaction cursor
-    unsigned long long pad[6];
+    unsigned long long bc_distinct;   // bin-local counting: distinct k-mers counted in shared memory (bincount.cuh)
+    unsigned long long pad[5];
 };
 
 // ------------------------------------------------------------------------------------------
@@ -829,6 +830,8 @@ struct SkmStage {
     uint32_t n_regions;
     int region_shift;
     uint32_t win;                 // primary window of the windowed placement (0 = plain linear probing), see placed_upsert_at
+    // MODE 3 (bin-local counting): records that find their bin's segment full go to this list instead
+    uint4 *ovf; unsigned int *ovf_cursor; uint32_t ovf_cap;
 };
 
 __device__ __forceinline__ uint32_t kmers_of_word(uint32_t w0, uint32_t w1, uint32_t w2, uint64_t flag_bits,
@@ -924,6 +927,10 @@ __device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32
 //         drains these segments straight from this GPU's memory, see drain_p2p_kernel).
 //         st.n_regions = number of shards, st.region_shift = log2(coarse buckets per shard);
 //         kmer_count[owner] as in mode 1 (warp-aggregated: 8 hot addresses would serialise in L2).
+// MODE 3: bucket = minimizer BIN of the bin-local count (bincount.cuh); st.n_regions = number of bins.  A full segment
+//         sends the record to the overflow list (st.ovf); only when that is full too the record is dropped and reported.
+// MODE 4: like 3 with shards: bucket = owner * bins_per_shard + bin (st.n_regions = shards, st.region_shift unused,
+//         st.win = bins per shard); kmer_count[owner] as in mode 2.
 __host__ __device__ __forceinline__ uint32_t coarse_of_minhash(uint32_t mh, int log2_buckets) {
     return log2_buckets ? region_hash(mh) >> (32 - log2_buckets) : 0u;              // monotone in the region index
 }
@@ -965,16 +972,19 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                 // the whole record from that one hash, under a table geometry the sender does not know.
                 // Two passes over the same state machine: pass 1 issues every cursor atomic of the
                 // thread back to back (their ~1 us round trips overlap), pass 2 writes the records.
-                constexpr bool BY_OWNER = MODE != 0;
+                constexpr bool BY_OWNER = MODE == 1 || MODE == 2;
                 auto bucket_of = [&](uint32_t mhv, uint32_t key) {
-                    if (MODE == 0) return key;
+                    if (MODE == 0 || MODE == 3 || MODE == 4) return key;
                     const uint32_t o = owner_of_minhash(mhv, st.n_regions);
                     return MODE == 1 ? o : ((o << st.region_shift) | coarse_of_minhash(mhv, st.region_shift));
                 };
                 const uint32_t seg32 = (uint32_t)st.seg_cap;
                 uint32_t rkey[16];                                  // run key of every start position, computed once
 #pragma unroll
-                for (int j = 0; j < 16; j++) rkey[j] = BY_OWNER ? mh[j] : region_of_minhash(mh[j], st.n_regions);
+                for (int j = 0; j < 16; j++)
+                    rkey[j] = BY_OWNER ? mh[j]
+                            : (MODE == 4 ? owner_of_minhash(mh[j], st.n_regions) * st.win + region_of_minhash(mh[j], st.win)
+                                         : region_of_minhash(mh[j], st.n_regions));
                 uint32_t pos[17];
                 {
                     uint32_t run_key = 0, run_mh = 0;
@@ -1008,13 +1018,23 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                             const uint32_t bucket = bucket_of(run_mh, run_key);
                             if (pos[j] < seg32) {
                                 // local staging holds < 2^32 records (reserve_staging caps it): 32-bit index arithmetic
-                                if (MODE == 0) st.recs[bucket * seg32 + pos[j]] = rec; else st.recs[(uint64_t)bucket * seg32 + pos[j]] = rec;
+                                if (MODE == 0) st.recs[bucket * seg32 + pos[j]] = rec; else st.recs[(uint64_t)bucket * seg32 + pos[j]] = rec;   // MODE 0: < 2^32 records
                                 if (MODE == 1) atomicAdd(&kmer_count[bucket], (unsigned long long)len);
-                                if (MODE == 2) {
-                                    const uint32_t o = bucket >> st.region_shift;
+                                if (MODE == 2 || MODE == 4) {
+                                    const uint32_t o = MODE == 4 ? bucket / st.win : bucket >> st.region_shift;
                                     if (st.n_regions <= 8) { if (o < 4) km_lo += (unsigned long long)len << (16 * o); else km_hi += (unsigned long long)len << (16 * (o - 4)); }
                                     else atomicAdd(&kmer_count[o], (unsigned long long)len);
                                 }
+                            } else if (MODE == 3 || MODE == 4) {    // segment full: overflow list (counted through the table later)
+                                const uint32_t o = atomicAdd(st.ovf_cursor, 1u);
+                                if (o < st.ovf_cap) {
+                                    st.ovf[o] = rec;
+                                    if (MODE == 4) {
+                                        const uint32_t ow = bucket / st.win;
+                                        if (st.n_regions <= 8) { if (ow < 4) km_lo += (unsigned long long)len << (16 * ow); else km_hi += (unsigned long long)len << (16 * (ow - 4)); }
+                                        else atomicAdd(&kmer_count[ow], (unsigned long long)len);
+                                    }
+                                } else dropped++;
                             } else if (!BY_OWNER) {                 // segment full: count the run directly (slow, exact)
                                 claimed += skm_count_direct(rec, bucket, st.region_shift, st.win, k, tb);
                             } else if (MODE == 2) dropped++;        // reported as an error by mfkc_flush (segments are sized with 2x slack)
@@ -1025,7 +1045,7 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                 }
             }
         }
-        if (MODE == 2 && st.n_regions <= 8) {                   // one atomic per (warp, owner) and tile
+        if ((MODE == 2 || MODE == 4) && st.n_regions <= 8) {    // one atomic per (warp, owner) and tile
 #pragma unroll
             for (int o = 16; o; o >>= 1) { km_lo += __shfl_xor_sync(0xffffffffu, km_lo, o); km_hi += __shfl_xor_sync(0xffffffffu, km_hi, o); }
             const uint32_t l = lane_id();
@@ -1039,7 +1059,7 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if (lane_id() == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
     if (__any_sync(0xffffffffu, bad != 0) && lane_id() == 0) atomicAdd(&ctr->bad_chars, 1ULL);
-    if (MODE == 2 && dropped) atomicAdd(&ctr->overflow, (unsigned long long)dropped);
+    if ((MODE == 2 || MODE == 3 || MODE == 4) && dropped) atomicAdd(&ctr->overflow, (unsigned long long)dropped);
 }
 
 // Send side for up to 8 owner shards with block-level aggregation.  With only G <= 8 destination

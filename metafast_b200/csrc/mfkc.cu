@@ -11,6 +11,7 @@
 
 #include "../../include/mfkc.h"
 #include "kernels.cuh"
+#include "bincount.cuh"
 #include "kernels128.cuh"
 #include "radix_sort.cuh"
 #include "kset.cuh"
@@ -25,12 +26,14 @@ using namespace mfkc;
 // ------------------------------------------------------------------------------------------
 enum ProfSlot {
     P_MARK = 0, P_EXTRACT_COUNT, P_EXTRACT_PARTITION, P_DRAIN, P_EXTRACT_BUCKET, P_COUNT_KEYS, P_REHASH, P_CLEAR, P_HIST, P_COMPACT,
-    P_SORT, P_RECORDS, P_RLE, P_FC_BUILD, P_FC_RECORDS, P_FC_READS, P_FC_FEATURES, P_GUPS, P_SYNTH, P_NSLOTS
+    P_SORT, P_RECORDS, P_RLE, P_FC_BUILD, P_FC_RECORDS, P_FC_READS, P_FC_FEATURES, P_GUPS, P_SYNTH, P_BIN_COUNT, P_DRAIN_HEAVY, P_EXTRACT_KEYS, P_NSLOTS
 };
+// slot names = the kernels they time (extract_skm: extract_skm_kernel<0|3>, extract_skm_shard: <1|2|4> and owner8;
+// drain_skm: drain_skm_kernel / drain_p2p_kernel / drain_regions_kernel of the region-blocked table)
 static const char *kProfNames[P_NSLOTS] = {
-    "mark_read_ends", "extract_count", "extract_partition", "drain_regions", "extract_bucket", "count_keys", "rehash", "table_clear", "table_hist",
-    "table_compact", "radix_sort", "records", "rle", "fc_build", "fc_records", "fc_reads", "fc_features",
-    "gups", "synth"};
+    "mark_read_ends", "extract_direct", "extract_skm", "drain_skm", "extract_skm_shard", "count_keys", "rehash", "table_clear", "table_hist",
+    "table_scan", "radix_sort", "records", "rle", "fc_build", "fc_records", "fc_reads", "fc_features",
+    "gups", "synth", "bin_count", "drain_heavy", "extract_keys"};
 
 struct PendingTiming { int slot; cudaEvent_t a, b; };
 
@@ -66,6 +69,8 @@ struct mfkc_ctx {
     uint64_t kmers_since_drain = 0; uint32_t drains_since_clear = 0;
     bool host_fed = false;            // the current sample arrives through mfkc_submit_reads (host buffers)
     uint64_t prev_sample_kmers = 0;   // k-mer instances of the previous sample of this context (drain cadence without hints)
+    uint64_t prev_sample_kmers_exact = 0;
+    bool tab_clean = true;            // no key has been put into the table since it was last cleared
     uint64_t distinct_ub = 0;          // host-side upper bound of occupied slots
     uint64_t kmers_ub_total = 0;       // cumulative upper bound of submitted k-mer instances
     uint64_t max_table_bytes = 0;
@@ -83,6 +88,22 @@ struct mfkc_ctx {
     // tight bound for the region-blocked variant: exact values at the last synchronisation point
     uint64_t distinct_base = 0, kmers_base = 0, recv_since_base = 0;
     unsigned long long *h_drain_snap = nullptr;
+
+    // bin-local counting (bincount.cuh): the default mode of MFKC_VARIANT_HASH for k <= 31 on one GPU.  A sample is staged
+    // as a whole, bin by bin, and counted in shared memory when its results are asked for; the global table only takes the
+    // heavy bins.  A sample that outgrows the staging buffer falls back to the region-blocked table for good (mode 0).
+    int mode = 0;                      // 0: region-blocked table, 1: bin-local
+    bool bins_ok = false;              // the context may use mode 1 (variant, k, no explicit table geometry, unsharded)
+    bool sample_open = false;          // a batch was submitted since the last reset
+    uint32_t os_n_bins = 0; uint64_t os_seg_cap = 0, os_ovf_cap = 0;
+    uint64_t os_kmers_budget = 0, os_kmers_staged = 0;
+    double os_R = 0, os_rpk = 0;       // previous sample: k-mer instances per distinct k-mer, records per k-mer instance
+    double os_good_frac = 0;           // previous count: selected entries per distinct k-mer
+    BinCtl *d_binctl = nullptr, *h_binctl = nullptr;
+    HeavyEnt *d_heavy = nullptr; uint32_t heavy_cap = 0;
+    bool os_counted = false; uint32_t os_thr = 0;             // results of the last count are valid for threshold os_thr
+    unsigned long long *os_keys = nullptr; uint16_t *os_counts = nullptr; uint64_t os_n_good = 0;
+    uint64_t os_heavy_bins = 0, os_heavy_recs = 0, os_splits = 0, os_ovf = 0, os_total_recs = 0;      // diagnostics of the last count
 
     // peer-memory shard exchange
     uint4 *p2p_recs = nullptr; unsigned int *p2p_cursor = nullptr; unsigned long long *p2p_kc = nullptr;
@@ -265,16 +286,18 @@ static int table_alloc(mfkc_ctx *ctx, uint64_t slots, Slot **out, bool plain_aos
     *out = t;
     return MFKC_OK;
 }
+static void table_touched(mfkc_ctx *ctx) { ctx->tab_clean = false; }
 
 extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     if (!cfg || !out) { g_create_err = "null argument"; return MFKC_E_BADARG; }
     if (cfg->struct_size != sizeof(mfkc_cfg)) { g_create_err = "mfkc_cfg.struct_size mismatch"; return MFKC_E_BADARG; }
     if (cfg->k <= 0) { g_create_err = "The size of k-mer must be at least 1."; return MFKC_E_BADARG; }        // KmersCounterMain.java:66-69
     if (cfg->k > 63) { g_create_err = "The size of k-mer must be no more than 63 (31 in the reference)."; return MFKC_E_BADARG; }
-    if (cfg->k > 31 && cfg->variant != MFKC_VARIANT_HASH) {        // the reference stops at 31 (KmersCounterMain.java:70-73)
+    if (cfg->k > 31 && cfg->variant != MFKC_VARIANT_HASH && cfg->variant != MFKC_VARIANT_HASH_TABLE) {        // the reference stops at 31 (KmersCounterMain.java:70-73)
         g_create_err = "k > 31 (128-bit keys) is only available with MFKC_VARIANT_HASH"; return MFKC_E_BADARG;
     }
-    if (cfg->variant != MFKC_VARIANT_HASH && cfg->variant != MFKC_VARIANT_SORT && cfg->variant != MFKC_VARIANT_HASH_DIRECT) {
+    if (cfg->variant != MFKC_VARIANT_HASH && cfg->variant != MFKC_VARIANT_SORT && cfg->variant != MFKC_VARIANT_HASH_DIRECT &&
+        cfg->variant != MFKC_VARIANT_HASH_TABLE) {
         g_create_err = "unknown variant"; return MFKC_E_BADARG;
     }
     if (cfg->region_shift && (cfg->region_shift < 4 || cfg->region_shift > 30)) { g_create_err = "bad region_shift"; return MFKC_E_BADARG; }
@@ -288,6 +311,9 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     mfkc_ctx *ctx = new mfkc_ctx();
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
+    const bool force_table = cfg->variant == MFKC_VARIANT_HASH_TABLE;      // the region-blocked table for everything
+    if (force_table) ctx->cfg.variant = MFKC_VARIANT_HASH;
+    cfg = &ctx->cfg;
     auto bail = [&](int code) { g_create_err = ctx->err; mfkc_destroy(ctx); return code; };
 #define CR_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return bail(MFKC_E_CUDA); } } while (0)
     CR_TRY(cudaSetDevice(ctx->device));
@@ -319,6 +345,9 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     CR_TRY(cudaMallocHost(&ctx->h_bucket, 64 * sizeof(uint64_t)));
     CR_TRY(cudaMemset(ctx->d_bucket_cursor, 0, 64 * sizeof(unsigned long long)));
     CR_TRY(cudaMemset(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t)));
+    CR_TRY(cudaMalloc(&ctx->d_binctl, sizeof(BinCtl)));
+    CR_TRY(cudaMemset(ctx->d_binctl, 0, sizeof(BinCtl)));
+    CR_TRY(cudaMallocHost(&ctx->h_binctl, sizeof(BinCtl)));
 
     {   // random 16-byte slot probes: do not let L2 promote a missing sector to a 64/128-byte DRAM fetch
         const char *g = getenv("MFKC_L2_FETCH");
@@ -349,10 +378,18 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
         { const char *dm = getenv("MFKC_DRAIN");
           ctx->smem_drain = ctx->place == 1 && !ctx->k128 && !ctx->soa && dm && !strcmp(dm, "smem") &&
                             (cfg->region_shift == 0 || (int)cfg->region_shift <= SMEM_MAX_SHIFT); }
+        // bin-local counting (bincount.cuh) unless the caller pinned the table geometry or asked for the table variant
+        static const int env_bins = getenv("MFKC_BINS") ? atoi(getenv("MFKC_BINS")) : 1;
+        ctx->bins_ok = env_bins && !force_table && ctx->place == 1 && !ctx->k128 && !ctx->soa && !ctx->smem_drain &&
+                       cfg->table_slots == 0 && cfg->staging_bytes == 0 && cfg->region_shift == 0 && cfg->n_shards <= 1;
+        if (ctx->bins_ok)
+            CR_TRY(cudaFuncSetAttribute(bin_count_kernel<BC_LOG2S, BC_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)bin_count_smem_bytes<BC_LOG2S, BC_THREADS>()));
     }
     if (cfg->variant != MFKC_VARIANT_SORT) {
         uint64_t slots = cfg->table_slots;
         if (!slots && cfg->expected_distinct) slots = cfg->expected_distinct * 2;      // load 0.5
+        if (!slots && ctx->bins_ok) slots = 1ull << 20;                               // only heavy bins reach the table
         if (!slots && cfg->expected_kmers && cfg->variant == MFKC_VARIANT_HASH)
             slots = std::min<uint64_t>((uint64_t)(cfg->expected_kmers / 0.85) + 1024, (uint64_t)(total_b * 0.35) / slot_bytes(ctx));
         if (!slots) slots = 1ull << 22;                                                // 64 MiB, grows on demand
@@ -381,6 +418,10 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
     return MFKC_OK;
 }
 
+static void free_bin_outputs(mfkc_ctx *ctx) {
+    TMP_FREE(ctx->os_keys); TMP_FREE(ctx->os_counts);
+    ctx->os_keys = nullptr; ctx->os_counts = nullptr;
+}
 static void free_emit(mfkc_ctx *ctx) {
     TMP_FREE(ctx->em_keys); TMP_FREE(ctx->em_counts); TMP_FREE(ctx->em_records);
     ctx->em_keys = nullptr; ctx->em_counts = nullptr; ctx->em_records = nullptr;
@@ -419,6 +460,8 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     cudaFree(ctx->d_synth);
     if (ctx->ev_drain) cudaEventDestroy(ctx->ev_drain);
     if (ctx->h_drain_snap) cudaFreeHost(ctx->h_drain_snap);
+    cudaFree(ctx->d_binctl); cudaFree(ctx->d_heavy);
+    if (ctx->h_binctl) cudaFreeHost(ctx->h_binctl);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     for (void *p : ctx->pinned) cudaFreeHost(p);
@@ -430,10 +473,18 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
 // A denser table is not only smaller to clear and scan: the region-blocked drain touches fewer sectors per
 // k-mer and keeps a higher L2 hit rate.
 static int resize_for_next_sample(mfkc_ctx *ctx) {
-    if (ctx->cfg.variant == MFKC_VARIANT_SORT || ctx->cfg.table_slots || !ctx->tab) return MFKC_OK;
+    if (ctx->cfg.variant == MFKC_VARIANT_SORT || !ctx->tab) return MFKC_OK;
+    if (read_counters(ctx) != MFKC_OK) return MFKC_OK;
+    if (ctx->h_ctr->kmers) ctx->prev_sample_kmers_exact = ctx->h_ctr->kmers;
+    if (ctx->mode == 1 && ctx->os_counted && ctx->h_ctr->kmers) {
+        // what the bins of the next sample are planned with: instances per distinct k-mer, records per instance
+        const uint64_t distinct = ctx->h_ctr->distinct + ctx->h_ctr->bc_distinct;
+        ctx->os_R = (double)ctx->h_ctr->kmers / (double)std::max<uint64_t>(distinct, 1);
+        ctx->os_rpk = (double)(ctx->os_total_recs + ctx->os_ovf) / (double)ctx->h_ctr->kmers;
+    }
+    if (ctx->bins_ok || ctx->cfg.table_slots) return MFKC_OK;          // the table only takes heavy bins: keep it as it is
     static const bool off = getenv("MFKC_NO_RESIZE") != nullptr;
     if (off) return MFKC_OK;
-    if (read_counters(ctx) != MFKC_OK) return MFKC_OK;
     const uint64_t distinct = ctx->h_ctr->distinct;
     if (distinct < (1u << 20)) return MFKC_OK;
     // load 0.4 for device-resident input; host-fed samples get more room (load 0.29): their drains are asynchronous and
@@ -467,14 +518,18 @@ extern "C" int mfkc_reset(mfkc_ctx *ctx) {
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(sync_all(ctx));
     TRY(resize_for_next_sample(ctx));
-    if (ctx->tab) {
+    if (ctx->tab && !ctx->tab_clean) {
         ProfScope ps(ctx, P_CLEAR, ctx->compute);
         if (ctx->k128) table128_clear_kernel<<<grid_for(ctx, 2 * ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab128, ctx->cap);
         else if (ctx->soa) {
             CU_TRY(cudaMemsetAsync(ctx->tab, 0xFF, ctx->cap * 8, ctx->compute));
             CU_TRY(cudaMemsetAsync(tab_soa(ctx).counts, 0, ctx->cap * 4, ctx->compute));
         } else table_clear_kernel<<<grid_for(ctx, ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap);
+        ctx->tab_clean = true;
     }
+    ctx->sample_open = false; ctx->os_counted = false; ctx->os_kmers_staged = 0;
+    free_bin_outputs(ctx);
+    CU_TRY(cudaMemsetAsync(ctx->d_binctl, 0, sizeof(BinCtl), ctx->compute));
     ctx->kmers_since_drain = 0; ctx->drains_since_clear = 0;
     if (ctx->kmers_ub_total) ctx->prev_sample_kmers = ctx->kmers_ub_total;
     CU_TRY(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->compute));
@@ -631,7 +686,7 @@ static TableGeom table_geom(const mfkc_ctx *ctx) {
     return g;
 }
 static SkmStage skm_stage(const mfkc_ctx *ctx) {
-    SkmStage st;
+    SkmStage st{};
     st.recs = reinterpret_cast<uint4 *>(ctx->rb_keys); st.cursor = ctx->rb_cursor;
     st.n_regions = ctx->n_regions; st.region_shift = ctx->region_shift; st.win = table_win(ctx);
     uint64_t seg = (ctx->rb_cap / 2) / ctx->n_regions;
@@ -791,6 +846,268 @@ static int extract_grid(const mfkc_ctx *ctx, uint64_t n_bases) {
     return grid_for(ctx, tiles * EX_THREADS, EX_THREADS, 8);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// bin-local counting (bincount.cuh): planning, staging, the count pass, the way back to the table
+// ------------------------------------------------------------------------------------------
+static SkmStage bin_stage(const mfkc_ctx *ctx) {
+    SkmStage st{};
+    st.recs = reinterpret_cast<uint4 *>(ctx->rb_keys); st.cursor = ctx->rb_cursor;
+    st.seg_cap = ctx->os_seg_cap; st.n_regions = ctx->os_n_bins; st.region_shift = 0; st.win = 0;
+    st.ovf = st.recs + (uint64_t)ctx->os_n_bins * ctx->os_seg_cap; st.ovf_cursor = &ctx->d_binctl->ovf_cursor; st.ovf_cap = (uint32_t)ctx->os_ovf_cap;
+    return st;
+}
+static BinSrc bin_src(const mfkc_ctx *ctx) {
+    BinSrc b{};
+    b.recs[0] = reinterpret_cast<const uint4 *>(ctx->rb_keys); b.cursor[0] = ctx->rb_cursor;
+    b.seg_cap = ctx->os_seg_cap; b.n_src = 1; b.seg0 = 0; b.rot = 0;
+    return b;
+}
+
+// Decide, at the first batch of a sample, whether the sample is counted bin-locally, and lay the staging buffer out:
+// n_bins segments of seg_cap records + the overflow list.  Sizes come from the caller's hints or the previous sample
+// of this context; a wrong guess costs speed (more heavy bins, more split passes) or sends the sample to the table
+// (bins_to_table), never results.
+static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
+    ctx->mode = 0;
+    if (!ctx->bins_ok) return MFKC_OK;
+    const int k = ctx->cfg.k;
+    uint64_t expect = ctx->cfg.expected_kmers ? ctx->cfg.expected_kmers
+                    : (ctx->prev_sample_kmers_exact ? ctx->prev_sample_kmers_exact + ctx->prev_sample_kmers_exact / 8 : 0);
+    if (!expect) expect = std::max<uint64_t>(4 * first_batch_kmers, 16ull << 20);
+    expect = std::max<uint64_t>(expect, first_batch_kmers);
+    const double kmers = (double)expect * 1.03 + 4096.0;
+    double R = ctx->os_R > 0 ? ctx->os_R : (ctx->cfg.expected_distinct ? kmers / (double)ctx->cfg.expected_distinct : 3.0);
+    R = std::min(64.0, std::max(1.0, R));
+    const int w = k - minimizer_len(k) + 1;
+    double rpk = ctx->os_rpk > 0 ? ctx->os_rpk * 1.05 : std::min(1.0, (1.0 / 16 + 2.0 / (w + 1)) * 1.2);
+    // tuning / test knobs (read per sample): slack of the staging segments, planned load of the shared-memory table,
+    // a fixed number of bins, a fixed overflow-list capacity
+    const double env_slack = getenv("MFKC_BIN_SLACK") ? atof(getenv("MFKC_BIN_SLACK")) : 0.0;
+    const double env_load = getenv("MFKC_BIN_LOAD") ? atof(getenv("MFKC_BIN_LOAD")) : 0.0;
+    const long env_nbins = getenv("MFKC_BIN_COUNT") ? atol(getenv("MFKC_BIN_COUNT")) : 0;
+    const long env_ovf = getenv("MFKC_BIN_OVF") ? atol(getenv("MFKC_BIN_OVF")) : 0;
+    const double slack = env_slack > 0.0 ? env_slack : 2.0;
+    const double load = env_load > 0 ? env_load : 0.45;
+    const double S = (double)(1u << BC_LOG2S);
+    uint64_t n_bins = (uint64_t)(kmers / R / (load * S)) + 1;
+    n_bins = std::min<uint64_t>(std::max<uint64_t>(n_bins, 16), (uint64_t)MAX_REGIONS_SKM);
+    if (env_nbins > 0) n_bins = std::min<uint64_t>((uint64_t)env_nbins, (uint64_t)MAX_REGIONS_SKM);
+    const double recs = kmers * rpk;
+    uint64_t seg_cap = (uint64_t)(recs / (double)n_bins * slack) + 64;
+    if (seg_cap > 0x7fffffffull) return MFKC_OK;
+    uint64_t ovf_cap = std::min<uint64_t>(std::max<uint64_t>((uint64_t)(recs * 0.06), 1ull << 16), 0x7fffffffull);
+    if (env_ovf > 0) ovf_cap = (uint64_t)env_ovf;
+    const uint64_t need_units = 2 * (n_bins * seg_cap + ovf_cap);            // 8-byte units of rb_keys
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t have = ctx->rb_cap * 8;
+    if (need_units * 8 > (uint64_t)((double)total_b * 0.45) || (need_units * 8 > have && need_units * 8 - have > (uint64_t)((double)free_b * 0.9)))
+        return MFKC_OK;                                                     // too big to stage as a whole: region-blocked table
+    if (need_units > ctx->rb_cap) {
+        TRY(sync_all(ctx));
+        cudaFree(ctx->rb_keys); ctx->rb_keys = nullptr; ctx->rb_cap = 0;
+        if (big_alloc(ctx, (void **)&ctx->rb_keys, need_units * 8) != cudaSuccess) return fail(ctx, MFKC_E_OOM, "cannot allocate the record staging buffer");
+        ctx->rb_cap = need_units;
+    }
+    if (ctx->heavy_cap < n_bins + 4096) {
+        TRY(sync_all(ctx));
+        cudaFree(ctx->d_heavy); ctx->d_heavy = nullptr;
+        ctx->heavy_cap = (uint32_t)std::min<uint64_t>(n_bins + n_bins / 4 + 4096, 0xffffffffull);
+        CU_TRY(cudaMalloc(&ctx->d_heavy, (size_t)ctx->heavy_cap * sizeof(HeavyEnt)));
+    }
+    ctx->os_n_bins = (uint32_t)n_bins; ctx->os_seg_cap = seg_cap; ctx->os_ovf_cap = ovf_cap;
+    ctx->os_kmers_budget = (uint64_t)(kmers * 1.2);
+    ctx->os_kmers_staged = 0;
+    ctx->mode = 1;
+    return MFKC_OK;
+}
+
+static int grow_table(mfkc_ctx *ctx, uint64_t need_slots);
+static int reserve_slots(mfkc_ctx *ctx, uint64_t add);
+
+// heavy entries [e0, e1) and, with ovf, the overflow list -> global table (placement by TableGeom g)
+static int launch_heavy(mfkc_ctx *ctx, uint32_t e0, uint32_t e1, bool ovf, const TableGeom &g) {
+    ProfScope ps(ctx, P_DRAIN_HEAVY, ctx->compute);
+    table_touched(ctx);
+    if (e1 > e0) {
+        const uint32_t bpe = 2;
+        drain_heavy_kernel<<<(e1 - e0) * bpe, 256, 0, ctx->compute>>>(bin_src(ctx), ctx->d_heavy + e0, e1 - e0, bpe, ctx->cfg.k, ctx->tab, g, ctx->d_ctr);
+        CU_TRY(cudaGetLastError());
+    }
+    if (ovf) {
+        const SkmStage st = bin_stage(ctx);
+        ctx->prof_launches[P_DRAIN_HEAVY]++;
+        drain_ovf_kernel<<<ctx->sm_count * 4, 256, 0, ctx->compute>>>(st.ovf, st.ovf_cursor, st.ovf_cap, 1u, 0u, ctx->cfg.k, ctx->tab, g, ctx->d_ctr);
+        CU_TRY(cudaGetLastError());
+    }
+    return MFKC_OK;
+}
+
+// The sample leaves the bin-local mode (it outgrew the staging buffer, the overflow list is filling up, or a caller
+// needs the table): every staged record is counted into the region-blocked table, chunk by chunk so that the table
+// grows on exact distinct counts, and the sample continues in mode 0.
+static int bins_to_table(mfkc_ctx *ctx) {
+    if (ctx->mode != 1) return MFKC_OK;
+    TRY(sync_all(ctx));
+    TRY(read_counters(ctx));
+    ctx->mode = 0; ctx->os_counted = false;
+    free_bin_outputs(ctx);
+    if (!ctx->tab_clean) {
+        ProfScope ps(ctx, P_CLEAR, ctx->compute);
+        table_clear_kernel<<<grid_for(ctx, ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap);
+        ctx->tab_clean = true;
+    }
+    CU_TRY(cudaMemsetAsync(&ctx->d_ctr->distinct, 0, sizeof(unsigned long long), ctx->compute));
+    CU_TRY(cudaMemsetAsync(&ctx->d_ctr->bc_distinct, 0, sizeof(unsigned long long), ctx->compute));
+    ctx->distinct_ub = ctx->distinct_base = 0; ctx->kmers_base = ctx->h_ctr->kmers; ctx->recv_since_base = 0;
+    const uint64_t staged = ctx->h_ctr->kmers;                      // exact k-mer instances extracted so far
+    if (staged) {
+        const uint32_t nb = ctx->os_n_bins;
+        heavy_all_bins_kernel<<<grid_for(ctx, nb, 256, 4), 256, 0, ctx->compute>>>(ctx->d_heavy, nb);
+        CU_TRY(cudaGetLastError());
+        // expected size first (one rehash of an empty table instead of a doubling ladder), exact bounds per chunk after
+        const double R = ctx->os_R > 0 ? ctx->os_R : 3.0;
+        const uint64_t guess = (uint64_t)((double)staged / R / 0.4);
+        if (guess > ctx->cap) { if (grow_table(ctx, guess) != MFKC_OK) ctx->err.clear(); }
+        uint64_t chunks = (uint64_t)((double)staged * 1.2 / (0.15 * (double)ctx->cap)) + 1;
+        if ((double)staged <= kMaxLoad * (double)ctx->cap) chunks = 1;
+        chunks = std::min<uint64_t>(chunks, nb);
+        for (uint64_t c = 0; c < chunks; c++) {
+            const uint32_t b0 = (uint32_t)(nb * c / chunks), b1 = (uint32_t)(nb * (c + 1) / chunks);
+            const uint64_t share = chunks == 1 ? staged : (uint64_t)((double)staged * (double)(b1 - b0) / (double)nb * 1.2) + 1024;
+            TRY(reserve_slots(ctx, share));
+            ctx->recv_since_base += share;
+            TRY(launch_heavy(ctx, b0, b1, false, table_geom(ctx)));
+        }
+        TRY(sync_all(ctx));
+        CU_TRY(cudaMemcpy(ctx->h_binctl, ctx->d_binctl, sizeof(BinCtl), cudaMemcpyDeviceToHost));
+        const uint64_t n_ovf = std::min<uint64_t>(ctx->h_binctl->ovf_cursor, ctx->os_ovf_cap);
+        if (n_ovf) {
+            TRY(reserve_slots(ctx, 16 * n_ovf));
+            ctx->recv_since_base += 16 * n_ovf;
+            TRY(launch_heavy(ctx, 0, 0, true, table_geom(ctx)));
+        }
+    }
+    CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS_SKM * sizeof(unsigned int), ctx->compute));
+    CU_TRY(cudaMemsetAsync(ctx->d_binctl, 0, sizeof(BinCtl), ctx->compute));
+    TRY(sync_all(ctx));
+    TRY(read_counters(ctx));
+    ctx->distinct_ub = ctx->distinct_base = ctx->h_ctr->distinct;
+    ctx->kmers_base = ctx->h_ctr->kmers; ctx->recv_since_base = 0;
+    ctx->staged_ub = 0; ctx->kmers_since_drain = 0;
+    return MFKC_OK;
+}
+
+// a table of at least `need_keys / 0.6` slots, empty, for the heavy bins of one count pass (plain hash placement)
+static int resid_table_prepare(mfkc_ctx *ctx, uint64_t need_keys) {
+    uint64_t want = (uint64_t)((double)need_keys / kMaxLoad) + 1024;
+    if (want > ctx->cap) {
+        if (want * sizeof(Slot) > ctx->max_table_bytes) return fail(ctx, MFKC_E_TABLE_FULL, "the heavy bins do not fit the table");
+        uint32_t nr = 1; int sh = 17;
+        plan_regions(ctx, want, &want, &nr, &sh);
+        CU_TRY(cudaStreamSynchronize(ctx->compute));
+        CU_TRY(cudaFree(ctx->tab));
+        ctx->tab = nullptr; ctx->tab128 = nullptr; ctx->cap = 0; ctx->tab_alloc_slots = 0;
+        Slot *nt = nullptr;
+        TRY(table_alloc(ctx, want, &nt));
+        ctx->tab = nt; ctx->tab128 = reinterpret_cast<Slot128 *>(nt); ctx->cap = want; ctx->tab_alloc_slots = want;
+        ctx->n_regions = nr; ctx->region_shift = sh;
+        ctx->tab_clean = true;
+    } else if (!ctx->tab_clean) {
+        ProfScope ps(ctx, P_CLEAR, ctx->compute);
+        table_clear_kernel<<<grid_for(ctx, ctx->cap, 256, 16), 256, 0, ctx->compute>>>(ctx->tab, ctx->cap);
+        ctx->tab_clean = true;
+    }
+    return MFKC_OK;
+}
+
+// entry points that put keys into the table themselves (receive sides of the shard exchange)
+static int ensure_table_mode(mfkc_ctx *ctx) {
+    if (ctx->mode == 1) TRY(bins_to_table(ctx));
+    ctx->mode = 0; ctx->sample_open = true;
+    table_touched(ctx);
+    return MFKC_OK;
+}
+
+static constexpr uint32_t kNoOutput = 0xFFFFFFFFu;
+
+// The count pass of the bin-local mode: histogram, distinct count and (thr != kNoOutput) the compacted entries with
+// count > thr in ctx->os_keys / os_counts (unsorted).  The staged records stay where they are, so the pass can be
+// repeated for another threshold.  Returns 1 when the sample had to fall back to the table (ctx->mode is 0 then).
+static int bins_count(mfkc_ctx *ctx, uint32_t thr) {
+    const bool want_out = thr != kNoOutput;
+    if (ctx->os_counted && (!want_out || (ctx->os_thr == thr && (ctx->os_keys || ctx->os_n_good == 0)))) return MFKC_OK;
+    cudaStream_t st = ctx->compute;
+    TRY(sync_all(ctx));
+    TRY(read_counters(ctx));
+    free_bin_outputs(ctx);
+    const uint64_t kmers = ctx->h_ctr->kmers;
+    uint64_t out_cap = 0;
+    if (want_out) {
+        const double R = ctx->os_R > 0 ? ctx->os_R : 3.0;
+        out_cap = ctx->os_good_frac > 0 ? (uint64_t)((double)kmers / R * ctx->os_good_frac * 1.3) + (1u << 16) : kmers / 6 + (1u << 16);
+        out_cap = std::min<uint64_t>(out_cap, kmers);
+    }
+    static const int env_tma = getenv("MFKC_BIN_TMA") ? atoi(getenv("MFKC_BIN_TMA")) : 1;
+    uint64_t good = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        unsigned long long *ok = nullptr; uint16_t *oc = nullptr;
+        if (out_cap) { TMP_ALLOC(ok, out_cap * 8); TMP_ALLOC(oc, out_cap * 2); }
+        CU_TRY(cudaMemsetAsync(ctx->d_hist, 0, MFKC_HIST_BINS * sizeof(unsigned long long), st));
+        CU_TRY(cudaMemsetAsync(&ctx->d_ctr->n_good, 0, 2 * sizeof(unsigned long long), st));            // n_good, bc_distinct
+        CU_TRY(cudaMemsetAsync(&ctx->d_ctr->distinct, 0, sizeof(unsigned long long), st));
+        CU_TRY(cudaMemsetAsync(ctx->d_binctl, 0, offsetof(BinCtl, ovf_cursor), st));
+        BinCountArgs a{};
+        a.src = bin_src(ctx); a.n_bins = ctx->os_n_bins; a.k = ctx->cfg.k; a.thr = want_out ? thr : 0x7FFFFFFFu;
+        a.limit = (uint32_t)(0.8 * (double)(1u << BC_LOG2S)); a.max_recs = 0xFFFFFFFFu; a.use_tma = env_tma;
+        a.out_keys = ok; a.out_counts = oc; a.out_cap = out_cap; a.hist = ctx->d_hist; a.ctr = ctx->d_ctr; a.ctl = ctx->d_binctl;
+        a.heavy = ctx->d_heavy; a.heavy_cap = ctx->heavy_cap;
+        if (kmers) {
+            ProfScope ps(ctx, P_BIN_COUNT, st);
+            const int grid = (int)std::min<uint64_t>(ctx->os_n_bins, (uint64_t)ctx->sm_count * 2);
+            bin_count_kernel<BC_LOG2S, BC_THREADS><<<grid, BC_THREADS, bin_count_smem_bytes<BC_LOG2S, BC_THREADS>(), st>>>(a);
+        }
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(ctx->h_binctl, ctx->d_binctl, sizeof(BinCtl), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        const BinCtl c = *ctx->h_binctl;
+        const uint64_t n_ovf = std::min<uint64_t>(c.ovf_cursor, ctx->os_ovf_cap);
+        ctx->os_heavy_bins = c.n_heavy; ctx->os_heavy_recs = c.heavy_recs; ctx->os_splits = c.n_split; ctx->os_ovf = n_ovf; ctx->os_total_recs = c.total_recs;
+        if (c.heavy_overflow) {                                  // more heavy entries than the list holds: the table takes the sample
+            TMP_FREE(ok); TMP_FREE(oc);
+            TRY(bins_to_table(ctx));
+            return 1;
+        }
+        if (c.n_heavy || n_ovf) {
+            const int r = resid_table_prepare(ctx, 16 * (c.heavy_recs + n_ovf));
+            if (r != MFKC_OK) { TMP_FREE(ok); TMP_FREE(oc); ctx->err.clear(); TRY(bins_to_table(ctx)); return 1; }
+            TableGeom g = table_geom(ctx); g.minimizer = 0; g.win = 0;
+            TRY(launch_heavy(ctx, 0, c.n_heavy, n_ovf != 0, g));
+            {
+                ProfScope ps(ctx, P_COMPACT, st);
+                table_scan_kernel<false><<<grid_for(ctx, (ctx->cap + 7) / 8, 256, 8), 256, 0, st>>>(
+                    ctx->tab, TabSoA{nullptr, nullptr, 0}, ctx->cap, a.thr, ctx->d_hist, ok, oc, out_cap, ctx->d_ctr);
+            }
+            CU_TRY(cudaGetLastError());
+        }
+        CU_TRY(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, MFKC_HIST_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        good = ctx->h_ctr->n_good;
+        if (good <= out_cap || !want_out) { ctx->os_keys = ok; ctx->os_counts = oc; break; }
+        TMP_FREE(ok); TMP_FREE(oc);
+        if (attempt == 1) return fail(ctx, MFKC_E_STATE, "internal: bin count output overflow");
+        out_cap = good;                                           // exact now
+    }
+    if (!want_out) good = 0;
+    ctx->os_n_good = good; ctx->os_thr = thr; ctx->os_counted = true; ctx->hist_valid = true;
+    const uint64_t distinct = ctx->h_ctr->distinct + ctx->h_ctr->bc_distinct;
+    if (want_out && distinct) ctx->os_good_frac = (double)good / (double)distinct;
+    ctx->distinct_ub = ctx->distinct_base = ctx->h_ctr->distinct;
+    return MFKC_OK;
+}
+
 static int sort_variant_reserve(mfkc_ctx *ctx, uint64_t add);
 
 // count a device-resident batch (bases/offsets already on the device, visible to the compute stream)
@@ -798,8 +1115,41 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
                               uint32_t n_reads, uint64_t n_bases, bool host_fed = false) {
     const int k = ctx->cfg.k;
     const uint64_t kmers_ub = n_bases >= (uint64_t)k ? n_bases - k + 1 : 0;
+    if (!ctx->sample_open) {
+        ctx->sample_open = true;
+        if (ctx->cfg.variant == MFKC_VARIANT_HASH) TRY(plan_bins(ctx, kmers_ub));
+    }
+    ctx->os_counted = false;
+    if (ctx->mode == 1) {
+        // bin-local mode: stage only.  The sample stays in this mode while it fits the plan and the overflow list
+        // (watched through asynchronous snapshots of its cursor) stays far from full.
+        uint64_t kmers_est = n_bases >= (uint64_t)n_reads * (uint64_t)(k - 1) ? n_bases - (uint64_t)n_reads * (uint64_t)(k - 1) : 0;
+        uint64_t ovf_seen = 0;
+        for (int i = 0; i < N_STAGE; i++) {
+            Staging &q = ctx->st[i];
+            if (q.pending && cudaEventQuery(q.ev_done) == cudaSuccess) { q.pending = false; ovf_seen = std::max<uint64_t>(ovf_seen, *q.h_snap); }
+        }
+        if (ctx->os_kmers_staged + kmers_est > ctx->os_kmers_budget || 2 * ovf_seen > ctx->os_ovf_cap) TRY(bins_to_table(ctx));
+        else {
+            ctx->os_kmers_staged += kmers_est; ctx->kmers_ub_total += kmers_ub;
+            TRY(launch_mark(ctx, s, d_offsets, n_reads, n_bases, ctx->cfg.min_seq_len, 1, ctx->d_ctr));
+            if (n_bases >= (uint64_t)k) {
+                ProfScope ps(ctx, P_EXTRACT_PARTITION, ctx->compute);
+                extract_skm_kernel<3, TabAoS><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+                    d_bases, n_bases, s.d_flags, k, bin_stage(ctx), TabAoS{nullptr, 0}, ctx->d_ctr, nullptr);
+                CU_TRY(cudaGetLastError());
+            }
+            *s.h_snap = 0;
+            CU_TRY(cudaMemcpyAsync(s.h_snap, &ctx->d_binctl->ovf_cursor, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->compute));
+            CU_TRY(cudaEventRecord(s.ev_done, ctx->compute));
+            s.pending = true; s.kmers_submitted_at_end = ctx->kmers_ub_total;
+            ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
+            ctx->host_fed = host_fed;
+            return MFKC_OK;
+        }
+    }
     if (ctx->cfg.variant == MFKC_VARIANT_SORT) TRY(sort_variant_reserve(ctx, kmers_ub));
-    else TRY(reserve_slots(ctx, kmers_ub));
+    else { TRY(reserve_slots(ctx, kmers_ub)); table_touched(ctx); }
     if (ctx->cfg.variant == MFKC_VARIANT_HASH) {
         if (ctx->soa && ctx->kmers_since_drain + kmers_ub > 4000000000ull) TRY(drain_regions(ctx));    // u32 counts cannot wrap
         // staging is sized by an ESTIMATE (a full segment only costs speed): bases - reads*(k-1) is exact when
@@ -837,7 +1187,7 @@ static int count_batch_device(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases,
             extract_kernel<SinkTable><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
                 d_bases, n_bases, s.d_flags, k, sink, ctx->d_ctr);
         } else {
-            ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
+            ProfScope ps(ctx, P_EXTRACT_KEYS, ctx->compute);
             BucketSink sink{ctx->sv_keys, ctx->d_bucket_base, &ctx->d_ctr->appended, ctx->sv_cap, 1, 0};
             extract_bucket_kernel<0><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
                 d_bases, n_bases, s.d_flags, k, sink, ctx->d_ctr);
@@ -1082,18 +1432,28 @@ extern "C" int mfkc_stats(mfkc_ctx *ctx, uint64_t stats[6]) {
     if (!ctx || !stats) return MFKC_E_BADARG;
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(finalize_counts(ctx));
+    if (ctx->mode == 1) { const int r = bins_count(ctx, kNoOutput); if (r < 0) return r; }
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
-    stats[0] = ctx->cfg.variant != MFKC_VARIANT_SORT ? ctx->h_ctr->distinct : ctx->svs_n;
+    stats[0] = ctx->cfg.variant != MFKC_VARIANT_SORT ? ctx->h_ctr->distinct + ctx->h_ctr->bc_distinct : ctx->svs_n;
     stats[1] = ctx->h_ctr->kmers;
     stats[2] = ctx->h_ctr->total_seq; stats[3] = ctx->h_ctr->good_seq;
     stats[4] = ctx->h_ctr->total_len; stats[5] = ctx->h_ctr->good_len;
     return MFKC_OK;
 }
 
+// diagnostics of the bin-local mode (see include/mfkc.h)
+extern "C" int mfkc_bin_stats(mfkc_ctx *ctx, uint64_t out[8]) {
+    if (!ctx || !out) return MFKC_E_BADARG;
+    out[0] = (uint64_t)ctx->mode; out[1] = ctx->os_n_bins; out[2] = ctx->os_seg_cap;
+    out[3] = ctx->os_heavy_bins; out[4] = ctx->os_heavy_recs; out[5] = ctx->os_splits; out[6] = ctx->os_ovf; out[7] = ctx->os_total_recs;
+    return MFKC_OK;
+}
+
 static int compute_hist(mfkc_ctx *ctx) {
     if (ctx->hist_valid) return MFKC_OK;
     TRY(finalize_counts(ctx));
+    if (ctx->mode == 1) { const int r = bins_count(ctx, kNoOutput); if (r < 0) return r; if (r == 0) return MFKC_OK; }
     cudaStream_t st = ctx->compute;
     CU_TRY(cudaMemsetAsync(ctx->d_hist, 0, MFKC_HIST_BINS * sizeof(unsigned long long), st));
     {
@@ -1219,38 +1579,54 @@ extern "C" int mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_goo
         return MFKC_OK;
     }
     if (ctx->cfg.variant != MFKC_VARIANT_SORT) {
-        // one pass over the table: histogram + compaction (buffers sized by the exact distinct count)
-        TRY(read_counters(ctx));
-        const uint64_t distinct = ctx->h_ctr->distinct;
-        if (distinct) {
-            unsigned long long *k1 = nullptr, *k2 = nullptr; uint16_t *c1 = nullptr, *c2 = nullptr;
-            TMP_ALLOC(k1, (size_t)distinct * 8);
-            TMP_ALLOC(c1, (size_t)distinct * 2);
-            CU_TRY(cudaMemsetAsync(ctx->d_hist, 0, MFKC_HIST_BINS * sizeof(unsigned long long), st));
-            CU_TRY(cudaMemsetAsync(&ctx->d_ctr->n_good, 0, sizeof(unsigned long long), st));
-            {
-                ProfScope ps(ctx, P_COMPACT, st);
-                if (ctx->soa) table_scan_kernel<true><<<grid_for(ctx, (ctx->cap + 7) / 8, 256, 8), 256, 0, st>>>(nullptr, tab_soa(ctx), ctx->cap, thr_u, ctx->d_hist, k1, c1, distinct, ctx->d_ctr);
-                else table_scan_kernel<false><<<grid_for(ctx, (ctx->cap + 7) / 8, 256, 8), 256, 0, st>>>(ctx->tab, TabSoA{nullptr, nullptr, 0}, ctx->cap, thr_u, ctx->d_hist, k1, c1, distinct, ctx->d_ctr);
+        unsigned long long *k1 = nullptr; uint16_t *c1 = nullptr;
+        bool counted = false;
+        if (ctx->mode == 1) {
+            // bin-local mode: the count pass itself selects the entries with count > threshold (unsorted)
+            const int r = bins_count(ctx, thr_u);
+            if (r < 0) return r;
+            if (r == 0) {
+                counted = true;
+                good = ctx->os_n_good;
+                k1 = ctx->os_keys; c1 = ctx->os_counts; ctx->os_keys = nullptr; ctx->os_counts = nullptr;
+                if (!good) { TMP_FREE(k1); TMP_FREE(c1); k1 = nullptr; c1 = nullptr; }
             }
-            CU_TRY(cudaGetLastError());
-            CU_TRY(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, MFKC_HIST_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaMemcpyAsync(&ctx->h_ctr->n_good, &ctx->d_ctr->n_good, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaStreamSynchronize(st));
-            ctx->hist_valid = true;
-            good = ctx->h_ctr->n_good;
-            if (good) {
-                TMP_ALLOC(k2, (size_t)good * 8);
-                TMP_ALLOC(c2, (size_t)good * 2);
-                int r = radix_sort<uint16_t, true>(ctx, st, k1, k2, c1, c2, good, 2 * ctx->cfg.k);
-                if (r != MFKC_OK) { TMP_FREE(k1); TMP_FREE(k2); TMP_FREE(c1); TMP_FREE(c2); return r; }
-                ctx->em_keys = k1; ctx->em_counts = c1;       // radix_sort leaves the result in (k1, c1)
-                TMP_FREE(k2); TMP_FREE(c2);
+        }
+        if (!counted) {
+            // one pass over the table: histogram + compaction (buffers sized by the exact distinct count)
+            TRY(read_counters(ctx));
+            const uint64_t distinct = ctx->h_ctr->distinct;
+            if (distinct) {
+                TMP_ALLOC(k1, (size_t)distinct * 8);
+                if (cudaMallocAsync((void **)&c1, (size_t)distinct * 2, st) != cudaSuccess) { cudaGetLastError(); TMP_FREE(k1); return fail(ctx, MFKC_E_OOM, "cannot allocate the emit buffers"); }
+                cudaError_t e = cudaMemsetAsync(ctx->d_hist, 0, MFKC_HIST_BINS * sizeof(unsigned long long), st);
+                if (e == cudaSuccess) e = cudaMemsetAsync(&ctx->d_ctr->n_good, 0, sizeof(unsigned long long), st);
+                if (e == cudaSuccess) {
+                    ProfScope ps(ctx, P_COMPACT, st);
+                    if (ctx->soa) table_scan_kernel<true><<<grid_for(ctx, (ctx->cap + 7) / 8, 256, 8), 256, 0, st>>>(nullptr, tab_soa(ctx), ctx->cap, thr_u, ctx->d_hist, k1, c1, distinct, ctx->d_ctr);
+                    else table_scan_kernel<false><<<grid_for(ctx, (ctx->cap + 7) / 8, 256, 8), 256, 0, st>>>(ctx->tab, TabSoA{nullptr, nullptr, 0}, ctx->cap, thr_u, ctx->d_hist, k1, c1, distinct, ctx->d_ctr);
+                    e = cudaGetLastError();
+                }
+                if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, MFKC_HIST_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(&ctx->h_ctr->n_good, &ctx->d_ctr->n_good, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) { TMP_FREE(k1); TMP_FREE(c1); ctx->err = std::string("emit: ") + cudaGetErrorString(e); return MFKC_E_CUDA; }
+                ctx->hist_valid = true;
+                good = ctx->h_ctr->n_good;
+                if (!good) { TMP_FREE(k1); TMP_FREE(c1); k1 = nullptr; c1 = nullptr; }
             } else {
-                TMP_FREE(k1); TMP_FREE(c1);
+                TRY(compute_hist(ctx));
             }
-        } else {
-            TRY(compute_hist(ctx));
+        }
+        if (good) {
+            unsigned long long *k2 = nullptr; uint16_t *c2 = nullptr;
+            cudaError_t e = cudaMallocAsync((void **)&k2, (size_t)good * 8, st);
+            if (e == cudaSuccess) e = cudaMallocAsync((void **)&c2, (size_t)good * 2, st);
+            if (e != cudaSuccess) { cudaGetLastError(); TMP_FREE(k1); TMP_FREE(c1); TMP_FREE(k2); return fail(ctx, MFKC_E_OOM, "cannot allocate the sort buffers"); }
+            const int r = radix_sort<uint16_t, true>(ctx, st, k1, k2, c1, c2, good, 2 * ctx->cfg.k);
+            if (r != MFKC_OK) { TMP_FREE(k1); TMP_FREE(k2); TMP_FREE(c1); TMP_FREE(c2); return r; }
+            ctx->em_keys = k1; ctx->em_counts = c1;       // radix_sort leaves the result in (k1, c1)
+            TMP_FREE(k2); TMP_FREE(c2);
         }
     } else {
         TRY(compute_hist(ctx));
@@ -1339,7 +1715,7 @@ extern "C" int mfkc_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, cons
     // pass 1: bucket sizes
     CU_TRY(cudaMemsetAsync(ctx->d_bucket_cursor, 0, 64 * sizeof(unsigned long long), ctx->compute));
     {
-        ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
+        ProfScope ps(ctx, P_EXTRACT_KEYS, ctx->compute);
         BucketSink sink{reinterpret_cast<unsigned long long *>(d_keys_out), ctx->d_bucket_base, ctx->d_bucket_cursor, cap_keys, ns, 1};
         extract_bucket_kernel<0><<<grid, EX_THREADS, 0, ctx->compute>>>(d_bases, n_bases, s.d_flags, k, sink, ctx->d_ctr);
     }
@@ -1353,7 +1729,7 @@ extern "C" int mfkc_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, cons
     CU_TRY(cudaMemsetAsync(ctx->d_bucket_cursor, 0, 64 * sizeof(unsigned long long), ctx->compute));
     // pass 2: write grouped keys
     {
-        ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
+        ProfScope ps(ctx, P_EXTRACT_KEYS, ctx->compute);
         BucketSink sink{reinterpret_cast<unsigned long long *>(d_keys_out), ctx->d_bucket_base, ctx->d_bucket_cursor, cap_keys, ns, 0};
         extract_bucket_kernel<0><<<grid, EX_THREADS, 0, ctx->compute>>>(d_bases, n_bases, s.d_flags, k, sink, ctx->d_ctr);
     }
@@ -1370,6 +1746,7 @@ extern "C" int mfkc_count_keys_device(mfkc_ctx *ctx, const uint64_t *d_keys, uin
     if (ctx->k128) return fail(ctx, MFKC_E_STATE, "this flavour of the shard exchange serves k <= 31; use mfkc_p2p_* for 128-bit keys");
     if (n == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
+    TRY(ensure_table_mode(ctx));
     TRY(reserve_slots(ctx, n));
     const bool stage_keys = ctx->cfg.variant == MFKC_VARIANT_HASH && !ctx->place;
     if (stage_keys) { TRY(reserve_staging(ctx, n)); ctx->staged_ub += n; }
@@ -1428,7 +1805,7 @@ extern "C" int mfkc_skm_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, 
     unsigned long long *d_kc = reinterpret_cast<unsigned long long *>(ctx->d_bucket_base);                                       // ... and k-mer counts (u64)
     CU_TRY(cudaMemsetAsync(ctx->d_bucket_cursor, 0, 64 * sizeof(unsigned long long), ctx->compute));
     CU_TRY(cudaMemsetAsync(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t), ctx->compute));
-    SkmStage st;
+    SkmStage st{};
     st.recs = reinterpret_cast<uint4 *>(d_recs_out); st.cursor = d_cur; st.seg_cap = seg_cap; st.n_regions = ns; st.region_shift = 0; st.win = 0;
     {
         ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
@@ -1462,6 +1839,7 @@ extern "C" int mfkc_skm_count_device(mfkc_ctx *ctx, const void *d_recs, uint64_t
     if (ctx->cfg.variant != MFKC_VARIANT_HASH || !ctx->place || ctx->k128) return fail(ctx, MFKC_E_STATE, "mfkc_skm_count_device needs the region-blocked hash variant with k <= 31");
     if (n_recs == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
+    TRY(ensure_table_mode(ctx));
     TRY(reserve_slots(ctx, n_kmers));
     if (ctx->soa && ctx->kmers_since_drain + n_kmers > 4000000000ull) TRY(drain_regions(ctx));
     ctx->kmers_since_drain += n_kmers;
@@ -1580,7 +1958,7 @@ static int p2p_extract_batch(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases, 
     const int k = ctx->cfg.k;
     TRY(launch_mark(ctx, s, d_offsets, n_reads, n_bases, ctx->cfg.min_seq_len, 1, ctx->d_ctr));
     if (n_bases >= (uint64_t)k) {
-        SkmStage st;
+        SkmStage st{};
         st.recs = ctx->p2p_recs; st.cursor = ctx->p2p_cursor; st.seg_cap = ctx->p2p_seg_cap;
         st.n_regions = (uint32_t)std::max(1, ctx->cfg.n_shards); st.region_shift = ctx->p2p_log2; st.win = 0;
         ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
@@ -1634,6 +2012,7 @@ extern "C" int mfkc_p2p_drain(mfkc_ctx *ctx, uint64_t n_kmers_in) {
     for (uint32_t i = 0; i < ns; i++) if (!ctx->p2p_peer_recs[i]) return fail(ctx, MFKC_E_STATE, "mfkc_p2p_drain: not every peer is attached");
     if (n_kmers_in == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
+    TRY(ensure_table_mode(ctx));
     P2PPeers pp;
     for (uint32_t i = 0; i < (uint32_t)P2P_MAX_PEERS; i++) { pp.recs[i] = i < ns ? ctx->p2p_peer_recs[i] : nullptr; pp.cursor[i] = i < ns ? ctx->p2p_peer_cursor[i] : nullptr; }
     pp.seg_cap = ctx->p2p_seg_cap; pp.n_peers = ns; pp.me = (uint32_t)ctx->cfg.shard_id; pp.log2_buckets = ctx->p2p_log2;

@@ -17,7 +17,7 @@ from tests.conftest import GOLDEN, INPUTS
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [m.VARIANT_HASH, m.VARIANT_SORT, m.VARIANT_HASH_DIRECT]
+VARIANTS = [m.VARIANT_HASH, m.VARIANT_SORT, m.VARIANT_HASH_DIRECT, m.VARIANT_HASH_TABLE]
 
 
 def run_counter(reads_batches, k, b, variant, min_len=0, **kw):
@@ -104,12 +104,81 @@ def test_empty_inputs(built, variant):
     assert rec == b"" and st["total_seq"] == 3 and st["kmers"] == 0
 
 
-@pytest.mark.parametrize("variant", [m.VARIANT_HASH, m.VARIANT_HASH_DIRECT])
+@pytest.mark.parametrize("variant", [m.VARIANT_HASH, m.VARIANT_HASH_DIRECT, m.VARIANT_HASH_TABLE])
 def test_table_growth(built, variant):
     """the table starts tiny and must grow (Long2ShortHashMap.enlargeAndRehash analogue)."""
     rng = np.random.default_rng(7)
     reads = ["".join(rng.choice(list("ACGT"), 150)) for _ in range(4000)]
     check_against_oracle(reads, 31, 0, variant, batches=16, table_slots=1024)
+
+
+def _skewed_reads(seed=11, n=6000):
+    rng = np.random.default_rng(seed)
+    genome = "".join(rng.choice(list("ACGT"), 20000))
+    reads = [genome[int(i):int(i) + 120] for i in rng.integers(0, len(genome) - 120, n)]
+    reads += ["A" * 100] * 300                       # one very hot key
+    reads += ["".join(rng.choice(list("ACGT"), 150)) for _ in range(3000)]      # singletons
+    return reads
+
+
+@pytest.mark.parametrize("knobs,expect", [
+    ({}, {}),                                                                        # planned normally: everything in shared memory
+    ({"MFKC_BIN_COUNT": "3"}, {"split_passes": 1}),                                 # 3 bins for ~400 k distinct k-mers: passes split by hash
+    ({"MFKC_BIN_COUNT": "1"}, {"heavy_entries": 1}),                                # one bin: 32 parts are not enough -> table
+    ({"MFKC_BIN_COUNT": "64", "MFKC_BIN_SLACK": "0.5", "MFKC_BIN_OVF": "1000000"}, {"overflow_recs": 1, "heavy_entries": 1}),   # segments too small: overflow list
+    ({"MFKC_BIN_COUNT": "64", "MFKC_BIN_SLACK": "0.25", "MFKC_BIN_OVF": "100000"}, {"bin_mode": 0}),  # overflow list half full: back to the table
+])
+def test_bin_local_paths(built, monkeypatch, knobs, expect):
+    """MFKC_VARIANT_HASH's bin-local count (bincount.cuh) with its exactness paths forced: split passes, heavy bins
+    through the table, the overflow list, and the fall-back of the whole sample to the region-blocked table."""
+    for k_, v_ in knobs.items():
+        monkeypatch.setenv(k_, v_)
+    reads = _skewed_reads()
+    k, b = 25, 1
+    step = 500
+    counts = orc.count_reads(reads, k, 0)
+    want = {t: orc.kmers_bin(counts, t, k) for t in (0, b)}
+    with m.KmerCounter(k, variant=m.VARIANT_HASH, expected_kmers=sum(len(r) - k + 1 for r in reads)) as kc:
+        for rep in range(2):                           # second sample: planned from the first one's statistics
+            if rep:
+                kc.reset()
+            for i in range(0, len(reads), step):
+                kc.submit_reads(reads[i:i + step])
+            kc.flush()
+            rec = kc.emit(b)
+            hist = kc.histogram()
+            st = kc.stats()
+            bs = kc.bin_stats()
+            assert rec == want[b]
+            assert {int(c): int(hist[c]) for c in np.nonzero(hist)[0]} == orc.histogram(counts)
+            assert st["distinct"] == len(counts)
+            assert kc.emit(0) == want[0]                                 # another threshold: the count pass runs again
+            if rep == 0:
+                if "bin_mode" not in expect:
+                    assert bs["bin_mode"] == 1
+                for name, least in expect.items():
+                    assert (bs[name] >= least) if name != "bin_mode" else (bs[name] == least), (name, bs)
+
+
+def test_bin_local_outgrows_plan(built):
+    """a sample far larger than the hint leaves the bin-local mode mid-way (bins_to_table) and stays exact"""
+    cfg = m.synth_cfg(total_genome_bp=300000, n_genomes=4)
+    raw = m.synth_reads_host(cfg, 0, 30000)
+    keep = ~(raw == ord("N")).any(axis=1)
+    bases = np.ascontiguousarray(raw[keep]).reshape(-1)
+    n = int(keep.sum())
+    offsets = (np.arange(n + 1, dtype=np.uint64) * np.uint64(cfg.read_len))
+    want_rec, want_hist, want_distinct, want_stats = _oracle_c.count(bases, offsets, 31, 1, P=4)
+    with m.KmerCounter(31, variant=m.VARIANT_HASH, expected_kmers=200000) as kc:
+        step = 2000
+        for s in range(0, n, step):
+            e = min(n, s + step)
+            kc.submit(bases, offsets[s:e + 1])
+        kc.flush()
+        assert kc.emit(1) == want_rec
+        assert kc.stats()["distinct"] == want_distinct
+        assert kc.bin_stats()["bin_mode"] == 0
+        assert (kc.histogram() == want_hist).all()
 
 
 @pytest.mark.parametrize("region_shift,staging_bytes", [(4, 0), (6, 8 * 5000), (8, 8 * 200000), (10, 8 * 100)])
