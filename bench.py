@@ -222,7 +222,7 @@ def run_reference(args):
         "impl": "reference", "metric": "canonical 31-mers counted/s", "value": value, "unit": "kmers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": dict(workload_config(args.gpus), sample_fraction=sample / N_READS, same_config=False),
         "cpu_baseline": {"value": value, "unit": "kmers/s", "cores": threads, "kind": "port",
                          "sample": "%d of the %d reads of the workload per step (oracle/ref_cpu.c: C restatement of the "
                                    "reference's threaded algorithm; no JVM in the image)" % (sample, N_READS)},
@@ -238,6 +238,104 @@ def workload_config(n_gpus):
             "variant": os.environ.get("MFKC_BENCH_VARIANT", "hash (bin-local)"),
             "parallelism": "1 GPU" if n_gpus == 1 else "hash-range sharded over %d GPUs, %s" % (n_gpus, "NCCL all-to-all + restage" if os.environ.get("MFKC_EXCHANGE") == "nccl" else "records drained straight from peer HBM over NVLink (CUDA IPC), no data-path collective"),
             "l2": "inputs (3 GB reads, multi-GB table) are far larger than the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------ parity at size
+def verify_at_size(m, kc, step_device, env):
+    """Checks, once per run and outside every timed region, that what is timed is right:
+      N = 1  (i)  the first MFKC_BENCH_VERIFY_READS (2 M) reads of the workload, counted on the GPU through the host-fed
+                  C-ABI path, equal oracle/ref_cpu.c's result: sha256 of the records, histogram, distinct count;
+             (ii) the full workload (20 M reads): the default variant, the region-blocked table, the sort-and-RLE variant
+                  and the direct-upsert variant produce identical records (sha256), histograms and distinct counts.
+      N > 1  (iii) the sharded path as timed (real CUDA IPC between the ranks' processes): the merged shard records and
+                  the summed histograms of G x 1 M reads equal ONE single-GPU count of the same reads (rank 0)."""
+    import hashlib
+    import numpy as np
+    world, rank, dist = env["world"], env["rank"], env["dist"]
+    out = {}
+
+    def digest(c):
+        c.flush()
+        rec = c.emit(B_THRESHOLD)
+        return hashlib.sha256(rec).hexdigest(), c.histogram(), c.stats()["distinct"], len(rec) // 10
+
+    if world == 1:
+        from tests import _oracle_c
+        import __graft_entry__ as g
+        g.build()
+        v_reads = int(os.environ.get("MFKC_BENCH_VERIFY_READS", 2_000_000))
+        raw = m.synth_reads_host(m.synth_cfg(), 0, v_reads)
+        keep = ~(raw == ord("N")).any(axis=1)
+        bases = np.ascontiguousarray(raw[keep]).reshape(-1)
+        nk = int(keep.sum())
+        offsets = np.arange(nk + 1, dtype=np.uint64) * np.uint64(READ_LEN)
+        del raw
+        want_rec, want_hist, want_distinct, _ = _oracle_c.count(bases, offsets, K, B_THRESHOLD, P=os.cpu_count() or 1)
+        with m.KmerCounter(K, device=env["local_rank"], variant=env["variant"], expected_kmers=nk * (READ_LEN - K + 1)) as kv:
+            step = 250_000
+            for s in range(0, nk, step):
+                kv.submit(bases, offsets[s:min(nk, s + step) + 1])          # host buffers, asynchronous pipeline
+            sha, hist, distinct, n_rec = digest(kv)
+        out["gpu_equals_cpu_oracle"] = bool(sha == hashlib.sha256(want_rec).hexdigest() and (hist == want_hist).all()
+                                            and distinct == want_distinct)
+        out["cpu_oracle_sample"] = {"reads": nk, "distinct": int(want_distinct), "records": len(want_rec) // 10}
+        del bases, offsets, want_rec
+        # (ii) every variant on the full workload
+        step_device()
+        ref = digest(kc)
+        names, agree = ["default"], True
+        for name, v in (("table", m.VARIANT_HASH_TABLE), ("sort", m.VARIANT_SORT), ("direct", m.VARIANT_HASH_DIRECT)):
+            if v == env["variant"] or name in os.environ.get("MFKC_BENCH_VERIFY_SKIP", "").split(","):
+                continue
+            with m.KmerCounter(K, device=env["local_rank"], variant=v, expected_kmers=env["kmers_ub"]) as kv:
+                n = env["n_reads"]
+                for s in range(0, n, BATCH_READS):
+                    e = min(n, s + BATCH_READS)
+                    kv.submit_device(env["d_bases"] + s * READ_LEN, env["d_offs"] + s * 8, e - s, (e - s) * READ_LEN)
+                got = digest(kv)
+            names.append(name)
+            agree = agree and got[0] == ref[0] and bool((got[1] == ref[1]).all()) and got[2] == ref[2]
+        out["variants_agree_full_workload"] = bool(agree)
+        out["variants_compared"] = names
+        out["full_workload"] = {"sha256_records": ref[0], "records": ref[3], "distinct": int(ref[2])}
+        return out
+
+    # (iii) N > 1
+    from metafast_b200.sharded import merge_sorted_records
+    vr = min(int(os.environ.get("MFKC_BENCH_VERIFY_SHARD_READS", 1_000_000)), env["n_reads"])
+    kc.reset()
+    if env["exchange"] == "p2p":
+        env["sharded"].begin()
+    env["sharded"].run_device(env["d_bases"], env["d_offs"], vr)
+    kc.flush()
+    rec = kc.emit(B_THRESHOLD)
+    mine = (rec, kc.histogram(), kc.stats()["distinct"])
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    ok = None
+    if rank == 0:
+        merged = merge_sorted_records([p[0] for p in parts])
+        hist = sum(p[1] for p in parts)
+        distinct = sum(int(p[2]) for p in parts)
+        with m.KmerCounter(K, device=env["local_rank"], expected_kmers=world * vr * (READ_LEN - K + 1)) as kv:
+            span = vr + vr // 50 + 1000
+            d_b = kv.device_alloc(span * READ_LEN)
+            d_o = kv.device_alloc((span + 1) * 8)
+            for r in range(world):                                     # the same reads every rank took: its first vr kept ones
+                cfg_r = m.synth_cfg(sample=r)
+                kept = C.c_uint64()
+                kv._ck(kv.lib.mfkc_synth_reads_device(kv.h, C.byref(cfg_r), r * N_READS, span, C.c_void_p(d_b), C.c_void_p(d_o), C.byref(kept)))
+                assert kept.value >= vr
+                kv.submit_device(d_b, d_o, vr, vr * READ_LEN)
+                kv.sync()
+            kv.flush()
+            one = kv.emit(B_THRESHOLD)
+            ok = bool(one == merged and (kv.histogram() == hist).all() and kv.stats()["distinct"] == distinct)
+            kv.device_free(d_b); kv.device_free(d_o)
+        out["sharded_equals_single_gpu"] = ok
+        out["sharded_sample"] = {"reads_per_gpu": vr, "records": len(merged) // 10, "distinct": distinct,
+                                 "sha256_records": hashlib.sha256(merged).hexdigest()}
+    return out
 
 
 # ------------------------------------------------------------------ this repository's arm
@@ -318,6 +416,15 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # ---- parity at size, before anything is timed (the oracle is the checker here, never the thing measured)
+    verified = None
+    if not os.environ.get("MFKC_BENCH_NO_VERIFY"):
+        verified = verify_at_size(m, kc, step_device, dict(world=world, rank=rank, local_rank=local_rank, dist=dist, variant=variant,
+                                                          d_bases=d_bases, d_offs=d_offs, n_reads=n_reads, kmers_ub=kmers_ub,
+                                                          sharded=sharded if world > 1 else None, exchange=exchange))
+        if rank == 0 and not all(v for k_, v in verified.items() if isinstance(v, bool)):
+            sys.stderr.write("bench.py: VERIFICATION FAILED: %s\n" % json.dumps(verified))
 
     for _ in range(args.warmup):
         n_good = step_device()
@@ -428,6 +535,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "verified": verified,
         "host_ingest": ingest,
         "result": {"kmers_per_step_per_gpu": kmers_per_step, "distinct": st["distinct"], "records_gt_b": int(n_good), "bins": kc.bin_stats(),
                    "host_wall_ms_per_step": 1e3 * wall / args.steps},

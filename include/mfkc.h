@@ -183,6 +183,17 @@ int  mfkc_skm_count_wait(mfkc_ctx *ctx);
  * A staging segment that overflows is reported by mfkc_flush (MFKC_E_STATE); nothing is dropped silently.
  * Works for 64-bit and 128-bit keys (k <= 63; 32-byte records for k > 31); up to 16 shards. */
 int  mfkc_p2p_stage_create(mfkc_ctx *ctx, uint32_t log2_buckets, uint64_t seg_cap);
+/* The same exchange for the bin-local count (MFKC_VARIANT_HASH, k <= 31; the default of bench.py and mfkc_cli --gpus):
+ * segments are (owner shard, minimizer bin), bins_per_shard bins per shard sized so that one bin's distinct k-mers fit a
+ * shared-memory table, plus an overflow list of ovf_cap records.  mfkc_p2p_drain then only notes the k-mer total; the
+ * result calls (mfkc_stats / mfkc_histogram / mfkc_emit_begin) run the counting kernel, which streams this shard's bins
+ * out of every peer's staging buffer over NVLink (TMA bulk copies from peer memory) straight into shared memory.  The
+ * peers' buffers must stay untouched (no mfkc_p2p_stage_reset) until every rank has fetched its results. */
+int  mfkc_p2p_stage_create_bins(mfkc_ctx *ctx, uint32_t bins_per_shard, uint64_t seg_cap, uint64_t ovf_cap);
+/* A geometry for mfkc_p2p_stage_create_bins from the expected k-mer instances per rank (host arithmetic only; every rank
+ * must pass the same numbers).  instances_per_distinct / slack: 0 = defaults (3.0 / 2.0). */
+int  mfkc_p2p_bin_geometry(uint64_t kmers_per_rank, uint32_t n_shards, int k, double instances_per_distinct, double slack,
+                           uint32_t *bins_per_shard, uint64_t *seg_cap, uint64_t *ovf_cap);
 int  mfkc_p2p_export(mfkc_ctx *ctx, uint8_t handles[128]);
 int  mfkc_p2p_attach(mfkc_ctx *ctx, uint32_t rank, const uint8_t handles[128]);
 int  mfkc_p2p_attach_ctx(mfkc_ctx *ctx, uint32_t rank, mfkc_ctx *peer);
@@ -280,7 +291,17 @@ int  mfkc_reader_next(mfkc_reader *r, uint8_t *bases, size_t cap_bases, uint64_t
 int  mfkc_reader_counters(const mfkc_reader *r, uint64_t counters[2]);
 const char *mfkc_reader_error(const mfkc_reader *r);
 const char *mfkc_reader_name(const mfkc_reader *r);   /* NamedSource.name() */
+/* the same name from the path alone (file name minus .fasta/.fa/.fn/.fna/.fastq/.fq and .gz): no reader, no threads.
+ * MFKC_E_FORMAT for a file whose format ReadersUtils.detectFileFormat would not accept. */
+int  mfkc_library_name(const char *path, char *out, size_t cap);
 void mfkc_reader_close(mfkc_reader *r);
+
+/* Deterministic merge of per-shard record streams into one .kmers.bin image (multi-GPU runs; no reference analogue,
+ * SURVEY.md 8e).  parts[i] = n_records[i] records of record_size bytes (10, or 18 for k > 31), each part in ascending
+ * big-endian key order; the shards own disjoint key sets, so the result is the ascending interleave.  `out` holds the sum
+ * of all records.  threads <= 0: all host threads.  CPU only. */
+int  mfkc_merge_records(const uint8_t *const *parts, const uint64_t *n_records, uint32_t n_parts, uint32_t record_size,
+                        uint8_t *out, int threads);
 
 /* .stat.txt text of QuickQuantitativeStatistics.printToFile (header of IOUtils.java:69). */
 int  mfkc_write_stat_file(const char *path, const uint64_t hist[MFKC_HIST_BINS]);

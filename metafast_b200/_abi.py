@@ -76,7 +76,9 @@ SIGNATURES = {
     "mfkc_submit_reads_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]),
     "mfkc_flush": (C.c_int, [C.c_void_p]),
     "mfkc_stats": (C.c_int, [C.c_void_p, u64p]),
+    "mfkc_library_name": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t]),
     "mfkc_bin_stats": (C.c_int, [C.c_void_p, u64p]),
+    "mfkc_merge_records": (C.c_int, [C.c_void_p, u64p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]),
     "mfkc_histogram": (C.c_int, [C.c_void_p, u64p]),
     "mfkc_emit_begin": (C.c_int, [C.c_void_p, C.c_int32, u64p]),
     "mfkc_emit_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -90,6 +92,8 @@ SIGNATURES = {
     "mfkc_skm_count_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "mfkc_skm_count_wait": (C.c_int, [C.c_void_p]),
     "mfkc_p2p_stage_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64]),
+    "mfkc_p2p_stage_create_bins": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]),
+    "mfkc_p2p_bin_geometry": (C.c_int, [C.c_uint64, C.c_uint32, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_uint32), u64p, u64p]),
     "mfkc_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mfkc_p2p_attach": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "mfkc_p2p_attach_ctx": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),

@@ -53,6 +53,7 @@ class _Ctx:
             raise _abi.MfkcError(rc, self.lib.mfkc_last_error(None).decode())
         self.h = h
         self.k = k
+        self.variant = variant
         self.rec_size = 18 if k > 31 else 10      # 16-byte BE key for 128-bit keys (extension)
 
     def _ck(self, rc: int):
@@ -242,6 +243,9 @@ class KmerCounter(_Ctx):
     # ---- peer-memory flavour of the exchange (mfkc_p2p_*)
     def p2p_stage_create(self, log2_buckets: int, seg_cap: int):
         self._ck(self.lib.mfkc_p2p_stage_create(self.h, log2_buckets, seg_cap))
+
+    def p2p_stage_create_bins(self, bins_per_shard: int, seg_cap: int, ovf_cap: int):
+        self._ck(self.lib.mfkc_p2p_stage_create_bins(self.h, bins_per_shard, seg_cap, ovf_cap))
 
     def p2p_export(self) -> bytes:
         buf = (C.c_uint8 * 128)()

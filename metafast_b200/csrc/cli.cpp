@@ -24,8 +24,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mfkc.h"
@@ -89,7 +92,8 @@ std::string java_double(double d) {
     return sign + digits.substr(0, 1) + "." + frac + "E" + std::to_string(exp10);
 }
 
-int g_ctx_gen = 0;                                        // bumped by make_ctx: function-local caches of pinned buffers follow it
+std::atomic<int> g_ctx_gen_counter{0};
+thread_local int g_ctx_gen = 0;                           // set by make_ctx in the calling thread: function-local caches of pinned buffers follow it
 bool g_sub_tool = false;                                  // inside matrix-builder: sub-tools do not print their output values
 #define OUT_VALUE(...) do { if (!g_sub_tool) printf(__VA_ARGS__); } while (0)
 
@@ -114,6 +118,7 @@ Args parse_args(int argc, char **argv) {
         {"-cm", "components-file"}, {"--components-file", "components-file"}, {"-ka", "kmers"}, {"--kmers", "kmers"},
         {"--selected", "selected"}, {"--threshold", "threshold"}, {"-p", "available-processors"},
         {"--available-processors", "available-processors"}, {"--gpu", "gpu"}, {"--gpu-variant", "gpu-variant"},
+        {"--gpus", "gpus"}, {"--gpu-mode", "gpu-mode"},
         {"--force", "force"}, {"-v", "verbose"}, {"--verbose", "verbose"}, {"--long-kmers", "long-kmers"},
         {"--k-mers", "reads"}, {"--filter-kmers", "filter-kmers"}, {"--max-thresh", "max-thresh"},
         {"--min-samples", "min-samples"}, {"--max-samples", "max-samples"}, {"--min-seq-len", "min-seq-len"}, {"-l", "l"},
@@ -157,8 +162,11 @@ int parse_int(const Args &a, const std::string &key, bool mandatory, int def) {
 }
 
 struct Gpu {
-    int device = 0;
+    int device = 0;               // first device
     int variant = MFKC_VARIANT_HASH;
+    int n_gpus = 1;               // --gpus G: devices device .. device + G - 1
+    std::string mode = "auto";    // --gpu-mode samples (one sample per GPU at a time) | shard (every sample over all GPUs) | auto
+    int n_shards = 0, shard_id = 0;
 };
 Gpu gpu_opts(const Args &a) {
     Gpu g;
@@ -167,16 +175,28 @@ Gpu gpu_opts(const Args &a) {
     if (v == "hash") g.variant = MFKC_VARIANT_HASH;
     else if (v == "sort") g.variant = MFKC_VARIANT_SORT;
     else if (v == "direct") g.variant = MFKC_VARIANT_HASH_DIRECT;
-    else die("--gpu-variant must be hash, sort or direct");
+    else if (v == "table") g.variant = MFKC_VARIANT_HASH_TABLE;
+    else die("--gpu-variant must be hash, table, sort or direct");
+    g.n_gpus = parse_int(a, "gpus", false, 1);
+    if (g.n_gpus < 1 || g.n_gpus > 16) die("--gpus must be 1..16");
+    g.mode = a.one("gpu-mode", "auto");
+    if (g.mode != "auto" && g.mode != "samples" && g.mode != "shard") die("--gpu-mode must be auto, samples or shard");
+    if (g.n_gpus > 1 && g.device + g.n_gpus > mfkc_device_count() && !getenv("MFKC_LOGICAL_GPUS"))
+        die("--gpus %d: only %d CUDA device(s) visible", g.n_gpus, mfkc_device_count());
     return g;
 }
 
 std::string reader_name(const std::string &path) {
-    mfkc_reader *r = nullptr; char err[512] = "";
-    if (mfkc_reader_open(path.c_str(), &r, err, sizeof err) != MFKC_OK) die("%s", err);
-    std::string n = mfkc_reader_name(r);
-    mfkc_reader_close(r);
-    return n;
+    char name[4096] = "";
+    if (mfkc_library_name(path.c_str(), name, sizeof name) != MFKC_OK) {
+        // same message and moment as the reference: opening the file fails (ReadersUtils.readDnaLazy)
+        mfkc_reader *r = nullptr; char err[512] = "";
+        if (mfkc_reader_open(path.c_str(), &r, err, sizeof err) != MFKC_OK) die("%s", err);
+        std::string n = mfkc_reader_name(r);
+        mfkc_reader_close(r);
+        return n;
+    }
+    return name;
 }
 
 #define CK(ctx, call) do { int rc__ = (call); if (rc__ != MFKC_OK) die("%s (libmfkc %d)", mfkc_last_error(ctx), rc__); } while (0)
@@ -193,7 +213,7 @@ void for_each_batch(mfkc_ctx *ctx, const std::string &file, F submit, mfkc_reade
     info("Loading file %s...", base_name(file).c_str());
     if (!r) r = open_reader(file);
     const size_t cap_bases = 256u << 20; const uint32_t cap_reads = 1u << 21;
-    static void *h_bases = nullptr, *h_offs = nullptr; static int owner_gen = -1;      // pinned buffers die with their context
+    static thread_local void *h_bases = nullptr, *h_offs = nullptr; static thread_local int owner_gen = -1;      // pinned buffers die with their context
     if (owner_gen != g_ctx_gen) { h_bases = h_offs = nullptr; owner_gen = g_ctx_gen; }
     if (!h_bases) { CK(ctx, mfkc_pinned_alloc(ctx, cap_bases, &h_bases)); CK(ctx, mfkc_pinned_alloc(ctx, ((size_t)cap_reads + 1) * 8, &h_offs)); }
     unsigned long long reads = 0;
@@ -212,16 +232,21 @@ void for_each_batch(mfkc_ctx *ctx, const std::string &file, F submit, mfkc_reade
     mfkc_reader_close(r);
 }
 
+void report_sample(int k, uint64_t size, uint64_t good, const std::string &out_file);
+
 // ---- KmersCounterMain.runImpl (src/tools/KmersCounterMain.java:65-120) for one sample
 std::string count_sample(mfkc_ctx *ctx, int k, int b, const std::vector<std::string> &files, const std::string &name,
                          const std::string &out_dir, const std::string &st_dir) {
     CK(ctx, mfkc_reset(ctx));
-    // open every file of the sample first: the readers inflate and parse in the background (mfkc_reader_open starts their
-    // threads), so the files of a pair are decompressed side by side while the first one is being submitted
-    std::vector<mfkc_reader *> readers;
-    for (const auto &f : files) readers.push_back(open_reader(f));
-    for (size_t i = 0; i < files.size(); i++)
-        for_each_batch(ctx, files[i], [&](const uint8_t *bases, const uint64_t *offs, uint32_t n) { CK(ctx, mfkc_submit_reads(ctx, bases, offs, n)); }, readers[i]);
+    // a sliding window of two open readers: file i + 1 inflates and parses in the background (mfkc_reader_open starts its
+    // threads) while file i is being submitted, whatever the number of files of the sample (a reader holds dozens of
+    // threads and tens of MB of queued chunks)
+    mfkc_reader *next = files.empty() ? nullptr : open_reader(files[0]);
+    for (size_t i = 0; i < files.size(); i++) {
+        mfkc_reader *cur = next;
+        next = i + 1 < files.size() ? open_reader(files[i + 1]) : nullptr;
+        for_each_batch(ctx, files[i], [&](const uint8_t *bases, const uint64_t *offs, uint32_t n) { CK(ctx, mfkc_submit_reads(ctx, bases, offs, n)); }, cur);
+    }
     CK(ctx, mfkc_flush(ctx));
     mkdirs(out_dir); mkdirs(st_dir);
     // k > 31 (--long-kmers, 18-byte records) gets its own extension so that no reference tool misreads the file
@@ -230,8 +255,8 @@ std::string count_sample(mfkc_ctx *ctx, int k, int b, const std::vector<std::str
     CK(ctx, mfkc_emit_begin(ctx, b, &good));
     FILE *f = fopen(out_file.c_str(), "wb");
     if (!f) die("Can't write %s", out_file.c_str());
-    static void *h_out = nullptr; const size_t chunk = 16777200;       // KMERS_WORK_RANGE_SIZE, src/io/IOUtils.java:30
-    static int owner_gen = -1;
+    static thread_local void *h_out = nullptr; const size_t chunk = 16777200;       // KMERS_WORK_RANGE_SIZE, src/io/IOUtils.java:30
+    static thread_local int owner_gen = -1;
     if (owner_gen != g_ctx_gen) { h_out = nullptr; owner_gen = g_ctx_gen; }
     if (!h_out) CK(ctx, mfkc_pinned_alloc(ctx, chunk, &h_out));
     for (;;) {
@@ -241,12 +266,90 @@ std::string count_sample(mfkc_ctx *ctx, int k, int b, const std::vector<std::str
         if (fwrite(h_out, 1, w, f) != w) die("Can't write %s", out_file.c_str());
     }
     fclose(f);
-    static uint64_t hist[MFKC_HIST_BINS];
-    CK(ctx, mfkc_histogram(ctx, hist));
-    if (mfkc_write_stat_file(st_file.c_str(), hist) != MFKC_OK) die("Can't write %s", st_file.c_str());
+    std::vector<uint64_t> hist(MFKC_HIST_BINS);
+    CK(ctx, mfkc_histogram(ctx, hist.data()));
+    if (mfkc_write_stat_file(st_file.c_str(), hist.data()) != MFKC_OK) die("Can't write %s", st_file.c_str());
     uint64_t st[6]; CK(ctx, mfkc_stats(ctx, st));
-    const uint64_t size = st[0];
-    // src/tools/KmersCounterMain.java:103-116
+    report_sample(k, st[0], good, out_file);
+    return out_file;
+}
+
+// ---- one sample over G GPUs (--gpus G --gpu-mode shard; no reference analogue): the batches of the sample go
+// round robin to G contexts, every context stages its k-mers per (owner shard, minimizer bin) in its own HBM, every owner
+// counts its bins straight out of all G staging buffers (peer memory), filter + histogram run per shard, and the per-shard
+// key-sorted records are merged into one .kmers.bin by mfkc_merge_records.  Byte-identical to the one-GPU file.
+std::string count_sample_sharded(std::vector<mfkc_ctx *> &ctxs, int k, int b, const std::vector<std::string> &files, const std::string &name,
+                                 const std::string &out_dir, const std::string &st_dir, uint64_t expected_kmers) {
+    const uint32_t G = (uint32_t)ctxs.size();
+    std::vector<std::vector<uint8_t>> parts(G);
+    std::vector<uint64_t> n_rec(G, 0), hist(MFKC_HIST_BINS, 0), hs(MFKC_HIST_BINS);
+    uint64_t st_sum[6] = {0, 0, 0, 0, 0, 0}, good = 0;
+    for (int attempt = 0;; attempt++) {
+        uint32_t bins = 0; uint64_t seg_cap = 0, ovf_cap = 0;
+        if (mfkc_p2p_bin_geometry(expected_kmers / G + 1, G, k, 0.0, 0.0, &bins, &seg_cap, &ovf_cap) != MFKC_OK) die("bad shard geometry");
+        for (auto *c : ctxs) { CK(c, mfkc_reset(c)); CK(c, mfkc_p2p_stage_create_bins(c, bins, seg_cap, ovf_cap)); }
+        for (auto *c : ctxs) for (uint32_t r = 0; r < G; r++) CK(c, mfkc_p2p_attach_ctx(c, r, ctxs[r]));
+        for (auto *c : ctxs) CK(c, mfkc_p2p_stage_reset(c));
+        uint64_t batch = 0;
+        mfkc_reader *next = files.empty() ? nullptr : open_reader(files[0]);
+        for (size_t i = 0; i < files.size(); i++) {
+            mfkc_reader *cur = next;
+            next = i + 1 < files.size() ? open_reader(files[i + 1]) : nullptr;
+            for_each_batch(ctxs[0], files[i], [&](const uint8_t *bases, const uint64_t *offs, uint32_t n) {
+                mfkc_ctx *c = ctxs[batch++ % G];
+                CK(c, mfkc_p2p_submit_reads(c, bases, offs, n));
+            }, cur);
+        }
+        std::vector<uint64_t> total(G, 0), per(G);
+        for (auto *c : ctxs) { CK(c, mfkc_p2p_counts(c, per.data())); for (uint32_t r = 0; r < G; r++) total[r] += per[r]; }
+        bool overflow = false;
+        for (uint32_t r = 0; r < G; r++) {
+            CK(ctxs[r], mfkc_p2p_drain(ctxs[r], total[r]));
+            const int rc = mfkc_flush(ctxs[r]);
+            if (rc == MFKC_E_STATE) overflow = true;                       // a staging buffer overflowed: the estimate was too small
+            else if (rc != MFKC_OK) die("%s (libmfkc %d)", mfkc_last_error(ctxs[r]), rc);
+        }
+        if (!overflow) break;
+        if (attempt == 3) die("the sample does not fit the staging buffers");
+        expected_kmers *= 2;
+        warn("sample larger than estimated, counting it again with larger staging buffers");
+    }
+    for (uint32_t r = 0; r < G; r++) {
+        mfkc_ctx *c = ctxs[r];
+        uint64_t g = 0;
+        CK(c, mfkc_emit_begin(c, b, &g));
+        const size_t rs = k > 31 ? 18 : 10;
+        parts[r].resize(g * rs);
+        for (size_t pos = 0; pos < parts[r].size();) {
+            size_t w = 0;
+            CK(c, mfkc_emit_next(c, parts[r].data() + pos, parts[r].size() - pos, &w));
+            if (!w) break;
+            pos += w;
+        }
+        n_rec[r] = g; good += g;
+        CK(c, mfkc_histogram(c, hs.data()));
+        for (int i = 0; i < MFKC_HIST_BINS; i++) hist[i] += hs[i];
+        uint64_t st[6]; CK(c, mfkc_stats(c, st));
+        for (int i = 0; i < 6; i++) st_sum[i] += st[i];
+    }
+    mkdirs(out_dir); mkdirs(st_dir);
+    const size_t rs = k > 31 ? 18 : 10;
+    const std::string out_file = out_dir + "/" + name + (k > 31 ? ".kmers128.bin" : ".kmers.bin"), st_file = st_dir + "/" + name + ".stat.txt";
+    std::vector<uint8_t> merged(good * rs);
+    std::vector<const uint8_t *> pp(G);
+    for (uint32_t r = 0; r < G; r++) pp[r] = parts[r].data();
+    if (mfkc_merge_records(pp.data(), n_rec.data(), G, (uint32_t)rs, merged.data(), 0) != MFKC_OK) die("record merge failed");
+    FILE *f = fopen(out_file.c_str(), "wb");
+    if (!f) die("Can't write %s", out_file.c_str());
+    if (!merged.empty() && fwrite(merged.data(), 1, merged.size(), f) != merged.size()) die("Can't write %s", out_file.c_str());
+    fclose(f);
+    if (mfkc_write_stat_file(st_file.c_str(), hist.data()) != MFKC_OK) die("Can't write %s", st_file.c_str());
+    report_sample(k, st_sum[0], good, out_file);
+    return out_file;
+}
+
+// src/tools/KmersCounterMain.java:103-116
+void report_sample(int k, uint64_t size, uint64_t good, const std::string &out_file) {
     info("%s k-mers found, %s (%.1f%%) of them is good (not erroneous)", group_digits(size).c_str(), group_digits(good).c_str(),
          good * 100.0 / size);
     if (size == 0) warn("No k-mers found in reads! Perhaps you reads file is empty or k-mer size is too big");
@@ -256,7 +359,6 @@ std::string count_sample(mfkc_ctx *ctx, int k, int b, const std::vector<std::str
     if (size == all) warn("All possible k-mers were found in reads! Perhaps you should increase k-mer size");
     else if (size >= (uint64_t)(all * 0.99)) warn("Almost all possible k-mers were found in reads! Perhaps you should increase k-mer size");
     info("Good k-mers printed to %s", out_file.c_str());
-    return out_file;
 }
 
 mfkc_ctx *make_ctx(int k, const Gpu &g, uint64_t expected_kmers, bool long_kmers = false, int min_seq_len = 0) {
@@ -266,10 +368,11 @@ mfkc_ctx *make_ctx(int k, const Gpu &g, uint64_t expected_kmers, bool long_kmers
     mfkc_cfg cfg; memset(&cfg, 0, sizeof cfg);
     cfg.struct_size = sizeof cfg; cfg.k = k; cfg.device = g.device; cfg.variant = g.variant;
     cfg.expected_kmers = expected_kmers; cfg.min_seq_len = min_seq_len;
+    cfg.n_shards = g.n_shards; cfg.shard_id = g.shard_id;
     mfkc_ctx *ctx = nullptr;
     const int rc = mfkc_create(&cfg, &ctx);
     if (rc != MFKC_OK) die("%s (libmfkc %d)", mfkc_last_error(nullptr), rc);
-    g_ctx_gen++;
+    g_ctx_gen = ++g_ctx_gen_counter;
     return ctx;
 }
 
@@ -321,10 +424,39 @@ int tool_counter(const Args &a, bool many) {
     for (const auto &s : samples) biggest = std::max(biggest, estimate_bases(s.second));
     // -l / --min-seq-len: the counting call of component-cutter's front half, IOUtils.loadReads(sequences, k, minLen)
     // (src/tools/ComponentCutterMain.java:81-82, src/io/IOUtils.java:761); kmer-counter itself passes 0
-    mfkc_ctx *ctx = make_ctx(k, g, biggest, a.has("long-kmers"), parse_int(a, a.has("min-seq-len") ? "min-seq-len" : "l", false, 0));
-    std::vector<std::string> outs;
-    for (const auto &s : samples) outs.push_back(count_sample(ctx, k, b, s.second, s.first, out_dir, st_dir));
-    mfkc_destroy(ctx);
+    const int min_len = parse_int(a, a.has("min-seq-len") ? "min-seq-len" : "l", false, 0);
+    std::vector<std::string> outs(samples.size());
+    const bool logical = getenv("MFKC_LOGICAL_GPUS") != nullptr;          // tests: G contexts on one device
+    if (g.n_gpus > 1 && (g.mode == "shard" || (g.mode == "auto" && samples.size() < (size_t)g.n_gpus))) {
+        // every sample over all GPUs: hash-range sharded, counted out of peer memory, merged (BASELINE config 4)
+        if (k > 31) die("--gpu-mode shard serves k <= 31");
+        std::vector<mfkc_ctx *> ctxs;
+        for (int d = 0; d < g.n_gpus; d++) {
+            Gpu gd = g; gd.device = logical ? g.device : g.device + d; gd.n_shards = g.n_gpus; gd.shard_id = d;
+            ctxs.push_back(make_ctx(k, gd, biggest / g.n_gpus + 1, false, min_len));
+        }
+        for (size_t i = 0; i < samples.size(); i++)
+            outs[i] = count_sample_sharded(ctxs, k, b, samples[i].second, samples[i].first, out_dir, st_dir, std::max<uint64_t>(estimate_bases(samples[i].second), 1u << 20));
+        for (auto *c : ctxs) mfkc_destroy(c);
+    } else if (g.n_gpus > 1) {
+        // batch mode (BASELINE config 3): the samples are independent, so one worker thread and one context per GPU take
+        // them from a shared counter; no exchange at all.  The reference queues one KmersCounterMain per sample
+        // (src/tools/KmersCounterForManyFilesMain.java:80-108).
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> th;
+        for (int d = 0; d < g.n_gpus; d++)
+            th.emplace_back([&, d] {
+                Gpu gd = g; gd.device = logical ? g.device : g.device + d;
+                mfkc_ctx *ctx = make_ctx(k, gd, biggest, a.has("long-kmers"), min_len);
+                for (size_t i; (i = next++) < samples.size();) outs[i] = count_sample(ctx, k, b, samples[i].second, samples[i].first, out_dir, st_dir);
+                mfkc_destroy(ctx);
+            });
+        for (auto &t : th) t.join();
+    } else {
+        mfkc_ctx *ctx = make_ctx(k, g, biggest, a.has("long-kmers"), min_len);
+        for (size_t i = 0; i < samples.size(); i++) outs[i] = count_sample(ctx, k, b, samples[i].second, samples[i].first, out_dir, st_dir);
+        mfkc_destroy(ctx);
+    }
     for (const auto &o : outs) OUT_VALUE("%s\n", o.c_str());              // "resulting-kmers-files"
     return 0;
 }

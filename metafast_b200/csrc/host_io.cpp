@@ -672,6 +672,15 @@ extern "C" int mfkc_reader_open(const char *path, mfkc_reader **out, char *errbu
     return MFKC_OK;
 }
 
+// NamedSource.name() of readDnaLazy(file) without opening a reader (no threads, no sniff, no I/O beyond nothing at all)
+extern "C" int mfkc_library_name(const char *path, char *out, size_t cap) {
+    if (!path || !out || !cap) return MFKC_E_BADARG;
+    const Format f = detect_format(path);
+    if (f == F_UNKNOWN || f == F_OTHER) { out[0] = 0; return MFKC_E_FORMAT; }
+    snprintf(out, cap, "%s", library_name(path, f).c_str());
+    return MFKC_OK;
+}
+
 extern "C" int mfkc_reader_next(mfkc_reader *r, uint8_t *bases, size_t cap_bases, uint64_t *offsets, uint32_t cap_reads,
                                 uint32_t *n_reads) {
     if (!r || !bases || !offsets || !n_reads) return MFKC_E_BADARG;
@@ -837,5 +846,104 @@ extern "C" int mfkc_synth_reads_host(const mfkc_synth_cfg *cfg, uint64_t first_r
     }
     for (auto &x : th) x.join();
     delete t;
+    return MFKC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Deterministic merge of per-shard record streams (multi-GPU runs, SURVEY.md 8e: "a deterministic sorted
+// merge produces the .kmers.bin output").  Every part is sorted by ascending big-endian key and the parts hold
+// disjoint key sets (one owner shard per k-mer), so the merge is an interleave; equal keys (never produced by the
+// shards) would keep part order.  The key range is cut at sampled splitters and every host thread merges one slice
+// of all parts into its place of `out`, so the result does not depend on the thread count.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct MergePart { const uint8_t *p; uint64_t n; };
+
+inline int key_cmp(const uint8_t *a, const uint8_t *b, uint32_t key_bytes) { return memcmp(a, b, key_bytes); }
+
+// first record of part with key >= key
+uint64_t lower_bound_rec(const MergePart &part, const uint8_t *key, uint32_t rs, uint32_t kb) {
+    uint64_t lo = 0, hi = part.n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (key_cmp(part.p + mid * rs, key, kb) < 0) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+void merge_slice(const std::vector<MergePart> &parts, const std::vector<uint64_t> &b, const std::vector<uint64_t> &e, uint32_t rs, uint32_t kb, uint8_t *out) {
+    const size_t P = parts.size();
+    std::vector<uint64_t> cur(b);
+    // small P (<= 16 shards): a linear scan for the minimum beats a heap
+    if (kb == 8) {
+        std::vector<uint64_t> head(P);
+        auto key_at = [&](size_t i, uint64_t idx) { uint64_t v; memcpy(&v, parts[i].p + idx * rs, 8); return __builtin_bswap64(v); };
+        size_t live = 0;
+        for (size_t i = 0; i < P; i++) if (cur[i] < e[i]) { head[i] = key_at(i, cur[i]); live++; }
+        while (live > 1) {
+            size_t best = P, second = P;                              // smallest head (ties: lowest part), and the next one
+            for (size_t i = 0; i < P; i++) {
+                if (cur[i] >= e[i]) continue;
+                if (best == P || head[i] < head[best]) { second = best; best = i; }
+                else if (second == P || head[i] < head[second]) second = i;
+            }
+            // the run of `best` that precedes the head of every other part
+            const uint64_t limit = head[second];
+            uint64_t c = cur[best] + 1;
+            while (c < e[best]) {
+                const uint64_t kk = key_at(best, c);
+                if (kk < limit || (kk == limit && best < second)) c++; else break;
+            }
+            memcpy(out, parts[best].p + cur[best] * rs, (size_t)(c - cur[best]) * rs);
+            out += (size_t)(c - cur[best]) * rs;
+            cur[best] = c;
+            if (c < e[best]) head[best] = key_at(best, c); else live--;
+        }
+        for (size_t i = 0; i < P; i++) if (cur[i] < e[i]) { memcpy(out, parts[i].p + cur[i] * rs, (size_t)(e[i] - cur[i]) * rs); out += (size_t)(e[i] - cur[i]) * rs; }
+        return;
+    }
+    for (;;) {
+        size_t best = P;
+        for (size_t i = 0; i < P; i++)
+            if (cur[i] < e[i] && (best == P || key_cmp(parts[i].p + cur[i] * rs, parts[best].p + cur[best] * rs, kb) < 0)) best = i;
+        if (best == P) break;
+        memcpy(out, parts[best].p + cur[best] * rs, rs);
+        out += rs; cur[best]++;
+    }
+}
+}  // namespace
+
+extern "C" int mfkc_merge_records(const uint8_t *const *parts_in, const uint64_t *n_records, uint32_t n_parts, uint32_t record_size,
+                                  uint8_t *out, int threads) {
+    if ((!parts_in || !n_records) && n_parts) return MFKC_E_BADARG;
+    if (record_size != 10 && record_size != 18) return MFKC_E_BADARG;
+    const uint32_t kb = record_size - 2;
+    std::vector<MergePart> parts;
+    uint64_t total = 0, biggest = 0; size_t big_i = 0;
+    for (uint32_t i = 0; i < n_parts; i++) {
+        if (n_records[i] && !parts_in[i]) return MFKC_E_BADARG;
+        parts.push_back({parts_in[i], n_records[i]});
+        total += n_records[i];
+        if (n_records[i] > biggest) { biggest = n_records[i]; big_i = i; }
+    }
+    if (!total) return MFKC_OK;
+    if (!out) return MFKC_E_BADARG;
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    uint32_t T = (uint32_t)std::min<uint64_t>((uint64_t)std::min(threads, 64), std::max<uint64_t>(1, total >> 16));
+    // slice j = keys in [splitter[j-1], splitter[j]); splitters = quantiles of the biggest part
+    std::vector<std::vector<uint64_t>> cut(T + 1, std::vector<uint64_t>(parts.size()));
+    for (size_t i = 0; i < parts.size(); i++) { cut[0][i] = 0; cut[T][i] = parts[i].n; }
+    for (uint32_t j = 1; j < T; j++) {
+        const uint8_t *sk = parts[big_i].p + (biggest * j / T) * record_size;
+        for (size_t i = 0; i < parts.size(); i++) cut[j][i] = std::max(cut[j - 1][i], lower_bound_rec(parts[i], sk, record_size, kb));
+    }
+    std::vector<uint64_t> out_off(T + 1, 0);
+    for (uint32_t j = 1; j <= T; j++) { uint64_t s = 0; for (size_t i = 0; i < parts.size(); i++) s += cut[j][i]; out_off[j] = s; }
+    std::vector<std::thread> th;
+    for (uint32_t j = 0; j < T; j++) {
+        auto work = [&, j] { merge_slice(parts, cut[j], cut[j + 1], record_size, kb, out + out_off[j] * record_size); };
+        if (T == 1) work(); else th.emplace_back(work);
+    }
+    for (auto &t : th) t.join();
     return MFKC_OK;
 }

@@ -108,6 +108,8 @@ struct mfkc_ctx {
     // peer-memory shard exchange
     uint4 *p2p_recs = nullptr; unsigned int *p2p_cursor = nullptr; unsigned long long *p2p_kc = nullptr;
     uint64_t p2p_seg_cap = 0; int p2p_log2 = 0;
+    bool p2p_bins = false;             // staging laid out for the bin-local count: (owner, bin) segments + overflow list
+    uint32_t p2p_B = 0; uint64_t p2p_ovf_cap = 0, p2p_kmers_in = 0, p2p_n_cursor = 0;
     const uint4 *p2p_peer_recs[P2P_MAX_PEERS] = {nullptr}; const unsigned int *p2p_peer_cursor[P2P_MAX_PEERS] = {nullptr};
     bool p2p_ipc[P2P_MAX_PEERS] = {false};
     const uint4 **d_peer_recs = nullptr; const unsigned int **d_peer_cursor = nullptr;    // device copies of the pointer tables (128-bit drain)
@@ -381,7 +383,7 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
         // bin-local counting (bincount.cuh) unless the caller pinned the table geometry or asked for the table variant
         static const int env_bins = getenv("MFKC_BINS") ? atoi(getenv("MFKC_BINS")) : 1;
         ctx->bins_ok = env_bins && !force_table && ctx->place == 1 && !ctx->k128 && !ctx->soa && !ctx->smem_drain &&
-                       cfg->table_slots == 0 && cfg->staging_bytes == 0 && cfg->region_shift == 0 && cfg->n_shards <= 1;
+                       cfg->table_slots == 0 && cfg->staging_bytes == 0 && cfg->region_shift == 0;
         if (ctx->bins_ok)
             CR_TRY(cudaFuncSetAttribute(bin_count_kernel<BC_LOG2S, BC_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)bin_count_smem_bytes<BC_LOG2S, BC_THREADS>()));
@@ -852,6 +854,13 @@ static int extract_grid(const mfkc_ctx *ctx, uint64_t n_bases) {
 // ------------------------------------------------------------------------------------------
 static SkmStage bin_stage(const mfkc_ctx *ctx) {
     SkmStage st{};
+    if (ctx->p2p_bins) {             // sharded: segment (owner * B + bin) of this rank's own staging buffer, extract mode 4
+        const uint64_t G = (uint64_t)std::max(1, ctx->cfg.n_shards);
+        st.recs = ctx->p2p_recs; st.cursor = ctx->p2p_cursor; st.seg_cap = ctx->p2p_seg_cap;
+        st.n_regions = (uint32_t)G; st.region_shift = 0; st.win = ctx->p2p_B;
+        st.ovf = st.recs + G * ctx->p2p_B * ctx->p2p_seg_cap; st.ovf_cursor = ctx->p2p_cursor + G * ctx->p2p_B; st.ovf_cap = (uint32_t)ctx->p2p_ovf_cap;
+        return st;
+    }
     st.recs = reinterpret_cast<uint4 *>(ctx->rb_keys); st.cursor = ctx->rb_cursor;
     st.seg_cap = ctx->os_seg_cap; st.n_regions = ctx->os_n_bins; st.region_shift = 0; st.win = 0;
     st.ovf = st.recs + (uint64_t)ctx->os_n_bins * ctx->os_seg_cap; st.ovf_cursor = &ctx->d_binctl->ovf_cursor; st.ovf_cap = (uint32_t)ctx->os_ovf_cap;
@@ -859,6 +868,12 @@ static SkmStage bin_stage(const mfkc_ctx *ctx) {
 }
 static BinSrc bin_src(const mfkc_ctx *ctx) {
     BinSrc b{};
+    if (ctx->p2p_bins) {             // this shard's bins in every peer's staging buffer (peer memory over NVLink)
+        const uint32_t G = (uint32_t)std::max(1, ctx->cfg.n_shards);
+        for (uint32_t i = 0; i < G; i++) { b.recs[i] = ctx->p2p_peer_recs[i]; b.cursor[i] = ctx->p2p_peer_cursor[i]; }
+        b.seg_cap = ctx->p2p_seg_cap; b.n_src = G; b.seg0 = (uint32_t)ctx->cfg.shard_id * ctx->p2p_B; b.rot = (uint32_t)ctx->cfg.shard_id;
+        return b;
+    }
     b.recs[0] = reinterpret_cast<const uint4 *>(ctx->rb_keys); b.cursor[0] = ctx->rb_cursor;
     b.seg_cap = ctx->os_seg_cap; b.n_src = 1; b.seg0 = 0; b.rot = 0;
     return b;
@@ -870,7 +885,7 @@ static BinSrc bin_src(const mfkc_ctx *ctx) {
 // (bins_to_table), never results.
 static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
     ctx->mode = 0;
-    if (!ctx->bins_ok) return MFKC_OK;
+    if (!ctx->bins_ok || ctx->cfg.n_shards > 1) return MFKC_OK;         // sharded contexts stage through mfkc_p2p_*
     const int k = ctx->cfg.k;
     uint64_t expect = ctx->cfg.expected_kmers ? ctx->cfg.expected_kmers
                     : (ctx->prev_sample_kmers_exact ? ctx->prev_sample_kmers_exact + ctx->prev_sample_kmers_exact / 8 : 0);
@@ -935,12 +950,40 @@ static int launch_heavy(mfkc_ctx *ctx, uint32_t e0, uint32_t e1, bool ovf, const
         drain_heavy_kernel<<<(e1 - e0) * bpe, 256, 0, ctx->compute>>>(bin_src(ctx), ctx->d_heavy + e0, e1 - e0, bpe, ctx->cfg.k, ctx->tab, g, ctx->d_ctr);
         CU_TRY(cudaGetLastError());
     }
-    if (ovf) {
+    if (ovf && ctx->p2p_bins) {      // every peer's overflow list, filtered by owner
+        const uint32_t G = (uint32_t)std::max(1, ctx->cfg.n_shards);
+        const uint64_t n_seg = (uint64_t)G * ctx->p2p_B;
+        for (uint32_t i = 0; i < G; i++) {
+            ctx->prof_launches[P_DRAIN_HEAVY]++;
+            drain_ovf_kernel<<<ctx->sm_count * 2, 256, 0, ctx->compute>>>(ctx->p2p_peer_recs[i] + n_seg * ctx->p2p_seg_cap, ctx->p2p_peer_cursor[i] + n_seg,
+                                                                          (uint32_t)ctx->p2p_ovf_cap, G, (uint32_t)ctx->cfg.shard_id, ctx->cfg.k, ctx->tab, g, ctx->d_ctr);
+            CU_TRY(cudaGetLastError());
+        }
+    } else if (ovf) {
         const SkmStage st = bin_stage(ctx);
         ctx->prof_launches[P_DRAIN_HEAVY]++;
         drain_ovf_kernel<<<ctx->sm_count * 4, 256, 0, ctx->compute>>>(st.ovf, st.ovf_cursor, st.ovf_cap, 1u, 0u, ctx->cfg.k, ctx->tab, g, ctx->d_ctr);
         CU_TRY(cudaGetLastError());
     }
+    return MFKC_OK;
+}
+
+// records in the overflow list(s) this context has to look at (an upper bound of its own share when sharded)
+static int overflow_records(mfkc_ctx *ctx, uint64_t *n) {
+    *n = 0;
+    if (ctx->p2p_bins) {
+        const uint32_t G = (uint32_t)std::max(1, ctx->cfg.n_shards);
+        const uint64_t n_seg = (uint64_t)G * ctx->p2p_B;
+        for (uint32_t i = 0; i < G; i++) {
+            unsigned int c = 0;
+            CU_TRY(cudaMemcpy(&c, ctx->p2p_peer_cursor[i] + n_seg, sizeof c, cudaMemcpyDeviceToHost));
+            *n += std::min<uint64_t>(c, ctx->p2p_ovf_cap);
+        }
+        return MFKC_OK;
+    }
+    unsigned int c = 0;
+    CU_TRY(cudaMemcpy(&c, &ctx->d_binctl->ovf_cursor, sizeof c, cudaMemcpyDeviceToHost));
+    *n = std::min<uint64_t>(c, ctx->os_ovf_cap);
     return MFKC_OK;
 }
 
@@ -961,7 +1004,7 @@ static int bins_to_table(mfkc_ctx *ctx) {
     CU_TRY(cudaMemsetAsync(&ctx->d_ctr->distinct, 0, sizeof(unsigned long long), ctx->compute));
     CU_TRY(cudaMemsetAsync(&ctx->d_ctr->bc_distinct, 0, sizeof(unsigned long long), ctx->compute));
     ctx->distinct_ub = ctx->distinct_base = 0; ctx->kmers_base = ctx->h_ctr->kmers; ctx->recv_since_base = 0;
-    const uint64_t staged = ctx->h_ctr->kmers;                      // exact k-mer instances extracted so far
+    const uint64_t staged = ctx->p2p_bins ? ctx->p2p_kmers_in : ctx->h_ctr->kmers;      // exact k-mer instances staged for this context
     if (staged) {
         const uint32_t nb = ctx->os_n_bins;
         heavy_all_bins_kernel<<<grid_for(ctx, nb, 256, 4), 256, 0, ctx->compute>>>(ctx->d_heavy, nb);
@@ -981,16 +1024,18 @@ static int bins_to_table(mfkc_ctx *ctx) {
             TRY(launch_heavy(ctx, b0, b1, false, table_geom(ctx)));
         }
         TRY(sync_all(ctx));
-        CU_TRY(cudaMemcpy(ctx->h_binctl, ctx->d_binctl, sizeof(BinCtl), cudaMemcpyDeviceToHost));
-        const uint64_t n_ovf = std::min<uint64_t>(ctx->h_binctl->ovf_cursor, ctx->os_ovf_cap);
+        uint64_t n_ovf = 0;
+        TRY(overflow_records(ctx, &n_ovf));
         if (n_ovf) {
             TRY(reserve_slots(ctx, 16 * n_ovf));
             ctx->recv_since_base += 16 * n_ovf;
             TRY(launch_heavy(ctx, 0, 0, true, table_geom(ctx)));
         }
     }
-    CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS_SKM * sizeof(unsigned int), ctx->compute));
-    CU_TRY(cudaMemsetAsync(ctx->d_binctl, 0, sizeof(BinCtl), ctx->compute));
+    if (!ctx->p2p_bins) {            // (a sharded context leaves the staging buffers alone: the peers read them too)
+        CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS_SKM * sizeof(unsigned int), ctx->compute));
+        CU_TRY(cudaMemsetAsync(ctx->d_binctl, 0, sizeof(BinCtl), ctx->compute));
+    }
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
     ctx->distinct_ub = ctx->distinct_base = ctx->h_ctr->distinct;
@@ -1042,7 +1087,7 @@ static int bins_count(mfkc_ctx *ctx, uint32_t thr) {
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
     free_bin_outputs(ctx);
-    const uint64_t kmers = ctx->h_ctr->kmers;
+    const uint64_t kmers = ctx->p2p_bins ? ctx->p2p_kmers_in : ctx->h_ctr->kmers;
     uint64_t out_cap = 0;
     if (want_out) {
         const double R = ctx->os_R > 0 ? ctx->os_R : 3.0;
@@ -1072,7 +1117,8 @@ static int bins_count(mfkc_ctx *ctx, uint32_t thr) {
         CU_TRY(cudaMemcpyAsync(ctx->h_binctl, ctx->d_binctl, sizeof(BinCtl), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
         const BinCtl c = *ctx->h_binctl;
-        const uint64_t n_ovf = std::min<uint64_t>(c.ovf_cursor, ctx->os_ovf_cap);
+        uint64_t n_ovf = 0;
+        TRY(overflow_records(ctx, &n_ovf));
         ctx->os_heavy_bins = c.n_heavy; ctx->os_heavy_recs = c.heavy_recs; ctx->os_splits = c.n_split; ctx->os_ovf = n_ovf; ctx->os_total_recs = c.total_recs;
         if (c.heavy_overflow) {                                  // more heavy entries than the list holds: the table takes the sample
             TMP_FREE(ok); TMP_FREE(oc);
@@ -1896,6 +1942,56 @@ extern "C" int mfkc_p2p_stage_create(mfkc_ctx *ctx, uint32_t log2_buckets, uint6
     CU_TRY(cudaMemset(ctx->p2p_cursor, 0, n_seg * sizeof(unsigned int)));
     CU_TRY(cudaMemset(ctx->p2p_kc, 0, P2P_MAX_PEERS * sizeof(unsigned long long)));
     ctx->p2p_seg_cap = seg_cap; ctx->p2p_log2 = (int)log2_buckets;
+    ctx->p2p_bins = false; ctx->p2p_n_cursor = n_seg;
+    return MFKC_OK;
+}
+
+// Geometry of the bin-local peer-memory staging, the same on every rank: a shard receives about what a rank sends
+// (kmers_per_rank instances); its bins are sized so that the distinct k-mers of one bin load the shared-memory table to
+// ~0.45 (instances_per_distinct: 0 = unknown, 3 assumed); every (sender, owner, bin) segment gets `slack` (0 = 2.0)
+// times its expected records (one record per 16-base word + one per minimizer change), the overflow list 6 %.
+extern "C" int mfkc_p2p_bin_geometry(uint64_t kmers_per_rank, uint32_t n_shards, int k, double instances_per_distinct, double slack,
+                                     uint32_t *bins_per_shard, uint64_t *seg_cap, uint64_t *ovf_cap) {
+    if (!bins_per_shard || !seg_cap || !ovf_cap || n_shards < 1 || k < 1) return MFKC_E_BADARG;
+    const double R = instances_per_distinct >= 1.0 ? instances_per_distinct : 3.0;
+    const double sl = slack > 0 ? slack : 2.0;
+    const int w = k - minimizer_len(k) + 1;
+    const double rpk = std::min(1.0, (1.0 / 16 + 2.0 / (w + 1)) * 1.2);
+    const double kmers = (double)kmers_per_rank * 1.03 + 4096.0;
+    uint64_t bins = (uint64_t)(kmers / R / (0.45 * (double)(1u << BC_LOG2S))) + 1;
+    bins = std::min<uint64_t>(std::max<uint64_t>(bins, 16), 1ull << 24);
+    const double recs = kmers * rpk;
+    *bins_per_shard = (uint32_t)bins;
+    *seg_cap = (uint64_t)(recs / ((double)n_shards * (double)bins) * sl) + 64;
+    *ovf_cap = std::max<uint64_t>((uint64_t)(recs * 0.06), 1ull << 16);
+    return MFKC_OK;
+}
+
+// Staging for the bin-local count over peer memory: n_shards x bins_per_shard segments of seg_cap records, then the
+// overflow list (ovf_cap records); cursors: one per segment + the overflow cursor.  Every rank passes the same geometry.
+extern "C" int mfkc_p2p_stage_create_bins(mfkc_ctx *ctx, uint32_t bins_per_shard, uint64_t seg_cap, uint64_t ovf_cap) {
+    TRY(p2p_check(ctx));
+    if (!ctx->bins_ok) return fail(ctx, MFKC_E_STATE, "the bin-local exchange needs MFKC_VARIANT_HASH with k <= 31 and no pinned table geometry");
+    if (bins_per_shard == 0 || bins_per_shard > (1u << 24) || seg_cap == 0 || seg_cap > 0x7fffffffull || ovf_cap == 0 || ovf_cap > 0x7fffffffull)
+        return fail(ctx, MFKC_E_BADARG, "bad p2p staging geometry");
+    CU_TRY(cudaSetDevice(ctx->device));
+    TRY(sync_all(ctx));
+    cudaFree(ctx->p2p_recs); cudaFree(ctx->p2p_cursor); cudaFree(ctx->p2p_kc);
+    ctx->p2p_recs = nullptr; ctx->p2p_cursor = nullptr; ctx->p2p_kc = nullptr;
+    const uint64_t n_seg = (uint64_t)std::max(1, ctx->cfg.n_shards) * bins_per_shard;
+    if (big_alloc(ctx, (void **)&ctx->p2p_recs, (n_seg * seg_cap + ovf_cap) * sizeof(uint4)) != cudaSuccess) return fail(ctx, MFKC_E_OOM, "cannot allocate the p2p staging buffer");
+    CU_TRY(cudaMalloc(&ctx->p2p_cursor, (n_seg + 1) * sizeof(unsigned int)));
+    CU_TRY(cudaMalloc(&ctx->p2p_kc, P2P_MAX_PEERS * sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(ctx->p2p_cursor, 0, (n_seg + 1) * sizeof(unsigned int)));
+    CU_TRY(cudaMemset(ctx->p2p_kc, 0, P2P_MAX_PEERS * sizeof(unsigned long long)));
+    ctx->p2p_seg_cap = seg_cap; ctx->p2p_log2 = 0; ctx->p2p_bins = true; ctx->p2p_B = bins_per_shard; ctx->p2p_ovf_cap = ovf_cap;
+    ctx->p2p_n_cursor = n_seg + 1;
+    ctx->os_n_bins = bins_per_shard; ctx->os_seg_cap = seg_cap; ctx->os_ovf_cap = ovf_cap;
+    if (ctx->heavy_cap < (uint64_t)bins_per_shard + 4096) {
+        cudaFree(ctx->d_heavy); ctx->d_heavy = nullptr;
+        ctx->heavy_cap = bins_per_shard + bins_per_shard / 4 + 4096;
+        CU_TRY(cudaMalloc(&ctx->d_heavy, (size_t)ctx->heavy_cap * sizeof(HeavyEnt)));
+    }
     return MFKC_OK;
 }
 
@@ -1933,7 +2029,8 @@ extern "C" int mfkc_p2p_attach(mfkc_ctx *ctx, uint32_t rank, const uint8_t handl
 extern "C" int mfkc_p2p_attach_ctx(mfkc_ctx *ctx, uint32_t rank, mfkc_ctx *peer) {
     TRY(p2p_check(ctx));
     if (!peer || !peer->p2p_recs || rank >= (uint32_t)std::max(1, ctx->cfg.n_shards)) return fail(ctx, MFKC_E_BADARG, "bad peer");
-    if (peer->p2p_seg_cap != ctx->p2p_seg_cap || peer->p2p_log2 != ctx->p2p_log2) return fail(ctx, MFKC_E_BADARG, "peer staging geometry differs");
+    if (peer->p2p_seg_cap != ctx->p2p_seg_cap || peer->p2p_log2 != ctx->p2p_log2 || peer->p2p_bins != ctx->p2p_bins || peer->p2p_B != ctx->p2p_B ||
+        peer->p2p_ovf_cap != ctx->p2p_ovf_cap) return fail(ctx, MFKC_E_BADARG, "peer staging geometry differs");
     if (peer->device != ctx->device) {
         CU_TRY(cudaSetDevice(ctx->device));
         cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
@@ -1948,16 +2045,21 @@ extern "C" int mfkc_p2p_stage_reset(mfkc_ctx *ctx) {
     TRY(p2p_check(ctx));
     if (!ctx->p2p_recs) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
-    const uint64_t n_seg = (uint64_t)std::max(1, ctx->cfg.n_shards) << ctx->p2p_log2;
-    CU_TRY(cudaMemsetAsync(ctx->p2p_cursor, 0, n_seg * sizeof(unsigned int), ctx->compute));
+    CU_TRY(cudaMemsetAsync(ctx->p2p_cursor, 0, ctx->p2p_n_cursor * sizeof(unsigned int), ctx->compute));
     CU_TRY(cudaMemsetAsync(ctx->p2p_kc, 0, P2P_MAX_PEERS * sizeof(unsigned long long), ctx->compute));
+    ctx->p2p_kmers_in = 0;
+    if (ctx->p2p_bins) { ctx->os_counted = false; if (ctx->mode == 1) ctx->mode = 0; }
     return MFKC_OK;
 }
 
 static int p2p_extract_batch(mfkc_ctx *ctx, Staging &s, const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t n_reads, uint64_t n_bases) {
     const int k = ctx->cfg.k;
     TRY(launch_mark(ctx, s, d_offsets, n_reads, n_bases, ctx->cfg.min_seq_len, 1, ctx->d_ctr));
-    if (n_bases >= (uint64_t)k) {
+    if (n_bases >= (uint64_t)k && ctx->p2p_bins) {
+        ProfScope ps(ctx, P_EXTRACT_BUCKET, ctx->compute);
+        extract_skm_kernel<4, TabAoS><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
+            d_bases, n_bases, s.d_flags, k, bin_stage(ctx), TabAoS{nullptr, 0}, ctx->d_ctr, ctx->p2p_kc);
+    } else if (n_bases >= (uint64_t)k) {
         SkmStage st{};
         st.recs = ctx->p2p_recs; st.cursor = ctx->p2p_cursor; st.seg_cap = ctx->p2p_seg_cap;
         st.n_regions = (uint32_t)std::max(1, ctx->cfg.n_shards); st.region_shift = ctx->p2p_log2; st.win = 0;
@@ -2010,6 +2112,13 @@ extern "C" int mfkc_p2p_drain(mfkc_ctx *ctx, uint64_t n_kmers_in) {
     TRY(p2p_check(ctx));
     const uint32_t ns = (uint32_t)std::max(1, ctx->cfg.n_shards);
     for (uint32_t i = 0; i < ns; i++) if (!ctx->p2p_peer_recs[i]) return fail(ctx, MFKC_E_STATE, "mfkc_p2p_drain: not every peer is attached");
+    if (ctx->p2p_bins) {
+        // bin-local: nothing is counted yet -- the result calls (stats / histogram / emit_begin) run bin_count_kernel over the
+        // peers' staging buffers, which therefore must stay untouched until every rank has fetched its results
+        ctx->p2p_kmers_in = n_kmers_in; ctx->mode = 1; ctx->sample_open = true; ctx->os_counted = false;
+        ctx->dirty = true; ctx->hist_valid = false; ctx->em_valid = false;
+        return MFKC_OK;
+    }
     if (n_kmers_in == 0) return MFKC_OK;
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(ensure_table_mode(ctx));

@@ -16,7 +16,6 @@ The exchange helpers are backend-agnostic so that the host logic is testable wit
 """
 from __future__ import annotations
 
-import heapq
 from typing import List, Sequence
 
 import numpy as np
@@ -66,12 +65,21 @@ def exchange_keys(dist, send, send_counts: Sequence[int], recv, recv_counts: Seq
     return n_recv
 
 
-def merge_sorted_records(parts: Sequence[bytes], record_size: int = 10) -> bytes:
-    """Deterministic k-way merge by key of per-shard key-sorted record streams (big-endian keys
-    compare like the byte strings themselves)."""
-    def recs(b):
-        return (b[i:i + record_size] for i in range(0, len(b), record_size))
-    return b"".join(heapq.merge(*[recs(p) for p in parts]))
+def merge_sorted_records(parts: Sequence[bytes], record_size: int = 10, threads: int = 0) -> bytes:
+    """Deterministic k-way merge by key of per-shard key-sorted record streams: libmfkc's native, multi-threaded
+    mfkc_merge_records (host C++; the shards own disjoint key sets, so the merge is an interleave)."""
+    import ctypes as C
+    from . import _abi
+    lib = _abi.load()
+    arrs = [np.frombuffer(p, dtype=np.uint8) if len(p) else np.zeros(1, dtype=np.uint8) for p in parts]
+    n = np.array([len(p) // record_size for p in parts], dtype=np.uint64)
+    ptrs = (C.c_void_p * max(len(parts), 1))(*[a.ctypes.data for a in arrs])
+    out = np.empty(int(n.sum()) * record_size or 1, dtype=np.uint8)
+    rc = lib.mfkc_merge_records(C.cast(ptrs, C.c_void_p), n.ctypes.data_as(_abi.u64p), len(parts), record_size,
+                                out.ctypes.data_as(C.c_void_p), threads)
+    if rc != 0:
+        raise _abi.MfkcError(rc, "mfkc_merge_records")
+    return out[: int(n.sum()) * record_size].tobytes()
 
 
 def exchange_table(dist, rows: Sequence[Sequence[int]], device=None):
@@ -187,6 +195,18 @@ def p2p_geometry(kmers_per_rank: int, world: int, table_bytes_per_rank: int = 0)
     return log2, seg_cap
 
 
+def p2p_bin_geometry(kmers_per_rank: int, world: int, k: int, instances_per_distinct: float = 0.0, slack: float = 0.0):
+    """(bins per shard, records per segment, overflow-list records) of the bin-local peer-memory staging:
+    libmfkc's mfkc_p2p_bin_geometry (host arithmetic; every rank computes the same numbers)."""
+    import ctypes as C
+    from . import _abi
+    bins, seg, ovf = C.c_uint32(), C.c_uint64(), C.c_uint64()
+    rc = _abi.load().mfkc_p2p_bin_geometry(kmers_per_rank, world, k, instances_per_distinct, slack, C.byref(bins), C.byref(seg), C.byref(ovf))
+    if rc != 0:
+        raise _abi.MfkcError(rc, "mfkc_p2p_bin_geometry")
+    return bins.value, seg.value, ovf.value
+
+
 class P2PShardedStep:
     """Per-rank driver of the sharded counting pass over peer memory (default of bench.py for N > 1).
 
@@ -201,8 +221,14 @@ class P2PShardedStep:
         self.kc, self.dist, self.world, self.rank, self.torch = kc, dist, world, rank, torch
         self.batch_reads, self.read_len, self.k = batch_reads, read_len, k
         kmers = reads_per_rank * (read_len - k + 1)
-        self.log2, self.seg_cap = p2p_geometry(kmers, world)
-        kc.p2p_stage_create(self.log2, self.seg_cap)
+        from . import _abi
+        self.bins = k <= 31 and getattr(kc, "variant", _abi.VARIANT_HASH) == _abi.VARIANT_HASH
+        if self.bins:                  # bin-local count straight out of the peers' staging buffers
+            self.n_bins, self.seg_cap, self.ovf_cap = p2p_bin_geometry(kmers, world, k)
+            kc.p2p_stage_create_bins(self.n_bins, self.seg_cap, self.ovf_cap)
+        else:                          # region-blocked table drained from peer memory (k > 31, MFKC_VARIANT_HASH_TABLE)
+            self.log2, self.seg_cap = p2p_geometry(kmers, world)
+            kc.p2p_stage_create(self.log2, self.seg_cap)
         mine = torch.frombuffer(bytearray(kc.p2p_export()), dtype=torch.uint8)
         if dist.get_backend() == "nccl":
             mine = mine.cuda()

@@ -66,6 +66,10 @@ class _StubCounter:
     def p2p_stage_create(self, log2_buckets, seg_cap):
         self.log.append(("create", log2_buckets, seg_cap))
 
+    def p2p_stage_create_bins(self, bins_per_shard, seg_cap, ovf_cap):
+        assert bins_per_shard >= 16 and seg_cap > 0 and ovf_cap > 0
+        self.log.append(("create", bins_per_shard, seg_cap, ovf_cap))
+
     def p2p_export(self):
         return (b"rank%03d" % self.rank).ljust(128, b".")
 

@@ -23,12 +23,31 @@ def run_cli(*args, ok=True):
     return r
 
 
-@pytest.mark.parametrize("variant", ["hash", "sort", "direct"])
+@pytest.mark.parametrize("variant", ["hash", "sort", "direct", "table"])
 def test_kmer_counter_many_config1(built, tmp_path, variant):
     """BASELINE config 1 through the CLI: default -b (1), default output locations."""
     files = [os.path.join(INPUTS, "meta_test_%d.fa" % n) for n in (3, 1, 2)]
     wd = tmp_path / "wd"
     r = run_cli("-t", "kmer-counter-many", "-k", 31, "-i", *files, "-w", wd, "--gpu-variant", variant)
+    want = orc.kmer_counter_many(files, 31, 1)
+    assert r.stdout.split() == [str(wd / "kmers" / ("meta_test_%d.kmers.bin" % n)) for n in (1, 2, 3)]
+    for name, (rec, stat, counts) in want.items():
+        assert open(wd / "kmers" / (name + ".kmers.bin"), "rb").read() == rec
+        assert open(wd / "stats" / (name + ".stat.txt")).read() == stat
+    assert "17'063 k-mers found, 16'918 (99.2%) of them is good (not erroneous)" in r.stderr
+
+
+@pytest.mark.parametrize("gpus,mode", [(2, "shard"), (3, "shard"), (2, "samples"), (8, "auto")])
+def test_kmer_counter_many_multi_gpu(built, tmp_path, gpus, mode):
+    """--gpus G: hash-range sharded over G contexts with the native merge (shard), or one sample per context at a time
+    (samples); with fewer samples than GPUs `auto` shards.  Logical GPUs (G contexts on the one device of the test box,
+    same kernels and peer pointers as across devices): every file byte-equal to the one-GPU / oracle result."""
+    files = [os.path.join(INPUTS, "meta_test_%d.fa" % n) for n in (3, 1, 2)]
+    wd = tmp_path / "wd"
+    env = dict(os.environ, MFKC_LOGICAL_GPUS="1")
+    r = subprocess.run([CLI, "-t", "kmer-counter-many", "-k", "31", "-i", *files, "-w", str(wd), "--gpus", str(gpus), "--gpu-mode", mode],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    assert r.returncode == 0, r.stderr
     want = orc.kmer_counter_many(files, 31, 1)
     assert r.stdout.split() == [str(wd / "kmers" / ("meta_test_%d.kmers.bin" % n)) for n in (1, 2, 3)]
     for name, (rec, stat, counts) in want.items():

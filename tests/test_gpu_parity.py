@@ -328,7 +328,15 @@ def test_logical_shards_equal_unsharded(built, n_shards):
             shards[s].device_free(d_part)
         # shards hold disjoint key sets: the deterministic merge is a k-way merge by key
         recs = sorted(r for part in merged for r in (part[i:i + 10] for i in range(0, len(part), 10)))
-        assert b"".join(recs) == want_rec
+        if b"".join(recs) != want_rec:                  # say what differs (key, got, want, owner shard)
+            got_d = {}
+            for sh, part in enumerate(merged):
+                for key, c in orc.load_kmers_bin(part):
+                    got_d.setdefault(key, []).append((c, sh))
+            want_d = dict(orc.load_kmers_bin(want_rec))
+            diff = [(hex(key), got_d.get(key), want_d.get(key), lib.mfkc_owner_shard(key, n_shards))
+                    for key in sorted(set(got_d) | set(want_d)) if [c for c, _ in got_d.get(key, [])] != ([want_d[key]] if key in want_d else [])]
+            raise AssertionError("records differ (%d keys): %r; part sizes %r, counts %r" % (len(diff), diff[:8], [len(p_) // 10 for p_ in merged], counts))
         assert (hist == want_hist).all()
         src.device_free(d_b); src.device_free(d_o); src.device_free(d_keys)
     finally:
@@ -439,6 +447,70 @@ def test_logical_shards_peer_memory_exchange(built, n_shards, log2_buckets):
             assert stats.tolist() == want_stats
             for s, d_b, d_o in bufs:
                 s.device_free(d_b); s.device_free(d_o)
+    finally:
+        for s in shards:
+            s.close()
+
+
+@pytest.mark.parametrize("n_shards,bins,slack", [(1, 40, 2.0), (2, 64, 2.0), (4, 3, 2.0), (8, 16, 0.5), (11, 1, 2.0)])
+def test_logical_shards_bin_local_exchange(built, n_shards, bins, slack):
+    """The bin-local count over peer memory (mfkc_p2p_stage_create_bins) with G contexts on one GPU: every shard stages
+    ITS slice of the reads per (owner, bin); every owner counts its bins in shared memory straight out of all G staging
+    buffers.  Few bins force split passes and heavy bins, slack < 1 the overflow lists.  Merged records, summed
+    histograms, distinct counts and read statistics must equal the unsharded result."""
+    from metafast_b200.sharded import merge_sorted_records
+    cfg = m.synth_cfg(total_genome_bp=100000, n_genomes=4, n_read_ppm=0)
+    n = 6000
+    raw = m.synth_reads_host(cfg, 0, n)
+    bases = np.ascontiguousarray(raw).reshape(-1)
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(cfg.read_len)
+    want_rec, want_hist, want_distinct, want_stats = _oracle_c.count(bases, offsets, 31, 1, P=2)
+    shards = [m.KmerCounter(31, n_shards=n_shards, shard_id=s) for s in range(n_shards)]
+    try:
+        recs_est = n * 120 * 0.19
+        seg_cap = int(recs_est / (n_shards * n_shards * bins) * slack) + 8
+        for s in shards:
+            s.p2p_stage_create_bins(bins, seg_cap, 1 << 18)
+        for s in shards:
+            for r, peer in enumerate(shards):
+                s.p2p_attach_ctx(r, peer)
+        bounds = np.linspace(0, n, n_shards + 1).astype(int) // 8 * 8
+        bounds[-1] = n
+        for rep in range(2):
+            for s in shards:
+                s.reset()
+            for s in shards:
+                s.p2p_stage_reset()
+            for r, s in enumerate(shards):
+                lo, hi = int(bounds[r]), int(bounds[r + 1])
+                if hi > lo:
+                    s.p2p_submit(bases, offsets[lo: (lo + hi) // 2 + 1])
+                    s.p2p_submit(bases, offsets[(lo + hi) // 2: hi + 1])
+            counts = [s.p2p_counts(n_shards) for s in shards]
+            assert sum(sum(c) for c in counts) == n * (cfg.read_len - 30)
+            for r, s in enumerate(shards):
+                s.p2p_drain(sum(c[r] for c in counts))
+                s.flush()
+            merged, hist, stats, distinct = [], np.zeros(m.HIST_BINS, dtype=np.uint64), np.zeros(4, dtype=np.int64), 0
+            seen = {"heavy_entries": 0, "split_passes": 0, "overflow_recs": 0}
+            for s in shards:
+                merged.append(s.emit(1))
+                hist += s.histogram()
+                st = s.stats()
+                distinct += st["distinct"]
+                stats += np.array([st["total_seq"], st["good_seq"], st["total_len"], st["good_len"]])
+                bs = s.bin_stats()
+                assert bs["bin_mode"] == 1
+                for key in seen:
+                    seen[key] += bs[key]
+            assert merge_sorted_records(merged) == want_rec
+            assert (hist == want_hist).all()
+            assert distinct == want_distinct
+            assert stats.tolist() == want_stats
+            if bins <= 3:
+                assert seen["split_passes"] + seen["heavy_entries"] > 0, seen
+            if slack < 1:
+                assert seen["overflow_recs"] > 0 and seen["heavy_entries"] > 0, seen
     finally:
         for s in shards:
             s.close()

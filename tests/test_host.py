@@ -772,3 +772,28 @@ def test_fastq_ingest_of_the_golden_samples(built, tmp_path):
         (tmp_path / ("b%d.fastq.gz" % n)).write_bytes(_bgzf(text, block=5000))
         for name in ("s%d.fastq", "g%d.fastq.gz", "b%d.fastq.gz"):
             assert m.read_file_reads(str(tmp_path / (name % n))) == want, name
+
+
+@pytest.mark.parametrize("record_size,n_parts,threads", [(10, 1, 1), (10, 2, 1), (10, 8, 0), (10, 11, 3), (18, 4, 0)])
+def test_native_record_merge(built, record_size, n_parts, threads):
+    """mfkc_merge_records (multi-GPU output merge): interleave of per-shard key-sorted streams, any thread count."""
+    from metafast_b200.sharded import merge_sorted_records
+    rng = np.random.default_rng(record_size * 100 + n_parts)
+    kb = record_size - 2
+    n = 300_000 if threads != 1 else 20_000
+    keys = np.unique(rng.integers(0, 2 ** 62, n, dtype=np.uint64))
+    be = np.zeros((len(keys), record_size), dtype=np.uint8)
+    be[:, kb - 8:kb] = keys.astype(">u8").view(np.uint8).reshape(-1, 8)
+    if kb == 16:
+        be[:, 0:8] = (keys % np.uint64(5)).astype(">u8").view(np.uint8).reshape(-1, 8)     # high word: few values, order decided by both
+    be[:, kb:] = rng.integers(0, 256, (len(keys), 2), dtype=np.uint8)
+    order = np.lexsort(tuple(be[:, i] for i in range(kb - 1, -1, -1)))
+    be = be[order]
+    owner = rng.integers(0, n_parts, len(keys))
+    owner[: len(keys) // 3] = 0                                  # uneven parts, and (n_parts > 1) some part may be empty
+    if n_parts > 2:
+        owner[owner == n_parts - 1] = 1
+    parts = [be[owner == p].tobytes() for p in range(n_parts)]
+    got = merge_sorted_records(parts, record_size, threads)
+    assert got == be.tobytes()
+    assert merge_sorted_records([b""] * n_parts, record_size) == b""
