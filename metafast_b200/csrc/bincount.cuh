@@ -55,6 +55,7 @@ struct BinCountArgs {
     uint32_t thr;                              // output entries with count > thr
     uint32_t limit;                            // claimed slots at which a pass aborts (< 2^BC_LOG2S)
     uint32_t max_recs;                         // bins with more records go straight to the heavy list
+    uint32_t bins_per_cta;                     // a CTA retires after this many bins, so that CTAs of other streams get SMs
     int use_tma;
     unsigned long long *out_keys; uint16_t *out_counts; uint64_t out_cap;
     unsigned long long *hist;
@@ -65,12 +66,10 @@ struct BinCountArgs {
 
 // slot / sub-range hash of the shared-memory table: the top bits pick the slot, the low bits the sub-range
 __host__ __device__ __forceinline__ uint32_t bc_hash(uint64_t key) {
-    uint32_t h = (uint32_t)key * 0x9E3779B1u;
-    h ^= h >> 16;
-    h += (uint32_t)(key >> 32) * 0x85EBCA6Bu;
-    h ^= h >> 13;
+    uint32_t h = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu);
+    h ^= h >> 15;
     h *= 0xC2B2AE35u;
-    return h ^ (h >> 16);
+    return h ^ (h >> 13);
 }
 
 // ---- mbarrier / TMA bulk copy (PTX; SASS: SYNCS.*, UBLKCP) ------------------------------------------------
@@ -94,9 +93,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// shared-memory table accesses by 32-bit shared-space address (the table base stays in one register; no generic-to-shared
+// conversions in the probe loop)
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long cas_shared_u64(uint32_t a, unsigned long long cmp, unsigned long long val) {
+    unsigned long long old;
+    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ void inc_shared_u32(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+
 template <int LOG2S, int NT>
 constexpr size_t bin_count_smem_bytes() {
-    return ((size_t)12 << LOG2S) + (size_t)(NT / 32) * (512 + 2 * 16 * 4) + BC_HIST * 4 + (size_t)(NT / 32) * 8 + (NT / 32) * 4 + 64 * 4 + 64;
+    return ((size_t)12 << LOG2S) + (size_t)(NT / 32) * (512 + 2 * 16 * 4) + BC_HIST * 4 + (size_t)(NT / 32) * 8 + (NT / 32) * 4 + 64 * 4 + (2 * BC_MAX_SRC + 8) * 4 + 64;
 }
 
 template <int LOG2S, int NT>
@@ -114,14 +126,17 @@ bin_count_kernel(const __grid_constant__ BinCountArgs a) {
     unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_hist + BC_HIST);     // NW mbarriers
     uint32_t *s_wgood = reinterpret_cast<uint32_t *>(s_bar + NW);                             // NW
     uint32_t *s_stack = s_wgood + NW;                                                         // 64 (p | P << 16)
-    uint32_t *s_ctl = s_stack + 64;                                                           // bin, sp, claimed, abort, done
+    uint32_t *s_srcstart = s_stack + 64;                                                      // BC_MAX_SRC + 1: first batch of every source
+    uint32_t *s_srcn = s_srcstart + BC_MAX_SRC + 1;                                           // BC_MAX_SRC: records of every source (+ 7 pad)
+    uint32_t *s_ctl = s_srcn + BC_MAX_SRC + 7;                                                // bin, sp, claimed, abort, done, next batch
     volatile uint32_t *vs_ctl = s_ctl;
     unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_ctl + 8);
-    enum { C_BIN = 0, C_SP, C_CLAIMED, C_ABORT, C_DONE };
+    enum { C_BIN = 0, C_SP, C_CLAIMED, C_ABORT, C_DONE, C_NEXTB };
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t lane_le = lanemask_lt() | (1u << lane);
     const int rs = 64 - 2 * a.k;
+    const uint32_t keys_a = smem_u32(s_keys), cnt_a = smem_u32(s_cnt);       // shared-space addresses of the table
     for (uint32_t i = tid; i < S; i += NT) { s_keys[i] = EMPTY_KEY; s_cnt[i] = 0; }
     for (uint32_t i = tid; i < BC_HIST; i += NT) s_hist[i] = 0;
     const uint32_t bar = smem_u32(&s_bar[warp]);
@@ -133,7 +148,7 @@ bin_count_kernel(const __grid_constant__ BinCountArgs a) {
     uint32_t parity = 0;
     unsigned long long occ_total = 0, recs_total = 0;
 
-    for (;;) {
+    for (uint32_t taken = 0; taken < a.bins_per_cta; taken++) {
         if (tid == 0) s_ctl[C_BIN] = atomicAdd(&a.ctl->next_bin, 1u);
         __syncthreads();
         const uint32_t bin = vs_ctl[C_BIN];
@@ -166,52 +181,60 @@ bin_count_kernel(const __grid_constant__ BinCountArgs a) {
             if (tid == 0) { s_ctl[C_SP] = sp - 1; s_ctl[C_CLAIMED] = 0; s_ctl[C_ABORT] = 0; s_ctl[C_DONE] = 0; }
             __syncthreads();
             const uint32_t p = item & 0xFFFFu, P = item >> 16;
-            uint32_t n_batches_total = 0;
 
-            // ---- count pass: every warp takes batches of 32 records
-            for (uint32_t sj = 0; sj < a.src.n_src; sj++) {
-                const uint32_t s = (sj + a.src.rot) % a.src.n_src;
-                uint32_t n = a.src.cursor[s][a.src.seg0 + bin];
-                if (n > a.src.seg_cap) n = (uint32_t)a.src.seg_cap;
-                const uint4 *__restrict__ recs = a.src.recs[s] + (uint64_t)(a.src.seg0 + bin) * a.src.seg_cap;
-                const uint32_t nb = (n + 31) >> 5;
-                n_batches_total += nb;
-                uint32_t b = warp;
-                bool inflight = false;
-                uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-                if (b < nb) {
-                    if (a.use_tma) {
-                        if (lane == 0) {
-                            const uint32_t bytes = min(32u, n - b * 32) * 16u;
-                            mbar_expect_tx(bar, bytes);
-                            bulk_g2s(ring, recs + (size_t)b * 32, bytes, bar);
-                        }
-                        inflight = true;
-                    } else if (b * 32 + lane < n) nxt = ld_nc_u128(&recs[b * 32 + lane]);
+            // ---- count pass: the warps take batches of 32 records from a shared counter (records hold 1..16 k-mers, so
+            // batches differ in work); the batches of all sources form one index space
+            if (tid == 0) {
+                uint32_t run = 0;
+                for (uint32_t sj = 0; sj < a.src.n_src; sj++) {
+                    const uint32_t sidx = (sj + a.src.rot) % a.src.n_src;
+                    uint32_t n = a.src.cursor[sidx][a.src.seg0 + bin];
+                    if (n > a.src.seg_cap) n = (uint32_t)a.src.seg_cap;
+                    s_srcn[sj] = n; s_srcstart[sj] = run;
+                    run += (n + 31) >> 5;
                 }
-                for (; b < nb; b += NW) {
+                s_srcstart[a.src.n_src] = run;
+                s_ctl[C_NEXTB] = 0;
+            }
+            __syncthreads();
+            const uint32_t n_batches_total = s_srcstart[a.src.n_src];
+            {
+                // batch g -> (source, first record, records in the batch); lane 0 fetches, everybody gets the same answer
+                uint32_t cnt = 0; const uint4 *src_ptr = nullptr;
+                auto fetch = [&]() -> bool {
+                    uint32_t g = 0;
+                    if (lane == 0) g = atomicAdd(&s_ctl[C_NEXTB], 1u);
+                    g = __shfl_sync(FULL, g, 0);
+                    if (g >= n_batches_total) return false;
+                    uint32_t sj = 0;
+                    while (g >= s_srcstart[sj + 1]) sj++;
+                    const uint32_t bb = g - s_srcstart[sj], n = s_srcn[sj];
+                    const uint32_t sidx = (sj + a.src.rot) % a.src.n_src;
+                    src_ptr = a.src.recs[sidx] + (uint64_t)(a.src.seg0 + bin) * a.src.seg_cap + (size_t)bb * 32;
+                    cnt = min(32u, n - bb * 32);
+                    return true;
+                };
+                uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+                auto issue = [&]() {                                 // start moving the fetched batch: TMA bulk copy, or a plain load
+                    if (a.use_tma) {
+                        if (lane == 0) { mbar_expect_tx(bar, cnt * 16u); bulk_g2s(ring, src_ptr, cnt * 16u, bar); }
+                    } else if (lane < cnt) nxt = ld_nc_u128(src_ptr + lane);
+                };
+                bool have = fetch();
+                if (have) issue();
+                while (have) {
                     const uint32_t ab = __shfl_sync(FULL, lane == 0 ? vs_ctl[C_ABORT] : 0u, 0);
                     if (ab) break;
-                    const uint32_t cnt = min(32u, n - b * 32);
+                    const uint32_t cur_cnt = cnt;
                     uint4 r;
-                    const uint32_t b2 = b + NW;
                     if (a.use_tma) {
-                        mbar_wait(bar, parity); parity ^= 1u; inflight = false;
-                        r = lane < cnt ? s_ring[warp * 32 + lane] : make_uint4(0u, 0u, 0u, 0u);
+                        mbar_wait(bar, parity); parity ^= 1u;
+                        r = lane < cur_cnt ? s_ring[warp * 32 + lane] : make_uint4(0u, 0u, 0u, 0u);
                         __syncwarp();
-                        if (b2 < nb) {                               // the ring is free again: next copy flies during the expansion
-                            if (lane == 0) {
-                                const uint32_t bytes = min(32u, n - b2 * 32) * 16u;
-                                mbar_expect_tx(bar, bytes);
-                                bulk_g2s(ring, recs + (size_t)b2 * 32, bytes, bar);
-                            }
-                            inflight = true;
-                        }
-                    } else {
-                        r = nxt;
-                        if (b2 < nb && b2 * 32 + lane < n) nxt = ld_nc_u128(&recs[b2 * 32 + lane]);
-                    }
-                    const uint32_t len = lane < cnt ? (r.z & 15u) + 1u : 0u;
+                    } else r = nxt;
+                    have = fetch();                                  // the ring is free again: the next copy flies during the expansion
+                    if (have) issue();
+                    const uint32_t len = lane < cur_cnt ? (r.z & 15u) + 1u : 0u;
                     uint32_t incl = len;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += v; }
@@ -251,16 +274,17 @@ bin_count_kernel(const __grid_constant__ BinCountArgs a) {
                                 uint32_t slot = h >> (32 - LOG2S);
                                 uint32_t probe = 0;
                                 for (;; probe++) {
-                                    const unsigned long long cur = s_keys[slot];
-                                    if (cur == key) { atomicAdd(&s_cnt[slot], 1u); break; }
+                                    const unsigned long long cur = lds_u64(keys_a + slot * 8u);
+                                    if (cur == key) break;
                                     if (cur == EMPTY_KEY) {
-                                        const unsigned long long prev = atomicCAS(&s_keys[slot], EMPTY_KEY, key);
-                                        if (prev == EMPTY_KEY) { atomicAdd(&s_cnt[slot], 1u); claimed_now = true; break; }
-                                        if (prev == key) { atomicAdd(&s_cnt[slot], 1u); break; }
+                                        const unsigned long long prev = cas_shared_u64(keys_a + slot * 8u, EMPTY_KEY, key);
+                                        if (prev == EMPTY_KEY) { claimed_now = true; break; }
+                                        if (prev == key) break;
                                     }
-                                    if (probe >= BC_MAX_PROBE) { s_ctl[C_ABORT] = 1u; break; }      // pass is void; it will be split
+                                    if (probe >= BC_MAX_PROBE) { s_ctl[C_ABORT] = 1u; slot = S; break; }      // pass is void; it will be split
                                     slot = (slot + 1u) & (S - 1u);
                                 }
+                                if (slot < S) inc_shared_u32(cnt_a + slot * 4u);               // one increment site for every exit of the probe loop
                             }
                         }
                         wclaimed += __popc(__ballot_sync(FULL, claimed_now));
@@ -271,7 +295,7 @@ bin_count_kernel(const __grid_constant__ BinCountArgs a) {
                     }
                     __syncwarp();
                 }
-                if (inflight) { mbar_wait(bar, parity); parity ^= 1u; }       // a copy issued for a batch this warp no longer takes
+                if (have && a.use_tma) { mbar_wait(bar, parity); parity ^= 1u; }      // left on abort: a copy for a batch this warp no longer takes
                 __syncwarp();
             }
             __syncthreads();
@@ -300,20 +324,20 @@ bin_count_kernel(const __grid_constant__ BinCountArgs a) {
                 continue;
             }
 
-            // ---- sweep: histogram of all entries, compaction of count > thr, clear for the next pass
+            // ---- sweep: histogram of all entries, compaction of count > thr, clear for the next pass.  A slot is occupied
+            // iff its count is non-zero (whoever claims a slot increments it), so phase 1 only reads the counts.
             uint32_t good_mask = 0, n_occ = 0, h1 = 0, h2 = 0;
 #pragma unroll
             for (uint32_t u = 0; u < U; u++) {
-                const uint32_t slot = u * NT + tid;
-                const bool occ = s_keys[slot] != EMPTY_KEY;
-                const uint32_t c = s_cnt[slot];
+                const uint32_t c = lds_u32(cnt_a + (u * NT + tid) * 4u);
                 const uint32_t cc = c < MAX_COUNT ? c : MAX_COUNT;
-                n_occ += occ ? 1u : 0u;
-                h1 += __popc(__ballot_sync(FULL, occ && cc == 1u));
-                h2 += __popc(__ballot_sync(FULL, occ && cc == 2u));
-                if (occ && cc > 2u) { if (cc < (uint32_t)BC_HIST) atomicAdd(&s_hist[cc], 1u); else atomicAdd(&a.hist[cc], 1ULL); }
-                if (occ && cc > a.thr) good_mask |= 1u << u;
+                n_occ += c != 0u ? 1u : 0u;
+                h1 += cc == 1u ? 1u : 0u;
+                h2 += cc == 2u ? 1u : 0u;
+                if (cc > 2u) { if (cc < (uint32_t)BC_HIST) atomicAdd(&s_hist[cc], 1u); else atomicAdd(&a.hist[cc], 1ULL); }
+                if (cc > a.thr) good_mask |= 1u << u;
             }
+            h1 = __reduce_add_sync(FULL, h1); h2 = __reduce_add_sync(FULL, h2);
             if (lane == 0) { if (h1) atomicAdd(&s_hist[1], h1); if (h2) atomicAdd(&s_hist[2], h2); }
             occ_total += n_occ;
             const uint32_t mine = __popc(good_mask);
@@ -333,13 +357,13 @@ bin_count_kernel(const __grid_constant__ BinCountArgs a) {
                 const uint32_t slot = u * NT + tid;
                 if ((good_mask >> u) & 1u) {
                     if (at < a.out_cap) {
-                        const uint32_t c = s_cnt[slot];
-                        a.out_keys[at] = s_keys[slot];
+                        const uint32_t c = lds_u32(cnt_a + slot * 4u);
+                        a.out_keys[at] = lds_u64(keys_a + slot * 8u);
                         a.out_counts[at] = (uint16_t)(c < MAX_COUNT ? c : MAX_COUNT);
                     }
                     at++;
                 }
-                s_keys[slot] = EMPTY_KEY; s_cnt[slot] = 0;
+                sts_u64(keys_a + slot * 8u, EMPTY_KEY); sts_u32(cnt_a + slot * 4u, 0u);
             }
             __syncthreads();
         }

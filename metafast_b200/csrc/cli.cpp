@@ -438,24 +438,29 @@ int tool_counter(const Args &a, bool many) {
         for (size_t i = 0; i < samples.size(); i++)
             outs[i] = count_sample_sharded(ctxs, k, b, samples[i].second, samples[i].first, out_dir, st_dir, std::max<uint64_t>(estimate_bases(samples[i].second), 1u << 20));
         for (auto *c : ctxs) mfkc_destroy(c);
-    } else if (g.n_gpus > 1) {
-        // batch mode (BASELINE config 3): the samples are independent, so one worker thread and one context per GPU take
-        // them from a shared counter; no exchange at all.  The reference queues one KmersCounterMain per sample
-        // (src/tools/KmersCounterForManyFilesMain.java:80-108).
-        std::atomic<size_t> next{0};
-        std::vector<std::thread> th;
-        for (int d = 0; d < g.n_gpus; d++)
-            th.emplace_back([&, d] {
-                Gpu gd = g; gd.device = logical ? g.device : g.device + d;
-                mfkc_ctx *ctx = make_ctx(k, gd, biggest, a.has("long-kmers"), min_len);
-                for (size_t i; (i = next++) < samples.size();) outs[i] = count_sample(ctx, k, b, samples[i].second, samples[i].first, out_dir, st_dir);
-                mfkc_destroy(ctx);
-            });
-        for (auto &t : th) t.join();
     } else {
-        mfkc_ctx *ctx = make_ctx(k, g, biggest, a.has("long-kmers"), min_len);
-        for (size_t i = 0; i < samples.size(); i++) outs[i] = count_sample(ctx, k, b, samples[i].second, samples[i].first, out_dir, st_dir);
-        mfkc_destroy(ctx);
+        // batch mode (BASELINE config 3): the samples are independent, so worker threads with one context each take them from
+        // a shared counter; no exchange at all.  Two contexts per GPU: while one sample is counted, sorted and written, the
+        // next one is already being parsed and copied.  The reference queues one KmersCounterMain per sample
+        // (src/tools/KmersCounterForManyFilesMain.java:80-108).
+        const int per_gpu = (samples.size() >= 2 * (size_t)g.n_gpus && !getenv("MFKC_ONE_CONTEXT")) ? 2 : 1;
+        const int workers = g.n_gpus * per_gpu;
+        if (workers == 1) {
+            mfkc_ctx *ctx = make_ctx(k, g, biggest, a.has("long-kmers"), min_len);
+            for (size_t i = 0; i < samples.size(); i++) outs[i] = count_sample(ctx, k, b, samples[i].second, samples[i].first, out_dir, st_dir);
+            mfkc_destroy(ctx);
+        } else {
+            std::atomic<size_t> next{0};
+            std::vector<std::thread> th;
+            for (int wk = 0; wk < workers; wk++)
+                th.emplace_back([&, wk] {
+                    Gpu gd = g; gd.device = logical ? g.device : g.device + wk % g.n_gpus;
+                    mfkc_ctx *ctx = make_ctx(k, gd, biggest, a.has("long-kmers"), min_len);
+                    for (size_t i; (i = next++) < samples.size();) outs[i] = count_sample(ctx, k, b, samples[i].second, samples[i].first, out_dir, st_dir);
+                    mfkc_destroy(ctx);
+                });
+            for (auto &t : th) t.join();
+        }
     }
     for (const auto &o : outs) OUT_VALUE("%s\n", o.c_str());              // "resulting-kmers-files"
     return 0;

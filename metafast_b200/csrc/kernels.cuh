@@ -295,6 +295,15 @@ struct TabSoAOps {
 // ------------------------------------------------------------------------------------------
 constexpr int MINI_M = 12;
 __host__ __device__ __forceinline__ int minimizer_len(int k) { return k < MINI_M ? k : MINI_M; }
+// Minimizer length of the bin-local count (bincount.cuh), 12..16: the k-mer instances concentrate on the ~2/(k-m+2) of
+// the m-mers with the smallest hashes, so a bin is the sum of (4^m / 2) * 0.1 / bins "effective" minimizers; with fewer
+// than a few dozen of them per bin the bins' sizes scatter too much (measured: 12-mers, 447 k bins -> 5 % of the bins
+// overflow a 2.6x segment).  4^m >= 640 * bins keeps >= 32 per bin.  (The table placement keeps m = 12.)
+__host__ __device__ __forceinline__ int bin_minimizer_len(int k, uint64_t bins_total) {
+    int m = MINI_M;
+    while (m < 16 && (1ull << (2 * m)) < 640ull * bins_total) m++;
+    return k < m ? k : m;
+}
 __host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {       // MurmurHash3 fmix32
     x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
     return x;
@@ -832,6 +841,7 @@ struct SkmStage {
     uint32_t win;                 // primary window of the windowed placement (0 = plain linear probing), see placed_upsert_at
     // MODE 3 (bin-local counting): records that find their bin's segment full go to this list instead
     uint4 *ovf; unsigned int *ovf_cursor; uint32_t ovf_cap;
+    int mlen;                     // MODE 3 / 4: minimizer length (bin_minimizer_len); other modes use minimizer_len(k)
 };
 
 __device__ __forceinline__ uint32_t kmers_of_word(uint32_t w0, uint32_t w1, uint32_t w2, uint64_t flag_bits,
@@ -879,8 +889,7 @@ __device__ __forceinline__ void window_mins_static(const uint32_t (&h)[36], uint
     }
 }
 
-__device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32_t w2, int k, uint32_t (&mh)[16]) {
-    const int m = minimizer_len(k);
+__device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32_t w2, int k, int m, uint32_t (&mh)[16]) {
     const int w = k - m + 1;                              // m-mers per k-mer, <= 20
     const int rs = 32 - 2 * m;
     const int top = 2 * m - 2;
@@ -934,8 +943,9 @@ __device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32
 __host__ __device__ __forceinline__ uint32_t coarse_of_minhash(uint32_t mh, int log2_buckets) {
     return log2_buckets ? region_hash(mh) >> (32 - log2_buckets) : 0u;              // monotone in the region index
 }
+// modes 3 / 4 (no table fallback inside the kernel) fit 80 registers: 3 CTAs per SM instead of 2 hide the cursor atomics
 template <int MODE, class Tab>
-__global__ void __launch_bounds__(EX_THREADS)
+__global__ void __launch_bounds__(EX_THREADS, (MODE >= 3 ? 3 : 2))
 extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
                    int k, SkmStage st, Tab tb, Counters *__restrict__ ctr,
                    unsigned long long *__restrict__ kmer_count) {
@@ -965,7 +975,7 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
             }
             if (valid) {
                 uint32_t mh[16];
-                minhash_of_word(w0, w1, w2, k, mh);
+                minhash_of_word(w0, w1, w2, k, (MODE == 3 || MODE == 4) ? st.mlen : minimizer_len(k), mh);
                 // Cut into runs of consecutive valid k-mers (fully unrolled: every register array keeps
                 // compile-time indices).  Local staging: a run = same table REGION.  Send buffer
                 // (BY_OWNER): a run = same MINIMIZER HASH, because the receiver derives the region of
@@ -1097,7 +1107,7 @@ extract_skm_owner8_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, c
 #pragma unroll
             for (int j = 0; j < 16; j++) valid |= ((((t.fbits >> j) & span) == 0 && (long long)j <= t.limit) ? 1u : 0u) << j;
         }
-        if (valid) minhash_of_word(w0, w1, w2, k, mh);
+        if (valid) minhash_of_word(w0, w1, w2, k, minimizer_len(k), mh);
         // runs of consecutive valid k-mers with the same minimizer hash; f(j0, len, minhash)
         auto for_each_run = [&](auto f) {
             uint32_t run_start = 0, run_mh = 0;

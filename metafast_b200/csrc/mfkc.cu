@@ -37,7 +37,7 @@ static const char *kProfNames[P_NSLOTS] = {
 
 struct PendingTiming { int slot; cudaEvent_t a, b; };
 
-static constexpr int N_STAGE = 4;
+static constexpr int N_STAGE = 8;
 
 struct Staging {
     uint8_t *d_bases = nullptr; size_t cap_bases = 0;
@@ -58,6 +58,10 @@ struct mfkc_ctx {
                                        // of the kernels (a drain on the compute stream must not stall the copy engine)
     cudaStream_t compute = nullptr;    // every kernel runs here, in submission order ...
     cudaStream_t aux = nullptr;        // ... except the receive side of the shard exchange, which overlaps the next extraction
+    cudaStream_t emit = nullptr;       // ... and the count + sort + records kernels of the bin-local mode: LOWEST priority, so that
+                                       // the extraction kernels of another context on the same GPU (next sample arriving over
+                                       // PCIe) are scheduled first whenever a CTA slot frees up
+    cudaEvent_t ev_order = nullptr;
     cudaEvent_t ev_aux = nullptr; bool aux_pending = false;
     int next_buf = 0;
 
@@ -108,6 +112,7 @@ struct mfkc_ctx {
     // peer-memory shard exchange
     uint4 *p2p_recs = nullptr; unsigned int *p2p_cursor = nullptr; unsigned long long *p2p_kc = nullptr;
     uint64_t p2p_seg_cap = 0; int p2p_log2 = 0;
+    int os_mlen = 12;                  // minimizer length the bins of the current sample derive from
     bool p2p_bins = false;             // staging laid out for the bin-local count: (owner, bin) segments + overflow list
     uint32_t p2p_B = 0; uint64_t p2p_ovf_cap = 0, p2p_kmers_in = 0, p2p_n_cursor = 0;
     const uint4 *p2p_peer_recs[P2P_MAX_PEERS] = {nullptr}; const unsigned int *p2p_peer_cursor[P2P_MAX_PEERS] = {nullptr};
@@ -190,6 +195,15 @@ static void drain_timings(mfkc_ctx *ctx) {
     ctx->pending.clear();
 }
 
+// work queued on `later` from here on runs after everything queued on `earlier` so far (temporaries are allocated on the
+// compute stream; the low-priority emit stream uses them)
+static int stream_after(mfkc_ctx *ctx, cudaStream_t later, cudaStream_t earlier) {
+    if (later == earlier) return MFKC_OK;
+    CU_TRY(cudaEventRecord(ctx->ev_order, earlier));
+    CU_TRY(cudaStreamWaitEvent(later, ctx->ev_order, 0));
+    return MFKC_OK;
+}
+
 static int grid_for(const mfkc_ctx *ctx, uint64_t work_items, int threads, int blocks_per_sm = 8) {
     uint64_t blocks = (work_items + threads - 1) / threads;
     const uint64_t cap = (uint64_t)ctx->sm_count * blocks_per_sm;
@@ -201,6 +215,7 @@ static int grid_for(const mfkc_ctx *ctx, uint64_t work_items, int threads, int b
 static int sync_all(mfkc_ctx *ctx) {
     for (int i = 0; i < N_STAGE; i++) CU_TRY(cudaStreamSynchronize(ctx->st[i].stream));
     CU_TRY(cudaStreamSynchronize(ctx->aux));
+    CU_TRY(cudaStreamSynchronize(ctx->emit));
     CU_TRY(cudaStreamSynchronize(ctx->compute));
     for (int i = 0; i < N_STAGE; i++) ctx->st[i].pending = false;
     ctx->drain_pending = false; ctx->aux_pending = false;
@@ -328,7 +343,13 @@ extern "C" int mfkc_create(const mfkc_cfg *cfg, mfkc_ctx **out) {
         CR_TRY(cudaEventCreateWithFlags(&ctx->st[i].ev_done, cudaEventDisableTiming));
         CR_TRY(cudaMallocHost(&ctx->st[i].h_snap, sizeof(unsigned long long)));
     }
-    CR_TRY(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    {
+        int prio_low = 0, prio_high = 0;
+        CR_TRY(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+        CR_TRY(cudaStreamCreateWithPriority(&ctx->compute, cudaStreamNonBlocking, prio_high));
+        CR_TRY(cudaStreamCreateWithPriority(&ctx->emit, cudaStreamNonBlocking, prio_low));
+        CR_TRY(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
+    }
     CR_TRY(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
     CR_TRY(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
     CR_TRY(cudaEventCreateWithFlags(&ctx->ev_drain, cudaEventDisableTiming));
@@ -447,6 +468,8 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     free_emit(ctx);
     if (ctx->compute) { cudaStreamSynchronize(ctx->compute); cudaStreamDestroy(ctx->compute); ctx->compute = nullptr; }
     if (ctx->aux) { cudaStreamSynchronize(ctx->aux); cudaStreamDestroy(ctx->aux); ctx->aux = nullptr; }
+    if (ctx->emit) { cudaStreamSynchronize(ctx->emit); cudaStreamDestroy(ctx->emit); ctx->emit = nullptr; }
+    if (ctx->ev_order) cudaEventDestroy(ctx->ev_order);
     if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
     cudaFree(ctx->rb_keys); cudaFree(ctx->rb_cursor);
     cudaFree(ctx->sp_ent); cudaFree(ctx->sp_cursor); cudaFree(ctx->sp_failed);
@@ -859,11 +882,13 @@ static SkmStage bin_stage(const mfkc_ctx *ctx) {
         st.recs = ctx->p2p_recs; st.cursor = ctx->p2p_cursor; st.seg_cap = ctx->p2p_seg_cap;
         st.n_regions = (uint32_t)G; st.region_shift = 0; st.win = ctx->p2p_B;
         st.ovf = st.recs + G * ctx->p2p_B * ctx->p2p_seg_cap; st.ovf_cursor = ctx->p2p_cursor + G * ctx->p2p_B; st.ovf_cap = (uint32_t)ctx->p2p_ovf_cap;
+        st.mlen = ctx->os_mlen;
         return st;
     }
     st.recs = reinterpret_cast<uint4 *>(ctx->rb_keys); st.cursor = ctx->rb_cursor;
     st.seg_cap = ctx->os_seg_cap; st.n_regions = ctx->os_n_bins; st.region_shift = 0; st.win = 0;
     st.ovf = st.recs + (uint64_t)ctx->os_n_bins * ctx->os_seg_cap; st.ovf_cursor = &ctx->d_binctl->ovf_cursor; st.ovf_cap = (uint32_t)ctx->os_ovf_cap;
+    st.mlen = ctx->os_mlen;
     return st;
 }
 static BinSrc bin_src(const mfkc_ctx *ctx) {
@@ -894,8 +919,6 @@ static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
     const double kmers = (double)expect * 1.03 + 4096.0;
     double R = ctx->os_R > 0 ? ctx->os_R : (ctx->cfg.expected_distinct ? kmers / (double)ctx->cfg.expected_distinct : 3.0);
     R = std::min(64.0, std::max(1.0, R));
-    const int w = k - minimizer_len(k) + 1;
-    double rpk = ctx->os_rpk > 0 ? ctx->os_rpk * 1.05 : std::min(1.0, (1.0 / 16 + 2.0 / (w + 1)) * 1.2);
     // tuning / test knobs (read per sample): slack of the staging segments, planned load of the shared-memory table,
     // a fixed number of bins, a fixed overflow-list capacity
     const double env_slack = getenv("MFKC_BIN_SLACK") ? atof(getenv("MFKC_BIN_SLACK")) : 0.0;
@@ -908,6 +931,9 @@ static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
     uint64_t n_bins = (uint64_t)(kmers / R / (load * S)) + 1;
     n_bins = std::min<uint64_t>(std::max<uint64_t>(n_bins, 16), (uint64_t)MAX_REGIONS_SKM);
     if (env_nbins > 0) n_bins = std::min<uint64_t>((uint64_t)env_nbins, (uint64_t)MAX_REGIONS_SKM);
+    const int mlen = getenv("MFKC_BIN_M") ? std::min(k, std::max(4, atoi(getenv("MFKC_BIN_M")))) : bin_minimizer_len(k, n_bins);
+    const int w = k - mlen + 1;
+    const double rpk = (ctx->os_rpk > 0 && mlen == ctx->os_mlen) ? ctx->os_rpk * 1.05 : std::min(1.0, (1.0 / 16 + 2.0 / (w + 1)) * 1.2);
     const double recs = kmers * rpk;
     uint64_t seg_cap = (uint64_t)(recs / (double)n_bins * slack) + 64;
     if (seg_cap > 0x7fffffffull) return MFKC_OK;
@@ -931,7 +957,7 @@ static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
         ctx->heavy_cap = (uint32_t)std::min<uint64_t>(n_bins + n_bins / 4 + 4096, 0xffffffffull);
         CU_TRY(cudaMalloc(&ctx->d_heavy, (size_t)ctx->heavy_cap * sizeof(HeavyEnt)));
     }
-    ctx->os_n_bins = (uint32_t)n_bins; ctx->os_seg_cap = seg_cap; ctx->os_ovf_cap = ovf_cap;
+    ctx->os_n_bins = (uint32_t)n_bins; ctx->os_seg_cap = seg_cap; ctx->os_ovf_cap = ovf_cap; ctx->os_mlen = mlen;
     ctx->os_kmers_budget = (uint64_t)(kmers * 1.2);
     ctx->os_kmers_staged = 0;
     ctx->mode = 1;
@@ -1083,7 +1109,8 @@ static constexpr uint32_t kNoOutput = 0xFFFFFFFFu;
 static int bins_count(mfkc_ctx *ctx, uint32_t thr) {
     const bool want_out = thr != kNoOutput;
     if (ctx->os_counted && (!want_out || (ctx->os_thr == thr && (ctx->os_keys || ctx->os_n_good == 0)))) return MFKC_OK;
-    cudaStream_t st = ctx->compute;
+    static const bool low = getenv("MFKC_EMIT_PRIORITY") == nullptr || atoi(getenv("MFKC_EMIT_PRIORITY")) != 0;
+    cudaStream_t st = low ? ctx->emit : ctx->compute;
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
     free_bin_outputs(ctx);
@@ -1099,6 +1126,7 @@ static int bins_count(mfkc_ctx *ctx, uint32_t thr) {
     for (int attempt = 0; attempt < 2; attempt++) {
         unsigned long long *ok = nullptr; uint16_t *oc = nullptr;
         if (out_cap) { TMP_ALLOC(ok, out_cap * 8); TMP_ALLOC(oc, out_cap * 2); }
+        TRY(stream_after(ctx, st, ctx->compute));
         CU_TRY(cudaMemsetAsync(ctx->d_hist, 0, MFKC_HIST_BINS * sizeof(unsigned long long), st));
         CU_TRY(cudaMemsetAsync(&ctx->d_ctr->n_good, 0, 2 * sizeof(unsigned long long), st));            // n_good, bc_distinct
         CU_TRY(cudaMemsetAsync(&ctx->d_ctr->distinct, 0, sizeof(unsigned long long), st));
@@ -1106,11 +1134,15 @@ static int bins_count(mfkc_ctx *ctx, uint32_t thr) {
         BinCountArgs a{};
         a.src = bin_src(ctx); a.n_bins = ctx->os_n_bins; a.k = ctx->cfg.k; a.thr = want_out ? thr : 0x7FFFFFFFu;
         a.limit = (uint32_t)(0.8 * (double)(1u << BC_LOG2S)); a.max_recs = 0xFFFFFFFFu; a.use_tma = env_tma;
+        // CTAs retire after a few dozen bins (~1 ms): a second context's extraction kernels (next sample arriving over PCIe
+        // while this one is counted) get SMs at every turnover instead of waiting for the whole count
+        static const int env_bpc = getenv("MFKC_BIN_PER_CTA") ? atoi(getenv("MFKC_BIN_PER_CTA")) : 0;
+        a.bins_per_cta = env_bpc > 0 ? (uint32_t)env_bpc : 32u;
         a.out_keys = ok; a.out_counts = oc; a.out_cap = out_cap; a.hist = ctx->d_hist; a.ctr = ctx->d_ctr; a.ctl = ctx->d_binctl;
         a.heavy = ctx->d_heavy; a.heavy_cap = ctx->heavy_cap;
         if (kmers) {
             ProfScope ps(ctx, P_BIN_COUNT, st);
-            const int grid = (int)std::min<uint64_t>(ctx->os_n_bins, (uint64_t)ctx->sm_count * 2);
+            const int grid = (int)((ctx->os_n_bins + a.bins_per_cta - 1) / a.bins_per_cta);
             bin_count_kernel<BC_LOG2S, BC_THREADS><<<grid, BC_THREADS, bin_count_smem_bytes<BC_LOG2S, BC_THREADS>(), st>>>(a);
         }
         CU_TRY(cudaGetLastError());
@@ -1129,7 +1161,8 @@ static int bins_count(mfkc_ctx *ctx, uint32_t thr) {
             const int r = resid_table_prepare(ctx, 16 * (c.heavy_recs + n_ovf));
             if (r != MFKC_OK) { TMP_FREE(ok); TMP_FREE(oc); ctx->err.clear(); TRY(bins_to_table(ctx)); return 1; }
             TableGeom g = table_geom(ctx); g.minimizer = 0; g.win = 0;
-            TRY(launch_heavy(ctx, 0, c.n_heavy, n_ovf != 0, g));
+            TRY(launch_heavy(ctx, 0, c.n_heavy, n_ovf != 0, g));          // (on the compute stream, like the table clear before)
+            TRY(stream_after(ctx, st, ctx->compute));
             {
                 ProfScope ps(ctx, P_COMPACT, st);
                 table_scan_kernel<false><<<grid_for(ctx, (ctx->cap + 7) / 8, 256, 8), 256, 0, st>>>(
@@ -1332,6 +1365,7 @@ static int radix_sort(mfkc_ctx *ctx, cudaStream_t st, unsigned long long *&a, un
     TMP_ALLOC(offs, plan.offs_bytes);
     TMP_ALLOC(chunk, plan.chunk_bytes);
     TMP_ALLOC(d_triv, sizeof(uint32_t));
+    TRY(stream_after(ctx, st, ctx->compute));
     const size_t smem = rs_scatter_smem_bytes<V, HAS_V>();
     CU_TRY(cudaFuncSetAttribute(rs_scatter_kernel<V, HAS_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::min<uint64_t>(plan.n_parts, (uint64_t)ctx->sm_count * 8);
@@ -1633,6 +1667,8 @@ extern "C" int mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_goo
             if (r < 0) return r;
             if (r == 0) {
                 counted = true;
+                static const bool low = getenv("MFKC_EMIT_PRIORITY") == nullptr || atoi(getenv("MFKC_EMIT_PRIORITY")) != 0;
+                if (low) st = ctx->emit;
                 good = ctx->os_n_good;
                 k1 = ctx->os_keys; c1 = ctx->os_counts; ctx->os_keys = nullptr; ctx->os_counts = nullptr;
                 if (!good) { TMP_FREE(k1); TMP_FREE(c1); k1 = nullptr; c1 = nullptr; }
@@ -1702,6 +1738,7 @@ extern "C" int mfkc_emit_begin(mfkc_ctx *ctx, int32_t threshold, uint64_t *n_goo
     ctx->em_n = good;
     if (good) {
         TMP_ALLOC(ctx->em_records, (size_t)good * 10);
+        TRY(stream_after(ctx, st, ctx->compute));
         {
             ProfScope ps(ctx, P_RECORDS, st);
             records_kernel<<<grid_for(ctx, good, 256, 8), 256, 0, st>>>(ctx->em_keys, ctx->em_counts, good,
@@ -1723,7 +1760,11 @@ extern "C" int mfkc_emit_next(mfkc_ctx *ctx, uint8_t *out, size_t cap, size_t *w
     const size_t rs = ctx->k128 ? 18 : 10;
     uint64_t take = std::min<uint64_t>(left, cap / rs);
     if (take && !out) return MFKC_E_BADARG;
-    if (take) CU_TRY(cudaMemcpy(out, ctx->em_records + ctx->em_cursor * rs, (size_t)take * rs, cudaMemcpyDeviceToHost));
+    if (take) {
+        // on a stream of its own (not the legacy default stream): the copy back overlaps another context's host-to-device copies
+        CU_TRY(cudaMemcpyAsync(out, ctx->em_records + ctx->em_cursor * rs, (size_t)take * rs, cudaMemcpyDeviceToHost, ctx->emit));
+        CU_TRY(cudaStreamSynchronize(ctx->emit));
+    }
     ctx->em_cursor += take;
     *written = (size_t)take * rs;
     return MFKC_OK;
@@ -1955,11 +1996,11 @@ extern "C" int mfkc_p2p_bin_geometry(uint64_t kmers_per_rank, uint32_t n_shards,
     if (!bins_per_shard || !seg_cap || !ovf_cap || n_shards < 1 || k < 1) return MFKC_E_BADARG;
     const double R = instances_per_distinct >= 1.0 ? instances_per_distinct : 3.0;
     const double sl = slack > 0 ? slack : 2.0;
-    const int w = k - minimizer_len(k) + 1;
-    const double rpk = std::min(1.0, (1.0 / 16 + 2.0 / (w + 1)) * 1.2);
     const double kmers = (double)kmers_per_rank * 1.03 + 4096.0;
     uint64_t bins = (uint64_t)(kmers / R / (0.45 * (double)(1u << BC_LOG2S))) + 1;
     bins = std::min<uint64_t>(std::max<uint64_t>(bins, 16), 1ull << 24);
+    const int w = k - bin_minimizer_len(k, bins * n_shards) + 1;
+    const double rpk = std::min(1.0, (1.0 / 16 + 2.0 / (w + 1)) * 1.2);
     const double recs = kmers * rpk;
     *bins_per_shard = (uint32_t)bins;
     *seg_cap = (uint64_t)(recs / ((double)n_shards * (double)bins) * sl) + 64;
@@ -1985,6 +2026,7 @@ extern "C" int mfkc_p2p_stage_create_bins(mfkc_ctx *ctx, uint32_t bins_per_shard
     CU_TRY(cudaMemset(ctx->p2p_cursor, 0, (n_seg + 1) * sizeof(unsigned int)));
     CU_TRY(cudaMemset(ctx->p2p_kc, 0, P2P_MAX_PEERS * sizeof(unsigned long long)));
     ctx->p2p_seg_cap = seg_cap; ctx->p2p_log2 = 0; ctx->p2p_bins = true; ctx->p2p_B = bins_per_shard; ctx->p2p_ovf_cap = ovf_cap;
+    ctx->os_mlen = bin_minimizer_len(ctx->cfg.k, n_seg);         // the same on every rank: a function of the geometry
     ctx->p2p_n_cursor = n_seg + 1;
     ctx->os_n_bins = bins_per_shard; ctx->os_seg_cap = seg_cap; ctx->os_ovf_cap = ovf_cap;
     if (ctx->heavy_cap < (uint64_t)bins_per_shard + 4096) {
