@@ -338,6 +338,227 @@ def verify_at_size(m, kc, step_device, env):
     return out
 
 
+# ------------------------------------------------------------------ the other BASELINE configs (not the driver's line)
+def _dist_setup():
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return rank, world, local_rank, dist
+
+
+def _max_over_ranks(dist, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(dist, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t)
+    return float(t.item())
+
+
+def _barrier(dist, kc):
+    kc.sync()
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def run_config3(args):
+    """BASELINE configs[2]: kmer-counter-many batch mode, S samples x R reads (100 x 5 M), k = 31, default -b 1, then
+    features-calculator of every sample's records against fixed components (10 000 x 2 000 k-mers).  The samples are
+    independent: rank r takes samples r, r + N, ... (no exchange).  value: reads of the rank's samples resident in HBM, the
+    records go from the counter to the features tables on the device; e2e: the same through host buffers (reads H2D,
+    records D2H, records H2D again as features-calculator's -ka input, vectors D2H), one sample after the other."""
+    import numpy as np
+    import metafast_b200 as m
+    rank, world, local_rank, dist = _dist_setup()
+    S = int(os.environ.get("MFKC_BENCH_SAMPLES", 100)); R = int(os.environ.get("MFKC_BENCH_SAMPLE_READS", 5_000_000))
+    n_comp, comp_size, b = 10_000, 2_000, 1
+    mine = list(range(rank, S, world))
+    kc = m.KmerCounter(K, device=local_rank, expected_kmers=R * (READ_LEN - K + 1))
+    fc = m.FeaturesCalculator(K, device=local_rank)
+    bufs = []
+    for sidx in mine:                                               # every sample: its own abundance vector of the community
+        d_b = kc.device_alloc(R * READ_LEN); d_o = kc.device_alloc((R + 1) * 8)
+        kept = C.c_uint64(); cfg = m.synth_cfg(sample=sidx)
+        kc._ck(kc.lib.mfkc_synth_reads_device(kc.h, C.byref(cfg), 0, R, C.c_void_p(d_b), C.c_void_p(d_o), C.byref(kept)))
+        bufs.append((d_b, d_o, kept.value))
+
+    def count(d_b, d_o, n):
+        kc.reset()
+        for s0 in range(0, n, BATCH_READS):
+            e = min(n, s0 + BATCH_READS)
+            kc.submit_device(d_b + s0 * READ_LEN, d_o + s0 * 8, e - s0, (e - s0) * READ_LEN)
+        kc.flush()
+        return kc.emit_begin(b)
+
+    # fixed components: consecutive runs of sample 0's records (the same on every rank)
+    kc0 = kc
+    d_b0 = kc0.device_alloc(R * READ_LEN); d_o0 = kc0.device_alloc((R + 1) * 8)
+    kept = C.c_uint64(); cfg0 = m.synth_cfg(sample=0)
+    kc0._ck(kc0.lib.mfkc_synth_reads_device(kc0.h, C.byref(cfg0), 0, R, C.c_void_p(d_b0), C.c_void_p(d_o0), C.byref(kept)))
+    count(d_b0, d_o0, kept.value)
+    rec0 = np.frombuffer(kc.emit(b), dtype=np.uint8).reshape(-1, 10)
+    kc0.device_free(d_b0); kc0.device_free(d_o0)
+    n_keys = min(len(rec0), n_comp * comp_size)
+    comp_size = max(1, n_keys // n_comp)
+    keys = np.ascontiguousarray(rec0[: n_comp * comp_size, :8]).view(">u8").astype(np.uint64).reshape(-1)
+    off = (np.arange(n_comp + 1, dtype=np.uint64) * np.uint64(comp_size))
+    fc._ck(fc.lib.mfkc_fc_load_components(fc.h, keys.view(np.int64).ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), n_comp))
+    fc.n_comp = n_comp
+    del rec0
+
+    kmers_mine = sum(n * (READ_LEN - K + 1) for _, _, n in bufs)
+    recs_mine = [0]
+
+    def step():
+        recs_mine[0] = 0
+        for d_b, d_o, n in bufs:
+            recs_mine[0] += count(d_b, d_o, n)
+            fc.reset_values()
+            fc.add_emitted(kc)
+            vec, found, cnt = fc.features(0)
+        return vec
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    _barrier(dist, kc)
+    kc.profile(enable=True, reset=True); fc.profile(enable=True, reset=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vec = step()
+    _barrier(dist, kc)
+    dt = _max_over_ranks(dist, time.perf_counter() - t0)
+    prof = kc.profile(enable=False); fprof = fc.profile(enable=False)
+    kmers_all = _sum_over_ranks(dist, kmers_mine)
+    # e2e through host buffers, the rank's first two samples in turn
+    import numpy as _np
+    host = []
+    for d_b, d_o, n in bufs[:2]:
+        hb = kc.pinned(n * READ_LEN); ho = kc.pinned((n + 1) * 8, _np.uint64)
+        kc.d2h(hb, d_b); kc.d2h(ho, d_o); host.append((hb, ho, n))
+    h_out = kc.pinned(max(int(recs_mine[0] / max(1, len(bufs)) * 1.3) + 4096, 4096) * 10)
+
+    def e2e_sample(hb, ho, n):
+        kc.reset()
+        for s0 in range(0, n, BATCH_READS):
+            kc.submit(hb, ho[s0:min(n, s0 + BATCH_READS) + 1])
+        kc.flush()
+        nbytes = kc.emit_into(b, h_out)
+        kc.histogram()
+        fc.reset_values()
+        fc._ck(fc.lib.mfkc_fc_add_records(fc.h, h_out.ctypes.data_as(C.c_void_p), nbytes // 10))
+        fc.features(0)
+        return nbytes
+    for hb, ho, n in host:
+        e2e_sample(hb, ho, n)
+    _barrier(dist, kc)
+    t0 = time.perf_counter()
+    reps = max(1, len(bufs))
+    for i in range(reps):
+        out_bytes = e2e_sample(*host[i % len(host)])
+    _barrier(dist, kc)
+    e2e_dt = _max_over_ranks(dist, time.perf_counter() - t0)
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        fc_ms = fprof.get("fc_records", (0, 0))[0] / args.steps
+        hits = float(n_comp * comp_size)                          # upper bound: every component k-mer met once per sample
+        recs = recs_mine[0]
+        fc_bytes = 10.0 * recs + 64.0 * hits * len(bufs)
+        line = {"metric": "canonical 31-mers counted/s", "value": kmers_all * args.steps / dt, "unit": "kmers/s", "n_gpus": world, "steps": args.steps,
+                "warmup": 1, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "int64", "data": "synthetic",
+                "config": {"workload": "configs[2]: %d synthetic samples x %d reads, k=31, -b 1, then features-calculator on %d components x %d k-mers"
+                                       % (S, R, n_comp, comp_size), "parallelism": "samples round robin over %d GPU(s), no exchange" % world},
+                "samples_per_s": S * args.steps / dt, "ms_per_sample": 1e3 * dt / args.steps / max(1, len(mine)),
+                "e2e": {"value": kmers_mine / max(1, len(bufs)) * reps * world / e2e_dt, "unit": "kmers/s", "ms_per_sample": 1e3 * e2e_dt / reps,
+                        "h2d_bytes_per_step": int(host[0][2] * READ_LEN + out_bytes), "d2h_bytes_per_step": int(out_bytes + 32768 * 8 + 3 * 8 * n_comp),
+                        "mode": "one sample after the other per GPU"},
+                "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in list(prof.items()) + list(fprof.items()) if v[1] and v[0]},
+                "features_roofline": {"bound": "hbm", "kernel": "fc_pairs", "achieved": fc_bytes / (fc_ms / 1e3) / 1e9 if fc_ms else None, "peak": peak, "unit": "GB/s",
+                                      "frac": (fc_bytes / (fc_ms / 1e3) / 1e9 / peak) if fc_ms else None,
+                                      "note": "10 B per record streamed + 64 B per hit (SURVEY 8d); records %d per rank and step" % recs},
+                "gpu_launches": int(sum(v[1] for v in prof.values()) + sum(v[1] for v in fprof.values()))}
+        print(json.dumps(line))
+    kc.close(); fc.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_config_sharded(args, k, config_name, total_reads, paired=False):
+    """BASELINE configs[3] (k = 31, one metagenome hash-range sharded over the GPUs) and configs[4] (k = 55, 128-bit keys,
+    paired-end files): ONE sample of `total_reads` reads, split between the ranks (strong scaling); every rank extracts its
+    slice, every owner counts its hash range out of the peers' staging buffers, filter + histogram per shard."""
+    import numpy as np
+    import metafast_b200 as m
+    rank, world, local_rank, dist = _dist_setup()
+    per_rank = total_reads // world
+    kmers_ub = per_rank * (READ_LEN - k + 1)
+    kc = m.KmerCounter(k, device=local_rank, expected_kmers=kmers_ub, n_shards=world if world > 1 else 0, shard_id=rank if world > 1 else 0)
+    cfg = m.synth_cfg(sample=0)
+    d_b = kc.device_alloc(per_rank * READ_LEN); d_o = kc.device_alloc((per_rank + 1) * 8)
+    kept = C.c_uint64()
+    # paired-end: mates are consecutive reads of the generator (R1 = even, R2 = odd); a rank takes whole pairs
+    kc._ck(kc.lib.mfkc_synth_reads_device(kc.h, C.byref(cfg), rank * per_rank, per_rank, C.c_void_p(d_b), C.c_void_p(d_o), C.byref(kept)))
+    n = kept.value
+    sharded = None
+    if world > 1:
+        from metafast_b200.sharded import P2PShardedStep
+        sharded = P2PShardedStep(kc, dist, world, rank, BATCH_READS, READ_LEN, k, per_rank)
+
+    def step():
+        kc.reset()
+        if sharded:
+            sharded.begin()
+            sharded.run_device(d_b, d_o, n)
+        else:
+            for s0 in range(0, n, BATCH_READS):
+                e = min(n, s0 + BATCH_READS)
+                kc.submit_device(d_b + s0 * READ_LEN, d_o + s0 * 8, e - s0, (e - s0) * READ_LEN)
+        kc.flush()
+        return kc.emit_begin(B_THRESHOLD)
+
+    for _ in range(args.warmup):
+        good = step()
+    _barrier(dist, kc)
+    kc.profile(enable=True, reset=True)
+    kc.timer_start()
+    for _ in range(args.steps):
+        good = step()
+    ms = _max_over_ranks(dist, kc.timer_stop_ms())
+    _barrier(dist, kc)
+    prof = kc.profile(enable=False)
+    st = kc.stats()
+    kmers_all = _sum_over_ranks(dist, n * (READ_LEN - k + 1))
+    distinct_all = _sum_over_ranks(dist, st["distinct"]); good_all = _sum_over_ranks(dist, good)
+    if rank == 0:
+        line = {"metric": "canonical %d-mers counted/s" % k, "value": kmers_all * args.steps / (ms / 1e3), "unit": "kmers/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "int64" if k <= 31 else "int128", "data": "synthetic",
+                "config": {"workload": "%s: ONE sample of %d synthetic 150-bp reads%s, k=%d, -b %d" % (config_name, total_reads, " (paired-end, _R1/_R2)" if paired else "", k, B_THRESHOLD),
+                           "reads_per_gpu": per_rank, "parallelism": "hash-range sharded over %d GPU(s); %s" % (world, "bin-local count out of peer memory" if k <= 31 else "region-blocked 128-bit table drained from peer memory")},
+                "kernel_ms_per_step": {k_: v[0] / args.steps for k_, v in prof.items() if v[1] and v[0]},
+                "gpu_launches": int(sum(v[1] for v in prof.values())),
+                "result": {"kmers": kmers_all, "distinct": distinct_all, "records_gt_b": good_all, "bins": kc.bin_stats()}}
+        print(json.dumps(line))
+    kc.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------ this repository's arm
 def main():
     ap = argparse.ArgumentParser()
@@ -345,10 +566,20 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mfkc", choices=["mfkc", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configs index + 1: 2 = the metric's configuration (default, the driver's line); 3 = batch of "
+                         "samples + features; 4 = one metagenome sharded over the GPUs (strong scaling); 5 = k = 55 paired-end")
+    ap.add_argument("--reads", type=int, default=0, help="configs 4 / 5: total reads of the one sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.config == 3:
+        return run_config3(args)
+    if args.config == 4:      # 2 G reads in BASELINE; default here = 10x scaled down (what fits device-resident at N >= 2)
+        return run_config_sharded(args, 31, "configs[3]", args.reads or 200_000_000)
+    if args.config == 5:      # 500 M reads in BASELINE; default here = 10x scaled down
+        return run_config_sharded(args, 55, "configs[4]", args.reads or 50_000_000, paired=True)
 
     import numpy as np
     import metafast_b200 as m
@@ -518,6 +749,13 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = kmers_per_step * world * args.steps / e2e_s
 
+    # what the host can feed: every rank copies its reads host -> device at the same time, nothing else running
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        kc.h2d(d_bases, h_bases)
+    barrier()
+    link_gbs = 3 * n_bases * world / max_over_ranks(time.perf_counter() - t0) / 1e9
     if rank != 0:
         kc.close()
         if dist is not None:
@@ -573,6 +811,7 @@ def main():
         "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": "kmers/s", "h2d_bytes_per_step": int(n_bases + (n_reads + 1) * 8),
                 "d2h_bytes_per_step": int(out_bytes + 32768 * 8), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "host_to_device_gbs_all_gpus": link_gbs, "h2d_floor_ms_per_step": 1e3 * n_bases * world / (link_gbs * 1e9),
                 "mode": "%d contexts take the samples in turn (H2D of sample i+1 overlaps count + emit + D2H of sample i)" % n_lanes if pipelined
                         else "one sample after the other"},
         "gpu_launches": int(launches),

@@ -218,6 +218,9 @@ int  mfkc_fc_set_selected(mfkc_ctx *ctx, const uint8_t *be_records, uint64_t n_r
 int  mfkc_fc_reset_values(mfkc_ctx *ctx);          /* hm.resetValues(), FeaturesCalculatorMain.java:122,151 */
 /* 10-byte BE records in any chunking (the reference reads 16 777 200-byte chunks, IOUtils.java:30). */
 int  mfkc_fc_add_records(mfkc_ctx *ctx, const uint8_t *be_records, uint64_t n_records);
+/* The same for the records a counter context on the same GPU has just selected (after its mfkc_emit_begin): the pairs
+ * are taken from the device arrays, no copy to the host and back (kmer-counter-many -> features-calculator in one run). */
+int  mfkc_fc_add_emitted(mfkc_ctx *ctx, mfkc_ctx *counter);
 /* reads mode (-i): same arguments as mfkc_submit_reads; no minSeqLen on this path. */
 int  mfkc_fc_add_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads);
 /* per component: vec = sum of values > threshold, found = how many such, cnt = keys considered.

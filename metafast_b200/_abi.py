@@ -106,6 +106,7 @@ SIGNATURES = {
     "mfkc_fc_set_selected": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "mfkc_fc_reset_values": (C.c_int, [C.c_void_p]),
     "mfkc_fc_add_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "mfkc_fc_add_emitted": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mfkc_fc_add_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "mfkc_fc_features": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mfkc_kset_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

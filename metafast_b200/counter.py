@@ -436,6 +436,10 @@ class FeaturesCalculator(_Ctx):
         b, o = pack_reads(reads)
         self._ck(self.lib.mfkc_fc_add_reads(self.h, _ptr(b), _ptr(o), len(reads)))
 
+    def add_emitted(self, counter: "KmerCounter"):
+        """the records `counter` (same GPU) selected with its last emit_begin, straight from device memory"""
+        self._ck(self.lib.mfkc_fc_add_emitted(self.h, counter.h))
+
     def features(self, threshold: int = 0):
         n = self.n_comp
         vec = np.zeros(max(n, 1), dtype=np.int64)

@@ -1745,6 +1745,15 @@ fc_records_kernel(const uint8_t *__restrict__ recs, uint64_t n, FcSlot *__restri
     }
 }
 
+// the same accumulate for (key, count) pairs that are still on the device (the counter's emit arrays): the
+// kmer-counter-many -> features-calculator hand-over without the round trip through a .kmers.bin file
+__global__ void __launch_bounds__(256)
+fc_pairs_kernel(const unsigned long long *__restrict__ keys, const uint16_t *__restrict__ counts, uint64_t n,
+                FcSlot *__restrict__ tab, uint64_t cap) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x)
+        fc_accumulate(tab, cap, keys[t], (long long)(short)counts[t]);
+}
+
 // Kmers2HMWorker.processKmer with threshold 0 (src/io/IOUtils.java:249-257): selected[key] =
 // sat_add16(selected[key], freq) for freq > 0.  The selected set reuses Slot.
 __global__ void __launch_bounds__(256)

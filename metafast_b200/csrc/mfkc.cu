@@ -2318,6 +2318,23 @@ extern "C" int mfkc_fc_add_records(mfkc_ctx *ctx, const uint8_t *be_records, uin
     return MFKC_OK;
 }
 
+// records that are still on the device: the emit arrays of a counter context on the same GPU (after mfkc_emit_begin)
+extern "C" int mfkc_fc_add_emitted(mfkc_ctx *ctx, mfkc_ctx *counter) {
+    if (!ctx || !counter) return fail(ctx, MFKC_E_BADARG, "null argument");
+    if (!ctx->fc_tab) return fail(ctx, MFKC_E_STATE, "no components loaded");
+    if (!counter->em_valid || counter->k128) return fail(ctx, MFKC_E_STATE, "mfkc_fc_add_emitted needs a counter after mfkc_emit_begin (k <= 31)");
+    if (counter->device != ctx->device) return fail(ctx, MFKC_E_BADARG, "the counter lives on another device");
+    if (counter->em_n == 0) return MFKC_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    {   // the counter's emit finished with a host synchronisation, so its arrays are complete
+        ProfScope ps(ctx, P_FC_RECORDS, ctx->compute);
+        fc_pairs_kernel<<<grid_for(ctx, counter->em_n, 256, 8), 256, 0, ctx->compute>>>(counter->em_keys, counter->em_counts, counter->em_n, ctx->fc_tab, ctx->fc_cap);
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(ctx->compute));             // the counter may reset its arrays as soon as this returns
+    return MFKC_OK;
+}
+
 extern "C" int mfkc_fc_add_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, uint32_t n_reads) {
     if (!ctx || (!bases && n_reads) || !offsets) return fail(ctx, MFKC_E_BADARG, "null argument");
     if (!ctx->fc_tab) return fail(ctx, MFKC_E_STATE, "no components loaded");

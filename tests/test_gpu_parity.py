@@ -617,6 +617,30 @@ def test_features_from_kmers_files(built):
         assert list(vec2) == orc.features([(0, c) for c in comps], acc, 0)[0]
 
 
+@pytest.mark.parametrize("variant", [m.VARIANT_HASH, m.VARIANT_SORT])
+def test_features_from_the_counters_device_arrays(built, variant):
+    """kmer-counter -> features-calculator without the .kmers.bin round trip (mfkc_fc_add_emitted): the same vectors as
+    from the records file."""
+    rng = np.random.default_rng(123)
+    reads = orc.parse_reads(os.path.join(INPUTS, "meta_test_1.fa"))
+    counts = orc.count_reads(reads, 31)
+    comps = _components_from(counts, rng)
+    with m.KmerCounter(31, variant=variant) as kc, m.FeaturesCalculator(31) as fc:
+        fc.load_components(comps)
+        kc.submit_reads(reads)
+        kc.flush()
+        for b, thr in ((1, 0), (0, 2)):
+            n_good = kc.emit_begin(b)
+            records = orc.kmers_bin(counts, b, 31)
+            assert n_good == len(records) // 10
+            fc.reset_values()
+            fc.add_emitted(kc)
+            vec, found, cnt = fc.features(thr)
+            acc = orc.presence_for_kmers([k for c in comps for k in c], orc.load_kmers_bin(records))
+            wv, wb, wf, wc = orc.features([(0, c) for c in comps], acc, thr)
+            assert list(vec) == wv and list(found) == wf and list(cnt) == wc
+
+
 def test_features_from_reads(built):
     rng = np.random.default_rng(5)
     reads = orc.parse_reads(os.path.join(INPUTS, "meta_test_2.fa"))
