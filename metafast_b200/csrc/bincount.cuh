@@ -15,13 +15,13 @@
 // the iteration + filter of IOUtils.printKmers (src/io/IOUtils.java:57-66) with identical results.
 //
 // Exactness under skew:
-//   * a bin whose records did not fit its staging segment (surplus in the overflow list) is HEAVY;
+//   * the records of a bin that did not fit its staging segment continue in 32-record chunks of an overflow pool
+//     (found through a tag table, ovf_chunk_of) and are streamed in like the segment's own batches;
 //   * a (sub-)pass that fills the shared-memory table aborts without output and is split by key hash into
 //     2..32 sub-ranges that are counted one after the other (the records are re-read from L2); a sub-range
 //     that still does not fit at 32 parts is HEAVY;
-//   * heavy (bin, sub-range) entries and the overflow list are counted by drain_heavy_kernel /
-//     drain_ovf_kernel into the global table (the legacy path of kernels.cuh) and emitted by table_scan_kernel
-//     into the same output arrays.  A k-mer belongs to exactly one (bin, sub-range), so nothing is counted twice.
+//   * heavy (bin, sub-range) entries are counted by drain_heavy_kernel into the global table (the legacy path of
+//     kernels.cuh) and emitted by table_scan_kernel into the same output arrays.  A k-mer belongs to exactly one (bin, sub-range), so nothing is counted twice.
 #pragma once
 #include "kernels.cuh"
 
@@ -36,7 +36,10 @@ constexpr uint32_t BC_MAX_PROBE = 256;     // probes after which an upsert gives
 
 struct BinSrc {
     const uint4 *recs[BC_MAX_SRC];             // source s: segment (seg0 + bin) of seg_cap records
-    const unsigned int *cursor[BC_MAX_SRC];    // records appended per segment (> seg_cap: the surplus is in the overflow list)
+    const unsigned int *cursor[BC_MAX_SRC];    // records appended per segment (> seg_cap: the surplus is in chunks of the overflow pool)
+    const uint4 *ovf[BC_MAX_SRC];              // overflow pool of source s: ovf_chunks chunks of 32 records ...
+    unsigned long long *ovf_tags[BC_MAX_SRC];  // ... and its tag table (ovf_chunk_of)
+    uint32_t ovf_chunks;
     uint64_t seg_cap;
     uint32_t n_src;
     uint32_t seg0;                             // first segment of this shard in every source (shard * n_bins)
@@ -153,12 +156,9 @@ bin_count_kernel(const __grid_constant__ BinCountArgs a) {
         __syncthreads();
         const uint32_t bin = vs_ctl[C_BIN];
         if (bin >= a.n_bins) break;
-        // records of this bin in every source; a source whose segment overflowed makes the bin heavy
-        uint64_t n_recs = 0; bool light = true;
-        for (uint32_t s = 0; s < a.src.n_src; s++) {
-            const uint32_t c = a.src.cursor[s][a.src.seg0 + bin];
-            if (c > a.src.seg_cap) { light = false; n_recs += a.src.seg_cap; } else n_recs += c;
-        }
+        // records of this bin in every source (segment + overflow chunks)
+        uint64_t n_recs = 0; const bool light = true;
+        for (uint32_t s = 0; s < a.src.n_src; s++) n_recs += a.src.cursor[s][a.src.seg0 + bin];
         if (tid == 0) recs_total += n_recs;
         if (n_recs == 0 && light) { __syncthreads(); continue; }
         if (!light || n_recs > a.max_recs) {
@@ -188,10 +188,10 @@ bin_count_kernel(const __grid_constant__ BinCountArgs a) {
                 uint32_t run = 0;
                 for (uint32_t sj = 0; sj < a.src.n_src; sj++) {
                     const uint32_t sidx = (sj + a.src.rot) % a.src.n_src;
-                    uint32_t n = a.src.cursor[sidx][a.src.seg0 + bin];
-                    if (n > a.src.seg_cap) n = (uint32_t)a.src.seg_cap;
+                    const uint32_t n = a.src.cursor[sidx][a.src.seg0 + bin];
+                    const uint32_t n_seg = n > a.src.seg_cap ? (uint32_t)a.src.seg_cap : n;
                     s_srcn[sj] = n; s_srcstart[sj] = run;
-                    run += (n + 31) >> 5;
+                    run += ((n_seg + 31) >> 5) + ((n - n_seg + 31) >> 5);      // batches of the segment, then one per overflow chunk
                 }
                 s_srcstart[a.src.n_src] = run;
                 s_ctl[C_NEXTB] = 0;
@@ -210,14 +210,28 @@ bin_count_kernel(const __grid_constant__ BinCountArgs a) {
                     while (g >= s_srcstart[sj + 1]) sj++;
                     const uint32_t bb = g - s_srcstart[sj], n = s_srcn[sj];
                     const uint32_t sidx = (sj + a.src.rot) % a.src.n_src;
-                    src_ptr = a.src.recs[sidx] + (uint64_t)(a.src.seg0 + bin) * a.src.seg_cap + (size_t)bb * 32;
-                    cnt = min(32u, n - bb * 32);
+                    const uint32_t n_seg = n > a.src.seg_cap ? (uint32_t)a.src.seg_cap : n;
+                    const uint32_t seg_batches = (n_seg + 31) >> 5;
+                    if (bb < seg_batches) {
+                        src_ptr = a.src.recs[sidx] + (uint64_t)(a.src.seg0 + bin) * a.src.seg_cap + (size_t)bb * 32;
+                        cnt = min(32u, n_seg - bb * 32);
+                    } else {                                         // overflow chunk j of this bin in this source
+                        const uint32_t j = bb - seg_batches;
+                        uint32_t ch = 0;
+                        if (lane == 0) ch = ovf_chunk_of<false>(a.src.ovf_tags[sidx], a.src.ovf_chunks, a.src.seg0 + bin, j, nullptr);
+                        ch = __shfl_sync(FULL, ch, 0);
+                        src_ptr = a.src.ovf[sidx] + (size_t)(ch == OVF_NO_CHUNK ? 0u : ch) * 32;
+                        cnt = ch == OVF_NO_CHUNK ? 0u : min(32u, n - n_seg - j * 32);      // (a missing chunk = dropped records: reported by mfkc_flush)
+                    }
                     return true;
                 };
                 uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
                 auto issue = [&]() {                                 // start moving the fetched batch: TMA bulk copy, or a plain load
                     if (a.use_tma) {
-                        if (lane == 0) { mbar_expect_tx(bar, cnt * 16u); bulk_g2s(ring, src_ptr, cnt * 16u, bar); }
+                        if (lane == 0) {
+                            if (cnt) { mbar_expect_tx(bar, cnt * 16u); bulk_g2s(ring, src_ptr, cnt * 16u, bar); }
+                            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");      // empty batch: complete the phase
+                        }
                     } else if (lane < cnt) nxt = ld_nc_u128(src_ptr + lane);
                 };
                 bool have = fetch();
@@ -392,15 +406,27 @@ drain_heavy_kernel(BinSrc src, const HeavyEnt *__restrict__ heavy, uint32_t n_he
     const HeavyEnt ent = heavy[e];
     const uint32_t p = ent.p, P = ent.P;
     uint32_t claimed = 0;
+    auto put = [&](uint64_t key, uint32_t) {
+        if (P > 1 && (bc_hash(key) & (P - 1u)) != p) return;
+        claimed += placed_upsert_at<true>(tab, g.cap, g.region_shift, g.minimizer ? g.win : 0u, geom_home(g, key), key, 1u) ? 1u : 0u;
+    };
+    const uint32_t warp = threadIdx.x >> 5;
     for (uint32_t sj = 0; sj < src.n_src; sj++) {
         const uint32_t s = (sj + src.rot) % src.n_src;
-        uint64_t n = src.cursor[s][src.seg0 + ent.bin];
-        if (n > src.seg_cap) n = src.seg_cap;
-        skm_expand_records(src.recs[s] + (uint64_t)(src.seg0 + ent.bin) * src.seg_cap, n, (uint64_t)sub * 256, (uint64_t)blocks_per_ent * 256, k, s_rec, s_pre,
-                           [&](uint64_t key, uint32_t) {
-                               if (P > 1 && (bc_hash(key) & (P - 1u)) != p) return;
-                               claimed += placed_upsert_at<true>(tab, g.cap, g.region_shift, g.minimizer ? g.win : 0u, geom_home(g, key), key, 1u) ? 1u : 0u;
-                           });
+        const uint64_t n = src.cursor[s][src.seg0 + ent.bin];
+        const uint64_t n_seg = n > src.seg_cap ? src.seg_cap : n;
+        skm_expand_records(src.recs[s] + (uint64_t)(src.seg0 + ent.bin) * src.seg_cap, n_seg, (uint64_t)sub * 256, (uint64_t)blocks_per_ent * 256, k, s_rec, s_pre, put);
+        // overflow chunks: chunk j goes to warp j of the entry's CTAs (skm_expand_records hands warp w the records
+        // [32 w, 32 w + 32) of its array, hence the shifted base pointer)
+        const uint32_t n_over = (uint32_t)(n - n_seg), n_chunks = (n_over + 31) >> 5;
+        for (uint32_t j = sub * 8 + warp; j < n_chunks; j += blocks_per_ent * 8) {
+            uint32_t ch = 0;
+            if ((threadIdx.x & 31) == 0) ch = ovf_chunk_of<false>(src.ovf_tags[s], src.ovf_chunks, src.seg0 + ent.bin, j, nullptr);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            if (ch == OVF_NO_CHUNK) continue;
+            const uint32_t cnt = min(32u, n_over - j * 32);
+            skm_expand_records(src.ovf[s] + (size_t)ch * 32 - (size_t)warp * 32, (uint64_t)warp * 32 + cnt, 0, ~0ull >> 2, k, s_rec, s_pre, put);
+        }
     }
     for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
     if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
@@ -410,25 +436,6 @@ drain_heavy_kernel(BinSrc src, const HeavyEnt *__restrict__ heavy, uint32_t n_he
 __global__ void __launch_bounds__(256)
 heavy_all_bins_kernel(HeavyEnt *__restrict__ heavy, uint32_t n_bins) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bins; i += gridDim.x * blockDim.x) { HeavyEnt e; e.bin = i; e.p = 0; e.P = 1; heavy[i] = e; }
-}
-
-// overflow list: records that found their segment full.  With n_shards > 1 the list of a peer holds records of every
-// owner; `me` keeps the ones whose minimizer belongs to this shard (the record carries its minimizer hash in w).
-__global__ void __launch_bounds__(256)
-drain_ovf_kernel(const uint4 *__restrict__ ovf, const unsigned int *__restrict__ ovf_cursor, uint32_t ovf_cap, uint32_t n_shards, uint32_t me, int k,
-                 Slot *__restrict__ tab, TableGeom g, Counters *__restrict__ ctr) {
-    __shared__ uint4 s_rec[8][32];
-    __shared__ uint32_t s_pre[8][33];
-    uint64_t n = *ovf_cursor;
-    if (n > ovf_cap) n = ovf_cap;
-    uint32_t claimed = 0;
-    skm_expand_records(ovf, n, (uint64_t)blockIdx.x * 256, (uint64_t)gridDim.x * 256, k, s_rec, s_pre,
-                       [&](uint64_t key, uint32_t mh) {
-                           if (n_shards > 1 && owner_of_minhash(mh, n_shards) != me) return;
-                           claimed += placed_upsert_at<true>(tab, g.cap, g.region_shift, g.minimizer ? g.win : 0u, geom_home(g, key), key, 1u) ? 1u : 0u;
-                       });
-    for (int o = 16; o; o >>= 1) claimed += __shfl_xor_sync(0xffffffffu, claimed, o);
-    if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(&ctr->distinct, (unsigned long long)claimed);
 }
 
 }  // namespace mfkc

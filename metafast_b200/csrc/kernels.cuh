@@ -839,13 +839,55 @@ struct SkmStage {
     uint32_t n_regions;
     int region_shift;
     uint32_t win;                 // primary window of the windowed placement (0 = plain linear probing), see placed_upsert_at
-    // MODE 3 (bin-local counting): records that find their bin's segment full go to this list instead
-    uint4 *ovf; unsigned int *ovf_cursor; uint32_t ovf_cap;
+    // MODE 3 / 4 (bin-local counting): records that find their bin's segment full are appended to this list together with
+    // (segment, position past the segment); ovf_place_kernel files them into the chunk pool before the count
+    uint4 *ovf; uint2 *ovf_meta; unsigned int *ovf_used; uint32_t ovf_cap;
     int mlen;                     // MODE 3 / 4: minimizer length (bin_minimizer_len); other modes use minimizer_len(k)
 };
 
 __device__ __forceinline__ uint32_t kmers_of_word(uint32_t w0, uint32_t w1, uint32_t w2, uint64_t flag_bits,
                                                   long long limit, int k, uint64_t (&keys)[16]);
+
+// Overflow pool of the bin staging: the records of a bin beyond its segment go to chunks of 32 records; chunk j of segment
+// `seg` lives wherever the probe sequence of (seg, j) first met a free or matching tag.  Writers claim (CLAIM = true, lock
+// free: the first record of a chunk to arrive takes the slot, nobody ever waits), readers only look up.  Returns the chunk
+// index or 0xFFFFFFFF (pool full / chunk never written).
+constexpr unsigned long long OVF_EMPTY_TAG = ~0ull;
+constexpr uint32_t OVF_NO_CHUNK = 0xFFFFFFFFu;
+constexpr uint32_t OVF_MAX_PROBE = 4096;
+template <bool CLAIM>
+__device__ __forceinline__ uint32_t ovf_chunk_of(unsigned long long *tags, uint32_t n_chunks, uint32_t seg, uint32_t j, unsigned int *used) {
+    const unsigned long long tag = ((unsigned long long)seg << 32) | j;
+    uint32_t c = (uint32_t)(((uint64_t)hash32(seg * 0x9E3779B1u + j * 0x85EBCA6Bu + 0x27d4eb2fu) * n_chunks) >> 32);
+    for (uint32_t probe = 0; probe < OVF_MAX_PROBE && probe < n_chunks; probe++) {
+        unsigned long long cur = ld_cg_u64(&tags[c]);
+        if (cur == tag) return c;
+        if (cur == OVF_EMPTY_TAG) {
+            if (!CLAIM) return OVF_NO_CHUNK;
+            cur = atomicCAS(&tags[c], OVF_EMPTY_TAG, tag);
+            if (cur == OVF_EMPTY_TAG) { if (used) atomicAdd(used, 1u); return c; }
+            if (cur == tag) return c;
+        }
+        if (++c == n_chunks) c = 0;
+    }
+    return OVF_NO_CHUNK;
+}
+// Overflow list -> chunk pool (run before every count; filing a record twice is harmless).  The list is filled by the
+// extraction kernel with one cursor atomic per record; doing the chunk lookup there instead costs that kernel registers.
+__global__ void __launch_bounds__(256)
+ovf_place_kernel(const uint4 *__restrict__ list, const uint2 *__restrict__ meta, const unsigned int *__restrict__ n_list, uint32_t list_cap,
+                 uint4 *__restrict__ pool, unsigned long long *__restrict__ tags, uint32_t n_chunks, Counters *__restrict__ ctr) {
+    uint32_t n = *n_list;
+    if (n > list_cap) n = list_cap;
+    uint32_t dropped = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 mt = meta[i];
+        const uint32_t ch = ovf_chunk_of<true>(tags, n_chunks, mt.x, mt.y >> 5, nullptr);
+        if (ch == OVF_NO_CHUNK) { dropped++; continue; }
+        pool[(uint64_t)ch * 32 + (mt.y & 31u)] = list[i];
+    }
+    if (dropped) atomicAdd(&ctr->overflow, (unsigned long long)dropped);
+}
 
 // a record that found its region segment full: count its k-mers straight into the table
 template <class Tab>
@@ -1035,16 +1077,14 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                                     if (st.n_regions <= 8) { if (o < 4) km_lo += (unsigned long long)len << (16 * o); else km_hi += (unsigned long long)len << (16 * (o - 4)); }
                                     else atomicAdd(&kmer_count[o], (unsigned long long)len);
                                 }
-                            } else if (MODE == 3 || MODE == 4) {    // segment full: overflow list (counted through the table later)
-                                const uint32_t o = atomicAdd(st.ovf_cursor, 1u);
-                                if (o < st.ovf_cap) {
-                                    st.ovf[o] = rec;
-                                    if (MODE == 4) {
-                                        const uint32_t ow = bucket / st.win;
-                                        if (st.n_regions <= 8) { if (ow < 4) km_lo += (unsigned long long)len << (16 * ow); else km_hi += (unsigned long long)len << (16 * (ow - 4)); }
-                                        else atomicAdd(&kmer_count[ow], (unsigned long long)len);
-                                    }
-                                } else dropped++;
+                            } else if (MODE == 3 || MODE == 4) {    // segment full: overflow list (filed into the chunk pool before the count)
+                                const uint32_t o = atomicAdd(st.ovf_used, 1u);
+                                if (o < st.ovf_cap) { st.ovf[o] = rec; st.ovf_meta[o] = make_uint2(bucket, pos[j] - seg32); } else dropped++;
+                                if (MODE == 4) {                    // (counted for its owner even if dropped: mfkc_flush reports the drop)
+                                    const uint32_t ow = bucket / st.win;
+                                    if (st.n_regions <= 8) { if (ow < 4) km_lo += (unsigned long long)len << (16 * ow); else km_hi += (unsigned long long)len << (16 * (ow - 4)); }
+                                    else atomicAdd(&kmer_count[ow], (unsigned long long)len);
+                                }
                             } else if (!BY_OWNER) {                 // segment full: count the run directly (slow, exact)
                                 claimed += skm_count_direct(rec, bucket, st.region_shift, st.win, k, tb);
                             } else if (MODE == 2) dropped++;        // reported as an error by mfkc_flush (segments are sized with 2x slack)

@@ -875,19 +875,32 @@ static int extract_grid(const mfkc_ctx *ctx, uint64_t n_bases) {
 // ------------------------------------------------------------------------------------------
 // bin-local counting (bincount.cuh): planning, staging, the count pass, the way back to the table
 // ------------------------------------------------------------------------------------------
+// overflow area behind the segments: [list: cap records][meta: cap x 8 B][pool: 2 cap records in chunks of 32][tags: cap / 16 x 8 B]
+struct OvfLayout { uint4 *list; uint2 *meta; uint4 *pool; unsigned long long *tags; uint32_t n_chunks; };
+static OvfLayout ovf_layout(uint4 *after_segments, uint64_t cap) {
+    OvfLayout o;
+    o.list = after_segments; o.meta = reinterpret_cast<uint2 *>(o.list + cap);
+    o.pool = reinterpret_cast<uint4 *>(o.meta + cap); o.tags = reinterpret_cast<unsigned long long *>(o.pool + 2 * cap);
+    o.n_chunks = (uint32_t)(2 * cap / 32);
+    return o;
+}
+static uint64_t ovf_bytes(uint64_t cap) { return cap * 16 + cap * 8 + 2 * cap * 16 + (2 * cap / 32) * 8; }
+
 static SkmStage bin_stage(const mfkc_ctx *ctx) {
     SkmStage st{};
     if (ctx->p2p_bins) {             // sharded: segment (owner * B + bin) of this rank's own staging buffer, extract mode 4
         const uint64_t G = (uint64_t)std::max(1, ctx->cfg.n_shards);
         st.recs = ctx->p2p_recs; st.cursor = ctx->p2p_cursor; st.seg_cap = ctx->p2p_seg_cap;
         st.n_regions = (uint32_t)G; st.region_shift = 0; st.win = ctx->p2p_B;
-        st.ovf = st.recs + G * ctx->p2p_B * ctx->p2p_seg_cap; st.ovf_cursor = ctx->p2p_cursor + G * ctx->p2p_B; st.ovf_cap = (uint32_t)ctx->p2p_ovf_cap;
+        const OvfLayout o = ovf_layout(st.recs + G * ctx->p2p_B * ctx->p2p_seg_cap, ctx->p2p_ovf_cap);
+        st.ovf = o.list; st.ovf_meta = o.meta; st.ovf_used = ctx->p2p_cursor + G * ctx->p2p_B; st.ovf_cap = (uint32_t)ctx->p2p_ovf_cap;
         st.mlen = ctx->os_mlen;
         return st;
     }
     st.recs = reinterpret_cast<uint4 *>(ctx->rb_keys); st.cursor = ctx->rb_cursor;
     st.seg_cap = ctx->os_seg_cap; st.n_regions = ctx->os_n_bins; st.region_shift = 0; st.win = 0;
-    st.ovf = st.recs + (uint64_t)ctx->os_n_bins * ctx->os_seg_cap; st.ovf_cursor = &ctx->d_binctl->ovf_cursor; st.ovf_cap = (uint32_t)ctx->os_ovf_cap;
+    const OvfLayout o = ovf_layout(st.recs + (uint64_t)ctx->os_n_bins * ctx->os_seg_cap, ctx->os_ovf_cap);
+    st.ovf = o.list; st.ovf_meta = o.meta; st.ovf_used = &ctx->d_binctl->ovf_cursor; st.ovf_cap = (uint32_t)ctx->os_ovf_cap;
     st.mlen = ctx->os_mlen;
     return st;
 }
@@ -895,11 +908,20 @@ static BinSrc bin_src(const mfkc_ctx *ctx) {
     BinSrc b{};
     if (ctx->p2p_bins) {             // this shard's bins in every peer's staging buffer (peer memory over NVLink)
         const uint32_t G = (uint32_t)std::max(1, ctx->cfg.n_shards);
-        for (uint32_t i = 0; i < G; i++) { b.recs[i] = ctx->p2p_peer_recs[i]; b.cursor[i] = ctx->p2p_peer_cursor[i]; }
+        const uint64_t n_seg_recs = (uint64_t)G * ctx->p2p_B * ctx->p2p_seg_cap;
+        for (uint32_t i = 0; i < G; i++) {
+            b.recs[i] = ctx->p2p_peer_recs[i]; b.cursor[i] = ctx->p2p_peer_cursor[i];
+            const OvfLayout o = ovf_layout(const_cast<uint4 *>(ctx->p2p_peer_recs[i]) + n_seg_recs, ctx->p2p_ovf_cap);
+            b.ovf[i] = o.pool; b.ovf_tags[i] = o.tags; b.ovf_chunks = o.n_chunks;
+        }
         b.seg_cap = ctx->p2p_seg_cap; b.n_src = G; b.seg0 = (uint32_t)ctx->cfg.shard_id * ctx->p2p_B; b.rot = (uint32_t)ctx->cfg.shard_id;
         return b;
     }
     b.recs[0] = reinterpret_cast<const uint4 *>(ctx->rb_keys); b.cursor[0] = ctx->rb_cursor;
+    {
+        const OvfLayout o = ovf_layout(reinterpret_cast<uint4 *>(ctx->rb_keys) + (uint64_t)ctx->os_n_bins * ctx->os_seg_cap, ctx->os_ovf_cap);
+        b.ovf[0] = o.pool; b.ovf_tags[0] = o.tags; b.ovf_chunks = o.n_chunks;
+    }
     b.seg_cap = ctx->os_seg_cap; b.n_src = 1; b.seg0 = 0; b.rot = 0;
     return b;
 }
@@ -925,7 +947,7 @@ static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
     const double env_load = getenv("MFKC_BIN_LOAD") ? atof(getenv("MFKC_BIN_LOAD")) : 0.0;
     const long env_nbins = getenv("MFKC_BIN_COUNT") ? atol(getenv("MFKC_BIN_COUNT")) : 0;
     const long env_ovf = getenv("MFKC_BIN_OVF") ? atol(getenv("MFKC_BIN_OVF")) : 0;
-    const double slack = env_slack > 0.0 ? env_slack : 2.0;
+    const double slack = env_slack > 0.0 ? env_slack : 1.5;          // what does not fit continues in the overflow pool, at no loss
     const double load = env_load > 0 ? env_load : 0.45;
     const double S = (double)(1u << BC_LOG2S);
     uint64_t n_bins = (uint64_t)(kmers / R / (load * S)) + 1;
@@ -939,7 +961,8 @@ static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
     if (seg_cap > 0x7fffffffull) return MFKC_OK;
     uint64_t ovf_cap = std::min<uint64_t>(std::max<uint64_t>((uint64_t)(recs * 0.06), 1ull << 16), 0x7fffffffull);
     if (env_ovf > 0) ovf_cap = (uint64_t)env_ovf;
-    const uint64_t need_units = 2 * (n_bins * seg_cap + ovf_cap);            // 8-byte units of rb_keys
+    ovf_cap = (ovf_cap + 31) / 32 * 32;                                     // whole chunks of 32 records
+    const uint64_t need_units = 2 * n_bins * seg_cap + ovf_bytes(ovf_cap) / 8 + 2;        // 8-byte units of rb_keys: segments + overflow area
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t have = ctx->rb_cap * 8;
@@ -958,6 +981,10 @@ static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
         CU_TRY(cudaMalloc(&ctx->d_heavy, (size_t)ctx->heavy_cap * sizeof(HeavyEnt)));
     }
     ctx->os_n_bins = (uint32_t)n_bins; ctx->os_seg_cap = seg_cap; ctx->os_ovf_cap = ovf_cap; ctx->os_mlen = mlen;
+    {   // no chunk of the overflow pool is taken
+        const OvfLayout o = ovf_layout(reinterpret_cast<uint4 *>(ctx->rb_keys) + n_bins * seg_cap, ovf_cap);
+        CU_TRY(cudaMemsetAsync(o.tags, 0xFF, (size_t)o.n_chunks * sizeof(unsigned long long), ctx->compute));
+    }
     ctx->os_kmers_budget = (uint64_t)(kmers * 1.2);
     ctx->os_kmers_staged = 0;
     ctx->mode = 1;
@@ -966,6 +993,15 @@ static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
 
 static int grow_table(mfkc_ctx *ctx, uint64_t need_slots);
 static int reserve_slots(mfkc_ctx *ctx, uint64_t add);
+
+// this context's overflow list -> chunk pool (before anybody counts its bins; idempotent)
+static int place_overflow(mfkc_ctx *ctx) {
+    const SkmStage st = bin_stage(ctx);
+    const OvfLayout o = ovf_layout(st.ovf, st.ovf_cap);
+    ovf_place_kernel<<<ctx->sm_count * 4, 256, 0, ctx->compute>>>(st.ovf, st.ovf_meta, st.ovf_used, st.ovf_cap, o.pool, o.tags, o.n_chunks, ctx->d_ctr);
+    CU_TRY(cudaGetLastError());
+    return MFKC_OK;
+}
 
 // heavy entries [e0, e1) and, with ovf, the overflow list -> global table (placement by TableGeom g)
 static int launch_heavy(mfkc_ctx *ctx, uint32_t e0, uint32_t e1, bool ovf, const TableGeom &g) {
@@ -976,21 +1012,7 @@ static int launch_heavy(mfkc_ctx *ctx, uint32_t e0, uint32_t e1, bool ovf, const
         drain_heavy_kernel<<<(e1 - e0) * bpe, 256, 0, ctx->compute>>>(bin_src(ctx), ctx->d_heavy + e0, e1 - e0, bpe, ctx->cfg.k, ctx->tab, g, ctx->d_ctr);
         CU_TRY(cudaGetLastError());
     }
-    if (ovf && ctx->p2p_bins) {      // every peer's overflow list, filtered by owner
-        const uint32_t G = (uint32_t)std::max(1, ctx->cfg.n_shards);
-        const uint64_t n_seg = (uint64_t)G * ctx->p2p_B;
-        for (uint32_t i = 0; i < G; i++) {
-            ctx->prof_launches[P_DRAIN_HEAVY]++;
-            drain_ovf_kernel<<<ctx->sm_count * 2, 256, 0, ctx->compute>>>(ctx->p2p_peer_recs[i] + n_seg * ctx->p2p_seg_cap, ctx->p2p_peer_cursor[i] + n_seg,
-                                                                          (uint32_t)ctx->p2p_ovf_cap, G, (uint32_t)ctx->cfg.shard_id, ctx->cfg.k, ctx->tab, g, ctx->d_ctr);
-            CU_TRY(cudaGetLastError());
-        }
-    } else if (ovf) {
-        const SkmStage st = bin_stage(ctx);
-        ctx->prof_launches[P_DRAIN_HEAVY]++;
-        drain_ovf_kernel<<<ctx->sm_count * 4, 256, 0, ctx->compute>>>(st.ovf, st.ovf_cursor, st.ovf_cap, 1u, 0u, ctx->cfg.k, ctx->tab, g, ctx->d_ctr);
-        CU_TRY(cudaGetLastError());
-    }
+    (void)ovf;                       // overflow chunks belong to their bins: drain_heavy_kernel reads them with the segment
     return MFKC_OK;
 }
 
@@ -1018,6 +1040,7 @@ static int overflow_records(mfkc_ctx *ctx, uint64_t *n) {
 // grows on exact distinct counts, and the sample continues in mode 0.
 static int bins_to_table(mfkc_ctx *ctx) {
     if (ctx->mode != 1) return MFKC_OK;
+    if (!ctx->p2p_bins) TRY(place_overflow(ctx));          // (a sharded context filed its list in mfkc_p2p_counts)
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
     ctx->mode = 0; ctx->os_counted = false;
@@ -1050,13 +1073,6 @@ static int bins_to_table(mfkc_ctx *ctx) {
             TRY(launch_heavy(ctx, b0, b1, false, table_geom(ctx)));
         }
         TRY(sync_all(ctx));
-        uint64_t n_ovf = 0;
-        TRY(overflow_records(ctx, &n_ovf));
-        if (n_ovf) {
-            TRY(reserve_slots(ctx, 16 * n_ovf));
-            ctx->recv_since_base += 16 * n_ovf;
-            TRY(launch_heavy(ctx, 0, 0, true, table_geom(ctx)));
-        }
     }
     if (!ctx->p2p_bins) {            // (a sharded context leaves the staging buffers alone: the peers read them too)
         CU_TRY(cudaMemsetAsync(ctx->rb_cursor, 0, MAX_REGIONS_SKM * sizeof(unsigned int), ctx->compute));
@@ -1111,8 +1127,10 @@ static int bins_count(mfkc_ctx *ctx, uint32_t thr) {
     if (ctx->os_counted && (!want_out || (ctx->os_thr == thr && (ctx->os_keys || ctx->os_n_good == 0)))) return MFKC_OK;
     static const bool low = getenv("MFKC_EMIT_PRIORITY") == nullptr || atoi(getenv("MFKC_EMIT_PRIORITY")) != 0;
     cudaStream_t st = low ? ctx->emit : ctx->compute;
+    if (!ctx->p2p_bins) TRY(place_overflow(ctx));          // (a sharded context filed its list in mfkc_p2p_counts)
     TRY(sync_all(ctx));
     TRY(read_counters(ctx));
+    if (ctx->h_ctr->overflow) return fail(ctx, MFKC_E_STATE, "internal key buffer overflow");
     free_bin_outputs(ctx);
     const uint64_t kmers = ctx->p2p_bins ? ctx->p2p_kmers_in : ctx->h_ctr->kmers;
     uint64_t out_cap = 0;
@@ -1157,11 +1175,11 @@ static int bins_count(mfkc_ctx *ctx, uint32_t thr) {
             TRY(bins_to_table(ctx));
             return 1;
         }
-        if (c.n_heavy || n_ovf) {
-            const int r = resid_table_prepare(ctx, 16 * (c.heavy_recs + n_ovf));
+        if (c.n_heavy) {
+            const int r = resid_table_prepare(ctx, 16 * c.heavy_recs);
             if (r != MFKC_OK) { TMP_FREE(ok); TMP_FREE(oc); ctx->err.clear(); TRY(bins_to_table(ctx)); return 1; }
             TableGeom g = table_geom(ctx); g.minimizer = 0; g.win = 0;
-            TRY(launch_heavy(ctx, 0, c.n_heavy, n_ovf != 0, g));          // (on the compute stream, like the table clear before)
+            TRY(launch_heavy(ctx, 0, c.n_heavy, false, g));               // (on the compute stream, like the table clear before)
             TRY(stream_after(ctx, st, ctx->compute));
             {
                 ProfScope ps(ctx, P_COMPACT, st);
@@ -2020,7 +2038,9 @@ extern "C" int mfkc_p2p_stage_create_bins(mfkc_ctx *ctx, uint32_t bins_per_shard
     cudaFree(ctx->p2p_recs); cudaFree(ctx->p2p_cursor); cudaFree(ctx->p2p_kc);
     ctx->p2p_recs = nullptr; ctx->p2p_cursor = nullptr; ctx->p2p_kc = nullptr;
     const uint64_t n_seg = (uint64_t)std::max(1, ctx->cfg.n_shards) * bins_per_shard;
-    if (big_alloc(ctx, (void **)&ctx->p2p_recs, (n_seg * seg_cap + ovf_cap) * sizeof(uint4)) != cudaSuccess) return fail(ctx, MFKC_E_OOM, "cannot allocate the p2p staging buffer");
+    ovf_cap = (ovf_cap + 31) / 32 * 32;                                       // whole chunks; the tag table follows the pool
+    if (big_alloc(ctx, (void **)&ctx->p2p_recs, n_seg * seg_cap * sizeof(uint4) + ovf_bytes(ovf_cap)) != cudaSuccess)
+        return fail(ctx, MFKC_E_OOM, "cannot allocate the p2p staging buffer");
     CU_TRY(cudaMalloc(&ctx->p2p_cursor, (n_seg + 1) * sizeof(unsigned int)));
     CU_TRY(cudaMalloc(&ctx->p2p_kc, P2P_MAX_PEERS * sizeof(unsigned long long)));
     CU_TRY(cudaMemset(ctx->p2p_cursor, 0, (n_seg + 1) * sizeof(unsigned int)));
@@ -2089,6 +2109,10 @@ extern "C" int mfkc_p2p_stage_reset(mfkc_ctx *ctx) {
     CU_TRY(cudaSetDevice(ctx->device));
     CU_TRY(cudaMemsetAsync(ctx->p2p_cursor, 0, ctx->p2p_n_cursor * sizeof(unsigned int), ctx->compute));
     CU_TRY(cudaMemsetAsync(ctx->p2p_kc, 0, P2P_MAX_PEERS * sizeof(unsigned long long), ctx->compute));
+    if (ctx->p2p_bins) {
+        const OvfLayout o = ovf_layout(ctx->p2p_recs + (uint64_t)std::max(1, ctx->cfg.n_shards) * ctx->p2p_B * ctx->p2p_seg_cap, ctx->p2p_ovf_cap);
+        CU_TRY(cudaMemsetAsync(o.tags, 0xFF, (size_t)o.n_chunks * sizeof(unsigned long long), ctx->compute));
+    }
     ctx->p2p_kmers_in = 0;
     if (ctx->p2p_bins) { ctx->os_counted = false; if (ctx->mode == 1) ctx->mode = 0; }
     return MFKC_OK;
@@ -2144,6 +2168,7 @@ extern "C" int mfkc_p2p_counts(mfkc_ctx *ctx, uint64_t *kmers_per_owner) {
     if (!kmers_per_owner || !ctx->p2p_kc) return fail(ctx, MFKC_E_BADARG, "null argument");
     CU_TRY(cudaSetDevice(ctx->device));
     const int ns = std::max(1, ctx->cfg.n_shards);
+    if (ctx->p2p_bins) TRY(place_overflow(ctx));            // the peers find this rank's overflow records through the chunk pool
     CU_TRY(cudaMemcpyAsync(ctx->h_bucket, ctx->p2p_kc, ns * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->compute));
     CU_TRY(cudaStreamSynchronize(ctx->compute));          // every record of this rank is in its staging buffer
     for (int i = 0; i < ns; i++) kmers_per_owner[i] = ctx->h_bucket[i];
