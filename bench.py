@@ -55,10 +55,10 @@ def load_peaks():
 
 
 def load_traffic():
-    """DRAM bytes (read + write) of the counting kernels per step, from the committed ncu --set full capture
-    (profiles/r1_traffic.json: 20 extract_skm launches + the drain of one cfg2 step); None if absent or if the
-    run is not the configuration the capture was taken on."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    """DRAM bytes (read + write) of the counting kernels per step, from the committed ncu capture of one step
+    (profiles/r2_traffic.json, written by tools/ncu_traffic.py: 20 mark + 20 extract_skm launches + bin_count); None if absent
+    or if the run is not the configuration the capture was taken on (other read count, other variant, N > 1)."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if N_READS != 20_000_000 or os.environ.get("MFKC_BENCH_VARIANT") or not os.path.exists(p):
         return None
     try:
@@ -775,7 +775,7 @@ def main():
     gups_rate = (1 << 28) / (gups_ms / 1e3)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-        "traffic": load_traffic(), "peak_source": peak_src,
+        "traffic": load_traffic() if world == 1 else None, "peak_source": peak_src,
         "kernel": "+".join(count_kernels), "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER,
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
         "kernel_launches_per_step": {k: v[1] / args.steps for k, v in prof.items() if v[1]},

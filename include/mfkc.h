@@ -78,7 +78,7 @@ typedef struct mfkc_cfg {
     uint64_t expected_distinct; /* sizing hint (distinct k-mers); 0 = unknown, table grows x2 on demand */
     uint64_t max_table_bytes;   /* growth limit; 0 = 80 % of free device memory */
     uint64_t staging_bytes;     /* HASH: key staging buffer; 0 = adaptive (starts at 4 batches, doubles when full) */
-    uint32_t region_shift;      /* HASH: log2(table slots per region); 0 = 19 (8 MiB regions) */
+    uint32_t region_shift;      /* HASH_TABLE path: log2(table slots per region); 0 = 17 (2 MiB regions of 16-byte slots) */
     uint32_t reserved2;
     uint64_t expected_kmers;    /* sizing hint: k-mer INSTANCES of the sample (<= bases in the input files).  HASH: staging
                                    holds them all (one drain) and, without expected_distinct, the table is sized for the

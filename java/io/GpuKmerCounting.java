@@ -103,8 +103,8 @@ public final class GpuKmerCounting {
     static long submitFileNative(MemorySegment ctx, File file, MemorySegment hBases, long capBases, MemorySegment hOffs,
                                  int capReads, Arena arena) throws Throwable {
         MemorySegment pReader = arena.allocate(ADDRESS), err = arena.allocate(512), n = arena.allocate(JAVA_INT);
-        int rc = (int) MfkcNative.READER_OPEN.invokeExact(arena.allocateUtf8String(file.getPath()), pReader, err, 512L);
-        if (rc != 0) throw new ExecutionFailedException(err.getUtf8String(0));
+        int rc = (int) MfkcNative.READER_OPEN.invokeExact(arena.allocateFrom(file.getPath()), pReader, err, 512L);
+        if (rc != 0) throw new ExecutionFailedException(err.getString(0));
         MemorySegment reader = pReader.get(ADDRESS, 0);
         long reads = 0;
         try {

@@ -71,6 +71,12 @@ public final class MfkcNative {
 
     // ---- multi-GPU: one context per GPU (cfg.n_shards / shard_id); a single JVM attaches the contexts to each other directly
     static final MethodHandle P2P_STAGE_CREATE = h("mfkc_p2p_stage_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG));
+    // the bin-local flavour (k <= 31): geometry from the expected k-mers per GPU, (owner, bin) staging + overflow pool
+    static final MethodHandle P2P_BIN_GEOMETRY = h("mfkc_p2p_bin_geometry", FunctionDescriptor.of(JAVA_INT, JAVA_LONG, JAVA_INT, JAVA_INT, JAVA_DOUBLE, JAVA_DOUBLE, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle P2P_STAGE_CREATE_BINS = h("mfkc_p2p_stage_create_bins", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG, JAVA_LONG));
+    static final MethodHandle MERGE_RECORDS = h("mfkc_merge_records", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_INT));
+    static final MethodHandle FC_ADD_EMITTED = h("mfkc_fc_add_emitted", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    static final MethodHandle LIBRARY_NAME = h("mfkc_library_name", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG));
     static final MethodHandle P2P_ATTACH_CTX = h("mfkc_p2p_attach_ctx", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
     static final MethodHandle P2P_STAGE_RESET = h("mfkc_p2p_stage_reset", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     static final MethodHandle P2P_SUBMIT_READS = h("mfkc_p2p_submit_reads", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT));

@@ -15,6 +15,7 @@
 // src/tools/FeaturesCalculatorMain.java:30-236 and src/structures/ConnectedComponent.java:95-122:
 // same option names, defaults, output locations, log lines and exit codes.
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <charconv>
@@ -39,7 +40,10 @@ namespace {
     va_list ap; va_start(ap, fmt);
     fputs("ERROR: ", stderr); vfprintf(stderr, fmt, ap); fputc('\n', stderr);
     va_end(ap);
-    exit(1);                                              // Tool.java:450-462: logged, System.exit(1)
+    // Tool.java:450-462: logged, System.exit(1).  _exit: reader / worker threads of other open files and GPU contexts may
+    // still be running; static destructors and CUDA teardown under their feet could crash and change the exit code
+    fflush(stdout); fflush(stderr);
+    _exit(1);
 }
 void info(const char *fmt, ...) { va_list ap; va_start(ap, fmt); fputs("INFO: ", stderr); vfprintf(stderr, fmt, ap); fputc('\n', stderr); va_end(ap); }
 void warn(const char *fmt, ...) { va_list ap; va_start(ap, fmt); fputs("WARN: ", stderr); vfprintf(stderr, fmt, ap); fputc('\n', stderr); va_end(ap); }

@@ -26,7 +26,8 @@ namespace mfkc {
 #if defined(__x86_64__)
 // reflected CRC-32 (polynomial 0xEDB88320) by carry-less multiplication, 64 bytes per iteration (the folding scheme of
 // Gopal et al., "Fast CRC Computation for Generic Polynomials Using PCLMULQDQ Instruction", Intel 2009, with the folding
-// constants for this polynomial as published there and used by zlib forks); len >= 64 and a multiple of 16; crc in / out = the raw register
+// constants for this polynomial as published there and used by zlib forks -- the routine follows the structure of
+// Chromium zlib's crc32_simd.c, (c) The Chromium Authors, BSD-style licence -- ); len >= 64 and a multiple of 16; crc in / out = the raw register
 // (the complement of zlib's value).  Checked against zlib's crc32 in tests/test_host.py.
 __attribute__((target("pclmul,sse4.1")))
 inline uint32_t crc32_clmul_raw(const uint8_t *buf, size_t len, uint32_t crc) {
@@ -430,7 +431,12 @@ protected:
         if (flg & 4) { if (short_of(2)) return fail("unexpected end of the gzip stream"); const size_t xlen = p[0] | (size_t)p[1] << 8; p += 2; if (short_of(xlen)) return fail("unexpected end of the gzip stream"); p += xlen; }
         for (int bit = 8; bit <= 16; bit <<= 1)
             if (flg & bit) { while (p < in_end_ && *p) p++; if (p >= in_end_) return fail("unexpected end of the gzip stream"); p++; }
-        if (flg & 2) { if (short_of(2)) return fail("unexpected end of the gzip stream"); p += 2; }
+        if (flg & 2) {                                                   // FHCRC: the low 16 bits of the CRC-32 of the header so far (RFC 1952)
+            if (short_of(2)) return fail("unexpected end of the gzip stream");
+            const uint32_t want = p[0] | (uint32_t)p[1] << 8;
+            if ((crc32_update(0, in_next_, (size_t)(p - in_next_)) & 0xFFFFu) != want) return fail("gzip header CRC mismatch");
+            p += 2;
+        }
         in_next_ = p;
         crc_ = 0; isize_ = 0; hist_ = 0;
         members_++;

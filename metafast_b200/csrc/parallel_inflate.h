@@ -486,16 +486,18 @@ private:
                 // wait for one of them to do so -- it will start a parallel run there, which is the whole point; walking
                 // over it would turn this run into a serial decode of the rest of the file.  Outside the window it is mine.
                 std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return stop_ || seg_state_[s].load() != SEG_FREE || s > consumed_seg_ + lookahead_; });
-                if (stop_) return 1;
+                // (a run its predecessor has already thrown away must not park here holding its worker: if every worker waits
+                // on FREE segments nobody is left to take them)
+                cv_.wait(lk, [&] { return stop_ || run.discarded || seg_state_[s].load() != SEG_FREE || s > consumed_seg_ + lookahead_; });
+                if (stop_ || run.discarded) return 1;
                 int expect = SEG_FREE;
                 if (seg_state_[s].compare_exchange_strong(expect, SEG_NONE)) { run.settled = s; continue; }
                 st = seg_state_[s].load();
             }
             if (st == SEG_PROBING) {                               // its prober may still find a start behind, at or in front of me
                 std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return stop_ || seg_state_[s].load() != SEG_PROBING; });
-                if (stop_) return 1;
+                cv_.wait(lk, [&] { return stop_ || run.discarded || seg_state_[s].load() != SEG_PROBING; });
+                if (stop_ || run.discarded) return 1;
                 st = seg_state_[s].load();
             }
             if (st == SEG_NONE) { run.settled = s; continue; }
