@@ -985,14 +985,15 @@ __device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32
 __host__ __device__ __forceinline__ uint32_t coarse_of_minhash(uint32_t mh, int log2_buckets) {
     return log2_buckets ? region_hash(mh) >> (32 - log2_buckets) : 0u;              // monotone in the region index
 }
-// modes 3 / 4 (no table fallback inside the kernel) fit 80 registers: 3 CTAs per SM instead of 2 hide the cursor atomics
+// modes 3 / 4 (mask-based run loop, no table fallback inside the kernel) fit 64 registers: 4 CTAs per SM hide the cursor atomics
 template <int MODE, class Tab>
-__global__ void __launch_bounds__(EX_THREADS, (MODE >= 3 ? 3 : 2))
+__global__ void __launch_bounds__(EX_THREADS, (MODE >= 3 ? 4 : 2))
 extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const uint32_t *__restrict__ flags,
                    int k, SkmStage st, Tab tb, Counters *__restrict__ ctr,
                    unsigned long long *__restrict__ kmer_count) {
     __shared__ uint32_t s_words[EX_THREADS + 2];
     __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
+    __shared__ uint32_t s_rkey[(MODE == 3 || MODE == 4) ? 16 : 1][EX_THREADS];      // bin ids of the 16 start positions of every thread
     const uint32_t tid = threadIdx.x;
     const uint64_t n_tiles = (((n_bases + 15) >> 4) + EX_THREADS - 1) / EX_THREADS;
     uint32_t claimed = 0, bad = 0, dropped = 0;
@@ -1015,9 +1016,60 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                 const uint32_t lim_mask = limit >= 15 ? 0xFFFFu : (limit < 0 ? 0u : ((2u << (int)limit) - 1u));
                 valid = ~(uint32_t)inv & lim_mask;
             }
-            if (valid) {
+            if (valid && (MODE == 3 || MODE == 4)) {
+                // Bin staging.  The runs of a thread (consecutive valid k-mers of one bin; 2.5 per thread on average, 16
+                // at most) are found with bit masks and walked in a loop: the bin ids wait in shared memory (a register
+                // array cannot be indexed by the run's start), the cursor atomic of the NEXT run is in flight while
+                // the record of the current one is built and stored.  (The fully unrolled two-pass state machine
+                // below spent half of the kernel's instructions on its 2 x 17 predicated steps.)
                 uint32_t mh[16];
-                minhash_of_word(w0, w1, w2, k, (MODE == 3 || MODE == 4) ? st.mlen : minimizer_len(k), mh);
+                minhash_of_word(w0, w1, w2, k, st.mlen, mh);
+                uint32_t eq = 0, prev_key = 0;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    // MODE 4: owner in the top byte (<= 16 shards), bin of the shard below (< 2^24)
+                    const uint32_t key = MODE == 4 ? ((owner_of_minhash(mh[j], st.n_regions) << 24) | region_of_minhash(mh[j], st.win))
+                                                   : region_of_minhash(mh[j], st.n_regions);
+                    s_rkey[j][tid] = key;
+                    if (j && key == prev_key) eq |= 1u << j;
+                    prev_key = key;
+                }
+                const uint32_t starts = valid & ~((valid << 1) & eq);       // valid, and not the continuation of the k-mer before
+                const uint32_t stops = (~valid | starts) | (1u << 16);       // a run ends in front of the next start / invalid position
+                const uint32_t seg32 = (uint32_t)st.seg_cap;
+                uint32_t left = starts;
+                uint32_t s_nx = __ffs(left) - 1, key_nx = s_rkey[s_nx][tid];
+                uint32_t bucket_nx = MODE == 4 ? (key_nx >> 24) * st.win + (key_nx & 0xFFFFFFu) : key_nx;
+                uint32_t pos_nx = atomicAdd(&st.cursor[bucket_nx], 1u);
+                while (left) {
+                    const uint32_t sj = s_nx, key = key_nx, bucket = bucket_nx, p = pos_nx;
+                    left &= left - 1;
+                    if (left) {
+                        s_nx = __ffs(left) - 1; key_nx = s_rkey[s_nx][tid];
+                        bucket_nx = MODE == 4 ? (key_nx >> 24) * st.win + (key_nx & 0xFFFFFFu) : key_nx;
+                        pos_nx = atomicAdd(&st.cursor[bucket_nx], 1u);
+                    }
+                    const uint32_t len = (uint32_t)__ffs(stops & ~((2u << sj) - 1u)) - 1u - sj;
+                    const uint32_t sh = 2u * sj;                          // normalise: first base of the run -> base 0
+                    uint4 rec;
+                    rec.x = __funnelshift_l(w1, w0, sh);
+                    rec.y = __funnelshift_l(w2, w1, sh);
+                    rec.z = ((w2 << sh) & ~15u) | (len - 1u);
+                    rec.w = key;
+                    if (p < seg32) st.recs[(uint64_t)bucket * seg32 + p] = rec;
+                    else {                                               // segment full: overflow list (filed into the chunk pool before the count)
+                        const uint32_t o = atomicAdd(st.ovf_used, 1u);
+                        if (o < st.ovf_cap) { st.ovf[o] = rec; st.ovf_meta[o] = make_uint2(bucket, p - seg32); } else dropped++;
+                    }
+                    if (MODE == 4) {                                     // k-mers per owner (counted even if dropped: mfkc_flush reports the drop)
+                        const uint32_t ow = key >> 24;
+                        if (st.n_regions <= 8) { if (ow < 4) km_lo += (unsigned long long)len << (16 * ow); else km_hi += (unsigned long long)len << (16 * (ow - 4)); }
+                        else atomicAdd(&kmer_count[ow], (unsigned long long)len);
+                    }
+                }
+            } else if (valid) {
+                uint32_t mh[16];
+                minhash_of_word(w0, w1, w2, k, minimizer_len(k), mh);
                 // Cut into runs of consecutive valid k-mers (fully unrolled: every register array keeps
                 // compile-time indices).  Local staging: a run = same table REGION.  Send buffer
                 // (BY_OWNER): a run = same MINIMIZER HASH, because the receiver derives the region of

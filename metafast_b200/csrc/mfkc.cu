@@ -1164,11 +1164,14 @@ static int bins_count(mfkc_ctx *ctx, uint32_t thr) {
             bin_count_kernel<BC_LOG2S, BC_THREADS><<<grid, BC_THREADS, bin_count_smem_bytes<BC_LOG2S, BC_THREADS>(), st>>>(a);
         }
         CU_TRY(cudaGetLastError());
+        // one read-back for the common case (no heavy bins): control block, histogram and counters together
         CU_TRY(cudaMemcpyAsync(ctx->h_binctl, ctx->d_binctl, sizeof(BinCtl), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, MFKC_HIST_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
         const BinCtl c = *ctx->h_binctl;
-        uint64_t n_ovf = 0;
-        TRY(overflow_records(ctx, &n_ovf));
+        uint64_t n_ovf = std::min<uint64_t>(c.ovf_cursor, ctx->os_ovf_cap);
+        if (ctx->p2p_bins) TRY(overflow_records(ctx, &n_ovf));
         ctx->os_heavy_bins = c.n_heavy; ctx->os_heavy_recs = c.heavy_recs; ctx->os_splits = c.n_split; ctx->os_ovf = n_ovf; ctx->os_total_recs = c.total_recs;
         if (c.heavy_overflow) {                                  // more heavy entries than the list holds: the table takes the sample
             TMP_FREE(ok); TMP_FREE(oc);
@@ -1187,10 +1190,10 @@ static int bins_count(mfkc_ctx *ctx, uint32_t thr) {
                     ctx->tab, TabSoA{nullptr, nullptr, 0}, ctx->cap, a.thr, ctx->d_hist, ok, oc, out_cap, ctx->d_ctr);
             }
             CU_TRY(cudaGetLastError());
+            CU_TRY(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, MFKC_HIST_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
         }
-        CU_TRY(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, MFKC_HIST_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        CU_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-        CU_TRY(cudaStreamSynchronize(st));
         good = ctx->h_ctr->n_good;
         if (good <= out_cap || !want_out) { ctx->os_keys = ok; ctx->os_counts = oc; break; }
         TMP_FREE(ok); TMP_FREE(oc);
@@ -1358,8 +1361,8 @@ extern "C" int mfkc_flush(mfkc_ctx *ctx) {
     if (!ctx) return MFKC_E_BADARG;
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(drain_regions(ctx));
+    CU_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->compute));     // rides on the synchronisation below
     TRY(sync_all(ctx));
-    TRY(read_counters(ctx));
     if (ctx->cfg.variant != MFKC_VARIANT_SORT) {
         ctx->distinct_ub = ctx->distinct_base = ctx->h_ctr->distinct;
         ctx->kmers_base = ctx->h_ctr->kmers; ctx->recv_since_base = 0;
@@ -1390,22 +1393,22 @@ static int radix_sort(mfkc_ctx *ctx, cudaStream_t st, unsigned long long *&a, un
     int rc = MFKC_OK;
     ProfScope ps(ctx, P_SORT, st);
     ctx->prof_launches[P_SORT]--;            // counted per kernel below
+    // No host round trip inside the loop: every pass is queued back to back (a pass whose digit is the same for all keys
+    // still runs -- it copies in order -- instead of being detected with a read-back and skipped; the number of passes is
+    // bounded by key_bits anyway).  A synchronisation per pass cost little on a quiet host and ~1 ms each on a busy one.
     for (int shift = 0; shift < key_bits; shift += 8) {
         rs_hist_kernel<<<grid, RS_THREADS, 0, st>>>(a, n, shift, plan.n_parts, hist);
         rs_chunk_kernel<<<plan.n_chunks, RS_RADIX, 0, st>>>(hist, plan.n_parts, chunk);
         rs_base_kernel<<<1, RS_RADIX, 0, st>>>(chunk, plan.n_chunks, n, d_triv);
-        uint32_t triv = 0;
-        if (cudaMemcpyAsync(&triv, d_triv, sizeof triv, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaStreamSynchronize(st) != cudaSuccess) { rc = MFKC_E_CUDA; break; }
-        ctx->prof_launches[P_SORT] += triv ? 3 : 5;
-        if (triv) continue;                                   // every key has the same digit: order unchanged
         rs_offsets_kernel<<<plan.n_chunks, RS_RADIX, 0, st>>>(hist, plan.n_parts, chunk, offs);
         rs_scatter_kernel<V, HAS_V><<<grid, RS_THREADS, smem, st>>>(a, va, n, shift, plan.n_parts, offs, b, vb);
+        ctx->prof_launches[P_SORT] += 5;
         std::swap(a, b);
         std::swap(va, vb);
     }
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    // the workspace goes back to the pool in stream order: frees are queued on the compute stream behind the sort
+    if (e == cudaSuccess && stream_after(ctx, ctx->compute, st) != MFKC_OK) e = cudaErrorUnknown;
     TMP_FREE(hist); TMP_FREE(offs); TMP_FREE(chunk); TMP_FREE(d_triv);
     if (e != cudaSuccess) { ctx->err = std::string("radix sort: ") + cudaGetErrorString(e); return MFKC_E_CUDA; }
     return rc;
