@@ -516,18 +516,35 @@ int tool_features(const Args &a) {
     if (n_comp == 0) die("No components were found in input files! Can't continue the calculations.");
     const std::string out_dir = work + "/vectors";
     mkdirs(out_dir);
-    mfkc_ctx *ctx = make_ctx(k, g, 0);
+    // --gpus G (records inputs, threshold >= 0): every GPU holds the component set and takes a share of each file's records.
+    // A k-mer occurs once per .kmers.bin file, so every key's value lives on exactly one GPU and is 0 on the others:
+    // `vec` and `found` add up over the GPUs (0 > threshold is false for threshold >= 0), `cnt` is the same on all.
+    // Reads inputs (-i) accumulate instances of the same k-mer and stay on one GPU.
+    const bool logical = getenv("MFKC_LOGICAL_GPUS") != nullptr;
+    const int G = (g.n_gpus > 1 && threshold >= 0) ? g.n_gpus : 1;
+    std::vector<mfkc_ctx *> ctxs;
+    for (int d = 0; d < G; d++) { Gpu gd = g; gd.device = logical ? g.device : g.device + d; ctxs.push_back(make_ctx(k, gd, 0)); }
+    mfkc_ctx *ctx = ctxs[0];
     if (keys.empty()) keys.push_back(0);
-    CK(ctx, mfkc_fc_load_components(ctx, keys.data(), off.data(), n_comp));
+    for (auto *c : ctxs) CK(c, mfkc_fc_load_components(c, keys.data(), off.data(), n_comp));
     const auto sel_files = a.many("selected");
     if (!sel_files.empty()) {
         static const uint8_t none = 0;
-        CK(ctx, mfkc_fc_set_selected(ctx, &none, 0));                       // an (initially empty) active filter
-        for (const auto &sf : sel_files) { info("Loading file %s...", base_name(sf).c_str()); auto b = slurp(sf); if (!b.empty()) CK(ctx, mfkc_fc_set_selected(ctx, b.data(), b.size() / 10)); }
+        for (auto *c : ctxs) CK(c, mfkc_fc_set_selected(c, &none, 0));      // an (initially empty) active filter
+        for (const auto &sf : sel_files) {
+            info("Loading file %s...", base_name(sf).c_str());
+            auto b = slurp(sf);
+            if (!b.empty()) for (auto *c : ctxs) CK(c, mfkc_fc_set_selected(c, b.data(), b.size() / 10));
+        }
     }
-    std::vector<int64_t> vec(n_comp); std::vector<uint64_t> found(n_comp), cnt(n_comp);
+    std::vector<int64_t> vec(n_comp), vec_g(n_comp); std::vector<uint64_t> found(n_comp), cnt(n_comp), found_g(n_comp), cnt_g(n_comp);
+    size_t active = 1;                                                       // contexts that took part in the current input
     auto print_vectors = [&](const std::string &stem, const std::string &shown) {
         CK(ctx, mfkc_fc_features(ctx, threshold, vec.data(), found.data(), cnt.data()));
+        for (size_t d = 1; d < active; d++) {
+            CK(ctxs[d], mfkc_fc_features(ctxs[d], threshold, vec_g.data(), found_g.data(), cnt_g.data()));
+            for (uint32_t i = 0; i < n_comp; i++) { vec[i] = (int64_t)((uint64_t)vec[i] + (uint64_t)vec_g[i]); found[i] += found_g[i]; }
+        }
         const std::string vf = out_dir + "/" + stem + ".vec", bf = out_dir + "/" + stem + ".breadth";
         FILE *f = fopen(vf.c_str(), "w"); if (!f) die("Can't write vector to file %s", vf.c_str());
         for (uint32_t i = 0; i < n_comp; i++) fprintf(f, "%lld\n", (long long)vec[i]);
@@ -540,24 +557,29 @@ int tool_features(const Args &a) {
         OUT_VALUE("%s\n", vf.c_str());                                     // "features-files"
     };
     for (const auto &rf : a.many("reads")) {                               // :120-134
+        active = 1;
         CK(ctx, mfkc_fc_reset_values(ctx));
         for_each_batch(ctx, rf, [&](const uint8_t *bases, const uint64_t *offs, uint32_t n) { CK(ctx, mfkc_fc_add_reads(ctx, bases, offs, n)); });
         print_vectors(reader_name(rf), base_name(rf));
     }
     for (const auto &kf : a.many("kmers")) {                               // :136-163
-        CK(ctx, mfkc_fc_reset_values(ctx));
+        active = ctxs.size();
+        for (auto *c : ctxs) CK(c, mfkc_fc_reset_values(c));
         info("Loading file %s...", base_name(kf).c_str());
         const auto recs = slurp(kf);
-        const size_t chunk = 16777200;                                      // src/io/IOUtils.java:30
-        for (size_t p = 0; p < recs.size(); p += chunk) {
+        size_t chunk = 16777200;                                            // src/io/IOUtils.java:30
+        if (ctxs.size() > 1) chunk = std::max<size_t>(10, std::min<size_t>(chunk, (recs.size() / 10 + ctxs.size() - 1) / ctxs.size() * 10));   // an even share per GPU
+        size_t turn = 0;
+        for (size_t p = 0; p < recs.size(); p += chunk, turn++) {           // the chunks go round the GPUs
             const size_t nbytes = std::min(chunk, recs.size() - p);
-            CK(ctx, mfkc_fc_add_records(ctx, recs.data() + p, nbytes / 10));
+            mfkc_ctx *c = ctxs[turn % ctxs.size()];
+            CK(c, mfkc_fc_add_records(c, recs.data() + p, nbytes / 10));
         }
         std::string stem = base_name(kf);
         if (ends_with_ci(stem, ".kmers.bin")) stem.resize(stem.size() - 10);
         print_vectors(stem, base_name(kf));
     }
-    mfkc_destroy(ctx);
+    for (auto *c : ctxs) mfkc_destroy(c);
     return 0;
 }
 

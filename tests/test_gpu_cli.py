@@ -130,6 +130,39 @@ def test_features_calculator_cli(built, tmp_path):
     assert open(fw2 / "vectors" / "meta_test_2.breadth").read() == orc.breadth_text(breadth)
 
 
+@pytest.mark.parametrize("gpus", [2, 8])
+def test_features_calculator_multi_gpu(built, tmp_path, gpus):
+    """features-calculator --gpus G on records inputs: the component set on every (logical) GPU, every file's records
+    shared out between them, per-component sums added up -- .vec / .breadth byte-equal to the oracle's (= one GPU's)."""
+    rng = np.random.default_rng(23)
+    files = [os.path.join(INPUTS, "meta_test_%d.fa" % n) for n in (1, 2, 3)]
+    per_sample = orc.kmer_counter_many(files, 31, 1)
+    kdir = tmp_path / "kmers"
+    kdir.mkdir()
+    for name, (rec, stat, counts) in per_sample.items():
+        (kdir / (name + ".kmers.bin")).write_bytes(rec)
+    all_keys = sorted(set().union(*[set(c) for _, _, c in per_sample.values()]))
+    comps = [(int(rng.integers(0, 1000)), [all_keys[int(i)] for i in rng.integers(0, len(all_keys), int(rng.integers(1, 600)))]) for _ in range(80)]
+    comps.append((0, []))
+    cm = tmp_path / "components.bin"
+    cm.write_bytes(orc.save_components(comps))
+    kfiles = [str(kdir / ("meta_test_%d.kmers.bin" % n)) for n in (1, 2, 3)]
+    env = dict(os.environ, MFKC_LOGICAL_GPUS="1")
+    for thr, sel in ((0, None), (2, kfiles[1])):
+        fw = tmp_path / ("fw%d" % thr)
+        cmd = [CLI, "-t", "features-calculator", "-k", "31", "-cm", str(cm), "-ka", *kfiles, "-w", str(fw), "--gpus", str(gpus), "--threshold", str(thr)]
+        if sel:
+            cmd += ["--selected", sel]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        selected = orc.load_kmers([per_sample["meta_test_2"][0]], 0) if sel else None
+        for n in (1, 2, 3):
+            acc = orc.presence_for_kmers([k for _, c in comps for k in c], orc.load_kmers_bin(per_sample["meta_test_%d" % n][0]))
+            vec, breadth, _, _ = orc.features(comps, acc, thr, selected)
+            assert open(fw / "vectors" / ("meta_test_%d.vec" % n)).read() == orc.vec_text(vec)
+            assert open(fw / "vectors" / ("meta_test_%d.breadth" % n)).read() == orc.breadth_text(breadth)
+
+
 def test_set_algebra_tools_cli(built, tmp_path):
     """kmers-filter, unique-kmers-multi, kmers-samples-counter on the .kmers.bin files the counter wrote:
     same options, default locations, output names and log lines as the reference tools."""

@@ -8,7 +8,8 @@ import metafast_b200 as m
 K, B, L = 31, 2, 150
 N = int(os.environ.get("MFKC_BENCH_READS", 20_000_000)); BATCH = int(os.environ.get("MFKC_BENCH_BATCH", 1_000_000))
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 6
-kcs = [m.KmerCounter(K, expected_kmers=N * (L - K + 1)) for _ in range(2)]
+LANES = int(os.environ.get('TL_LANES', 3))
+kcs = [m.KmerCounter(K, expected_kmers=N * (L - K + 1)) for _ in range(LANES)]
 kc = kcs[0]
 d_b = kc.device_alloc(N * L); d_o = kc.device_alloc((N + 1) * 8)
 kept = C.c_uint64(); cfg = m.synth_cfg()
@@ -66,8 +67,8 @@ def run(nsteps, use_lock=True, lanes=2):
     [t.start() for t in ts]; [t.join() for t in ts]
     return 1e3 * (time.perf_counter() - t0) / nsteps
 
-run(4)
-for name, kw in (("serial (1 context)", dict(lanes=1)), ("pipelined, link lock", dict())):
+run(2 * LANES, lanes=LANES)
+for name, kw in (("serial (1 context)", dict(lanes=1)), ("pipelined, link lock", dict(lanes=LANES))):
     del log[:]
     ms = run(steps, **kw)
     print("%s: %.1f ms per sample" % (name, ms))
