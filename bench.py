@@ -682,17 +682,18 @@ def main():
     kc.d2h(h_offs, d_offs)
     h_out = kc.pinned(max(int(n_good * 1.05) + 1024, 1024) * 10)
 
-    def step_e2e(c=None, out=None, lock=None):
+    def step_e2e(c=None, out=None, lock=None, shd=None):
         c = c or kc
         out = h_out if out is None else out
+        shd = shd or (sharded if world > 1 else None)
+        if world > 1 and exchange == "p2p":
+            shd.begin()                      # (a barrier between the ranks: outside the link lock, other lanes keep submitting)
         if lock:
             lock.acquire()                   # one sample at a time on the host-to-device link
         try:
             c.reset()
             if world > 1:
-                if exchange == "p2p":
-                    sharded.begin()
-                sharded.run_host(h_bases, h_offs, n_reads)
+                shd.run_host(h_bases, h_offs, n_reads)
             else:
                 for s in range(0, n_reads, BATCH_READS):
                     e = min(n_reads, s + BATCH_READS)
@@ -708,11 +709,21 @@ def main():
     # N = 1: the samples of a kmer-counter-many run are independent, so a few contexts take them in turn (what mfkc_cli does
     # in batch mode): while one sample is counted, sorted and copied back, the next one's reads are already crossing PCIe.
     # Every step still does the whole job through the C ABI: reads host -> device, records + histogram device -> host.
-    pipelined = world == 1 and not os.environ.get("MFKC_BENCH_E2E_SERIAL")
+    # N > 1: the same with one sharded group of contexts per lane; the lanes' tiny exchanges (G numbers, barriers) run on CPU
+    # process groups of their own, so that lanes of different ranks may be at different points.
+    pipelined = not os.environ.get("MFKC_BENCH_E2E_SERIAL") and (world == 1 or (exchange == "p2p" and variant == m.VARIANT_HASH))
     if pipelined:
         n_lanes = max(2, int(os.environ.get("MFKC_BENCH_E2E_LANES", 3)))
-        extra = [m.KmerCounter(K, device=local_rank, variant=variant, expected_kmers=kmers_ub) for _ in range(n_lanes - 1)]
-        lanes = [(kc, h_out)] + [(c, c.pinned(h_out.nbytes)) for c in extra]
+        extra = [m.KmerCounter(K, device=local_rank, variant=variant, expected_kmers=kmers_ub,
+                               n_shards=world if world > 1 else 0, shard_id=rank if world > 1 else 0) for _ in range(n_lanes - 1)]
+        lanes = [(kc, h_out, sharded if world > 1 else None)]
+        if world > 1:
+            sharded.group = dist.new_group(backend="gloo")
+        for c in extra:
+            shd = None
+            if world > 1:
+                shd = P2PShardedStep(c, dist, world, rank, BATCH_READS, READ_LEN, K, N_READS, group=dist.new_group(backend="gloo"))
+            lanes.append((c, c.pinned(h_out.nbytes), shd))
         link = threading.Lock()
 
         def run_pipelined(n_steps):
@@ -720,7 +731,7 @@ def main():
 
             def lane(j):
                 for i in range(j, n_steps, n_lanes):
-                    res[i] = step_e2e(lanes[j][0], lanes[j][1], link)
+                    res[i] = step_e2e(lanes[j][0], lanes[j][1], link, lanes[j][2])
             ts = [threading.Thread(target=lane, args=(j,)) for j in range(n_lanes)]
             for t in ts:
                 t.start()
@@ -735,9 +746,13 @@ def main():
         for c in extra:
             c.sync()
         barrier()
-        e2e_s = time.perf_counter() - t0
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
         for c in extra:
             c.close()
+        barrier()
+        if world > 1:
+            sharded.group = None
     else:
         for _ in range(2):                       # the first host-fed samples size the staging / table of the context
             step_e2e()

@@ -108,8 +108,10 @@ rs_offsets_kernel(const uint32_t *__restrict__ hist, uint32_t n_tiles, const uns
     }
 }
 
-template <typename V, bool HAS_V>
-__global__ void __launch_bounds__(RS_THREADS)
+// MINB = CTAs per SM the kernel is compiled for: 2 (128 registers, no spills) or 3 (80 registers, a few spilled values):
+// the kernel is latency-bound (ncu: 23 % issue utilisation at 25 % occupancy), see radix_sort() for which one is used
+template <typename V, bool HAS_V, int MINB>
+__global__ void __launch_bounds__(RS_THREADS, MINB)
 rs_scatter_kernel(const unsigned long long *__restrict__ keys_in, const V *__restrict__ vals_in, uint64_t n, int shift,
                   uint32_t n_tiles, const unsigned long long *__restrict__ offs,
                   unsigned long long *__restrict__ keys_out, V *__restrict__ vals_out) {

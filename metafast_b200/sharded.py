@@ -82,18 +82,20 @@ def merge_sorted_records(parts: Sequence[bytes], record_size: int = 10, threads:
     return out[: int(n.sum()) * record_size].tobytes()
 
 
-def exchange_table(dist, rows: Sequence[Sequence[int]], device=None):
-    """all-to-all of one small int64 row per destination -> one row per source."""
+def exchange_table(dist, rows: Sequence[Sequence[int]], device=None, group=None):
+    """all-to-all of one small int64 row per destination -> one row per source.  `group`: a process group of its own
+    (CPU / gloo) when several sample lanes of one rank exchange concurrently from different threads."""
     import torch
     world = dist.get_world_size()
     width = len(rows[0])
-    send = torch.tensor([list(r) for r in rows], dtype=torch.int64, device=device).reshape(world, width)
-    if dist.get_backend() == "nccl":
+    if group is None and dist.get_backend() == "nccl":
+        send = torch.tensor([list(r) for r in rows], dtype=torch.int64, device=device).reshape(world, width)
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv, send)
         return [[int(x) for x in row] for row in recv.tolist()]
+    send = torch.tensor([list(r) for r in rows], dtype=torch.int64).reshape(world, width)
     gathered = [torch.empty(world, width, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(gathered, send.cpu())
+    dist.all_gather(gathered, send, group=group)
     me = dist.get_rank()
     return [[int(x) for x in gathered[src][me].tolist()] for src in range(world)]
 
@@ -216,9 +218,10 @@ class P2PShardedStep:
     (mfkc_p2p_drain -> drain_p2p_kernel).  torch.distributed only moves the 128-byte IPC handles and the
     per-owner totals."""
 
-    def __init__(self, kc, dist, world: int, rank: int, batch_reads: int, read_len: int, k: int, reads_per_rank: int):
+    def __init__(self, kc, dist, world: int, rank: int, batch_reads: int, read_len: int, k: int, reads_per_rank: int, group=None):
         import torch
         self.kc, self.dist, self.world, self.rank, self.torch = kc, dist, world, rank, torch
+        self.group = group                 # a CPU process group of this lane's own (several lanes per rank run from threads)
         self.batch_reads, self.read_len, self.k = batch_reads, read_len, k
         kmers = reads_per_rank * (read_len - k + 1)
         from . import _abi
@@ -240,13 +243,14 @@ class P2PShardedStep:
     def begin(self):
         """call after kc.reset(): every rank has finished draining the previous sample before any staging buffer
         is cleared"""
-        self.dist.barrier()
+        self.dist.barrier(group=self.group) if self.group is not None else self.dist.barrier()
         self.kc.p2p_stage_reset()
 
     def _finish(self):
         kc, world = self.kc, self.world
         counts = kc.p2p_counts(world)                                        # synchronises this rank's extraction
-        rows = exchange_table(self.dist, [[counts[d]] for d in range(world)], device="cuda" if self.dist.get_backend() == "nccl" else None)
+        rows = exchange_table(self.dist, [[counts[d]] for d in range(world)], device="cuda" if self.dist.get_backend() == "nccl" else None,
+                              group=self.group)
         kc.p2p_drain(sum(r[0] for r in rows))
 
     def run_device(self, d_bases: int, d_offs: int, n_reads: int):
