@@ -69,49 +69,83 @@ def load_traffic():
 
 # ------------------------------------------------------------------ clocks under load
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  NVML from a thread of this process (a handful of light
+    queries every 50 ms); falls back to an `nvidia-smi -lms` child, whose full queries can stall kernel launches for
+    milliseconds on a busy host."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.samples = []
+        self.samples = []          # (sm_mhz, max_mhz, [reasons])
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._run_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "250"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t = threading.Thread(target=self._run_smi, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _run(self):
+    def _run_nvml(self):
+        n = self.nvml
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+        masks = [(nm, getattr(n, a, None) or getattr(n, b, 0)) for nm, a, b in names]
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+                r = get_reasons(self.h)
+                self.samples.append((float(sm), float(self.max), [nm for nm, m_ in masks if m_ and (r & m_)]))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def _run_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
             if len(f) >= 7:
-                self.samples.append(f)
+                try:
+                    self.samples.append((float(f[0]), float(f[1]), [n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
+                except ValueError:
+                    pass
 
     def stop(self):
-        if not self.proc:
+        if self.nvml is None and not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for f in self.samples:
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.t.join(timeout=1)
+        sm = sorted(x[0] for x in self.samples)
+        reasons = set(r for x in self.samples for r in x[2])
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((x[1] for x in self.samples), default=None),
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------ reference arm (CPU)
@@ -619,9 +653,13 @@ def main():
         else:
             sharded = ShardedStep(kc, dist, world, rank, BATCH_READS, READ_LEN, K)
 
+    phases = {"reset": 0.0, "submit": 0.0, "flush": 0.0, "emit_begin": 0.0}       # host wall time per phase (where a slow host shows)
+
     def step_device():
         """one whole pass, inputs resident in HBM"""
+        t0 = time.perf_counter()
         kc.reset()
+        t1 = time.perf_counter()
         if world > 1:
             if exchange == "p2p":
                 sharded.begin()
@@ -630,8 +668,13 @@ def main():
             for s in range(0, n_reads, BATCH_READS):
                 e = min(n_reads, s + BATCH_READS)
                 kc.submit_device(d_bases + s * READ_LEN, d_offs + s * 8, e - s, (e - s) * READ_LEN)
+        t2 = time.perf_counter()
         kc.flush()
-        return kc.emit_begin(B_THRESHOLD)
+        t3 = time.perf_counter()
+        n = kc.emit_begin(B_THRESHOLD)
+        t4 = time.perf_counter()
+        phases["reset"] += t1 - t0; phases["submit"] += t2 - t1; phases["flush"] += t3 - t2; phases["emit_begin"] += t4 - t3
+        return n
 
     def barrier():
         kc.sync()
@@ -662,6 +705,8 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     kc.profile(enable=True, reset=True)
+    for k_ in phases:
+        phases[k_] = 0.0
     kc.timer_start()
     t_wall = time.perf_counter()
     for _ in range(args.steps):
@@ -836,7 +881,8 @@ def main():
         "verified": verified,
         "host_ingest": ingest,
         "result": {"kmers_per_step_per_gpu": kmers_per_step, "distinct": st["distinct"], "records_gt_b": int(n_good), "bins": kc.bin_stats(),
-                   "host_wall_ms_per_step": 1e3 * wall / args.steps},
+                   "host_wall_ms_per_step": 1e3 * wall / args.steps,
+                   "host_phase_ms_per_step": {k_: 1e3 * v / args.steps for k_, v in phases.items()}},
     }
     print(json.dumps(line))
     kc.close()

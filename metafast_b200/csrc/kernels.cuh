@@ -931,14 +931,15 @@ __device__ __forceinline__ void window_mins_static(const uint32_t (&h)[36], uint
     }
 }
 
-__device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32_t w2, int k, int m, uint32_t (&mh)[16]) {
-    const int w = k - m + 1;                              // m-mers per k-mer, <= 20
+// hashes of the canonical m-mers at base offsets q0 .. q0 + N - 1 of the window (w0, w1, w2): forward m-mer by funnel shift,
+// reverse complement seeded once and rolled
+template <int N>
+__device__ __forceinline__ void mmer_hashes(uint32_t w0, uint32_t w1, uint32_t w2, int m, uint32_t (&h)[N]) {
     const int rs = 32 - 2 * m;
     const int top = 2 * m - 2;
-    uint32_t h[36];                                       // m-mer hashes at base offsets 0..35
     uint32_t rc = 0;
 #pragma unroll
-    for (int q = 0; q < 36; q++) {
+    for (int q = 0; q < N; q++) {
         const uint32_t lo_w = q < 16 ? w0 : (q < 32 ? w1 : w2);
         const uint32_t hi_w = q < 16 ? w1 : (q < 32 ? w2 : 0u);
         const int sh = 2 * (q & 15);
@@ -953,8 +954,12 @@ __device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32
         }
         h[q] = mmer_hash(fw < rc ? fw : rc);
     }
+}
+
+// minimizer hash of the 16 k-mers starting at offsets 0..15, from the m-mer hashes at offsets 0..35 (w = k - m + 1 per k-mer)
+__device__ __forceinline__ void window_mins(const uint32_t (&h)[36], int w, uint32_t (&mh)[16]) {
     switch (w) {                                          // uniform branch
-        case 20: window_mins_static<20>(h, mh); return;   // k = 31
+        case 20: window_mins_static<20>(h, mh); return;   // k = 31, m = 12
         case 19: window_mins_static<19>(h, mh); return;
         case 18: window_mins_static<18>(h, mh); return;
         case 17: window_mins_static<17>(h, mh); return;
@@ -968,6 +973,12 @@ __device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32
         for (int q = 0; q < 15; q++) if (q < w) best = min(best, h[j + q]);
         mh[j] = best;
     }
+}
+
+__device__ __forceinline__ void minhash_of_word(uint32_t w0, uint32_t w1, uint32_t w2, int k, int m, uint32_t (&mh)[16]) {
+    uint32_t h[36];                                       // m-mer hashes at base offsets 0..35
+    mmer_hashes<36>(w0, w1, w2, m, h);
+    window_mins(h, k - m + 1, mh);
 }
 
 // MODE 0: bucket = table region of this GPU (single-GPU path, full segments fall back to direct upserts);
@@ -993,13 +1004,29 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                    unsigned long long *__restrict__ kmer_count) {
     __shared__ uint32_t s_words[EX_THREADS + 2];
     __shared__ uint32_t s_flags[EX_THREADS / 2 + 2];
-    __shared__ uint32_t s_rkey[(MODE == 3 || MODE == 4) ? 16 : 1][EX_THREADS];      // bin ids of the 16 start positions of every thread
+    __shared__ uint32_t s_rkey[(MODE == 3 || MODE == 4) ? 16 : 1][EX_THREADS];      // minimizer hashes of the 16 start positions of every thread
+    __shared__ uint32_t s_h[(MODE == 3 || MODE == 4) ? 16 : 1][EX_THREADS + 2];     // m-mer hashes of the tile: [offset in word][word]
     const uint32_t tid = threadIdx.x;
     const uint64_t n_tiles = (((n_bases + 15) >> 4) + EX_THREADS - 1) / EX_THREADS;
     uint32_t claimed = 0, bad = 0, dropped = 0;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const TileWord t = load_tile_word<EX_THREADS>(bases, n_bases, flags, tile, k, s_words, s_flags, bad);
+        uint32_t hq[16];
+        if constexpr (MODE == 3 || MODE == 4) {
+            // every thread hashes the 16 m-mers that start in ITS word (instead of all 35 its k-mers touch) and shares them
+            // through shared memory; threads 0 and 1 also do the two halo words of the tile
+            mmer_hashes<16>(t.w0, t.w1, 0u, st.mlen, hq);
+#pragma unroll
+            for (int q = 0; q < 16; q++) s_h[q][tid] = hq[q];
+            if (tid < 2) {
+                uint32_t hh[16];
+                mmer_hashes<16>(s_words[EX_THREADS + tid], tid == 0 ? s_words[EX_THREADS + 1] : 0u, 0u, st.mlen, hh);
+#pragma unroll
+                for (int q = 0; q < 16; q++) s_h[q][EX_THREADS + tid] = hh[q];
+            }
+            __syncthreads();
+        }
         unsigned long long km_lo = 0, km_hi = 0;                // MODE 2: k-mers per owner of this tile, 16-bit fields
         if (t.active) {
             const uint32_t w0 = t.w0, w1 = t.w1, w2 = t.w2;
@@ -1016,36 +1043,44 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                 const uint32_t lim_mask = limit >= 15 ? 0xFFFFu : (limit < 0 ? 0u : ((2u << (int)limit) - 1u));
                 valid = ~(uint32_t)inv & lim_mask;
             }
-            if (valid && (MODE == 3 || MODE == 4)) {
-                // Bin staging.  The runs of a thread (consecutive valid k-mers of one bin; 2.5 per thread on average, 16
-                // at most) are found with bit masks and walked in a loop: the bin ids wait in shared memory (a register
-                // array cannot be indexed by the run's start), the cursor atomic of the NEXT run is in flight while
-                // the record of the current one is built and stored.  (The fully unrolled two-pass state machine
-                // below spent half of the kernel's instructions on its 2 x 17 predicated steps.)
+            if constexpr (MODE == 3 || MODE == 4) { if (valid) {
+                // Bin staging.  The runs of a thread (consecutive valid k-mers of one minimizer; 2.5 per thread on average,
+                // 16 at most) are found with bit masks and walked in a loop: the minimizer hashes wait in shared memory (a
+                // register array cannot be indexed by the run's start), the bin is derived per RUN, the cursor atomic of the
+                // NEXT run is in flight while the record of the current one is built and stored.  (The fully unrolled
+                // two-pass state machine below spent half of the kernel's instructions on its 2 x 17 predicated steps.)
                 uint32_t mh[16];
-                minhash_of_word(w0, w1, w2, k, st.mlen, mh);
-                uint32_t eq = 0, prev_key = 0;
+                {
+                    // m-mer hashes 0..15 are this thread's own (computed for the whole tile above), 16..34 its neighbours'
+                    uint32_t h[36];
+#pragma unroll
+                    for (int q = 0; q < 16; q++) { h[q] = hq[q]; h[16 + q] = s_h[q][tid + 1]; }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) h[32 + q] = q < 3 ? s_h[q][tid + 2] : 0xFFFFFFFFu;
+                    window_mins(h, k - st.mlen + 1, mh);
+                }
+                uint32_t eq = 0;
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
-                    // MODE 4: owner in the top byte (<= 16 shards), bin of the shard below (< 2^24)
-                    const uint32_t key = MODE == 4 ? ((owner_of_minhash(mh[j], st.n_regions) << 24) | region_of_minhash(mh[j], st.win))
-                                                   : region_of_minhash(mh[j], st.n_regions);
-                    s_rkey[j][tid] = key;
-                    if (j && key == prev_key) eq |= 1u << j;
-                    prev_key = key;
+                    s_rkey[j][tid] = mh[j];
+                    if (j && mh[j] == mh[j - 1]) eq |= 1u << j;
                 }
+                // MODE 4: owner in the top byte (<= 16 shards), bin of the shard below (< 2^24)
+                auto key_of = [&](uint32_t mhv) {
+                    return MODE == 4 ? ((owner_of_minhash(mhv, st.n_regions) << 24) | region_of_minhash(mhv, st.win)) : region_of_minhash(mhv, st.n_regions);
+                };
                 const uint32_t starts = valid & ~((valid << 1) & eq);       // valid, and not the continuation of the k-mer before
                 const uint32_t stops = (~valid | starts) | (1u << 16);       // a run ends in front of the next start / invalid position
                 const uint32_t seg32 = (uint32_t)st.seg_cap;
                 uint32_t left = starts;
-                uint32_t s_nx = __ffs(left) - 1, key_nx = s_rkey[s_nx][tid];
+                uint32_t s_nx = __ffs(left) - 1, key_nx = key_of(s_rkey[s_nx][tid]);
                 uint32_t bucket_nx = MODE == 4 ? (key_nx >> 24) * st.win + (key_nx & 0xFFFFFFu) : key_nx;
                 uint32_t pos_nx = atomicAdd(&st.cursor[bucket_nx], 1u);
                 while (left) {
                     const uint32_t sj = s_nx, key = key_nx, bucket = bucket_nx, p = pos_nx;
                     left &= left - 1;
                     if (left) {
-                        s_nx = __ffs(left) - 1; key_nx = s_rkey[s_nx][tid];
+                        s_nx = __ffs(left) - 1; key_nx = key_of(s_rkey[s_nx][tid]);
                         bucket_nx = MODE == 4 ? (key_nx >> 24) * st.win + (key_nx & 0xFFFFFFu) : key_nx;
                         pos_nx = atomicAdd(&st.cursor[bucket_nx], 1u);
                     }
@@ -1067,7 +1102,7 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                         else atomicAdd(&kmer_count[ow], (unsigned long long)len);
                     }
                 }
-            } else if (valid) {
+            } } else if (valid) {
                 uint32_t mh[16];
                 minhash_of_word(w0, w1, w2, k, minimizer_len(k), mh);
                 // Cut into runs of consecutive valid k-mers (fully unrolled: every register array keeps

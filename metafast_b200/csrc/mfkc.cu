@@ -103,6 +103,7 @@ struct mfkc_ctx {
     uint64_t os_kmers_budget = 0, os_kmers_staged = 0;
     double os_R = 0, os_rpk = 0;       // previous sample: k-mer instances per distinct k-mer, records per k-mer instance
     double os_good_frac = 0;           // previous count: selected entries per distinct k-mer
+    double os_plan_kmers = 0, os_plan_R = 0;      // what the current bin geometry was planned for
     BinCtl *d_binctl = nullptr, *h_binctl = nullptr;
     HeavyEnt *d_heavy = nullptr; uint32_t heavy_cap = 0;
     bool os_counted = false; uint32_t os_thr = 0;             // results of the last count are valid for threshold os_thr
@@ -950,6 +951,17 @@ static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
     const double slack = env_slack > 0.0 ? env_slack : 1.5;          // what does not fit continues in the overflow pool, at no loss
     const double load = env_load > 0 ? env_load : 0.45;
     const double S = (double)(1u << BC_LOG2S);
+    // a sample that looks like the one the current geometry was planned for keeps it (kmer-counter-many over similar samples):
+    // no re-allocation, no churn from small changes of R
+    if (ctx->os_n_bins && !ctx->p2p_bins && ctx->rb_keys && ctx->os_plan_kmers > 0 && kmers <= ctx->os_plan_kmers * 1.05 && kmers >= ctx->os_plan_kmers * 0.8 &&
+        R <= ctx->os_plan_R * 1.2 && R >= ctx->os_plan_R * 0.8 && !getenv("MFKC_BIN_COUNT")) {
+        const OvfLayout o = ovf_layout(reinterpret_cast<uint4 *>(ctx->rb_keys) + (uint64_t)ctx->os_n_bins * ctx->os_seg_cap, ctx->os_ovf_cap);
+        CU_TRY(cudaMemsetAsync(o.tags, 0xFF, (size_t)o.n_chunks * sizeof(unsigned long long), ctx->compute));
+        ctx->os_kmers_budget = (uint64_t)(ctx->os_plan_kmers * 1.2);
+        ctx->os_kmers_staged = 0;
+        ctx->mode = 1;
+        return MFKC_OK;
+    }
     uint64_t n_bins = (uint64_t)(kmers / R / (load * S)) + 1;
     n_bins = std::min<uint64_t>(std::max<uint64_t>(n_bins, 16), (uint64_t)MAX_REGIONS_SKM);
     if (env_nbins > 0) n_bins = std::min<uint64_t>((uint64_t)env_nbins, (uint64_t)MAX_REGIONS_SKM);
@@ -963,11 +975,14 @@ static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
     if (env_ovf > 0) ovf_cap = (uint64_t)env_ovf;
     ovf_cap = (ovf_cap + 31) / 32 * 32;                                     // whole chunks of 32 records
     const uint64_t need_units = 2 * n_bins * seg_cap + ovf_bytes(ovf_cap) / 8 + 2;        // 8-byte units of rb_keys: segments + overflow area
-    size_t free_b = 0, total_b = 0;
-    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t have = ctx->rb_cap * 8;
-    if (need_units * 8 > (uint64_t)((double)total_b * 0.45) || (need_units * 8 > have && need_units * 8 - have > (uint64_t)((double)free_b * 0.9)))
-        return MFKC_OK;                                                     // too big to stage as a whole: region-blocked table
+    if (need_units > ctx->rb_cap) {
+        // (cudaMemGetInfo only when the buffer has to grow: the call takes 1-15 ms on a busy host, with the GPU idle behind it)
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t have = ctx->rb_cap * 8;
+        if (need_units * 8 > (uint64_t)((double)total_b * 0.45) || need_units * 8 - have > (uint64_t)((double)free_b * 0.9))
+            return MFKC_OK;                                                 // too big to stage as a whole: region-blocked table
+    }
     if (need_units > ctx->rb_cap) {
         TRY(sync_all(ctx));
         cudaFree(ctx->rb_keys); ctx->rb_keys = nullptr; ctx->rb_cap = 0;
@@ -981,6 +996,7 @@ static int plan_bins(mfkc_ctx *ctx, uint64_t first_batch_kmers) {
         CU_TRY(cudaMalloc(&ctx->d_heavy, (size_t)ctx->heavy_cap * sizeof(HeavyEnt)));
     }
     ctx->os_n_bins = (uint32_t)n_bins; ctx->os_seg_cap = seg_cap; ctx->os_ovf_cap = ovf_cap; ctx->os_mlen = mlen;
+    ctx->os_plan_kmers = kmers; ctx->os_plan_R = R;
     {   // no chunk of the overflow pool is taken
         const OvfLayout o = ovf_layout(reinterpret_cast<uint4 *>(ctx->rb_keys) + n_bins * seg_cap, ovf_cap);
         CU_TRY(cudaMemsetAsync(o.tags, 0xFF, (size_t)o.n_chunks * sizeof(unsigned long long), ctx->compute));
