@@ -1072,18 +1072,7 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                 const uint32_t starts = valid & ~((valid << 1) & eq);       // valid, and not the continuation of the k-mer before
                 const uint32_t stops = (~valid | starts) | (1u << 16);       // a run ends in front of the next start / invalid position
                 const uint32_t seg32 = (uint32_t)st.seg_cap;
-                uint32_t left = starts;
-                uint32_t s_nx = __ffs(left) - 1, key_nx = key_of(s_rkey[s_nx][tid]);
-                uint32_t bucket_nx = MODE == 4 ? (key_nx >> 24) * st.win + (key_nx & 0xFFFFFFu) : key_nx;
-                uint32_t pos_nx = atomicAdd(&st.cursor[bucket_nx], 1u);
-                while (left) {
-                    const uint32_t sj = s_nx, key = key_nx, bucket = bucket_nx, p = pos_nx;
-                    left &= left - 1;
-                    if (left) {
-                        s_nx = __ffs(left) - 1; key_nx = key_of(s_rkey[s_nx][tid]);
-                        bucket_nx = MODE == 4 ? (key_nx >> 24) * st.win + (key_nx & 0xFFFFFFu) : key_nx;
-                        pos_nx = atomicAdd(&st.cursor[bucket_nx], 1u);
-                    }
+                auto emit_run = [&](uint32_t sj, uint32_t key, uint32_t bucket, uint32_t p) {
                     const uint32_t len = (uint32_t)__ffs(stops & ~((2u << sj) - 1u)) - 1u - sj;
                     const uint32_t sh = 2u * sj;                          // normalise: first base of the run -> base 0
                     uint4 rec;
@@ -1101,6 +1090,37 @@ extract_skm_kernel(const uint8_t *__restrict__ bases, uint64_t n_bases, const ui
                         if (st.n_regions <= 8) { if (ow < 4) km_lo += (unsigned long long)len << (16 * ow); else km_hi += (unsigned long long)len << (16 * (ow - 4)); }
                         else atomicAdd(&kmer_count[ow], (unsigned long long)len);
                     }
+                };
+                // The first EX_RUNS runs of the thread (practically always all of them): every cursor atomic is issued before the
+                // first record is stored, so their ~1 us round trips overlap (ncu of the one-ahead loop: long scoreboard 9 of
+                // 20 stall cycles per issue).  Positions and keys stay in registers: the loops are unrolled and predicated.
+                constexpr int EX_RUNS = 6;
+                uint32_t left = starts;
+                uint32_t r_pos[EX_RUNS], r_key[EX_RUNS], r_sj[EX_RUNS];
+#pragma unroll
+                for (int r = 0; r < EX_RUNS; r++) {
+                    r_pos[r] = 0; r_key[r] = 0; r_sj[r] = 0xFFu;
+                    if (left) {
+                        const uint32_t sj = __ffs(left) - 1;
+                        left &= left - 1;
+                        const uint32_t key = key_of(s_rkey[sj][tid]);
+                        const uint32_t bucket = MODE == 4 ? (key >> 24) * st.win + (key & 0xFFFFFFu) : key;
+                        r_sj[r] = sj; r_key[r] = key;
+                        r_pos[r] = atomicAdd(&st.cursor[bucket], 1u);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < EX_RUNS; r++)
+                    if (r_sj[r] != 0xFFu) {
+                        const uint32_t key = r_key[r];
+                        emit_run(r_sj[r], key, MODE == 4 ? (key >> 24) * st.win + (key & 0xFFFFFFu) : key, r_pos[r]);
+                    }
+                while (left) {                                           // more than EX_RUNS runs in 16 positions: one by one
+                    const uint32_t sj = __ffs(left) - 1;
+                    left &= left - 1;
+                    const uint32_t key = key_of(s_rkey[sj][tid]);
+                    const uint32_t bucket = MODE == 4 ? (key >> 24) * st.win + (key & 0xFFFFFFu) : key;
+                    emit_run(sj, key, bucket, atomicAdd(&st.cursor[bucket], 1u));
                 }
             } } else if (valid) {
                 uint32_t mh[16];

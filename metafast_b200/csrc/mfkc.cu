@@ -1404,9 +1404,9 @@ static int radix_sort(mfkc_ctx *ctx, cudaStream_t st, unsigned long long *&a, un
     TMP_ALLOC(d_triv, sizeof(uint32_t));
     TRY(stream_after(ctx, st, ctx->compute));
     const size_t smem = rs_scatter_smem_bytes<V, HAS_V>();
-    static const int minb = getenv("MFKC_RS_MINB") ? atoi(getenv("MFKC_RS_MINB")) : 2;
+    static const int minb = getenv("MFKC_RS_MINB") ? atoi(getenv("MFKC_RS_MINB")) : 4;      // measured on cfg2: 9.8 ms (4) vs 11.3 ms (2) for 120 M records
     CU_TRY(cudaFuncSetAttribute(rs_scatter_kernel<V, HAS_V, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU_TRY(cudaFuncSetAttribute(rs_scatter_kernel<V, HAS_V, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaFuncSetAttribute(rs_scatter_kernel<V, HAS_V, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::min<uint64_t>(plan.n_parts, (uint64_t)ctx->sm_count * 8);
     int rc = MFKC_OK;
     ProfScope ps(ctx, P_SORT, st);
@@ -1419,7 +1419,7 @@ static int radix_sort(mfkc_ctx *ctx, cudaStream_t st, unsigned long long *&a, un
         rs_chunk_kernel<<<plan.n_chunks, RS_RADIX, 0, st>>>(hist, plan.n_parts, chunk);
         rs_base_kernel<<<1, RS_RADIX, 0, st>>>(chunk, plan.n_chunks, n, d_triv);
         rs_offsets_kernel<<<plan.n_chunks, RS_RADIX, 0, st>>>(hist, plan.n_parts, chunk, offs);
-        if (minb == 3) rs_scatter_kernel<V, HAS_V, 3><<<grid, RS_THREADS, smem, st>>>(a, va, n, shift, plan.n_parts, offs, b, vb);
+        if (minb == 4) rs_scatter_kernel<V, HAS_V, 4><<<grid, RS_THREADS, smem, st>>>(a, va, n, shift, plan.n_parts, offs, b, vb);
         else rs_scatter_kernel<V, HAS_V, 2><<<grid, RS_THREADS, smem, st>>>(a, va, n, shift, plan.n_parts, offs, b, vb);
         ctx->prof_launches[P_SORT] += 5;
         std::swap(a, b);

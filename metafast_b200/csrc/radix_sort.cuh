@@ -133,27 +133,47 @@ rs_scatter_kernel(const unsigned long long *__restrict__ keys_in, const V *__res
         __syncthreads();
 
         // warp w owns tile positions [w*512, (w+1)*512): round r, lane l -> w*512 + r*32 + l
-        unsigned long long key[RS_ITEMS];
-        V val[HAS_V ? RS_ITEMS : 1];
-        uint32_t rk[RS_ITEMS / 2];                        // rank inside the warp's digit group, 16 bits each
+        // MINB <= 3: keys and payloads stay in registers between ranking and reordering (128 / 80 registers).
+        // MINB == 4: only (digit | rank << 8) is kept; the reorder phase reads the tile again (L2 hits): ~56 registers,
+        //            4 CTAs per SM to hide the latencies this kernel is bound by.
+        constexpr bool RELOAD = MINB >= 4;
+        unsigned long long key[RELOAD ? 1 : RS_ITEMS];
+        V val[(HAS_V && !RELOAD) ? RS_ITEMS : 1];
+        uint32_t rk[RELOAD ? RS_ITEMS : RS_ITEMS / 2];    // RELOAD: digit | rank << 8 per item; else rank inside the warp's digit group, 16 bits each
+        if constexpr (!RELOAD) {
 #pragma unroll
-        for (int r = 0; r < RS_ITEMS; r++) {
-            const uint32_t p = warp * RS_WARP_ITEMS + r * 32 + lane;
-            key[r] = p < tile_n ? keys_in[lo + p] : ~0ull;
-            if (HAS_V) val[r] = p < tile_n ? vals_in[lo + p] : V();
+            for (int r = 0; r < RS_ITEMS; r++) {
+                const uint32_t p = warp * RS_WARP_ITEMS + r * 32 + lane;
+                key[r] = p < tile_n ? keys_in[lo + p] : ~0ull;
+                if (HAS_V) val[r] = p < tile_n ? vals_in[lo + p] : V();
+            }
         }
 #pragma unroll
-        for (int r = 0; r < RS_ITEMS; r++) {
-            const uint32_t p = warp * RS_WARP_ITEMS + r * 32 + lane;
-            const bool ok = p < tile_n;
-            const uint32_t d = ok ? ((uint32_t)(key[r] >> shift) & (RS_RADIX - 1)) : 0xFFFFFFFFu;
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            uint32_t rank = 0;
-            if (ok) rank = s_cnt[warp][d] + __popc(peers & lt);
-            __syncwarp();
-            if (ok && (peers & lt) == 0) s_cnt[warp][d] += __popc(peers);     // lowest peer advances the counter
-            __syncwarp();
-            if (r & 1) rk[r >> 1] |= rank << 16; else rk[r >> 1] = rank;
+        for (int half = 0; half < 2; half++) {
+            unsigned long long kh[RELOAD ? RS_ITEMS / 2 : 1];
+            if constexpr (RELOAD) {
+#pragma unroll
+                for (int q = 0; q < RS_ITEMS / 2; q++) {
+                    const uint32_t p = warp * RS_WARP_ITEMS + (half * (RS_ITEMS / 2) + q) * 32 + lane;
+                    kh[q] = p < tile_n ? keys_in[lo + p] : ~0ull;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < RS_ITEMS / 2; q++) {
+                const int r = half * (RS_ITEMS / 2) + q;
+                const uint32_t p = warp * RS_WARP_ITEMS + r * 32 + lane;
+                const bool ok = p < tile_n;
+                const unsigned long long kk = RELOAD ? kh[RELOAD ? q : 0] : key[RELOAD ? 0 : r];
+                const uint32_t d = ok ? ((uint32_t)(kk >> shift) & (RS_RADIX - 1)) : 0xFFFFFFFFu;
+                const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                uint32_t rank = 0;
+                if (ok) rank = s_cnt[warp][d] + __popc(peers & lt);
+                __syncwarp();
+                if (ok && (peers & lt) == 0) s_cnt[warp][d] += __popc(peers);     // lowest peer advances the counter
+                __syncwarp();
+                if constexpr (RELOAD) rk[r] = (d & 0xFFu) | (rank << 8);
+                else { if (r & 1) rk[r >> 1] |= rank << 16; else rk[r >> 1] = rank; }
+            }
         }
         __syncthreads();
 
@@ -174,6 +194,29 @@ rs_scatter_kernel(const unsigned long long *__restrict__ keys_in, const V *__res
         __syncthreads();
 
         // reorder the tile by digit in shared memory (stable)
+        if constexpr (RELOAD) {
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                unsigned long long kh[RS_ITEMS / 2]; V vh[HAS_V ? RS_ITEMS / 2 : 1];
+#pragma unroll
+                for (int q = 0; q < RS_ITEMS / 2; q++) {
+                    const uint32_t p = warp * RS_WARP_ITEMS + (half * (RS_ITEMS / 2) + q) * 32 + lane;
+                    kh[q] = p < tile_n ? keys_in[lo + p] : ~0ull;
+                    if (HAS_V) vh[q] = p < tile_n ? vals_in[lo + p] : V();
+                }
+#pragma unroll
+                for (int q = 0; q < RS_ITEMS / 2; q++) {
+                    const int r = half * (RS_ITEMS / 2) + q;
+                    const uint32_t p = warp * RS_WARP_ITEMS + r * 32 + lane;
+                    if (p < tile_n) {
+                        const uint32_t d = rk[r] & 0xFFu, rank = rk[r] >> 8;
+                        const uint32_t pos = s_dstart[d] + s_cnt[warp][d] + rank;
+                        s_keys[pos] = kh[q];
+                        if (HAS_V) s_vals[pos] = vh[q];
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for (int r = 0; r < RS_ITEMS; r++) {
             const uint32_t p = warp * RS_WARP_ITEMS + r * 32 + lane;
@@ -184,6 +227,7 @@ rs_scatter_kernel(const unsigned long long *__restrict__ keys_in, const V *__res
                 s_keys[pos] = key[r];
                 if (HAS_V) s_vals[pos] = val[r];
             }
+        }
         }
         __syncthreads();
 

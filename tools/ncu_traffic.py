@@ -20,9 +20,22 @@ out = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__
 for name, m in per.items():
     out["kernels"][name] = {"launches": len(launches[name]), "dram_read_bytes": m.get("dram__bytes_read.sum", 0), "dram_write_bytes": m.get("dram__bytes_write.sum", 0),
                             "time_ms_under_ncu": m.get("gpu__time_duration.sum", 0)}
-counting = [k for k in out["kernels"] if k.startswith(("extract_skm", "bin_count", "drain_heavy", "ovf_place", "mark_read_ends"))]
+# the capture window need not coincide with one step: per-launch averages x the launches one cfg2 step makes (20 batches)
+per_step = {"extract_skm_kernel": 20, "mark_read_ends_kernel": 20, "ovf_place_kernel": 1, "bin_count_kernel": 1, "drain_heavy_kernel": 0,
+            "rs_hist_kernel": 8, "rs_chunk_kernel": 8, "rs_base_kernel": 8, "rs_offsets_kernel": 8, "rs_scatter_kernel": 8, "records_kernel": 1}
+def short(k):
+    return k.split("(")[0]
+tot_c = tot_a = 0.0
+counting = []
+for k, v in out["kernels"].items():
+    n = per_step.get(short(k), v["launches"])
+    b = (v["dram_read_bytes"] + v["dram_write_bytes"]) / max(1, v["launches"]) * n
+    v["launches_per_step"] = n; v["dram_bytes_per_step"] = b
+    tot_a += b
+    if short(k) in ("extract_skm_kernel", "bin_count_kernel", "drain_heavy_kernel", "ovf_place_kernel", "mark_read_ends_kernel"):
+        counting.append(short(k)); tot_c += b
 out["per_step_bytes"]["counting_kernels"] = counting
-out["per_step_bytes"]["total_counting"] = sum(out["kernels"][k]["dram_read_bytes"] + out["kernels"][k]["dram_write_bytes"] for k in counting)
-out["per_step_bytes"]["total_all"] = sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in out["kernels"].values())
+out["per_step_bytes"]["total_counting"] = tot_c
+out["per_step_bytes"]["total_all"] = tot_a
 json.dump(out, open(sys.argv[2], "w"), indent=1)
 print(json.dumps(out["per_step_bytes"]))
