@@ -394,9 +394,13 @@ struct SinkTable {              // hash variant: upsert into the HBM-resident ta
 };
 
 struct SinkPresence {           // features-calculator reads mode: if (contains(key)) acc += 1
-    FcSlot *tab; uint64_t cap;
+    FcSlot *tab; uint64_t cap; const uint32_t *bloom; uint32_t bmask;
     static constexpr bool kPrefetch = true;
-    __device__ __forceinline__ void prefetch(uint64_t key) const { prefetch_l2(&tab[home_slot(key, cap)]); }
+    __device__ __forceinline__ void prefetch(uint64_t key) const {
+        const uint64_t mx = mix64(key);
+        if (bmask) { const uint32_t b = (uint32_t)mx & bmask; if (!((__ldg(&bloom[b >> 5]) >> (b & 31u)) & 1u)) return; }
+        prefetch_l2(&tab[mulhi64(mx, cap)]);
+    }
     __device__ __forceinline__ uint32_t put(uint64_t key) const;
     __device__ __forceinline__ void finish(uint32_t) const {}
 };
@@ -409,8 +413,17 @@ __device__ __forceinline__ long long add_and_bound64(long long v, long long inc)
 }
 
 // if (hm.contains(key)) hm.addAndBound(key, inc)   (src/io/IOUtils.java:583-587, 817-821)
-__device__ __forceinline__ void fc_accumulate(FcSlot *__restrict__ tab, uint64_t cap, uint64_t key, long long inc) {
-    uint64_t i = home_slot(key, cap);
+// A one-hash Bloom bitmap in front (16 bits per component k-mer, at most 64 MiB: L2-resident): most records of a sample are
+// not component k-mers, and the bitmap turns their random DRAM probe of the set into an L2 hit (no false negatives, so
+// results are unchanged).  bmask = 0: no filter.
+__device__ __forceinline__ void fc_accumulate(FcSlot *__restrict__ tab, uint64_t cap, uint64_t key, long long inc,
+                                              const uint32_t *__restrict__ bloom = nullptr, uint32_t bmask = 0) {
+    const uint64_t mx = mix64(key);
+    if (bmask) {
+        const uint32_t b = (uint32_t)mx & bmask;
+        if (!((__ldg(&bloom[b >> 5]) >> (b & 31u)) & 1u)) return;
+    }
+    uint64_t i = mulhi64(mx, cap);
     for (;;) {
         const unsigned long long cur = ld_cg_u64x2(&tab[i]).x;
         if (cur == EMPTY_KEY) return;                 // not a component k-mer
@@ -426,7 +439,7 @@ __device__ __forceinline__ void fc_accumulate(FcSlot *__restrict__ tab, uint64_t
         if (++i == cap) i = 0;
     }
 }
-__device__ __forceinline__ uint32_t SinkPresence::put(uint64_t key) const { fc_accumulate(tab, cap, key, 1); return 0; }
+__device__ __forceinline__ uint32_t SinkPresence::put(uint64_t key) const { fc_accumulate(tab, cap, key, 1, bloom, bmask); return 0; }
 
 // ------------------------------------------------------------------------------------------
 // K1+K2(+K3): flat extraction.  The batch is one concatenated ASCII stream; thread t of a tile
@@ -1844,10 +1857,11 @@ pairs_hist_kernel(const uint32_t *__restrict__ counts, uint64_t n, unsigned long
 // hm.put(kmer, 0) for every component k-mer (FeaturesCalculatorMain.java:97-103)
 __global__ void __launch_bounds__(256)
 fc_build_kernel(const unsigned long long *__restrict__ keys, uint64_t n, FcSlot *__restrict__ tab, uint64_t cap,
-                Counters *__restrict__ ctr) {
+                Counters *__restrict__ ctr, uint32_t *__restrict__ bloom, uint32_t bmask) {
     uint32_t claimed = 0;
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
         const unsigned long long key = keys[t];
+        if (bmask) { const uint32_t b = (uint32_t)mix64(key) & bmask; atomicOr(&bloom[b >> 5], 1u << (b & 31u)); }
         uint64_t i = home_slot(key, cap);
         for (;;) {
             unsigned long long cur = ld_cg_u64x2(&tab[i]).x;
@@ -1884,11 +1898,12 @@ __device__ __forceinline__ void load_record(const uint8_t *__restrict__ rec, uns
 
 // KmersPresenceWorker.processKmer (src/io/IOUtils.java:583-587)
 __global__ void __launch_bounds__(256)
-fc_records_kernel(const uint8_t *__restrict__ recs, uint64_t n, FcSlot *__restrict__ tab, uint64_t cap) {
+fc_records_kernel(const uint8_t *__restrict__ recs, uint64_t n, FcSlot *__restrict__ tab, uint64_t cap,
+                  const uint32_t *__restrict__ bloom, uint32_t bmask) {
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
         unsigned long long key; int freq;
         load_record(recs + 10 * t, key, freq);
-        fc_accumulate(tab, cap, key, (long long)freq);
+        fc_accumulate(tab, cap, key, (long long)freq, bloom, bmask);
     }
 }
 
@@ -1896,9 +1911,9 @@ fc_records_kernel(const uint8_t *__restrict__ recs, uint64_t n, FcSlot *__restri
 // kmer-counter-many -> features-calculator hand-over without the round trip through a .kmers.bin file
 __global__ void __launch_bounds__(256)
 fc_pairs_kernel(const unsigned long long *__restrict__ keys, const uint16_t *__restrict__ counts, uint64_t n,
-                FcSlot *__restrict__ tab, uint64_t cap) {
+                FcSlot *__restrict__ tab, uint64_t cap, const uint32_t *__restrict__ bloom, uint32_t bmask) {
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x)
-        fc_accumulate(tab, cap, keys[t], (long long)(short)counts[t]);
+        fc_accumulate(tab, cap, keys[t], (long long)(short)counts[t], bloom, bmask);
 }
 
 // Kmers2HMWorker.processKmer with threshold 0 (src/io/IOUtils.java:249-257): selected[key] =

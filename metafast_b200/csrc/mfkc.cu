@@ -136,6 +136,7 @@ struct mfkc_ctx {
 
     // features-calculator
     FcSlot *fc_tab = nullptr; uint64_t fc_cap = 0;
+    uint32_t *fc_bloom = nullptr; uint32_t fc_bmask = 0;     // one-hash Bloom bitmap in front of fc_tab (see fc_accumulate)
     unsigned long long *fc_keys = nullptr; uint64_t *fc_off = nullptr; uint32_t fc_ncomp = 0; uint64_t fc_nkeys = 0;
     Slot *fc_sel = nullptr; uint64_t fc_sel_cap = 0; uint64_t fc_sel_n = 0;
     Counters *d_fc_ctr = nullptr;
@@ -482,7 +483,7 @@ extern "C" void mfkc_destroy(mfkc_ctx *ctx) {
     cudaFree(ctx->d_ctr); cudaFree(ctx->d_fc_ctr); cudaFree(ctx->d_hist);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->h_hist) cudaFreeHost(ctx->h_hist);
-    cudaFree(ctx->fc_tab); cudaFree(ctx->fc_keys); cudaFree(ctx->fc_off); cudaFree(ctx->fc_sel);
+    cudaFree(ctx->fc_tab); cudaFree(ctx->fc_keys); cudaFree(ctx->fc_off); cudaFree(ctx->fc_sel); cudaFree(ctx->fc_bloom);
     cudaFree(ctx->d_synth);
     if (ctx->ev_drain) cudaEventDestroy(ctx->ev_drain);
     if (ctx->h_drain_snap) cudaFreeHost(ctx->h_drain_snap);
@@ -2269,12 +2270,19 @@ extern "C" int mfkc_fc_load_components(mfkc_ctx *ctx, const int64_t *keys, const
     if (ctx->k128) return fail(ctx, MFKC_E_BADARG, "features-calculator works on 64-bit keys (k <= 31), like the reference");
     CU_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->compute;
-    cudaFree(ctx->fc_tab); cudaFree(ctx->fc_keys); cudaFree(ctx->fc_off);
-    ctx->fc_tab = nullptr; ctx->fc_keys = nullptr; ctx->fc_off = nullptr;
+    cudaFree(ctx->fc_tab); cudaFree(ctx->fc_keys); cudaFree(ctx->fc_off); cudaFree(ctx->fc_bloom);
+    ctx->fc_tab = nullptr; ctx->fc_keys = nullptr; ctx->fc_off = nullptr; ctx->fc_bloom = nullptr; ctx->fc_bmask = 0;
     const uint64_t nk = comp_offsets[n_comp] - comp_offsets[0];
     ctx->fc_nkeys = nk; ctx->fc_ncomp = n_comp;
     ctx->fc_cap = std::max<uint64_t>(nk * 2 + 64, 1024);
     CU_TRY(cudaMalloc(&ctx->fc_tab, ctx->fc_cap * sizeof(FcSlot)));
+    if (!getenv("MFKC_FC_NO_BLOOM")) {
+        uint64_t bits = 1ull << 16;
+        while (bits < 16 * nk && bits < (1ull << 29)) bits <<= 1;           // 16 bits per key, 64 MiB at most (stays in L2)
+        CU_TRY(cudaMalloc(&ctx->fc_bloom, bits / 8));
+        CU_TRY(cudaMemsetAsync(ctx->fc_bloom, 0, bits / 8, st));
+        ctx->fc_bmask = (uint32_t)(bits - 1);
+    }
     CU_TRY(cudaMalloc(&ctx->fc_keys, std::max<uint64_t>(nk, 1) * 8));
     CU_TRY(cudaMalloc(&ctx->fc_off, ((size_t)n_comp + 1) * 8));
     std::vector<uint64_t> off(n_comp + 1);
@@ -2285,7 +2293,7 @@ extern "C" int mfkc_fc_load_components(mfkc_ctx *ctx, const int64_t *keys, const
     fc_clear_kernel<<<grid_for(ctx, ctx->fc_cap, 256, 8), 256, 0, st>>>(ctx->fc_tab, ctx->fc_cap, 1);
     if (nk) {
         ProfScope ps(ctx, P_FC_BUILD, st);
-        fc_build_kernel<<<grid_for(ctx, nk, 256, 8), 256, 0, st>>>(ctx->fc_keys, nk, ctx->fc_tab, ctx->fc_cap, ctx->d_fc_ctr);
+        fc_build_kernel<<<grid_for(ctx, nk, 256, 8), 256, 0, st>>>(ctx->fc_keys, nk, ctx->fc_tab, ctx->fc_cap, ctx->d_fc_ctr, ctx->fc_bloom, ctx->fc_bmask);
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(st));
@@ -2357,7 +2365,7 @@ extern "C" int mfkc_fc_add_records(mfkc_ctx *ctx, const uint8_t *be_records, uin
     CU_TRY(cudaStreamWaitEvent(ctx->compute, s.ev_copy, 0));
     {
         ProfScope ps(ctx, P_FC_RECORDS, ctx->compute);
-        fc_records_kernel<<<grid_for(ctx, n_records, 256, 8), 256, 0, ctx->compute>>>(s.d_bases, n_records, ctx->fc_tab, ctx->fc_cap);
+        fc_records_kernel<<<grid_for(ctx, n_records, 256, 8), 256, 0, ctx->compute>>>(s.d_bases, n_records, ctx->fc_tab, ctx->fc_cap, ctx->fc_bloom, ctx->fc_bmask);
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(s.ev_done, ctx->compute));
@@ -2375,7 +2383,7 @@ extern "C" int mfkc_fc_add_emitted(mfkc_ctx *ctx, mfkc_ctx *counter) {
     CU_TRY(cudaSetDevice(ctx->device));
     {   // the counter's emit finished with a host synchronisation, so its arrays are complete
         ProfScope ps(ctx, P_FC_RECORDS, ctx->compute);
-        fc_pairs_kernel<<<grid_for(ctx, counter->em_n, 256, 8), 256, 0, ctx->compute>>>(counter->em_keys, counter->em_counts, counter->em_n, ctx->fc_tab, ctx->fc_cap);
+        fc_pairs_kernel<<<grid_for(ctx, counter->em_n, 256, 8), 256, 0, ctx->compute>>>(counter->em_keys, counter->em_counts, counter->em_n, ctx->fc_tab, ctx->fc_cap, ctx->fc_bloom, ctx->fc_bmask);
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(ctx->compute));             // the counter may reset its arrays as soon as this returns
@@ -2401,7 +2409,7 @@ extern "C" int mfkc_fc_add_reads(mfkc_ctx *ctx, const uint8_t *bases, const uint
     TRY(launch_mark(ctx, s, s.d_offsets, n_reads, n_bases, 0, 0, ctx->d_fc_ctr));
     if (n_bases >= (uint64_t)ctx->cfg.k) {
         ProfScope ps(ctx, P_FC_READS, ctx->compute);
-        SinkPresence sink{ctx->fc_tab, ctx->fc_cap};
+        SinkPresence sink{ctx->fc_tab, ctx->fc_cap, ctx->fc_bloom, ctx->fc_bmask};
         extract_kernel<SinkPresence><<<extract_grid(ctx, n_bases), EX_THREADS, 0, ctx->compute>>>(
             s.d_bases, n_bases, s.d_flags, ctx->cfg.k, sink, ctx->d_fc_ctr);
         CU_TRY(cudaGetLastError());

@@ -395,8 +395,11 @@ def test_fast_inflate_matches_zlib(built):
     assert _fast_inflate(multi + b"\x00garbage", 65536)[0] == got
     # header fields: FEXTRA + FNAME + FCOMMENT + FHCRC
     body = gz(texts["fastq"])[10:]
-    hdr = b"\x1f\x8b\x08\x1e\0\0\0\0\0\x03" + b"\x06\x00BC\x02\x00\x12\x34" + b"name.fq\0" + b"a comment\0" + b"\xab\xcd"
-    assert _fast_inflate(hdr + body)[0] == texts["fastq"]
+    hdr = b"\x1f\x8b\x08\x1e\0\0\0\0\0\x03" + b"\x06\x00BC\x02\x00\x12\x34" + b"name.fq\0" + b"a comment\0"
+    hcrc = (zlib.crc32(hdr) & 0xFFFF).to_bytes(2, "little")                 # FHCRC = low 16 bits of the header's CRC-32 (RFC 1952)
+    assert _fast_inflate(hdr + hcrc + body)[0] == texts["fastq"]
+    got_bad, err_bad, _ = _fast_inflate(hdr + bytes([hcrc[0] ^ 1, hcrc[1]]) + body)
+    assert got_bad is None and "header CRC" in err_bad
     # a member must not reach into the previous member's text
     assert n_cases > 100
 
