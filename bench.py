@@ -494,7 +494,10 @@ def run_config3(args):
         nbytes = kc.emit_into(b, h_out)
         kc.histogram()
         fc.reset_values()
-        fc._ck(fc.lib.mfkc_fc_add_records(fc.h, h_out.ctypes.data_as(C.c_void_p), nbytes // 10))
+        chunk = 16777200                                              # the reference's KMERS_WORK_RANGE_SIZE (src/io/IOUtils.java:30)
+        for pos in range(0, nbytes, chunk):
+            nb = min(chunk, nbytes - pos)
+            fc._ck(fc.lib.mfkc_fc_add_records(fc.h, C.c_void_p(h_out.ctypes.data + pos), nb // 10))
         fc.features(0)
         return nbytes
     for hb, ho, n in host:

@@ -2278,7 +2278,7 @@ extern "C" int mfkc_fc_load_components(mfkc_ctx *ctx, const int64_t *keys, const
     CU_TRY(cudaMalloc(&ctx->fc_tab, ctx->fc_cap * sizeof(FcSlot)));
     if (!getenv("MFKC_FC_NO_BLOOM")) {
         uint64_t bits = 1ull << 16;
-        while (bits < 16 * nk && bits < (1ull << 29)) bits <<= 1;           // 16 bits per key, 64 MiB at most (stays in L2)
+        while (bits < 8 * nk && bits < (1ull << 29)) bits <<= 1;            // 8-16 bits per key, 64 MiB at most (stays in L2)
         CU_TRY(cudaMalloc(&ctx->fc_bloom, bits / 8));
         CU_TRY(cudaMemsetAsync(ctx->fc_bloom, 0, bits / 8, st));
         ctx->fc_bmask = (uint32_t)(bits - 1);
