@@ -734,14 +734,16 @@ def main():
         c = c or kc
         out = h_out if out is None else out
         shd = shd or (sharded if world > 1 else None)
+        c.reset()
         if world > 1 and exchange == "p2p":
-            shd.begin()                      # (a barrier between the ranks: outside the link lock, other lanes keep submitting)
+            shd.begin()                      # a barrier between the ranks: never under the link lock
         if lock:
             lock.acquire()                   # one sample at a time on the host-to-device link
         try:
-            c.reset()
-            if world > 1:
-                shd.run_host(h_bases, h_offs, n_reads)
+            if world > 1 and exchange == "p2p":
+                shd.submit_host(h_bases, h_offs, n_reads)      # this rank's copies + launches only: waits for no other rank
+            elif world > 1:
+                shd.run_host(h_bases, h_offs, n_reads)         # (collectives inside: only ever run without lanes)
             else:
                 for s in range(0, n_reads, BATCH_READS):
                     e = min(n_reads, s + BATCH_READS)
@@ -749,6 +751,11 @@ def main():
         finally:
             if lock:
                 lock.release()
+        if world > 1 and exchange == "p2p":
+            # The exchange of the totals waits for the same lane of every other rank.  It must not run under the link lock:
+            # rank A's lane 0 holding A's lock in this exchange while rank B's lane 1 holds B's lock in its own is a deadlock
+            # (A's lane 1 and B's lane 0 are both queued behind those locks) -- seen as a hung 8-rank run.
+            shd.finish()
         c.flush()
         nbytes = c.emit_into(B_THRESHOLD, out)
         c.histogram()
@@ -758,43 +765,47 @@ def main():
     # in batch mode): while one sample is counted, sorted and copied back, the next one's reads are already crossing PCIe.
     # Every step still does the whole job through the C ABI: reads host -> device, records + histogram device -> host.
     # N > 1: the same with one sharded group of contexts per lane; the lanes' tiny exchanges (G numbers, barriers) run on CPU
-    # process groups of their own, so that lanes of different ranks may be at different points.
+    # process groups of their own, so that lanes of different ranks may be at different points.  Those groups time out after
+    # a few minutes: a protocol error ends the run with a message instead of hanging it.
     pipelined = not os.environ.get("MFKC_BENCH_E2E_SERIAL") and (world == 1 or (exchange == "p2p" and variant == m.VARIANT_HASH))
+    e2e_error = None
     if pipelined:
+        import datetime
+        from metafast_b200.sharded import run_lanes
         n_lanes = max(2, int(os.environ.get("MFKC_BENCH_E2E_LANES", 3)))
+        lane_timeout = datetime.timedelta(seconds=int(os.environ.get("MFKC_BENCH_LANE_TIMEOUT_S", 120)))
         extra = [m.KmerCounter(K, device=local_rank, variant=variant, expected_kmers=kmers_ub,
                                n_shards=world if world > 1 else 0, shard_id=rank if world > 1 else 0) for _ in range(n_lanes - 1)]
         lanes = [(kc, h_out, sharded if world > 1 else None)]
         if world > 1:
-            sharded.group = dist.new_group(backend="gloo")
+            sharded.group = dist.new_group(backend="gloo", timeout=lane_timeout)
         for c in extra:
             shd = None
             if world > 1:
-                shd = P2PShardedStep(c, dist, world, rank, BATCH_READS, READ_LEN, K, N_READS, group=dist.new_group(backend="gloo"))
+                shd = P2PShardedStep(c, dist, world, rank, BATCH_READS, READ_LEN, K, N_READS,
+                                     group=dist.new_group(backend="gloo", timeout=lane_timeout))
             lanes.append((c, c.pinned(h_out.nbytes), shd))
         link = threading.Lock()
 
         def run_pipelined(n_steps):
-            res = [0] * n_steps
+            return run_lanes(n_steps, lanes, lambda ln, i: step_e2e(ln[0], ln[1], link, ln[2]))[-1]
 
-            def lane(j):
-                for i in range(j, n_steps, n_lanes):
-                    res[i] = step_e2e(lanes[j][0], lanes[j][1], link, lanes[j][2])
-            ts = [threading.Thread(target=lane, args=(j,)) for j in range(n_lanes)]
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
-            return res[-1]
-
-        run_pipelined(2 * n_lanes)           # every context: plan from a first sample, allocate, warm up
+        out_bytes = 0
+        try:
+            run_pipelined(2 * n_lanes)       # every context: plan from a first sample, allocate, warm up
+        except RuntimeError as e:            # (a lane group timed out or a context failed: every rank gets here)
+            e2e_error = str(e)[:300]
         barrier()
         t0 = time.perf_counter()
-        out_bytes = run_pipelined(args.steps)
+        try:
+            if e2e_error is None:
+                out_bytes = run_pipelined(args.steps)
+        except RuntimeError as e:
+            e2e_error = str(e)[:300]
         for c in extra:
             c.sync()
         barrier()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_s = max_over_ranks(time.perf_counter() - t0 if e2e_error is None else float("inf"))
         barrier()
         for c in extra:
             c.close()
@@ -810,7 +821,8 @@ def main():
             out_bytes = step_e2e()
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = kmers_per_step * world * args.steps / e2e_s
+    e2e_failed = e2e_s == float("inf")                # on any rank (the maximum over the ranks)
+    e2e_value = None if e2e_failed else kmers_per_step * world * args.steps / e2e_s
 
     # what the host can feed: every rank copies its reads host -> device at the same time, nothing else running
     barrier()
@@ -873,7 +885,8 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": "kmers/s", "h2d_bytes_per_step": int(n_bases + (n_reads + 1) * 8),
-                "d2h_bytes_per_step": int(out_bytes + 32768 * 8), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "d2h_bytes_per_step": int(out_bytes + 32768 * 8), "ms_per_step": None if e2e_failed else 1e3 * e2e_s / args.steps,
+                "error": (e2e_error or "the end-to-end pass failed on another rank") if e2e_failed else None,
                 "host_to_device_gbs_all_gpus": link_gbs, "h2d_floor_ms_per_step": 1e3 * n_bases * world / (link_gbs * 1e9),
                 "mode": "%d contexts take the samples in turn (H2D of sample i+1 overlaps count + emit + D2H of sample i)" % n_lanes if pipelined
                         else "one sample after the other"},

@@ -41,7 +41,7 @@ extern "C" int mfkc_kset_create(mfkc_ctx *ctx, mfkc_kset **out) {
     mfkc_kset *ks = new mfkc_kset();
     ks->ctx = ctx;
     if (cudaMalloc(&ks->d_cursor, sizeof(unsigned long long)) != cudaSuccess) { delete ks; return fail(ctx, MFKC_E_OOM, "cudaMalloc"); }
-    cudaMemset(ks->d_cursor, 0, sizeof(unsigned long long));
+    cudaMemsetAsync(ks->d_cursor, 0, sizeof(unsigned long long), ctx->compute);
     *out = ks;
     return MFKC_OK;
 }
@@ -114,7 +114,7 @@ extern "C" int mfkc_kset_load_finish(mfkc_kset *ks) {
         ks->n = on;
     }
     cudaFree(ks->pk); cudaFree(ks->pv); ks->pk = nullptr; ks->pv = nullptr; ks->p_cap = ks->p_ub = 0;
-    CU_TRY(cudaMemset(ks->d_cursor, 0, sizeof(unsigned long long)));
+    CU_TRY(cudaMemsetAsync(ks->d_cursor, 0, sizeof(unsigned long long), ctx->compute));
     ks->sel_valid = false;
     return MFKC_OK;
 }

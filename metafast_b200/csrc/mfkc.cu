@@ -1864,7 +1864,7 @@ extern "C" int mfkc_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, cons
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(ctx->compute));
     // restore the sort-variant base (bucket 0 starts at 0)
-    CU_TRY(cudaMemset(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t)));
+    CU_TRY(cudaMemsetAsync(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t), ctx->compute));
     return MFKC_OK;
 }
 
@@ -1951,7 +1951,7 @@ extern "C" int mfkc_skm_extract_bucketed(mfkc_ctx *ctx, const uint8_t *d_bases, 
     CU_TRY(cudaStreamSynchronize(ctx->compute));
     bool overflow = false;
     for (uint32_t i = 0; i < ns; i++) { rec_counts[i] = h_cur[i]; kmer_counts[i] = ctx->h_bucket[i]; if (h_cur[i] > seg_cap) overflow = true; }
-    CU_TRY(cudaMemset(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t)));                    // bucket 0 of the sort variant starts at 0
+    CU_TRY(cudaMemsetAsync(ctx->d_bucket_base, 0, 64 * sizeof(uint64_t), ctx->compute)); // bucket 0 of the sort variant starts at 0
     if (overflow) {
         // undo this attempt's statistics; the caller re-submits the same reads in smaller pieces
         CU_TRY(cudaMemcpy(ctx->d_ctr, ctx->h_ctr, sizeof(Counters), cudaMemcpyHostToDevice));
@@ -2023,6 +2023,7 @@ extern "C" int mfkc_p2p_stage_create(mfkc_ctx *ctx, uint32_t log2_buckets, uint6
     CU_TRY(cudaMalloc(&ctx->p2p_kc, P2P_MAX_PEERS * sizeof(unsigned long long)));
     CU_TRY(cudaMemset(ctx->p2p_cursor, 0, n_seg * sizeof(unsigned int)));
     CU_TRY(cudaMemset(ctx->p2p_kc, 0, P2P_MAX_PEERS * sizeof(unsigned long long)));
+    CU_TRY(cudaDeviceSynchronize());                                          // peers write these once the handles are out
     ctx->p2p_seg_cap = seg_cap; ctx->p2p_log2 = (int)log2_buckets;
     ctx->p2p_bins = false; ctx->p2p_n_cursor = n_seg;
     return MFKC_OK;
@@ -2068,6 +2069,7 @@ extern "C" int mfkc_p2p_stage_create_bins(mfkc_ctx *ctx, uint32_t bins_per_shard
     CU_TRY(cudaMalloc(&ctx->p2p_kc, P2P_MAX_PEERS * sizeof(unsigned long long)));
     CU_TRY(cudaMemset(ctx->p2p_cursor, 0, (n_seg + 1) * sizeof(unsigned int)));
     CU_TRY(cudaMemset(ctx->p2p_kc, 0, P2P_MAX_PEERS * sizeof(unsigned long long)));
+    CU_TRY(cudaDeviceSynchronize());                                          // peers write these once the handles are out
     ctx->p2p_seg_cap = seg_cap; ctx->p2p_log2 = 0; ctx->p2p_bins = true; ctx->p2p_B = bins_per_shard; ctx->p2p_ovf_cap = ovf_cap;
     ctx->os_mlen = bin_minimizer_len(ctx->cfg.k, n_seg);         // the same on every rank: a function of the geometry
     ctx->p2p_n_cursor = n_seg + 1;
@@ -2513,13 +2515,18 @@ extern "C" int mfkc_device_free(mfkc_ctx *ctx, void *d_ptr) {
 extern "C" int mfkc_memcpy_h2d(mfkc_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
     if (!ctx) return MFKC_E_BADARG;
     CU_TRY(cudaSetDevice(ctx->device));
-    CU_TRY(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+    // On the compute stream and awaited: a legacy-stream cudaMemcpy from pageable memory may return
+    // while its last staged chunk is still in flight, and the (non-blocking) compute stream does not
+    // wait for the legacy stream -- a kernel launched right after could read the old bytes.
+    CU_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->compute));
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
     return MFKC_OK;
 }
 extern "C" int mfkc_memcpy_d2h(mfkc_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
     if (!ctx) return MFKC_E_BADARG;
     CU_TRY(cudaSetDevice(ctx->device));
-    CU_TRY(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->compute));   // after the compute stream's kernels
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
     return MFKC_OK;
 }
 extern "C" int mfkc_device_sync(mfkc_ctx *ctx) {
@@ -2569,8 +2576,8 @@ extern "C" int mfkc_gups_ex(mfkc_ctx *ctx, uint64_t bytes, uint64_t n_updates, i
     CU_TRY(cudaSetDevice(ctx->device));
     unsigned long long *tab = nullptr;
     CU_TRY(cudaMalloc(&tab, bytes));
-    CU_TRY(cudaMemset(tab, 0, bytes));
     cudaStream_t st = ctx->compute;
+    CU_TRY(cudaMemsetAsync(tab, 0, bytes, st));
     const uint64_t n_sectors = bytes / 32;
     uint64_t win = window_bytes / 32;
     if (win == 0 || win > n_sectors) win = n_sectors;

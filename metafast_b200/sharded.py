@@ -259,8 +259,43 @@ class P2PShardedStep:
             self.kc.p2p_extract(d_bases + s * self.read_len, d_offs + s * 8, e - s, (e - s) * self.read_len)
         self._finish()
 
-    def run_host(self, h_bases: np.ndarray, h_offs: np.ndarray, n_reads: int):
+    def submit_host(self, h_bases: np.ndarray, h_offs: np.ndarray, n_reads: int):
+        """this rank's part only (host -> device copies + extraction launches): no other rank is waited for, so a caller
+        that runs several lanes may hold a rank-local lock around it"""
         for s in range(0, n_reads, self.batch_reads):
             e = min(n_reads, s + self.batch_reads)
             self.kc.p2p_submit(h_bases, h_offs[s:e + 1])
+
+    def finish(self):
+        """the exchange of the per-owner totals (every rank of the group takes part) + this owner's count.  Never call it
+        while holding a rank-local lock that another lane needs for its own submit_host: two ranks whose lanes took their
+        locks in different orders would wait for each other for ever."""
         self._finish()
+
+    def run_host(self, h_bases: np.ndarray, h_offs: np.ndarray, n_reads: int):
+        self.submit_host(h_bases, h_offs, n_reads)
+        self._finish()
+
+
+def run_lanes(n_steps: int, lanes, step):
+    """Samples 0..n_steps-1 over len(lanes) lanes, one host thread per lane: lane j takes samples j, j+L, j+2L, ...
+    step(lane, i) does one sample.  An exception in any lane is re-raised here (after all lanes ended) instead of
+    dying with its thread -- a rank must not carry on while its peers wait for the failed lane."""
+    import threading
+    n_lanes = len(lanes)
+    res, errors = [None] * n_steps, []
+
+    def lane(j):
+        try:
+            for i in range(j, n_steps, n_lanes):
+                res[i] = step(lanes[j], i)
+        except BaseException as e:          # noqa: BLE001 -- reported below
+            errors.append((j, e))
+    ts = [threading.Thread(target=lane, args=(j,)) for j in range(n_lanes)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errors:
+        raise RuntimeError("lane %d failed: %r" % (errors[0][0], errors[0][1])) from errors[0][1]
+    return res

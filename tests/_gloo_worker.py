@@ -132,3 +132,60 @@ def run_p2p(rank, world, port, out_dir):
         f.write(orc.kmers_bin(kc.counts, b, k))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def run_p2p_lanes(rank, world, port, out_dir):
+    """bench.py's multi-lane end-to-end protocol for N > 1: several samples in flight per rank, one lane = one context +
+    one sharded step + one CPU process group; a rank-local lock serialises the lanes' submissions.  Random delays make
+    the lanes of different ranks take that lock in different orders."""
+    import datetime
+    import random
+    import threading
+    import time
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import metafast_b200 as m
+    from metafast_b200 import sharded
+    k, L, n_lanes, n_steps = 21, 100, 3, 24
+    cfg = m.synth_cfg(total_genome_bp=20000, n_genomes=2, n_read_ppm=0, read_len=L)
+    raw = m.synth_reads_host(cfg, 0, 60 * world)
+    mine = np.ascontiguousarray(raw[rank::world])
+    offs = np.arange(len(mine) + 1, dtype=np.uint64) * np.uint64(L)
+    lib = m.load()
+    lanes = []
+    for j in range(n_lanes):
+        d = os.path.join(out_dir, "lane%d" % j)
+        os.makedirs(d, exist_ok=True)
+        kc = _StubCounter(rank, world, k, d, lib)
+        grp = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=60))
+        lanes.append((kc, sharded.P2PShardedStep(kc, dist, world, rank, 25, L, k, len(mine), group=grp)))
+    link = threading.Lock()
+    rnd = random.Random(1000 + rank)
+    sizes = []
+
+    def step(lane, i):
+        kc, shd = lane
+        kc.counts = {}
+        shd.begin()
+        with link:
+            time.sleep(rnd.random() * 0.01)
+            shd.submit_host(mine.reshape(-1), offs, len(mine))
+        shd.finish()
+        time.sleep(rnd.random() * 0.01)
+        return len(kc.counts), sum(kc.counts.values())
+    res = sharded.run_lanes(n_steps, lanes, step)
+    assert len(set(res)) == 1 and res[0][0] > 0                # every sample of every lane: the same counts
+    with open(os.path.join(out_dir, "lanes_rank%d.txt" % rank), "w") as f:
+        f.write("%d %d\n" % res[0])
+
+    def failing(lane, i):
+        raise ValueError("boom")
+    try:
+        sharded.run_lanes(3, lanes, failing)
+        raise AssertionError("run_lanes swallowed a lane's exception")
+    except RuntimeError as e:
+        assert "boom" in str(e)
+    dist.barrier()
+    dist.destroy_process_group()

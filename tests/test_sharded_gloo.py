@@ -49,3 +49,19 @@ def test_peer_memory_protocol_two_ranks(built, tmp_path):
     assert sharded.merge_sorted_records(parts) == orc.kmers_bin(orc.count_reads(reads, 21), 1, 21)
     log2, seg_cap = sharded.p2p_geometry(20_000_000 * 120, 8)
     assert 8 <= log2 <= 14 and (8 << log2) * seg_cap * 16 < 20e9         # cfg2 at 8 GPUs: staging fits comfortably
+
+
+def test_lanes_of_sharded_steps_do_not_wait_in_a_cycle(built, tmp_path):
+    """Several samples in flight per rank (bench.py's end-to-end path for N > 1): the exchange of a lane waits for the
+    same lane of the other ranks, so it must run outside the rank-local lock that orders the lanes' submissions.
+    With the exchange under the lock this test ends in the groups' timeout."""
+    import torch.multiprocessing as mp
+    from tests import _gloo_worker
+    import metafast_b200 as m
+    world = 3
+    mp.spawn(_gloo_worker.run_p2p_lanes, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [tuple(int(x) for x in open(os.path.join(tmp_path, "lanes_rank%d.txt" % r)).read().split()) for r in range(world)]
+    cfg = m.synth_cfg(total_genome_bp=20000, n_genomes=2, n_read_ppm=0, read_len=100)
+    reads = [bytes(r).decode() for r in m.synth_reads_host(cfg, 0, 60 * world)]
+    counts = orc.count_reads(reads, 21)
+    assert sum(g[0] for g in got) == len(counts) and sum(g[1] for g in got) == sum(counts.values())
