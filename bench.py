@@ -842,8 +842,11 @@ def main():
     count_kernels = {"hash (bin-local)": ["extract_skm", "bin_count", "drain_heavy"], "table": ["extract_skm", "drain_skm"],
                      "direct": ["extract_direct"], "sort": ["extract_keys", "radix_sort", "rle"]}[workload_config(1)["variant"]]
     if world > 1:
-        count_kernels = ["extract_skm_shard", "extract_skm", "drain_skm"]      # p2p: extract_skm_shard + drain_skm (NVLink reads inside)
-    t_count_ms = sum(prof[k][0] for k in count_kernels if k in prof) / args.steps
+        # p2p: extract_skm_shard stages by (owner, bin); bin_count (+ drain_heavy) reads the peers' staging over NVLink.
+        # drain_skm / extract_skm: the table variant of the exchange (k > 31, MFKC_VARIANT_HASH_TABLE)
+        count_kernels = ["extract_skm_shard", "bin_count", "drain_heavy", "extract_skm", "drain_skm"]
+    count_kernels = [k for k in count_kernels if k in prof and prof[k][1]]     # those that ran
+    t_count_ms = sum(prof[k][0] for k in count_kernels) / args.steps
     launches = sum(v[1] for v in prof.values())
     achieved = ALGO_BYTES_PER_KMER * kmers_per_step / (t_count_ms / 1e3) / 1e9 if t_count_ms else None
     gups_ms = kc.gups(8 << 30, 1 << 28, 1)
