@@ -287,9 +287,13 @@ int  mfkc_kset_components_fetch(mfkc_kset *hm, uint64_t *comp_offsets, int64_t *
 typedef struct mfkc_reader mfkc_reader;
 int  mfkc_reader_open(const char *path, mfkc_reader **out, char *err, size_t err_cap);
 /* Fill `bases` (cap_bases bytes) and `offsets` (cap_reads+1 entries) with the next kept reads;
- * *n_reads = 0 at end of file.  A read longer than cap_bases is an MFKC_E_BADARG. */
+ * *n_reads = 0 at end of file.  A read longer than cap_bases is an MFKC_E_BADARG that loses nothing: the read stays
+ * pending, mfkc_reader_pending_bases tells its length, and the next call with a buffer of at least that size returns it
+ * (the reference takes FASTA records of any length, e.g. a whole chromosome: FastaReader.java:54-108). */
 int  mfkc_reader_next(mfkc_reader *r, uint8_t *bases, size_t cap_bases, uint64_t *offsets,
                       uint32_t cap_reads, uint32_t *n_reads);
+/* length of the read the next mfkc_reader_next call starts with, if it is already known (0 otherwise) */
+int  mfkc_reader_pending_bases(const mfkc_reader *r, uint64_t *n_bases);
 /* counters: [0] = records seen, [1] = records dropped (N / phred 0) */
 int  mfkc_reader_counters(const mfkc_reader *r, uint64_t counters[2]);
 const char *mfkc_reader_error(const mfkc_reader *r);

@@ -125,6 +125,7 @@ SIGNATURES = {
     "mfkc_kset_components_fetch": (C.c_int, [C.c_void_p, u64p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mfkc_reader_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),
     "mfkc_reader_next": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "mfkc_reader_pending_bases": (C.c_int, [C.c_void_p, u64p]),
     "mfkc_reader_counters": (C.c_int, [C.c_void_p, u64p]),
     "mfkc_reader_error": (C.c_char_p, [C.c_void_p]),
     "mfkc_reader_name": (C.c_char_p, [C.c_void_p]),

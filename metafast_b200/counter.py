@@ -468,6 +468,12 @@ def read_file(path: str, batch_reads: int = 1 << 15, batch_bases: int = 1 << 24)
         n = C.c_uint32()
         while True:
             rc = lib.mfkc_reader_next(h, _ptr(bases), bases.nbytes, _ptr(offsets), batch_reads, C.byref(n))
+            if rc == _abi.E_BADARG:                       # one read longer than the buffer: it stays pending, take it with a larger one
+                pending = C.c_uint64()
+                lib.mfkc_reader_pending_bases(h, C.byref(pending))
+                if pending.value > bases.nbytes:
+                    bases = np.empty(pending.value + pending.value // 8, dtype=np.uint8)
+                    rc = lib.mfkc_reader_next(h, _ptr(bases), bases.nbytes, _ptr(offsets), batch_reads, C.byref(n))
             if rc != 0:
                 raise ReaderError(rc, lib.mfkc_reader_error(h).decode())
             if n.value == 0:

@@ -216,14 +216,29 @@ template <class F>
 void for_each_batch(mfkc_ctx *ctx, const std::string &file, F submit, mfkc_reader *r = nullptr) {
     info("Loading file %s...", base_name(file).c_str());
     if (!r) r = open_reader(file);
-    const size_t cap_bases = 256u << 20; const uint32_t cap_reads = 1u << 21;
+    const uint32_t cap_reads = 1u << 21;
     static thread_local void *h_bases = nullptr, *h_offs = nullptr; static thread_local int owner_gen = -1;      // pinned buffers die with their context
+    static thread_local size_t cap_bases = 0;
     if (owner_gen != g_ctx_gen) { h_bases = h_offs = nullptr; owner_gen = g_ctx_gen; }
-    if (!h_bases) { CK(ctx, mfkc_pinned_alloc(ctx, cap_bases, &h_bases)); CK(ctx, mfkc_pinned_alloc(ctx, ((size_t)cap_reads + 1) * 8, &h_offs)); }
+    if (!h_bases) {
+        cap_bases = 256u << 20;
+        if (const char *e = getenv("MFKC_CLI_BATCH_BASES")) cap_bases = std::max<size_t>(64, strtoull(e, nullptr, 10));      // small batches: tests
+        CK(ctx, mfkc_pinned_alloc(ctx, cap_bases, &h_bases)); CK(ctx, mfkc_pinned_alloc(ctx, ((size_t)cap_reads + 1) * 8, &h_offs));
+    }
     unsigned long long reads = 0;
     for (;;) {
         uint32_t n = 0;
-        const int rc = mfkc_reader_next(r, (uint8_t *)h_bases, cap_bases, (uint64_t *)h_offs, cap_reads, &n);
+        int rc = mfkc_reader_next(r, (uint8_t *)h_bases, cap_bases, (uint64_t *)h_offs, cap_reads, &n);
+        uint64_t pending = 0;
+        if (rc == MFKC_E_BADARG && mfkc_reader_pending_bases(r, &pending) == MFKC_OK && pending > cap_bases) {
+            // one record longer than the batch buffer (a chromosome-sized FASTA record; the reference takes any length):
+            // the reader kept it, take it with a larger buffer
+            CK(ctx, mfkc_pinned_free(ctx, h_bases));
+            h_bases = nullptr;
+            cap_bases = (size_t)pending + (pending >> 3);
+            CK(ctx, mfkc_pinned_alloc(ctx, cap_bases, &h_bases));
+            rc = mfkc_reader_next(r, (uint8_t *)h_bases, cap_bases, (uint64_t *)h_offs, cap_reads, &n);
+        }
         if (rc != MFKC_OK) die("%s: %s", file.c_str(), mfkc_reader_error(r));
         if (!n) break;
         submit((const uint8_t *)h_bases, (const uint64_t *)h_offs, n);

@@ -405,6 +405,24 @@ static size_t last_boundary(const char *p, size_t n, bool fastq, bool eof) {
     return cut;
 }
 
+// FASTA flavour with a resume point: the last line start in [max(from, 1), n) that opens a header ('>' or ';'), 0 = none.
+// Positions below `from` are known to hold none (an earlier call on a shorter prefix returned 0), so a record of L bytes
+// costs O(L) to step over while the block is widened chunk by chunk, not O(L^2 / chunk).
+static size_t fasta_boundary_from(const char *p, size_t from, size_t n) {
+    if (from < 1) from = 1;
+    size_t end = n;
+    while (end > from) {
+        const char *a = (const char *)memrchr(p + from, '>', end - from);
+        const char *b = (const char *)memrchr(p + from, ';', end - from);
+        const char *q = !a ? b : !b ? a : (a > b ? a : b);
+        if (!q) return 0;
+        const size_t i = (size_t)(q - p);
+        if (p[i - 1] == '\n' || p[i - 1] == '\r') return i;
+        end = i;
+    }
+    return 0;
+}
+
 struct mfkc_reader {
     std::string path, name, err;
     Format fmt = F_UNKNOWN;
@@ -514,13 +532,14 @@ struct mfkc_reader {
             size_t pos = 0;
             bool more = true;
             while (more) {
-                size_t want = kChunkText, cut = 0;
+                size_t want = kChunkText, cut = 0, scanned = 0;
                 bool eof = false;
                 for (;;) {                                      // widen until the block holds at least one whole record
                     const size_t have = std::min(want, map_len - pos);
                     eof = pos + have == map_len;
-                    cut = eof ? have : last_boundary(base + pos, have, is_fastq(), false);
+                    cut = eof ? have : is_fastq() ? last_boundary(base + pos, have, true, false) : fasta_boundary_from(base + pos, scanned, have);
                     if (cut || eof) break;
+                    scanned = have;
                     want += kChunkText;
                 }
                 auto ch = fresh_chunk();
@@ -562,7 +581,7 @@ struct mfkc_reader {
             if (!carry.empty()) memcpy(ch->text.data(), carry.data(), carry.size());
             size_t have = carry.size();
             carry.clear();
-            size_t cut = 0;
+            size_t cut = 0, scanned = 0;
             for (;;) {                                          // read until the block holds at least one whole record
                 if (ch->text.size() < have + kChunkText) ch->text.resize(have + kChunkText);
                 int r;
@@ -574,8 +593,9 @@ struct mfkc_reader {
                 if (r < 0) { io_error = true; eof = true; }
                 else if (r == 0) eof = true;
                 else have += (size_t)r;
-                cut = eof ? have : last_boundary(ch->text.data(), have, is_fastq(), false);
+                cut = eof ? have : is_fastq() ? last_boundary(ch->text.data(), have, true, false) : fasta_boundary_from(ch->text.data(), scanned, have);
                 if (cut || eof) break;
+                scanned = have;
             }
             if (!eof) carry.assign(ch->text.data() + cut, ch->text.data() + have);
             ch->tptr = ch->text.data(); ch->tlen = cut;
@@ -678,6 +698,16 @@ extern "C" int mfkc_library_name(const char *path, char *out, size_t cap) {
     const Format f = detect_format(path);
     if (f == F_UNKNOWN || f == F_OTHER) { out[0] = 0; return MFKC_E_FORMAT; }
     snprintf(out, cap, "%s", library_name(path, f).c_str());
+    return MFKC_OK;
+}
+
+extern "C" int mfkc_reader_pending_bases(const mfkc_reader *r, uint64_t *n_bases) {
+    if (!r || !n_bases) return MFKC_E_BADARG;
+    *n_bases = 0;
+    if (r->n_threads > 1) {
+        if (r->cur_chunk && r->cur_read + 1 < r->cur_chunk->offs.size())
+            *n_bases = r->cur_chunk->offs[r->cur_read + 1] - r->cur_chunk->offs[r->cur_read];
+    } else if (r->have_cur) *n_bases = r->cur.size();
     return MFKC_OK;
 }
 

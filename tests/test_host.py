@@ -232,6 +232,48 @@ def test_parallel_reader_equals_serial(built, tmp_path, monkeypatch):
             assert want[0] == "error"
 
 
+def test_record_longer_than_the_batch_buffer(built, tmp_path, monkeypatch):
+    """The reference takes FASTA records of any length (FastaReader.java:54-108).  mfkc_reader_next keeps a read that
+    does not fit the caller's buffer pending and tells its length; the same reads come out whatever the buffer, the
+    chunk size and the number of threads, and a record that spans dozens of producer chunks is stepped over once."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    seq = lambda n: "".join(rng.choice(list("ACGT"), n))
+    long1, long2 = seq(300_000), seq(90_001)
+    recs = [seq(50), long1, seq(70), seq(1), long2]
+    text = "".join(">r%d some; text > here\n" % i + "\n".join(r[j:j + 60] for j in range(0, len(r), 60)) + "\n" for i, r in enumerate(recs))
+    fa = tmp_path / "long.fa"
+    fa.write_bytes(text.encode())
+    fq = tmp_path / "long.fastq"
+    fq.write_bytes("".join("@r%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)) for i, r in enumerate(recs)).encode())
+    lib = m.load()
+    for path in (fa, fq):
+        for threads, chunk in ((1, None), (3, 4096), (4, None)):
+            monkeypatch.setenv("MFKC_READER_THREADS", str(threads))
+            if chunk:
+                monkeypatch.setenv("MFKC_READER_CHUNK", str(chunk))
+            else:
+                monkeypatch.delenv("MFKC_READER_CHUNK", raising=False)
+            got = []
+            for b, o in m.read_file(str(path), batch_reads=8, batch_bases=1000):
+                s = b.tobytes().decode()
+                got += [s[int(o[i]):int(o[i + 1])] for i in range(len(o) - 1)]
+            assert got == recs, (path.name, threads, chunk)
+            # the raw protocol: error, pending length, retry
+            h, err, n = C.c_void_p(), C.create_string_buffer(512), C.c_uint32()
+            assert lib.mfkc_reader_open(str(path).encode(), C.byref(h), err, 512) == 0
+            small = np.empty(100, dtype=np.uint8); offs = np.empty(9, dtype=np.uint64); pend = C.c_uint64()
+            vp = lambda a: a.ctypes.data_as(C.c_void_p)
+            assert lib.mfkc_reader_next(h, vp(small), small.nbytes, vp(offs), 8, C.byref(n)) == 0 and n.value == 1     # r0 alone fits
+            assert lib.mfkc_reader_next(h, vp(small), small.nbytes, vp(offs), 8, C.byref(n)) == _abi.E_BADARG
+            assert b"longer than the batch buffer" in lib.mfkc_reader_error(h)
+            assert lib.mfkc_reader_pending_bases(h, C.byref(pend)) == 0 and pend.value == len(long1)
+            big = np.empty(pend.value, dtype=np.uint8)
+            assert lib.mfkc_reader_next(h, vp(big), big.nbytes, vp(offs), 8, C.byref(n)) == 0 and n.value == 1
+            assert big.tobytes().decode() == long1
+            lib.mfkc_reader_close(h)
+
+
 # ---------------------------------------------------------------- the main caller's remaining stages (matrix-builder)
 def _emulated_components(hm, k, b1, b2, grid=1):
     """tests/emu/cc_emu.cpp: the kernels of metafast_b200/csrc/components.cuh compiled for the host"""
