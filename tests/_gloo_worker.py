@@ -189,3 +189,32 @@ def run_p2p_lanes(rank, world, port, out_dir):
         assert "boom" in str(e)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def run_bench_fake_device(rank, world, port, out_dir):
+    """bench.py's N > 1 control flow on CPU: one process per "GPU", gloo in place of NCCL, tests/_fake_device.py in place
+    of the device (tests/test_bench_dry_run.py)."""
+    import contextlib
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MFKC_FAKE_SHARE_DIR=out_dir, MFKC_BENCH_NO_INGEST="1", MFKC_BENCH_VERIFY_SHARD_READS="1500",
+                      MFKC_BENCH_LANE_TIMEOUT_S="60")
+    for k in ("MFKC_BENCH_VARIANT", "MFKC_BENCH_NO_VERIFY", "MFKC_EXCHANGE", "MFKC_BENCH_E2E_SERIAL"):
+        os.environ.pop(k, None)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device = lambda *a, **k: None
+    torch.cuda.synchronize = lambda *a, **k: None
+    real_init, real_tensor = dist.init_process_group, torch.tensor
+    dist.init_process_group = lambda backend=None, **kw: real_init("gloo", rank=rank, world_size=world)
+    torch.tensor = lambda *a, **kw: real_tensor(*a, **{k: v for k, v in kw.items() if k != "device"})
+    import bench
+    import metafast_b200.sharded                                 # noqa: F401  (resolved before the package is swapped)
+    from tests import _fake_device
+    sys.modules["metafast_b200"] = _fake_device.module()
+    bench.N_READS, bench.BATCH_READS, bench.B_THRESHOLD = 3000, 1000, 0
+    sys.argv = ["bench.py", "--gpus", str(world), "--steps", "5", "--warmup", "3"]
+    with open(os.path.join(out_dir, "bench_rank%d.out" % rank), "w") as f, contextlib.redirect_stdout(f):
+        bench.main()
+    calls = _fake_device.FakeCounter.calls
+    with open(os.path.join(out_dir, "calls_rank%d.txt" % rank), "w") as f:
+        f.write("\n".join(" ".join(str(x) for x in c) for c in calls))
