@@ -30,6 +30,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <memory>
 #include <vector>
 
 #include "../../include/mfkc.h"
@@ -300,7 +301,7 @@ std::string count_sample(mfkc_ctx *ctx, int k, int b, const std::vector<std::str
 std::string count_sample_sharded(std::vector<mfkc_ctx *> &ctxs, int k, int b, const std::vector<std::string> &files, const std::string &name,
                                  const std::string &out_dir, const std::string &st_dir, uint64_t expected_kmers) {
     const uint32_t G = (uint32_t)ctxs.size();
-    std::vector<std::vector<uint8_t>> parts(G);
+    std::vector<std::unique_ptr<uint8_t[]>> parts(G);         // (not vectors: no zero-fill of gigabytes that are overwritten right away)
     std::vector<uint64_t> n_rec(G, 0), hist(MFKC_HIST_BINS, 0), hs(MFKC_HIST_BINS);
     uint64_t st_sum[6] = {0, 0, 0, 0, 0, 0}, good = 0;
     for (int attempt = 0;; attempt++) {
@@ -337,11 +338,11 @@ std::string count_sample_sharded(std::vector<mfkc_ctx *> &ctxs, int k, int b, co
         mfkc_ctx *c = ctxs[r];
         uint64_t g = 0;
         CK(c, mfkc_emit_begin(c, b, &g));
-        const size_t rs = k > 31 ? 18 : 10;
-        parts[r].resize(g * rs);
-        for (size_t pos = 0; pos < parts[r].size();) {
+        const size_t rs = k > 31 ? 18 : 10, part_bytes = (size_t)g * rs;
+        parts[r].reset(new uint8_t[part_bytes + 1]);
+        for (size_t pos = 0; pos < part_bytes;) {
             size_t w = 0;
-            CK(c, mfkc_emit_next(c, parts[r].data() + pos, parts[r].size() - pos, &w));
+            CK(c, mfkc_emit_next(c, parts[r].get() + pos, part_bytes - pos, &w));
             if (!w) break;
             pos += w;
         }
@@ -354,13 +355,14 @@ std::string count_sample_sharded(std::vector<mfkc_ctx *> &ctxs, int k, int b, co
     mkdirs(out_dir); mkdirs(st_dir);
     const size_t rs = k > 31 ? 18 : 10;
     const std::string out_file = out_dir + "/" + name + (k > 31 ? ".kmers128.bin" : ".kmers.bin"), st_file = st_dir + "/" + name + ".stat.txt";
-    std::vector<uint8_t> merged(good * rs);
+    const size_t merged_bytes = (size_t)good * rs;
+    std::unique_ptr<uint8_t[]> merged(new uint8_t[merged_bytes + 1]);      // first touched by the merge threads, slice by slice
     std::vector<const uint8_t *> pp(G);
-    for (uint32_t r = 0; r < G; r++) pp[r] = parts[r].data();
-    if (mfkc_merge_records(pp.data(), n_rec.data(), G, (uint32_t)rs, merged.data(), 0) != MFKC_OK) die("record merge failed");
+    for (uint32_t r = 0; r < G; r++) pp[r] = parts[r].get();
+    if (mfkc_merge_records(pp.data(), n_rec.data(), G, (uint32_t)rs, merged.get(), 0) != MFKC_OK) die("record merge failed");
     FILE *f = fopen(out_file.c_str(), "wb");
     if (!f) die("Can't write %s", out_file.c_str());
-    if (!merged.empty() && fwrite(merged.data(), 1, merged.size(), f) != merged.size()) die("Can't write %s", out_file.c_str());
+    if (merged_bytes && fwrite(merged.get(), 1, merged_bytes, f) != merged_bytes) die("Can't write %s", out_file.c_str());
     fclose(f);
     if (mfkc_write_stat_file(st_file.c_str(), hist.data()) != MFKC_OK) die("Can't write %s", st_file.c_str());
     report_sample(k, st_sum[0], good, out_file);

@@ -901,46 +901,53 @@ uint64_t lower_bound_rec(const MergePart &part, const uint8_t *key, uint32_t rs,
     return lo;
 }
 
-void merge_slice(const std::vector<MergePart> &parts, const std::vector<uint64_t> &b, const std::vector<uint64_t> &e, uint32_t rs, uint32_t kb, uint8_t *out) {
-    const size_t P = parts.size();
-    std::vector<uint64_t> cur(b);
-    // small P (<= 16 shards): a linear scan for the minimum beats a heap
-    if (kb == 8) {
-        std::vector<uint64_t> head(P);
-        auto key_at = [&](size_t i, uint64_t idx) { uint64_t v; memcpy(&v, parts[i].p + idx * rs, 8); return __builtin_bswap64(v); };
-        size_t live = 0;
-        for (size_t i = 0; i < P; i++) if (cur[i] < e[i]) { head[i] = key_at(i, cur[i]); live++; }
-        while (live > 1) {
-            size_t best = P, second = P;                              // smallest head (ties: lowest part), and the next one
-            for (size_t i = 0; i < P; i++) {
-                if (cur[i] >= e[i]) continue;
-                if (best == P || head[i] < head[best]) { second = best; best = i; }
-                else if (second == P || head[i] < head[second]) second = i;
-            }
-            // the run of `best` that precedes the head of every other part
-            const uint64_t limit = head[second];
-            uint64_t c = cur[best] + 1;
-            while (c < e[best]) {
-                const uint64_t kk = key_at(best, c);
-                if (kk < limit || (kk == limit && best < second)) c++; else break;
-            }
-            memcpy(out, parts[best].p + cur[best] * rs, (size_t)(c - cur[best]) * rs);
-            out += (size_t)(c - cur[best]) * rs;
-            cur[best] = c;
-            if (c < e[best]) head[best] = key_at(best, c); else live--;
-        }
-        for (size_t i = 0; i < P; i++) if (cur[i] < e[i]) { memcpy(out, parts[i].p + cur[i] * rs, (size_t)(e[i] - cur[i]) * rs); out += (size_t)(e[i] - cur[i]) * rs; }
-        return;
-    }
-    for (;;) {
-        size_t best = P;
-        for (size_t i = 0; i < P; i++)
-            if (cur[i] < e[i] && (best == P || key_cmp(parts[i].p + cur[i] * rs, parts[best].p + cur[best] * rs, kb) < 0)) best = i;
-        if (best == P) break;
-        memcpy(out, parts[best].p + cur[best] * rs, rs);
-        out += rs; cur[best]++;
-    }
+// big-endian key of a record as a native integer (8-byte keys: k <= 31; 16-byte keys: k > 31)
+template <class K> inline K load_key(const uint8_t *p);
+template <> inline uint64_t load_key<uint64_t>(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return __builtin_bswap64(v); }
+typedef unsigned __int128 u128_t;
+template <> inline u128_t load_key<u128_t>(const uint8_t *p) {
+    uint64_t hi, lo; memcpy(&hi, p, 8); memcpy(&lo, p + 8, 8);
+    return ((u128_t)__builtin_bswap64(hi) << 64) | __builtin_bswap64(lo);
 }
+
+// One slice of the key range: records [b[i], e[i]) of every part into `out`.  The shards split the keys by a hash, so
+// the parts interleave record by record and the cost is what is spent per RECORD: the heads' keys live in a small
+// array as native integers, the smallest is found by a branch-free scan (compare + conditional moves; ties go to the
+// lowest part, so equal keys -- never produced by the shards -- would keep part order), the record moves with two
+// fixed-size copies.  An exhausted part leaves the array (order kept); the last part standing is one memcpy.
+// One slice of the key range: records [b[i], e[i]) of every part into `out`.  The shards split the keys by a hash, so
+// the parts interleave record by record and the cost is what is spent per RECORD: the heads' keys live in a small
+// array as native integers, the smallest is found by a branch-free scan (compare + conditional moves; ties go to the
+// lowest part, so equal keys -- never produced by the shards -- would keep part order), the record moves with two
+// fixed-size copies.  An exhausted part leaves the array (order kept); the last part standing is one memcpy.
+// (Tried and dropped, both slower here: a balanced compare tree over 8 / 16 padded slots, and register-resident heads
+// with the next key loaded one pop ahead.)
+template <class K, uint32_t RS>
+void merge_slice_t(const std::vector<MergePart> &parts, const std::vector<uint64_t> &b, const std::vector<uint64_t> &e, uint8_t *out) {
+    constexpr uint32_t KB = RS - 2;
+    const size_t P = parts.size();
+    std::vector<K> hk(P);
+    std::vector<const uint8_t *> hp(P), he(P);
+    size_t n = 0;
+    for (size_t i = 0; i < P; i++)
+        if (b[i] < e[i]) { hp[n] = parts[i].p + b[i] * RS; he[n] = parts[i].p + e[i] * RS; hk[n] = load_key<K>(hp[n]); n++; }
+    K *k = hk.data();
+    while (n > 1) {
+        size_t best = 0; K bk = k[0];
+        for (size_t i = 1; i < n; i++) { const bool lt = k[i] < bk; bk = lt ? k[i] : bk; best = lt ? i : best; }
+        const uint8_t *src = hp[best];
+        memcpy(out, src, KB); memcpy(out + KB, src + KB, 2);
+        out += RS; src += RS;
+        hp[best] = src;
+        if (__builtin_expect(src != he[best], 1)) k[best] = load_key<K>(src);
+        else {
+            for (size_t i = best + 1; i < n; i++) { k[i - 1] = k[i]; hp[i - 1] = hp[i]; he[i - 1] = he[i]; }
+            n--;
+        }
+    }
+    if (n == 1) memcpy(out, hp[0], (size_t)(he[0] - hp[0]));
+}
+
 }  // namespace
 
 extern "C" int mfkc_merge_records(const uint8_t *const *parts_in, const uint64_t *n_records, uint32_t n_parts, uint32_t record_size,
@@ -971,7 +978,11 @@ extern "C" int mfkc_merge_records(const uint8_t *const *parts_in, const uint64_t
     for (uint32_t j = 1; j <= T; j++) { uint64_t s = 0; for (size_t i = 0; i < parts.size(); i++) s += cut[j][i]; out_off[j] = s; }
     std::vector<std::thread> th;
     for (uint32_t j = 0; j < T; j++) {
-        auto work = [&, j] { merge_slice(parts, cut[j], cut[j + 1], record_size, kb, out + out_off[j] * record_size); };
+        auto work = [&, j] {
+            uint8_t *o = out + out_off[j] * record_size;
+            if (record_size == 10) merge_slice_t<uint64_t, 10>(parts, cut[j], cut[j + 1], o);
+            else merge_slice_t<u128_t, 18>(parts, cut[j], cut[j + 1], o);
+        };
         if (T == 1) work(); else th.emplace_back(work);
     }
     for (auto &t : th) t.join();

@@ -842,3 +842,17 @@ def test_native_record_merge(built, record_size, n_parts, threads):
     got = merge_sorted_records(parts, record_size, threads)
     assert got == be.tobytes()
     assert merge_sorted_records([b""] * n_parts, record_size) == b""
+
+
+def test_native_record_merge_ties_and_extreme_keys(built):
+    """equal keys (the shards never produce them) keep part order; the all-ones and the zero key are ordinary keys"""
+    from metafast_b200.sharded import merge_sorted_records
+    rec = lambda key, tag: int(key).to_bytes(8, "big") + bytes([0, tag])
+    top = 2 ** 64 - 1
+    a = [rec(0, 1), rec(5, 1), rec(5, 2), rec(top, 1)]
+    b = [rec(0, 3), rec(5, 3), rec(7, 3), rec(top, 3), rec(top, 4)]
+    c = [rec(6, 5)]
+    want = [rec(0, 1), rec(0, 3), rec(5, 1), rec(5, 2), rec(5, 3), rec(6, 5), rec(7, 3), rec(top, 1), rec(top, 3), rec(top, 4)]
+    for threads in (1, 0):
+        assert merge_sorted_records([b"".join(a), b"".join(b), b"".join(c)], 10, threads) == b"".join(want)
+        assert merge_sorted_records([b"".join(a), b"", b"".join(c)], 10, threads) == b"".join(sorted(a + c, key=lambda r: r[:8]))
