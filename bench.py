@@ -851,16 +851,21 @@ def main():
     achieved = ALGO_BYTES_PER_KMER * kmers_per_step / (t_count_ms / 1e3) / 1e9 if t_count_ms else None
     gups_ms = kc.gups(8 << 30, 1 << 28, 1)
     gups_rate = (1 << 28) / (gups_ms / 1e3)
+    traffic = load_traffic() if world == 1 else None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-        "traffic": load_traffic() if world == 1 else None, "peak_source": peak_src,
+        "traffic": traffic, "peak_source": peak_src,
+        # what the DRAM really does: ncu bytes of the counting kernels / their time, as a fraction of the same peak
+        "traffic_frac_of_peak": traffic / (t_count_ms / 1e3) / 1e9 / peak if traffic and t_count_ms else None,
         "kernel": "+".join(count_kernels), "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER,
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
         "kernel_launches_per_step": {k: v[1] / args.steps for k, v in prof.items() if v[1]},
         "gups_random_sector_upserts_per_s": gups_rate,
         "gups_algorithmic_gbs": gups_rate * 64 / 1e9,
         "frac_of_gups": (kmers_per_step / (t_count_ms / 1e3)) / gups_rate if t_count_ms else None,
-        "note": "achieved = 64.3125 B per k-mer instance (SURVEY 8d) / summed CUDA-event time of the counting kernels; "
+        "note": "achieved = 64.3125 B per k-mer instance (SURVEY 8d: one random 32 B sector read + written per instance) / summed "
+                "CUDA-event time of the counting kernels; the bin-local design does not move those bytes (traffic = ncu DRAM bytes "
+                "of the same kernels per step), it is bound by instruction issue and shared-memory atomics (DESIGN 4); "
                 "gups_* = dependent 16 B load + red.add on random 32 B sectors of an 8 GiB table, measured in this run",
     }
     cpu = None

@@ -27,6 +27,7 @@ def test_bench_main_runs_through_on_a_fake_device(built, monkeypatch, serial_e2e
         monkeypatch.delenv(k, raising=False)
     if serial_e2e:
         monkeypatch.setenv("MFKC_BENCH_E2E_SERIAL", "1")
+        monkeypatch.setattr(bench, "load_traffic", lambda: 19.1e9)      # as on the real workload: a committed ncu figure
     else:
         monkeypatch.delenv("MFKC_BENCH_E2E_SERIAL", raising=False)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "4", "--warmup", "3"])
@@ -50,7 +51,10 @@ def test_bench_main_runs_through_on_a_fake_device(built, monkeypatch, serial_e2e
     assert ("one sample after the other" in e["mode"]) == serial_e2e
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["kernel"] == "extract_skm+bin_count" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
-    assert r["traffic"] is None                                  # the committed ncu traffic belongs to the 20 M-read workload only
+    if serial_e2e:
+        assert r["traffic"] == 19.1e9 and r["traffic_frac_of_peak"] > 0
+    else:
+        assert r["traffic"] is None and r["traffic_frac_of_peak"] is None     # the committed ncu traffic belongs to the 20 M-read workload only
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0
     v = d["verified"]
