@@ -234,7 +234,7 @@ void for_each_batch(mfkc_ctx *ctx, const std::string &file, F submit, mfkc_reade
         if (rc == MFKC_E_BADARG && mfkc_reader_pending_bases(r, &pending) == MFKC_OK && pending > cap_bases) {
             // one record longer than the batch buffer (a chromosome-sized FASTA record; the reference takes any length):
             // the reader kept it, take it with a larger buffer
-            CK(ctx, mfkc_pinned_free(ctx, h_bases));
+            (void)mfkc_pinned_free(ctx, h_bases);      // (a buffer that another context of this thread allocated stays with it until it is destroyed)
             h_bases = nullptr;
             cap_bases = (size_t)pending + (pending >> 3);
             CK(ctx, mfkc_pinned_alloc(ctx, cap_bases, &h_bases));
