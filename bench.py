@@ -697,9 +697,13 @@ def main():
     # ---- parity at size, before anything is timed (the oracle is the checker here, never the thing measured)
     verified = None
     if not os.environ.get("MFKC_BENCH_NO_VERIFY"):
-        verified = verify_at_size(m, kc, step_device, dict(world=world, rank=rank, local_rank=local_rank, dist=dist, variant=variant,
-                                                          d_bases=d_bases, d_offs=d_offs, n_reads=n_reads, kmers_ub=kmers_ub,
-                                                          sharded=sharded if world > 1 else None, exchange=exchange))
+        try:
+            verified = verify_at_size(m, kc, step_device, dict(world=world, rank=rank, local_rank=local_rank, dist=dist, variant=variant,
+                                                              d_bases=d_bases, d_offs=d_offs, n_reads=n_reads, kmers_ub=kmers_ub,
+                                                              sharded=sharded if world > 1 else None, exchange=exchange))
+        except Exception as ex:              # the checker broke (not: the check failed): say so in the line, still measure
+            verified = {"checker_error": repr(ex)[:300]}
+            sys.stderr.write("bench.py: the verification could not run: %r\n" % (ex,))
         if rank == 0 and not all(v for k_, v in verified.items() if isinstance(v, bool)):
             sys.stderr.write("bench.py: VERIFICATION FAILED: %s\n" % json.dumps(verified))
 
