@@ -225,7 +225,9 @@ static int sync_all(mfkc_ctx *ctx) {
 }
 
 static int read_counters(mfkc_ctx *ctx) {      // requires streams idle
-    CU_TRY(cudaMemcpy(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost));
+    // (not cudaMemcpy: the legacy default stream is shared by every context of the process)
+    CU_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
     return MFKC_OK;
 }
 
@@ -1041,13 +1043,15 @@ static int overflow_records(mfkc_ctx *ctx, uint64_t *n) {
         const uint64_t n_seg = (uint64_t)G * ctx->p2p_B;
         for (uint32_t i = 0; i < G; i++) {
             unsigned int c = 0;
-            CU_TRY(cudaMemcpy(&c, ctx->p2p_peer_cursor[i] + n_seg, sizeof c, cudaMemcpyDeviceToHost));
+            CU_TRY(cudaMemcpyAsync(&c, ctx->p2p_peer_cursor[i] + n_seg, sizeof c, cudaMemcpyDeviceToHost, ctx->compute));
+            CU_TRY(cudaStreamSynchronize(ctx->compute));
             *n += std::min<uint64_t>(c, ctx->p2p_ovf_cap);
         }
         return MFKC_OK;
     }
     unsigned int c = 0;
-    CU_TRY(cudaMemcpy(&c, &ctx->d_binctl->ovf_cursor, sizeof c, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpyAsync(&c, &ctx->d_binctl->ovf_cursor, sizeof c, cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
     *n = std::min<uint64_t>(c, ctx->os_ovf_cap);
     return MFKC_OK;
 }
@@ -2426,7 +2430,8 @@ extern "C" int mfkc_fc_features(mfkc_ctx *ctx, int64_t threshold, int64_t *vec, 
     if (!ctx->fc_tab) return fail(ctx, MFKC_E_STATE, "no components loaded");
     CU_TRY(cudaSetDevice(ctx->device));
     TRY(sync_all(ctx));
-    CU_TRY(cudaMemcpy(ctx->h_ctr, ctx->d_fc_ctr, sizeof(Counters), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpyAsync(ctx->h_ctr, ctx->d_fc_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->compute));
+    CU_TRY(cudaStreamSynchronize(ctx->compute));
     if (ctx->h_ctr->bad_chars) return fail(ctx, MFKC_E_FORMAT, "Incorrect nucleotide char in submitted reads (only AaCcGgTt are accepted)");
     const uint32_t nc = ctx->fc_ncomp;
     if (nc == 0) return MFKC_OK;
