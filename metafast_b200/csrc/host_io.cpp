@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <atomic>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -347,23 +348,34 @@ struct IngestChunk {
 // the block is not of that shape (CRLF files, blank lines, ...): the exact machine then decides.
 static bool fastq_boundary_by_line_count(const char *p, size_t n, size_t *cut) {
     if (!n || p[0] == '\n') return false;
-    size_t lines = 0, i = 0;
-    unsigned prev_nl = 0;                                       // was the byte before position i a '\n'?
+    size_t lines = 0, i = 1;                                    // byte 0 is not a newline: every position below has a left neighbour
+    if (p[0] == '\r') return false;
 #if defined(__x86_64__)
-    const __m128i nl = _mm_set1_epi8('\n'), cr = _mm_set1_epi8('\r');
-    for (; i + 16 <= n; i += 16) {
-        const __m128i v = _mm_loadu_si128((const __m128i *)(p + i));
-        if (_mm_movemask_epi8(_mm_cmpeq_epi8(v, cr))) return false;
-        const unsigned m = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, nl));
-        if (m & ((m << 1) | prev_nl)) return false;             // "\n\n": an empty line
-        prev_nl = (m >> 15) & 1u;
-        lines += (size_t)__builtin_popcount(m);
+    // Plain SSE2, no movemask / popcount per vector (the baseline x86-64 target has no popcnt instruction: the builtin is
+    // a dozen ALU operations): newlines are counted in 16 byte-wide counters (compare result = -1 per hit), folded with
+    // psadbw every 255 vectors; "\n\n" = a newline whose left neighbour is one (second load, shifted by one byte);
+    // '\r' hits are ORed together.  Both are looked at when the counters are folded.
+    const __m128i nl = _mm_set1_epi8('\n'), cr = _mm_set1_epi8('\r'), zero = _mm_setzero_si128();
+    __m128i bad = zero;
+    while (i + 16 <= n) {
+        __m128i acc = zero;
+        const size_t stop = std::min(n - 15, i + 255 * 16);      // i + 16 <= n  <=>  i < n - 15
+        for (; i < stop; i += 16) {
+            const __m128i v = _mm_loadu_si128((const __m128i *)(p + i));
+            const __m128i left = _mm_loadu_si128((const __m128i *)(p + i - 1));
+            const __m128i is_nl = _mm_cmpeq_epi8(v, nl);
+            bad = _mm_or_si128(bad, _mm_or_si128(_mm_cmpeq_epi8(v, cr), _mm_and_si128(is_nl, _mm_cmpeq_epi8(left, nl))));
+            acc = _mm_sub_epi8(acc, is_nl);
+        }
+        const __m128i sums = _mm_sad_epu8(acc, zero);
+        lines += (size_t)_mm_cvtsi128_si64(sums) + (size_t)_mm_cvtsi128_si64(_mm_unpackhi_epi64(sums, sums));
+        if (_mm_movemask_epi8(bad)) return false;
     }
 #endif
     for (; i < n; i++) {
         const char c = p[i];
         if (c == '\r') return false;
-        if (c == '\n') { if (prev_nl) return false; prev_nl = 1; lines++; } else prev_nl = 0;
+        if (c == '\n') { if (p[i - 1] == '\n') return false; lines++; }
     }
     if (lines < 4) { *cut = 0; return true; }
     // the cut is just behind the newline that ends line 4 * (lines / 4): step back over the surplus newlines
@@ -371,6 +383,43 @@ static bool fastq_boundary_by_line_count(const char *p, size_t n, size_t *cut) {
     for (size_t r = lines & 3; r; r--) q = (const char *)memrchr(p, '\n', (size_t)(q - p));
     *cut = (size_t)(q - p) + 1;
     return true;
+}
+
+// Scout's view of one block [lo, hi) of a text that starts at `base`: number of '\n' in it, or -1 when the block holds a
+// '\r' or an empty line ("\n\n", also across its left edge; a '\n' as the very first byte of the text) -- then the exact
+// state machine has to decide.  Same vector body as above.
+static int64_t count_clean_newlines(const char *base, size_t lo, size_t hi) {
+    const char *p = base;
+    size_t i = lo, lines = 0;
+    if (i == 0) {
+        if (hi == 0) return 0;
+        if (p[0] == '\n' || p[0] == '\r') return -1;
+        i = 1;
+    }
+#if defined(__x86_64__)
+    const __m128i nl = _mm_set1_epi8('\n'), cr = _mm_set1_epi8('\r'), zero = _mm_setzero_si128();
+    __m128i bad = zero;
+    while (i + 16 <= hi) {
+        __m128i acc = zero;
+        const size_t stop = std::min(hi - 15, i + 255 * 16);
+        for (; i < stop; i += 16) {
+            const __m128i v = _mm_loadu_si128((const __m128i *)(p + i));
+            const __m128i left = _mm_loadu_si128((const __m128i *)(p + i - 1));
+            const __m128i is_nl = _mm_cmpeq_epi8(v, nl);
+            bad = _mm_or_si128(bad, _mm_or_si128(_mm_cmpeq_epi8(v, cr), _mm_and_si128(is_nl, _mm_cmpeq_epi8(left, nl))));
+            acc = _mm_sub_epi8(acc, is_nl);
+        }
+        const __m128i sums = _mm_sad_epu8(acc, zero);
+        lines += (size_t)_mm_cvtsi128_si64(sums) + (size_t)_mm_cvtsi128_si64(_mm_unpackhi_epi64(sums, sums));
+        if (_mm_movemask_epi8(bad)) return -1;
+    }
+#endif
+    for (; i < hi; i++) {
+        const char c = p[i];
+        if (c == '\r') return -1;
+        if (c == '\n') { if (p[i - 1] == '\n') return -1; lines++; }
+    }
+    return (int64_t)lines;
 }
 
 // offset of the last record boundary in [p, p+n) (0 = none); `eof`: the text ends here
@@ -531,6 +580,50 @@ struct mfkc_reader {
             const char *base = (const char *)map;
             size_t pos = 0;
             bool more = true;
+            // FASTQ: finding the cuts is the one serial pass over the text (a 4-line record ends where the newline count
+            // is a multiple of 4, so the cut behind a block needs the number of newlines in front of it).  The counting is
+            // handed to a few scout threads, block by block; this thread adds the counts up and steps back over
+            // (count mod 4) newlines from each block end.  A block with a '\r' or an empty line ends the fast path: the
+            // exact line machine takes over at the last cut, as it does for the tail of the file.
+            int n_scouts = is_fastq() && map_len > 4 * kChunkText ? std::max(1, std::min(4, n_threads / 3)) : 0;
+            if (const char *e = getenv("MFKC_READER_SCOUTS")) n_scouts = is_fastq() ? std::max(0, atoi(e)) : 0;
+            if (n_scouts) {
+                const size_t C = kChunkText, nb = (map_len + C - 1) / C;
+                std::unique_ptr<std::atomic<int64_t>[]> cnt(new std::atomic<int64_t>[nb]);
+                for (size_t b = 0; b < nb; b++) cnt[b].store(-2, std::memory_order_relaxed);       // -2 = not counted yet
+                std::atomic<size_t> next_block{0};
+                std::atomic<bool> quit{false};
+                std::vector<std::thread> scouts;
+                for (int t = 0; t < n_scouts; t++)
+                    scouts.emplace_back([&] {
+                        for (;;) {
+                            const size_t b = next_block.fetch_add(1);
+                            if (b >= nb || quit.load(std::memory_order_relaxed)) return;
+                            cnt[b].store(count_clean_newlines(base, b * C, std::min(map_len, (b + 1) * C)), std::memory_order_release);
+                        }
+                    });
+                uint64_t lines = 0;
+                bool open_queue = true;
+                for (size_t b = 0; b + 1 < nb && open_queue; b++) {               // (the last block belongs to the tail)
+                    int64_t c;
+                    while ((c = cnt[b].load(std::memory_order_acquire)) == -2) std::this_thread::yield();
+                    if (c < 0) break;                                               // not of the simple shape from here on
+                    lines += (uint64_t)c;
+                    const size_t E = (b + 1) * C;
+                    if (E <= pos) continue;
+                    const char *q = (const char *)memrchr(base + pos, '\n', E - pos);
+                    for (uint64_t r = lines & 3; q && r; r--) q = (const char *)memrchr(base + pos, '\n', (size_t)(q - (base + pos)));
+                    if (!q) continue;                                               // no whole record in [pos, E) yet
+                    const size_t cut = (size_t)(q - base) + 1;
+                    auto ch = fresh_chunk();
+                    ch->tptr = base + pos; ch->tlen = cut - pos; ch->last = false;
+                    pos = cut;
+                    if (!publish(ch)) open_queue = false;
+                }
+                quit.store(true);
+                for (auto &t : scouts) t.join();
+                more = open_queue;
+            }
             while (more) {
                 size_t want = kChunkText, cut = 0, scanned = 0;
                 bool eof = false;

@@ -232,6 +232,38 @@ def test_parallel_reader_equals_serial(built, tmp_path, monkeypatch):
             assert want[0] == "error"
 
 
+def test_fastq_cuts_from_scouted_newline_counts(built, tmp_path, monkeypatch):
+    """Plain FASTQ: scout threads count the newlines block by block, the producer derives the record cuts from the running
+    count (mod 4) and hands over to the exact line machine at the first block that is not of the simple shape.  Same reads
+    as the serial parser, whatever the number of scouts and the block size; quality lines may start with '@' or '+'."""
+    rng = np.random.default_rng(21)
+    seq = lambda n: "".join(rng.choice(list("ACGT"), n))
+    recs = []
+    for i in range(2500):
+        s = seq(int(rng.integers(1, 140)))
+        q = "".join(rng.choice(list("@+#5?FI"), len(s)))
+        recs.append("@r%d\n%s\n+\n%s\n" % (i, s, q))
+    text = "".join(recs)
+    cases = {
+        "clean.fastq": text,
+        "notail.fastq": text.rstrip("\n"),
+        "crlf_late.fastq": text + "".join(recs[:300]).replace("\n", "\r\n") + text,
+        "blank_mid.fastq": "".join(recs[:1200]) + "\n\n" + "".join(recs[1200:]),
+        "blank_first.fastq": "\n" + text,
+        "trunc.fastq": text[: len(text) * 2 // 3],
+    }
+    for name, t in cases.items():
+        p = tmp_path / name
+        p.write_bytes(t.encode())
+        monkeypatch.delenv("MFKC_READER_SCOUTS", raising=False)
+        want = _read_all(str(p), 1, monkeypatch=monkeypatch)
+        for scouts in (0, 1, 3):
+            monkeypatch.setenv("MFKC_READER_SCOUTS", str(scouts))
+            for threads, chunk in ((2, 256), (4, 5000), (3, 70000)):
+                assert _read_all(str(p), threads, chunk, monkeypatch) == want, (name, scouts, threads, chunk)
+    monkeypatch.delenv("MFKC_READER_SCOUTS", raising=False)
+
+
 def test_record_longer_than_the_batch_buffer(built, tmp_path, monkeypatch):
     """The reference takes FASTA records of any length (FastaReader.java:54-108).  mfkc_reader_next keeps a read that
     does not fit the caller's buffer pending and tells its length; the same reads come out whatever the buffer, the
