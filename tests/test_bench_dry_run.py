@@ -135,3 +135,37 @@ def test_bench_sharded_runs_through_on_fake_devices(built, tmp_path, world):
             elif what == "p2p_drain":
                 assert state.get(cid) == "counted", ln
                 state[cid] = "drained"
+
+
+def test_cpu_baseline_prefers_a_reference_jvm_when_the_box_has_one(built, tmp_path, monkeypatch):
+    """the CPU baseline is the reference JVM if `java` and a complete MetaFast jar exist, else the C
+    restatement.  Neither exists in this image: a stand-in `java` (a script that writes the output file) checks the command
+    line bench.py would run, and the fall-backs."""
+    import os
+    import stat
+    import bench
+    monkeypatch.delenv("JAVA_HOME", raising=False)
+    monkeypatch.delenv("METAFAST_JAR", raising=False)
+    if not os.path.exists(os.path.join(bench.ROOT, "baseline", "_ref", "metafast.jar")):
+        assert bench.jvm_reference_run(1000, 2) is None                      # nothing to run here
+    kmers, dt, kind = bench.cpu_baseline_run(3000, 2)
+    assert kind == "port" and kmers > 0 and dt > 0
+    fake = tmp_path / "bin"
+    fake.mkdir()
+    log = tmp_path / "java_args.txt"
+    (fake / "java").write_text('#!/bin/sh\necho "$@" > %s\nwhile [ $# -gt 0 ]; do if [ "$1" = "-w" ]; then W="$2"; fi; shift; done\n'
+                               'mkdir -p "$W/kmers" && : > "$W/kmers/sample.kmers.bin"\n' % log)
+    os.chmod(fake / "java", os.stat(fake / "java").st_mode | stat.S_IEXEC)
+    jar = tmp_path / "metafast.jar"
+    jar.write_bytes(b"PK")
+    monkeypatch.setenv("PATH", str(fake) + os.pathsep + os.environ["PATH"])
+    monkeypatch.setenv("METAFAST_JAR", str(jar))
+    kmers, dt, kind = bench.cpu_baseline_run(3000, 2)
+    assert kind == "reference" and 0 < kmers <= 3000 * 120 and dt > 0
+    args = log.read_text().split()
+    assert args[:2] == ["-jar", str(jar)] and args[2:10] == ["-t", "kmer-counter-many", "-k", "31", "-b", "2", "-p", "2"]
+    assert args[10] == "-i" and args[11].endswith("sample.fastq") and args[12] == "-w"
+    # a JVM run that fails falls back to the C restatement
+    (fake / "java").write_text("#!/bin/sh\necho boom >&2\nexit 3\n")
+    kmers, dt, kind = bench.cpu_baseline_run(3000, 2)
+    assert kind == "port"
