@@ -110,6 +110,18 @@ public final class GpuKmerCounting {
         try {
             while (true) {
                 rc = (int) MfkcNative.READER_NEXT.invokeExact(reader, hBases, capBases, hOffs, capReads, n);
+                if (rc == -1) {                                    // MFKC_E_BADARG: a read longer than hBases stays pending
+                    MemorySegment pending = arena.allocate(JAVA_LONG);
+                    MfkcNative.READER_PENDING_BASES.invokeExact(reader, pending);
+                    long need = pending.get(JAVA_LONG, 0);
+                    if (need > capBases) {                         // (a chromosome-sized FASTA record: take it with a larger buffer)
+                        MemorySegment pBuf = arena.allocate(ADDRESS);
+                        MfkcNative.check(ctx, (int) MfkcNative.PINNED_ALLOC.invokeExact(ctx, need, pBuf));
+                        hBases = pBuf.get(ADDRESS, 0).reinterpret(need);
+                        capBases = need;
+                        continue;
+                    }
+                }
                 if (rc != 0) throw new ExecutionFailedException("Error while reading " + file.getName());   // text: mfkc_reader_error
                 int got = n.get(JAVA_INT, 0);
                 if (got == 0) break;

@@ -48,6 +48,7 @@ public final class MfkcNative {
     static final MethodHandle FC_FEATURES = h("mfkc_fc_features", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle READER_OPEN = h("mfkc_reader_open", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_LONG));
     static final MethodHandle READER_NEXT = h("mfkc_reader_next", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, JAVA_INT, ADDRESS));
+    static final MethodHandle READER_PENDING_BASES = h("mfkc_reader_pending_bases", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle READER_CLOSE = h("mfkc_reader_close", FunctionDescriptor.ofVoid(ADDRESS));
 
     // ---- the .kmers.bin consumers (kmers-filter, unique-kmers-multi, kmers-samples-counter, seq-builder): one mfkc_kset per
