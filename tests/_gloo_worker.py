@@ -197,7 +197,7 @@ def run_bench_fake_device(rank, world, port, out_dir):
     import contextlib
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
                       MFKC_FAKE_SHARE_DIR=out_dir, MFKC_BENCH_NO_INGEST="1", MFKC_BENCH_VERIFY_SHARD_READS="1500",
-                      MFKC_BENCH_LANE_TIMEOUT_S="60")
+                      MFKC_BENCH_LANE_TIMEOUT_S="240")
     for k in ("MFKC_BENCH_VARIANT", "MFKC_BENCH_NO_VERIFY", "MFKC_EXCHANGE", "MFKC_BENCH_E2E_SERIAL"):
         os.environ.pop(k, None)
     import torch
