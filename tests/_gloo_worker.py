@@ -159,7 +159,7 @@ def run_p2p_lanes(rank, world, port, out_dir):
         d = os.path.join(out_dir, "lane%d" % j)
         os.makedirs(d, exist_ok=True)
         kc = _StubCounter(rank, world, k, d, lib)
-        grp = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=60))
+        grp = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=240))
         lanes.append((kc, sharded.P2PShardedStep(kc, dist, world, rank, 25, L, k, len(mine), group=grp)))
     link = threading.Lock()
     rnd = random.Random(1000 + rank)
